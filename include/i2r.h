@@ -1,0 +1,122 @@
+/*
+ * i2r.h -- C ABI of libi2r_sm100.so: the B200 (sm_100a) kernels behind the I2R-Net forward path.
+ *
+ * Boundary: the reference has no FFI of its own -- its forward is a chain of torch
+ * ops inside `model(x, pos_mask, length)` (lib/core/function.py:135).  Each entry point below
+ * replaces the torch/cuDNN/cuBLAS call sequence of one group of reference lines; the Python module
+ * that mirrors the reference's `lib/models/*.py` surface (get_pose_net / forward) loads this
+ * library with ctypes and is the only caller.
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative I2R_E_* code for argument errors, or the
+ *     positive cudaError_t of a failed launch; i2r_last_error() gives a thread-local message;
+ *   - nothing here allocates device memory or synchronises; all pointers are device pointers owned
+ *     by the caller (torch), `stream` is a cudaStream_t passed as void*;
+ *   - activations are NHWC fp16 ("pixel-major": one row of C channels per pixel); accumulation is
+ *     fp32 in TMEM; weights are fp16 in the packed K-major core-matrix layout documented at
+ *     i2r_conv_problem::w.
+ */
+#ifndef I2R_H_
+#define I2R_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define I2R_ABI_VERSION 1
+
+#define I2R_E_BADARG (-1)
+#define I2R_E_UNSUPPORTED (-2)
+#define I2R_E_DEVICE (-3)
+
+#define I2R_MAX_TAPS 9
+#define I2R_MAX_GROUP 4
+
+/* i2r_conv_problem::flags */
+#define I2R_F_RELU 1u        /* clamp at 0 after scale/bias/addends                         */
+#define I2R_F_OUT_NCHW_F32 2u /* write fp32 NCHW (heatmap head) instead of fp16 NHWC         */
+#define I2R_F_OUT_F32 4u      /* write fp32 NHWC (row-major [pixels, Cout])                  */
+
+/*
+ * One implicit-GEMM problem:  Y[p, n] = act( scale[n] * sum_{t,c} X[src(p,t), c] * W[t, c, n]
+ *                                           + bias[n] + add0[p >> s0, n] + add1[p >> s1, n] )
+ * with p an output pixel (b, oy, ox), taps t with integer offsets, and c the input channel.
+ * Covers (reference lines): nn.Conv2d 3x3/1x1 stride 1/2 + eval BatchNorm2d + ReLU + residual
+ * (lib/models/interformer_pureMulti.py:37-107, :543-582), HRNet fuse layers incl. nearest upsample
+ * (:353-387, :392-410), nn.Linear (attention/FFN projections, :174-213), ConvTranspose2d 4x4 s2
+ * as four 2x2-tap phases (:648-672), and the final 1x1 head (:489-495).
+ */
+typedef struct i2r_conv_problem {
+  const void* x;     /* fp16 NHWC source [NB, IH>>in_shift, IW>>in_shift, *] ; pixel stride in_pix_stride  */
+  const void* w;     /* fp16 packed [ntaps][Cin/KC][KC/8][Npad][8]  (B operand, K-major core matrices)      */
+  const float* scale; /* [Npad] per-output-channel scale (folded BatchNorm gamma/sqrt(var+eps)), or 1       */
+  const float* bias;  /* [Npad] per-output-channel bias (folded BN beta - mean*scale, or conv/linear bias)  */
+  const void* add0;  /* optional fp16 NHWC addend at output resolution >> add0_shift, Cout channels        */
+  const void* add1;  /* optional second addend                                                              */
+  void* y;           /* output, see flags                                                                   */
+  int32_t NB, IH, IW;      /* logical input extent (after the nearest-upsample by 2^in_shift)              */
+  int32_t Cin, KC;         /* input channels, K-chunk per pipeline stage (48 or 64; divides Cin)            */
+  int32_t in_pix_stride;   /* elements between consecutive source pixels (>= Cin)                          */
+  int32_t in_shift;        /* source pixel = (iy >> in_shift, ix >> in_shift)                              */
+  int32_t OH, OW;          /* GEMM-M index space: M = NB*OH*OW, iy = oy*stride + dy[t]                      */
+  int32_t stride;
+  int32_t Cout, Npad;      /* real / padded (multiple of 16, <= 256) output channels                        */
+  int32_t out_pix_stride;  /* elements between consecutive output pixels (NHWC modes)                       */
+  int32_t OHf, OWf;        /* full output extent; output pixel = (oy*out_mul+out_offy, ox*out_mul+out_offx) */
+  int32_t out_mul, out_offy, out_offx;
+  int32_t add0_shift, add1_shift;
+  int32_t ntaps;
+  int8_t dy[I2R_MAX_TAPS + 3];
+  int8_t dx[I2R_MAX_TAPS + 3];
+  uint32_t flags;
+} i2r_conv_problem;
+
+int i2r_version(void);
+const char* i2r_last_error(void);
+/* 0 iff device `dev` is compute capability 10.x (sm_100a code is loadable). */
+int i2r_device_check(int dev);
+int i2r_sm_count(int dev);
+
+/* Launch `nprob` (1..I2R_MAX_GROUP) independent problems as ONE grid of 128-pixel tiles on the
+ * tcgen05 path.  impl: 0 = tcgen05/TMEM kernel (product path), 1 = scalar SIMT check kernel
+ * (tests only; same problem struct, same packed weights). */
+int i2r_conv_igemm(const i2r_conv_problem* probs, int nprob, int impl, void* stream);
+
+/* Stem / mask convolution on fp32 NCHW input with tiny Cin (3 or 1): 3x3 stride 2 pad 1 + folded
+ * BN + ReLU -> fp16 NHWC [NB, H/2, W/2, Cout].  Replaces conv1/bn1/relu
+ * (interformer_pureMulti.py:677-679) and position_embedding.conv1/bn1/relu
+ * (position_embedding.py:108-110).  w: fp32 [Cin*9][Cout] (k = (c*3+ky)*3+kx). */
+int i2r_stem_conv3x3s2(const float* x, const float* w, const float* scale, const float* bias, void* y,
+                       int NB, int Cin, int H, int W, int Cout, void* stream);
+
+/* MaxPool2d(kernel 3, stride 2, padding 1) on fp16 NHWC (position_embedding.py:9,:113-114;
+ * interformer.py:260-264). */
+int i2r_maxpool3x3s2(const void* x, void* y, int NB, int H, int W, int C, void* stream);
+
+/* Single-head scaled-dot-product attention over ragged sequences (one per image):
+ *   out[t, :] = softmax_j( scale * q[t,:] . k[j,:] ) v[j,:]   for j in the same sequence.
+ * q,k,v,out: fp16 row-major with row strides ldq/ldk/ldv/ldo elements, head dim D (multiple of 16,
+ * <= 96); cu_seqlens: int32 [nseq+1] token offsets on the device.  Equivalent to
+ * nn.MultiheadAttention(nhead=1) with key_padding_mask on padded persons
+ * (interformer_pureMulti.py:199-204; torch F.multi_head_attention_forward). */
+int i2r_attention_varlen(const void* q, const void* k, const void* v, void* out, int ldq, int ldk, int ldv,
+                         int ldo, int D, const int32_t* cu_seqlens, int nseq, int max_seqlen, float scale,
+                         void* stream);
+
+/* y = LayerNorm(x) * gamma + beta over the last dim C (<= 256, multiple of 8), fp16 in/out, fp32
+ * math; optional y2 = y + pos (the next layer's q/k input).  (interformer_pureMulti.py:206,:209) */
+int i2r_layernorm(const void* x, const float* gamma, const float* beta, const void* pos, void* y, void* y2,
+                  int rows, int C, float eps, void* stream);
+
+/* y = a + b elementwise on fp16, n multiple of 8 (with_pos_embed, interformer_pureMulti.py:189). */
+int i2r_add_f16(const void* a, const void* b, void* y, int64_t n, void* stream);
+
+/* sizeof(i2r_conv_problem) as compiled -- lets the ctypes binding verify its struct layout. */
+int i2r_sizeof_conv_problem(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* I2R_H_ */

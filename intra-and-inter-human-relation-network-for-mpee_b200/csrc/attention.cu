@@ -1,0 +1,233 @@
+// Ragged single-head attention (one sequence per image): flash-style streaming softmax, scores never
+// leave the SM.  v1 uses warp-level mma.sync (fp16 in, fp32 accumulate) -- this stage is <2 % of the
+// vanilla model's FLOPs; the tcgen05 version is tracked in DESIGN.md ("next").
+//
+// CTA = 4 warps = 64 query rows of one sequence; K/V stream through a 2-stage cp.async ring in
+// 64-key tiles.  Row pitch in shared memory is HD+8 halves so that ldmatrix rows fall in distinct banks.
+#include "i2r_common.cuh"
+
+namespace i2r {
+
+constexpr int ATT_BQ = 64;
+constexpr int ATT_BK = 64;
+
+__device__ __forceinline__ void ldsm_x4(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3)
+               : "r"(addr));
+}
+__device__ __forceinline__ void ldsm_x4_t(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3)
+               : "r"(addr));
+}
+__device__ __forceinline__ void mma16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+template <int HD>
+__device__ __forceinline__ void load_tile(uint32_t sdst, const __half* __restrict__ g, int ld, int row0, int nrows_valid,
+                                          int tid) {
+  constexpr int PITCH = (HD + 8) * 2;  // bytes
+  constexpr int CPR = HD / 8;          // 16-byte chunks per row
+  for (int j = tid; j < ATT_BK * CPR; j += 128) {
+    const int r = j / CPR, c = j - r * CPR;
+    const bool ok = r < nrows_valid;
+    const __half* src = ok ? g + static_cast<int64_t>(row0 + r) * ld + c * 8 : g;
+    cp_async16(sdst + r * PITCH + c * 16, src, ok ? 16u : 0u);
+  }
+}
+
+template <int HD>
+__global__ void __launch_bounds__(128) attention_kernel(const __half* __restrict__ q, const __half* __restrict__ k,
+                                                        const __half* __restrict__ v, __half* __restrict__ out,
+                                                        int ldq, int ldk, int ldv, int ldo,
+                                                        const int32_t* __restrict__ cu_seqlens, float scale_log2e) {
+  constexpr int PITCH = (HD + 8) * 2;
+  constexpr int TILE = ATT_BK * PITCH;
+  constexpr int KS = HD / 16;  // k-steps over the head dim
+  constexpr int DT = HD / 8;   // 8-wide output tiles over the head dim
+  extern __shared__ __align__(128) uint8_t smem[];
+  const int seq = blockIdx.y;
+  const int t0 = cu_seqlens[seq];
+  const int L = cu_seqlens[seq + 1] - t0;
+  const int q0 = blockIdx.x * ATT_BQ;
+  if (q0 >= L) return;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t sQ = smem_u32(smem);
+  const uint32_t sK = sQ + TILE;       // 2 stages
+  const uint32_t sV = sK + 2 * TILE;   // 2 stages
+
+  const int ntiles = (L + ATT_BK - 1) / ATT_BK;
+  load_tile<HD>(sQ, q, ldq, t0 + q0, min(ATT_BQ, L - q0), tid);
+  load_tile<HD>(sK, k, ldk, t0, min(ATT_BK, L), tid);
+  load_tile<HD>(sV, v, ldv, t0, min(ATT_BK, L), tid);
+  cp_async_commit();
+
+  uint32_t qf[KS][4];
+  float o[DT][4];
+#pragma unroll
+  for (int i = 0; i < DT; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) o[i][j] = 0.f;
+  float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
+
+  for (int kt = 0; kt < ntiles; ++kt) {
+    const int st = kt & 1;
+    if (kt + 1 < ntiles) {
+      const int kr = (kt + 1) * ATT_BK;
+      load_tile<HD>(sK + (st ^ 1) * TILE, k, ldk, t0 + kr, min(ATT_BK, L - kr), tid);
+      load_tile<HD>(sV + (st ^ 1) * TILE, v, ldv, t0 + kr, min(ATT_BK, L - kr), tid);
+      cp_async_commit();
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
+    }
+    __syncthreads();
+    if (kt == 0) {
+#pragma unroll
+      for (int ks = 0; ks < KS; ++ks) {
+        const int row = warp * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
+        const int col = ks * 16 + (lane >> 4) * 8;
+        ldsm_x4(sQ + row * PITCH + col * 2, qf[ks][0], qf[ks][1], qf[ks][2], qf[ks][3]);
+      }
+    }
+    // ---- S = Q K^T for this warp's 16 rows x 64 keys
+    float s[8][4];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) s[i][j] = 0.f;
+    const uint32_t kb = sK + st * TILE;
+#pragma unroll
+    for (int ks = 0; ks < KS; ++ks) {
+#pragma unroll
+      for (int nt = 0; nt < 8; nt += 2) {
+        const int key = nt * 8 + (lane >> 4) * 8 + (lane & 7);
+        const int col = ks * 16 + ((lane >> 3) & 1) * 8;
+        uint32_t b0, b1, b2, b3;
+        ldsm_x4(kb + key * PITCH + col * 2, b0, b1, b2, b3);
+        mma16816(s[nt], qf[ks], b0, b1);
+        mma16816(s[nt + 1], qf[ks], b2, b3);
+      }
+    }
+    // ---- online softmax (rows r0 = lane/4, r1 = r0+8 of the warp's 16)
+    const int kbase = kt * ATT_BK;
+    float mx0 = m0, mx1 = m1;
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int key = kbase + nt * 8 + (lane & 3) * 2 + (j & 1);
+        float val = s[nt][j] * scale_log2e;
+        if (key >= L) val = -INFINITY;
+        s[nt][j] = val;
+        if (j < 2) mx0 = fmaxf(mx0, val); else mx1 = fmaxf(mx1, val);
+      }
+    }
+    mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
+    mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+    mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
+    mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+    const float c0 = exp2f(m0 - mx0), c1 = exp2f(m1 - mx1);
+    m0 = mx0;
+    m1 = mx1;
+    float rs0 = 0.f, rs1 = 0.f;
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+      s[nt][0] = exp2f(s[nt][0] - mx0);
+      s[nt][1] = exp2f(s[nt][1] - mx0);
+      s[nt][2] = exp2f(s[nt][2] - mx1);
+      s[nt][3] = exp2f(s[nt][3] - mx1);
+      rs0 += s[nt][0] + s[nt][1];
+      rs1 += s[nt][2] + s[nt][3];
+    }
+    l0 = l0 * c0 + rs0;
+    l1 = l1 * c1 + rs1;
+#pragma unroll
+    for (int i = 0; i < DT; ++i) {
+      o[i][0] *= c0;
+      o[i][1] *= c0;
+      o[i][2] *= c1;
+      o[i][3] *= c1;
+    }
+    // ---- O += P V
+    const uint32_t vb = sV + st * TILE;
+#pragma unroll
+    for (int j = 0; j < ATT_BK / 16; ++j) {
+      uint32_t pa[4];
+      pa[0] = pack_h2(s[2 * j][0], s[2 * j][1]);
+      pa[1] = pack_h2(s[2 * j][2], s[2 * j][3]);
+      pa[2] = pack_h2(s[2 * j + 1][0], s[2 * j + 1][1]);
+      pa[3] = pack_h2(s[2 * j + 1][2], s[2 * j + 1][3]);
+#pragma unroll
+      for (int dt = 0; dt < DT; dt += 2) {
+        const int key = j * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
+        const int col = dt * 8 + (lane >> 4) * 8;
+        uint32_t b0, b1, b2, b3;
+        ldsm_x4_t(vb + key * PITCH + col * 2, b0, b1, b2, b3);
+        mma16816(o[dt], pa, b0, b1);
+        mma16816(o[dt + 1], pa, b2, b3);
+      }
+    }
+    __syncthreads();  // all warps done with stage st before it is refilled
+  }
+  l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
+  l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+  l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
+  l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+  const float i0 = 1.f / l0, i1 = 1.f / l1;
+  const int r0 = q0 + warp * 16 + (lane >> 2);
+  const int r1 = r0 + 8;
+#pragma unroll
+  for (int dt = 0; dt < DT; ++dt) {
+    const int col = dt * 8 + (lane & 3) * 2;
+    if (r0 < L)
+      *reinterpret_cast<uint32_t*>(out + static_cast<int64_t>(t0 + r0) * ldo + col) = pack_h2(o[dt][0] * i0, o[dt][1] * i0);
+    if (r1 < L)
+      *reinterpret_cast<uint32_t*>(out + static_cast<int64_t>(t0 + r1) * ldo + col) = pack_h2(o[dt][2] * i1, o[dt][3] * i1);
+  }
+}
+
+template <int HD>
+static int launch_attention(const void* q, const void* k, const void* v, void* out, int ldq, int ldk, int ldv, int ldo,
+                            const int32_t* cu, int nseq, int max_seqlen, float scale, cudaStream_t st) {
+  constexpr int smem = 5 * ATT_BK * (HD + 8) * 2;
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(attention_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) {
+      set_error("cudaFuncSetAttribute(attention): %s", cudaGetErrorString(e));
+      return static_cast<int>(e);
+    }
+    attr_done = true;
+  }
+  dim3 grid((max_seqlen + ATT_BQ - 1) / ATT_BQ, nseq);
+  attention_kernel<HD><<<grid, 128, smem, st>>>(static_cast<const __half*>(q), static_cast<const __half*>(k),
+                                                static_cast<const __half*>(v), static_cast<__half*>(out), ldq, ldk,
+                                                ldv, ldo, cu, scale * 1.4426950408889634f);
+  return check_launch("attention_kernel");
+}
+
+}  // namespace i2r
+
+extern "C" int i2r_attention_varlen(const void* q, const void* k, const void* v, void* out, int ldq, int ldk, int ldv,
+                                    int ldo, int D, const int32_t* cu_seqlens, int nseq, int max_seqlen, float scale,
+                                    void* stream) {
+  using namespace i2r;
+  if (!q || !k || !v || !out || !cu_seqlens || nseq <= 0 || max_seqlen <= 0 || (ldq | ldk | ldv | ldo) % 8 != 0) {
+    set_error("i2r_attention_varlen: bad arguments");
+    return I2R_E_BADARG;
+  }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  switch (D) {
+    case 96: return launch_attention<96>(q, k, v, out, ldq, ldk, ldv, ldo, cu_seqlens, nseq, max_seqlen, scale, st);
+    case 80: return launch_attention<80>(q, k, v, out, ldq, ldk, ldv, ldo, cu_seqlens, nseq, max_seqlen, scale, st);
+    default:
+      set_error("i2r_attention_varlen: head dim %d unsupported (80 or 96)", D);
+      return I2R_E_UNSUPPORTED;
+  }
+}

@@ -1,0 +1,466 @@
+// Implicit-GEMM convolution / linear layer on tcgen05 tensor cores (sm_100a).
+//
+// One CTA computes a tile of 128 output pixels x Npad output channels:
+//   warps 0-3 (128 threads): A-operand producers (im2col gather with cp.async, zero-fill for padding
+//                            taps) and, afterwards, the epilogue (TMEM -> registers -> global);
+//   warp 4  : TMEM allocation + the single MMA-issuing thread (tcgen05.mma, accumulator in TMEM).
+// The B operand (weights, pre-packed on the host in the exact shared-memory core-matrix layout)
+// arrives with one 1-D bulk copy (TMA unit) per pipeline stage.  Stages form an mbarrier ring
+// (full[]: 128 producer arrivals + 1 expect_tx arrival; empty[]: tcgen05.commit).
+//
+// Shared-memory operand layout (K-major, no swizzle): [k-group of 8 channels][row][8 x fp16]; one core
+// matrix = 8 consecutive rows x 16 B.  A uses a k-group stride of 128*16+16 bytes so that the eight
+// 16-byte cp.async writes of a quarter-warp (same pixel, consecutive k-groups) hit distinct banks.
+#include <cstdio>
+
+#include "i2r_common.cuh"
+
+namespace i2r {
+
+struct ConvGroup {
+  int nprob;
+  int tile_end[I2R_MAX_GROUP];  // exclusive prefix of 128-pixel tiles per problem
+  i2r_conv_problem p[I2R_MAX_GROUP];
+};
+
+constexpr int BM = 128;
+constexpr int NPROD = 128;
+constexpr int NTHREADS = 160;
+constexpr int A_KG_STRIDE = BM * 16 + 16;  // bytes between k-groups of the A stage (padded: bank spread)
+constexpr int SMEM_HDR = 2304;             // barriers (<=128 B) | tmem ptr | scale[256] | bias[256]
+constexpr int SMEM_SCALE_OFF = 256;
+constexpr int SMEM_BIAS_OFF = 256 + 1024;
+
+__device__ __forceinline__ int stage_bytes(int KG, int Npad) { return KG * A_KG_STRIDE + KG * Npad * 16; }
+
+template <int KG, int STAGES>
+__device__ __forceinline__ void run_tile(const i2r_conv_problem& P, const int tile, uint8_t* smem) {
+  constexpr int LOOK = STAGES - 1;
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5;
+  const int lane = tid & 31;
+
+  const uint32_t sbase = smem_u32(smem);
+  const uint32_t bar_full = sbase;                  // STAGES x 8 B
+  const uint32_t bar_empty = sbase + 8 * STAGES;    // STAGES x 8 B
+  const uint32_t bar_accum = sbase + 16 * STAGES;   // 8 B
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + 16 * STAGES + 8);
+  float* s_scale = reinterpret_cast<float*>(smem + SMEM_SCALE_OFF);
+  float* s_bias = reinterpret_cast<float*>(smem + SMEM_BIAS_OFF);
+
+  const int Npad = P.Npad;
+  const int a_bytes = KG * A_KG_STRIDE;
+  const int b_bytes = KG * Npad * 16;
+  const int st_bytes = a_bytes + b_bytes;
+  const uint32_t stages0 = sbase + SMEM_HDR;
+
+  const int nchunks = P.Cin / (KG * 8);
+  const int niter = P.ntaps * nchunks;
+  const int M = P.NB * P.OH * P.OW;
+
+  uint32_t ncols = 32;
+  while (ncols < static_cast<uint32_t>(Npad)) ncols <<= 1;
+
+  // ---------------- setup
+  if (tid == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(bar_full + 8 * s, NPROD + 1);
+      mbar_init(bar_empty + 8 * s, 1);
+    }
+    mbar_init(bar_accum, 1);
+    fence_mbar_init();
+  }
+  if (warp == 4) {
+    tmem_alloc(smem_u32(tmem_slot), ncols);
+    tmem_relinquish();
+  }
+  if (tid < NPROD) {
+    for (int i = tid; i < Npad; i += NPROD) {
+      s_scale[i] = P.scale[i];
+      s_bias[i] = P.bias[i];
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp < 4) {
+    // =============================================================== A/B producers
+    const __half* __restrict__ X = reinterpret_cast<const __half*>(P.x);
+    const uint8_t* __restrict__ Wp = reinterpret_cast<const uint8_t*>(P.w);
+    const int sh = P.in_shift;
+    const int IHs = P.IH >> sh, IWs = P.IW >> sh;
+    const int ohow = P.OH * P.OW;
+
+    // Per-thread gather slots: chunk j = tid + i*128 -> (row, k-group).
+    int r_oy[KG], r_ox[KG], r_nb[KG];
+    uint32_t r_dst[KG];
+    int r_g[KG];
+#pragma unroll
+    for (int i = 0; i < KG; ++i) {
+      const int j = tid + i * NPROD;
+      const int row = j / KG;
+      const int g = j - row * KG;
+      r_g[i] = g;
+      r_dst[i] = g * A_KG_STRIDE + row * 16;
+      const int p = tile * BM + row;
+      if (p < M) {
+        const int n = p / ohow;
+        const int rem = p - n * ohow;
+        const int oy = rem / P.OW;
+        const int ox = rem - oy * P.OW;
+        r_oy[i] = oy * P.stride;
+        r_ox[i] = ox * P.stride;
+        r_nb[i] = n * IHs;
+      } else {
+        r_oy[i] = -100000;  // always out of range -> zero fill
+        r_ox[i] = 0;
+        r_nb[i] = 0;
+      }
+    }
+
+    int it = 0;
+    for (int t = 0; t < P.ntaps; ++t) {
+      const int dy = P.dy[t], dx = P.dx[t];
+      for (int c = 0; c < nchunks; ++c, ++it) {
+        const int s = it % STAGES;
+        const uint32_t ph = (it / STAGES) & 1;
+        mbar_wait(bar_empty + 8 * s, ph ^ 1);
+        const uint32_t a_s = stages0 + s * st_bytes;
+        if (tid == 0) {
+          mbar_arrive_expect_tx(bar_full + 8 * s, b_bytes);
+          bulk_g2s(a_s + a_bytes, Wp + static_cast<size_t>(it) * b_bytes, b_bytes, bar_full + 8 * s);
+        }
+#pragma unroll
+        for (int i = 0; i < KG; ++i) {
+          const int iy = r_oy[i] + dy;
+          const int ix = r_ox[i] + dx;
+          const bool ok = (static_cast<unsigned>(iy) < static_cast<unsigned>(P.IH)) &&
+                          (static_cast<unsigned>(ix) < static_cast<unsigned>(P.IW));
+          const __half* src = X;
+          if (ok) {
+            const int64_t pix = static_cast<int64_t>(r_nb[i] + (iy >> sh)) * IWs + (ix >> sh);
+            src = X + pix * P.in_pix_stride + c * (KG * 8) + r_g[i] * 8;
+          }
+          cp_async16(a_s + r_dst[i], src, ok ? 16u : 0u);
+        }
+        cp_async_commit();
+        if (it >= LOOK) {
+          cp_async_wait<LOOK>();
+          fence_proxy_async();
+          mbar_arrive(bar_full + 8 * ((it - LOOK) % STAGES));
+        }
+      }
+    }
+    cp_async_wait<0>();
+    fence_proxy_async();
+    for (int j = (niter > LOOK ? niter - LOOK : 0); j < niter; ++j) mbar_arrive(bar_full + 8 * (j % STAGES));
+
+    // =============================================================== epilogue
+    mbar_wait(bar_accum, 0);
+    tc_fence_after();
+
+    const int row = warp * 32 + lane;
+    const int p = tile * BM + row;
+    const bool valid = p < M;
+    int n = 0, oyf = 0, oxf = 0;
+    if (valid) {
+      n = p / ohow;
+      const int rem = p - n * ohow;
+      const int oy = rem / P.OW;
+      const int ox = rem - oy * P.OW;
+      oyf = oy * P.out_mul + P.out_offy;
+      oxf = ox * P.out_mul + P.out_offx;
+    }
+    const int Cout = P.Cout;
+    const __half* a0 = nullptr;
+    const __half* a1 = nullptr;
+    if (P.add0 != nullptr) {
+      const int s0 = P.add0_shift;
+      const int64_t ap = (static_cast<int64_t>(n) * (P.OHf >> s0) + (oyf >> s0)) * (P.OWf >> s0) + (oxf >> s0);
+      a0 = reinterpret_cast<const __half*>(P.add0) + ap * Cout;
+    }
+    if (P.add1 != nullptr) {
+      const int s1 = P.add1_shift;
+      const int64_t ap = (static_cast<int64_t>(n) * (P.OHf >> s1) + (oyf >> s1)) * (P.OWf >> s1) + (oxf >> s1);
+      a1 = reinterpret_cast<const __half*>(P.add1) + ap * Cout;
+    }
+    const int64_t opix = (static_cast<int64_t>(n) * P.OHf + oyf) * P.OWf + oxf;
+    const bool relu = (P.flags & I2R_F_RELU) != 0;
+    const uint32_t taddr_row = tmem_base + (static_cast<uint32_t>(warp * 32) << 16);
+
+    for (int c0 = 0; c0 < Npad; c0 += 16) {
+      uint32_t r[16];
+      tmem_ld16(taddr_row + c0, r);
+      tmem_ld_wait();
+      float v[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]) * s_scale[c0 + i] + s_bias[c0 + i];
+      if (valid) {
+        if (a0 != nullptr) {
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            if (c0 + h * 8 < Cout) {
+              const uint4 q = *reinterpret_cast<const uint4*>(a0 + c0 + h * 8);
+              const uint32_t w4[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const float2 f = unpack_h2(w4[i]);
+                v[h * 8 + 2 * i] += f.x;
+                v[h * 8 + 2 * i + 1] += f.y;
+              }
+            }
+          }
+        }
+        if (a1 != nullptr) {
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            if (c0 + h * 8 < Cout) {
+              const uint4 q = *reinterpret_cast<const uint4*>(a1 + c0 + h * 8);
+              const uint32_t w4[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const float2 f = unpack_h2(w4[i]);
+                v[h * 8 + 2 * i] += f.x;
+                v[h * 8 + 2 * i + 1] += f.y;
+              }
+            }
+          }
+        }
+        if (relu) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.0f);
+        }
+        if (P.flags & I2R_F_OUT_NCHW_F32) {
+          float* Y = reinterpret_cast<float*>(P.y);
+          const int64_t plane = static_cast<int64_t>(P.OHf) * P.OWf;
+          const int64_t base = static_cast<int64_t>(n) * Cout * plane + static_cast<int64_t>(oyf) * P.OWf + oxf;
+#pragma unroll
+          for (int i = 0; i < 16; ++i)
+            if (c0 + i < Cout) Y[base + (c0 + i) * plane] = v[i];
+        } else if (P.flags & I2R_F_OUT_F32) {
+          float* Y = reinterpret_cast<float*>(P.y) + opix * P.out_pix_stride + c0;
+#pragma unroll
+          for (int i = 0; i < 16; ++i)
+            if (c0 + i < Cout) Y[i] = v[i];
+        } else {
+          __half* Y = reinterpret_cast<__half*>(P.y) + opix * P.out_pix_stride + c0;
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            if (c0 + h * 8 < Cout) {
+              uint4 q;
+              q.x = pack_h2(v[h * 8 + 0], v[h * 8 + 1]);
+              q.y = pack_h2(v[h * 8 + 2], v[h * 8 + 3]);
+              q.z = pack_h2(v[h * 8 + 4], v[h * 8 + 5]);
+              q.w = pack_h2(v[h * 8 + 6], v[h * 8 + 7]);
+              *reinterpret_cast<uint4*>(Y + h * 8) = q;
+            }
+          }
+        }
+      }
+    }
+  } else if (lane == 0) {
+    // =============================================================== MMA issuer (one thread)
+    const uint32_t idesc = make_idesc_f16(BM, Npad);
+    const uint32_t b_lbo = static_cast<uint32_t>(Npad) * 16;
+    for (int it = 0; it < niter; ++it) {
+      const int s = it % STAGES;
+      const uint32_t ph = (it / STAGES) & 1;
+      mbar_wait(bar_full + 8 * s, ph);
+      tc_fence_after();
+      const uint32_t a_s = stages0 + s * st_bytes;
+      const uint32_t b_s = a_s + a_bytes;
+#pragma unroll
+      for (int k = 0; k < KG / 2; ++k) {
+        const uint64_t ad = make_smem_desc(a_s + 2 * k * A_KG_STRIDE, A_KG_STRIDE, 128);
+        const uint64_t bd = make_smem_desc(b_s + 2 * k * b_lbo, b_lbo, 128);
+        umma_f16(tmem_base, ad, bd, idesc, (it | k) != 0 ? 1u : 0u);
+      }
+      umma_commit(bar_empty + 8 * s);
+    }
+    umma_commit(bar_accum);
+  }
+
+  // ---------------- teardown
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) tmem_dealloc(tmem_base, ncols);
+}
+
+template <int STAGES>
+__global__ void __launch_bounds__(NTHREADS) igemm_tc_kernel(const __grid_constant__ ConvGroup G) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  int tile = blockIdx.x;
+  int pi = 0;
+  while (pi < G.nprob - 1 && tile >= G.tile_end[pi]) ++pi;
+  if (pi > 0) tile -= G.tile_end[pi - 1];
+  const i2r_conv_problem& P = G.p[pi];
+  if (P.KC == 48) {
+    run_tile<6, STAGES>(P, tile, smem);
+  } else {
+    run_tile<8, STAGES>(P, tile, smem);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Scalar check kernel (tests only): same problem struct and packed weights, one thread per output
+// pixel, fp32 accumulation of fp16 products.
+__global__ void __launch_bounds__(128) igemm_check_kernel(const __grid_constant__ ConvGroup G) {
+  int tile = blockIdx.x;
+  int pi = 0;
+  while (pi < G.nprob - 1 && tile >= G.tile_end[pi]) ++pi;
+  if (pi > 0) tile -= G.tile_end[pi - 1];
+  const i2r_conv_problem& P = G.p[pi];
+  const int M = P.NB * P.OH * P.OW;
+  const int p = tile * BM + threadIdx.x;
+  if (p >= M) return;
+  const int ohow = P.OH * P.OW;
+  const int n = p / ohow;
+  const int rem = p - n * ohow;
+  const int oy = rem / P.OW, ox = rem - (rem / P.OW) * P.OW;
+  const int oyf = oy * P.out_mul + P.out_offy, oxf = ox * P.out_mul + P.out_offx;
+  const int sh = P.in_shift;
+  const int IHs = P.IH >> sh, IWs = P.IW >> sh;
+  const int KG = P.KC / 8;
+  const int nchunks = P.Cin / P.KC;
+  const __half* X = reinterpret_cast<const __half*>(P.x);
+  const __half* Wp = reinterpret_cast<const __half*>(P.w);
+  const int64_t opix = (static_cast<int64_t>(n) * P.OHf + oyf) * P.OWf + oxf;
+  for (int co = 0; co < P.Cout; ++co) {
+    float acc = 0.f;
+    for (int t = 0; t < P.ntaps; ++t) {
+      const int iy = oy * P.stride + P.dy[t], ix = ox * P.stride + P.dx[t];
+      if (static_cast<unsigned>(iy) >= static_cast<unsigned>(P.IH) ||
+          static_cast<unsigned>(ix) >= static_cast<unsigned>(P.IW))
+        continue;
+      const __half* xp = X + (static_cast<int64_t>(n * IHs + (iy >> sh)) * IWs + (ix >> sh)) * P.in_pix_stride;
+      for (int c = 0; c < P.Cin; ++c) {
+        const int ch = c / P.KC, g = (c % P.KC) / 8, e = c % 8;
+        const int64_t wi = ((static_cast<int64_t>(t * nchunks + ch) * KG + g) * P.Npad + co) * 8 + e;
+        acc += __half2float(xp[c]) * __half2float(Wp[wi]);
+      }
+    }
+    float v = acc * P.scale[co] + P.bias[co];
+    if (P.add0) {
+      const int s0 = P.add0_shift;
+      const int64_t ap = (static_cast<int64_t>(n) * (P.OHf >> s0) + (oyf >> s0)) * (P.OWf >> s0) + (oxf >> s0);
+      v += __half2float(reinterpret_cast<const __half*>(P.add0)[ap * P.Cout + co]);
+    }
+    if (P.add1) {
+      const int s1 = P.add1_shift;
+      const int64_t ap = (static_cast<int64_t>(n) * (P.OHf >> s1) + (oyf >> s1)) * (P.OWf >> s1) + (oxf >> s1);
+      v += __half2float(reinterpret_cast<const __half*>(P.add1)[ap * P.Cout + co]);
+    }
+    if (P.flags & I2R_F_RELU) v = fmaxf(v, 0.f);
+    if (P.flags & I2R_F_OUT_NCHW_F32) {
+      const int64_t plane = static_cast<int64_t>(P.OHf) * P.OWf;
+      reinterpret_cast<float*>(P.y)[(static_cast<int64_t>(n) * P.Cout + co) * plane +
+                                    static_cast<int64_t>(oyf) * P.OWf + oxf] = v;
+    } else if (P.flags & I2R_F_OUT_F32) {
+      reinterpret_cast<float*>(P.y)[opix * P.out_pix_stride + co] = v;
+    } else {
+      reinterpret_cast<__half*>(P.y)[opix * P.out_pix_stride + co] = __float2half_rn(v);
+    }
+  }
+}
+
+static int validate(const i2r_conv_problem& P, int idx) {
+  if (!P.x || !P.w || !P.scale || !P.bias || !P.y) {
+    set_error("conv problem %d: null pointer", idx);
+    return I2R_E_BADARG;
+  }
+  if (P.KC != 48 && P.KC != 64) {
+    set_error("conv problem %d: KC=%d unsupported (48 or 64)", idx, P.KC);
+    return I2R_E_UNSUPPORTED;
+  }
+  if (P.Cin <= 0 || P.Cin % P.KC != 0) {
+    set_error("conv problem %d: Cin=%d not a multiple of KC=%d", idx, P.Cin, P.KC);
+    return I2R_E_BADARG;
+  }
+  if (P.Npad < 16 || P.Npad > 256 || P.Npad % 16 != 0 || P.Cout > P.Npad || P.Cout <= 0) {
+    set_error("conv problem %d: Cout=%d Npad=%d invalid", idx, P.Cout, P.Npad);
+    return I2R_E_BADARG;
+  }
+  if (P.ntaps < 1 || P.ntaps > I2R_MAX_TAPS) {
+    set_error("conv problem %d: ntaps=%d", idx, P.ntaps);
+    return I2R_E_BADARG;
+  }
+  const bool nhwc16 = !(P.flags & (I2R_F_OUT_NCHW_F32 | I2R_F_OUT_F32));
+  if (nhwc16 && (P.Cout % 8 != 0 || P.out_pix_stride % 8 != 0)) {
+    set_error("conv problem %d: fp16 NHWC output needs Cout, out_pix_stride multiples of 8", idx);
+    return I2R_E_BADARG;
+  }
+  if ((P.add0 || P.add1) && P.Cout % 8 != 0) {
+    set_error("conv problem %d: addends need Cout multiple of 8", idx);
+    return I2R_E_BADARG;
+  }
+  if (P.in_pix_stride % 8 != 0 || P.in_pix_stride < P.Cin) {
+    set_error("conv problem %d: in_pix_stride=%d", idx, P.in_pix_stride);
+    return I2R_E_BADARG;
+  }
+  if (P.NB <= 0 || P.OH <= 0 || P.OW <= 0 || P.IH <= 0 || P.IW <= 0 || P.stride <= 0 || P.out_mul <= 0) {
+    set_error("conv problem %d: bad extents", idx);
+    return I2R_E_BADARG;
+  }
+  return 0;
+}
+
+template <int STAGES>
+static int launch_tc(const ConvGroup& G, int tiles, size_t smem, cudaStream_t st) {
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(igemm_tc_kernel<STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e != cudaSuccess) {
+      set_error("cudaFuncSetAttribute(igemm_tc): %s", cudaGetErrorString(e));
+      return static_cast<int>(e);
+    }
+    attr_done = true;
+  }
+  igemm_tc_kernel<STAGES><<<tiles, NTHREADS, smem, st>>>(G);
+  return check_launch("igemm_tc_kernel");
+}
+
+}  // namespace i2r
+
+extern "C" int i2r_conv_igemm(const i2r_conv_problem* probs, int nprob, int impl, void* stream) {
+  using namespace i2r;
+  if (!probs || nprob < 1 || nprob > I2R_MAX_GROUP) {
+    set_error("i2r_conv_igemm: nprob=%d out of range", nprob);
+    return I2R_E_BADARG;
+  }
+  ConvGroup G;
+  G.nprob = nprob;
+  int tiles = 0;
+  int max_stage = 0;
+  for (int i = 0; i < nprob; ++i) {
+    int rc = validate(probs[i], i);
+    if (rc) return rc;
+    G.p[i] = probs[i];
+    const int64_t M = static_cast<int64_t>(probs[i].NB) * probs[i].OH * probs[i].OW;
+    tiles += static_cast<int>((M + BM - 1) / BM);
+    G.tile_end[i] = tiles;
+    const int KG = probs[i].KC / 8;
+    const int sb = KG * A_KG_STRIDE + KG * probs[i].Npad * 16;
+    if (sb > max_stage) max_stage = sb;
+  }
+  for (int i = nprob; i < I2R_MAX_GROUP; ++i) G.tile_end[i] = tiles;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (impl == 1) {
+    igemm_check_kernel<<<tiles, 128, 0, st>>>(G);
+    return check_launch("igemm_check_kernel");
+  }
+  if (impl != 0) {
+    set_error("i2r_conv_igemm: impl=%d", impl);
+    return I2R_E_BADARG;
+  }
+  int stages = (96 * 1024) / max_stage;
+  if (stages > 4) stages = 4;
+  if (stages < 2) stages = 2;
+  const size_t smem = SMEM_HDR + static_cast<size_t>(stages) * max_stage;
+  switch (stages) {
+    case 2: return launch_tc<2>(G, tiles, smem, st);
+    case 3: return launch_tc<3>(G, tiles, smem, st);
+    default: return launch_tc<4>(G, tiles, smem, st);
+  }
+}

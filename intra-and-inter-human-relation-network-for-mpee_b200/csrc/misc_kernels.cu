@@ -1,0 +1,292 @@
+// HBM-bound helper kernels: tiny-Cin stem convolution (fp32 NCHW -> fp16 NHWC), max-pool,
+// LayerNorm (+ fused positional add), elementwise add.  Warp-shuffle / 16-byte vectorised.
+#include <cstdarg>
+#include <cstdio>
+
+#include "i2r_common.cuh"
+
+namespace i2r {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int check_launch(const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    set_error("%s: %s", what, cudaGetErrorString(e));
+    return static_cast<int>(e);
+  }
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// 3x3 stride-2 pad-1 convolution with Cin in {1,3}: each thread produces CPT=16 output channels of one
+// output pixel; a warp covers 8 consecutive pixels x 4 channel groups of a 64-channel output.
+template <int CIN>
+__global__ void __launch_bounds__(256) stem_conv_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                        const float* __restrict__ scale,
+                                                        const float* __restrict__ bias, __half* __restrict__ y,
+                                                        int NB, int H, int W, int Cout) {
+  extern __shared__ float sw[];  // [CIN*9][Cout] then scale[Cout], bias[Cout]
+  const int K = CIN * 9;
+  for (int i = threadIdx.x; i < K * Cout; i += blockDim.x) sw[i] = w[i];
+  float* ssc = sw + K * Cout;
+  float* sbi = ssc + Cout;
+  for (int i = threadIdx.x; i < Cout; i += blockDim.x) {
+    ssc[i] = scale[i];
+    sbi[i] = bias[i];
+  }
+  __syncthreads();
+  const int OH = H >> 1, OW = W >> 1;
+  const int groups = Cout / 16;
+  const int64_t total = static_cast<int64_t>(NB) * OH * OW * groups;
+  for (int64_t idx = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int g = static_cast<int>(idx % groups);
+    const int64_t p = idx / groups;
+    const int ox = static_cast<int>(p % OW);
+    const int oy = static_cast<int>((p / OW) % OH);
+    const int n = static_cast<int>(p / (static_cast<int64_t>(OW) * OH));
+    float acc[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) acc[i] = 0.f;
+#pragma unroll
+    for (int c = 0; c < CIN; ++c) {
+      const float* xc = x + (static_cast<int64_t>(n) * CIN + c) * H * W;
+#pragma unroll
+      for (int ky = 0; ky < 3; ++ky) {
+        const int iy = oy * 2 - 1 + ky;
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) {
+          const int ix = ox * 2 - 1 + kx;
+          float v = 0.f;
+          if (iy >= 0 && iy < H && ix >= 0 && ix < W) v = __ldg(xc + static_cast<int64_t>(iy) * W + ix);
+          const float* wk = sw + ((c * 3 + ky) * 3 + kx) * Cout + g * 16;
+#pragma unroll
+          for (int i = 0; i < 16; ++i) acc[i] = fmaf(v, wk[i], acc[i]);
+        }
+      }
+    }
+    uint32_t o[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float a = fmaxf(acc[2 * i] * ssc[g * 16 + 2 * i] + sbi[g * 16 + 2 * i], 0.f);
+      const float b = fmaxf(acc[2 * i + 1] * ssc[g * 16 + 2 * i + 1] + sbi[g * 16 + 2 * i + 1], 0.f);
+      o[i] = pack_h2(a, b);
+    }
+    uint4* dst = reinterpret_cast<uint4*>(y + p * Cout + g * 16);
+    dst[0] = make_uint4(o[0], o[1], o[2], o[3]);
+    dst[1] = make_uint4(o[4], o[5], o[6], o[7]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) maxpool3x3s2_kernel(const __half* __restrict__ x, __half* __restrict__ y,
+                                                           int NB, int H, int W, int C) {
+  const int OH = (H + 1) >> 1, OW = (W + 1) >> 1;
+  const int cv = C >> 3;
+  const int64_t total = static_cast<int64_t>(NB) * OH * OW * cv;
+  for (int64_t idx = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int c8 = static_cast<int>(idx % cv);
+    const int64_t p = idx / cv;
+    const int ox = static_cast<int>(p % OW);
+    const int oy = static_cast<int>((p / OW) % OH);
+    const int n = static_cast<int>(p / (static_cast<int64_t>(OW) * OH));
+    __half2 m[4];
+    const __half2 ninf = __float2half2_rn(-65504.f);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) m[i] = ninf;
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky) {
+      const int iy = oy * 2 - 1 + ky;
+      if (iy < 0 || iy >= H) continue;
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx) {
+        const int ix = ox * 2 - 1 + kx;
+        if (ix < 0 || ix >= W) continue;
+        const uint4 q = *reinterpret_cast<const uint4*>(x + ((static_cast<int64_t>(n) * H + iy) * W + ix) * C + c8 * 8);
+        const __half2* h = reinterpret_cast<const __half2*>(&q);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) m[i] = __hmax2(m[i], h[i]);
+      }
+    }
+    *reinterpret_cast<uint4*>(y + p * C + c8 * 8) = *reinterpret_cast<uint4*>(m);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// LayerNorm: one warp per row, 8 channels (16 B) per lane per pass, fp32 statistics (two-pass in
+// registers), optional y2 = y + pos.
+__global__ void __launch_bounds__(256) layernorm_kernel(const __half* __restrict__ x, const float* __restrict__ gamma,
+                                                        const float* __restrict__ beta,
+                                                        const __half* __restrict__ pos, __half* __restrict__ y,
+                                                        __half* __restrict__ y2, int rows, int C, float eps) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= rows) return;
+  const int c = lane * 8;
+  const bool act = c < C;
+  float v[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = 0.f;
+  if (act) {
+    const uint4 q = *reinterpret_cast<const uint4*>(x + static_cast<int64_t>(warp) * C + c);
+    const uint32_t w4[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float2 f = unpack_h2(w4[i]);
+      v[2 * i] = f.x;
+      v[2 * i + 1] = f.y;
+    }
+  }
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s += v[i];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  const float mean = s / C;
+  float sq = 0.f;
+  if (act) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float d = v[i] - mean;
+      sq += d * d;
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+  const float rstd = rsqrtf(sq / C + eps);
+  if (act) {
+    float o8[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) o8[i] = (v[i] - mean) * rstd * gamma[c + i] + beta[c + i];
+    uint4 q;
+    q.x = pack_h2(o8[0], o8[1]);
+    q.y = pack_h2(o8[2], o8[3]);
+    q.z = pack_h2(o8[4], o8[5]);
+    q.w = pack_h2(o8[6], o8[7]);
+    *reinterpret_cast<uint4*>(y + static_cast<int64_t>(warp) * C + c) = q;
+    if (y2 != nullptr) {
+      const uint4 pq = *reinterpret_cast<const uint4*>(pos + static_cast<int64_t>(warp) * C + c);
+      const uint32_t p4[4] = {pq.x, pq.y, pq.z, pq.w};
+      uint32_t r4[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float2 f = unpack_h2(p4[i]);
+        r4[i] = pack_h2(o8[2 * i] + f.x, o8[2 * i + 1] + f.y);
+      }
+      *reinterpret_cast<uint4*>(y2 + static_cast<int64_t>(warp) * C + c) = make_uint4(r4[0], r4[1], r4[2], r4[3]);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) add_f16_kernel(const uint4* __restrict__ a, const uint4* __restrict__ b,
+                                                      uint4* __restrict__ y, int64_t n8) {
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n8;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const uint4 qa = a[i], qb = b[i];
+    const __half2* ha = reinterpret_cast<const __half2*>(&qa);
+    const __half2* hb = reinterpret_cast<const __half2*>(&qb);
+    __half2 r[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) r[k] = __hadd2(ha[k], hb[k]);
+    y[i] = *reinterpret_cast<uint4*>(r);
+  }
+}
+
+static int grid_for(int64_t work_items, int block) {
+  int64_t g = (work_items + block - 1) / block;
+  const int64_t cap = 148 * 16;
+  if (g > cap) g = cap;
+  if (g < 1) g = 1;
+  return static_cast<int>(g);
+}
+
+}  // namespace i2r
+
+using namespace i2r;
+
+extern "C" int i2r_version(void) { return I2R_ABI_VERSION; }
+extern "C" const char* i2r_last_error(void) { return g_err; }
+extern "C" int i2r_sizeof_conv_problem(void) { return static_cast<int>(sizeof(i2r_conv_problem)); }
+
+extern "C" int i2r_device_check(int dev) {
+  cudaDeviceProp prop;
+  cudaError_t e = cudaGetDeviceProperties(&prop, dev);
+  if (e != cudaSuccess) {
+    set_error("cudaGetDeviceProperties(%d): %s", dev, cudaGetErrorString(e));
+    return I2R_E_DEVICE;
+  }
+  if (prop.major != 10) {
+    set_error("device %d is sm_%d%d; libi2r_sm100 contains sm_100a code only", dev, prop.major, prop.minor);
+    return I2R_E_DEVICE;
+  }
+  return 0;
+}
+
+extern "C" int i2r_sm_count(int dev) {
+  int n = 0;
+  if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return I2R_E_DEVICE;
+  return n;
+}
+
+extern "C" int i2r_stem_conv3x3s2(const float* x, const float* w, const float* scale, const float* bias, void* y,
+                                  int NB, int Cin, int H, int W, int Cout, void* stream) {
+  if (!x || !w || !scale || !bias || !y || NB <= 0 || (H & 1) || (W & 1) || Cout % 16 != 0 || Cout > 128) {
+    set_error("i2r_stem_conv3x3s2: bad arguments (Cin=%d H=%d W=%d Cout=%d)", Cin, H, W, Cout);
+    return I2R_E_BADARG;
+  }
+  const int64_t items = static_cast<int64_t>(NB) * (H / 2) * (W / 2) * (Cout / 16);
+  const size_t smem = (static_cast<size_t>(Cin) * 9 * Cout + 2 * Cout) * sizeof(float);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (Cin == 3) {
+    stem_conv_kernel<3><<<grid_for(items, 256), 256, smem, st>>>(x, w, scale, bias, static_cast<__half*>(y), NB, H, W, Cout);
+  } else if (Cin == 1) {
+    stem_conv_kernel<1><<<grid_for(items, 256), 256, smem, st>>>(x, w, scale, bias, static_cast<__half*>(y), NB, H, W, Cout);
+  } else {
+    set_error("i2r_stem_conv3x3s2: Cin=%d unsupported (1 or 3)", Cin);
+    return I2R_E_UNSUPPORTED;
+  }
+  return check_launch("stem_conv_kernel");
+}
+
+extern "C" int i2r_maxpool3x3s2(const void* x, void* y, int NB, int H, int W, int C, void* stream) {
+  if (!x || !y || NB <= 0 || H <= 0 || W <= 0 || C % 8 != 0) {
+    set_error("i2r_maxpool3x3s2: bad arguments");
+    return I2R_E_BADARG;
+  }
+  const int64_t items = static_cast<int64_t>(NB) * ((H + 1) / 2) * ((W + 1) / 2) * (C / 8);
+  maxpool3x3s2_kernel<<<grid_for(items, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __half*>(x), static_cast<__half*>(y), NB, H, W, C);
+  return check_launch("maxpool3x3s2_kernel");
+}
+
+extern "C" int i2r_layernorm(const void* x, const float* gamma, const float* beta, const void* pos, void* y,
+                             void* y2, int rows, int C, float eps, void* stream) {
+  if (!x || !gamma || !beta || !y || rows <= 0 || C % 8 != 0 || C > 256 || (y2 && !pos)) {
+    set_error("i2r_layernorm: bad arguments (rows=%d C=%d)", rows, C);
+    return I2R_E_BADARG;
+  }
+  const int wpb = 8;
+  layernorm_kernel<<<(rows + wpb - 1) / wpb, wpb * 32, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __half*>(x), gamma, beta, static_cast<const __half*>(pos), static_cast<__half*>(y),
+      static_cast<__half*>(y2), rows, C, eps);
+  return check_launch("layernorm_kernel");
+}
+
+extern "C" int i2r_add_f16(const void* a, const void* b, void* y, int64_t n, void* stream) {
+  if (!a || !b || !y || n <= 0 || n % 8 != 0) {
+    set_error("i2r_add_f16: bad arguments");
+    return I2R_E_BADARG;
+  }
+  add_f16_kernel<<<grid_for(n / 8, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const uint4*>(a), static_cast<const uint4*>(b), static_cast<uint4*>(y), n / 8);
+  return check_launch("add_f16_kernel");
+}

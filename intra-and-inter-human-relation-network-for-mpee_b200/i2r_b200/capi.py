@@ -1,0 +1,83 @@
+"""ctypes binding of include/i2r.h.  There is no fallback: a missing library is an error."""
+import ctypes
+import os
+import threading
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libi2r_sm100.so")
+
+I2R_MAX_TAPS = 9
+I2R_MAX_GROUP = 4
+F_RELU = 1
+F_OUT_NCHW_F32 = 2
+F_OUT_F32 = 4
+
+EXPORTS = [
+    "i2r_version", "i2r_last_error", "i2r_device_check", "i2r_sm_count", "i2r_conv_igemm",
+    "i2r_sizeof_conv_problem", "i2r_stem_conv3x3s2", "i2r_maxpool3x3s2", "i2r_attention_varlen", "i2r_layernorm", "i2r_add_f16",
+]
+
+
+class ConvProblem(ctypes.Structure):
+    _fields_ = [
+        ("x", ctypes.c_void_p), ("w", ctypes.c_void_p), ("scale", ctypes.c_void_p), ("bias", ctypes.c_void_p),
+        ("add0", ctypes.c_void_p), ("add1", ctypes.c_void_p), ("y", ctypes.c_void_p),
+        ("NB", ctypes.c_int32), ("IH", ctypes.c_int32), ("IW", ctypes.c_int32),
+        ("Cin", ctypes.c_int32), ("KC", ctypes.c_int32),
+        ("in_pix_stride", ctypes.c_int32), ("in_shift", ctypes.c_int32),
+        ("OH", ctypes.c_int32), ("OW", ctypes.c_int32), ("stride", ctypes.c_int32),
+        ("Cout", ctypes.c_int32), ("Npad", ctypes.c_int32), ("out_pix_stride", ctypes.c_int32),
+        ("OHf", ctypes.c_int32), ("OWf", ctypes.c_int32),
+        ("out_mul", ctypes.c_int32), ("out_offy", ctypes.c_int32), ("out_offx", ctypes.c_int32),
+        ("add0_shift", ctypes.c_int32), ("add1_shift", ctypes.c_int32),
+        ("ntaps", ctypes.c_int32),
+        ("dy", ctypes.c_int8 * (I2R_MAX_TAPS + 3)), ("dx", ctypes.c_int8 * (I2R_MAX_TAPS + 3)),
+        ("flags", ctypes.c_uint32),
+    ]
+
+
+class I2RError(RuntimeError):
+    pass
+
+
+_lock = threading.Lock()
+_lib = None
+
+
+def load():
+    """Load libi2r_sm100.so (building is the job of build.py / __graft_entry__.build())."""
+    global _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        if not os.path.exists(LIB_PATH):
+            raise I2RError(
+                "libi2r_sm100.so not found at %s -- run `python __graft_entry__.py build` "
+                "(there is no CPU or PyTorch fallback for the hot path)" % LIB_PATH)
+        lib = ctypes.CDLL(LIB_PATH)
+        vp, i32, i64, f32 = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_float
+        lib.i2r_version.restype = ctypes.c_int
+        lib.i2r_last_error.restype = ctypes.c_char_p
+        lib.i2r_device_check.argtypes = [i32]
+        lib.i2r_sm_count.argtypes = [i32]
+        lib.i2r_conv_igemm.argtypes = [ctypes.POINTER(ConvProblem), i32, i32, vp]
+        lib.i2r_stem_conv3x3s2.argtypes = [vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp]
+        lib.i2r_maxpool3x3s2.argtypes = [vp, vp, i32, i32, i32, i32, vp]
+        lib.i2r_attention_varlen.argtypes = [vp, vp, vp, vp, i32, i32, i32, i32, i32, vp, i32, i32, f32, vp]
+        lib.i2r_layernorm.argtypes = [vp, vp, vp, vp, vp, vp, i32, i32, f32, vp]
+        lib.i2r_add_f16.argtypes = [vp, vp, vp, i64, vp]
+        for name in EXPORTS:
+            getattr(lib, name)  # raises AttributeError if the symbol is missing
+        if lib.i2r_sizeof_conv_problem() != ctypes.sizeof(ConvProblem):
+            raise I2RError("i2r_conv_problem layout mismatch: C %d vs ctypes %d" % (
+                lib.i2r_sizeof_conv_problem(), ctypes.sizeof(ConvProblem)))
+        if lib.i2r_version() != 1:
+            raise I2RError("libi2r_sm100.so ABI version %d, binding expects 1" % lib.i2r_version())
+        _lib = lib
+        return lib
+
+
+def check(rc, what):
+    if rc != 0:
+        msg = load().i2r_last_error().decode("utf-8", "replace")
+        raise I2RError("%s failed (rc=%d): %s" % (what, rc, msg))

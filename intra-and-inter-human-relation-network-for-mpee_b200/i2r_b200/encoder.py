@@ -1,0 +1,67 @@
+"""Post-norm Transformer encoder over ragged token sequences (inter-human stage; also the TransPose-H
+intra stage).  Reference semantics: TransformerEncoderLayer.forward_post
+(lib/models/interformer_pureMulti.py:182-213; lib/models/attention.py:61-82) on top of
+nn.MultiheadAttention(nhead=1): q = k = (src+pos) W_qk + b, v = src W_v + b, q scaled by
+head_dim**-0.5, softmax over the keys of the same image (padded persons never exist here: sequences
+are stored ragged, which is exactly equivalent to key_padding_mask on zero-padded persons because
+padded query rows are discarded by get_valid_output).
+"""
+import math
+
+import torch
+
+from .ops import ConvLayer
+
+
+def _linear_layer(weight, bias, relu=False, device="cuda"):
+    return ConvLayer([weight.float()], [0], [0], torch.ones(weight.shape[0]), bias.float(), relu=relu, device=device)
+
+
+class EncoderLayerProgram:
+    def __init__(self, sd, prefix, d_model, device):
+        w = sd[prefix + ".self_attn.in_proj_weight"].float()
+        b = sd[prefix + ".self_attn.in_proj_bias"].float()
+        d = d_model
+        self.d = d
+        self.qk = _linear_layer(w[: 2 * d], b[: 2 * d], device=device)
+        self.v = _linear_layer(w[2 * d:], b[2 * d:], device=device)
+        self.out = _linear_layer(sd[prefix + ".self_attn.out_proj.weight"], sd[prefix + ".self_attn.out_proj.bias"],
+                                 device=device)
+        self.ff1 = _linear_layer(sd[prefix + ".linear1.weight"], sd[prefix + ".linear1.bias"], relu=True,
+                                 device=device)
+        self.ff2 = _linear_layer(sd[prefix + ".linear2.weight"], sd[prefix + ".linear2.bias"], device=device)
+        self.n1 = (sd[prefix + ".norm1.weight"].float().to(device), sd[prefix + ".norm1.bias"].float().to(device))
+        self.n2 = (sd[prefix + ".norm2.weight"].float().to(device), sd[prefix + ".norm2.bias"].float().to(device))
+
+
+class EncoderProgram:
+    """`layers`-deep encoder; tokens [T, d] fp16, sequences delimited by cu_seqlens (int32, device)."""
+
+    def __init__(self, sd, prefix, num_layers, d_model, nhead, device, normalize_before=False):
+        if nhead != 1:
+            raise NotImplementedError("N_HEAD=%d (all shipped configs use 1 head)" % nhead)
+        if normalize_before:
+            raise NotImplementedError("NORMALIZE_BEFORE=True (default False in every shipped config)")
+        self.layers = [EncoderLayerProgram(sd, "%s.layers.%d" % (prefix, i), d_model, device)
+                       for i in range(num_layers)]
+        self.d = d_model
+        self.scale = 1.0 / math.sqrt(d_model // nhead)
+
+    def run(self, r, src, pos, cu_seqlens, max_seqlen):
+        d = self.d
+        sp = r.add(src, pos) if pos is not None else src
+        for li, L in enumerate(self.layers):
+            pq, _ = r.linear_problem(L.qk, sp)
+            pv, _ = r.linear_problem(L.v, src)
+            r.launch([pq, pv])
+            qk = pq._keep[4].view(-1, 2 * d)
+            v = pv._keep[4].view(-1, d)
+            a = r.attention(qk[:, :d], qk[:, d:], v, cu_seqlens, max_seqlen, self.scale)
+            x1 = r.linear(L.out, a, add0=src)
+            s1, _ = r.layernorm(x1, L.n1[0], L.n1[1])
+            h = r.linear(L.ff1, s1)
+            x2 = r.linear(L.ff2, h, add0=s1)
+            last = li == len(self.layers) - 1
+            src, sp2 = r.layernorm(x2, L.n2[0], L.n2[1], pos=None if (last or pos is None) else pos)
+            sp = sp2 if sp2 is not None else src
+        return src

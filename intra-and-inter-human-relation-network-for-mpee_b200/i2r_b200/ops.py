@@ -1,0 +1,191 @@
+"""Op wrappers: fill i2r_conv_problem structs / argument lists and launch through the C ABI on
+torch's current CUDA stream.  Activations are fp16 NHWC torch tensors (device memory plumbing only)."""
+import ctypes
+
+import torch
+
+from . import capi
+from .packing import ceil_to, pad_vec, pick_kc, pack_taps
+
+
+class ConvLayer:
+    """Device-resident parameters of one implicit-GEMM problem (weights packed, BN folded)."""
+
+    def __init__(self, mats, dys, dxs, scale, bias, stride=1, relu=False, device="cuda"):
+        cout, cin = mats[0].shape
+        self.cin, self.cout = cin, cout
+        self.kc = pick_kc(cin)
+        self.npad = ceil_to(cout, 16)
+        self.ntaps = len(mats)
+        if self.ntaps > capi.I2R_MAX_TAPS:
+            raise ValueError("too many taps")
+        self.dy, self.dx = list(dys), list(dxs)
+        self.stride, self.relu = stride, relu
+        self.w = pack_taps(mats, self.kc).to(device)
+        self.scale = pad_vec(scale, self.npad, 1.0).to(device)
+        self.bias = pad_vec(bias, self.npad, 0.0).to(device)
+
+
+def _stream_ptr():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+class Runner:
+    """Launch helper bound to one device.  impl=0: tcgen05 kernels (product); impl=1: scalar check kernel."""
+
+    def __init__(self, device, impl=0):
+        self.lib = capi.load()
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise capi.I2RError("the I2R-Net hot path runs on CUDA devices only (got %s)" % device)
+        capi.check(self.lib.i2r_device_check(self.device.index or 0), "i2r_device_check")
+        self.impl = impl
+        self.launches = 0
+
+    # ------------------------------------------------------------------ implicit GEMM
+    def problem(self, L, x, out=None, add0=None, add0_shift=0, add1=None, add1_shift=0, in_shift=0,
+                relu=None, out_mode="nhwc16", out_hw=None, out_mul=1, out_off=(0, 0), ohow=None):
+        """Build one problem.  x: fp16 [NB, Hs, Ws, C>=Cin] (channel stride 1).  Returns (ConvProblem, out)."""
+        assert x.dtype == torch.float16 and x.dim() == 4 and x.stride(3) == 1
+        nb, hs, ws, _ = x.shape
+        pix = x.stride(2)
+        assert x.stride(1) == ws * pix and (nb == 1 or x.stride(0) == hs * ws * pix), "x must be pixel-contiguous"
+        ih, iw = hs << in_shift, ws << in_shift
+        if ohow is None:
+            if L.stride == 1:
+                oh, ow = ih, iw
+            else:
+                oh, ow = (ih + L.stride - 1) // L.stride, (iw + L.stride - 1) // L.stride
+        else:
+            oh, ow = ohow
+        ohf, owf = out_hw if out_hw is not None else (oh * out_mul, ow * out_mul)
+        flags = 0
+        if (L.relu if relu is None else relu):
+            flags |= capi.F_RELU
+        if out is None:
+            if out_mode == "nhwc16":
+                out = torch.empty((nb, ohf, owf, L.cout), dtype=torch.float16, device=x.device)
+            elif out_mode == "nchw32":
+                out = torch.empty((nb, L.cout, ohf, owf), dtype=torch.float32, device=x.device)
+            elif out_mode == "nhwc32":
+                out = torch.empty((nb, ohf, owf, L.cout), dtype=torch.float32, device=x.device)
+            else:
+                raise ValueError(out_mode)
+        if out_mode == "nchw32":
+            flags |= capi.F_OUT_NCHW_F32
+            out_pix = 0
+            assert out.is_contiguous()
+        else:
+            if out_mode == "nhwc32":
+                flags |= capi.F_OUT_F32
+            assert out.stride(3) == 1
+            out_pix = out.stride(2)
+        p = capi.ConvProblem()
+        p.x, p.w, p.scale, p.bias = x.data_ptr(), L.w.data_ptr(), L.scale.data_ptr(), L.bias.data_ptr()
+        p.add0 = add0.data_ptr() if add0 is not None else None
+        p.add1 = add1.data_ptr() if add1 is not None else None
+        for a in (add0, add1):
+            if a is not None:
+                assert a.dtype == torch.float16 and a.is_contiguous() and a.shape[-1] == L.cout
+        p.y = out.data_ptr()
+        p.NB, p.IH, p.IW, p.Cin, p.KC = nb, ih, iw, L.cin, L.kc
+        p.in_pix_stride, p.in_shift = pix, in_shift
+        p.OH, p.OW, p.stride = oh, ow, L.stride
+        p.Cout, p.Npad, p.out_pix_stride = L.cout, L.npad, out_pix
+        p.OHf, p.OWf = ohf, owf
+        p.out_mul, p.out_offy, p.out_offx = out_mul, out_off[0], out_off[1]
+        p.add0_shift, p.add1_shift = add0_shift, add1_shift
+        p.ntaps = L.ntaps
+        for t in range(L.ntaps):
+            p.dy[t], p.dx[t] = L.dy[t], L.dx[t]
+        p.flags = flags
+        p._keep = (x, L, add0, add1, out)
+        return p, out
+
+    def launch(self, problems):
+        n = len(problems)
+        arr = (capi.ConvProblem * n)(*problems)
+        capi.check(self.lib.i2r_conv_igemm(arr, n, self.impl, _stream_ptr()), "i2r_conv_igemm")
+        self.launches += 1
+
+    def conv(self, L, x, **kw):
+        p, out = self.problem(L, x, **kw)
+        self.launch([p])
+        return out
+
+    def conv_group(self, specs):
+        """specs: list of (L, x, kwargs) launched as one grid.  Returns the list of outputs."""
+        probs, outs = [], []
+        for L, x, kw in specs:
+            p, o = self.problem(L, x, **kw)
+            probs.append(p)
+            outs.append(o)
+        for i in range(0, len(probs), capi.I2R_MAX_GROUP):
+            self.launch(probs[i:i + capi.I2R_MAX_GROUP])
+        return outs
+
+    def linear(self, L, x2d, add0=None, relu=None):
+        """x2d: fp16 [T, Cin] (row stride >= Cin) -> contiguous [T, Cout]: a 1x1 'convolution' over T pixels."""
+        p, out = self.linear_problem(L, x2d, add0=add0, relu=relu)
+        self.launch([p])
+        return out.view(x2d.shape[0], L.cout)
+
+    def linear_problem(self, L, x2d, add0=None, relu=None):
+        t, c = x2d.shape
+        assert x2d.stride(1) == 1
+        ld = x2d.stride(0)
+        x4 = x2d.as_strided((1, t, 1, c), (t * ld, ld, ld, 1))
+        a4 = add0.view(1, t, 1, -1) if add0 is not None else None
+        return self.problem(L, x4, add0=a4, relu=relu)
+
+    # ------------------------------------------------------------------ small kernels
+    def stem(self, x, w, scale, bias, cout):
+        nb, cin, h, wd = x.shape
+        assert x.dtype == torch.float32 and x.is_contiguous()
+        y = torch.empty((nb, h // 2, wd // 2, cout), dtype=torch.float16, device=x.device)
+        capi.check(self.lib.i2r_stem_conv3x3s2(x.data_ptr(), w.data_ptr(), scale.data_ptr(), bias.data_ptr(),
+                                                y.data_ptr(), nb, cin, h, wd, cout, _stream_ptr()),
+                   "i2r_stem_conv3x3s2")
+        self.launches += 1
+        return y
+
+    def maxpool(self, x):
+        nb, h, w, c = x.shape
+        assert x.is_contiguous() and x.dtype == torch.float16
+        y = torch.empty((nb, (h + 1) // 2, (w + 1) // 2, c), dtype=torch.float16, device=x.device)
+        capi.check(self.lib.i2r_maxpool3x3s2(x.data_ptr(), y.data_ptr(), nb, h, w, c, _stream_ptr()),
+                   "i2r_maxpool3x3s2")
+        self.launches += 1
+        return y
+
+    def layernorm(self, x2d, gamma, beta, eps=1e-5, pos=None):
+        rows, c = x2d.shape
+        assert x2d.is_contiguous() and x2d.dtype == torch.float16
+        y = torch.empty_like(x2d)
+        y2 = torch.empty_like(x2d) if pos is not None else None
+        capi.check(self.lib.i2r_layernorm(x2d.data_ptr(), gamma.data_ptr(), beta.data_ptr(),
+                                           pos.data_ptr() if pos is not None else None, y.data_ptr(),
+                                           y2.data_ptr() if y2 is not None else None, rows, c, eps,
+                                           _stream_ptr()), "i2r_layernorm")
+        self.launches += 1
+        return y, y2
+
+    def add(self, a, b):
+        assert a.shape == b.shape and a.is_contiguous() and b.is_contiguous()
+        y = torch.empty_like(a)
+        capi.check(self.lib.i2r_add_f16(a.data_ptr(), b.data_ptr(), y.data_ptr(), a.numel(), _stream_ptr()),
+                   "i2r_add_f16")
+        self.launches += 1
+        return y
+
+    def attention(self, q, k, v, cu_seqlens, max_seqlen, scale):
+        """q,k,v: fp16 2-D views [T, D] (row stride arbitrary multiple of 8); returns [T, D] contiguous."""
+        t, d = q.shape
+        out = torch.empty((t, d), dtype=torch.float16, device=q.device)
+        nseq = cu_seqlens.numel() - 1
+        capi.check(self.lib.i2r_attention_varlen(q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(),
+                                                  q.stride(0), k.stride(0), v.stride(0), out.stride(0), d,
+                                                  cu_seqlens.data_ptr(), nseq, max_seqlen, scale, _stream_ptr()),
+                   "i2r_attention_varlen")
+        self.launches += 1
+        return out

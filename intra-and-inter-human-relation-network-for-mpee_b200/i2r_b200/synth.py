@@ -1,0 +1,63 @@
+"""Deterministic synthetic weights and inputs (there are no datasets or checkpoints offline).
+
+`synth_state_dict` fills a state_dict *by key name*, independent of module construction order, so
+the reference model (when generating golden vectors), the oracle and the B200 module all receive
+bit-identical fp32 weights.  Scales follow PyTorch's default initialisers (conv/linear
+U(+-1/sqrt(fan_in)), encoder matrices xavier-uniform) so activations stay O(1); BatchNorm /
+LayerNorm statistics are made non-trivial so folding errors cannot hide.
+"""
+import zlib
+
+import numpy as np
+import torch
+
+
+def _rng(seed, key):
+    return np.random.default_rng([int(seed), zlib.crc32(key.encode("utf-8"))])
+
+
+def synth_state_dict(reference_sd, seed=0):
+    """Return a new state_dict with the keys/shapes/dtypes of `reference_sd` and synthetic values."""
+    out = {}
+    keys = list(reference_sd.keys())
+    keyset = set(keys)
+    for key in keys:
+        ref = reference_sd[key]
+        shape = tuple(ref.shape)
+        leaf = key.rsplit(".", 1)[-1]
+        prefix = key.rsplit(".", 1)[0] if "." in key else ""
+        g = _rng(seed, key)
+        if leaf == "num_batches_tracked":
+            out[key] = torch.zeros(shape, dtype=ref.dtype)
+            continue
+        if leaf in ("pos_embedding",) or not ref.dtype.is_floating_point:
+            out[key] = ref.detach().clone()  # structural constants (sine table) stay as constructed
+            continue
+        is_norm = (prefix + ".running_var") in keyset or ("norm" in prefix.rsplit(".", 1)[-1] and len(shape) == 1)
+        if leaf == "running_var":
+            val = g.uniform(0.5, 1.5, size=shape)
+        elif leaf == "running_mean":
+            val = g.normal(0.0, 0.1, size=shape)
+        elif is_norm and leaf == "weight":
+            val = g.uniform(0.5, 1.5, size=shape)
+        elif is_norm and leaf == "bias":
+            val = g.normal(0.0, 0.1, size=shape)
+        elif len(shape) >= 2:
+            fan_in = int(np.prod(shape[1:]))
+            if "encoder" in key and len(shape) == 2:
+                bound = float(np.sqrt(6.0 / (shape[0] + shape[1])))  # xavier-uniform
+            else:
+                bound = 1.0 / float(np.sqrt(fan_in))
+            val = g.uniform(-bound, bound, size=shape)
+        else:
+            val = g.uniform(-0.1, 0.1, size=shape)
+        out[key] = torch.from_numpy(np.asarray(val, dtype=np.float32)).to(ref.dtype)
+    return out
+
+
+def synth_inputs(num_crops, height=256, width=192, seed=1):
+    """x ~ N(0,1) [S,3,H,W] and pos_mask ~ U(0,1) [S,1,H,W], fp32."""
+    g = np.random.default_rng(int(seed))
+    x = g.standard_normal(size=(num_crops, 3, height, width), dtype=np.float32)
+    pm = g.random(size=(num_crops, 1, height, width), dtype=np.float32)
+    return torch.from_numpy(x), torch.from_numpy(pm)

@@ -1,0 +1,3 @@
+"""Model registry: `eval('models.' + cfg.MODEL.NAME + '.get_pose_net')` must resolve exactly as in the
+reference (tools/test.py:87), so the sub-module names are part of the API (lib/models/__init__.py:16-23)."""
+import models.interformer_pureMulti  # noqa: F401

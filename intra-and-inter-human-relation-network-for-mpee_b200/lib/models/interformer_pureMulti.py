@@ -1,0 +1,226 @@
+"""Vanilla I2R-Net ("interformer_pureMulti"): HRNet-W48-S -> reduce -> inter-human encoder over the
+16x12 token maps of all persons of an image -> the same deconv applied twice -> 1x1 heatmap head.
+
+Drop-in for the reference module of the same name (lib/models/interformer_pureMulti.py):
+`get_pose_net(cfg, is_train)` returns an nn.Module with identical state_dict keys/shapes whose
+`forward(x, pos_mask, length)` runs entirely in the sm_100a kernels of libi2r_sm100.so.
+There is no torch/CPU forward here: calling it off-GPU raises.
+"""
+import logging
+import math
+import os
+
+import torch
+import torch.nn as nn
+
+from i2r_b200 import capi
+from i2r_b200.encoder import EncoderProgram
+from i2r_b200.hrnet_w48 import BackboneProgram, attach_backbone_params, conv_bn_layer
+from i2r_b200.ops import ConvLayer, Runner
+from i2r_b200.packing import deconv4x4s2_phase_taps, fold_bn
+from i2r_b200.position import MaskEmbedParams, MaskEmbedProgram, sine_table
+from i2r_b200.engine import GraphedForward
+
+logger = logging.getLogger(__name__)
+
+
+class EncoderLayerParams(nn.Module):
+    """self_attn / linear1 / linear2 / norm1 / norm2 holder (reference :169-180)."""
+
+    def __init__(self, d_model, nhead, dim_feedforward):
+        super().__init__()
+        self.self_attn = nn.MultiheadAttention(d_model, nhead, dropout=0.1)
+        self.linear1 = nn.Linear(d_model, dim_feedforward)
+        self.linear2 = nn.Linear(dim_feedforward, d_model)
+        self.norm1 = nn.LayerNorm(d_model)
+        self.norm2 = nn.LayerNorm(d_model)
+
+
+class EncoderParams(nn.Module):
+    def __init__(self, d_model, nhead, dim_feedforward, num_layers):
+        super().__init__()
+        self.layers = nn.ModuleList([EncoderLayerParams(d_model, nhead, dim_feedforward) for _ in range(num_layers)])
+        for p in self.parameters():
+            if p.dim() > 1:
+                nn.init.xavier_uniform_(p)
+
+
+class DeconvProgram:
+    """ConvTranspose2d(4, s=2, p=1) + BN + ReLU as four 2x2-tap phase problems in one grid."""
+
+    def __init__(self, sd, conv_key, bn_key, device):
+        w = sd[conv_key + ".weight"].float()          # [Cin, Cout, 4, 4]
+        scale, bias = fold_bn(sd, bn_key, w.shape[1], conv_bias=sd.get(conv_key + ".bias"))
+        self.phases = []
+        for py in (0, 1):
+            for px in (0, 1):
+                mats, dys, dxs = deconv4x4s2_phase_taps(w, py, px)
+                self.phases.append(((py, px), ConvLayer(mats, dys, dxs, scale, bias, relu=True, device=device)))
+        self.cout = w.shape[1]
+
+    def run(self, r, x):
+        nb, h, w, _ = x.shape
+        out = torch.empty((nb, 2 * h, 2 * w, self.cout), dtype=torch.float16, device=x.device)
+        r.conv_group([(L, x, dict(out=out, out_hw=(2 * h, 2 * w), out_mul=2, out_off=off)) for off, L in self.phases])
+        return out
+
+
+class TransPoseH(nn.Module):
+    def __init__(self, cfg, **kwargs):
+        super().__init__()
+        extra = cfg["MODEL"]["EXTRA"]
+        pre = attach_backbone_params(self, extra)
+        m = cfg.MODEL
+        self.trans_size = list(m.TRANS_SIZE)
+        d_model = m.DIM_MODEL
+        w, h = m.IMAGE_SIZE
+        self.use_multi_pos = bool(m.USE_MULTI_POS)
+        self.position_embedding = MaskEmbedParams(self.trans_size, d_model, mode=m.MULTI_POS_EMBEDDING,
+                                                  vec_dim=d_model)
+        self.reduce = nn.Conv2d(pre[-1], d_model, 1, bias=False)
+        if m.POS_EMBEDDING not in ("none", "learnable", "sine"):
+            raise AssertionError("POS_EMBEDDING must be none/learnable/sine")
+        if m.POS_EMBEDDING == "none":
+            self.pos_embedding = None
+        elif m.POS_EMBEDDING == "learnable":
+            self.pos_embedding = nn.Parameter(torch.randn((h // 4) * (w // 4), 1, d_model))
+        else:
+            self.pos_embedding = nn.Parameter(sine_table(h // 4, w // 4, d_model), requires_grad=False)
+        self.global_encoder = EncoderParams(d_model, m.N_HEAD, m.DIM_FEEDFORWARD, m.ENCODER_LAYERS)
+        self.deconv_with_bias = bool(extra.DECONV_WITH_BIAS)
+        nl, nf, nk = extra.NUM_DECONV_LAYERS, list(extra.NUM_DECONV_FILTERS), list(extra.NUM_DECONV_KERNELS)
+        assert nl == len(nf), "ERROR: num_deconv_layers is different len(num_deconv_filters)"
+        assert nl == len(nk), "ERROR: num_deconv_layers is different len(num_deconv_filters)"
+        mods = []
+        for i in range(nl):
+            if nk[i] != 4:
+                raise NotImplementedError("deconv kernel %d (shipped configs use 4)" % nk[i])
+            mods += [nn.ConvTranspose2d(nf[i], nf[i], 4, 2, 1, 0, bias=self.deconv_with_bias),
+                     nn.BatchNorm2d(nf[i], momentum=0.1), nn.ReLU(inplace=True)]
+        self.deconv_layers = nn.Sequential(*mods)
+        k = extra["FINAL_CONV_KERNEL"]
+        self.final_layer = nn.Conv2d(d_model, cfg["MODEL"]["NUM_JOINTS"], k, 1, 1 if k == 3 else 0)
+        self.pretrained_layers = extra["PRETRAINED_LAYERS"]
+        self._cfg = dict(d_model=d_model, nhead=m.N_HEAD, layers=m.ENCODER_LAYERS, num_deconv=nl, final_k=k,
+                         mode=m.MULTI_POS_EMBEDDING)
+        self._program = None
+        self._graphs = GraphedForward(self._eager)
+        self.use_cuda_graph = os.environ.get("I2R_CUDA_GRAPH", "1") != "0"
+        self.check_impl = False   # tests: route implicit GEMMs through the scalar check kernel
+
+    # ------------------------------------------------------------------ weights -> device program
+    def prepare(self, device=None):
+        """Fold BN, pack weights and upload (called lazily by forward; call again after loading weights)."""
+        device = torch.device(device) if device is not None else self.final_layer.weight.device
+        sd = {k: v.detach().cpu() for k, v in self.state_dict().items()}
+        c = self._cfg
+        if c["mode"] != "conv" and self.use_multi_pos:
+            raise NotImplementedError("MULTI_POS_EMBEDDING=%r (shipped configs use 'conv')" % c["mode"])
+        if c["final_k"] != 1:
+            raise NotImplementedError("FINAL_CONV_KERNEL=3")
+        prog = type("Program", (), {})()
+        prog.device = device
+        prog.runner = Runner(device, impl=1 if self.check_impl else 0)
+        prog.backbone = BackboneProgram(self, sd, device)
+        prog.reduce = conv_bn_layer(sd, "reduce", None, device=device)
+        prog.mask_embed = MaskEmbedProgram(sd, "position_embedding", device) if self.use_multi_pos else None
+        prog.encoder = EncoderProgram(sd, "global_encoder", c["layers"], c["d_model"], c["nhead"], device)
+        prog.deconvs = [DeconvProgram(sd, "deconv_layers.%d" % (3 * i), "deconv_layers.%d" % (3 * i + 1), device)
+                        for i in range(c["num_deconv"])]
+        prog.head = conv_bn_layer(sd, "final_layer", None, device=device)
+        offsets = {}
+
+        def seq_offsets(length, tokens_per_person):
+            # device copy of the per-image token offsets; cached so that graph capture sees no H2D copy
+            key = (tuple(length), tokens_per_person)
+            if key not in offsets:
+                offsets[key] = GraphedForward.seq_offsets(length, tokens_per_person, device)
+            return offsets[key]
+        prog.seq_offsets = seq_offsets
+        self._program = prog
+        self._graphs.reset()
+        return self
+
+    def load_state_dict(self, *a, **kw):
+        out = super().load_state_dict(*a, **kw)
+        self._program = None
+        return out
+
+    def _apply(self, fn, *a, **kw):
+        out = super()._apply(fn, *a, **kw)
+        self._program = None
+        return out
+
+    # ------------------------------------------------------------------ forward
+    def _eager(self, x, pos_mask, length):
+        p = self._program
+        r = p.runner
+        feats = p.backbone.run(r, x)
+        tok_map = r.conv(p.reduce, feats[-1])                      # [S, 16, 12, d]
+        s, th, tw, d = tok_map.shape
+        src = tok_map.view(s * th * tw, d)
+        pos = None
+        if p.mask_embed is not None:
+            pos = p.mask_embed.run(r, pos_mask, (th, tw)).view(s * th * tw, d)
+        cu = p.seq_offsets(length, th * tw)
+        y = p.encoder.run(r, src, pos, cu, max(length) * th * tw)
+        y = y.view(s, th, tw, d)
+        for dc in p.deconvs:      # the reference applies the same deconv stack twice (:774-775)
+            y = dc.run(r, y)
+        for dc in p.deconvs:
+            y = dc.run(r, y)
+        return r.conv(p.head, y, out_mode="nchw32")
+
+    def forward(self, x, pos_mask, length):
+        length = [int(n) for n in length]
+        if sum(length) != x.shape[0] or x.shape[0] != pos_mask.shape[0]:
+            raise ValueError("sum(length)=%d must equal the number of crops %d" % (sum(length), x.shape[0]))
+        if min(length) < 1:
+            raise ValueError("every image needs at least one person crop")
+        dev = self.final_layer.weight.device
+        if dev.type != "cuda":
+            raise capi.I2RError("interformer_pureMulti forward runs on a CUDA (sm_100a) device only; "
+                                "move the module with .cuda() -- there is no CPU fallback")
+        if self._program is None or self._program.device != dev:
+            self.prepare(dev)
+        x = x.to(dev, dtype=torch.float32, non_blocking=True).contiguous()
+        pos_mask = pos_mask.to(dev, dtype=torch.float32, non_blocking=True).contiguous()
+        with torch.no_grad():
+            if self.use_cuda_graph:
+                return self._graphs(x, pos_mask, length)
+            return self._eager(x, pos_mask, length)
+
+    def init_weights(self, pretrained="", fixed=False, print_load_info=False):
+        """Training-time initialisation (reference :779-813): N(0, 0.001) convs, identity BN, then the
+        ImageNet backbone checkpoint restricted to PRETRAINED_LAYERS."""
+        for mod in self.modules():
+            if isinstance(mod, (nn.Conv2d, nn.ConvTranspose2d)):
+                nn.init.normal_(mod.weight, std=0.001)
+                if mod.bias is not None:
+                    nn.init.constant_(mod.bias, 0)
+            elif isinstance(mod, nn.BatchNorm2d):
+                nn.init.constant_(mod.weight, 1)
+                nn.init.constant_(mod.bias, 0)
+        if os.path.isfile(pretrained):
+            ckpt = torch.load(pretrained, map_location="cpu")
+            own = self.state_dict()
+            keep = {}
+            for name, t in ckpt.items():
+                if (name.split(".")[0] in self.pretrained_layers and name in own) or self.pretrained_layers[0] == "*":
+                    if fixed:
+                        t.requires_grad_(False)
+                    keep[name] = t
+                    if print_load_info:
+                        print(":: {} is loaded from {}".format(name, pretrained))
+            self.load_state_dict(keep, strict=False)
+        elif pretrained:
+            logger.error("=> please download pre-trained models first!")
+            raise ValueError("{} is not exist!".format(pretrained))
+        self._program = None
+
+
+def get_pose_net(cfg, is_train, **kwargs):
+    model = TransPoseH(cfg, **kwargs)
+    if is_train and cfg["MODEL"]["INIT_WEIGHTS"]:
+        model.init_weights(cfg["MODEL"]["PRETRAINED"], cfg["MODEL"]["BACKBONE_FIX"])
+    return model

@@ -1,0 +1,1 @@
+from torch.nn.modules.batchnorm import _BatchNorm  # noqa: F401

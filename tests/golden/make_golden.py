@@ -1,0 +1,72 @@
+"""Generate tests/golden/*.npz and *.json from the REAL reference (run in the build container only):
+
+    python tests/golden/make_golden.py
+
+For each case: build the reference model from its own yaml, load the deterministic synthetic weights
+(i2r_b200.synth.synth_state_dict -- keyed by parameter name), run the reference forward on the
+synthetic inputs in fp32 on CPU, and store the heatmaps plus two intermediate taps (forward hooks on
+`reduce` and `global_encoder`).  The key/shape list of the state_dict is stored as JSON so the
+drop-in module's parameter surface can be checked without the reference.
+"""
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REPO = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, REPO)
+sys.path.insert(0, os.path.join(REPO, "intra-and-inter-human-relation-network-for-mpee_b200"))
+
+from oracle import ref_harness  # noqa: E402
+from i2r_b200.synth import synth_inputs, synth_state_dict  # noqa: E402
+
+CASES = {
+    # name: (yaml, length, H, W)
+    "vanilla_c1": ("coco/interformer_coco_w48_pure_en6.yaml", [1], 256, 192),
+    "vanilla_ragged": ("coco/interformer_coco_w48_pure_en6.yaml", [2, 1], 256, 192),
+}
+
+
+def main():
+    torch.manual_seed(0)
+    torch.set_num_threads(os.cpu_count())
+    models = {}
+    for name, (yaml_rel, length, h, w) in CASES.items():
+        if yaml_rel not in models:
+            cfg, model = ref_harness.build_reference_model(yaml_rel)
+            sd = synth_state_dict(model.state_dict(), seed=0)
+            model.load_state_dict(sd, strict=True)
+            models[yaml_rel] = model
+            keys = {k: [list(v.shape), str(v.dtype).replace("torch.", "")] for k, v in model.state_dict().items()}
+            with open(os.path.join(HERE, "state_dict_%s.json" % cfg.MODEL.NAME), "w") as f:
+                json.dump(keys, f, indent=0, sort_keys=True)
+        model = models[yaml_rel]
+        x, pm = synth_inputs(sum(length), h, w, seed=1)
+        taps = {}
+        hooks = []
+        if hasattr(model, "reduce"):
+            hooks.append(model.reduce.register_forward_hook(lambda m, i, o: taps.__setitem__("reduce", o.detach())))
+        if hasattr(model, "global_encoder"):
+            hooks.append(model.global_encoder.register_forward_hook(
+                lambda m, i, o: taps.__setitem__("encoded_lbc", o.detach())))
+        with torch.no_grad():
+            out = model(x, pm, length)
+        for hk in hooks:
+            hk.remove()
+        arrays = {"length": np.asarray(length, dtype=np.int64)}
+        if isinstance(out, dict):
+            for k, v in out.items():
+                arrays["out_" + k] = v.numpy()
+        else:
+            arrays["out"] = out.numpy()
+        for k, v in taps.items():
+            arrays["tap_" + k] = v.numpy()
+        np.savez_compressed(os.path.join(HERE, name + ".npz"), **arrays)
+        print(name, {k: (v.shape, float(np.abs(v).max())) for k, v in arrays.items()})
+
+
+if __name__ == "__main__":
+    main()
