@@ -1,0 +1,264 @@
+#!/usr/bin/env python
+"""bench.py -- person-crops/s of the I2R-Net forward (BASELINE config C2: vanilla HRNet-W48-S,
+256x192, 8 images x 4 persons = 32 crops per GPU per step), one process per GPU.
+
+  python bench.py --gpus 1 --steps 20 --warmup 5
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+         --master-port P bench.py --gpus N --steps K --warmup W
+  python bench.py --impl reference ...     # the reference algorithm on the host CPU cores (oracle port)
+
+One JSON line on stdout (rank 0).  `value` = crops/s with inputs resident in HBM; `e2e` = the same
+through the public module call with pinned HOST inputs and a host read of the heatmaps every step.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+import paths  # noqa: F401
+
+GFLOP_PER_CROP = {"C2": 19.43}      # algorithmic, 2*MAC, BASELINE.md section 2
+IMAGES_PER_RANK, PERSONS = 8, 4
+H, W = 256, 192
+
+
+def _peaks():
+    p = os.path.join(paths.REPO, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return d, "measured"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.stop_flag = index, [], False
+        self.proc = None
+
+    def run(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                self.samples.append([s.strip() for s in line.split(",")])
+                if self.stop_flag:
+                    break
+        except Exception:
+            pass
+
+    def finish(self):
+        self.stop_flag = True
+        if self.proc is not None:
+            self.proc.terminate()
+        sm, mx, reasons = [], 0, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for s in self.samples:
+            try:
+                sm.append(float(s[0]))
+                mx = max(mx, float(s[1]))
+                for n, v in zip(names, s[2:6]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                continue
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def _dist_env():
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    return rank, world, local
+
+
+def cpu_forward_timer(steps, warmup):
+    """Times the reference algorithm (oracle port, torch CPU fp32, all host threads) on the C2 batch."""
+    sys.path.insert(0, os.path.join(paths.REPO, "tests"))
+    from helpers import build_model, inputs_for
+    from oracle import i2r_oracle
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    cfg, _, sd = build_model()
+    length = [PERSONS] * IMAGES_PER_RANK
+    x, pm = inputs_for(length)
+    times = []
+    with torch.no_grad():
+        for i in range(warmup + steps):
+            t0 = time.perf_counter()
+            i2r_oracle.vanilla_forward(sd, cfg, x, pm, length)
+            dt = time.perf_counter() - t0
+            if i >= warmup:
+                times.append(dt)
+    crops = sum(length)
+    mean = sum(times) / len(times)
+    return {"value": crops / mean, "unit": "crops/s", "cores": cores, "kind": "port",
+            "sample": "%d forwards of the C2 batch (%d crops, 256x192), oracle port of the reference forward, "
+                      "torch CPU fp32, %d threads" % (len(times), crops, cores)}, mean
+
+
+def run_reference(args):
+    rank, world, _ = _dist_env()
+    if rank != 0:
+        return
+    steps, warmup = min(args.steps, 10), min(args.warmup, 2)
+    base, mean = cpu_forward_timer(steps, warmup)
+    line = {"impl": "reference", "metric": "person-crops/sec", "value": base["value"], "unit": "crops/s",
+            "n_gpus": args.gpus, "steps": steps, "warmup": warmup, "ms_per_step": mean * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "C2: vanilla I2R-Net HRNet-W48-S 256x192, 8 images x 4 persons (32 crops), "
+                                   "CPU forward of the reference algorithm"},
+            "cpu_baseline": base,
+            "e2e": {"value": base["value"], "unit": "crops/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    rank, world, local = _dist_env()
+    if args.warmup < 3:
+        args.warmup = 3
+    import torch.distributed as dist
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    sys.path.insert(0, os.path.join(paths.REPO, "tests"))
+    from helpers import build_model
+    from i2r_b200.synth import synth_inputs
+    cfg, model, sd = build_model()
+    model = model.cuda(dev)
+    length = [PERSONS] * IMAGES_PER_RANK
+    crops = sum(length)
+
+    # ---- inputs: NBUF distinct batches so consecutive steps do not re-read the same lines from L2
+    NBUF = 8
+    hx, hm = [], []
+    for i in range(NBUF):
+        x, pm = synth_inputs(crops, H, W, seed=100 + rank * NBUF + i)
+        hx.append(x.pin_memory())
+        hm.append(pm.pin_memory())
+    dx = [t.to(dev) for t in hx]
+    dm = [t.to(dev) for t in hm]
+    in_bytes = hx[0].numel() * 4 + hm[0].numel() * 4
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    # ---- launches per forward (eager, counted by the Runner) and per-kernel timing of the dominant kernel
+    model.use_cuda_graph = False
+    model(dx[0], dm[0], length)
+    torch.cuda.synchronize(dev)
+    r = model._program.runner
+    r.launches = 0
+    r.timing = []
+    for i in range(3):
+        model(dx[i % NBUF], dm[i % NBUF], length)
+    torch.cuda.synchronize(dev)
+    launches_per_forward = r.launches // 3
+    ig_ms = sum(a.elapsed_time(b) for a, b, _, _ in r.timing) / 3
+    ig_flops = sum(f for _, _, f, _ in r.timing) / 3
+    ig_launches = len(r.timing) // 3
+    r.timing = None
+    model.use_cuda_graph = True
+
+    # ---- resident-input throughput
+    for i in range(args.warmup):
+        out = model(dx[i % NBUF], dm[i % NBUF], length)
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for i in range(args.steps):
+        out = model(dx[i % NBUF], dm[i % NBUF], length)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    # ---- end-to-end: pinned host inputs -> module call -> host read of the heatmaps, every step
+    host_out = torch.empty(out.shape, dtype=out.dtype).pin_memory()
+    for i in range(2):
+        host_out.copy_(model(hx[i % NBUF], hm[i % NBUF], length))
+    barrier()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record()
+    for i in range(args.steps):
+        host_out.copy_(model(hx[i % NBUF], hm[i % NBUF], length), non_blocking=False)
+    f1.record()
+    barrier()
+    ms_e2e = f0.elapsed_time(f1)
+    clocks = sampler.finish() if rank == 0 else None
+
+    t = torch.tensor([ms, ms_e2e], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, ms_e2e = float(t[0]), float(t[1])
+
+    if rank == 0:
+        peaks, peak_kind = _peaks()
+        total = crops * world * args.steps
+        value = total / (ms * 1e-3)
+        e2e_value = total / (ms_e2e * 1e-3)
+        peak = float(peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"]))
+        achieved = ig_flops / (ig_ms * 1e-3) / 1e12 if ig_ms > 0 else 0.0
+        line = {
+            "metric": "person-crops/sec", "value": value, "unit": "crops/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f16", "data": "synthetic",
+            "config": {"workload": "C2: vanilla I2R-Net (interformer_pureMulti) HRNet-W48-S 256x192, "
+                                   "8 images x 4 persons = 32 crops per GPU per step, whole images per rank "
+                                   "(no data-path collective)",
+                       "l2": "inputs rotate over %d distinct batches (%.0f MB > 126 MB L2)" % (
+                           NBUF, NBUF * in_bytes / 1e6),
+                       "precision": "fp16 operands, fp32 accumulate (tcgen05 kind::f16), single pass",
+                       "cuda_graph": True},
+            "e2e": {"value": e2e_value, "unit": "crops/s", "h2d_bytes_per_step": in_bytes,
+                    "d2h_bytes_per_step": out.numel() * 4},
+            "gpu_launches": launches_per_forward * args.steps,
+            "model_tflops": value * GFLOP_PER_CROP["C2"] / 1e3,
+            "model_frac_of_peak": value * GFLOP_PER_CROP["C2"] / 1e3 / (peak * world),
+            "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+                         "frac": achieved / peak, "traffic": None,
+                         "kernel": "igemm_tc_kernel (%d launches/forward, CUDA events around every launch of an "
+                                   "eager forward; algorithmic 2*M*Cout*Cin*taps)" % ig_launches,
+                         "peak_kind": "bf16_tflops_sustained, %s" % peak_kind},
+            "clocks": clocks,
+        }
+        if not args.no_cpu_baseline and world == 1:
+            base, _ = cpu_forward_timer(3, 1)
+            line["cpu_baseline"] = base
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

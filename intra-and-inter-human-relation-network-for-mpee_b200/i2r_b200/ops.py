@@ -41,6 +41,7 @@ class Runner:
         capi.check(self.lib.i2r_device_check(self.device.index or 0), "i2r_device_check")
         self.impl = impl
         self.launches = 0
+        self.timing = None     # bench.py: list of (start_event, end_event, algorithmic_flops, nprob) per igemm launch
 
     # ------------------------------------------------------------------ implicit GEMM
     def problem(self, L, x, out=None, add0=None, add0_shift=0, add1=None, add1_shift=0, in_shift=0,
@@ -105,7 +106,14 @@ class Runner:
     def launch(self, problems):
         n = len(problems)
         arr = (capi.ConvProblem * n)(*problems)
+        if self.timing is not None:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
         capi.check(self.lib.i2r_conv_igemm(arr, n, self.impl, _stream_ptr()), "i2r_conv_igemm")
+        if self.timing is not None:
+            e1.record()
+            flops = sum(2.0 * p.NB * p.OH * p.OW * p.Cout * p.Cin * p.ntaps for p in problems)
+            self.timing.append((e0, e1, flops, n))
         self.launches += 1
 
     def conv(self, L, x, **kw):

@@ -107,6 +107,7 @@ class TransPoseH(nn.Module):
         self._graphs = GraphedForward(self._eager)
         self.use_cuda_graph = os.environ.get("I2R_CUDA_GRAPH", "1") != "0"
         self.check_impl = False   # tests: route implicit GEMMs through the scalar check kernel
+        self._runner_factory = Runner
 
     # ------------------------------------------------------------------ weights -> device program
     def prepare(self, device=None):
@@ -120,7 +121,7 @@ class TransPoseH(nn.Module):
             raise NotImplementedError("FINAL_CONV_KERNEL=3")
         prog = type("Program", (), {})()
         prog.device = device
-        prog.runner = Runner(device, impl=1 if self.check_impl else 0)
+        prog.runner = self._runner_factory(device, 1 if self.check_impl else 0)
         prog.backbone = BackboneProgram(self, sd, device)
         prog.reduce = conv_bn_layer(sd, "reduce", None, device=device)
         prog.mask_embed = MaskEmbedProgram(sd, "position_embedding", device) if self.use_multi_pos else None

@@ -1,0 +1,92 @@
+"""GPU parity of the whole drop-in forward (through get_pose_net / forward, i.e. through the C ABI):
+against the committed golden outputs of the real reference (small cases) and against the pinned
+oracle on the BASELINE batch (32 crops).  Tolerance: 1e-3 max-abs on fp32 heatmaps (north_star)."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import paths
+from helpers import build_model, inputs_for, load_golden
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-3
+REPORT = os.path.join(paths.REPO, "gpurun_out", "model_report.jsonl")
+
+
+def _report(**kw):
+    os.makedirs(os.path.dirname(REPORT), exist_ok=True)
+    with open(REPORT, "a") as f:
+        f.write(json.dumps(kw) + "\n")
+
+
+@pytest.fixture(scope="module")
+def vanilla_cuda():
+    cfg, model, sd = build_model()
+    return cfg, model.cuda(), sd
+
+
+@pytest.mark.parametrize("impl", ["check", "tcgen05"])
+@pytest.mark.parametrize("case", ["vanilla_c1", "vanilla_ragged"])
+def test_vanilla_matches_reference_golden(vanilla_cuda, case, impl):
+    cfg, model, _ = vanilla_cuda
+    g = load_golden(case)
+    length = [int(v) for v in g["length"]]
+    x, pm = inputs_for(length)
+    model.check_impl = impl == "check"
+    model.use_cuda_graph = False
+    model.prepare("cuda:0")
+    out = model(x, pm, length)
+    torch.cuda.synchronize()
+    assert out.dtype == torch.float32 and tuple(out.shape) == g["out"].shape and out.is_cuda
+    err = float(np.abs(out.cpu().numpy() - g["out"]).max())
+    _report(test="vanilla_golden", case=case, impl=impl, max_abs_err=err, out_max=float(np.abs(g["out"]).max()))
+    assert np.isfinite(err) and err <= TOL, err
+
+
+def test_vanilla_graph_replay_equals_eager(vanilla_cuda):
+    cfg, model, _ = vanilla_cuda
+    length = [2, 1]
+    x, pm = inputs_for(length)
+    model.check_impl = False
+    model.prepare("cuda:0")
+    model.use_cuda_graph = False
+    eager = model(x, pm, length).clone()
+    model.use_cuda_graph = True
+    g1 = model(x, pm, length).clone()
+    g2 = model(x, pm, length).clone()     # second call = pure replay
+    torch.cuda.synchronize()
+    assert torch.equal(g1, g2)
+    assert torch.equal(eager, g1)
+
+
+def test_vanilla_c2_batch32_matches_oracle(vanilla_cuda):
+    """BASELINE config C2: 8 images x 4 persons; the oracle (pinned on the golden cases) is the checker."""
+    from oracle import i2r_oracle
+    cfg, model, sd = vanilla_cuda
+    length = [4] * 8
+    x, pm = inputs_for(length)
+    model.check_impl = False
+    model.use_cuda_graph = True
+    model.prepare("cuda:0")
+    out = model(x, pm, length)
+    torch.cuda.synchronize()
+    torch.set_num_threads(os.cpu_count())
+    with torch.no_grad():
+        ref = i2r_oracle.vanilla_forward(sd, cfg, x, pm, length)
+    err = float((out.cpu() - ref).abs().max())
+    _report(test="vanilla_c2", max_abs_err=err, out_max=float(ref.abs().max()))
+    assert err <= TOL, err
+
+
+def test_forward_rejects_bad_length_and_cpu(vanilla_cuda):
+    from i2r_b200 import capi
+    cfg, model, _ = vanilla_cuda
+    x, pm = inputs_for([1])
+    with pytest.raises(ValueError):
+        model(x, pm, [2])
+    cpu_cfg, cpu_model, _ = build_model()
+    with pytest.raises(capi.I2RError):
+        cpu_model(x, pm, [1])
