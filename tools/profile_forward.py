@@ -1,0 +1,27 @@
+"""Run eager forwards of the C2 batch for ncu: warm-up outside the profiled range, then
+cudaProfilerStart .. one forward .. cudaProfilerStop (use `ncu --profile-from-start off`)."""
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import paths  # noqa: E402,F401
+
+sys.path.insert(0, os.path.join(paths.REPO, "tests"))
+from helpers import build_model, inputs_for  # noqa: E402
+
+images = int(sys.argv[1]) if len(sys.argv) > 1 else 8
+cfg, model, sd = build_model()
+model = model.cuda()
+model.use_cuda_graph = False
+length = [4] * images
+x, pm = inputs_for(length)
+x, pm = x.cuda(), pm.cuda()
+for _ in range(2):
+    model(x, pm, length)
+torch.cuda.synchronize()
+torch.cuda.profiler.start()
+model(x, pm, length)
+torch.cuda.synchronize()
+torch.cuda.profiler.stop()
