@@ -32,7 +32,7 @@ extern "C" {
 #define I2R_E_DEVICE (-3)
 
 #define I2R_MAX_TAPS 9
-#define I2R_MAX_GROUP 4
+#define I2R_MAX_GROUP 6
 
 /* i2r_conv_problem::flags */
 #define I2R_F_RELU 1u        /* clamp at 0 after scale/bias/addends                         */
@@ -67,6 +67,7 @@ typedef struct i2r_conv_problem {
   int32_t OHf, OWf;        /* full output extent; output pixel = (oy*out_mul+out_offy, ox*out_mul+out_offx) */
   int32_t out_mul, out_offy, out_offx;
   int32_t add0_shift, add1_shift;
+  int32_t add_pix_stride;  /* elements between consecutive addend pixels (>= Cout; = Cout when dense)      */
   int32_t ntaps;
   int8_t dy[I2R_MAX_TAPS + 3];
   int8_t dx[I2R_MAX_TAPS + 3];
@@ -83,6 +84,15 @@ int i2r_sm_count(int dev);
  * tcgen05 path.  impl: 0 = tcgen05/TMEM kernel (product path), 1 = scalar SIMT check kernel
  * (tests only; same problem struct, same packed weights). */
 int i2r_conv_igemm(const i2r_conv_problem* probs, int nprob, int impl, void* stream);
+
+/* Persistent TMA-fed variant for the problems that dominate the FLOPs: stride-1 3x3 (BasicBlock /
+ * Bottleneck convs, interformer_pureMulti.py:37-107) and 1x1 / nn.Linear problems with no resampling
+ * (in_shift 0, out_mul 1, addend shifts 0).  Activation halo tiles arrive by TMA (one 5-D box per
+ * tile and K-chunk), weights stay resident in shared memory when they fit, two TMEM accumulators
+ * overlap the epilogue with the next tile.  i2r_conv_tma_supported() returns 1 when a problem
+ * qualifies; others go through i2r_conv_igemm. */
+int i2r_conv_tma_supported(const i2r_conv_problem* prob);
+int i2r_conv_tma(const i2r_conv_problem* probs, int nprob, void* stream);
 
 /* Stem / mask convolution on fp32 NCHW input with tiny Cin (3 or 1): 3x3 stride 2 pad 1 + folded
  * BN + ReLU -> fp16 NHWC [NB, H/2, W/2, Cout].  Replaces conv1/bn1/relu

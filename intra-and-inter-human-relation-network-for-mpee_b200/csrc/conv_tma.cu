@@ -1,0 +1,576 @@
+// Persistent, warp-specialised convolution kernel for stride-1 3x3 and 1x1 problems (sm_100a):
+// TMA-staged activation tiles -> tcgen05.mma with TMEM accumulators -> fused epilogue.
+//
+//   tile        : 8 (x) by 16 (y) output pixels = 128 accumulator rows, all Npad output channels
+//   A operand   : ONE 5-D TMA box per (tile, K-chunk) brings the (8+2) x (16+2) halo tile of KCH channels
+//                 into shared memory as [k-group of 8 ch][halo y][halo x][8 x fp16]; out-of-image
+//                 pixels are zero-filled by the TMA unit (this is the conv padding).  The nine taps
+//                 of a 3x3 filter are nine shifted windows of that single tile: the UMMA descriptor's
+//                 start address moves by ((dy*10+dx)*16 B), SBO = one halo row (160 B), LBO = one
+//                 k-group plane -- every activation byte is fetched once instead of nine times.
+//   B operand   : weights pre-packed in core-matrix order; resident in shared memory for the whole
+//                 kernel when they fit (<= 120 KB), else streamed per (K-chunk, tap) through a ring.
+//   D           : two TMEM accumulators (2 x Npad columns) so the epilogue of tile i overlaps the
+//                 MMAs of tile i+1.
+//   warps       : 0 = activation TMA producer, 1 = weight producer, 2 = MMA issuer, 3 = TMEM owner,
+//                 4..7 = epilogue (TMEM -> registers -> scale/bias/residual/ReLU -> global).
+//   grid        : persistent; each problem of a grouped launch owns a contiguous CTA range sized
+//                 by its share of the MMA work, CTAs stride over that problem's tiles.
+#include <cuda.h>
+
+#include <cstdio>
+#include <cstring>
+
+#include "i2r_common.cuh"
+
+namespace i2r {
+
+struct TmaProblem {
+  const uint8_t* w;
+  const float* scale;
+  const float* bias;
+  const __half* add0;
+  const __half* add1;
+  void* y;
+  int NB, H, W, C, Cout, Npad;
+  int ntaps, halo;
+  int KCH, nkc;        // channels per A stage, A stages per tile
+  int kgp, nchp;       // packed-weight geometry: k-groups per packed chunk, packed chunks per tap
+  int tiles_x, tiles_per_img, ntiles;
+  int out_pix_stride, add_pix_stride;
+  int plane;           // real OH*OW of the output (NCHW addressing)
+  uint32_t flags;
+  int cta_begin, cta_count;
+  int w_resident;
+  uint32_t w_total_bytes, w_stage_bytes;
+  int rank5;
+  uint32_t a_stage_bytes, a_tx_bytes;
+  int a_stages, w_stages;
+  uint32_t w_off;      // byte offset of the weight region in dynamic smem
+};
+
+struct TmaGroup {
+  CUtensorMap amap[I2R_MAX_GROUP];
+  TmaProblem p[I2R_MAX_GROUP];
+  int nprob;
+};
+
+constexpr int T_THREADS = 256;
+constexpr int T_TW = 8, T_TH = 16;
+constexpr uint32_t T_A_OFF = 3072;          // dynamic smem: [0,256) barriers | [256,2304) scale,bias | A ring
+constexpr uint32_t T_MAX_SMEM = 225 * 1024;
+constexpr uint32_t T_W_RES_MAX = 120 * 1024;
+
+__device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, int c3,
+                                            int c4, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2,%3,%4,%5,%6}], [%7];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4), "r"(bar)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, int c3,
+                                            uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2,%3,%4,%5}], [%6];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(bar)
+      : "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
+}
+
+__global__ void __launch_bounds__(T_THREADS, 1) conv_tma_kernel(const __grid_constant__ TmaGroup G) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  int pi = 0;
+  while (pi < G.nprob - 1 && static_cast<int>(blockIdx.x) >= G.p[pi].cta_begin + G.p[pi].cta_count) ++pi;
+  const TmaProblem& P = G.p[pi];
+  const CUtensorMap* amap = &G.amap[pi];
+  const int cta = blockIdx.x - P.cta_begin;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  const uint32_t sbase = smem_u32(smem);
+  const uint32_t bar_afull = sbase, bar_aempty = sbase + 32, bar_wfull = sbase + 64, bar_wempty = sbase + 96;
+  const uint32_t bar_accfull = sbase + 128, bar_accempty = sbase + 144, bar_wres = sbase + 160;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + 176);
+  float* s_scale = reinterpret_cast<float*>(smem + 256);
+  float* s_bias = reinterpret_cast<float*>(smem + 256 + 1024);
+  const uint32_t a_base = sbase + T_A_OFF;
+  const uint32_t w_base = sbase + P.w_off;
+
+  const int Npad = P.Npad;
+  uint32_t ncols = 32;
+  while (ncols < static_cast<uint32_t>(2 * Npad)) ncols <<= 1;
+
+  if (tid == 0) {
+    for (int i = 0; i < 4; ++i) {
+      mbar_init(bar_afull + 8 * i, 1);
+      mbar_init(bar_aempty + 8 * i, 1);
+      mbar_init(bar_wfull + 8 * i, 1);
+      mbar_init(bar_wempty + 8 * i, 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(bar_accfull + 8 * i, 1);
+      mbar_init(bar_accempty + 8 * i, 4);
+    }
+    mbar_init(bar_wres, 1);
+    fence_mbar_init();
+    prefetch_tmap(amap);
+  }
+  if (warp == 3) {
+    tmem_alloc(smem_u32(tmem_slot), ncols);
+    tmem_relinquish();
+  }
+  for (int i = tid; i < Npad; i += T_THREADS) {
+    s_scale[i] = P.scale[i];
+    s_bias[i] = P.bias[i];
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int hw = T_TW + 2 * P.halo, hh = T_TH + 2 * P.halo;
+  const int kg_per_stage = P.KCH >> 3;
+
+  if (warp == 0 && lane == 0) {
+    // ================================================= activation producer (TMA)
+    int s = 0;
+    uint32_t ph = 0;
+    const uint32_t grp_bytes = static_cast<uint32_t>(hh * hw * 16);
+    for (int t = cta; t < P.ntiles; t += P.cta_count) {
+      const int n = t / P.tiles_per_img;
+      const int r = t - n * P.tiles_per_img;
+      const int ty = r / P.tiles_x, tx = r - ty * P.tiles_x;
+      const int x0 = tx * T_TW - P.halo, y0 = ty * T_TH - P.halo;
+      for (int kc = 0; kc < P.nkc; ++kc) {
+        mbar_wait(bar_aempty + 8 * s, ph ^ 1);
+        mbar_arrive_expect_tx(bar_afull + 8 * s, P.a_tx_bytes);
+        const uint32_t dst = a_base + s * P.a_stage_bytes;
+        if (P.rank5) {
+          tma_load_5d(dst, amap, 0, x0, y0, kc * kg_per_stage, n, bar_afull + 8 * s);
+        } else {
+          for (int g = 0; g < kg_per_stage; ++g)
+            tma_load_4d(dst + g * grp_bytes, amap, (kc * kg_per_stage + g) * 8, x0, y0, n, bar_afull + 8 * s);
+        }
+        if (++s == P.a_stages) {
+          s = 0;
+          ph ^= 1;
+        }
+      }
+    }
+  } else if (warp == 1 && lane == 0) {
+    // ================================================= weight producer (bulk copies)
+    if (P.w_resident) {
+      mbar_arrive_expect_tx(bar_wres, P.w_total_bytes);
+      for (uint32_t off = 0; off < P.w_total_bytes; off += 16384) {
+        const uint32_t sz = min(16384u, P.w_total_bytes - off);
+        bulk_g2s(w_base + off, P.w + off, sz, bar_wres);
+      }
+    } else {
+      int s = 0;
+      uint32_t ph = 0;
+      for (int t = cta; t < P.ntiles; t += P.cta_count) {
+        for (int kc = 0; kc < P.nkc; ++kc) {
+          for (int tap = 0; tap < P.ntaps; ++tap) {
+            mbar_wait(bar_wempty + 8 * s, ph ^ 1);
+            mbar_arrive_expect_tx(bar_wfull + 8 * s, P.w_stage_bytes);
+            bulk_g2s(w_base + s * P.w_stage_bytes,
+                     P.w + static_cast<size_t>(tap * P.nchp + kc) * P.w_stage_bytes, P.w_stage_bytes,
+                     bar_wfull + 8 * s);
+            if (++s == P.w_stages) {
+              s = 0;
+              ph ^= 1;
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 2 && lane == 0) {
+    // ================================================= MMA issuer
+    const uint32_t idesc = make_idesc_f16(128, Npad);
+    const uint32_t a_lbo = static_cast<uint32_t>(hh * hw * 16), a_sbo = static_cast<uint32_t>(hw * 16);
+    const uint32_t b_lbo = static_cast<uint32_t>(Npad) * 16;
+    int as = 0, ws = 0, acc = 0;
+    uint32_t aph = 0, wph = 0, accph = 0;
+    if (P.w_resident) mbar_wait(bar_wres, 0);
+    for (int t = cta; t < P.ntiles; t += P.cta_count) {
+      mbar_wait(bar_accempty + 8 * acc, accph ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc) * (ncols >> 1);
+      uint32_t accum = 0;
+      for (int kc = 0; kc < P.nkc; ++kc) {
+        mbar_wait(bar_afull + 8 * as, aph);
+        tc_fence_after();
+        const uint32_t a_s = a_base + as * P.a_stage_bytes;
+        for (int tap = 0; tap < P.ntaps; ++tap) {
+          uint32_t wb;
+          if (P.w_resident) {
+            wb = w_base;
+          } else {
+            mbar_wait(bar_wfull + 8 * ws, wph);
+            tc_fence_after();
+            wb = w_base + ws * P.w_stage_bytes;
+          }
+          uint32_t tap_off = 0;
+          if (P.ntaps == 9) tap_off = static_cast<uint32_t>(((tap / 3) * hw + (tap % 3)) * 16);
+          for (int k2 = 0; k2 < (kg_per_stage >> 1); ++k2) {
+            const uint64_t ad = make_smem_desc(a_s + 2 * k2 * a_lbo + tap_off, a_lbo, a_sbo);
+            uint32_t boff;
+            if (P.w_resident) {
+              const int gk = kc * kg_per_stage + 2 * k2;
+              const int chunk = gk / P.kgp, g = gk - chunk * P.kgp;
+              boff = static_cast<uint32_t>(((tap * P.nchp + chunk) * P.kgp + g)) * b_lbo;
+            } else {
+              boff = 2 * k2 * b_lbo;
+            }
+            const uint64_t bd = make_smem_desc(wb + boff, b_lbo, 128);
+            umma_f16(d_tmem, ad, bd, idesc, accum);
+            accum = 1;
+          }
+          if (!P.w_resident) {
+            umma_commit(bar_wempty + 8 * ws);
+            if (++ws == P.w_stages) {
+              ws = 0;
+              wph ^= 1;
+            }
+          }
+        }
+        umma_commit(bar_aempty + 8 * as);
+        if (++as == P.a_stages) {
+          as = 0;
+          aph ^= 1;
+        }
+      }
+      umma_commit(bar_accfull + 8 * acc);
+      acc ^= 1;
+      if (acc == 0) accph ^= 1;
+    }
+  } else if (warp >= 4) {
+    // ================================================= epilogue
+    const int ew = warp - 4;
+    const int row = ew * 32 + lane;
+    const int ty_in = row >> 3, tx_in = row & 7;
+    const int Cout = P.Cout;
+    const bool relu = (P.flags & I2R_F_RELU) != 0;
+    int acc = 0;
+    uint32_t accph = 0;
+    for (int t = cta; t < P.ntiles; t += P.cta_count) {
+      const int n = t / P.tiles_per_img;
+      const int r = t - n * P.tiles_per_img;
+      const int ty = r / P.tiles_x, tx = r - ty * P.tiles_x;
+      const int x = tx * T_TW + tx_in, y = ty * T_TH + ty_in;
+      const bool valid = (x < P.W) && (y < P.H);
+      const int64_t p = (static_cast<int64_t>(n) * P.H + y) * P.W + x;
+      mbar_wait(bar_accfull + 8 * acc, accph);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + static_cast<uint32_t>(acc) * (ncols >> 1);
+      const __half* a0 = P.add0 ? P.add0 + p * P.add_pix_stride : nullptr;
+      const __half* a1 = P.add1 ? P.add1 + p * P.add_pix_stride : nullptr;
+      for (int c0 = 0; c0 < Npad; c0 += 16) {
+        uint32_t rg[16];
+        tmem_ld16(taddr + c0, rg);
+        tmem_ld_wait();
+        if (!valid) continue;
+        float v[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(rg[i]) * s_scale[c0 + i] + s_bias[c0 + i];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          if (c0 + h * 8 < Cout) {
+            if (a0 != nullptr) {
+              const uint4 q = *reinterpret_cast<const uint4*>(a0 + c0 + h * 8);
+              const uint32_t w4[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const float2 f = unpack_h2(w4[i]);
+                v[h * 8 + 2 * i] += f.x;
+                v[h * 8 + 2 * i + 1] += f.y;
+              }
+            }
+            if (a1 != nullptr) {
+              const uint4 q = *reinterpret_cast<const uint4*>(a1 + c0 + h * 8);
+              const uint32_t w4[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const float2 f = unpack_h2(w4[i]);
+                v[h * 8 + 2 * i] += f.x;
+                v[h * 8 + 2 * i + 1] += f.y;
+              }
+            }
+          }
+        }
+        if (relu) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.0f);
+        }
+        if (P.flags & I2R_F_OUT_NCHW_F32) {
+          float* Y = reinterpret_cast<float*>(P.y);
+          const int64_t nr = p / P.plane, rem = p - nr * P.plane;
+          const int64_t base = nr * Cout * P.plane + rem;
+#pragma unroll
+          for (int i = 0; i < 16; ++i)
+            if (c0 + i < Cout) Y[base + static_cast<int64_t>(c0 + i) * P.plane] = v[i];
+        } else if (P.flags & I2R_F_OUT_F32) {
+          float* Y = reinterpret_cast<float*>(P.y) + p * P.out_pix_stride + c0;
+#pragma unroll
+          for (int i = 0; i < 16; ++i)
+            if (c0 + i < Cout) Y[i] = v[i];
+        } else {
+          __half* Y = reinterpret_cast<__half*>(P.y) + p * P.out_pix_stride + c0;
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            if (c0 + h * 8 < Cout) {
+              uint4 q;
+              q.x = pack_h2(v[h * 8 + 0], v[h * 8 + 1]);
+              q.y = pack_h2(v[h * 8 + 2], v[h * 8 + 3]);
+              q.z = pack_h2(v[h * 8 + 4], v[h * 8 + 5]);
+              q.w = pack_h2(v[h * 8 + 6], v[h * 8 + 7]);
+              *reinterpret_cast<uint4*>(Y + h * 8) = q;
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_accempty + 8 * acc);
+      acc ^= 1;
+      if (acc == 0) accph ^= 1;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 3) tmem_dealloc(tmem_base, ncols);
+}
+
+// ------------------------------------------------------------------------------------------------ host
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+static int g_force_rank4 = 0;  // test hook (I2R_TMA_RANK4=1): exercise the 4-D fallback path
+
+static int encode_amap(CUtensorMap* map, const void* x, int NB, int H, int W, int C, int pix_stride, int hw, int hh,
+                       int kch, int* rank5) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) {
+    set_error("cuTensorMapEncodeTiled entry point unavailable");
+    return I2R_E_DEVICE;
+  }
+  const cuuint64_t pb = static_cast<cuuint64_t>(pix_stride) * 2;
+  const cuuint32_t ones[5] = {1, 1, 1, 1, 1};
+  if (!g_force_rank4) {
+    const cuuint64_t dims[5] = {8, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)(C / 8), (cuuint64_t)NB};
+    const cuuint64_t strides[4] = {pb, pb * W, 16, pb * W * H};
+    const cuuint32_t box[5] = {8, (cuuint32_t)hw, (cuuint32_t)hh, (cuuint32_t)(kch / 8), 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 5, const_cast<void*>(x), dims, strides, box, ones,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r == CUDA_SUCCESS) {
+      *rank5 = 1;
+      return 0;
+    }
+  }
+  const cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)NB};
+  const cuuint64_t strides[3] = {pb, pb * W, pb * W * H};
+  const cuuint32_t box[4] = {8, (cuuint32_t)hw, (cuuint32_t)hh, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(x), dims, strides, box, ones,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed (%d) for [%d,%d,%d,%d] pix_stride %d", (int)r, NB, H, W, C, pix_stride);
+    return I2R_E_DEVICE;
+  }
+  *rank5 = 0;
+  return 0;
+}
+
+static bool is_std3x3(const i2r_conv_problem& P) {
+  if (P.ntaps != 9) return false;
+  for (int t = 0; t < 9; ++t)
+    if (P.dy[t] != t / 3 - 1 || P.dx[t] != t % 3 - 1) return false;
+  return true;
+}
+
+}  // namespace i2r
+
+extern "C" int i2r_conv_tma_supported(const i2r_conv_problem* P) {
+  using namespace i2r;
+  if (!P) return 0;
+  const bool k1 = P->ntaps == 1 && P->dy[0] == 0 && P->dx[0] == 0;
+  if (!(k1 || is_std3x3(*P))) return 0;
+  if (P->stride != 1 || P->in_shift != 0 || P->out_mul != 1 || P->out_offy != 0 || P->out_offx != 0) return 0;
+  if (P->OH != P->IH || P->OW != P->IW || P->OHf != P->OH || P->OWf != P->OW) return 0;
+  if ((P->add0 && P->add0_shift != 0) || (P->add1 && P->add1_shift != 0)) return 0;
+  if (P->Cin % 16 != 0 || P->Npad > 256 || P->Npad % 16 != 0) return 0;
+  const int kch = P->Cin <= 96 ? P->Cin : P->KC;
+  if (P->Cin % kch != 0) return 0;
+  const uint32_t wtot = static_cast<uint32_t>(P->ntaps) * (P->Cin / 8) * P->Npad * 16;
+  if (wtot > T_W_RES_MAX && kch != P->KC) return 0;
+  if (P->in_pix_stride % 8 != 0) return 0;
+  if ((P->add0 || P->add1) && (P->add_pix_stride % 8 != 0 || P->add_pix_stride < P->Cout)) return 0;
+  return 1;
+}
+
+extern "C" int i2r_conv_tma(const i2r_conv_problem* probs, int nprob, void* stream) {
+  using namespace i2r;
+  if (!probs || nprob < 1 || nprob > I2R_MAX_GROUP) {
+    set_error("i2r_conv_tma: nprob=%d out of range", nprob);
+    return I2R_E_BADARG;
+  }
+  static int num_sms = 0;
+  if (num_sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+    const char* e = getenv("I2R_TMA_RANK4");
+    g_force_rank4 = (e && e[0] == '1') ? 1 : 0;
+  }
+  TmaGroup G;
+  memset(&G, 0, sizeof(G));
+  G.nprob = nprob;
+  double cost[I2R_MAX_GROUP];
+  double total_cost = 0;
+  int total_tiles = 0;
+  uint32_t smem_need = 0;
+  for (int i = 0; i < nprob; ++i) {
+    const i2r_conv_problem& S = probs[i];
+    if (!i2r_conv_tma_supported(&S)) {
+      set_error("i2r_conv_tma: problem %d is not a stride-1 3x3 / 1x1 problem this kernel supports", i);
+      return I2R_E_UNSUPPORTED;
+    }
+    if (!S.x || !S.w || !S.scale || !S.bias || !S.y) {
+      set_error("i2r_conv_tma: problem %d: null pointer", i);
+      return I2R_E_BADARG;
+    }
+    TmaProblem& P = G.p[i];
+    P.w = static_cast<const uint8_t*>(S.w);
+    P.scale = S.scale;
+    P.bias = S.bias;
+    P.add0 = static_cast<const __half*>(S.add0);
+    P.add1 = static_cast<const __half*>(S.add1);
+    P.y = S.y;
+    P.ntaps = S.ntaps;
+    P.halo = S.ntaps == 9 ? 1 : 0;
+    P.NB = S.NB;
+    P.H = S.IH;
+    P.W = S.IW;
+    const int64_t mtot = static_cast<int64_t>(S.NB) * S.IH * S.IW;
+    P.plane = S.OHf * S.OWf;
+    if (S.ntaps == 1 && mtot % 8 == 0) {  // pixels are independent: re-tile as an 8-wide strip
+      P.NB = 1;
+      P.W = 8;
+      P.H = static_cast<int>(mtot / 8);
+    }
+    P.C = S.Cin;
+    P.Cout = S.Cout;
+    P.Npad = S.Npad;
+    P.KCH = S.Cin <= 96 ? S.Cin : S.KC;
+    P.nkc = S.Cin / P.KCH;
+    P.kgp = S.KC / 8;
+    P.nchp = S.Cin / S.KC;
+    P.tiles_x = (P.W + T_TW - 1) / T_TW;
+    P.tiles_per_img = P.tiles_x * ((P.H + T_TH - 1) / T_TH);
+    P.ntiles = P.tiles_per_img * P.NB;
+    P.out_pix_stride = S.out_pix_stride;
+    P.add_pix_stride = S.add_pix_stride;
+    P.flags = S.flags;
+    const int hw = T_TW + 2 * P.halo, hh = T_TH + 2 * P.halo;
+    P.a_tx_bytes = static_cast<uint32_t>((P.KCH / 8) * hh * hw * 16);
+    P.a_stage_bytes = (P.a_tx_bytes + 127u) & ~127u;
+    P.w_total_bytes = static_cast<uint32_t>(S.ntaps) * (S.Cin / 8) * S.Npad * 16;
+    P.w_resident = P.w_total_bytes <= T_W_RES_MAX ? 1 : 0;
+    P.w_stage_bytes = static_cast<uint32_t>(P.kgp) * S.Npad * 16;
+    uint32_t wregion;
+    if (P.w_resident) {
+      P.w_stages = 1;
+      wregion = P.w_total_bytes;
+    } else {
+      P.w_stages = 4;
+      while (P.w_stages > 2 && P.w_stages * P.w_stage_bytes > 110 * 1024) --P.w_stages;
+      wregion = P.w_stages * P.w_stage_bytes;
+    }
+    int astg = static_cast<int>((T_MAX_SMEM - T_A_OFF - wregion) / P.a_stage_bytes);
+    if (astg > 4) astg = 4;
+    if (astg < 2) {
+      set_error("i2r_conv_tma: problem %d does not fit shared memory (A stage %u B, W region %u B)", i,
+                P.a_stage_bytes, wregion);
+      return I2R_E_UNSUPPORTED;
+    }
+    P.a_stages = astg;
+    P.w_off = T_A_OFF + static_cast<uint32_t>(astg) * P.a_stage_bytes;
+    const uint32_t need = P.w_off + wregion;
+    if (need > smem_need) smem_need = need;
+    int rc = encode_amap(&G.amap[i], S.x, P.NB, P.H, P.W, P.C, S.in_pix_stride, hw, hh, P.KCH, &P.rank5);
+    if (rc) return rc;
+    cost[i] = static_cast<double>(P.ntiles) * S.ntaps * S.Cin * (S.Npad < 64 ? 64 : S.Npad);
+    total_cost += cost[i];
+    total_tiles += P.ntiles;
+  }
+  // CTA ranges: one CTA per tile while they fit, else split the SMs by MMA work.
+  int begin = 0;
+  if (total_tiles <= num_sms) {
+    for (int i = 0; i < nprob; ++i) {
+      G.p[i].cta_begin = begin;
+      G.p[i].cta_count = G.p[i].ntiles;
+      begin += G.p[i].ntiles;
+    }
+  } else {
+    int left = num_sms;
+    int cnt[I2R_MAX_GROUP];
+    for (int i = 0; i < nprob; ++i) {
+      int c = static_cast<int>(cost[i] / total_cost * num_sms);
+      if (c < 1) c = 1;
+      if (c > G.p[i].ntiles) c = G.p[i].ntiles;
+      cnt[i] = c;
+      left -= c;
+    }
+    // hand out the remainder (or take back an overdraft) on the problems with the most tiles per CTA
+    while (left != 0) {
+      int best = -1;
+      double bestv = -1;
+      for (int i = 0; i < nprob; ++i) {
+        if (left > 0 && cnt[i] >= G.p[i].ntiles) continue;
+        if (left < 0 && cnt[i] <= 1) continue;
+        const double v = left > 0 ? cost[i] / cnt[i] : -cost[i] / cnt[i];
+        if (best < 0 || v > bestv) {
+          best = i;
+          bestv = v;
+        }
+      }
+      if (best < 0) break;
+      cnt[best] += left > 0 ? 1 : -1;
+      left += left > 0 ? -1 : 1;
+    }
+    for (int i = 0; i < nprob; ++i) {
+      G.p[i].cta_begin = begin;
+      G.p[i].cta_count = cnt[i];
+      begin += cnt[i];
+    }
+  }
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(conv_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, T_MAX_SMEM);
+    if (e != cudaSuccess) {
+      set_error("cudaFuncSetAttribute(conv_tma): %s", cudaGetErrorString(e));
+      return static_cast<int>(e);
+    }
+    attr_done = true;
+  }
+  conv_tma_kernel<<<begin, T_THREADS, smem_need, static_cast<cudaStream_t>(stream)>>>(G);
+  return check_launch("conv_tma_kernel");
+}

@@ -179,12 +179,12 @@ __device__ __forceinline__ void run_tile(const i2r_conv_problem& P, const int ti
     if (P.add0 != nullptr) {
       const int s0 = P.add0_shift;
       const int64_t ap = (static_cast<int64_t>(n) * (P.OHf >> s0) + (oyf >> s0)) * (P.OWf >> s0) + (oxf >> s0);
-      a0 = reinterpret_cast<const __half*>(P.add0) + ap * Cout;
+      a0 = reinterpret_cast<const __half*>(P.add0) + ap * P.add_pix_stride;
     }
     if (P.add1 != nullptr) {
       const int s1 = P.add1_shift;
       const int64_t ap = (static_cast<int64_t>(n) * (P.OHf >> s1) + (oyf >> s1)) * (P.OWf >> s1) + (oxf >> s1);
-      a1 = reinterpret_cast<const __half*>(P.add1) + ap * Cout;
+      a1 = reinterpret_cast<const __half*>(P.add1) + ap * P.add_pix_stride;
     }
     const int64_t opix = (static_cast<int64_t>(n) * P.OHf + oyf) * P.OWf + oxf;
     const bool relu = (P.flags & I2R_F_RELU) != 0;
@@ -345,12 +345,12 @@ __global__ void __launch_bounds__(128) igemm_check_kernel(const __grid_constant_
     if (P.add0) {
       const int s0 = P.add0_shift;
       const int64_t ap = (static_cast<int64_t>(n) * (P.OHf >> s0) + (oyf >> s0)) * (P.OWf >> s0) + (oxf >> s0);
-      v += __half2float(reinterpret_cast<const __half*>(P.add0)[ap * P.Cout + co]);
+      v += __half2float(reinterpret_cast<const __half*>(P.add0)[ap * P.add_pix_stride + co]);
     }
     if (P.add1) {
       const int s1 = P.add1_shift;
       const int64_t ap = (static_cast<int64_t>(n) * (P.OHf >> s1) + (oyf >> s1)) * (P.OWf >> s1) + (oxf >> s1);
-      v += __half2float(reinterpret_cast<const __half*>(P.add1)[ap * P.Cout + co]);
+      v += __half2float(reinterpret_cast<const __half*>(P.add1)[ap * P.add_pix_stride + co]);
     }
     if (P.flags & I2R_F_RELU) v = fmaxf(v, 0.f);
     if (P.flags & I2R_F_OUT_NCHW_F32) {
@@ -391,8 +391,8 @@ static int validate(const i2r_conv_problem& P, int idx) {
     set_error("conv problem %d: fp16 NHWC output needs Cout, out_pix_stride multiples of 8", idx);
     return I2R_E_BADARG;
   }
-  if ((P.add0 || P.add1) && P.Cout % 8 != 0) {
-    set_error("conv problem %d: addends need Cout multiple of 8", idx);
+  if ((P.add0 || P.add1) && (P.Cout % 8 != 0 || P.add_pix_stride % 8 != 0 || P.add_pix_stride < P.Cout)) {
+    set_error("conv problem %d: addends need Cout and add_pix_stride (>= Cout) multiples of 8", idx);
     return I2R_E_BADARG;
   }
   if (P.in_pix_stride % 8 != 0 || P.in_pix_stride < P.Cin) {

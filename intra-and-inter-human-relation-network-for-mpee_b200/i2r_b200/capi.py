@@ -7,13 +7,13 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libi2r_sm100.so")
 
 I2R_MAX_TAPS = 9
-I2R_MAX_GROUP = 4
+I2R_MAX_GROUP = 6
 F_RELU = 1
 F_OUT_NCHW_F32 = 2
 F_OUT_F32 = 4
 
 EXPORTS = [
-    "i2r_version", "i2r_last_error", "i2r_device_check", "i2r_sm_count", "i2r_conv_igemm",
+    "i2r_version", "i2r_last_error", "i2r_device_check", "i2r_sm_count", "i2r_conv_igemm", "i2r_conv_tma", "i2r_conv_tma_supported",
     "i2r_sizeof_conv_problem", "i2r_stem_conv3x3s2", "i2r_maxpool3x3s2", "i2r_attention_varlen", "i2r_layernorm", "i2r_add_f16",
 ]
 
@@ -29,7 +29,7 @@ class ConvProblem(ctypes.Structure):
         ("Cout", ctypes.c_int32), ("Npad", ctypes.c_int32), ("out_pix_stride", ctypes.c_int32),
         ("OHf", ctypes.c_int32), ("OWf", ctypes.c_int32),
         ("out_mul", ctypes.c_int32), ("out_offy", ctypes.c_int32), ("out_offx", ctypes.c_int32),
-        ("add0_shift", ctypes.c_int32), ("add1_shift", ctypes.c_int32),
+        ("add0_shift", ctypes.c_int32), ("add1_shift", ctypes.c_int32), ("add_pix_stride", ctypes.c_int32),
         ("ntaps", ctypes.c_int32),
         ("dy", ctypes.c_int8 * (I2R_MAX_TAPS + 3)), ("dx", ctypes.c_int8 * (I2R_MAX_TAPS + 3)),
         ("flags", ctypes.c_uint32),
@@ -61,6 +61,8 @@ def load():
         lib.i2r_device_check.argtypes = [i32]
         lib.i2r_sm_count.argtypes = [i32]
         lib.i2r_conv_igemm.argtypes = [ctypes.POINTER(ConvProblem), i32, i32, vp]
+        lib.i2r_conv_tma.argtypes = [ctypes.POINTER(ConvProblem), i32, vp]
+        lib.i2r_conv_tma_supported.argtypes = [ctypes.POINTER(ConvProblem)]
         lib.i2r_stem_conv3x3s2.argtypes = [vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp]
         lib.i2r_maxpool3x3s2.argtypes = [vp, vp, i32, i32, i32, i32, vp]
         lib.i2r_attention_varlen.argtypes = [vp, vp, vp, vp, i32, i32, i32, i32, i32, vp, i32, i32, f32, vp]

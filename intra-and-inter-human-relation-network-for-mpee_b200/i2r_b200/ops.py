@@ -24,6 +24,29 @@ class ConvLayer:
         self.w = pack_taps(mats, self.kc).to(device)
         self.scale = pad_vec(scale, self.npad, 1.0).to(device)
         self.bias = pad_vec(bias, self.npad, 0.0).to(device)
+        self._halves = None
+
+    @property
+    def weight_bytes(self):
+        return self.ntaps * self.cin * self.npad * 2
+
+    def halves(self):
+        """Two layers producing output channels [0, Cout/2) and [Cout/2, Cout) (N-split for the TMA kernel:
+        halves the weight footprint per CTA so it can stay resident, doubles the CTA count)."""
+        if self._halves is None:
+            h = self.cout // 2
+            parts = []
+            for c0 in (0, h):
+                sub = ConvLayer.__new__(ConvLayer)
+                sub.__dict__.update(self.__dict__)
+                sub.cout, sub.npad = h, h
+                sub.w = self.w[:, :, :, c0:c0 + h, :].contiguous()
+                sub.scale = self.scale[c0:c0 + h].contiguous()
+                sub.bias = self.bias[c0:c0 + h].contiguous()
+                sub._halves = None
+                parts.append((c0, sub))
+            self._halves = parts
+        return self._halves
 
 
 def _stream_ptr():
@@ -40,6 +63,7 @@ class Runner:
             raise capi.I2RError("the I2R-Net hot path runs on CUDA devices only (got %s)" % device)
         capi.check(self.lib.i2r_device_check(self.device.index or 0), "i2r_device_check")
         self.impl = impl
+        self.use_tma = impl == 0   # route eligible problems to the persistent TMA kernel
         self.launches = 0
         self.timing = None     # bench.py: list of (start_event, end_event, algorithmic_flops, nprob) per igemm launch
 
@@ -85,9 +109,14 @@ class Runner:
         p.x, p.w, p.scale, p.bias = x.data_ptr(), L.w.data_ptr(), L.scale.data_ptr(), L.bias.data_ptr()
         p.add0 = add0.data_ptr() if add0 is not None else None
         p.add1 = add1.data_ptr() if add1 is not None else None
+        add_pix = L.cout
         for a in (add0, add1):
             if a is not None:
-                assert a.dtype == torch.float16 and a.is_contiguous() and a.shape[-1] == L.cout
+                assert a.dtype == torch.float16 and a.dim() == 4 and a.stride(3) == 1 and a.shape[-1] == L.cout
+                assert a.stride(1) == a.shape[2] * a.stride(2)
+                add_pix = a.stride(2)
+        if add0 is not None and add1 is not None:
+            assert add0.stride(2) == add1.stride(2), "both addends must share one pixel stride"
         p.y = out.data_ptr()
         p.NB, p.IH, p.IW, p.Cin, p.KC = nb, ih, iw, L.cin, L.kc
         p.in_pix_stride, p.in_shift = pix, in_shift
@@ -96,6 +125,7 @@ class Runner:
         p.OHf, p.OWf = ohf, owf
         p.out_mul, p.out_offy, p.out_offx = out_mul, out_off[0], out_off[1]
         p.add0_shift, p.add1_shift = add0_shift, add1_shift
+        p.add_pix_stride = add_pix
         p.ntaps = L.ntaps
         for t in range(L.ntaps):
             p.dy[t], p.dx[t] = L.dy[t], L.dx[t]
@@ -103,33 +133,65 @@ class Runner:
         p._keep = (x, L, add0, add1, out)
         return p, out
 
+    TMA_WEIGHT_RESIDENT_MAX = 120 * 1024
+
+    def problems(self, L, x, **kw):
+        """Like problem(), but may split the output channels in two (see ConvLayer.halves).  Returns (list, out)."""
+        std = (L.ntaps == 1 and L.dy[0] == 0 and L.dx[0] == 0) or (
+            L.ntaps == 9 and all(L.dy[t] == t // 3 - 1 and L.dx[t] == t % 3 - 1 for t in range(9)))
+        split = (self.use_tma and std and L.stride == 1 and kw.get("in_shift", 0) == 0 and
+                 kw.get("out_mul", 1) == 1 and kw.get("out_mode", "nhwc16") == "nhwc16" and
+                 kw.get("add0_shift", 0) == 0 and kw.get("add1_shift", 0) == 0 and
+                 L.weight_bytes > self.TMA_WEIGHT_RESIDENT_MAX and L.cout == L.npad and L.cout % 32 == 0)
+        if not split:
+            p, out = self.problem(L, x, **kw)
+            return [p], out
+        out = kw.pop("out", None)
+        if out is None:
+            out = torch.empty((x.shape[0], x.shape[1], x.shape[2], L.cout), dtype=torch.float16, device=x.device)
+        add0, add1 = kw.pop("add0", None), kw.pop("add1", None)
+        probs = []
+        for c0, sub in L.halves():
+            sl = slice(c0, c0 + sub.cout)
+            p, _ = self.problem(sub, x, out=out[..., sl], add0=None if add0 is None else add0[..., sl],
+                                add1=None if add1 is None else add1[..., sl], **kw)
+            probs.append(p)
+        return probs, out
+
     def launch(self, problems):
-        n = len(problems)
-        arr = (capi.ConvProblem * n)(*problems)
         if self.timing is not None:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-        capi.check(self.lib.i2r_conv_igemm(arr, n, self.impl, _stream_ptr()), "i2r_conv_igemm")
+        tma, gen = [], []
+        for p in problems:
+            (tma if (self.use_tma and self.lib.i2r_conv_tma_supported(ctypes.byref(p))) else gen).append(p)
+        for group, fn in ((tma, "tma"), (gen, "igemm")):
+            for i in range(0, len(group), capi.I2R_MAX_GROUP):
+                chunk = group[i:i + capi.I2R_MAX_GROUP]
+                arr = (capi.ConvProblem * len(chunk))(*chunk)
+                if fn == "tma":
+                    capi.check(self.lib.i2r_conv_tma(arr, len(chunk), _stream_ptr()), "i2r_conv_tma")
+                else:
+                    capi.check(self.lib.i2r_conv_igemm(arr, len(chunk), self.impl, _stream_ptr()), "i2r_conv_igemm")
+                self.launches += 1
         if self.timing is not None:
             e1.record()
             flops = sum(2.0 * p.NB * p.OH * p.OW * p.Cout * p.Cin * p.ntaps for p in problems)
-            self.timing.append((e0, e1, flops, n))
-        self.launches += 1
+            self.timing.append((e0, e1, flops, len(problems)))
 
     def conv(self, L, x, **kw):
-        p, out = self.problem(L, x, **kw)
-        self.launch([p])
+        probs, out = self.problems(L, x, **kw)
+        self.launch(probs)
         return out
 
     def conv_group(self, specs):
-        """specs: list of (L, x, kwargs) launched as one grid.  Returns the list of outputs."""
+        """specs: list of (L, x, kwargs) launched together (one grid per kernel kind).  Returns the outputs."""
         probs, outs = [], []
         for L, x, kw in specs:
-            p, o = self.problem(L, x, **kw)
-            probs.append(p)
+            ps, o = self.problems(L, x, **dict(kw))
+            probs.extend(ps)
             outs.append(o)
-        for i in range(0, len(probs), capi.I2R_MAX_GROUP):
-            self.launch(probs[i:i + capi.I2R_MAX_GROUP])
+        self.launch(probs)
         return outs
 
     def linear(self, L, x2d, add0=None, relu=None):
@@ -143,7 +205,8 @@ class Runner:
         assert x2d.stride(1) == 1
         ld = x2d.stride(0)
         x4 = x2d.as_strided((1, t, 1, c), (t * ld, ld, ld, 1))
-        a4 = add0.view(1, t, 1, -1) if add0 is not None else None
+        a4 = add0.as_strided((1, t, 1, add0.shape[1]), (t * add0.stride(0), add0.stride(0), add0.stride(0), 1)) \
+            if add0 is not None else None
         return self.problem(L, x4, add0=a4, relu=relu)
 
     # ------------------------------------------------------------------ small kernels

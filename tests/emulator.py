@@ -15,6 +15,8 @@ from i2r_b200.ops import Runner
 class EmuRunner(Runner):
     def __init__(self):
         self.impl = -1
+        self.use_tma = True     # exercise the N-split logic of Runner.problems
+        self.timing = None
         self.launches = 0
         self.device = torch.device("cpu")
 
@@ -48,8 +50,8 @@ class EmuRunner(Runner):
         fx = ox * p.out_mul + p.out_offx
         for a, s in ((add0, p.add0_shift), (add1, p.add1_shift)):
             if a is not None:
-                a4 = a.reshape(nb, p.OHf >> s, p.OWf >> s, cout).float()
-                v = v + a4[:, fy >> s, fx >> s, :]
+                assert tuple(a.shape) == (nb, p.OHf >> s, p.OWf >> s, cout) and a.stride(2) == p.add_pix_stride
+                v = v + a.float()[:, fy >> s, fx >> s, :]
         if p.flags & capi.F_RELU:
             v = F.relu(v)
         if p.flags & capi.F_OUT_NCHW_F32:

@@ -30,8 +30,18 @@ def dev():
 
 @pytest.fixture(scope="module")
 def runners(dev):
+    """(product runner: TMA kernel where eligible, else gather kernel; scalar check kernel)."""
     from i2r_b200.ops import Runner
     return Runner(dev, impl=0), Runner(dev, impl=1)
+
+
+@pytest.fixture(scope="module")
+def gather_runner(dev):
+    """tcgen05 gather kernel for every problem (TMA routing off)."""
+    from i2r_b200.ops import Runner
+    r = Runner(dev, impl=0)
+    r.use_tma = False
+    return r
 
 
 def _mk_conv(cout, cin, k, stride, relu, dev, seed):
@@ -61,11 +71,17 @@ CONV_CASES = [
     ("c192to96_1x1", 5, 16, 12, 192, 96, 1, 1, False),
     ("c64_3x3_s2_big", 2, 128, 96, 64, 64, 3, 2, True),
     ("ragged_M", 1, 10, 7, 48, 48, 3, 1, True),
+    ("c96_3x3_s1_b32", 32, 32, 24, 96, 96, 3, 1, True),        # N-split, resident weights, persistent loop
+    ("c192_3x3_s1_b32", 32, 16, 12, 192, 192, 3, 1, True),     # streamed weights, partial x tiles
+    ("c256to48_3x3_s1", 4, 64, 48, 256, 48, 3, 1, True),       # streamed weights, 4 K-chunks
+    ("c48_3x3_s1_b32", 32, 64, 48, 48, 48, 3, 1, True),        # 768 tiles over 148 persistent CTAs
+    ("c96to192_1x1_tokens", 1, 6144, 1, 96, 192, 1, 1, True),  # nn.Linear shape (re-tiled 8-wide)
+    ("odd_map_3x3", 3, 21, 13, 64, 64, 3, 1, False),           # ragged tiles in x and y
 ]
 
 
 @pytest.mark.parametrize("case", CONV_CASES, ids=[c[0] for c in CONV_CASES])
-def test_igemm_conv(case, dev, runners):
+def test_igemm_conv(case, dev, runners, gather_runner):
     name, nb, h, w, cin, cout, k, stride, relu = case
     tc, chk = runners
     L, wt, scale, bias = _mk_conv(cout, cin, k, stride, relu, dev, seed=hash(name) % 1000)
@@ -74,6 +90,7 @@ def test_igemm_conv(case, dev, runners):
     res = None
     y_tc = tc.conv(L, x)
     y_ck = chk.conv(L, x)
+    y_ga = gather_runner.conv(L, x)
     torch.cuda.synchronize()
     # torch fp32 reference on the same fp16-rounded operands
     xr = x.float().permute(0, 3, 1, 2)
@@ -85,7 +102,9 @@ def test_igemm_conv(case, dev, runners):
     e_ck = _diff(y_ck, ref)
     e_tc = _diff(y_tc, ref)
     e_x = _diff(y_tc, y_ck)
-    _report(test="igemm_conv", case=name, check_vs_torch=e_ck, tc_vs_torch=e_tc, tc_vs_check=e_x)
+    e_ga = _diff(y_ga, ref)
+    _report(test="igemm_conv", case=name, check_vs_torch=e_ck, tc_vs_torch=e_tc, tc_vs_check=e_x, gather_vs_torch=e_ga)
+    assert e_ga[0] <= 4e-3, ("tcgen05 gather kernel vs torch", e_ga)
     # fp16 output rounding: |y| <~ 4 -> half-ulp 2e-3
     assert e_ck[0] <= 4e-3, ("check kernel vs torch", e_ck)
     assert e_tc[0] <= 4e-3, ("tcgen05 kernel vs torch", e_tc, "vs check", e_x)
@@ -252,3 +271,41 @@ def test_bad_arguments_raise(dev, runners):
         tc.attention(torch.zeros(8, 72, device=dev).half(), torch.zeros(8, 72, device=dev).half(),
                      torch.zeros(8, 72, device=dev).half(), torch.tensor([0, 8], dtype=torch.int32, device=dev),
                      8, 1.0)   # head dim 72 unsupported
+
+
+def test_tma_residual_group_and_rank4_fallback(dev, runners):
+    """BasicBlock second conv for three resolution branches in one persistent grid (residual addends,
+    N-split halves writing channel slices), and the 4-D tensor-map fallback in a fresh process."""
+    import subprocess
+    import sys
+    tc, chk = runners
+    g = torch.Generator().manual_seed(17)
+    specs_in = []
+    for (c, h, w) in ((48, 64, 48), (96, 32, 24), (192, 16, 12)):
+        L, wt, sc, bi = _mk_conv(c, c, 3, 1, True, dev, c)
+        x = torch.randn(4, h, w, c, generator=g).to(dev).half()
+        res = torch.randn(4, h, w, c, generator=g).to(dev).half()
+        specs_in.append((L, wt, sc, bi, x, res))
+    outs = tc.conv_group([(L, x, {"add0": res}) for L, _, _, _, x, res in specs_in])
+    torch.cuda.synchronize()
+    for (L, wt, sc, bi, x, res), y in zip(specs_in, outs):
+        ref = F.conv2d(x.float().permute(0, 3, 1, 2), wt.to(dev).half().float(), None, 1, 1)
+        ref = ref * sc.to(dev).view(1, -1, 1, 1) + bi.to(dev).view(1, -1, 1, 1)
+        ref = F.relu(ref + res.float().permute(0, 3, 1, 2)).permute(0, 2, 3, 1)
+        e = _diff(y, ref)
+        _report(test="tma_group", c=L.cout, err=e)
+        assert e[0] <= 8e-3, (L.cout, e)
+    code = (
+        "import sys; sys.path.insert(0, %r); import paths, torch, math;"
+        "sys.path.insert(0, paths.REPO + '/tests');"
+        "import test_kernels_gpu as t; from i2r_b200.ops import Runner;"
+        "dev = torch.device('cuda:0'); r = Runner(dev, 0); c = Runner(dev, 1);"
+        "L, w, s, b = t._mk_conv(48, 48, 3, 1, True, dev, 1);"
+        "x = torch.randn(2, 64, 48, 48).to(dev).half();"
+        "d = (r.conv(L, x).float() - c.conv(L, x).float()).abs().max().item(); torch.cuda.synchronize();"
+        "print('RANK4_DIFF', d); assert d <= 2e-3"
+    ) % paths.REPO
+    env = dict(os.environ, I2R_TMA_RANK4="1")
+    out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
+    _report(test="tma_rank4", rc=out.returncode, tail=(out.stdout + out.stderr)[-400:])
+    assert out.returncode == 0, out.stdout + out.stderr
