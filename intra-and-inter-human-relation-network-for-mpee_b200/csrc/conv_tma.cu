@@ -43,7 +43,6 @@ struct TmaProblem {
   int cta_begin, cta_count;
   int w_resident;
   uint32_t w_total_bytes, w_stage_bytes;
-  int rank5;
   uint32_t a_stage_bytes, a_tx_bytes;
   int a_stages, w_stages;
   uint32_t w_off;      // byte offset of the weight region in dynamic smem
@@ -68,15 +67,93 @@ __device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* map
       ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4), "r"(bar)
       : "memory");
 }
-__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, int c3,
-                                            uint32_t bar) {
-  asm volatile(
-      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2,%3,%4,%5}], [%6];"
-      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(bar)
-      : "memory");
-}
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
+}
+
+// MMA issue loop.  Everything here is warp-uniform (kernel parameters, loop counters, shared-memory
+// addresses), so descriptor arithmetic stays on the uniform datapath and costs two 32-bit adds per
+// tcgen05.mma: the loop must sustain one MMA every ~25 cycles for N = 48.
+template <int NTAPS, int KG2>
+__device__ __forceinline__ void mma_role(const TmaProblem& P, const int cta, const uint32_t sbase,
+                                         const uint32_t tmem_base, const uint32_t ncols) {
+  constexpr int HALO = NTAPS == 9 ? 1 : 0;
+  constexpr int HW = T_TW + 2 * HALO, HH = T_TH + 2 * HALO;
+  constexpr uint32_t A_LBO = HH * HW * 16, A_SBO = HW * 16;
+  const uint32_t bar_afull = sbase, bar_aempty = sbase + 32, bar_wfull = sbase + 64, bar_wempty = sbase + 96;
+  const uint32_t bar_accfull = sbase + 128, bar_accempty = sbase + 144, bar_wres = sbase + 160;
+  const uint32_t a_base = sbase + T_A_OFF;
+  const uint32_t w_base = sbase + P.w_off;
+  const int Npad = P.Npad;
+  const uint32_t idesc = make_idesc_f16(128, Npad);
+  const uint32_t b_lbo = static_cast<uint32_t>(Npad) * 16;
+  const uint32_t a_hi = smem_desc_hi(A_SBO), b_hi = smem_desc_hi(128);
+  const uint32_t b_k2 = (2 * b_lbo) >> 4;                                   // one K=16 step, descriptor units
+  const uint32_t b_tap = (static_cast<uint32_t>(P.C >> 3) * b_lbo) >> 4;   // resident: next tap
+  const uint32_t b_kc = (static_cast<uint32_t>(2 * KG2) * b_lbo) >> 4;     // resident: next K-chunk
+  const uint32_t w_lo0 = smem_desc_lo(w_base, b_lbo);
+  const uint32_t w_stage16 = P.w_stage_bytes >> 4;
+  const uint32_t a_stage16 = P.a_stage_bytes >> 4;
+  const uint32_t a_lo0 = smem_desc_lo(a_base, A_LBO);
+  const bool resident = P.w_resident != 0;
+  const bool leader = elect_one();
+  int as = 0, ws = 0, acc = 0;
+  uint32_t aph = 0, wph = 0, accph = 0;
+  if (resident) mbar_wait(bar_wres, 0);
+  for (int t = cta; t < P.ntiles; t += P.cta_count) {
+    mbar_wait(bar_accempty + 8 * acc, accph ^ 1);
+    tc_fence_after();
+    const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc) * (ncols >> 1);
+    uint32_t accum = 0;
+    for (int kc = 0; kc < P.nkc; ++kc) {
+      mbar_wait(bar_afull + 8 * as, aph);
+      tc_fence_after();
+      const uint32_t a_lo = a_lo0 + as * a_stage16;
+      const uint32_t b_lo_kc = w_lo0 + kc * b_kc;
+      if (resident) {
+#pragma unroll
+        for (int tap = 0; tap < NTAPS; ++tap) {
+          const uint32_t b_lo = b_lo_kc + tap * b_tap;
+          const uint32_t a_t = a_lo + (HALO ? static_cast<uint32_t>((tap / 3) * HW + (tap % 3)) : 0u);
+#pragma unroll
+          for (int k2 = 0; k2 < KG2; ++k2) {
+            if (leader)
+              umma_f16(d_tmem, desc64(a_t + k2 * ((2 * A_LBO) >> 4), a_hi), desc64(b_lo + k2 * b_k2, b_hi), idesc,
+                       accum);
+            accum = 1;
+          }
+        }
+      } else {
+#pragma unroll
+        for (int tap = 0; tap < NTAPS; ++tap) {
+          mbar_wait(bar_wfull + 8 * ws, wph);
+          tc_fence_after();
+          const uint32_t b_lo = w_lo0 + ws * w_stage16;
+          const uint32_t a_t = a_lo + (HALO ? static_cast<uint32_t>((tap / 3) * HW + (tap % 3)) : 0u);
+#pragma unroll
+          for (int k2 = 0; k2 < KG2; ++k2) {
+            if (leader)
+              umma_f16(d_tmem, desc64(a_t + k2 * ((2 * A_LBO) >> 4), a_hi), desc64(b_lo + k2 * b_k2, b_hi), idesc,
+                       accum);
+            accum = 1;
+          }
+          if (leader) umma_commit(bar_wempty + 8 * ws);
+          if (++ws == P.w_stages) {
+            ws = 0;
+            wph ^= 1;
+          }
+        }
+      }
+      if (leader) umma_commit(bar_aempty + 8 * as);
+      if (++as == P.a_stages) {
+        as = 0;
+        aph ^= 1;
+      }
+    }
+    if (leader) umma_commit(bar_accfull + 8 * acc);
+    acc ^= 1;
+    if (acc == 0) accph ^= 1;
+  }
 }
 
 __global__ void __launch_bounds__(T_THREADS, 1) conv_tma_kernel(const __grid_constant__ TmaGroup G) {
@@ -129,14 +206,12 @@ __global__ void __launch_bounds__(T_THREADS, 1) conv_tma_kernel(const __grid_con
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  const int hw = T_TW + 2 * P.halo, hh = T_TH + 2 * P.halo;
   const int kg_per_stage = P.KCH >> 3;
 
   if (warp == 0 && lane == 0) {
     // ================================================= activation producer (TMA)
     int s = 0;
     uint32_t ph = 0;
-    const uint32_t grp_bytes = static_cast<uint32_t>(hh * hw * 16);
     for (int t = cta; t < P.ntiles; t += P.cta_count) {
       const int n = t / P.tiles_per_img;
       const int r = t - n * P.tiles_per_img;
@@ -146,12 +221,7 @@ __global__ void __launch_bounds__(T_THREADS, 1) conv_tma_kernel(const __grid_con
         mbar_wait(bar_aempty + 8 * s, ph ^ 1);
         mbar_arrive_expect_tx(bar_afull + 8 * s, P.a_tx_bytes);
         const uint32_t dst = a_base + s * P.a_stage_bytes;
-        if (P.rank5) {
-          tma_load_5d(dst, amap, 0, x0, y0, kc * kg_per_stage, n, bar_afull + 8 * s);
-        } else {
-          for (int g = 0; g < kg_per_stage; ++g)
-            tma_load_4d(dst + g * grp_bytes, amap, (kc * kg_per_stage + g) * 8, x0, y0, n, bar_afull + 8 * s);
-        }
+        tma_load_5d(dst, amap, 0, x0, y0, kc * kg_per_stage, n, bar_afull + 8 * s);
         if (++s == P.a_stages) {
           s = 0;
           ph ^= 1;
@@ -185,65 +255,16 @@ __global__ void __launch_bounds__(T_THREADS, 1) conv_tma_kernel(const __grid_con
         }
       }
     }
-  } else if (warp == 2 && lane == 0) {
-    // ================================================= MMA issuer
-    const uint32_t idesc = make_idesc_f16(128, Npad);
-    const uint32_t a_lbo = static_cast<uint32_t>(hh * hw * 16), a_sbo = static_cast<uint32_t>(hw * 16);
-    const uint32_t b_lbo = static_cast<uint32_t>(Npad) * 16;
-    int as = 0, ws = 0, acc = 0;
-    uint32_t aph = 0, wph = 0, accph = 0;
-    if (P.w_resident) mbar_wait(bar_wres, 0);
-    for (int t = cta; t < P.ntiles; t += P.cta_count) {
-      mbar_wait(bar_accempty + 8 * acc, accph ^ 1);
-      tc_fence_after();
-      const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc) * (ncols >> 1);
-      uint32_t accum = 0;
-      for (int kc = 0; kc < P.nkc; ++kc) {
-        mbar_wait(bar_afull + 8 * as, aph);
-        tc_fence_after();
-        const uint32_t a_s = a_base + as * P.a_stage_bytes;
-        for (int tap = 0; tap < P.ntaps; ++tap) {
-          uint32_t wb;
-          if (P.w_resident) {
-            wb = w_base;
-          } else {
-            mbar_wait(bar_wfull + 8 * ws, wph);
-            tc_fence_after();
-            wb = w_base + ws * P.w_stage_bytes;
-          }
-          uint32_t tap_off = 0;
-          if (P.ntaps == 9) tap_off = static_cast<uint32_t>(((tap / 3) * hw + (tap % 3)) * 16);
-          for (int k2 = 0; k2 < (kg_per_stage >> 1); ++k2) {
-            const uint64_t ad = make_smem_desc(a_s + 2 * k2 * a_lbo + tap_off, a_lbo, a_sbo);
-            uint32_t boff;
-            if (P.w_resident) {
-              const int gk = kc * kg_per_stage + 2 * k2;
-              const int chunk = gk / P.kgp, g = gk - chunk * P.kgp;
-              boff = static_cast<uint32_t>(((tap * P.nchp + chunk) * P.kgp + g)) * b_lbo;
-            } else {
-              boff = 2 * k2 * b_lbo;
-            }
-            const uint64_t bd = make_smem_desc(wb + boff, b_lbo, 128);
-            umma_f16(d_tmem, ad, bd, idesc, accum);
-            accum = 1;
-          }
-          if (!P.w_resident) {
-            umma_commit(bar_wempty + 8 * ws);
-            if (++ws == P.w_stages) {
-              ws = 0;
-              wph ^= 1;
-            }
-          }
-        }
-        umma_commit(bar_aempty + 8 * as);
-        if (++as == P.a_stages) {
-          as = 0;
-          aph ^= 1;
-        }
-      }
-      umma_commit(bar_accfull + 8 * acc);
-      acc ^= 1;
-      if (acc == 0) accph ^= 1;
+  } else if (warp == 2) {
+    // ================================================= MMA issuer (whole warp runs the loop, one lane issues)
+    const int sel = P.ntaps == 9 ? 0 : 3;
+    switch (sel + (kg_per_stage == 6 ? 0 : kg_per_stage == 8 ? 1 : 2)) {
+      case 0: mma_role<9, 3>(P, cta, sbase, tmem_base, ncols); break;
+      case 1: mma_role<9, 4>(P, cta, sbase, tmem_base, ncols); break;
+      case 2: mma_role<9, 6>(P, cta, sbase, tmem_base, ncols); break;
+      case 3: mma_role<1, 3>(P, cta, sbase, tmem_base, ncols); break;
+      case 4: mma_role<1, 4>(P, cta, sbase, tmem_base, ncols); break;
+      default: mma_role<1, 6>(P, cta, sbase, tmem_base, ncols); break;
     }
   } else if (warp >= 4) {
     // ================================================= epilogue
@@ -362,40 +383,27 @@ static EncodeTiledFn get_encode() {
   return fn;
 }
 
-static int g_force_rank4 = 0;  // test hook (I2R_TMA_RANK4=1): exercise the 4-D fallback path
-
 static int encode_amap(CUtensorMap* map, const void* x, int NB, int H, int W, int C, int pix_stride, int hw, int hh,
-                       int kch, int* rank5) {
+                       int kch) {
   EncodeTiledFn enc = get_encode();
   if (!enc) {
     set_error("cuTensorMapEncodeTiled entry point unavailable");
     return I2R_E_DEVICE;
   }
+  // 5-D view of the NHWC tensor: (8 channels, x, y, channel group, image); the group dimension has a
+  // 16-byte stride, so one box lands in shared memory as [group][y][x][8 ch] = the UMMA core-matrix order.
   const cuuint64_t pb = static_cast<cuuint64_t>(pix_stride) * 2;
   const cuuint32_t ones[5] = {1, 1, 1, 1, 1};
-  if (!g_force_rank4) {
-    const cuuint64_t dims[5] = {8, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)(C / 8), (cuuint64_t)NB};
-    const cuuint64_t strides[4] = {pb, pb * W, 16, pb * W * H};
-    const cuuint32_t box[5] = {8, (cuuint32_t)hw, (cuuint32_t)hh, (cuuint32_t)(kch / 8), 1};
-    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 5, const_cast<void*>(x), dims, strides, box, ones,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r == CUDA_SUCCESS) {
-      *rank5 = 1;
-      return 0;
-    }
-  }
-  const cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)NB};
-  const cuuint64_t strides[3] = {pb, pb * W, pb * W * H};
-  const cuuint32_t box[4] = {8, (cuuint32_t)hw, (cuuint32_t)hh, 1};
-  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(x), dims, strides, box, ones,
+  const cuuint64_t dims[5] = {8, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)(C / 8), (cuuint64_t)NB};
+  const cuuint64_t strides[4] = {pb, pb * W, 16, pb * W * H};
+  const cuuint32_t box[5] = {8, (cuuint32_t)hw, (cuuint32_t)hh, (cuuint32_t)(kch / 8), 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 5, const_cast<void*>(x), dims, strides, box, ones,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled failed (%d) for [%d,%d,%d,%d] pix_stride %d", (int)r, NB, H, W, C, pix_stride);
     return I2R_E_DEVICE;
   }
-  *rank5 = 0;
   return 0;
 }
 
@@ -437,8 +445,6 @@ extern "C" int i2r_conv_tma(const i2r_conv_problem* probs, int nprob, void* stre
     int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
-    const char* e = getenv("I2R_TMA_RANK4");
-    g_force_rank4 = (e && e[0] == '1') ? 1 : 0;
   }
   TmaGroup G;
   memset(&G, 0, sizeof(G));
@@ -515,7 +521,7 @@ extern "C" int i2r_conv_tma(const i2r_conv_problem* probs, int nprob, void* stre
     P.w_off = T_A_OFF + static_cast<uint32_t>(astg) * P.a_stage_bytes;
     const uint32_t need = P.w_off + wregion;
     if (need > smem_need) smem_need = need;
-    int rc = encode_amap(&G.amap[i], S.x, P.NB, P.H, P.W, P.C, S.in_pix_stride, hw, hh, P.KCH, &P.rank5);
+    int rc = encode_amap(&G.amap[i], S.x, P.NB, P.H, P.W, P.C, S.in_pix_stride, hw, hh, P.KCH);
     if (rc) return rc;
     cost[i] = static_cast<double>(P.ntiles) * S.ntaps * S.Cin * (S.Npad < 64 ? 64 : S.Npad);
     total_cost += cost[i];

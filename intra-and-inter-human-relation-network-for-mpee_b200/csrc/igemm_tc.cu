@@ -260,26 +260,33 @@ __device__ __forceinline__ void run_tile(const i2r_conv_problem& P, const int ti
         }
       }
     }
-  } else if (lane == 0) {
-    // =============================================================== MMA issuer (one thread)
+  } else {
+    // =============================================================== MMA issuer (warp-uniform loop, one lane issues)
     const uint32_t idesc = make_idesc_f16(BM, Npad);
     const uint32_t b_lbo = static_cast<uint32_t>(Npad) * 16;
+    const uint32_t a_hi = smem_desc_hi(128), b_hi = smem_desc_hi(128);
+    const uint32_t a_lo0 = smem_desc_lo(stages0, A_KG_STRIDE);
+    const uint32_t b_lo0 = smem_desc_lo(stages0 + a_bytes, b_lbo);
+    const uint32_t st16 = static_cast<uint32_t>(st_bytes) >> 4;
+    const uint32_t b_k2 = (2 * b_lbo) >> 4;
+    const bool leader = elect_one();
+    uint32_t accum = 0;
     for (int it = 0; it < niter; ++it) {
       const int s = it % STAGES;
       const uint32_t ph = (it / STAGES) & 1;
       mbar_wait(bar_full + 8 * s, ph);
       tc_fence_after();
-      const uint32_t a_s = stages0 + s * st_bytes;
-      const uint32_t b_s = a_s + a_bytes;
+      const uint32_t a_lo = a_lo0 + s * st16, b_lo = b_lo0 + s * st16;
 #pragma unroll
       for (int k = 0; k < KG / 2; ++k) {
-        const uint64_t ad = make_smem_desc(a_s + 2 * k * A_KG_STRIDE, A_KG_STRIDE, 128);
-        const uint64_t bd = make_smem_desc(b_s + 2 * k * b_lbo, b_lbo, 128);
-        umma_f16(tmem_base, ad, bd, idesc, (it | k) != 0 ? 1u : 0u);
+        if (leader)
+          umma_f16(tmem_base, desc64(a_lo + k * ((2 * A_KG_STRIDE) >> 4), a_hi), desc64(b_lo + k * b_k2, b_hi), idesc,
+                   accum);
+        accum = 1;
       }
-      umma_commit(bar_empty + 8 * s);
+      if (leader) umma_commit(bar_empty + 8 * s);
     }
-    umma_commit(bar_accum);
+    if (leader) umma_commit(bar_accum);
   }
 
   // ---------------- teardown
