@@ -13,7 +13,8 @@
 //   D           : two TMEM accumulators (2 x Npad columns) so the epilogue of tile i overlaps the
 //                 MMAs of tile i+1.
 //   warps       : 0 = activation TMA producer, 1 = weight producer, 2 = MMA issuer, 3 = TMEM owner,
-//                 4..7 = epilogue (TMEM -> registers -> scale/bias/residual/ReLU -> global).
+//                 4..11 = epilogue (TMEM -> registers -> scale/bias/residual/ReLU -> global), two warps per
+//                 TMEM lane quadrant, each owning half of the output channels.
 //   grid        : persistent; each problem of a grouped launch owns a contiguous CTA range sized
 //                 by its share of the MMA work, CTAs stride over that problem's tiles.
 #include <cuda.h>
@@ -54,7 +55,7 @@ struct TmaGroup {
   int nprob;
 };
 
-constexpr int T_THREADS = 256;
+constexpr int T_THREADS = 384;
 constexpr int T_TW = 8, T_TH = 16;
 constexpr uint32_t T_A_OFF = 3072;          // dynamic smem: [0,256) barriers | [256,2304) scale,bias | A ring
 constexpr uint32_t T_MAX_SMEM = 225 * 1024;
@@ -187,7 +188,7 @@ __global__ void __launch_bounds__(T_THREADS, 1) conv_tma_kernel(const __grid_con
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(bar_accfull + 8 * i, 1);
-      mbar_init(bar_accempty + 8 * i, 4);
+      mbar_init(bar_accempty + 8 * i, 8);
     }
     mbar_init(bar_wres, 1);
     fence_mbar_init();
@@ -267,12 +268,19 @@ __global__ void __launch_bounds__(T_THREADS, 1) conv_tma_kernel(const __grid_con
       default: mma_role<1, 6>(P, cta, sbase, tmem_base, ncols); break;
     }
   } else if (warp >= 4) {
-    // ================================================= epilogue
+    // ================================================= epilogue: 8 warps, two per TMEM lane quadrant, each
+    // owning half of the output channels of its 32 rows; residual loads are issued before the accumulator
+    // wait so their latency hides behind the MMAs of the tile.
     const int ew = warp - 4;
-    const int row = ew * 32 + lane;
+    const int quad = ew & 3;               // == warp % 4: the TMEM lanes this warp may read
+    const int row = quad * 32 + lane;
     const int ty_in = row >> 3, tx_in = row & 7;
     const int Cout = P.Cout;
     const bool relu = (P.flags & I2R_F_RELU) != 0;
+    const int n8 = Npad >> 3, half8 = (n8 + 1) >> 1;
+    const int cb = (ew >> 2) ? half8 : 0, ce = (ew >> 2) ? n8 : half8;   // 8-column chunks [cb, ce)
+    const float4* s_scale4 = reinterpret_cast<const float4*>(s_scale);
+    const float4* s_bias4 = reinterpret_cast<const float4*>(s_bias);
     int acc = 0;
     uint32_t accph = 0;
     for (int t = cta; t < P.ntiles; t += P.cta_count) {
@@ -282,74 +290,85 @@ __global__ void __launch_bounds__(T_THREADS, 1) conv_tma_kernel(const __grid_con
       const int x = tx * T_TW + tx_in, y = ty * T_TH + ty_in;
       const bool valid = (x < P.W) && (y < P.H);
       const int64_t p = (static_cast<int64_t>(n) * P.H + y) * P.W + x;
-      mbar_wait(bar_accfull + 8 * acc, accph);
-      tc_fence_after();
-      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + static_cast<uint32_t>(acc) * (ncols >> 1);
-      const __half* a0 = P.add0 ? P.add0 + p * P.add_pix_stride : nullptr;
-      const __half* a1 = P.add1 ? P.add1 + p * P.add_pix_stride : nullptr;
-      for (int c0 = 0; c0 < Npad; c0 += 16) {
-        uint32_t rg[16];
-        tmem_ld16(taddr + c0, rg);
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + static_cast<uint32_t>(acc) * (ncols >> 1);
+      const __half* a0 = (P.add0 && valid) ? P.add0 + p * P.add_pix_stride : nullptr;
+      const __half* a1 = (P.add1 && valid) ? P.add1 + p * P.add_pix_stride : nullptr;
+      bool waited = false;
+      for (int c = cb; c < ce; c += 4) {
+        const int nc = min(4, ce - c);
+        uint4 r0[4], r1[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          r0[j] = make_uint4(0, 0, 0, 0);
+          r1[j] = make_uint4(0, 0, 0, 0);
+          if (j < nc && (c + j) * 8 < Cout) {
+            if (a0 != nullptr) r0[j] = __ldg(reinterpret_cast<const uint4*>(a0 + (c + j) * 8));
+            if (a1 != nullptr) r1[j] = __ldg(reinterpret_cast<const uint4*>(a1 + (c + j) * 8));
+          }
+        }
+        if (!waited) {
+          mbar_wait(bar_accfull + 8 * acc, accph);
+          tc_fence_after();
+          waited = true;
+        }
+        uint32_t av[4][8];
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (j < nc) tmem_ld8(taddr + (c + j) * 8, av[j]);
         tmem_ld_wait();
-        if (!valid) continue;
-        float v[16];
 #pragma unroll
-        for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(rg[i]) * s_scale[c0 + i] + s_bias[c0 + i];
+        for (int j = 0; j < 4; ++j) {
+          if (j < nc && valid && (c + j) * 8 < Cout) {
+            const int c0 = (c + j) * 8;
+            const float4 sa = s_scale4[2 * (c + j)], sb = s_scale4[2 * (c + j) + 1];
+            const float4 ba = s_bias4[2 * (c + j)], bb = s_bias4[2 * (c + j) + 1];
+            float v[8];
+            v[0] = __uint_as_float(av[j][0]) * sa.x + ba.x;
+            v[1] = __uint_as_float(av[j][1]) * sa.y + ba.y;
+            v[2] = __uint_as_float(av[j][2]) * sa.z + ba.z;
+            v[3] = __uint_as_float(av[j][3]) * sa.w + ba.w;
+            v[4] = __uint_as_float(av[j][4]) * sb.x + bb.x;
+            v[5] = __uint_as_float(av[j][5]) * sb.y + bb.y;
+            v[6] = __uint_as_float(av[j][6]) * sb.z + bb.z;
+            v[7] = __uint_as_float(av[j][7]) * sb.w + bb.w;
+            const uint32_t q0[4] = {r0[j].x, r0[j].y, r0[j].z, r0[j].w};
+            const uint32_t q1[4] = {r1[j].x, r1[j].y, r1[j].z, r1[j].w};
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          if (c0 + h * 8 < Cout) {
-            if (a0 != nullptr) {
-              const uint4 q = *reinterpret_cast<const uint4*>(a0 + c0 + h * 8);
-              const uint32_t w4[4] = {q.x, q.y, q.z, q.w};
-#pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                const float2 f = unpack_h2(w4[i]);
-                v[h * 8 + 2 * i] += f.x;
-                v[h * 8 + 2 * i + 1] += f.y;
-              }
+            for (int i = 0; i < 4; ++i) {
+              const float2 f0 = unpack_h2(q0[i]), f1 = unpack_h2(q1[i]);
+              v[2 * i] += f0.x + f1.x;
+              v[2 * i + 1] += f0.y + f1.y;
             }
-            if (a1 != nullptr) {
-              const uint4 q = *reinterpret_cast<const uint4*>(a1 + c0 + h * 8);
-              const uint32_t w4[4] = {q.x, q.y, q.z, q.w};
+            if (relu) {
 #pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                const float2 f = unpack_h2(w4[i]);
-                v[h * 8 + 2 * i] += f.x;
-                v[h * 8 + 2 * i + 1] += f.y;
-              }
+              for (int i = 0; i < 8; ++i) v[i] = fmaxf(v[i], 0.0f);
             }
-          }
-        }
-        if (relu) {
+            if (P.flags & I2R_F_OUT_NCHW_F32) {
+              float* Y = reinterpret_cast<float*>(P.y);
+              const int64_t nr = p / P.plane, rem = p - nr * P.plane;
+              const int64_t base = nr * Cout * P.plane + rem;
 #pragma unroll
-          for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.0f);
-        }
-        if (P.flags & I2R_F_OUT_NCHW_F32) {
-          float* Y = reinterpret_cast<float*>(P.y);
-          const int64_t nr = p / P.plane, rem = p - nr * P.plane;
-          const int64_t base = nr * Cout * P.plane + rem;
+              for (int i = 0; i < 8; ++i)
+                if (c0 + i < Cout) Y[base + static_cast<int64_t>(c0 + i) * P.plane] = v[i];
+            } else if (P.flags & I2R_F_OUT_F32) {
+              float* Y = reinterpret_cast<float*>(P.y) + p * P.out_pix_stride + c0;
 #pragma unroll
-          for (int i = 0; i < 16; ++i)
-            if (c0 + i < Cout) Y[base + static_cast<int64_t>(c0 + i) * P.plane] = v[i];
-        } else if (P.flags & I2R_F_OUT_F32) {
-          float* Y = reinterpret_cast<float*>(P.y) + p * P.out_pix_stride + c0;
-#pragma unroll
-          for (int i = 0; i < 16; ++i)
-            if (c0 + i < Cout) Y[i] = v[i];
-        } else {
-          __half* Y = reinterpret_cast<__half*>(P.y) + p * P.out_pix_stride + c0;
-#pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            if (c0 + h * 8 < Cout) {
+              for (int i = 0; i < 8; ++i)
+                if (c0 + i < Cout) Y[i] = v[i];
+            } else {
               uint4 q;
-              q.x = pack_h2(v[h * 8 + 0], v[h * 8 + 1]);
-              q.y = pack_h2(v[h * 8 + 2], v[h * 8 + 3]);
-              q.z = pack_h2(v[h * 8 + 4], v[h * 8 + 5]);
-              q.w = pack_h2(v[h * 8 + 6], v[h * 8 + 7]);
-              *reinterpret_cast<uint4*>(Y + h * 8) = q;
+              q.x = pack_h2(v[0], v[1]);
+              q.y = pack_h2(v[2], v[3]);
+              q.z = pack_h2(v[4], v[5]);
+              q.w = pack_h2(v[6], v[7]);
+              *reinterpret_cast<uint4*>(reinterpret_cast<__half*>(P.y) + p * P.out_pix_stride + c0) = q;
             }
           }
         }
+      }
+      if (!waited) {  // no columns assigned to this warp (tiny N): still take part in the hand-shake
+        mbar_wait(bar_accfull + 8 * acc, accph);
+        tc_fence_after();
       }
       tc_fence_before();
       __syncwarp();
