@@ -85,14 +85,15 @@ int i2r_sm_count(int dev);
  * (tests only; same problem struct, same packed weights). */
 int i2r_conv_igemm(const i2r_conv_problem* probs, int nprob, int impl, void* stream);
 
-/* Persistent TMA-fed variant for the problems that dominate the FLOPs: stride-1 3x3 (BasicBlock /
+/* Persistent halo-tile variant for the problems that dominate the FLOPs: stride-1 3x3 (BasicBlock /
  * Bottleneck convs, interformer_pureMulti.py:37-107) and 1x1 / nn.Linear problems with no resampling
- * (in_shift 0, out_mul 1, addend shifts 0).  Activation halo tiles arrive by TMA (one 5-D box per
- * tile and K-chunk), weights stay resident in shared memory when they fit, two TMEM accumulators
- * overlap the epilogue with the next tile.  i2r_conv_tma_supported() returns 1 when a problem
- * qualifies; others go through i2r_conv_igemm. */
-int i2r_conv_tma_supported(const i2r_conv_problem* prob);
-int i2r_conv_tma(const i2r_conv_problem* probs, int nprob, void* stream);
+ * (in_shift 0, out_mul 1, addend shifts 0).  Each 8x16-pixel tile's activation halo is staged once in
+ * shared memory and the nine taps are shifted UMMA descriptor windows of it; weights arrive as TMA
+ * bulk copies and stay resident in shared memory when they fit; two TMEM accumulators overlap the
+ * epilogue with the next tile.  i2r_conv_halo_supported() returns 1 when a problem qualifies;
+ * others go through i2r_conv_igemm. */
+int i2r_conv_halo_supported(const i2r_conv_problem* prob);
+int i2r_conv_halo(const i2r_conv_problem* probs, int nprob, void* stream);
 
 /* Stem / mask convolution on fp32 NCHW input with tiny Cin (3 or 1): 3x3 stride 2 pad 1 + folded
  * BN + ReLU -> fp16 NHWC [NB, H/2, W/2, Cout].  Replaces conv1/bn1/relu

@@ -1,24 +1,24 @@
 // Persistent, warp-specialised convolution kernel for stride-1 3x3 and 1x1 problems (sm_100a):
-// TMA-staged activation tiles -> tcgen05.mma with TMEM accumulators -> fused epilogue.
+// halo-tile activation staging -> tcgen05.mma with TMEM accumulators -> fused epilogue.
 //
 //   tile        : 8 (x) by 16 (y) output pixels = 128 accumulator rows, all Npad output channels
-//   A operand   : ONE 5-D TMA box per (tile, K-chunk) brings the (8+2) x (16+2) halo tile of KCH channels
-//                 into shared memory as [k-group of 8 ch][halo y][halo x][8 x fp16]; out-of-image
-//                 pixels are zero-filled by the TMA unit (this is the conv padding).  The nine taps
-//                 of a 3x3 filter are nine shifted windows of that single tile: the UMMA descriptor's
-//                 start address moves by ((dy*10+dx)*16 B), SBO = one halo row (160 B), LBO = one
-//                 k-group plane -- every activation byte is fetched once instead of nine times.
-//   B operand   : weights pre-packed in core-matrix order; resident in shared memory for the whole
-//                 kernel when they fit (<= 120 KB), else streamed per (K-chunk, tap) through a ring.
-//   D           : two TMEM accumulators (2 x Npad columns) so the epilogue of tile i overlaps the
-//                 MMAs of tile i+1.
-//   warps       : 0 = activation TMA producer, 1 = weight producer, 2 = MMA issuer, 3 = TMEM owner,
-//                 4..11 = epilogue (TMEM -> registers -> scale/bias/residual/ReLU -> global), two warps per
+//   A operand   : per (tile, K-chunk) the (8+2) x (16+2) halo tile of KCH channels is staged ONCE in shared
+//                 memory as [k-group of 8 ch][halo y][halo x][8 x fp16] by four producer warps with
+//                 coalesced 16-byte cp.async (zero-fill outside the image = conv padding).  The nine
+//                 taps of a 3x3 filter are nine shifted windows of that single tile: the UMMA descriptor's
+//                 start address moves by ((dy*10+dx)*16 B), SBO = one halo row (160 B), LBO = one k-group
+//                 plane -- every activation byte is fetched once instead of nine times.
+//                 (A 5-D TMA box can deposit exactly this layout, but its 16-byte inner rows were measured
+//                 at ~4 B/cycle/SM on B200 -- see profiles/ -- so cp.async feeds this operand.)
+//   B operand   : weights pre-packed in core-matrix order, moved by the TMA unit as 1-D bulk copies;
+//                 resident in shared memory for the whole kernel when they fit (<= 120 KB), else streamed
+//                 per (K-chunk, tap) through an mbarrier ring.
+//   D           : two TMEM accumulators so the epilogue of tile i overlaps the MMAs of tile i+1.
+//   warps       : 0..3 = activation producers, 4 = weight producer, 5 = TMEM owner + MMA issuer,
+//                 6..13 = epilogue (TMEM -> registers -> scale/bias/residual/ReLU -> global), two warps per
 //                 TMEM lane quadrant, each owning half of the output channels.
 //   grid        : persistent; each problem of a grouped launch owns a contiguous CTA range sized
-//                 by its share of the MMA work, CTAs stride over that problem's tiles.
-#include <cuda.h>
-
+//                 by its share of the work, CTAs stride over that problem's tiles.
 #include <cstdio>
 #include <cstring>
 
@@ -26,7 +26,8 @@
 
 namespace i2r {
 
-struct TmaProblem {
+struct HaloProblem {
+  const __half* x;
   const uint8_t* w;
   const float* scale;
   const float* bias;
@@ -38,49 +39,38 @@ struct TmaProblem {
   int KCH, nkc;        // channels per A stage, A stages per tile
   int kgp, nchp;       // packed-weight geometry: k-groups per packed chunk, packed chunks per tap
   int tiles_x, tiles_per_img, ntiles;
-  int out_pix_stride, add_pix_stride;
+  int in_pix_stride, out_pix_stride, add_pix_stride;
   int plane;           // real OH*OW of the output (NCHW addressing)
   uint32_t flags;
   int cta_begin, cta_count;
   int w_resident;
   uint32_t w_total_bytes, w_stage_bytes;
   uint32_t a_stage_bytes, a_tx_bytes;
-  int a_stages, w_stages;
+  int a_stages, w_stages, look;
   uint32_t w_off;      // byte offset of the weight region in dynamic smem
 };
 
-struct TmaGroup {
-  CUtensorMap amap[I2R_MAX_GROUP];
-  TmaProblem p[I2R_MAX_GROUP];
+struct HaloGroup {
+  HaloProblem p[I2R_MAX_GROUP];
   int nprob;
 };
 
-constexpr int T_THREADS = 384;
+constexpr int T_THREADS = 448;
+constexpr int T_NPROD = 128;
 constexpr int T_TW = 8, T_TH = 16;
 constexpr uint32_t T_A_OFF = 3072;          // dynamic smem: [0,256) barriers | [256,2304) scale,bias | A ring
 constexpr uint32_t T_MAX_SMEM = 225 * 1024;
 constexpr uint32_t T_W_RES_MAX = 120 * 1024;
 
-__device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, int c3,
-                                            int c4, uint32_t bar) {
-  asm volatile(
-      "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2,%3,%4,%5,%6}], [%7];"
-      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4), "r"(bar)
-      : "memory");
-}
-__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
-  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
-}
-
 // MMA issue loop.  Everything here is warp-uniform (kernel parameters, loop counters, shared-memory
 // addresses), so descriptor arithmetic stays on the uniform datapath and costs two 32-bit adds per
 // tcgen05.mma: the loop must sustain one MMA every ~25 cycles for N = 48.
 template <int NTAPS, int KG2>
-__device__ __forceinline__ void mma_role(const TmaProblem& P, const int cta, const uint32_t sbase,
+__device__ __forceinline__ void mma_role(const HaloProblem& P, const int cta, const uint32_t sbase,
                                          const uint32_t tmem_base, const uint32_t ncols) {
   constexpr int HALO = NTAPS == 9 ? 1 : 0;
   constexpr int HW = T_TW + 2 * HALO, HH = T_TH + 2 * HALO;
-  constexpr uint32_t A_LBO = HH * HW * 16, A_SBO = HW * 16;
+  constexpr uint32_t A_LBO = HH * HW * 16 + 16, A_SBO = HW * 16;   // +16: bank spread for the producers
   const uint32_t bar_afull = sbase, bar_aempty = sbase + 32, bar_wfull = sbase + 64, bar_wempty = sbase + 96;
   const uint32_t bar_accfull = sbase + 128, bar_accempty = sbase + 144, bar_wres = sbase + 160;
   const uint32_t a_base = sbase + T_A_OFF;
@@ -157,12 +147,77 @@ __device__ __forceinline__ void mma_role(const TmaProblem& P, const int cta, con
   }
 }
 
-__global__ void __launch_bounds__(T_THREADS, 1) conv_tma_kernel(const __grid_constant__ TmaGroup G) {
+// Activation producers (warps 0..3).  Slot i of thread tid covers 16-byte chunk j = tid + 128*i of the
+// halo tile, j = (halo pixel) * KG + (k-group): consecutive threads read consecutive 16 B of a pixel row
+// (coalesced) and write [k-group][pixel] with a padded k-group stride (bank-conflict free).
+template <int NTAPS, int KG>
+__device__ __forceinline__ void producer_role(const HaloProblem& P, const int cta, const uint32_t sbase) {
+  constexpr int HALO = NTAPS == 9 ? 1 : 0;
+  constexpr int HW = T_TW + 2 * HALO, HH = T_TH + 2 * HALO;
+  constexpr int CHUNKS = HH * HW * KG;
+  constexpr int SLOTS = (CHUNKS + T_NPROD - 1) / T_NPROD;
+  constexpr uint32_t A_LBO = HH * HW * 16 + 16;
+  const uint32_t bar_afull = sbase, bar_aempty = sbase + 32;
+  const uint32_t a_base = sbase + T_A_OFF;
+  const int tid = threadIdx.x;
+  const int look = P.look;   // groups kept in flight (2 when the ring has >= 3 stages)
+  int goff[SLOTS], hyx[SLOTS];   // hyx = halo y << 16 | halo x << 8 | k-group  (-1: slot past the tile)
+#pragma unroll
+  for (int i = 0; i < SLOTS; ++i) {
+    const int j = tid + i * T_NPROD;
+    const int pix = j / KG, g = j - pix * KG;
+    const int hy = pix / HW, hx = pix - hy * HW;
+    goff[i] = (hy * P.W + hx) * P.in_pix_stride + g * 8;
+    hyx[i] = (j < CHUNKS) ? ((hy << 16) | (hx << 8) | g) : -1;
+  }
+  int it = 0;
+  for (int t = cta; t < P.ntiles; t += P.cta_count) {
+    const int n = t / P.tiles_per_img;
+    const int r = t - n * P.tiles_per_img;
+    const int ty = r / P.tiles_x, tx = r - ty * P.tiles_x;
+    const int x0 = tx * T_TW - HALO, y0 = ty * T_TH - HALO;
+    const __half* origin = P.x + (static_cast<int64_t>(n) * P.H + y0) * P.W * P.in_pix_stride +
+                           static_cast<int64_t>(x0) * P.in_pix_stride;
+    for (int kc = 0; kc < P.nkc; ++kc, ++it) {
+      const int s = it % P.a_stages;
+      const uint32_t ph = (it / P.a_stages) & 1;
+      mbar_wait(bar_aempty + 8 * s, ph ^ 1);
+      const uint32_t a_s = a_base + s * P.a_stage_bytes;
+      const __half* src0 = origin + kc * (KG * 8);
+#pragma unroll
+      for (int i = 0; i < SLOTS; ++i) {
+        if (hyx[i] >= 0) {
+          const int hy = hyx[i] >> 16, hx = (hyx[i] >> 8) & 0xff, g = hyx[i] & 0xff;
+          const int iy = y0 + hy, ix = x0 + hx;
+          const bool ok = (static_cast<unsigned>(iy) < static_cast<unsigned>(P.H)) &&
+                          (static_cast<unsigned>(ix) < static_cast<unsigned>(P.W));
+          const uint32_t soff = static_cast<uint32_t>(g) * A_LBO + static_cast<uint32_t>(hy * HW + hx) * 16;
+          cp_async16(a_s + soff, ok ? static_cast<const void*>(src0 + goff[i]) : static_cast<const void*>(P.x),
+                     ok ? 16u : 0u);
+        }
+      }
+      cp_async_commit();
+      if (it >= look) {
+        if (look == 2) {
+          cp_async_wait<2>();
+        } else {
+          cp_async_wait<1>();
+        }
+        fence_proxy_async();
+        mbar_arrive(bar_afull + 8 * ((it - look) % P.a_stages));
+      }
+    }
+  }
+  cp_async_wait<0>();
+  fence_proxy_async();
+  for (int j = (it > look ? it - look : 0); j < it; ++j) mbar_arrive(bar_afull + 8 * (j % P.a_stages));
+}
+
+__global__ void __launch_bounds__(T_THREADS, 1) conv_halo_kernel(const __grid_constant__ HaloGroup G) {
   extern __shared__ __align__(1024) uint8_t smem[];
   int pi = 0;
   while (pi < G.nprob - 1 && static_cast<int>(blockIdx.x) >= G.p[pi].cta_begin + G.p[pi].cta_count) ++pi;
-  const TmaProblem& P = G.p[pi];
-  const CUtensorMap* amap = &G.amap[pi];
+  const HaloProblem& P = G.p[pi];
   const int cta = blockIdx.x - P.cta_begin;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
@@ -172,7 +227,6 @@ __global__ void __launch_bounds__(T_THREADS, 1) conv_tma_kernel(const __grid_con
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + 176);
   float* s_scale = reinterpret_cast<float*>(smem + 256);
   float* s_bias = reinterpret_cast<float*>(smem + 256 + 1024);
-  const uint32_t a_base = sbase + T_A_OFF;
   const uint32_t w_base = sbase + P.w_off;
 
   const int Npad = P.Npad;
@@ -181,7 +235,7 @@ __global__ void __launch_bounds__(T_THREADS, 1) conv_tma_kernel(const __grid_con
 
   if (tid == 0) {
     for (int i = 0; i < 4; ++i) {
-      mbar_init(bar_afull + 8 * i, 1);
+      mbar_init(bar_afull + 8 * i, T_NPROD);
       mbar_init(bar_aempty + 8 * i, 1);
       mbar_init(bar_wfull + 8 * i, 1);
       mbar_init(bar_wempty + 8 * i, 1);
@@ -192,9 +246,8 @@ __global__ void __launch_bounds__(T_THREADS, 1) conv_tma_kernel(const __grid_con
     }
     mbar_init(bar_wres, 1);
     fence_mbar_init();
-    prefetch_tmap(amap);
   }
-  if (warp == 3) {
+  if (warp == 5) {
     tmem_alloc(smem_u32(tmem_slot), ncols);
     tmem_relinquish();
   }
@@ -209,28 +262,20 @@ __global__ void __launch_bounds__(T_THREADS, 1) conv_tma_kernel(const __grid_con
 
   const int kg_per_stage = P.KCH >> 3;
 
-  if (warp == 0 && lane == 0) {
-    // ================================================= activation producer (TMA)
-    int s = 0;
-    uint32_t ph = 0;
-    for (int t = cta; t < P.ntiles; t += P.cta_count) {
-      const int n = t / P.tiles_per_img;
-      const int r = t - n * P.tiles_per_img;
-      const int ty = r / P.tiles_x, tx = r - ty * P.tiles_x;
-      const int x0 = tx * T_TW - P.halo, y0 = ty * T_TH - P.halo;
-      for (int kc = 0; kc < P.nkc; ++kc) {
-        mbar_wait(bar_aempty + 8 * s, ph ^ 1);
-        mbar_arrive_expect_tx(bar_afull + 8 * s, P.a_tx_bytes);
-        const uint32_t dst = a_base + s * P.a_stage_bytes;
-        tma_load_5d(dst, amap, 0, x0, y0, kc * kg_per_stage, n, bar_afull + 8 * s);
-        if (++s == P.a_stages) {
-          s = 0;
-          ph ^= 1;
-        }
-      }
+  const int variant = (P.ntaps == 9 ? 0 : 3) + (kg_per_stage == 6 ? 0 : kg_per_stage == 8 ? 1 : 2);
+  if (warp < 4) {
+    // ================================================= activation producers (cp.async halo gather)
+    switch (variant) {
+      case 0: producer_role<9, 6>(P, cta, sbase); break;
+      case 1: producer_role<9, 8>(P, cta, sbase); break;
+      case 2: producer_role<9, 12>(P, cta, sbase); break;
+      case 3: producer_role<1, 6>(P, cta, sbase); break;
+      case 4: producer_role<1, 8>(P, cta, sbase); break;
+      default: producer_role<1, 12>(P, cta, sbase); break;
     }
-  } else if (warp == 1 && lane == 0) {
-    // ================================================= weight producer (bulk copies)
+  } else if (warp == 4) {
+    if (lane == 0) {
+    // ================================================= weight producer (1-D bulk copies on the TMA unit)
     if (P.w_resident) {
       mbar_arrive_expect_tx(bar_wres, P.w_total_bytes);
       for (uint32_t off = 0; off < P.w_total_bytes; off += 16384) {
@@ -256,10 +301,10 @@ __global__ void __launch_bounds__(T_THREADS, 1) conv_tma_kernel(const __grid_con
         }
       }
     }
-  } else if (warp == 2) {
+    }
+  } else if (warp == 5) {
     // ================================================= MMA issuer (whole warp runs the loop, one lane issues)
-    const int sel = P.ntaps == 9 ? 0 : 3;
-    switch (sel + (kg_per_stage == 6 ? 0 : kg_per_stage == 8 ? 1 : 2)) {
+    switch (variant) {
       case 0: mma_role<9, 3>(P, cta, sbase, tmem_base, ncols); break;
       case 1: mma_role<9, 4>(P, cta, sbase, tmem_base, ncols); break;
       case 2: mma_role<9, 6>(P, cta, sbase, tmem_base, ncols); break;
@@ -267,12 +312,12 @@ __global__ void __launch_bounds__(T_THREADS, 1) conv_tma_kernel(const __grid_con
       case 4: mma_role<1, 4>(P, cta, sbase, tmem_base, ncols); break;
       default: mma_role<1, 6>(P, cta, sbase, tmem_base, ncols); break;
     }
-  } else if (warp >= 4) {
+  } else {
     // ================================================= epilogue: 8 warps, two per TMEM lane quadrant, each
     // owning half of the output channels of its 32 rows; residual loads are issued before the accumulator
     // wait so their latency hides behind the MMAs of the tile.
-    const int ew = warp - 4;
-    const int quad = ew & 3;               // == warp % 4: the TMEM lanes this warp may read
+    const int ew = warp - 6;
+    const int quad = warp & 3;             // warp % 4: the TMEM lanes this warp may read
     const int row = quad * 32 + lane;
     const int ty_in = row >> 3, tx_in = row & 7;
     const int Cout = P.Cout;
@@ -380,52 +425,10 @@ __global__ void __launch_bounds__(T_THREADS, 1) conv_tma_kernel(const __grid_con
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 3) tmem_dealloc(tmem_base, ncols);
+  if (warp == 5) tmem_dealloc(tmem_base, ncols);
 }
 
 // ------------------------------------------------------------------------------------------------ host
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-static EncodeTiledFn get_encode() {
-  static EncodeTiledFn fn = nullptr;
-  static bool tried = false;
-  if (!tried) {
-    tried = true;
-    void* p = nullptr;
-    cudaDriverEntryPointQueryResult q;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
-        q == cudaDriverEntryPointSuccess)
-      fn = reinterpret_cast<EncodeTiledFn>(p);
-  }
-  return fn;
-}
-
-static int encode_amap(CUtensorMap* map, const void* x, int NB, int H, int W, int C, int pix_stride, int hw, int hh,
-                       int kch) {
-  EncodeTiledFn enc = get_encode();
-  if (!enc) {
-    set_error("cuTensorMapEncodeTiled entry point unavailable");
-    return I2R_E_DEVICE;
-  }
-  // 5-D view of the NHWC tensor: (8 channels, x, y, channel group, image); the group dimension has a
-  // 16-byte stride, so one box lands in shared memory as [group][y][x][8 ch] = the UMMA core-matrix order.
-  const cuuint64_t pb = static_cast<cuuint64_t>(pix_stride) * 2;
-  const cuuint32_t ones[5] = {1, 1, 1, 1, 1};
-  const cuuint64_t dims[5] = {8, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)(C / 8), (cuuint64_t)NB};
-  const cuuint64_t strides[4] = {pb, pb * W, 16, pb * W * H};
-  const cuuint32_t box[5] = {8, (cuuint32_t)hw, (cuuint32_t)hh, (cuuint32_t)(kch / 8), 1};
-  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 5, const_cast<void*>(x), dims, strides, box, ones,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) {
-    set_error("cuTensorMapEncodeTiled failed (%d) for [%d,%d,%d,%d] pix_stride %d", (int)r, NB, H, W, C, pix_stride);
-    return I2R_E_DEVICE;
-  }
-  return 0;
-}
-
 static bool is_std3x3(const i2r_conv_problem& P) {
   if (P.ntaps != 9) return false;
   for (int t = 0; t < 9; ++t)
@@ -435,7 +438,7 @@ static bool is_std3x3(const i2r_conv_problem& P) {
 
 }  // namespace i2r
 
-extern "C" int i2r_conv_tma_supported(const i2r_conv_problem* P) {
+extern "C" int i2r_conv_halo_supported(const i2r_conv_problem* P) {
   using namespace i2r;
   if (!P) return 0;
   const bool k1 = P->ntaps == 1 && P->dy[0] == 0 && P->dx[0] == 0;
@@ -453,10 +456,10 @@ extern "C" int i2r_conv_tma_supported(const i2r_conv_problem* P) {
   return 1;
 }
 
-extern "C" int i2r_conv_tma(const i2r_conv_problem* probs, int nprob, void* stream) {
+extern "C" int i2r_conv_halo(const i2r_conv_problem* probs, int nprob, void* stream) {
   using namespace i2r;
   if (!probs || nprob < 1 || nprob > I2R_MAX_GROUP) {
-    set_error("i2r_conv_tma: nprob=%d out of range", nprob);
+    set_error("i2r_conv_halo: nprob=%d out of range", nprob);
     return I2R_E_BADARG;
   }
   static int num_sms = 0;
@@ -465,7 +468,7 @@ extern "C" int i2r_conv_tma(const i2r_conv_problem* probs, int nprob, void* stre
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
   }
-  TmaGroup G;
+  HaloGroup G;
   memset(&G, 0, sizeof(G));
   G.nprob = nprob;
   double cost[I2R_MAX_GROUP];
@@ -474,15 +477,16 @@ extern "C" int i2r_conv_tma(const i2r_conv_problem* probs, int nprob, void* stre
   uint32_t smem_need = 0;
   for (int i = 0; i < nprob; ++i) {
     const i2r_conv_problem& S = probs[i];
-    if (!i2r_conv_tma_supported(&S)) {
-      set_error("i2r_conv_tma: problem %d is not a stride-1 3x3 / 1x1 problem this kernel supports", i);
+    if (!i2r_conv_halo_supported(&S)) {
+      set_error("i2r_conv_halo: problem %d is not a stride-1 3x3 / 1x1 problem this kernel supports", i);
       return I2R_E_UNSUPPORTED;
     }
     if (!S.x || !S.w || !S.scale || !S.bias || !S.y) {
-      set_error("i2r_conv_tma: problem %d: null pointer", i);
+      set_error("i2r_conv_halo: problem %d: null pointer", i);
       return I2R_E_BADARG;
     }
-    TmaProblem& P = G.p[i];
+    HaloProblem& P = G.p[i];
+    P.x = static_cast<const __half*>(S.x);
     P.w = static_cast<const uint8_t*>(S.w);
     P.scale = S.scale;
     P.bias = S.bias;
@@ -511,11 +515,12 @@ extern "C" int i2r_conv_tma(const i2r_conv_problem* probs, int nprob, void* stre
     P.tiles_x = (P.W + T_TW - 1) / T_TW;
     P.tiles_per_img = P.tiles_x * ((P.H + T_TH - 1) / T_TH);
     P.ntiles = P.tiles_per_img * P.NB;
+    P.in_pix_stride = S.in_pix_stride;
     P.out_pix_stride = S.out_pix_stride;
     P.add_pix_stride = S.add_pix_stride;
     P.flags = S.flags;
     const int hw = T_TW + 2 * P.halo, hh = T_TH + 2 * P.halo;
-    P.a_tx_bytes = static_cast<uint32_t>((P.KCH / 8) * hh * hw * 16);
+    P.a_tx_bytes = static_cast<uint32_t>((P.KCH / 8) * (hh * hw * 16 + 16));
     P.a_stage_bytes = (P.a_tx_bytes + 127u) & ~127u;
     P.w_total_bytes = static_cast<uint32_t>(S.ntaps) * (S.Cin / 8) * S.Npad * 16;
     P.w_resident = P.w_total_bytes <= T_W_RES_MAX ? 1 : 0;
@@ -532,16 +537,15 @@ extern "C" int i2r_conv_tma(const i2r_conv_problem* probs, int nprob, void* stre
     int astg = static_cast<int>((T_MAX_SMEM - T_A_OFF - wregion) / P.a_stage_bytes);
     if (astg > 4) astg = 4;
     if (astg < 2) {
-      set_error("i2r_conv_tma: problem %d does not fit shared memory (A stage %u B, W region %u B)", i,
+      set_error("i2r_conv_halo: problem %d does not fit shared memory (A stage %u B, W region %u B)", i,
                 P.a_stage_bytes, wregion);
       return I2R_E_UNSUPPORTED;
     }
     P.a_stages = astg;
+    P.look = astg >= 3 ? 2 : 1;
     P.w_off = T_A_OFF + static_cast<uint32_t>(astg) * P.a_stage_bytes;
     const uint32_t need = P.w_off + wregion;
     if (need > smem_need) smem_need = need;
-    int rc = encode_amap(&G.amap[i], S.x, P.NB, P.H, P.W, P.C, S.in_pix_stride, hw, hh, P.KCH);
-    if (rc) return rc;
     cost[i] = static_cast<double>(P.ntiles) * S.ntaps * S.Cin * (S.Npad < 64 ? 64 : S.Npad);
     total_cost += cost[i];
     total_tiles += P.ntiles;
@@ -589,13 +593,13 @@ extern "C" int i2r_conv_tma(const i2r_conv_problem* probs, int nprob, void* stre
   }
   static bool attr_done = false;
   if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(conv_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, T_MAX_SMEM);
+    cudaError_t e = cudaFuncSetAttribute(conv_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, T_MAX_SMEM);
     if (e != cudaSuccess) {
-      set_error("cudaFuncSetAttribute(conv_tma): %s", cudaGetErrorString(e));
+      set_error("cudaFuncSetAttribute(conv_halo): %s", cudaGetErrorString(e));
       return static_cast<int>(e);
     }
     attr_done = true;
   }
-  conv_tma_kernel<<<begin, T_THREADS, smem_need, static_cast<cudaStream_t>(stream)>>>(G);
-  return check_launch("conv_tma_kernel");
+  conv_halo_kernel<<<begin, T_THREADS, smem_need, static_cast<cudaStream_t>(stream)>>>(G);
+  return check_launch("conv_halo_kernel");
 }

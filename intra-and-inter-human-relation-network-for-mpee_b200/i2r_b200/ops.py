@@ -164,13 +164,13 @@ class Runner:
             e0.record()
         tma, gen = [], []
         for p in problems:
-            (tma if (self.use_tma and self.lib.i2r_conv_tma_supported(ctypes.byref(p))) else gen).append(p)
+            (tma if (self.use_tma and self.lib.i2r_conv_halo_supported(ctypes.byref(p))) else gen).append(p)
         for group, fn in ((tma, "tma"), (gen, "igemm")):
             for i in range(0, len(group), capi.I2R_MAX_GROUP):
                 chunk = group[i:i + capi.I2R_MAX_GROUP]
                 arr = (capi.ConvProblem * len(chunk))(*chunk)
                 if fn == "tma":
-                    capi.check(self.lib.i2r_conv_tma(arr, len(chunk), _stream_ptr()), "i2r_conv_tma")
+                    capi.check(self.lib.i2r_conv_halo(arr, len(chunk), _stream_ptr()), "i2r_conv_halo")
                 else:
                     capi.check(self.lib.i2r_conv_igemm(arr, len(chunk), self.impl, _stream_ptr()), "i2r_conv_igemm")
                 self.launches += 1

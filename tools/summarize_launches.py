@@ -18,7 +18,7 @@ for k in sorted(tot, key=lambda k: -tot[k]):
 if len(sys.argv) > 2:
     i = 0
     for row in rows:
-        if "igemm" in row["Kernel Name"] or "conv_tma" in row["Kernel Name"]:
+        if "igemm" in row["Kernel Name"] or "conv_halo" in row["Kernel Name"]:
             print("%3d %-9s %-14s %8.1f" % (i, row["Kernel Name"][:9], row["Grid Size"], float(row["Metric Value"].replace(",", "")) / 1e3), end=" | ")
             i += 1
             if i % 4 == 0:
