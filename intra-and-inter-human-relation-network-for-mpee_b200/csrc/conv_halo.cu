@@ -3,11 +3,11 @@
 //
 //   tile        : 8 (x) by 16 (y) output pixels = 128 accumulator rows, all Npad output channels
 //   A operand   : per (tile, K-chunk) the (8+2) x (16+2) halo tile of KCH channels is staged ONCE in shared
-//                 memory as [k-group of 8 ch][halo y][halo x][8 x fp16] by four producer warps with
-//                 coalesced 16-byte cp.async (zero-fill outside the image = conv padding).  The nine
-//                 taps of a 3x3 filter are nine shifted windows of that single tile: the UMMA descriptor's
-//                 start address moves by ((dy*10+dx)*16 B), SBO = one halo row (160 B), LBO = one k-group
-//                 plane -- every activation byte is fetched once instead of nine times.
+//                 memory as SWIZZLE_128B rows -- one 128-byte row per halo pixel, 16 pixel slots per halo line
+//                 (10 used) -- by four producer warps with coalesced 16-byte cp.async (zero-fill outside the
+//                 image = conv padding).  The nine taps of a 3x3 filter are nine shifted windows of that
+//                 single tile: the UMMA descriptor's start address moves by (dy*16+dx)*128 B, SBO = one halo
+//                 line (2048 B), base_offset = dx -- every activation byte is fetched once instead of nine times.
 //                 (A 5-D TMA box can deposit exactly this layout, but its 16-byte inner rows were measured
 //                 at ~4 B/cycle/SM on B200 -- see profiles/ -- so cp.async feeds this operand.)
 //   B operand   : weights pre-packed in core-matrix order, moved by the TMA unit as 1-D bulk copies;
@@ -46,7 +46,7 @@ struct HaloProblem {
   int w_resident;
   uint32_t w_total_bytes, w_stage_bytes;
   uint32_t a_stage_bytes, a_tx_bytes;
-  int a_stages, w_stages, look;
+  int a_stages, w_stages, look, bo_mode;
   uint32_t w_off;      // byte offset of the weight region in dynamic smem
 };
 
@@ -59,7 +59,7 @@ constexpr int T_THREADS = 448;
 constexpr int T_NPROD = 128;
 constexpr int T_TW = 8, T_TH = 16;
 constexpr uint32_t T_A_OFF = 3072;          // dynamic smem: [0,256) barriers | [256,2304) scale,bias | A ring
-constexpr uint32_t T_MAX_SMEM = 225 * 1024;
+constexpr uint32_t T_MAX_SMEM = 226 * 1024;   // + 1 KB alignment slack = 227 KB opt-in limit
 constexpr uint32_t T_W_RES_MAX = 120 * 1024;
 
 // MMA issue loop.  Everything here is warp-uniform (kernel parameters, loop counters, shared-memory
@@ -70,22 +70,22 @@ __device__ __forceinline__ void mma_role(const HaloProblem& P, const int cta, co
                                          const uint32_t tmem_base, const uint32_t ncols) {
   constexpr int HALO = NTAPS == 9 ? 1 : 0;
   constexpr int HW = T_TW + 2 * HALO, HH = T_TH + 2 * HALO;
-  constexpr uint32_t A_LBO = HH * HW * 16 + 16, A_SBO = HW * 16;   // +16: bank spread for the producers
+  constexpr int PW = HALO ? 16 : 8;
+  constexpr uint32_t A_SBO = PW * 128;
   const uint32_t bar_afull = sbase, bar_aempty = sbase + 32, bar_wfull = sbase + 64, bar_wempty = sbase + 96;
   const uint32_t bar_accfull = sbase + 128, bar_accempty = sbase + 144, bar_wres = sbase + 160;
   const uint32_t a_base = sbase + T_A_OFF;
   const uint32_t w_base = sbase + P.w_off;
   const int Npad = P.Npad;
   const uint32_t idesc = make_idesc_f16(128, Npad);
-  const uint32_t b_lbo = static_cast<uint32_t>(Npad) * 16;
-  const uint32_t a_hi = smem_desc_hi(A_SBO), b_hi = smem_desc_hi(128);
-  const uint32_t b_k2 = (2 * b_lbo) >> 4;                                   // one K=16 step, descriptor units
-  const uint32_t b_tap = (static_cast<uint32_t>(P.C >> 3) * b_lbo) >> 4;   // resident: next tap
-  const uint32_t b_kc = (static_cast<uint32_t>(2 * KG2) * b_lbo) >> 4;     // resident: next K-chunk
-  const uint32_t w_lo0 = smem_desc_lo(w_base, b_lbo);
-  const uint32_t w_stage16 = P.w_stage_bytes >> 4;
+  const uint32_t b_hi = sw128_desc_hi(1024, 0);
+  const uint32_t bo_on = P.bo_mode ? 1u : 0u;   // descriptor base_offset for dx-shifted windows (debug switch)
+  const uint32_t a_hi_dx[3] = {sw128_desc_hi(A_SBO, 0), sw128_desc_hi(A_SBO, bo_on * 1u), sw128_desc_hi(A_SBO, bo_on * 2u)};
+  const uint32_t w_stage16 = P.w_stage_bytes >> 4;                         // one (tap, K-chunk) block = Npad rows x 128 B
+  const uint32_t b_tap = static_cast<uint32_t>(P.nkc) * w_stage16;         // resident: next tap
+  const uint32_t w_lo0 = sw128_desc_lo(w_base);
   const uint32_t a_stage16 = P.a_stage_bytes >> 4;
-  const uint32_t a_lo0 = smem_desc_lo(a_base, A_LBO);
+  const uint32_t a_lo0 = sw128_desc_lo(a_base);
   const bool resident = P.w_resident != 0;
   const bool leader = elect_one();
   int as = 0, ws = 0, acc = 0;
@@ -100,17 +100,17 @@ __device__ __forceinline__ void mma_role(const HaloProblem& P, const int cta, co
       mbar_wait(bar_afull + 8 * as, aph);
       tc_fence_after();
       const uint32_t a_lo = a_lo0 + as * a_stage16;
-      const uint32_t b_lo_kc = w_lo0 + kc * b_kc;
+      const uint32_t b_lo_kc = w_lo0 + kc * w_stage16;
       if (resident) {
 #pragma unroll
         for (int tap = 0; tap < NTAPS; ++tap) {
           const uint32_t b_lo = b_lo_kc + tap * b_tap;
-          const uint32_t a_t = a_lo + (HALO ? static_cast<uint32_t>((tap / 3) * HW + (tap % 3)) : 0u);
+          const uint32_t a_t = a_lo + (HALO ? static_cast<uint32_t>(((tap / 3) * PW + (tap % 3)) * 8) : 0u);
+          const uint32_t a_hi = a_hi_dx[HALO ? tap % 3 : 0];
 #pragma unroll
           for (int k2 = 0; k2 < KG2; ++k2) {
             if (leader)
-              umma_f16(d_tmem, desc64(a_t + k2 * ((2 * A_LBO) >> 4), a_hi), desc64(b_lo + k2 * b_k2, b_hi), idesc,
-                       accum);
+              umma_f16(d_tmem, desc64(a_t + k2 * 2, a_hi), desc64(b_lo + k2 * 2, b_hi), idesc, accum);
             accum = 1;
           }
         }
@@ -120,12 +120,12 @@ __device__ __forceinline__ void mma_role(const HaloProblem& P, const int cta, co
           mbar_wait(bar_wfull + 8 * ws, wph);
           tc_fence_after();
           const uint32_t b_lo = w_lo0 + ws * w_stage16;
-          const uint32_t a_t = a_lo + (HALO ? static_cast<uint32_t>((tap / 3) * HW + (tap % 3)) : 0u);
+          const uint32_t a_t = a_lo + (HALO ? static_cast<uint32_t>(((tap / 3) * PW + (tap % 3)) * 8) : 0u);
+          const uint32_t a_hi = a_hi_dx[HALO ? tap % 3 : 0];
 #pragma unroll
           for (int k2 = 0; k2 < KG2; ++k2) {
             if (leader)
-              umma_f16(d_tmem, desc64(a_t + k2 * ((2 * A_LBO) >> 4), a_hi), desc64(b_lo + k2 * b_k2, b_hi), idesc,
-                       accum);
+              umma_f16(d_tmem, desc64(a_t + k2 * 2, a_hi), desc64(b_lo + k2 * 2, b_hi), idesc, accum);
             accum = 1;
           }
           if (leader) umma_commit(bar_wempty + 8 * ws);
@@ -156,7 +156,7 @@ __device__ __forceinline__ void producer_role(const HaloProblem& P, const int ct
   constexpr int HW = T_TW + 2 * HALO, HH = T_TH + 2 * HALO;
   constexpr int CHUNKS = HH * HW * KG;
   constexpr int SLOTS = (CHUNKS + T_NPROD - 1) / T_NPROD;
-  constexpr uint32_t A_LBO = HH * HW * 16 + 16;
+  constexpr int PW = HALO ? 16 : 8;   // pixel slots per halo line in shared memory (keeps 8-row groups 1024-B aligned)
   const uint32_t bar_afull = sbase, bar_aempty = sbase + 32;
   const uint32_t a_base = sbase + T_A_OFF;
   const int tid = threadIdx.x;
@@ -191,7 +191,7 @@ __device__ __forceinline__ void producer_role(const HaloProblem& P, const int ct
           const int iy = y0 + hy, ix = x0 + hx;
           const bool ok = (static_cast<unsigned>(iy) < static_cast<unsigned>(P.H)) &&
                           (static_cast<unsigned>(ix) < static_cast<unsigned>(P.W));
-          const uint32_t soff = static_cast<uint32_t>(g) * A_LBO + static_cast<uint32_t>(hy * HW + hx) * 16;
+          const uint32_t soff = sw128_off(static_cast<uint32_t>(hy * PW + hx), static_cast<uint32_t>(g));
           cp_async16(a_s + soff, ok ? static_cast<const void*>(src0 + goff[i]) : static_cast<const void*>(P.x),
                      ok ? 16u : 0u);
         }
@@ -214,7 +214,8 @@ __device__ __forceinline__ void producer_role(const HaloProblem& P, const int ct
 }
 
 __global__ void __launch_bounds__(T_THREADS, 1) conv_halo_kernel(const __grid_constant__ HaloGroup G) {
-  extern __shared__ __align__(1024) uint8_t smem[];
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // SW128 tiles need 1024-B alignment
   int pi = 0;
   while (pi < G.nprob - 1 && static_cast<int>(blockIdx.x) >= G.p[pi].cta_begin + G.p[pi].cta_count) ++pi;
   const HaloProblem& P = G.p[pi];
@@ -262,16 +263,14 @@ __global__ void __launch_bounds__(T_THREADS, 1) conv_halo_kernel(const __grid_co
 
   const int kg_per_stage = P.KCH >> 3;
 
-  const int variant = (P.ntaps == 9 ? 0 : 3) + (kg_per_stage == 6 ? 0 : kg_per_stage == 8 ? 1 : 2);
+  const int variant = (P.ntaps == 9 ? 0 : 2) + (kg_per_stage == 6 ? 0 : 1);   // KCH is 48 or 64
   if (warp < 4) {
     // ================================================= activation producers (cp.async halo gather)
     switch (variant) {
       case 0: producer_role<9, 6>(P, cta, sbase); break;
       case 1: producer_role<9, 8>(P, cta, sbase); break;
-      case 2: producer_role<9, 12>(P, cta, sbase); break;
-      case 3: producer_role<1, 6>(P, cta, sbase); break;
-      case 4: producer_role<1, 8>(P, cta, sbase); break;
-      default: producer_role<1, 12>(P, cta, sbase); break;
+      case 2: producer_role<1, 6>(P, cta, sbase); break;
+      default: producer_role<1, 8>(P, cta, sbase); break;
     }
   } else if (warp == 4) {
     if (lane == 0) {
@@ -307,10 +306,8 @@ __global__ void __launch_bounds__(T_THREADS, 1) conv_halo_kernel(const __grid_co
     switch (variant) {
       case 0: mma_role<9, 3>(P, cta, sbase, tmem_base, ncols); break;
       case 1: mma_role<9, 4>(P, cta, sbase, tmem_base, ncols); break;
-      case 2: mma_role<9, 6>(P, cta, sbase, tmem_base, ncols); break;
-      case 3: mma_role<1, 3>(P, cta, sbase, tmem_base, ncols); break;
-      case 4: mma_role<1, 4>(P, cta, sbase, tmem_base, ncols); break;
-      default: mma_role<1, 6>(P, cta, sbase, tmem_base, ncols); break;
+      case 2: mma_role<1, 3>(P, cta, sbase, tmem_base, ncols); break;
+      default: mma_role<1, 4>(P, cta, sbase, tmem_base, ncols); break;
     }
   } else {
     // ================================================= epilogue: 8 warps, two per TMEM lane quadrant, each
@@ -429,6 +426,8 @@ __global__ void __launch_bounds__(T_THREADS, 1) conv_halo_kernel(const __grid_co
 }
 
 // ------------------------------------------------------------------------------------------------ host
+static int g_bo_mode = 1;   // I2R_DESC_BASE_OFFSET=0 disables the descriptor base_offset (hardware bring-up switch)
+
 static bool is_std3x3(const i2r_conv_problem& P) {
   if (P.ntaps != 9) return false;
   for (int t = 0; t < 9; ++t)
@@ -447,10 +446,7 @@ extern "C" int i2r_conv_halo_supported(const i2r_conv_problem* P) {
   if (P->OH != P->IH || P->OW != P->IW || P->OHf != P->OH || P->OWf != P->OW) return 0;
   if ((P->add0 && P->add0_shift != 0) || (P->add1 && P->add1_shift != 0)) return 0;
   if (P->Cin % 16 != 0 || P->Npad > 256 || P->Npad % 16 != 0) return 0;
-  const int kch = P->Cin <= 96 ? P->Cin : P->KC;
-  if (P->Cin % kch != 0) return 0;
-  const uint32_t wtot = static_cast<uint32_t>(P->ntaps) * (P->Cin / 8) * P->Npad * 16;
-  if (wtot > T_W_RES_MAX && kch != P->KC) return 0;
+  if ((P->KC != 48 && P->KC != 64) || P->Cin % P->KC != 0) return 0;
   if (P->in_pix_stride % 8 != 0) return 0;
   if ((P->add0 || P->add1) && (P->add_pix_stride % 8 != 0 || P->add_pix_stride < P->Cout)) return 0;
   return 1;
@@ -467,6 +463,8 @@ extern "C" int i2r_conv_halo(const i2r_conv_problem* probs, int nprob, void* str
     int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+    const char* e = getenv("I2R_DESC_BASE_OFFSET");
+    if (e && e[0] == '0') g_bo_mode = 0;
   }
   HaloGroup G;
   memset(&G, 0, sizeof(G));
@@ -508,7 +506,7 @@ extern "C" int i2r_conv_halo(const i2r_conv_problem* probs, int nprob, void* str
     P.C = S.Cin;
     P.Cout = S.Cout;
     P.Npad = S.Npad;
-    P.KCH = S.Cin <= 96 ? S.Cin : S.KC;
+    P.KCH = S.KC;
     P.nkc = S.Cin / P.KCH;
     P.kgp = S.KC / 8;
     P.nchp = S.Cin / S.KC;
@@ -520,11 +518,11 @@ extern "C" int i2r_conv_halo(const i2r_conv_problem* probs, int nprob, void* str
     P.add_pix_stride = S.add_pix_stride;
     P.flags = S.flags;
     const int hw = T_TW + 2 * P.halo, hh = T_TH + 2 * P.halo;
-    P.a_tx_bytes = static_cast<uint32_t>((P.KCH / 8) * (hh * hw * 16 + 16));
-    P.a_stage_bytes = (P.a_tx_bytes + 127u) & ~127u;
-    P.w_total_bytes = static_cast<uint32_t>(S.ntaps) * (S.Cin / 8) * S.Npad * 16;
+    P.a_tx_bytes = static_cast<uint32_t>(hh * (P.halo ? 16 : 8) * 128);
+    P.a_stage_bytes = P.a_tx_bytes;   // multiple of 1024
+    P.w_total_bytes = static_cast<uint32_t>(S.ntaps) * (S.Cin / S.KC) * S.Npad * 128;
     P.w_resident = P.w_total_bytes <= T_W_RES_MAX ? 1 : 0;
-    P.w_stage_bytes = static_cast<uint32_t>(P.kgp) * S.Npad * 16;
+    P.w_stage_bytes = static_cast<uint32_t>(S.Npad) * 128;
     uint32_t wregion;
     if (P.w_resident) {
       P.w_stages = 1;
@@ -543,6 +541,7 @@ extern "C" int i2r_conv_halo(const i2r_conv_problem* probs, int nprob, void* str
     }
     P.a_stages = astg;
     P.look = astg >= 3 ? 2 : 1;
+    P.bo_mode = g_bo_mode;
     P.w_off = T_A_OFF + static_cast<uint32_t>(astg) * P.a_stage_bytes;
     const uint32_t need = P.w_off + wregion;
     if (need > smem_need) smem_need = need;
@@ -593,13 +592,13 @@ extern "C" int i2r_conv_halo(const i2r_conv_problem* probs, int nprob, void* str
   }
   static bool attr_done = false;
   if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(conv_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, T_MAX_SMEM);
+    cudaError_t e = cudaFuncSetAttribute(conv_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, T_MAX_SMEM + 1024);
     if (e != cudaSuccess) {
       set_error("cudaFuncSetAttribute(conv_halo): %s", cudaGetErrorString(e));
       return static_cast<int>(e);
     }
     attr_done = true;
   }
-  conv_halo_kernel<<<begin, T_THREADS, smem_need, static_cast<cudaStream_t>(stream)>>>(G);
+  conv_halo_kernel<<<begin, T_THREADS, smem_need + 1024, static_cast<cudaStream_t>(stream)>>>(G);
   return check_launch("conv_halo_kernel");
 }

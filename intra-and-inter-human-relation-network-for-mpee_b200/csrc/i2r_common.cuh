@@ -131,6 +131,18 @@ __device__ __forceinline__ uint32_t make_idesc_f16(int M, int N) {
   return (1u << 4) | (static_cast<uint32_t>(N >> 3) << 17) | (static_cast<uint32_t>(M >> 4) << 24);
 }
 
+// ---- SWIZZLE_128B K-major operands (the full-rate shared-memory path of the tensor core) ----------------
+// A row (one pixel / one output channel) is 128 B = 64 fp16 of K; rows are 128 B apart, 8-row groups SBO bytes
+// apart; inside a row the eight 16-byte chunks are XOR-ed with (row address >> 7) & 7.  One K=16 MMA step
+// consumes 32 B of every row: advance the start address by 32 B.  base_offset = (start >> 7) & 7 when the
+// start address is not 1024-byte aligned (shifted conv windows).
+__device__ __forceinline__ uint32_t sw128_desc_lo(uint32_t saddr) { return ((saddr >> 4) & 0x3FFFu) | (1u << 16); }
+__device__ __forceinline__ uint32_t sw128_desc_hi(uint32_t sbo_bytes, uint32_t base_offset) {
+  return ((sbo_bytes >> 4) & 0x3FFFu) | (1u << 14) | ((base_offset & 7u) << 17) | (2u << 29);
+}
+// byte offset of 16-byte chunk `c` of row `row` inside a 1024-byte-aligned SW128 tile with 128-byte rows
+__device__ __forceinline__ uint32_t sw128_off(uint32_t row, uint32_t c) { return row * 128u + ((c ^ (row & 7u)) << 4); }
+
 // Split form for hot issue loops: `hi` is loop-invariant, `lo` = (addr >> 4) | (LBO >> 4) << 16 advances by
 // plain 32-bit adds of (byte_offset >> 4).
 __device__ __forceinline__ uint32_t smem_desc_lo(uint32_t saddr, uint32_t lbo_bytes) {

@@ -8,9 +8,10 @@
 // arrives with one 1-D bulk copy (TMA unit) per pipeline stage.  Stages form an mbarrier ring
 // (full[]: 128 producer arrivals + 1 expect_tx arrival; empty[]: tcgen05.commit).
 //
-// Shared-memory operand layout (K-major, no swizzle): [k-group of 8 channels][row][8 x fp16]; one core
-// matrix = 8 consecutive rows x 16 B.  A uses a k-group stride of 128*16+16 bytes so that the eight
-// 16-byte cp.async writes of a quarter-warp (same pixel, consecutive k-groups) hit distinct banks.
+// Shared-memory operand layout: SWIZZLE_128B K-major -- one 128-byte row per output pixel (A) or per
+// output channel (B) holding the K-chunk's channels (48 or 64 real, zero-padded to 64 slots for B; A's pad
+// slots are never read because only KC/16 K-steps are issued); the 16-byte chunks of a row are XOR-ed
+// with (row & 7), which also makes the producers' cp.async writes bank-conflict free.
 #include <cstdio>
 
 #include "i2r_common.cuh"
@@ -26,12 +27,11 @@ struct ConvGroup {
 constexpr int BM = 128;
 constexpr int NPROD = 128;
 constexpr int NTHREADS = 160;
-constexpr int A_KG_STRIDE = BM * 16 + 16;  // bytes between k-groups of the A stage (padded: bank spread)
-constexpr int SMEM_HDR = 2304;             // barriers (<=128 B) | tmem ptr | scale[256] | bias[256]
+constexpr int A_STAGE = BM * 128;           // one 128-byte swizzled row per output pixel
+constexpr int SMEM_HDR = 3072;             // barriers (<=128 B) | tmem ptr | scale[256] | bias[256]; stages 1024-aligned
 constexpr int SMEM_SCALE_OFF = 256;
 constexpr int SMEM_BIAS_OFF = 256 + 1024;
 
-__device__ __forceinline__ int stage_bytes(int KG, int Npad) { return KG * A_KG_STRIDE + KG * Npad * 16; }
 
 template <int KG, int STAGES>
 __device__ __forceinline__ void run_tile(const i2r_conv_problem& P, const int tile, uint8_t* smem) {
@@ -49,8 +49,8 @@ __device__ __forceinline__ void run_tile(const i2r_conv_problem& P, const int ti
   float* s_bias = reinterpret_cast<float*>(smem + SMEM_BIAS_OFF);
 
   const int Npad = P.Npad;
-  const int a_bytes = KG * A_KG_STRIDE;
-  const int b_bytes = KG * Npad * 16;
+  const int a_bytes = A_STAGE;
+  const int b_bytes = Npad * 128;
   const int st_bytes = a_bytes + b_bytes;
   const uint32_t stages0 = sbase + SMEM_HDR;
 
@@ -103,7 +103,7 @@ __device__ __forceinline__ void run_tile(const i2r_conv_problem& P, const int ti
       const int row = j / KG;
       const int g = j - row * KG;
       r_g[i] = g;
-      r_dst[i] = g * A_KG_STRIDE + row * 16;
+      r_dst[i] = sw128_off(row, g);
       const int p = tile * BM + row;
       if (p < M) {
         const int n = p / ohow;
@@ -263,12 +263,10 @@ __device__ __forceinline__ void run_tile(const i2r_conv_problem& P, const int ti
   } else {
     // =============================================================== MMA issuer (warp-uniform loop, one lane issues)
     const uint32_t idesc = make_idesc_f16(BM, Npad);
-    const uint32_t b_lbo = static_cast<uint32_t>(Npad) * 16;
-    const uint32_t a_hi = smem_desc_hi(128), b_hi = smem_desc_hi(128);
-    const uint32_t a_lo0 = smem_desc_lo(stages0, A_KG_STRIDE);
-    const uint32_t b_lo0 = smem_desc_lo(stages0 + a_bytes, b_lbo);
+    const uint32_t a_hi = sw128_desc_hi(1024, 0), b_hi = a_hi;
+    const uint32_t a_lo0 = sw128_desc_lo(stages0);
+    const uint32_t b_lo0 = sw128_desc_lo(stages0 + a_bytes);
     const uint32_t st16 = static_cast<uint32_t>(st_bytes) >> 4;
-    const uint32_t b_k2 = (2 * b_lbo) >> 4;
     const bool leader = elect_one();
     uint32_t accum = 0;
     for (int it = 0; it < niter; ++it) {
@@ -280,8 +278,7 @@ __device__ __forceinline__ void run_tile(const i2r_conv_problem& P, const int ti
 #pragma unroll
       for (int k = 0; k < KG / 2; ++k) {
         if (leader)
-          umma_f16(tmem_base, desc64(a_lo + k * ((2 * A_KG_STRIDE) >> 4), a_hi), desc64(b_lo + k * b_k2, b_hi), idesc,
-                   accum);
+          umma_f16(tmem_base, desc64(a_lo + k * 2, a_hi), desc64(b_lo + k * 2, b_hi), idesc, accum);
         accum = 1;
       }
       if (leader) umma_commit(bar_empty + 8 * s);
@@ -297,7 +294,8 @@ __device__ __forceinline__ void run_tile(const i2r_conv_problem& P, const int ti
 
 template <int STAGES>
 __global__ void __launch_bounds__(NTHREADS) igemm_tc_kernel(const __grid_constant__ ConvGroup G) {
-  extern __shared__ __align__(128) uint8_t smem[];
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // SW128 tiles need 1024-B alignment
   int tile = blockIdx.x;
   int pi = 0;
   while (pi < G.nprob - 1 && tile >= G.tile_end[pi]) ++pi;
@@ -329,7 +327,6 @@ __global__ void __launch_bounds__(128) igemm_check_kernel(const __grid_constant_
   const int oyf = oy * P.out_mul + P.out_offy, oxf = ox * P.out_mul + P.out_offx;
   const int sh = P.in_shift;
   const int IHs = P.IH >> sh, IWs = P.IW >> sh;
-  const int KG = P.KC / 8;
   const int nchunks = P.Cin / P.KC;
   const __half* X = reinterpret_cast<const __half*>(P.x);
   const __half* Wp = reinterpret_cast<const __half*>(P.w);
@@ -344,7 +341,7 @@ __global__ void __launch_bounds__(128) igemm_check_kernel(const __grid_constant_
       const __half* xp = X + (static_cast<int64_t>(n * IHs + (iy >> sh)) * IWs + (ix >> sh)) * P.in_pix_stride;
       for (int c = 0; c < P.Cin; ++c) {
         const int ch = c / P.KC, g = (c % P.KC) / 8, e = c % 8;
-        const int64_t wi = ((static_cast<int64_t>(t * nchunks + ch) * KG + g) * P.Npad + co) * 8 + e;
+        const int64_t wi = (static_cast<int64_t>(t * nchunks + ch) * P.Npad + co) * 64 + ((g ^ (co & 7)) << 3) + e;
         acc += __half2float(xp[c]) * __half2float(Wp[wi]);
       }
     }
@@ -447,8 +444,7 @@ extern "C" int i2r_conv_igemm(const i2r_conv_problem* probs, int nprob, int impl
     const int64_t M = static_cast<int64_t>(probs[i].NB) * probs[i].OH * probs[i].OW;
     tiles += static_cast<int>((M + BM - 1) / BM);
     G.tile_end[i] = tiles;
-    const int KG = probs[i].KC / 8;
-    const int sb = KG * A_KG_STRIDE + KG * probs[i].Npad * 16;
+    const int sb = A_STAGE + probs[i].Npad * 128;
     if (sb > max_stage) max_stage = sb;
   }
   for (int i = nprob; i < I2R_MAX_GROUP; ++i) G.tile_end[i] = tiles;
@@ -464,7 +460,7 @@ extern "C" int i2r_conv_igemm(const i2r_conv_problem* probs, int nprob, int impl
   int stages = (96 * 1024) / max_stage;
   if (stages > 4) stages = 4;
   if (stages < 2) stages = 2;
-  const size_t smem = SMEM_HDR + static_cast<size_t>(stages) * max_stage;
+  const size_t smem = 1024 + SMEM_HDR + static_cast<size_t>(stages) * max_stage;
   switch (stages) {
     case 2: return launch_tc<2>(G, tiles, smem, st);
     case 3: return launch_tc<3>(G, tiles, smem, st);

@@ -28,7 +28,7 @@ class ConvLayer:
 
     @property
     def weight_bytes(self):
-        return self.ntaps * self.cin * self.npad * 2
+        return self.w.numel() * 2
 
     def halves(self):
         """Two layers producing output channels [0, Cout/2) and [Cout/2, Cout) (N-split for the TMA kernel:
@@ -40,7 +40,7 @@ class ConvLayer:
                 sub = ConvLayer.__new__(ConvLayer)
                 sub.__dict__.update(self.__dict__)
                 sub.cout, sub.npad = h, h
-                sub.w = self.w[:, :, :, c0:c0 + h, :].contiguous()
+                sub.w = self.w[:, :, c0:c0 + h, :].contiguous()   # c0 % 8 == 0 keeps the row swizzle phase
                 sub.scale = self.scale[c0:c0 + h].contiguous()
                 sub.bias = self.bias[c0:c0 + h].contiguous()
                 sub._halves = None

@@ -1,9 +1,9 @@
 """BatchNorm folding and weight packing into the shared-memory operand layout of the tcgen05 kernel.
 
-Packed B operand (see include/i2r.h, i2r_conv_problem::w):  fp16 [ntaps][Cin/KC][KC/8][Npad][8]
--- for every tap and K-chunk, KC/8 groups of 8 input channels, each holding Npad rows (output
-channels) of 8 contiguous fp16: exactly the K-major no-swizzle core-matrix image the kernel bulk-copies
-into shared memory, so no device-side reordering exists.
+Packed B operand (see include/i2r.h, i2r_conv_problem::w):  fp16 [ntaps][Cin/KC][Npad][64]
+-- for every tap and K-chunk, Npad rows (output channels) of 128 bytes (KC real K-slots + zero pad),
+16-byte chunks XOR-swizzled by the row index: exactly the SWIZZLE_128B K-major image the kernels
+bulk-copy into shared memory, so no device-side reordering exists.
 """
 import torch
 
@@ -37,15 +37,36 @@ def fold_bn(bn_sd, prefix, cout, conv_bias=None, eps=BN_EPS):
 
 
 def pack_taps(mats, kc):
-    """mats: list over taps of fp32 [Cout, Cin] matrices -> fp16 [ntaps, Cin/kc, kc/8, Npad, 8]."""
+    """mats: list over taps of fp32 [Cout, Cin] matrices -> fp16 [ntaps, Cin/kc, Npad, 64].
+
+    Per (tap, K-chunk) block: Npad rows (output channels) of 128 B = 64 fp16 K-slots, of which the first
+    `kc` hold input channels and the rest are zero; the eight 16-byte chunks of row n are stored at chunk
+    position (c XOR (n & 7)) -- the SWIZZLE_128B K-major image the kernels bulk-copy into shared memory.
+    """
     cout, cin = mats[0].shape
     npad = ceil_to(cout, 16)
     nch, kg = cin // kc, kc // 8
-    out = torch.zeros(len(mats), nch, kg, npad, 8, dtype=torch.float16)
+    out = torch.zeros(len(mats), nch, npad, 8, 8, dtype=torch.float16)
+    rows = torch.arange(npad)
     for t, m in enumerate(mats):
-        mm = m.float().reshape(cout, nch, kg, 8).permute(1, 2, 0, 3)
-        out[t, :, :, :cout, :] = mm.to(torch.float16)
-    return out.contiguous()
+        mm = m.float().reshape(cout, nch, kg, 8).permute(1, 0, 2, 3).to(torch.float16)   # [nch, cout, kg, 8]
+        for c in range(kg):
+            pos = (c ^ (rows[:cout] & 7))
+            out[t, :, rows[:cout], pos, :] = mm[:, :, c, :]
+    return out.reshape(len(mats), nch, npad, 64).contiguous()
+
+
+def unpack_taps(packed, kc):
+    """Inverse of pack_taps: fp16 [ntaps, nch, Npad, 64] -> fp32 [ntaps, Npad, Cin] (tests / emulator)."""
+    ntaps, nch, npad, _ = packed.shape
+    kg = kc // 8
+    p5 = packed.reshape(ntaps, nch, npad, 8, 8).float()
+    rows = torch.arange(npad)
+    out = torch.zeros(ntaps, nch, npad, kg, 8)
+    for c in range(kg):
+        pos = (c ^ (rows & 7))
+        out[:, :, rows, c, :] = p5[:, :, rows, pos, :]
+    return out.permute(0, 2, 1, 3, 4).reshape(ntaps, npad, nch * kc)
 
 
 def conv_taps(weight, pad):

@@ -10,6 +10,7 @@ import torch.nn.functional as F
 
 from i2r_b200 import capi
 from i2r_b200.ops import Runner
+from i2r_b200.packing import unpack_taps
 
 
 class EmuRunner(Runner):
@@ -31,13 +32,13 @@ class EmuRunner(Runner):
         nb, hs, ws, _ = x.shape
         sh = p.in_shift
         cin, npad, cout = p.Cin, p.Npad, p.Cout
-        w = L.w.float()                                   # [ntaps, nch, kg, npad, 8]
+        w = unpack_taps(L.w, p.KC)                        # [ntaps, npad, cin]
         oy = torch.arange(p.OH).view(-1, 1).expand(p.OH, p.OW)
         ox = torch.arange(p.OW).view(1, -1).expand(p.OH, p.OW)
         acc = torch.zeros(nb, p.OH, p.OW, npad)
         xf = x[..., :cin].float()
         for t in range(p.ntaps):
-            wt = w[t].permute(2, 0, 1, 3).reshape(npad, cin)
+            wt = w[t]
             iy = oy * p.stride + int(p.dy[t])
             ix = ox * p.stride + int(p.dx[t])
             ok = (iy >= 0) & (iy < p.IH) & (ix >= 0) & (ix < p.IW)

@@ -51,12 +51,16 @@ def test_cabi_library_exports_every_declared_symbol():
 
 
 def test_weight_packing_layout():
-    from i2r_b200.packing import conv_taps, pack_taps
+    """[tap][K-chunk][Npad rows][64 slots], 16-byte chunks XOR-swizzled by (row & 7), zero pad slots/rows."""
+    from i2r_b200.packing import conv_taps, pack_taps, unpack_taps
     w = torch.arange(17 * 48 * 9, dtype=torch.float32).reshape(17, 48, 3, 3) / 1000.0
     mats, dys, dxs = conv_taps(w, pad=1)
     packed = pack_taps(mats, 48)
-    assert tuple(packed.shape) == (9, 1, 6, 32, 8)
+    assert tuple(packed.shape) == (9, 1, 32, 64)
     assert (dys[0], dxs[0], dys[8], dxs[8]) == (-1, -1, 1, 1)
     t, n, c = 5, 13, 29                      # tap (ky=1,kx=2), out channel 13, in channel 29
-    assert packed[t, 0, c // 8, n, c % 8] == w[n, c, 1, 2].half()
-    assert float(packed[:, :, :, 17:, :].abs().max()) == 0.0
+    slot = ((c // 8) ^ (n & 7)) * 8 + c % 8
+    assert packed[t, 0, n, slot] == w[n, c, 1, 2].half()
+    assert float(packed[:, :, 17:, :].abs().max()) == 0.0
+    back = unpack_taps(packed, 48)
+    assert torch.equal(back[5, :17], w[:, :, 1, 2].half().float())
