@@ -426,7 +426,8 @@ __global__ void __launch_bounds__(T_THREADS, 1) conv_halo_kernel(const __grid_co
 }
 
 // ------------------------------------------------------------------------------------------------ host
-static int g_bo_mode = 1;   // I2R_DESC_BASE_OFFSET=0 disables the descriptor base_offset (hardware bring-up switch)
+static int g_bo_mode = 0;   // measured on B200: the swizzle XOR uses absolute smem address bits, so shifted windows need base_offset 0
+                            // (I2R_DESC_BASE_OFFSET=1 sets base_offset = dx; kept as a bring-up switch, see tools/probe_base_offset.py)
 
 static bool is_std3x3(const i2r_conv_problem& P) {
   if (P.ntaps != 9) return false;
@@ -464,7 +465,7 @@ extern "C" int i2r_conv_halo(const i2r_conv_problem* probs, int nprob, void* str
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
     const char* e = getenv("I2R_DESC_BASE_OFFSET");
-    if (e && e[0] == '0') g_bo_mode = 0;
+    if (e && e[0] == '1') g_bo_mode = 1;
   }
   HaloGroup G;
   memset(&G, 0, sizeof(G));
