@@ -124,6 +124,12 @@ int i2r_layernorm(const void* x, const float* gamma, const float* beta, const vo
 /* y = a + b elementwise on fp16, n multiple of 8 (with_pos_embed, interformer_pureMulti.py:189). */
 int i2r_add_f16(const void* a, const void* b, void* y, int64_t n, void* stream);
 
+/* Profiling aid: while dev_buffer != NULL, CTA `cta` of every i2r_conv_halo launch writes (tag<<32 | tile, clock64)
+ * pairs into three role regions (producer, MMA, epilogue) of `capacity_events` pairs each (zero-filled by the caller).  Tags: 1/2/3
+ * producer slot free / loads issued / stage published, 10/11/12 MMA accumulator free / operands landed / tile
+ * committed, 20/21 epilogue accumulator ready / tile stored.  Pass NULL to switch tracing off. */
+int i2r_debug_trace(void* dev_buffer, int capacity_events, int cta);
+
 /* sizeof(i2r_conv_problem) as compiled -- lets the ctypes binding verify its struct layout. */
 int i2r_sizeof_conv_problem(void);
 

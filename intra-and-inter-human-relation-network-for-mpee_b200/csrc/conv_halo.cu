@@ -2,23 +2,25 @@
 // halo-tile activation staging -> tcgen05.mma with TMEM accumulators -> fused epilogue.
 //
 //   tile        : 8 (x) by 16 (y) output pixels = 128 accumulator rows, all Npad output channels
-//   A operand   : per (tile, K-chunk) the (8+2) x (16+2) halo tile of KCH channels is staged ONCE in shared
-//                 memory as SWIZZLE_128B rows -- one 128-byte row per halo pixel, 16 pixel slots per halo line
-//                 (10 used) -- by four producer warps with coalesced 16-byte cp.async (zero-fill outside the
-//                 image = conv padding).  The nine taps of a 3x3 filter are nine shifted windows of that
-//                 single tile: the UMMA descriptor's start address moves by (dy*16+dx)*128 B, SBO = one halo
-//                 line (2048 B), base_offset = dx -- every activation byte is fetched once instead of nine times.
-//                 (A 5-D TMA box can deposit exactly this layout, but its 16-byte inner rows were measured
-//                 at ~4 B/cycle/SM on B200 -- see profiles/ -- so cp.async feeds this operand.)
+//   A operand   : per (tile, 64-channel K-chunk) ONE 4-D TMA box (64 ch, 10 px, 18 lines, 1 image) with
+//                 CU_TENSOR_MAP_SWIZZLE_128B deposits the (8+2) x (16+2) halo tile as 128-byte rows, one per
+//                 halo pixel; pixels outside the image and channels past C are zero-filled by the TMA unit
+//                 (= conv padding / K padding).  The nine taps of a 3x3 filter are nine shifted windows of
+//                 that single tile: the UMMA descriptor's start address moves by (dy*10+dx)*128 B with
+//                 SBO = one halo line (1280 B) -- the swizzle XOR is a function of the absolute shared-memory
+//                 address on sm_100 (probed: tools/probe_base_offset.py), so shifted windows stay consistent
+//                 with what TMA wrote.  Every activation byte is fetched once instead of nine times.
 //   B operand   : weights pre-packed in core-matrix order, moved by the TMA unit as 1-D bulk copies;
 //                 resident in shared memory for the whole kernel when they fit (<= 120 KB), else streamed
 //                 per (K-chunk, tap) through an mbarrier ring.
 //   D           : two TMEM accumulators so the epilogue of tile i overlaps the MMAs of tile i+1.
-//   warps       : 0..3 = activation producers, 4 = weight producer, 5 = TMEM owner + MMA issuer,
-//                 6..13 = epilogue (TMEM -> registers -> scale/bias/residual/ReLU -> global), two warps per
+//   warps       : 0 = activation TMA producer, 1 = weight producer, 2 = TMEM owner + MMA issuer,
+//                 4..11 = epilogue (TMEM -> registers -> scale/bias/residual/ReLU -> global), two warps per
 //                 TMEM lane quadrant, each owning half of the output channels.
 //   grid        : persistent; each problem of a grouped launch owns a contiguous CTA range sized
 //                 by its share of the work, CTAs stride over that problem's tiles.
+#include <cuda.h>
+
 #include <cstdio>
 #include <cstring>
 
@@ -51,26 +53,38 @@ struct HaloProblem {
 };
 
 struct HaloGroup {
+  CUtensorMap amap[I2R_MAX_GROUP];
+  unsigned long long* trace;   // optional event trace (tools/trace_halo.py): three role regions of trace_cap (tag<<32|tile, clock64) pairs
+  int trace_cta, trace_cap;
   HaloProblem p[I2R_MAX_GROUP];
   int nprob;
 };
 
-constexpr int T_THREADS = 448;
-constexpr int T_NPROD = 128;
+constexpr int T_THREADS = 384;
 constexpr int T_TW = 8, T_TH = 16;
 constexpr uint32_t T_A_OFF = 3072;          // dynamic smem: [0,256) barriers | [256,2304) scale,bias | A ring
 constexpr uint32_t T_MAX_SMEM = 226 * 1024;   // + 1 KB alignment slack = 227 KB opt-in limit
 constexpr uint32_t T_W_RES_MAX = 120 * 1024;
 
+// Fire-and-forget trace record (no atomics: each role owns region `role` of the buffer and a private counter).
+__device__ __forceinline__ void trace_ev(unsigned long long* tr, int cap, int role, int& idx, int tag, int tile) {
+  if (tr != nullptr && idx < cap) {
+    unsigned long long* e = tr + (static_cast<size_t>(role) * cap + idx) * 2;
+    e[0] = (static_cast<unsigned long long>(tag) << 32) | static_cast<unsigned>(tile);
+    e[1] = clock64();
+    ++idx;
+  }
+}
+
 // MMA issue loop.  Everything here is warp-uniform (kernel parameters, loop counters, shared-memory
 // addresses), so descriptor arithmetic stays on the uniform datapath and costs two 32-bit adds per
 // tcgen05.mma: the loop must sustain one MMA every ~25 cycles for N = 48.
-template <int NTAPS, int KG2>
+template <int NTAPS>
 __device__ __forceinline__ void mma_role(const HaloProblem& P, const int cta, const uint32_t sbase,
-                                         const uint32_t tmem_base, const uint32_t ncols) {
+                                         const uint32_t tmem_base, const uint32_t ncols, unsigned long long* tr,
+                                         const int trcap) {
   constexpr int HALO = NTAPS == 9 ? 1 : 0;
-  constexpr int HW = T_TW + 2 * HALO, HH = T_TH + 2 * HALO;
-  constexpr int PW = HALO ? 16 : 8;
+  constexpr int PW = T_TW + 2 * HALO;   // halo line = PW pixels = PW 128-byte rows (dense TMA box)
   constexpr uint32_t A_SBO = PW * 128;
   const uint32_t bar_afull = sbase, bar_aempty = sbase + 32, bar_wfull = sbase + 64, bar_wempty = sbase + 96;
   const uint32_t bar_accfull = sbase + 128, bar_accempty = sbase + 144, bar_wres = sbase + 160;
@@ -88,19 +102,23 @@ __device__ __forceinline__ void mma_role(const HaloProblem& P, const int cta, co
   const uint32_t a_lo0 = sw128_desc_lo(a_base);
   const bool resident = P.w_resident != 0;
   const bool leader = elect_one();
+  int tri = 0;
   int as = 0, ws = 0, acc = 0;
   uint32_t aph = 0, wph = 0, accph = 0;
   if (resident) mbar_wait(bar_wres, 0);
   for (int t = cta; t < P.ntiles; t += P.cta_count) {
     mbar_wait(bar_accempty + 8 * acc, accph ^ 1);
     tc_fence_after();
+    if (leader) trace_ev(tr, trcap, 1, tri, 10, t);
     const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc) * (ncols >> 1);
     uint32_t accum = 0;
     for (int kc = 0; kc < P.nkc; ++kc) {
       mbar_wait(bar_afull + 8 * as, aph);
       tc_fence_after();
+      if (leader) trace_ev(tr, trcap, 1, tri, 11, t);
       const uint32_t a_lo = a_lo0 + as * a_stage16;
       const uint32_t b_lo_kc = w_lo0 + kc * w_stage16;
+      const int ksteps = min(4, (P.C - kc * 64) >> 4);   // K=16 steps holding real channels in this chunk
       if (resident) {
 #pragma unroll
         for (int tap = 0; tap < NTAPS; ++tap) {
@@ -108,10 +126,11 @@ __device__ __forceinline__ void mma_role(const HaloProblem& P, const int cta, co
           const uint32_t a_t = a_lo + (HALO ? static_cast<uint32_t>(((tap / 3) * PW + (tap % 3)) * 8) : 0u);
           const uint32_t a_hi = a_hi_dx[HALO ? tap % 3 : 0];
 #pragma unroll
-          for (int k2 = 0; k2 < KG2; ++k2) {
-            if (leader)
-              umma_f16(d_tmem, desc64(a_t + k2 * 2, a_hi), desc64(b_lo + k2 * 2, b_hi), idesc, accum);
-            accum = 1;
+          for (int k2 = 0; k2 < 4; ++k2) {
+            if (k2 < ksteps) {
+              if (leader) umma_f16(d_tmem, desc64(a_t + k2 * 2, a_hi), desc64(b_lo + k2 * 2, b_hi), idesc, accum);
+              accum = 1;
+            }
           }
         }
       } else {
@@ -123,10 +142,11 @@ __device__ __forceinline__ void mma_role(const HaloProblem& P, const int cta, co
           const uint32_t a_t = a_lo + (HALO ? static_cast<uint32_t>(((tap / 3) * PW + (tap % 3)) * 8) : 0u);
           const uint32_t a_hi = a_hi_dx[HALO ? tap % 3 : 0];
 #pragma unroll
-          for (int k2 = 0; k2 < KG2; ++k2) {
-            if (leader)
-              umma_f16(d_tmem, desc64(a_t + k2 * 2, a_hi), desc64(b_lo + k2 * 2, b_hi), idesc, accum);
-            accum = 1;
+          for (int k2 = 0; k2 < 4; ++k2) {
+            if (k2 < ksteps) {
+              if (leader) umma_f16(d_tmem, desc64(a_t + k2 * 2, a_hi), desc64(b_lo + k2 * 2, b_hi), idesc, accum);
+              accum = 1;
+            }
           }
           if (leader) umma_commit(bar_wempty + 8 * ws);
           if (++ws == P.w_stages) {
@@ -142,75 +162,21 @@ __device__ __forceinline__ void mma_role(const HaloProblem& P, const int cta, co
       }
     }
     if (leader) umma_commit(bar_accfull + 8 * acc);
+    if (leader) trace_ev(tr, trcap, 1, tri, 12, t);
     acc ^= 1;
     if (acc == 0) accph ^= 1;
   }
 }
 
-// Activation producers (warps 0..3).  Slot i of thread tid covers 16-byte chunk j = tid + 128*i of the
-// halo tile, j = (halo pixel) * KG + (k-group): consecutive threads read consecutive 16 B of a pixel row
-// (coalesced) and write [k-group][pixel] with a padded k-group stride (bank-conflict free).
-template <int NTAPS, int KG>
-__device__ __forceinline__ void producer_role(const HaloProblem& P, const int cta, const uint32_t sbase) {
-  constexpr int HALO = NTAPS == 9 ? 1 : 0;
-  constexpr int HW = T_TW + 2 * HALO, HH = T_TH + 2 * HALO;
-  constexpr int CHUNKS = HH * HW * KG;
-  constexpr int SLOTS = (CHUNKS + T_NPROD - 1) / T_NPROD;
-  constexpr int PW = HALO ? 16 : 8;   // pixel slots per halo line in shared memory (keeps 8-row groups 1024-B aligned)
-  const uint32_t bar_afull = sbase, bar_aempty = sbase + 32;
-  const uint32_t a_base = sbase + T_A_OFF;
-  const int tid = threadIdx.x;
-  const int look = P.look;   // groups kept in flight (2 when the ring has >= 3 stages)
-  int goff[SLOTS], hyx[SLOTS];   // hyx = halo y << 16 | halo x << 8 | k-group  (-1: slot past the tile)
-#pragma unroll
-  for (int i = 0; i < SLOTS; ++i) {
-    const int j = tid + i * T_NPROD;
-    const int pix = j / KG, g = j - pix * KG;
-    const int hy = pix / HW, hx = pix - hy * HW;
-    goff[i] = (hy * P.W + hx) * P.in_pix_stride + g * 8;
-    hyx[i] = (j < CHUNKS) ? ((hy << 16) | (hx << 8) | g) : -1;
-  }
-  int it = 0;
-  for (int t = cta; t < P.ntiles; t += P.cta_count) {
-    const int n = t / P.tiles_per_img;
-    const int r = t - n * P.tiles_per_img;
-    const int ty = r / P.tiles_x, tx = r - ty * P.tiles_x;
-    const int x0 = tx * T_TW - HALO, y0 = ty * T_TH - HALO;
-    const __half* origin = P.x + (static_cast<int64_t>(n) * P.H + y0) * P.W * P.in_pix_stride +
-                           static_cast<int64_t>(x0) * P.in_pix_stride;
-    for (int kc = 0; kc < P.nkc; ++kc, ++it) {
-      const int s = it % P.a_stages;
-      const uint32_t ph = (it / P.a_stages) & 1;
-      mbar_wait(bar_aempty + 8 * s, ph ^ 1);
-      const uint32_t a_s = a_base + s * P.a_stage_bytes;
-      const __half* src0 = origin + kc * (KG * 8);
-#pragma unroll
-      for (int i = 0; i < SLOTS; ++i) {
-        if (hyx[i] >= 0) {
-          const int hy = hyx[i] >> 16, hx = (hyx[i] >> 8) & 0xff, g = hyx[i] & 0xff;
-          const int iy = y0 + hy, ix = x0 + hx;
-          const bool ok = (static_cast<unsigned>(iy) < static_cast<unsigned>(P.H)) &&
-                          (static_cast<unsigned>(ix) < static_cast<unsigned>(P.W));
-          const uint32_t soff = sw128_off(static_cast<uint32_t>(hy * PW + hx), static_cast<uint32_t>(g));
-          cp_async16(a_s + soff, ok ? static_cast<const void*>(src0 + goff[i]) : static_cast<const void*>(P.x),
-                     ok ? 16u : 0u);
-        }
-      }
-      cp_async_commit();
-      if (it >= look) {
-        if (look == 2) {
-          cp_async_wait<2>();
-        } else {
-          cp_async_wait<1>();
-        }
-        fence_proxy_async();
-        mbar_arrive(bar_afull + 8 * ((it - look) % P.a_stages));
-      }
-    }
-  }
-  cp_async_wait<0>();
-  fence_proxy_async();
-  for (int j = (it > look ? it - look : 0); j < it; ++j) mbar_arrive(bar_afull + 8 * (j % P.a_stages));
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, int c3,
+                                            uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2,%3,%4,%5}], [%6];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(bar)
+      : "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
 }
 
 __global__ void __launch_bounds__(T_THREADS, 1) conv_halo_kernel(const __grid_constant__ HaloGroup G) {
@@ -228,6 +194,7 @@ __global__ void __launch_bounds__(T_THREADS, 1) conv_halo_kernel(const __grid_co
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + 176);
   float* s_scale = reinterpret_cast<float*>(smem + 256);
   float* s_bias = reinterpret_cast<float*>(smem + 256 + 1024);
+  const uint32_t a_base = sbase + T_A_OFF;
   const uint32_t w_base = sbase + P.w_off;
 
   const int Npad = P.Npad;
@@ -236,7 +203,7 @@ __global__ void __launch_bounds__(T_THREADS, 1) conv_halo_kernel(const __grid_co
 
   if (tid == 0) {
     for (int i = 0; i < 4; ++i) {
-      mbar_init(bar_afull + 8 * i, T_NPROD);
+      mbar_init(bar_afull + 8 * i, 1);
       mbar_init(bar_aempty + 8 * i, 1);
       mbar_init(bar_wfull + 8 * i, 1);
       mbar_init(bar_wempty + 8 * i, 1);
@@ -248,7 +215,7 @@ __global__ void __launch_bounds__(T_THREADS, 1) conv_halo_kernel(const __grid_co
     mbar_init(bar_wres, 1);
     fence_mbar_init();
   }
-  if (warp == 5) {
+  if (warp == 2) {
     tmem_alloc(smem_u32(tmem_slot), ncols);
     tmem_relinquish();
   }
@@ -261,18 +228,34 @@ __global__ void __launch_bounds__(T_THREADS, 1) conv_halo_kernel(const __grid_co
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  const int kg_per_stage = P.KCH >> 3;
+  unsigned long long* tr = (G.trace != nullptr && static_cast<int>(blockIdx.x) == G.trace_cta) ? G.trace : nullptr;
 
-  const int variant = (P.ntaps == 9 ? 0 : 2) + (kg_per_stage == 6 ? 0 : 1);   // KCH is 48 or 64
-  if (warp < 4) {
-    // ================================================= activation producers (cp.async halo gather)
-    switch (variant) {
-      case 0: producer_role<9, 6>(P, cta, sbase); break;
-      case 1: producer_role<9, 8>(P, cta, sbase); break;
-      case 2: producer_role<1, 6>(P, cta, sbase); break;
-      default: producer_role<1, 8>(P, cta, sbase); break;
+  if (warp == 0) {
+    if (lane == 0) {
+      // ================================================= activation producer: one TMA box per (tile, K-chunk)
+      const CUtensorMap* amap = &G.amap[pi];
+      prefetch_tmap(amap);
+      int s = 0, tri = 0;
+      uint32_t ph = 0;
+      for (int t = cta; t < P.ntiles; t += P.cta_count) {
+        const int n = t / P.tiles_per_img;
+        const int r = t - n * P.tiles_per_img;
+        const int ty = r / P.tiles_x, tx = r - ty * P.tiles_x;
+        const int x0 = tx * T_TW - P.halo, y0 = ty * T_TH - P.halo;
+        for (int kc = 0; kc < P.nkc; ++kc) {
+          mbar_wait(bar_aempty + 8 * s, ph ^ 1);
+          trace_ev(tr, G.trace_cap, 0, tri, 1, t);
+          mbar_arrive_expect_tx(bar_afull + 8 * s, P.a_tx_bytes);
+          tma_load_4d(a_base + s * P.a_stage_bytes, amap, kc * 64, x0, y0, n, bar_afull + 8 * s);
+          trace_ev(tr, G.trace_cap, 0, tri, 2, t);
+          if (++s == P.a_stages) {
+            s = 0;
+            ph ^= 1;
+          }
+        }
+      }
     }
-  } else if (warp == 4) {
+  } else if (warp == 1) {
     if (lane == 0) {
     // ================================================= weight producer (1-D bulk copies on the TMA unit)
     if (P.w_resident) {
@@ -301,19 +284,18 @@ __global__ void __launch_bounds__(T_THREADS, 1) conv_halo_kernel(const __grid_co
       }
     }
     }
-  } else if (warp == 5) {
+  } else if (warp == 2) {
     // ================================================= MMA issuer (whole warp runs the loop, one lane issues)
-    switch (variant) {
-      case 0: mma_role<9, 3>(P, cta, sbase, tmem_base, ncols); break;
-      case 1: mma_role<9, 4>(P, cta, sbase, tmem_base, ncols); break;
-      case 2: mma_role<1, 3>(P, cta, sbase, tmem_base, ncols); break;
-      default: mma_role<1, 4>(P, cta, sbase, tmem_base, ncols); break;
+    if (P.ntaps == 9) {
+      mma_role<9>(P, cta, sbase, tmem_base, ncols, tr, G.trace_cap);
+    } else {
+      mma_role<1>(P, cta, sbase, tmem_base, ncols, tr, G.trace_cap);
     }
-  } else {
+  } else if (warp >= 4) {
     // ================================================= epilogue: 8 warps, two per TMEM lane quadrant, each
     // owning half of the output channels of its 32 rows; residual loads are issued before the accumulator
     // wait so their latency hides behind the MMAs of the tile.
-    const int ew = warp - 6;
+    const int ew = warp - 4;
     const int quad = warp & 3;             // warp % 4: the TMEM lanes this warp may read
     const int row = quad * 32 + lane;
     const int ty_in = row >> 3, tx_in = row & 7;
@@ -324,6 +306,7 @@ __global__ void __launch_bounds__(T_THREADS, 1) conv_halo_kernel(const __grid_co
     const float4* s_scale4 = reinterpret_cast<const float4*>(s_scale);
     const float4* s_bias4 = reinterpret_cast<const float4*>(s_bias);
     int acc = 0;
+    int tri = 0;
     uint32_t accph = 0;
     for (int t = cta; t < P.ntiles; t += P.cta_count) {
       const int n = t / P.tiles_per_img;
@@ -352,6 +335,7 @@ __global__ void __launch_bounds__(T_THREADS, 1) conv_halo_kernel(const __grid_co
           mbar_wait(bar_accfull + 8 * acc, accph);
           tc_fence_after();
           waited = true;
+          if (ew == 0 && lane == 0) trace_ev(tr, G.trace_cap, 2, tri, 20, t);
         }
         uint32_t av[4][8];
 #pragma unroll
@@ -415,6 +399,7 @@ __global__ void __launch_bounds__(T_THREADS, 1) conv_halo_kernel(const __grid_co
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_accempty + 8 * acc);
+      if (ew == 0 && lane == 0) trace_ev(tr, G.trace_cap, 2, tri, 21, t);
       acc ^= 1;
       if (acc == 0) accph ^= 1;
     }
@@ -422,10 +407,53 @@ __global__ void __launch_bounds__(T_THREADS, 1) conv_halo_kernel(const __grid_co
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 5) tmem_dealloc(tmem_base, ncols);
+  if (warp == 2) tmem_dealloc(tmem_base, ncols);
 }
 
 // ------------------------------------------------------------------------------------------------ host
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// NHWC activation tensor as a 4-D TMA tensor (C, W, H, N); box = (64 channels, halo width, halo height, 1) with
+// 128-byte swizzle: one 128-byte shared-memory row per pixel.  Out-of-range pixels and channels read as zero.
+static int encode_amap(CUtensorMap* map, const void* x, int NB, int H, int W, int C, int pix_stride, int hw, int hh) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) {
+    set_error("cuTensorMapEncodeTiled entry point unavailable");
+    return I2R_E_DEVICE;
+  }
+  const cuuint64_t pb = static_cast<cuuint64_t>(pix_stride) * 2;
+  const cuuint32_t ones[4] = {1, 1, 1, 1};
+  const cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)NB};
+  const cuuint64_t strides[3] = {pb, pb * W, pb * W * H};
+  const cuuint32_t box[4] = {64, (cuuint32_t)hw, (cuuint32_t)hh, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(x), dims, strides, box, ones,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed (%d) for [%d,%d,%d,%d] pix_stride %d", (int)r, NB, H, W, C, pix_stride);
+    return I2R_E_DEVICE;
+  }
+  return 0;
+}
+
+static unsigned long long* g_trace = nullptr;
+static int g_trace_cta = 0, g_trace_cap = 0;
 static int g_bo_mode = 0;   // measured on B200: the swizzle XOR uses absolute smem address bits, so shifted windows need base_offset 0
                             // (I2R_DESC_BASE_OFFSET=1 sets base_offset = dx; kept as a bring-up switch, see tools/probe_base_offset.py)
 
@@ -447,7 +475,7 @@ extern "C" int i2r_conv_halo_supported(const i2r_conv_problem* P) {
   if (P->OH != P->IH || P->OW != P->IW || P->OHf != P->OH || P->OWf != P->OW) return 0;
   if ((P->add0 && P->add0_shift != 0) || (P->add1 && P->add1_shift != 0)) return 0;
   if (P->Cin % 16 != 0 || P->Npad > 256 || P->Npad % 16 != 0) return 0;
-  if ((P->KC != 48 && P->KC != 64) || P->Cin % P->KC != 0) return 0;
+  if (P->KC != 64) return 0;
   if (P->in_pix_stride % 8 != 0) return 0;
   if ((P->add0 || P->add1) && (P->add_pix_stride % 8 != 0 || P->add_pix_stride < P->Cout)) return 0;
   return 1;
@@ -470,6 +498,9 @@ extern "C" int i2r_conv_halo(const i2r_conv_problem* probs, int nprob, void* str
   HaloGroup G;
   memset(&G, 0, sizeof(G));
   G.nprob = nprob;
+  G.trace = g_trace;
+  G.trace_cta = g_trace_cta;
+  G.trace_cap = g_trace_cap;
   double cost[I2R_MAX_GROUP];
   double total_cost = 0;
   int total_tiles = 0;
@@ -507,10 +538,10 @@ extern "C" int i2r_conv_halo(const i2r_conv_problem* probs, int nprob, void* str
     P.C = S.Cin;
     P.Cout = S.Cout;
     P.Npad = S.Npad;
-    P.KCH = S.KC;
-    P.nkc = S.Cin / P.KCH;
-    P.kgp = S.KC / 8;
-    P.nchp = S.Cin / S.KC;
+    P.KCH = 64;
+    P.nkc = (S.Cin + 63) / 64;
+    P.kgp = 8;
+    P.nchp = P.nkc;
     P.tiles_x = (P.W + T_TW - 1) / T_TW;
     P.tiles_per_img = P.tiles_x * ((P.H + T_TH - 1) / T_TH);
     P.ntiles = P.tiles_per_img * P.NB;
@@ -519,9 +550,9 @@ extern "C" int i2r_conv_halo(const i2r_conv_problem* probs, int nprob, void* str
     P.add_pix_stride = S.add_pix_stride;
     P.flags = S.flags;
     const int hw = T_TW + 2 * P.halo, hh = T_TH + 2 * P.halo;
-    P.a_tx_bytes = static_cast<uint32_t>(hh * (P.halo ? 16 : 8) * 128);
-    P.a_stage_bytes = P.a_tx_bytes;   // multiple of 1024
-    P.w_total_bytes = static_cast<uint32_t>(S.ntaps) * (S.Cin / S.KC) * S.Npad * 128;
+    P.a_tx_bytes = static_cast<uint32_t>(hh * hw * 128);          // full box, zero-filled parts included
+    P.a_stage_bytes = (P.a_tx_bytes + 1023u) & ~1023u;            // stages stay 1024-byte aligned (SW128)
+    P.w_total_bytes = static_cast<uint32_t>(S.ntaps) * P.nkc * S.Npad * 128;
     P.w_resident = P.w_total_bytes <= T_W_RES_MAX ? 1 : 0;
     P.w_stage_bytes = static_cast<uint32_t>(S.Npad) * 128;
     uint32_t wregion;
@@ -541,8 +572,12 @@ extern "C" int i2r_conv_halo(const i2r_conv_problem* probs, int nprob, void* str
       return I2R_E_UNSUPPORTED;
     }
     P.a_stages = astg;
-    P.look = astg >= 3 ? 2 : 1;
+    P.look = 0;
     P.bo_mode = g_bo_mode;
+    {
+      int rc = encode_amap(&G.amap[i], S.x, P.NB, P.H, P.W, P.C, S.in_pix_stride, hw, hh);
+      if (rc) return rc;
+    }
     P.w_off = T_A_OFF + static_cast<uint32_t>(astg) * P.a_stage_bytes;
     const uint32_t need = P.w_off + wregion;
     if (need > smem_need) smem_need = need;
@@ -602,4 +637,11 @@ extern "C" int i2r_conv_halo(const i2r_conv_problem* probs, int nprob, void* str
   }
   conv_halo_kernel<<<begin, T_THREADS, smem_need + 1024, static_cast<cudaStream_t>(stream)>>>(G);
   return check_launch("conv_halo_kernel");
+}
+
+extern "C" int i2r_debug_trace(void* dev_buffer, int capacity_events, int cta) {
+  i2r::g_trace = static_cast<unsigned long long*>(dev_buffer);
+  i2r::g_trace_cap = capacity_events;
+  i2r::g_trace_cta = cta;
+  return 0;
 }

@@ -33,9 +33,10 @@ constexpr int SMEM_SCALE_OFF = 256;
 constexpr int SMEM_BIAS_OFF = 256 + 1024;
 
 
-template <int KG, int STAGES>
+template <int STAGES>
 __device__ __forceinline__ void run_tile(const i2r_conv_problem& P, const int tile, uint8_t* smem) {
   constexpr int LOOK = STAGES - 1;
+  constexpr int KG = 8;   // 16-byte chunk slots per 128-byte row; the last K-chunk may use fewer (Cin % 64 != 0)
   const int tid = threadIdx.x;
   const int warp = tid >> 5;
   const int lane = tid & 31;
@@ -54,7 +55,7 @@ __device__ __forceinline__ void run_tile(const i2r_conv_problem& P, const int ti
   const int st_bytes = a_bytes + b_bytes;
   const uint32_t stages0 = sbase + SMEM_HDR;
 
-  const int nchunks = P.Cin / (KG * 8);
+  const int nchunks = (P.Cin + 63) >> 6;
   const int niter = P.ntaps * nchunks;
   const int M = P.NB * P.OH * P.OW;
 
@@ -124,6 +125,7 @@ __device__ __forceinline__ void run_tile(const i2r_conv_problem& P, const int ti
     for (int t = 0; t < P.ntaps; ++t) {
       const int dy = P.dy[t], dx = P.dx[t];
       for (int c = 0; c < nchunks; ++c, ++it) {
+        const int kgc = min(8, (P.Cin - c * 64) >> 3);   // real 16-byte chunks per row in this K-chunk
         const int s = it % STAGES;
         const uint32_t ph = (it / STAGES) & 1;
         mbar_wait(bar_empty + 8 * s, ph ^ 1);
@@ -138,12 +140,14 @@ __device__ __forceinline__ void run_tile(const i2r_conv_problem& P, const int ti
           const int ix = r_ox[i] + dx;
           const bool ok = (static_cast<unsigned>(iy) < static_cast<unsigned>(P.IH)) &&
                           (static_cast<unsigned>(ix) < static_cast<unsigned>(P.IW));
-          const __half* src = X;
-          if (ok) {
-            const int64_t pix = static_cast<int64_t>(r_nb[i] + (iy >> sh)) * IWs + (ix >> sh);
-            src = X + pix * P.in_pix_stride + c * (KG * 8) + r_g[i] * 8;
+          if (r_g[i] < kgc) {
+            const __half* src = X;
+            if (ok) {
+              const int64_t pix = static_cast<int64_t>(r_nb[i] + (iy >> sh)) * IWs + (ix >> sh);
+              src = X + pix * P.in_pix_stride + c * 64 + r_g[i] * 8;
+            }
+            cp_async16(a_s + r_dst[i], src, ok ? 16u : 0u);
           }
-          cp_async16(a_s + r_dst[i], src, ok ? 16u : 0u);
         }
         cp_async_commit();
         if (it >= LOOK) {
@@ -275,11 +279,14 @@ __device__ __forceinline__ void run_tile(const i2r_conv_problem& P, const int ti
       mbar_wait(bar_full + 8 * s, ph);
       tc_fence_after();
       const uint32_t a_lo = a_lo0 + s * st16, b_lo = b_lo0 + s * st16;
+      const int ksteps = min(4, (P.Cin - (it % nchunks) * 64) >> 4);
 #pragma unroll
-      for (int k = 0; k < KG / 2; ++k) {
-        if (leader)
-          umma_f16(tmem_base, desc64(a_lo + k * 2, a_hi), desc64(b_lo + k * 2, b_hi), idesc, accum);
-        accum = 1;
+      for (int k = 0; k < 4; ++k) {
+        if (k < ksteps) {
+          if (leader)
+            umma_f16(tmem_base, desc64(a_lo + k * 2, a_hi), desc64(b_lo + k * 2, b_hi), idesc, accum);
+          accum = 1;
+        }
       }
       if (leader) umma_commit(bar_empty + 8 * s);
     }
@@ -301,11 +308,7 @@ __global__ void __launch_bounds__(NTHREADS) igemm_tc_kernel(const __grid_constan
   while (pi < G.nprob - 1 && tile >= G.tile_end[pi]) ++pi;
   if (pi > 0) tile -= G.tile_end[pi - 1];
   const i2r_conv_problem& P = G.p[pi];
-  if (P.KC == 48) {
-    run_tile<6, STAGES>(P, tile, smem);
-  } else {
-    run_tile<8, STAGES>(P, tile, smem);
-  }
+  run_tile<STAGES>(P, tile, smem);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -327,7 +330,7 @@ __global__ void __launch_bounds__(128) igemm_check_kernel(const __grid_constant_
   const int oyf = oy * P.out_mul + P.out_offy, oxf = ox * P.out_mul + P.out_offx;
   const int sh = P.in_shift;
   const int IHs = P.IH >> sh, IWs = P.IW >> sh;
-  const int nchunks = P.Cin / P.KC;
+  const int nchunks = (P.Cin + 63) >> 6;
   const __half* X = reinterpret_cast<const __half*>(P.x);
   const __half* Wp = reinterpret_cast<const __half*>(P.w);
   const int64_t opix = (static_cast<int64_t>(n) * P.OHf + oyf) * P.OWf + oxf;
@@ -340,7 +343,7 @@ __global__ void __launch_bounds__(128) igemm_check_kernel(const __grid_constant_
         continue;
       const __half* xp = X + (static_cast<int64_t>(n * IHs + (iy >> sh)) * IWs + (ix >> sh)) * P.in_pix_stride;
       for (int c = 0; c < P.Cin; ++c) {
-        const int ch = c / P.KC, g = (c % P.KC) / 8, e = c % 8;
+        const int ch = c >> 6, g = (c & 63) >> 3, e = c & 7;
         const int64_t wi = (static_cast<int64_t>(t * nchunks + ch) * P.Npad + co) * 64 + ((g ^ (co & 7)) << 3) + e;
         acc += __half2float(xp[c]) * __half2float(Wp[wi]);
       }
@@ -374,12 +377,12 @@ static int validate(const i2r_conv_problem& P, int idx) {
     set_error("conv problem %d: null pointer", idx);
     return I2R_E_BADARG;
   }
-  if (P.KC != 48 && P.KC != 64) {
-    set_error("conv problem %d: KC=%d unsupported (48 or 64)", idx, P.KC);
+  if (P.KC != 64) {
+    set_error("conv problem %d: KC=%d unsupported (weights are packed in 64-slot K-chunks)", idx, P.KC);
     return I2R_E_UNSUPPORTED;
   }
-  if (P.Cin <= 0 || P.Cin % P.KC != 0) {
-    set_error("conv problem %d: Cin=%d not a multiple of KC=%d", idx, P.Cin, P.KC);
+  if (P.Cin <= 0 || P.Cin % 16 != 0) {
+    set_error("conv problem %d: Cin=%d not a multiple of 16", idx, P.Cin);
     return I2R_E_BADARG;
   }
   if (P.Npad < 16 || P.Npad > 256 || P.Npad % 16 != 0 || P.Cout > P.Npad || P.Cout <= 0) {

@@ -14,12 +14,14 @@ def ceil_to(x, m):
     return (x + m - 1) // m * m
 
 
+KC = 64   # K-chunk = 64 channel slots = one 128-byte SWIZZLE_128B row
+
+
 def pick_kc(cin):
-    if cin % 64 == 0:
-        return 64
-    if cin % 48 == 0:
-        return 48
-    raise ValueError("Cin=%d is not a multiple of 48 or 64 (channel padding not implemented)" % cin)
+    """All problems use 64-slot K-chunks; the last chunk may be partially filled (Cin multiple of 16)."""
+    if cin % 16 != 0:
+        raise ValueError("Cin=%d is not a multiple of 16 (channel padding not implemented)" % cin)
+    return KC
 
 
 def fold_bn(bn_sd, prefix, cout, conv_bias=None, eps=BN_EPS):
@@ -36,37 +38,37 @@ def fold_bn(bn_sd, prefix, cout, conv_bias=None, eps=BN_EPS):
     return scale, bias
 
 
-def pack_taps(mats, kc):
-    """mats: list over taps of fp32 [Cout, Cin] matrices -> fp16 [ntaps, Cin/kc, Npad, 64].
+def pack_taps(mats, kc=KC):
+    """mats: list over taps of fp32 [Cout, Cin] matrices -> fp16 [ntaps, ceil(Cin/64), Npad, 64].
 
-    Per (tap, K-chunk) block: Npad rows (output channels) of 128 B = 64 fp16 K-slots, of which the first
-    `kc` hold input channels and the rest are zero; the eight 16-byte chunks of row n are stored at chunk
-    position (c XOR (n & 7)) -- the SWIZZLE_128B K-major image the kernels bulk-copy into shared memory.
+    Per (tap, K-chunk) block: Npad rows (output channels) of 128 B = 64 fp16 K-slots holding input
+    channels [64*chunk, 64*chunk+64) (zero past Cin); the eight 16-byte chunks of row n are stored at
+    chunk position (c XOR (n & 7)) -- the SWIZZLE_128B K-major image the kernels bulk-copy into shared memory.
     """
+    assert kc == KC
     cout, cin = mats[0].shape
     npad = ceil_to(cout, 16)
-    nch, kg = cin // kc, kc // 8
+    nch = (cin + KC - 1) // KC
     out = torch.zeros(len(mats), nch, npad, 8, 8, dtype=torch.float16)
-    rows = torch.arange(npad)
+    rows = torch.arange(cout)
     for t, m in enumerate(mats):
-        mm = m.float().reshape(cout, nch, kg, 8).permute(1, 0, 2, 3).to(torch.float16)   # [nch, cout, kg, 8]
-        for c in range(kg):
-            pos = (c ^ (rows[:cout] & 7))
-            out[t, :, rows[:cout], pos, :] = mm[:, :, c, :]
+        mm = torch.zeros(cout, nch * KC)
+        mm[:, :cin] = m.float()
+        mm = mm.reshape(cout, nch, 8, 8).to(torch.float16)
+        for c in range(8):
+            out[t, :, rows, c ^ (rows & 7), :] = mm[:, :, c, :].permute(1, 0, 2)
     return out.reshape(len(mats), nch, npad, 64).contiguous()
 
 
-def unpack_taps(packed, kc):
-    """Inverse of pack_taps: fp16 [ntaps, nch, Npad, 64] -> fp32 [ntaps, Npad, Cin] (tests / emulator)."""
+def unpack_taps(packed, cin):
+    """Inverse of pack_taps: fp16 [ntaps, nch, Npad, 64] -> fp32 [ntaps, Npad, cin] (tests / emulator)."""
     ntaps, nch, npad, _ = packed.shape
-    kg = kc // 8
     p5 = packed.reshape(ntaps, nch, npad, 8, 8).float()
     rows = torch.arange(npad)
-    out = torch.zeros(ntaps, nch, npad, kg, 8)
-    for c in range(kg):
-        pos = (c ^ (rows & 7))
-        out[:, :, rows, c, :] = p5[:, :, rows, pos, :]
-    return out.permute(0, 2, 1, 3, 4).reshape(ntaps, npad, nch * kc)
+    out = torch.zeros(ntaps, nch, npad, 8, 8)
+    for c in range(8):
+        out[:, :, rows, c, :] = p5[:, :, rows, c ^ (rows & 7), :]
+    return out.permute(0, 2, 1, 3, 4).reshape(ntaps, npad, nch * KC)[:, :, :cin]
 
 
 def conv_taps(weight, pad):

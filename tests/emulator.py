@@ -32,7 +32,7 @@ class EmuRunner(Runner):
         nb, hs, ws, _ = x.shape
         sh = p.in_shift
         cin, npad, cout = p.Cin, p.Npad, p.Cout
-        w = unpack_taps(L.w, p.KC)                        # [ntaps, npad, cin]
+        w = unpack_taps(L.w, cin)                         # [ntaps, npad, cin]
         oy = torch.arange(p.OH).view(-1, 1).expand(p.OH, p.OW)
         ox = torch.arange(p.OW).view(1, -1).expand(p.OH, p.OW)
         acc = torch.zeros(nb, p.OH, p.OW, npad)

@@ -55,7 +55,7 @@ def test_weight_packing_layout():
     from i2r_b200.packing import conv_taps, pack_taps, unpack_taps
     w = torch.arange(17 * 48 * 9, dtype=torch.float32).reshape(17, 48, 3, 3) / 1000.0
     mats, dys, dxs = conv_taps(w, pad=1)
-    packed = pack_taps(mats, 48)
+    packed = pack_taps(mats)
     assert tuple(packed.shape) == (9, 1, 32, 64)
     assert (dys[0], dxs[0], dys[8], dxs[8]) == (-1, -1, 1, 1)
     t, n, c = 5, 13, 29                      # tap (ky=1,kx=2), out channel 13, in channel 29
