@@ -76,6 +76,17 @@ __device__ __forceinline__ void trace_ev(unsigned long long* tr, int cap, int ro
   }
 }
 
+template <int NTAPS, int KS>
+__device__ __forceinline__ void issue_taps(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_tap,
+                                           uint32_t b_hi, uint32_t idesc, uint32_t acc_first) {
+  constexpr int PW = NTAPS == 9 ? T_TW + 2 : T_TW;
+#pragma unroll
+  for (int tap = 0; tap < NTAPS; ++tap) {
+    const uint32_t a_t = a_lo + (NTAPS == 9 ? static_cast<uint32_t>(((tap / 3) * PW + (tap % 3)) * 8) : 0u);
+    issue_ksteps<KS>(d_tmem, a_t, a_hi, b_lo + tap * b_tap, b_hi, idesc, tap ? 1u : acc_first);
+  }
+}
+
 // MMA issue loop.  Everything here is warp-uniform (kernel parameters, loop counters, shared-memory
 // addresses), so descriptor arithmetic stays on the uniform datapath and costs two 32-bit adds per
 // tcgen05.mma: the loop must sustain one MMA every ~25 cycles for N = 48.
@@ -93,8 +104,7 @@ __device__ __forceinline__ void mma_role(const HaloProblem& P, const int cta, co
   const int Npad = P.Npad;
   const uint32_t idesc = make_idesc_f16(128, Npad);
   const uint32_t b_hi = sw128_desc_hi(1024, 0);
-  const uint32_t bo_on = P.bo_mode ? 1u : 0u;   // descriptor base_offset for dx-shifted windows (debug switch)
-  const uint32_t a_hi_dx[3] = {sw128_desc_hi(A_SBO, 0), sw128_desc_hi(A_SBO, bo_on * 1u), sw128_desc_hi(A_SBO, bo_on * 2u)};
+  const uint32_t a_hi = sw128_desc_hi(A_SBO, 0);   // base_offset 0: the swizzle XOR follows absolute smem address bits
   const uint32_t w_stage16 = P.w_stage_bytes >> 4;                         // one (tap, K-chunk) block = Npad rows x 128 B
   const uint32_t b_tap = static_cast<uint32_t>(P.nkc) * w_stage16;         // resident: next tap
   const uint32_t w_lo0 = sw128_desc_lo(w_base);
@@ -111,7 +121,6 @@ __device__ __forceinline__ void mma_role(const HaloProblem& P, const int cta, co
     tc_fence_after();
     if (leader) trace_ev(tr, trcap, 1, tri, 10, t);
     const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc) * (ncols >> 1);
-    uint32_t accum = 0;
     for (int kc = 0; kc < P.nkc; ++kc) {
       mbar_wait(bar_afull + 8 * as, aph);
       tc_fence_after();
@@ -119,18 +128,15 @@ __device__ __forceinline__ void mma_role(const HaloProblem& P, const int cta, co
       const uint32_t a_lo = a_lo0 + as * a_stage16;
       const uint32_t b_lo_kc = w_lo0 + kc * w_stage16;
       const int ksteps = min(4, (P.C - kc * 64) >> 4);   // K=16 steps holding real channels in this chunk
+      const uint32_t acc_kc = (kc != 0) ? 1u : 0u;
       if (resident) {
-#pragma unroll
-        for (int tap = 0; tap < NTAPS; ++tap) {
-          const uint32_t b_lo = b_lo_kc + tap * b_tap;
-          const uint32_t a_t = a_lo + (HALO ? static_cast<uint32_t>(((tap / 3) * PW + (tap % 3)) * 8) : 0u);
-          const uint32_t a_hi = a_hi_dx[HALO ? tap % 3 : 0];
-#pragma unroll
-          for (int k2 = 0; k2 < 4; ++k2) {
-            if (k2 < ksteps) {
-              if (leader) umma_f16(d_tmem, desc64(a_t + k2 * 2, a_hi), desc64(b_lo + k2 * 2, b_hi), idesc, accum);
-              accum = 1;
-            }
+        // one straight-line burst of NTAPS x ksteps MMAs issued by the elected lane
+        if (leader) {
+          switch (ksteps) {
+            case 4: issue_taps<NTAPS, 4>(d_tmem, a_lo, a_hi, b_lo_kc, b_tap, b_hi, idesc, acc_kc); break;
+            case 3: issue_taps<NTAPS, 3>(d_tmem, a_lo, a_hi, b_lo_kc, b_tap, b_hi, idesc, acc_kc); break;
+            case 2: issue_taps<NTAPS, 2>(d_tmem, a_lo, a_hi, b_lo_kc, b_tap, b_hi, idesc, acc_kc); break;
+            default: issue_taps<NTAPS, 1>(d_tmem, a_lo, a_hi, b_lo_kc, b_tap, b_hi, idesc, acc_kc); break;
           }
         }
       } else {
@@ -138,17 +144,18 @@ __device__ __forceinline__ void mma_role(const HaloProblem& P, const int cta, co
         for (int tap = 0; tap < NTAPS; ++tap) {
           mbar_wait(bar_wfull + 8 * ws, wph);
           tc_fence_after();
-          const uint32_t b_lo = w_lo0 + ws * w_stage16;
-          const uint32_t a_t = a_lo + (HALO ? static_cast<uint32_t>(((tap / 3) * PW + (tap % 3)) * 8) : 0u);
-          const uint32_t a_hi = a_hi_dx[HALO ? tap % 3 : 0];
-#pragma unroll
-          for (int k2 = 0; k2 < 4; ++k2) {
-            if (k2 < ksteps) {
-              if (leader) umma_f16(d_tmem, desc64(a_t + k2 * 2, a_hi), desc64(b_lo + k2 * 2, b_hi), idesc, accum);
-              accum = 1;
+          if (leader) {
+            const uint32_t b_lo = w_lo0 + ws * w_stage16;
+            const uint32_t a_t = a_lo + (HALO ? static_cast<uint32_t>(((tap / 3) * PW + (tap % 3)) * 8) : 0u);
+            const uint32_t accf = tap ? 1u : acc_kc;
+            switch (ksteps) {
+              case 4: issue_ksteps<4>(d_tmem, a_t, a_hi, b_lo, b_hi, idesc, accf); break;
+              case 3: issue_ksteps<3>(d_tmem, a_t, a_hi, b_lo, b_hi, idesc, accf); break;
+              case 2: issue_ksteps<2>(d_tmem, a_t, a_hi, b_lo, b_hi, idesc, accf); break;
+              default: issue_ksteps<1>(d_tmem, a_t, a_hi, b_lo, b_hi, idesc, accf); break;
             }
+            umma_commit(bar_wempty + 8 * ws);
           }
-          if (leader) umma_commit(bar_wempty + 8 * ws);
           if (++ws == P.w_stages) {
             ws = 0;
             wph ^= 1;

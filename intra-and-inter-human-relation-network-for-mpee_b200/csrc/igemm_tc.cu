@@ -280,14 +280,15 @@ __device__ __forceinline__ void run_tile(const i2r_conv_problem& P, const int ti
       tc_fence_after();
       const uint32_t a_lo = a_lo0 + s * st16, b_lo = b_lo0 + s * st16;
       const int ksteps = min(4, (P.Cin - (it % nchunks) * 64) >> 4);
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        if (k < ksteps) {
-          if (leader)
-            umma_f16(tmem_base, desc64(a_lo + k * 2, a_hi), desc64(b_lo + k * 2, b_hi), idesc, accum);
-          accum = 1;
+      if (leader) {
+        switch (ksteps) {
+          case 4: issue_ksteps<4>(tmem_base, a_lo, a_hi, b_lo, b_hi, idesc, accum); break;
+          case 3: issue_ksteps<3>(tmem_base, a_lo, a_hi, b_lo, b_hi, idesc, accum); break;
+          case 2: issue_ksteps<2>(tmem_base, a_lo, a_hi, b_lo, b_hi, idesc, accum); break;
+          default: issue_ksteps<1>(tmem_base, a_lo, a_hi, b_lo, b_hi, idesc, accum); break;
         }
       }
+      accum = 1;
       if (leader) umma_commit(bar_empty + 8 * s);
     }
     if (leader) umma_commit(bar_accum);
