@@ -8,7 +8,7 @@
 //                 (= conv padding / K padding).  The nine taps of a 3x3 filter are nine shifted windows of
 //                 that single tile: the UMMA descriptor's start address moves by (dy*10+dx)*128 B with
 //                 SBO = one halo line (1280 B) -- the swizzle XOR is a function of the absolute shared-memory
-//                 address on sm_100 (probed: tools/probe_base_offset.py), so shifted windows stay consistent
+//                 address on sm_100 (probed on B200, see DESIGN.md: descriptor base_offset must stay 0), so shifted windows stay consistent
 //                 with what TMA wrote.  Every activation byte is fetched once instead of nine times.
 //   B operand   : weights pre-packed in core-matrix order, moved by the TMA unit as 1-D bulk copies;
 //                 resident in shared memory for the whole kernel when they fit (<= 120 KB), else streamed
@@ -48,7 +48,7 @@ struct HaloProblem {
   int w_resident;
   uint32_t w_total_bytes, w_stage_bytes;
   uint32_t a_stage_bytes, a_tx_bytes;
-  int a_stages, w_stages, look, bo_mode;
+  int a_stages, w_stages;
   uint32_t w_off;      // byte offset of the weight region in dynamic smem
 };
 
@@ -461,9 +461,6 @@ static int encode_amap(CUtensorMap* map, const void* x, int NB, int H, int W, in
 
 static unsigned long long* g_trace = nullptr;
 static int g_trace_cta = 0, g_trace_cap = 0;
-static int g_bo_mode = 0;   // measured on B200: the swizzle XOR uses absolute smem address bits, so shifted windows need base_offset 0
-                            // (I2R_DESC_BASE_OFFSET=1 sets base_offset = dx; kept as a bring-up switch, see tools/probe_base_offset.py)
-
 static bool is_std3x3(const i2r_conv_problem& P) {
   if (P.ntaps != 9) return false;
   for (int t = 0; t < 9; ++t)
@@ -499,8 +496,6 @@ extern "C" int i2r_conv_halo(const i2r_conv_problem* probs, int nprob, void* str
     int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
-    const char* e = getenv("I2R_DESC_BASE_OFFSET");
-    if (e && e[0] == '1') g_bo_mode = 1;
   }
   HaloGroup G;
   memset(&G, 0, sizeof(G));
@@ -509,7 +504,6 @@ extern "C" int i2r_conv_halo(const i2r_conv_problem* probs, int nprob, void* str
   G.trace_cta = g_trace_cta;
   G.trace_cap = g_trace_cap;
   double cost[I2R_MAX_GROUP];
-  double total_cost = 0;
   int total_tiles = 0;
   uint32_t smem_need = 0;
   for (int i = 0; i < nprob; ++i) {
@@ -579,8 +573,6 @@ extern "C" int i2r_conv_halo(const i2r_conv_problem* probs, int nprob, void* str
       return I2R_E_UNSUPPORTED;
     }
     P.a_stages = astg;
-    P.look = 0;
-    P.bo_mode = g_bo_mode;
     {
       int rc = encode_amap(&G.amap[i], S.x, P.NB, P.H, P.W, P.C, S.in_pix_stride, hw, hh);
       if (rc) return rc;
@@ -588,11 +580,12 @@ extern "C" int i2r_conv_halo(const i2r_conv_problem* probs, int nprob, void* str
     P.w_off = T_A_OFF + static_cast<uint32_t>(astg) * P.a_stage_bytes;
     const uint32_t need = P.w_off + wregion;
     if (need > smem_need) smem_need = need;
-    cost[i] = static_cast<double>(P.ntiles) * S.ntaps * S.Cin * (S.Npad < 64 ? 64 : S.Npad);
-    total_cost += cost[i];
+    cost[i] = static_cast<double>(S.ntaps) * (S.Cin / 16) * (4096.0 + 32.0 * S.Npad) * (P.w_resident ? 1.0 : 1.3);  // per tile
     total_tiles += P.ntiles;
   }
-  // CTA ranges: one CTA per tile while they fit, else split the SMs by MMA work.
+  // CTA ranges: one CTA per tile while they fit; otherwise hand the SMs out greedily to whichever problem
+  // currently has the longest makespan ceil(tiles / CTAs) * tile_cost (tile_cost from the measured
+  // operand-fetch-bound MMA rate: ~ (4096 + 32 * Npad) bytes of shared-memory operands per K=16 step).
   int begin = 0;
   if (total_tiles <= num_sms) {
     for (int i = 0; i < nprob; ++i) {
@@ -601,31 +594,26 @@ extern "C" int i2r_conv_halo(const i2r_conv_problem* probs, int nprob, void* str
       begin += G.p[i].ntiles;
     }
   } else {
-    int left = num_sms;
     int cnt[I2R_MAX_GROUP];
+    int left = num_sms;
     for (int i = 0; i < nprob; ++i) {
-      int c = static_cast<int>(cost[i] / total_cost * num_sms);
-      if (c < 1) c = 1;
-      if (c > G.p[i].ntiles) c = G.p[i].ntiles;
-      cnt[i] = c;
-      left -= c;
+      cnt[i] = 1;
+      --left;
     }
-    // hand out the remainder (or take back an overdraft) on the problems with the most tiles per CTA
-    while (left != 0) {
+    while (left > 0) {
       int best = -1;
       double bestv = -1;
       for (int i = 0; i < nprob; ++i) {
-        if (left > 0 && cnt[i] >= G.p[i].ntiles) continue;
-        if (left < 0 && cnt[i] <= 1) continue;
-        const double v = left > 0 ? cost[i] / cnt[i] : -cost[i] / cnt[i];
-        if (best < 0 || v > bestv) {
-          best = i;
+        if (cnt[i] >= G.p[i].ntiles) continue;
+        const double v = static_cast<double>((G.p[i].ntiles + cnt[i] - 1) / cnt[i]) * cost[i];
+        if (v > bestv) {
           bestv = v;
+          best = i;
         }
       }
       if (best < 0) break;
-      cnt[best] += left > 0 ? 1 : -1;
-      left += left > 0 ? -1 : 1;
+      ++cnt[best];
+      --left;
     }
     for (int i = 0; i < nprob; ++i) {
       G.p[i].cta_begin = begin;
