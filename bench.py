@@ -217,10 +217,8 @@ def main():
     ms_e2e = f0.elapsed_time(f1)
     clocks = sampler.finish() if rank == 0 else None
 
-    t = torch.tensor([ms, ms_e2e], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms, ms_e2e = float(t[0]), float(t[1])
+    from i2r_b200.sharding import max_over_ranks
+    ms, ms_e2e = max_over_ranks([ms, ms_e2e], device=dev)
 
     if rank == 0:
         peaks, peak_kind = _peaks()
@@ -247,8 +245,9 @@ def main():
             "model_frac_of_peak": value * GFLOP_PER_CROP["C2"] / 1e3 / (peak * world),
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                          "frac": achieved / peak, "traffic": None,
-                         "kernel": "igemm_tc_kernel (%d launches/forward, CUDA events around every launch of an "
-                                   "eager forward; algorithmic 2*M*Cout*Cin*taps)" % ig_launches,
+                         "kernel": "tcgen05 conv kernels conv_halo_kernel + igemm_tc_kernel (%d launch groups/forward, "
+                                   "CUDA events around every group of an eager forward; algorithmic "
+                                   "2*M*Cout*Cin*taps)" % ig_launches,
                          "peak_kind": "bf16_tflops_sustained, %s" % peak_kind},
             "clocks": clocks,
         }

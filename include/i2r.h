@@ -108,13 +108,16 @@ int i2r_maxpool3x3s2(const void* x, void* y, int NB, int H, int W, int C, void* 
 
 /* Single-head scaled-dot-product attention over ragged sequences (one per image):
  *   out[t, :] = softmax_j( scale * q[t,:] . k[j,:] ) v[j,:]   for j in the same sequence.
- * q,k,v,out: fp16 row-major with row strides ldq/ldk/ldv/ldo elements, head dim D (multiple of 16,
- * <= 96); cu_seqlens: int32 [nseq+1] token offsets on the device.  Equivalent to
- * nn.MultiheadAttention(nhead=1) with key_padding_mask on padded persons
+ * q,k,v,out: fp16 row-major with row strides ldq/ldk/ldv/ldo elements, head dim D (80 or 96);
+ * cu_seqlens: int32 [nseq+1] token offsets on the device; total_tokens = cu_seqlens[nseq].
+ * When few (sequence, query-tile) pairs exist the keys are split across CTAs and merged by a second
+ * kernel; `workspace` (i2r_attention_workspace_bytes(), may be NULL/0 = no splitting) holds the fp32 partials.
+ * Equivalent to nn.MultiheadAttention(nhead=1) with key_padding_mask on padded persons
  * (interformer_pureMulti.py:199-204; torch F.multi_head_attention_forward). */
+int64_t i2r_attention_workspace_bytes(int total_tokens, int D, int nseq, int max_seqlen);
 int i2r_attention_varlen(const void* q, const void* k, const void* v, void* out, int ldq, int ldk, int ldv,
-                         int ldo, int D, const int32_t* cu_seqlens, int nseq, int max_seqlen, float scale,
-                         void* stream);
+                         int ldo, int D, const int32_t* cu_seqlens, int nseq, int max_seqlen, int total_tokens,
+                         float scale, void* workspace, int64_t workspace_bytes, void* stream);
 
 /* y = LayerNorm(x) * gamma + beta over the last dim C (<= 256, multiple of 8), fp16 in/out, fp32
  * math; optional y2 = y + pos (the next layer's q/k input).  (interformer_pureMulti.py:206,:209) */

@@ -45,7 +45,9 @@ template <int HD>
 __global__ void __launch_bounds__(128) attention_kernel(const __half* __restrict__ q, const __half* __restrict__ k,
                                                         const __half* __restrict__ v, __half* __restrict__ out,
                                                         int ldq, int ldk, int ldv, int ldo,
-                                                        const int32_t* __restrict__ cu_seqlens, float scale_log2e) {
+                                                        const int32_t* __restrict__ cu_seqlens, float scale_log2e,
+                                                        int nsplit, float* __restrict__ opart,
+                                                        float* __restrict__ mlpart) {
   constexpr int PITCH = (HD + 8) * 2;
   constexpr int TILE = ATT_BK * PITCH;
   constexpr int KS = HD / 16;  // k-steps over the head dim
@@ -61,11 +63,17 @@ __global__ void __launch_bounds__(128) attention_kernel(const __half* __restrict
   const uint32_t sK = sQ + TILE;       // 2 stages
   const uint32_t sV = sK + 2 * TILE;   // 2 stages
 
-  const int ntiles = (L + ATT_BK - 1) / ATT_BK;
-  load_tile<HD>(sQ, q, ldq, t0 + q0, min(ATT_BQ, L - q0), tid);
-  load_tile<HD>(sK, k, ldk, t0, min(ATT_BK, L), tid);
-  load_tile<HD>(sV, v, ldv, t0, min(ATT_BK, L), tid);
-  cp_async_commit();
+  // split-KV: this CTA covers key tiles [kt_begin, kt_end) of the sequence (all of them when nsplit == 1)
+  const int ntiles_all = (L + ATT_BK - 1) / ATT_BK;
+  const int per_split = (ntiles_all + nsplit - 1) / nsplit;
+  const int kt_begin = blockIdx.z * per_split;
+  const int kt_end = min(ntiles_all, kt_begin + per_split);
+  if (kt_begin < kt_end) {
+    load_tile<HD>(sQ, q, ldq, t0 + q0, min(ATT_BQ, L - q0), tid);
+    load_tile<HD>(sK, k, ldk, t0 + kt_begin * ATT_BK, min(ATT_BK, L - kt_begin * ATT_BK), tid);
+    load_tile<HD>(sV, v, ldv, t0 + kt_begin * ATT_BK, min(ATT_BK, L - kt_begin * ATT_BK), tid);
+    cp_async_commit();
+  }
 
   uint32_t qf[KS][4];
   float o[DT][4];
@@ -75,9 +83,9 @@ __global__ void __launch_bounds__(128) attention_kernel(const __half* __restrict
     for (int j = 0; j < 4; ++j) o[i][j] = 0.f;
   float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
 
-  for (int kt = 0; kt < ntiles; ++kt) {
-    const int st = kt & 1;
-    if (kt + 1 < ntiles) {
+  for (int kt = kt_begin; kt < kt_end; ++kt) {
+    const int st = (kt - kt_begin) & 1;
+    if (kt + 1 < kt_end) {
       const int kr = (kt + 1) * ATT_BK;
       load_tile<HD>(sK + (st ^ 1) * TILE, k, ldk, t0 + kr, min(ATT_BK, L - kr), tid);
       load_tile<HD>(sV + (st ^ 1) * TILE, v, ldv, t0 + kr, min(ATT_BK, L - kr), tid);
@@ -87,7 +95,7 @@ __global__ void __launch_bounds__(128) attention_kernel(const __half* __restrict
       cp_async_wait<0>();
     }
     __syncthreads();
-    if (kt == 0) {
+    if (kt == kt_begin) {
 #pragma unroll
       for (int ks = 0; ks < KS; ++ks) {
         const int row = warp * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
@@ -179,22 +187,83 @@ __global__ void __launch_bounds__(128) attention_kernel(const __half* __restrict
   l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
   l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
   l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
-  const float i0 = 1.f / l0, i1 = 1.f / l1;
   const int r0 = q0 + warp * 16 + (lane >> 2);
   const int r1 = r0 + 8;
+  if (nsplit == 1) {
+    const float i0 = 1.f / l0, i1 = 1.f / l1;
 #pragma unroll
-  for (int dt = 0; dt < DT; ++dt) {
-    const int col = dt * 8 + (lane & 3) * 2;
-    if (r0 < L)
-      *reinterpret_cast<uint32_t*>(out + static_cast<int64_t>(t0 + r0) * ldo + col) = pack_h2(o[dt][0] * i0, o[dt][1] * i0);
-    if (r1 < L)
-      *reinterpret_cast<uint32_t*>(out + static_cast<int64_t>(t0 + r1) * ldo + col) = pack_h2(o[dt][2] * i1, o[dt][3] * i1);
+    for (int dt = 0; dt < DT; ++dt) {
+      const int col = dt * 8 + (lane & 3) * 2;
+      if (r0 < L)
+        *reinterpret_cast<uint32_t*>(out + static_cast<int64_t>(t0 + r0) * ldo + col) = pack_h2(o[dt][0] * i0, o[dt][1] * i0);
+      if (r1 < L)
+        *reinterpret_cast<uint32_t*>(out + static_cast<int64_t>(t0 + r1) * ldo + col) = pack_h2(o[dt][2] * i1, o[dt][3] * i1);
+    }
+  } else {
+    // un-normalised partial result + (running max, running sum) for the merge kernel
+    const int sp = blockIdx.z;
+#pragma unroll
+    for (int dt = 0; dt < DT; ++dt) {
+      const int col = dt * 8 + (lane & 3) * 2;
+      if (r0 < L)
+        *reinterpret_cast<float2*>(opart + (static_cast<int64_t>(t0 + r0) * nsplit + sp) * HD + col) = make_float2(o[dt][0], o[dt][1]);
+      if (r1 < L)
+        *reinterpret_cast<float2*>(opart + (static_cast<int64_t>(t0 + r1) * nsplit + sp) * HD + col) = make_float2(o[dt][2], o[dt][3]);
+    }
+    if ((lane & 3) == 0) {
+      if (r0 < L) *reinterpret_cast<float2*>(mlpart + (static_cast<int64_t>(t0 + r0) * nsplit + sp) * 2) = make_float2(m0, l0);
+      if (r1 < L) *reinterpret_cast<float2*>(mlpart + (static_cast<int64_t>(t0 + r1) * nsplit + sp) * 2) = make_float2(m1, l1);
+    }
   }
+}
+
+// Merge the split-KV partials: out = sum_s O_s 2^(m_s - M) / sum_s l_s 2^(m_s - M).  One warp per token row.
+template <int HD>
+__global__ void __launch_bounds__(256) attention_merge_kernel(const float* __restrict__ opart,
+                                                              const float* __restrict__ mlpart,
+                                                              __half* __restrict__ out, int ldo, int rows, int nsplit) {
+  const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  float M = -INFINITY;
+  for (int s = 0; s < nsplit; ++s) M = fmaxf(M, mlpart[(static_cast<int64_t>(row) * nsplit + s) * 2]);
+  float den = 0.f;
+  float acc[(HD + 31) / 32];
+#pragma unroll
+  for (int i = 0; i < (HD + 31) / 32; ++i) acc[i] = 0.f;
+  for (int s = 0; s < nsplit; ++s) {
+    const float2 ml = *reinterpret_cast<const float2*>(mlpart + (static_cast<int64_t>(row) * nsplit + s) * 2);
+    const float wgt = (ml.x == -INFINITY) ? 0.f : exp2f(ml.x - M);
+    den += ml.y * wgt;
+#pragma unroll
+    for (int i = 0; i < (HD + 31) / 32; ++i) {
+      const int c = lane + 32 * i;
+      if (c < HD) acc[i] += wgt * opart[(static_cast<int64_t>(row) * nsplit + s) * HD + c];
+    }
+  }
+  const float inv = 1.f / den;
+#pragma unroll
+  for (int i = 0; i < (HD + 31) / 32; ++i) {
+    const int c = lane + 32 * i;
+    if (c < HD) out[static_cast<int64_t>(row) * ldo + c] = __float2half_rn(acc[i] * inv);
+  }
+}
+
+static int choose_nsplit(int nseq, int max_seqlen) {
+  // enough CTAs for ~2 waves of 148 SMs, never more splits than key tiles, at most 8
+  const int qtiles = (max_seqlen + ATT_BQ - 1) / ATT_BQ;
+  const int ktiles = (max_seqlen + ATT_BK - 1) / ATT_BK;
+  int ns = (2 * 148 + qtiles * nseq - 1) / (qtiles * nseq);
+  if (ns > ktiles) ns = ktiles;
+  if (ns > 8) ns = 8;
+  if (ns < 1) ns = 1;
+  return ns;
 }
 
 template <int HD>
 static int launch_attention(const void* q, const void* k, const void* v, void* out, int ldq, int ldk, int ldv, int ldo,
-                            const int32_t* cu, int nseq, int max_seqlen, float scale, cudaStream_t st) {
+                            const int32_t* cu, int nseq, int max_seqlen, int total_tokens, float scale, void* ws,
+                            int64_t ws_bytes, cudaStream_t st) {
   constexpr int smem = 5 * ATT_BK * (HD + 8) * 2;
   static bool attr_done = false;
   if (!attr_done) {
@@ -205,27 +274,47 @@ static int launch_attention(const void* q, const void* k, const void* v, void* o
     }
     attr_done = true;
   }
-  dim3 grid((max_seqlen + ATT_BQ - 1) / ATT_BQ, nseq);
+  int nsplit = choose_nsplit(nseq, max_seqlen);
+  const int64_t need = static_cast<int64_t>(total_tokens) * nsplit * (HD + 2) * 4;
+  if (nsplit > 1 && (ws == nullptr || ws_bytes < need)) nsplit = 1;   // no workspace: single pass
+  float* opart = static_cast<float*>(ws);
+  float* mlpart = opart ? opart + static_cast<int64_t>(total_tokens) * nsplit * HD : nullptr;
+  dim3 grid((max_seqlen + ATT_BQ - 1) / ATT_BQ, nseq, nsplit);
   attention_kernel<HD><<<grid, 128, smem, st>>>(static_cast<const __half*>(q), static_cast<const __half*>(k),
                                                 static_cast<const __half*>(v), static_cast<__half*>(out), ldq, ldk,
-                                                ldv, ldo, cu, scale * 1.4426950408889634f);
-  return check_launch("attention_kernel");
+                                                ldv, ldo, cu, scale * 1.4426950408889634f, nsplit, opart, mlpart);
+  int rc = check_launch("attention_kernel");
+  if (rc || nsplit == 1) return rc;
+  attention_merge_kernel<HD><<<(total_tokens + 7) / 8, 256, 0, st>>>(opart, mlpart, static_cast<__half*>(out), ldo,
+                                                                     total_tokens, nsplit);
+  return check_launch("attention_merge_kernel");
 }
 
 }  // namespace i2r
 
+extern "C" int64_t i2r_attention_workspace_bytes(int total_tokens, int D, int nseq, int max_seqlen) {
+  const int ns = i2r::choose_nsplit(nseq, max_seqlen);
+  return ns > 1 ? static_cast<int64_t>(total_tokens) * ns * (D + 2) * 4 : 0;
+}
+
 extern "C" int i2r_attention_varlen(const void* q, const void* k, const void* v, void* out, int ldq, int ldk, int ldv,
-                                    int ldo, int D, const int32_t* cu_seqlens, int nseq, int max_seqlen, float scale,
+                                    int ldo, int D, const int32_t* cu_seqlens, int nseq, int max_seqlen,
+                                    int total_tokens, float scale, void* workspace, int64_t workspace_bytes,
                                     void* stream) {
   using namespace i2r;
-  if (!q || !k || !v || !out || !cu_seqlens || nseq <= 0 || max_seqlen <= 0 || (ldq | ldk | ldv | ldo) % 8 != 0) {
+  if (!q || !k || !v || !out || !cu_seqlens || nseq <= 0 || max_seqlen <= 0 || total_tokens <= 0 ||
+      (ldq | ldk | ldv | ldo) % 8 != 0) {
     set_error("i2r_attention_varlen: bad arguments");
     return I2R_E_BADARG;
   }
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   switch (D) {
-    case 96: return launch_attention<96>(q, k, v, out, ldq, ldk, ldv, ldo, cu_seqlens, nseq, max_seqlen, scale, st);
-    case 80: return launch_attention<80>(q, k, v, out, ldq, ldk, ldv, ldo, cu_seqlens, nseq, max_seqlen, scale, st);
+    case 96:
+      return launch_attention<96>(q, k, v, out, ldq, ldk, ldv, ldo, cu_seqlens, nseq, max_seqlen, total_tokens, scale,
+                                  workspace, workspace_bytes, st);
+    case 80:
+      return launch_attention<80>(q, k, v, out, ldq, ldk, ldv, ldo, cu_seqlens, nseq, max_seqlen, total_tokens, scale,
+                                  workspace, workspace_bytes, st);
     default:
       set_error("i2r_attention_varlen: head dim %d unsupported (80 or 96)", D);
       return I2R_E_UNSUPPORTED;

@@ -95,7 +95,7 @@ __device__ __forceinline__ void run_tile(const i2r_conv_problem& P, const int ti
     const int ohow = P.OH * P.OW;
 
     // Per-thread gather slots: chunk j = tid + i*128 -> (row, k-group).
-    int r_oy[KG], r_ox[KG], r_nb[KG];
+    int r_oy[KG], r_ox[KG], r_nb[KG], r_base[KG];
     uint32_t r_dst[KG];
     int r_g[KG];
 #pragma unroll
@@ -114,16 +114,19 @@ __device__ __forceinline__ void run_tile(const i2r_conv_problem& P, const int ti
         r_oy[i] = oy * P.stride;
         r_ox[i] = ox * P.stride;
         r_nb[i] = n * IHs;
+        r_base[i] = ((n * IHs + oy * P.stride) * IWs + ox * P.stride) * P.in_pix_stride + g * 8;   // in_shift == 0 only
       } else {
         r_oy[i] = -100000;  // always out of range -> zero fill
         r_ox[i] = 0;
         r_nb[i] = 0;
+        r_base[i] = 0;
       }
     }
 
     int it = 0;
     for (int t = 0; t < P.ntaps; ++t) {
       const int dy = P.dy[t], dx = P.dx[t];
+      const int tapoff = (dy * IWs + dx) * P.in_pix_stride;   // element offset of this tap (in_shift == 0)
       for (int c = 0; c < nchunks; ++c, ++it) {
         const int kgc = min(8, (P.Cin - c * 64) >> 3);   // real 16-byte chunks per row in this K-chunk
         const int s = it % STAGES;
@@ -134,19 +137,33 @@ __device__ __forceinline__ void run_tile(const i2r_conv_problem& P, const int ti
           mbar_arrive_expect_tx(bar_full + 8 * s, b_bytes);
           bulk_g2s(a_s + a_bytes, Wp + static_cast<size_t>(it) * b_bytes, b_bytes, bar_full + 8 * s);
         }
+        if (sh == 0) {
+          // fast path: source address = per-row base + per-tap offset (+ K-chunk), bounds from two compares
+          const __half* xc = X + tapoff + c * 64;
 #pragma unroll
-        for (int i = 0; i < KG; ++i) {
-          const int iy = r_oy[i] + dy;
-          const int ix = r_ox[i] + dx;
-          const bool ok = (static_cast<unsigned>(iy) < static_cast<unsigned>(P.IH)) &&
-                          (static_cast<unsigned>(ix) < static_cast<unsigned>(P.IW));
-          if (r_g[i] < kgc) {
-            const __half* src = X;
-            if (ok) {
-              const int64_t pix = static_cast<int64_t>(r_nb[i] + (iy >> sh)) * IWs + (ix >> sh);
-              src = X + pix * P.in_pix_stride + c * 64 + r_g[i] * 8;
+          for (int i = 0; i < KG; ++i) {
+            if (r_g[i] < kgc) {
+              const bool ok = (static_cast<unsigned>(r_oy[i] + dy) < static_cast<unsigned>(P.IH)) &&
+                              (static_cast<unsigned>(r_ox[i] + dx) < static_cast<unsigned>(P.IW));
+              cp_async16(a_s + r_dst[i], ok ? static_cast<const void*>(xc + r_base[i]) : static_cast<const void*>(X),
+                         ok ? 16u : 0u);
             }
-            cp_async16(a_s + r_dst[i], src, ok ? 16u : 0u);
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < KG; ++i) {
+            const int iy = r_oy[i] + dy;
+            const int ix = r_ox[i] + dx;
+            const bool ok = (static_cast<unsigned>(iy) < static_cast<unsigned>(P.IH)) &&
+                            (static_cast<unsigned>(ix) < static_cast<unsigned>(P.IW));
+            if (r_g[i] < kgc) {
+              const __half* src = X;
+              if (ok) {
+                const int64_t pix = static_cast<int64_t>(r_nb[i] + (iy >> sh)) * IWs + (ix >> sh);
+                src = X + pix * P.in_pix_stride + c * 64 + r_g[i] * 8;
+              }
+              cp_async16(a_s + r_dst[i], src, ok ? 16u : 0u);
+            }
           }
         }
         cp_async_commit();
@@ -406,6 +423,10 @@ static int validate(const i2r_conv_problem& P, int idx) {
   if (P.in_pix_stride % 8 != 0 || P.in_pix_stride < P.Cin) {
     set_error("conv problem %d: in_pix_stride=%d", idx, P.in_pix_stride);
     return I2R_E_BADARG;
+  }
+  if (static_cast<int64_t>(P.NB) * P.IH * P.IW * P.in_pix_stride >= (1ll << 31)) {
+    set_error("conv problem %d: input larger than 2^31 elements", idx);
+    return I2R_E_UNSUPPORTED;
   }
   if (P.NB <= 0 || P.OH <= 0 || P.OW <= 0 || P.IH <= 0 || P.IW <= 0 || P.stride <= 0 || P.out_mul <= 0) {
     set_error("conv problem %d: bad extents", idx);

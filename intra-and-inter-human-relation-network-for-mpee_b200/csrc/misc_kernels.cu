@@ -26,63 +26,79 @@ int check_launch(const char* what) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// 3x3 stride-2 pad-1 convolution with Cin in {1,3}: each thread produces CPT=16 output channels of one
-// output pixel; a warp covers 8 consecutive pixels x 4 channel groups of a 64-channel output.
+// 3x3 stride-2 pad-1 convolution with Cin in {1,3} and 64 output channels (stem / mask embedding).
+// CTA = 8 x 32 output pixels: the (17 x 65 x CIN) fp32 input patch is staged in shared memory with coalesced
+// loads; each thread owns one output pixel and all 64 channels (weights are warp-broadcast float4 reads),
+// then writes its 128-byte NHWC row.
+constexpr int STEM_TH = 8, STEM_TW = 32, STEM_PH = 2 * STEM_TH + 1, STEM_PW = 2 * STEM_TW + 1, STEM_PWP = STEM_PW + 1;
+
 template <int CIN>
 __global__ void __launch_bounds__(256) stem_conv_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                         const float* __restrict__ scale,
                                                         const float* __restrict__ bias, __half* __restrict__ y,
-                                                        int NB, int H, int W, int Cout) {
-  extern __shared__ float sw[];  // [CIN*9][Cout] then scale[Cout], bias[Cout]
-  const int K = CIN * 9;
-  for (int i = threadIdx.x; i < K * Cout; i += blockDim.x) sw[i] = w[i];
-  float* ssc = sw + K * Cout;
-  float* sbi = ssc + Cout;
-  for (int i = threadIdx.x; i < Cout; i += blockDim.x) {
-    ssc[i] = scale[i];
-    sbi[i] = bias[i];
+                                                        int NB, int H, int W) {
+  constexpr int K = CIN * 9;
+  __shared__ __align__(16) float sw[K * 64];
+  __shared__ __align__(16) float ssc[64];
+  __shared__ __align__(16) float sbi[64];
+  __shared__ float patch[CIN][STEM_PH][STEM_PWP];
+  const int tid = threadIdx.x;
+  for (int i = tid; i < K * 64; i += 256) sw[i] = w[i];
+  if (tid < 64) {
+    ssc[tid] = scale[tid];
+    sbi[tid] = bias[tid];
+  }
+  const int OH = H >> 1, OW = W >> 1;
+  const int n = blockIdx.z;
+  const int oy0 = blockIdx.y * STEM_TH, ox0 = blockIdx.x * STEM_TW;
+  const int iy0 = oy0 * 2 - 1, ix0 = ox0 * 2 - 1;
+  for (int i = tid; i < CIN * STEM_PH * STEM_PW; i += 256) {
+    const int c = i / (STEM_PH * STEM_PW);
+    const int r = i - c * (STEM_PH * STEM_PW);
+    const int py = r / STEM_PW, px = r - py * STEM_PW;
+    const int iy = iy0 + py, ix = ix0 + px;
+    float v = 0.f;
+    if (iy >= 0 && iy < H && ix >= 0 && ix < W) v = __ldg(x + ((static_cast<int64_t>(n) * CIN + c) * H + iy) * W + ix);
+    patch[c][py][px] = v;
   }
   __syncthreads();
-  const int OH = H >> 1, OW = W >> 1;
-  const int groups = Cout / 16;
-  const int64_t total = static_cast<int64_t>(NB) * OH * OW * groups;
-  for (int64_t idx = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; idx < total;
-       idx += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-    const int g = static_cast<int>(idx % groups);
-    const int64_t p = idx / groups;
-    const int ox = static_cast<int>(p % OW);
-    const int oy = static_cast<int>((p / OW) % OH);
-    const int n = static_cast<int>(p / (static_cast<int64_t>(OW) * OH));
-    float acc[16];
+  const int ty = tid >> 5, tx = tid & 31;
+  const int oy = oy0 + ty, ox = ox0 + tx;
+  float acc[64];
 #pragma unroll
-    for (int i = 0; i < 16; ++i) acc[i] = 0.f;
+  for (int i = 0; i < 64; ++i) acc[i] = 0.f;
+  const float4* sw4 = reinterpret_cast<const float4*>(sw);
 #pragma unroll
-    for (int c = 0; c < CIN; ++c) {
-      const float* xc = x + (static_cast<int64_t>(n) * CIN + c) * H * W;
+  for (int c = 0; c < CIN; ++c) {
 #pragma unroll
-      for (int ky = 0; ky < 3; ++ky) {
-        const int iy = oy * 2 - 1 + ky;
+    for (int ky = 0; ky < 3; ++ky) {
 #pragma unroll
-        for (int kx = 0; kx < 3; ++kx) {
-          const int ix = ox * 2 - 1 + kx;
-          float v = 0.f;
-          if (iy >= 0 && iy < H && ix >= 0 && ix < W) v = __ldg(xc + static_cast<int64_t>(iy) * W + ix);
-          const float* wk = sw + ((c * 3 + ky) * 3 + kx) * Cout + g * 16;
+      for (int kx = 0; kx < 3; ++kx) {
+        const float v = patch[c][2 * ty + ky][2 * tx + kx];
+        const int k = (c * 3 + ky) * 3 + kx;
 #pragma unroll
-          for (int i = 0; i < 16; ++i) acc[i] = fmaf(v, wk[i], acc[i]);
+        for (int q = 0; q < 16; ++q) {
+          const float4 wq = sw4[k * 16 + q];
+          acc[4 * q + 0] = fmaf(v, wq.x, acc[4 * q + 0]);
+          acc[4 * q + 1] = fmaf(v, wq.y, acc[4 * q + 1]);
+          acc[4 * q + 2] = fmaf(v, wq.z, acc[4 * q + 2]);
+          acc[4 * q + 3] = fmaf(v, wq.w, acc[4 * q + 3]);
         }
       }
     }
-    uint32_t o[8];
+  }
+  if (oy < OH && ox < OW) {
+    uint4* dst = reinterpret_cast<uint4*>(y + ((static_cast<int64_t>(n) * OH + oy) * OW + ox) * 64);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const float a = fmaxf(acc[2 * i] * ssc[g * 16 + 2 * i] + sbi[g * 16 + 2 * i], 0.f);
-      const float b = fmaxf(acc[2 * i + 1] * ssc[g * 16 + 2 * i + 1] + sbi[g * 16 + 2 * i + 1], 0.f);
-      o[i] = pack_h2(a, b);
+    for (int q = 0; q < 8; ++q) {
+      uint32_t o[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int c = q * 8 + 2 * i;
+        o[i] = pack_h2(fmaxf(acc[c] * ssc[c] + sbi[c], 0.f), fmaxf(acc[c + 1] * ssc[c + 1] + sbi[c + 1], 0.f));
+      }
+      dst[q] = make_uint4(o[0], o[1], o[2], o[3]);
     }
-    uint4* dst = reinterpret_cast<uint4*>(y + p * Cout + g * 16);
-    dst[0] = make_uint4(o[0], o[1], o[2], o[3]);
-    dst[1] = make_uint4(o[4], o[5], o[6], o[7]);
   }
 }
 
@@ -239,17 +255,16 @@ extern "C" int i2r_sm_count(int dev) {
 
 extern "C" int i2r_stem_conv3x3s2(const float* x, const float* w, const float* scale, const float* bias, void* y,
                                   int NB, int Cin, int H, int W, int Cout, void* stream) {
-  if (!x || !w || !scale || !bias || !y || NB <= 0 || (H & 1) || (W & 1) || Cout % 16 != 0 || Cout > 128) {
-    set_error("i2r_stem_conv3x3s2: bad arguments (Cin=%d H=%d W=%d Cout=%d)", Cin, H, W, Cout);
+  if (!x || !w || !scale || !bias || !y || NB <= 0 || (H & 1) || (W & 1) || Cout != 64) {
+    set_error("i2r_stem_conv3x3s2: bad arguments (Cin=%d H=%d W=%d Cout=%d; Cout must be 64)", Cin, H, W, Cout);
     return I2R_E_BADARG;
   }
-  const int64_t items = static_cast<int64_t>(NB) * (H / 2) * (W / 2) * (Cout / 16);
-  const size_t smem = (static_cast<size_t>(Cin) * 9 * Cout + 2 * Cout) * sizeof(float);
+  const dim3 grid((W / 2 + STEM_TW - 1) / STEM_TW, (H / 2 + STEM_TH - 1) / STEM_TH, NB);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (Cin == 3) {
-    stem_conv_kernel<3><<<grid_for(items, 256), 256, smem, st>>>(x, w, scale, bias, static_cast<__half*>(y), NB, H, W, Cout);
+    stem_conv_kernel<3><<<grid, 256, 0, st>>>(x, w, scale, bias, static_cast<__half*>(y), NB, H, W);
   } else if (Cin == 1) {
-    stem_conv_kernel<1><<<grid_for(items, 256), 256, smem, st>>>(x, w, scale, bias, static_cast<__half*>(y), NB, H, W, Cout);
+    stem_conv_kernel<1><<<grid, 256, 0, st>>>(x, w, scale, bias, static_cast<__half*>(y), NB, H, W);
   } else {
     set_error("i2r_stem_conv3x3s2: Cin=%d unsupported (1 or 3)", Cin);
     return I2R_E_UNSUPPORTED;

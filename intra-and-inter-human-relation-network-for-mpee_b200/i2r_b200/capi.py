@@ -14,7 +14,7 @@ F_OUT_F32 = 4
 
 EXPORTS = [
     "i2r_version", "i2r_last_error", "i2r_device_check", "i2r_sm_count", "i2r_conv_igemm", "i2r_conv_halo", "i2r_conv_halo_supported", "i2r_debug_trace",
-    "i2r_sizeof_conv_problem", "i2r_stem_conv3x3s2", "i2r_maxpool3x3s2", "i2r_attention_varlen", "i2r_layernorm", "i2r_add_f16",
+    "i2r_sizeof_conv_problem", "i2r_stem_conv3x3s2", "i2r_maxpool3x3s2", "i2r_attention_varlen", "i2r_attention_workspace_bytes", "i2r_layernorm", "i2r_add_f16",
 ]
 
 
@@ -66,7 +66,9 @@ def load():
         lib.i2r_debug_trace.argtypes = [vp, i32, i32]
         lib.i2r_stem_conv3x3s2.argtypes = [vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp]
         lib.i2r_maxpool3x3s2.argtypes = [vp, vp, i32, i32, i32, i32, vp]
-        lib.i2r_attention_varlen.argtypes = [vp, vp, vp, vp, i32, i32, i32, i32, i32, vp, i32, i32, f32, vp]
+        lib.i2r_attention_varlen.argtypes = [vp, vp, vp, vp, i32, i32, i32, i32, i32, vp, i32, i32, i32, f32, vp, i64, vp]
+        lib.i2r_attention_workspace_bytes.argtypes = [i32, i32, i32, i32]
+        lib.i2r_attention_workspace_bytes.restype = i64
         lib.i2r_layernorm.argtypes = [vp, vp, vp, vp, vp, vp, i32, i32, f32, vp]
         lib.i2r_add_f16.argtypes = [vp, vp, vp, i64, vp]
         for name in EXPORTS:

@@ -254,9 +254,12 @@ class Runner:
         t, d = q.shape
         out = torch.empty((t, d), dtype=torch.float16, device=q.device)
         nseq = cu_seqlens.numel() - 1
+        ws_bytes = int(self.lib.i2r_attention_workspace_bytes(t, d, nseq, max_seqlen))
+        ws = torch.empty(max(ws_bytes, 16), dtype=torch.uint8, device=q.device) if ws_bytes else None
         capi.check(self.lib.i2r_attention_varlen(q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(),
                                                   q.stride(0), k.stride(0), v.stride(0), out.stride(0), d,
-                                                  cu_seqlens.data_ptr(), nseq, max_seqlen, scale, _stream_ptr()),
+                                                  cu_seqlens.data_ptr(), nseq, max_seqlen, t, scale,
+                                                  ws.data_ptr() if ws is not None else None, ws_bytes, _stream_ptr()),
                    "i2r_attention_varlen")
         self.launches += 1
         return out
