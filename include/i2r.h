@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define I2R_ABI_VERSION 1
+#define I2R_ABI_VERSION 2
 
 #define I2R_E_BADARG (-1)
 #define I2R_E_UNSUPPORTED (-2)
@@ -72,6 +72,9 @@ typedef struct i2r_conv_problem {
   int8_t dy[I2R_MAX_TAPS + 3];
   int8_t dx[I2R_MAX_TAPS + 3];
   uint32_t flags;
+  const void* w_folded;    /* i2r_conv_halo only: fp16 [1 + ntaps*ceil(Cin/64)][Npad][64] -- block 0 is the bias  */
+                           /* block (K slot 0 = fp16(bias), slot 1 = fp16(bias - slot 0)), blocks 1.. are `w`     */
+                           /* with scale[n] folded into every row n before the fp16 rounding                     */
 } i2r_conv_problem;
 
 int i2r_version(void);
@@ -128,10 +131,14 @@ int i2r_layernorm(const void* x, const float* gamma, const float* beta, const vo
 int i2r_add_f16(const void* a, const void* b, void* y, int64_t n, void* stream);
 
 /* Profiling aid: while dev_buffer != NULL, CTA `cta` of every i2r_conv_halo launch writes (tag<<32 | tile, clock64)
- * pairs into three role regions (producer, MMA, epilogue) of `capacity_events` pairs each (zero-filled by the caller).  Tags: 1/2/3
+ * pairs into four role regions (producer, MMA, epilogue, kernel start/end) of `capacity_events` pairs each (zero-filled by the caller).  Tags: 1/2/3
  * producer slot free / loads issued / stage published, 10/11/12 MMA accumulator free / operands landed / tile
  * committed, 20/21 epilogue accumulator ready / tile stored.  Pass NULL to switch tracing off. */
 int i2r_debug_trace(void* dev_buffer, int capacity_events, int cta);
+/* Profiling aid: ablation bits for i2r_conv_halo (results become wrong): 1 = epilogue hand-shake only,
+ * 2 = epilogue without global stores / residual loads, 4 = activation TMA only for the first ring pass,
+ * 8 = no MMAs (commits only).  0 restores the product behaviour. */
+int i2r_debug_flags(int flags);
 
 /* sizeof(i2r_conv_problem) as compiled -- lets the ctypes binding verify its struct layout. */
 int i2r_sizeof_conv_problem(void);

@@ -13,6 +13,9 @@
 //   B operand   : weights pre-packed in core-matrix order, moved by the TMA unit as 1-D bulk copies;
 //                 resident in shared memory for the whole kernel when they fit (<= 120 KB), else streamed
 //                 per (K-chunk, tap) through an mbarrier ring.
+//   scale/bias  : the per-channel BatchNorm scale is folded into the packed fp16 weights and the bias enters through
+//                 ONE extra K=16 MMA per tile (A = a tile of ones, B = [bias_hi, bias_lo, 0...] per channel) that
+//                 initialises the accumulator, so the epilogue touches neither shared nor constant memory.
 //   D           : two TMEM accumulators so the epilogue of tile i overlaps the MMAs of tile i+1.
 //   warps       : 0 = activation TMA producer, 1 = weight producer, 2 = TMEM owner + MMA issuer,
 //                 4..11 = epilogue (TMEM -> registers -> scale/bias/residual/ReLU -> global), two warps per
@@ -31,8 +34,6 @@ namespace i2r {
 struct HaloProblem {
   const __half* x;
   const uint8_t* w;
-  const float* scale;
-  const float* bias;
   const __half* add0;
   const __half* add1;
   void* y;
@@ -54,19 +55,69 @@ struct HaloProblem {
 
 struct HaloGroup {
   CUtensorMap amap[I2R_MAX_GROUP];
-  unsigned long long* trace;   // optional event trace (tools/trace_halo.py): three role regions of trace_cap (tag<<32|tile, clock64) pairs
+  unsigned long long* trace;   // optional event trace (tools/trace_halo.py): four role regions of trace_cap (tag<<32|tile, clock64) pairs
   int trace_cta, trace_cap;
+  int dbg;                     // debug ablations (i2r_debug_flags): 1 = epilogue hand-shake only, 2 = no global stores / residual loads
   HaloProblem p[I2R_MAX_GROUP];
   int nprob;
 };
 
+// Launch parameters live in the constant bank; a loop that mentions P.field re-reads it with an indexed uniform
+// load (LDCU c[0][UR+off], ~100 cycles of latency on the branch that consumes it -- measured as the top
+// non-barrier stall of the epilogue).  Passing every field through an empty asm makes it an ordinary
+// register value the compiler cannot rematerialise from the constant bank.
+__device__ __forceinline__ int opaque(int v) {
+  asm("" : "+r"(v));
+  return v;
+}
+__device__ __forceinline__ uint32_t opaque(uint32_t v) {
+  asm("" : "+r"(v));
+  return v;
+}
+template <class T>
+__device__ __forceinline__ T* opaque(T* v) {
+  asm("" : "+l"(v));
+  return v;
+}
+__device__ __forceinline__ HaloProblem load_problem(const HaloProblem& s) {
+  HaloProblem p;
+  p.x = opaque(s.x); p.w = opaque(s.w); p.add0 = opaque(s.add0); p.add1 = opaque(s.add1); p.y = opaque(s.y);
+  p.NB = opaque(s.NB); p.H = opaque(s.H); p.W = opaque(s.W); p.C = opaque(s.C); p.Cout = opaque(s.Cout);
+  p.Npad = opaque(s.Npad); p.ntaps = opaque(s.ntaps); p.halo = opaque(s.halo); p.KCH = opaque(s.KCH);
+  p.nkc = opaque(s.nkc); p.kgp = opaque(s.kgp); p.nchp = opaque(s.nchp); p.tiles_x = opaque(s.tiles_x);
+  p.tiles_per_img = opaque(s.tiles_per_img); p.ntiles = opaque(s.ntiles);
+  p.in_pix_stride = opaque(s.in_pix_stride); p.out_pix_stride = opaque(s.out_pix_stride);
+  p.add_pix_stride = opaque(s.add_pix_stride); p.plane = opaque(s.plane); p.flags = opaque(s.flags);
+  p.cta_begin = opaque(s.cta_begin); p.cta_count = opaque(s.cta_count); p.w_resident = opaque(s.w_resident);
+  p.w_total_bytes = opaque(s.w_total_bytes); p.w_stage_bytes = opaque(s.w_stage_bytes);
+  p.a_stage_bytes = opaque(s.a_stage_bytes); p.a_tx_bytes = opaque(s.a_tx_bytes);
+  p.a_stages = opaque(s.a_stages); p.w_stages = opaque(s.w_stages); p.w_off = opaque(s.w_off);
+  return p;
+}
+
 constexpr int T_THREADS = 384;
 constexpr int T_TW = 8, T_TH = 16;
-constexpr uint32_t T_A_OFF = 3072;          // dynamic smem: [0,256) barriers | [256,2304) scale,bias | A ring
+constexpr uint32_t T_ONES_OFF = 1024;       // 1 KB of fp16 1.0: the A operand of the bias MMA
+constexpr uint32_t T_A_OFF = 2048;          // dynamic smem: [0,256) barriers | [1024,2048) ones | A ring
 constexpr uint32_t T_MAX_SMEM = 226 * 1024;   // + 1 KB alignment slack = 227 KB opt-in limit
 constexpr uint32_t T_W_RES_MAX = 120 * 1024;
 
 // Fire-and-forget trace record (no atomics: each role owns region `role` of the buffer and a private counter).
+// clock read that cannot issue before `dep` has been produced (scoreboard dependency through the asm operand)
+__device__ __forceinline__ unsigned long long clock_after(uint32_t dep) {
+  unsigned long long t;
+  asm volatile("{\n\t.reg .b32 z;\n\tand.b32 z, %1, 0;\n\tmov.u64 %0, %%clock64;\n\t}" : "=l"(t) : "r"(dep) : "memory");
+  return t;
+}
+__device__ __forceinline__ void trace_ev_dep(unsigned long long* tr, int cap, int role, int& idx, int tag, int tile,
+                                             uint32_t dep) {
+  if (tr != nullptr && idx < cap) {
+    unsigned long long* e = tr + (static_cast<size_t>(role) * cap + idx) * 2;
+    e[0] = (static_cast<unsigned long long>(tag) << 32) | static_cast<unsigned>(tile);
+    e[1] = clock_after(dep);
+    ++idx;
+  }
+}
 __device__ __forceinline__ void trace_ev(unsigned long long* tr, int cap, int role, int& idx, int tag, int tile) {
   if (tr != nullptr && idx < cap) {
     unsigned long long* e = tr + (static_cast<size_t>(role) * cap + idx) * 2;
@@ -93,7 +144,7 @@ __device__ __forceinline__ void issue_taps(uint32_t d_tmem, uint32_t a_lo, uint3
 template <int NTAPS>
 __device__ __forceinline__ void mma_role(const HaloProblem& P, const int cta, const uint32_t sbase,
                                          const uint32_t tmem_base, const uint32_t ncols, unsigned long long* tr,
-                                         const int trcap) {
+                                         const int trcap, const int dbg, const int iw) {
   constexpr int HALO = NTAPS == 9 ? 1 : 0;
   constexpr int PW = T_TW + 2 * HALO;   // halo line = PW pixels = PW 128-byte rows (dense TMA box)
   constexpr uint32_t A_SBO = PW * 128;
@@ -113,25 +164,57 @@ __device__ __forceinline__ void mma_role(const HaloProblem& P, const int cta, co
   const bool resident = P.w_resident != 0;
   const bool leader = elect_one();
   int tri = 0;
-  int as = 0, ws = 0, acc = 0;
-  uint32_t aph = 0, wph = 0, accph = 0;
+  // Two issuer warps alternate over the CTA's tiles: issuer iw owns TMEM accumulator iw and local tiles
+  // iw, iw+2, ...  While one issuer sits in its barrier waits (~300 cycles each with the shared-memory port
+  // busy) the other keeps the 8-deep MMA queue fed.
+  // (streamed-weight problems keep ONE issuer and the full rings: the weight stream is sequential anyway and needs
+  // the deeper prefetch)
+  const bool dual = resident;
+  if (!dual && iw != 0) return;
+  int acc = dual ? iw : 0;
+  uint32_t accph = 0;
+  // Each issuer consumes its OWN half of the activation ring and of the weight ring (stages [iw*half, iw*half+half)):
+  // an mbarrier phase-parity wait is only sound when the waiter observes every phase of the barrier, which two
+  // issuers skipping each other's stages of one shared ring would not.
+  const int a_half = dual ? P.a_stages >> 1 : P.a_stages, w_half = dual ? P.w_stages >> 1 : P.w_stages;
+  const int a_first = iw * a_half, w_first = iw * w_half;
+  int as = 0, ws = 0;
+  uint32_t aph = 0, wph = 0;
   if (resident) mbar_wait(bar_wres, 0);
-  for (int t = cta; t < P.ntiles; t += P.cta_count) {
+  if (leader) trace_ev(tr, trcap, 1, tri, 13, 0);
+  const uint32_t ones_lo = sw128_desc_lo(sbase + T_ONES_OFF);
+  const uint32_t ones_hi = sw128_desc_hi(0, 0);   // SBO 0: every 8-row group reads the same 1 KB atom of ones
+  for (int t = cta + iw * P.cta_count; t < P.ntiles; t += (dual ? 2 : 1) * P.cta_count) {
+    const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc) * (ncols >> 1);
     mbar_wait(bar_accempty + 8 * acc, accph ^ 1);
     tc_fence_after();
     if (leader) trace_ev(tr, trcap, 1, tri, 10, t);
-    const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc) * (ncols >> 1);
+    // accumulator := bias (block 0 of the packed weights), then every tap accumulates
+    if (resident) {
+      if (leader) umma_f16(d_tmem, desc64(ones_lo, ones_hi), desc64(w_lo0, b_hi), idesc, 0u);
+    } else {
+      mbar_wait(bar_wfull + 8 * (w_first + ws), wph);
+      tc_fence_after();
+      if (leader) {
+        umma_f16(d_tmem, desc64(ones_lo, ones_hi), desc64(w_lo0 + (w_first + ws) * w_stage16, b_hi), idesc, 0u);
+        umma_commit(bar_wempty + 8 * (w_first + ws));
+      }
+      if (++ws == w_half) {
+        ws = 0;
+        wph ^= 1;
+      }
+    }
     for (int kc = 0; kc < P.nkc; ++kc) {
-      mbar_wait(bar_afull + 8 * as, aph);
+      mbar_wait(bar_afull + 8 * (a_first + as), aph);
       tc_fence_after();
       if (leader) trace_ev(tr, trcap, 1, tri, 11, t);
-      const uint32_t a_lo = a_lo0 + as * a_stage16;
-      const uint32_t b_lo_kc = w_lo0 + kc * w_stage16;
+      const uint32_t a_lo = a_lo0 + (a_first + as) * a_stage16;
+      const uint32_t b_lo_kc = w_lo0 + (kc + 1) * w_stage16;   // block 0 is the bias block
       const int ksteps = min(4, (P.C - kc * 64) >> 4);   // K=16 steps holding real channels in this chunk
-      const uint32_t acc_kc = (kc != 0) ? 1u : 0u;
+      const uint32_t acc_kc = 1u;
       if (resident) {
         // one straight-line burst of NTAPS x ksteps MMAs issued by the elected lane
-        if (leader) {
+        if (leader && !(dbg & 8)) {
           switch (ksteps) {
             case 4: issue_taps<NTAPS, 4>(d_tmem, a_lo, a_hi, b_lo_kc, b_tap, b_hi, idesc, acc_kc); break;
             case 3: issue_taps<NTAPS, 3>(d_tmem, a_lo, a_hi, b_lo_kc, b_tap, b_hi, idesc, acc_kc); break;
@@ -142,10 +225,10 @@ __device__ __forceinline__ void mma_role(const HaloProblem& P, const int cta, co
       } else {
 #pragma unroll
         for (int tap = 0; tap < NTAPS; ++tap) {
-          mbar_wait(bar_wfull + 8 * ws, wph);
+          mbar_wait(bar_wfull + 8 * (w_first + ws), wph);
           tc_fence_after();
           if (leader) {
-            const uint32_t b_lo = w_lo0 + ws * w_stage16;
+            const uint32_t b_lo = w_lo0 + (w_first + ws) * w_stage16;
             const uint32_t a_t = a_lo + (HALO ? static_cast<uint32_t>(((tap / 3) * PW + (tap % 3)) * 8) : 0u);
             const uint32_t accf = tap ? 1u : acc_kc;
             switch (ksteps) {
@@ -154,24 +237,28 @@ __device__ __forceinline__ void mma_role(const HaloProblem& P, const int cta, co
               case 2: issue_ksteps<2>(d_tmem, a_t, a_hi, b_lo, b_hi, idesc, accf); break;
               default: issue_ksteps<1>(d_tmem, a_t, a_hi, b_lo, b_hi, idesc, accf); break;
             }
-            umma_commit(bar_wempty + 8 * ws);
+            umma_commit(bar_wempty + 8 * (w_first + ws));
           }
-          if (++ws == P.w_stages) {
+          if (++ws == w_half) {
             ws = 0;
             wph ^= 1;
           }
         }
       }
-      if (leader) umma_commit(bar_aempty + 8 * as);
-      if (++as == P.a_stages) {
+      if (leader) umma_commit(bar_aempty + 8 * (a_first + as));
+      if (++as == a_half) {
         as = 0;
         aph ^= 1;
       }
     }
     if (leader) umma_commit(bar_accfull + 8 * acc);
     if (leader) trace_ev(tr, trcap, 1, tri, 12, t);
-    acc ^= 1;
-    if (acc == 0) accph ^= 1;
+    if (dual) {
+      accph ^= 1;
+    } else {
+      acc ^= 1;
+      if (acc == 0) accph ^= 1;
+    }
   }
 }
 
@@ -186,21 +273,144 @@ __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
 }
 
+// ---------------------------------------------------------------------------------------------- epilogue
+// One thread = one accumulator row (pixel) x a contiguous range of 8-channel chunks [cb, ce).  OUT: 0 = fp16 NHWC
+// (the hot mode: nothing but TMEM loads, residual adds, ReLU, packs and 16-byte stores), 1 = fp32 modes (flags).
+struct EpiArgs {
+  const __half* add0;
+  const __half* add1;
+  void* y;
+  int H, W, Cout, tiles_x, tiles_per_img, ntiles, cta_count;
+  int out_pix_stride, add_pix_stride, plane;
+  uint32_t flags;
+};
+
+template <int OUT>
+__device__ __forceinline__ void epilogue_role(const EpiArgs E, const int cta, const uint32_t sbase, const uint32_t tmem_base,
+                                              const uint32_t ncols, const int Npad, const int ew, const int quad,
+                                              const int lane, unsigned long long* tr, const int trcap, const int dbg) {
+  const uint32_t bar_accfull = sbase + 128, bar_accempty = sbase + 144;
+  const int row = quad * 32 + lane;
+  const int ty_in = row >> 3, tx_in = row & 7;
+  const int n8 = Npad >> 3, half8 = (n8 + 1) >> 1;
+  const int cb = (ew >> 2) ? half8 : 0, ce = (ew >> 2) ? n8 : half8;   // 8-column chunks [cb, ce)
+  const float lo = (E.flags & I2R_F_RELU) ? 0.0f : -3.0e38f;
+  const float inv_tpi = 1.0f / static_cast<float>(E.tiles_per_img), inv_tx = 1.0f / static_cast<float>(E.tiles_x);
+  const bool has0 = E.add0 != nullptr && !(dbg & 2), has1 = E.add1 != nullptr && !(dbg & 2);
+  int acc = 0, tri = 0;
+  uint32_t accph = 0;
+  for (int t = cta; t < E.ntiles; t += E.cta_count) {
+    // tile coordinates without integer division (exact for t < 2^22)
+    const int n = __float2int_rd((static_cast<float>(t) + 0.5f) * inv_tpi);
+    const int r = t - n * E.tiles_per_img;
+    const int ty = __float2int_rd((static_cast<float>(r) + 0.5f) * inv_tx);
+    const int tx = r - ty * E.tiles_x;
+    const int x = tx * T_TW + tx_in, y = ty * T_TH + ty_in;
+    const bool valid = (x < E.W) && (y < E.H);
+    const int p = (n * E.H + y) * E.W + x;                       // pixel index (< 2^31)
+    const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + static_cast<uint32_t>(acc) * (ncols >> 1);
+    const __half* a0 = E.add0 + static_cast<int64_t>(p) * E.add_pix_stride;
+    const __half* a1 = E.add1 + static_cast<int64_t>(p) * E.add_pix_stride;
+    bool waited = false;
+    for (int c = cb; c < ce; c += 4) {
+      const int nc = min(4, ce - c);
+      // residual loads first: their latency hides behind the accumulator wait
+      uint4 r0[4], r1[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        r0[j] = make_uint4(0, 0, 0, 0);
+        r1[j] = make_uint4(0, 0, 0, 0);
+        if (j < nc && valid && (c + j) * 8 < E.Cout) {
+          if (has0) r0[j] = __ldg(reinterpret_cast<const uint4*>(a0 + (c + j) * 8));
+          if (has1) r1[j] = __ldg(reinterpret_cast<const uint4*>(a1 + (c + j) * 8));
+        }
+      }
+      if (!waited) {
+        mbar_wait(bar_accfull + 8 * acc, accph);
+        tc_fence_after();
+        waited = true;
+        if (ew == 0 && lane == 0) trace_ev(tr, trcap, 2, tri, 20, t);
+      }
+      uint32_t av[4][8];
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (j < nc) tmem_ld8(taddr + (c + j) * 8, av[j]);
+      tmem_ld_wait();
+      if (ew == 0 && lane == 0) trace_ev(tr, trcap, 2, tri, 22, t);
+      if (!(dbg & 1)) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          if (j < nc && valid && (c + j) * 8 < E.Cout) {
+            const int c0 = (c + j) * 8;
+            const uint32_t q0[4] = {r0[j].x, r0[j].y, r0[j].z, r0[j].w};
+            const uint32_t q1[4] = {r1[j].x, r1[j].y, r1[j].z, r1[j].w};
+            float v[8];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const float2 f0 = unpack_h2(q0[i]), f1 = unpack_h2(q1[i]);
+              v[2 * i] = fmaxf(__uint_as_float(av[j][2 * i]) + (f0.x + f1.x), lo);
+              v[2 * i + 1] = fmaxf(__uint_as_float(av[j][2 * i + 1]) + (f0.y + f1.y), lo);
+            }
+            if (OUT == 0) {
+              uint4 q;
+              q.x = pack_h2(v[0], v[1]);
+              q.y = pack_h2(v[2], v[3]);
+              q.z = pack_h2(v[4], v[5]);
+              q.w = pack_h2(v[6], v[7]);
+              if (!(dbg & 2))
+                *reinterpret_cast<uint4*>(reinterpret_cast<__half*>(E.y) + static_cast<int64_t>(p) * E.out_pix_stride + c0) = q;
+              else if (q.x == 0x12345678u)
+                *reinterpret_cast<uint4*>(E.y) = q;
+            } else if (E.flags & I2R_F_OUT_NCHW_F32) {
+              float* Y = reinterpret_cast<float*>(E.y);
+              const int nr = p / E.plane, rem = p - nr * E.plane;
+              const int64_t base = static_cast<int64_t>(nr) * E.Cout * E.plane + rem;
+#pragma unroll
+              for (int i = 0; i < 8; ++i)
+                if (c0 + i < E.Cout) Y[base + static_cast<int64_t>(c0 + i) * E.plane] = v[i];
+            } else {
+              float* Y = reinterpret_cast<float*>(E.y) + static_cast<int64_t>(p) * E.out_pix_stride + c0;
+#pragma unroll
+              for (int i = 0; i < 8; ++i)
+                if (c0 + i < E.Cout) Y[i] = v[i];
+            }
+          }
+        }
+      }
+    }
+    if (!waited) {  // no columns assigned to this warp (tiny N): still take part in the hand-shake
+      mbar_wait(bar_accfull + 8 * acc, accph);
+      tc_fence_after();
+    }
+    if (ew == 0 && lane == 0) trace_ev(tr, trcap, 2, tri, 23, t);
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(bar_accempty + 8 * acc);
+    if (ew == 0 && lane == 0) trace_ev(tr, trcap, 2, tri, 21, t);
+    acc ^= 1;
+    if (acc == 0) accph ^= 1;
+  }
+}
+
 __global__ void __launch_bounds__(T_THREADS, 1) conv_halo_kernel(const __grid_constant__ HaloGroup G) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // SW128 tiles need 1024-B alignment
   int pi = 0;
   while (pi < G.nprob - 1 && static_cast<int>(blockIdx.x) >= G.p[pi].cta_begin + G.p[pi].cta_count) ++pi;
-  const HaloProblem& P = G.p[pi];
+  const HaloProblem P = load_problem(G.p[pi]);
   const int cta = blockIdx.x - P.cta_begin;
+  const int dbg = opaque(G.dbg);
+  const int trace_cap = opaque(G.trace_cap);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
   const uint32_t sbase = smem_u32(smem);
   const uint32_t bar_afull = sbase, bar_aempty = sbase + 32, bar_wfull = sbase + 64, bar_wempty = sbase + 96;
   const uint32_t bar_accfull = sbase + 128, bar_accempty = sbase + 144, bar_wres = sbase + 160;
+  if (G.trace != nullptr && static_cast<int>(blockIdx.x) == G.trace_cta && tid == 96) {
+    int i0 = 0;
+    trace_ev(G.trace, trace_cap, 3, i0, 30, 0);
+  }
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + 176);
-  float* s_scale = reinterpret_cast<float*>(smem + 256);
-  float* s_bias = reinterpret_cast<float*>(smem + 256 + 1024);
   const uint32_t a_base = sbase + T_A_OFF;
   const uint32_t w_base = sbase + P.w_off;
 
@@ -226,10 +436,8 @@ __global__ void __launch_bounds__(T_THREADS, 1) conv_halo_kernel(const __grid_co
     tmem_alloc(smem_u32(tmem_slot), ncols);
     tmem_relinquish();
   }
-  for (int i = tid; i < Npad; i += T_THREADS) {
-    s_scale[i] = P.scale[i];
-    s_bias[i] = P.bias[i];
-  }
+  if (tid < 256) reinterpret_cast<uint32_t*>(smem + T_ONES_OFF)[tid] = 0x3c003c00u;   // fp16 (1.0, 1.0)
+  fence_proxy_async();   // the ones tile is read by the tensor core (async proxy)
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -242,178 +450,93 @@ __global__ void __launch_bounds__(T_THREADS, 1) conv_halo_kernel(const __grid_co
       // ================================================= activation producer: one TMA box per (tile, K-chunk)
       const CUtensorMap* amap = &G.amap[pi];
       prefetch_tmap(amap);
-      int s = 0, tri = 0;
-      uint32_t ph = 0;
-      for (int t = cta; t < P.ntiles; t += P.cta_count) {
+      const int dual = P.w_resident;   // two MMA issuers, each with its own half-ring (see mma_role)
+      const int a_half = dual ? P.a_stages >> 1 : P.a_stages;
+      int sr[2] = {0, 0}, tri = 0, ring = 0;
+      uint32_t phr[2] = {0, 0};
+      for (int t = cta; t < P.ntiles; t += P.cta_count, ring ^= dual) {
         const int n = t / P.tiles_per_img;
         const int r = t - n * P.tiles_per_img;
         const int ty = r / P.tiles_x, tx = r - ty * P.tiles_x;
         const int x0 = tx * T_TW - P.halo, y0 = ty * T_TH - P.halo;
         for (int kc = 0; kc < P.nkc; ++kc) {
-          mbar_wait(bar_aempty + 8 * s, ph ^ 1);
-          trace_ev(tr, G.trace_cap, 0, tri, 1, t);
-          mbar_arrive_expect_tx(bar_afull + 8 * s, P.a_tx_bytes);
-          tma_load_4d(a_base + s * P.a_stage_bytes, amap, kc * 64, x0, y0, n, bar_afull + 8 * s);
-          trace_ev(tr, G.trace_cap, 0, tri, 2, t);
-          if (++s == P.a_stages) {
-            s = 0;
-            ph ^= 1;
+          const int s = ring * a_half + sr[ring];
+          mbar_wait_relaxed(bar_aempty + 8 * s, phr[ring] ^ 1);
+          trace_ev(tr, trace_cap, 0, tri, 1, t);
+          if ((dbg & 4) && t >= cta + P.a_stages * P.cta_count) {
+            mbar_arrive(bar_afull + 8 * s);
+          } else {
+            mbar_arrive_expect_tx(bar_afull + 8 * s, P.a_tx_bytes);
+            tma_load_4d(a_base + s * P.a_stage_bytes, amap, kc * 64, x0, y0, n, bar_afull + 8 * s);
+          }
+          trace_ev(tr, trace_cap, 0, tri, 2, t);
+          if (++sr[ring] == a_half) {
+            sr[ring] = 0;
+            phr[ring] ^= 1;
           }
         }
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
-    // ================================================= weight producer (1-D bulk copies on the TMA unit)
-    if (P.w_resident) {
-      mbar_arrive_expect_tx(bar_wres, P.w_total_bytes);
-      for (uint32_t off = 0; off < P.w_total_bytes; off += 16384) {
-        const uint32_t sz = min(16384u, P.w_total_bytes - off);
-        bulk_g2s(w_base + off, P.w + off, sz, bar_wres);
-      }
-    } else {
-      int s = 0;
-      uint32_t ph = 0;
-      for (int t = cta; t < P.ntiles; t += P.cta_count) {
-        for (int kc = 0; kc < P.nkc; ++kc) {
-          for (int tap = 0; tap < P.ntaps; ++tap) {
-            mbar_wait(bar_wempty + 8 * s, ph ^ 1);
+      // ================================================= weight producer (1-D bulk copies on the TMA unit)
+      if (P.w_resident) {
+        mbar_arrive_expect_tx(bar_wres, P.w_total_bytes);
+        for (uint32_t off = 0; off < P.w_total_bytes; off += 16384) {
+          const uint32_t sz = min(16384u, P.w_total_bytes - off);
+          bulk_g2s(w_base + off, P.w + off, sz, bar_wres);
+        }
+      } else {
+        const int w_half = P.w_stages;   // streamed weights: single issuer, one ring
+        int sr[2] = {0, 0};
+        const int ring = 0;
+        uint32_t phr[2] = {0, 0};
+        const int nblk = P.nkc * P.ntaps + 1;   // block 0 = bias, then (kc, tap) in the order the MMA issuers consume
+        for (int t = cta; t < P.ntiles; t += P.cta_count) {
+          for (int b = 0; b < nblk; ++b) {
+            const int kc = (b - 1) / P.ntaps, tap = (b - 1) - kc * P.ntaps;
+            const int blk = b == 0 ? 0 : 1 + tap * P.nchp + kc;
+            const int s = ring * w_half + sr[ring];
+            mbar_wait_relaxed(bar_wempty + 8 * s, phr[ring] ^ 1);
             mbar_arrive_expect_tx(bar_wfull + 8 * s, P.w_stage_bytes);
-            bulk_g2s(w_base + s * P.w_stage_bytes,
-                     P.w + static_cast<size_t>(tap * P.nchp + kc) * P.w_stage_bytes, P.w_stage_bytes,
+            bulk_g2s(w_base + s * P.w_stage_bytes, P.w + static_cast<size_t>(blk) * P.w_stage_bytes, P.w_stage_bytes,
                      bar_wfull + 8 * s);
-            if (++s == P.w_stages) {
-              s = 0;
-              ph ^= 1;
+            if (++sr[ring] == w_half) {
+              sr[ring] = 0;
+              phr[ring] ^= 1;
             }
           }
         }
       }
     }
-    }
-  } else if (warp == 2) {
-    // ================================================= MMA issuer (whole warp runs the loop, one lane issues)
+  } else if (warp == 2 || warp == 3) {
+    // ================================================= MMA issuers (whole warp runs the loop, one lane issues)
     if (P.ntaps == 9) {
-      mma_role<9>(P, cta, sbase, tmem_base, ncols, tr, G.trace_cap);
+      mma_role<9>(P, cta, sbase, tmem_base, ncols, warp == 2 ? tr : nullptr, trace_cap, dbg, warp - 2);
     } else {
-      mma_role<1>(P, cta, sbase, tmem_base, ncols, tr, G.trace_cap);
+      mma_role<1>(P, cta, sbase, tmem_base, ncols, warp == 2 ? tr : nullptr, trace_cap, dbg, warp - 2);
     }
-  } else if (warp >= 4) {
+  } else {
     // ================================================= epilogue: 8 warps, two per TMEM lane quadrant, each
-    // owning half of the output channels of its 32 rows; residual loads are issued before the accumulator
-    // wait so their latency hides behind the MMAs of the tile.
-    const int ew = warp - 4;
-    const int quad = warp & 3;             // warp % 4: the TMEM lanes this warp may read
-    const int row = quad * 32 + lane;
-    const int ty_in = row >> 3, tx_in = row & 7;
-    const int Cout = P.Cout;
-    const bool relu = (P.flags & I2R_F_RELU) != 0;
-    const int n8 = Npad >> 3, half8 = (n8 + 1) >> 1;
-    const int cb = (ew >> 2) ? half8 : 0, ce = (ew >> 2) ? n8 : half8;   // 8-column chunks [cb, ce)
-    const float4* s_scale4 = reinterpret_cast<const float4*>(s_scale);
-    const float4* s_bias4 = reinterpret_cast<const float4*>(s_bias);
-    int acc = 0;
-    int tri = 0;
-    uint32_t accph = 0;
-    for (int t = cta; t < P.ntiles; t += P.cta_count) {
-      const int n = t / P.tiles_per_img;
-      const int r = t - n * P.tiles_per_img;
-      const int ty = r / P.tiles_x, tx = r - ty * P.tiles_x;
-      const int x = tx * T_TW + tx_in, y = ty * T_TH + ty_in;
-      const bool valid = (x < P.W) && (y < P.H);
-      const int64_t p = (static_cast<int64_t>(n) * P.H + y) * P.W + x;
-      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + static_cast<uint32_t>(acc) * (ncols >> 1);
-      const __half* a0 = (P.add0 && valid) ? P.add0 + p * P.add_pix_stride : nullptr;
-      const __half* a1 = (P.add1 && valid) ? P.add1 + p * P.add_pix_stride : nullptr;
-      bool waited = false;
-      for (int c = cb; c < ce; c += 4) {
-        const int nc = min(4, ce - c);
-        uint4 r0[4], r1[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          r0[j] = make_uint4(0, 0, 0, 0);
-          r1[j] = make_uint4(0, 0, 0, 0);
-          if (j < nc && (c + j) * 8 < Cout) {
-            if (a0 != nullptr) r0[j] = __ldg(reinterpret_cast<const uint4*>(a0 + (c + j) * 8));
-            if (a1 != nullptr) r1[j] = __ldg(reinterpret_cast<const uint4*>(a1 + (c + j) * 8));
-          }
-        }
-        if (!waited) {
-          mbar_wait(bar_accfull + 8 * acc, accph);
-          tc_fence_after();
-          waited = true;
-          if (ew == 0 && lane == 0) trace_ev(tr, G.trace_cap, 2, tri, 20, t);
-        }
-        uint32_t av[4][8];
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
-          if (j < nc) tmem_ld8(taddr + (c + j) * 8, av[j]);
-        tmem_ld_wait();
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          if (j < nc && valid && (c + j) * 8 < Cout) {
-            const int c0 = (c + j) * 8;
-            const float4 sa = s_scale4[2 * (c + j)], sb = s_scale4[2 * (c + j) + 1];
-            const float4 ba = s_bias4[2 * (c + j)], bb = s_bias4[2 * (c + j) + 1];
-            float v[8];
-            v[0] = __uint_as_float(av[j][0]) * sa.x + ba.x;
-            v[1] = __uint_as_float(av[j][1]) * sa.y + ba.y;
-            v[2] = __uint_as_float(av[j][2]) * sa.z + ba.z;
-            v[3] = __uint_as_float(av[j][3]) * sa.w + ba.w;
-            v[4] = __uint_as_float(av[j][4]) * sb.x + bb.x;
-            v[5] = __uint_as_float(av[j][5]) * sb.y + bb.y;
-            v[6] = __uint_as_float(av[j][6]) * sb.z + bb.z;
-            v[7] = __uint_as_float(av[j][7]) * sb.w + bb.w;
-            const uint32_t q0[4] = {r0[j].x, r0[j].y, r0[j].z, r0[j].w};
-            const uint32_t q1[4] = {r1[j].x, r1[j].y, r1[j].z, r1[j].w};
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const float2 f0 = unpack_h2(q0[i]), f1 = unpack_h2(q1[i]);
-              v[2 * i] += f0.x + f1.x;
-              v[2 * i + 1] += f0.y + f1.y;
-            }
-            if (relu) {
-#pragma unroll
-              for (int i = 0; i < 8; ++i) v[i] = fmaxf(v[i], 0.0f);
-            }
-            if (P.flags & I2R_F_OUT_NCHW_F32) {
-              float* Y = reinterpret_cast<float*>(P.y);
-              const int64_t nr = p / P.plane, rem = p - nr * P.plane;
-              const int64_t base = nr * Cout * P.plane + rem;
-#pragma unroll
-              for (int i = 0; i < 8; ++i)
-                if (c0 + i < Cout) Y[base + static_cast<int64_t>(c0 + i) * P.plane] = v[i];
-            } else if (P.flags & I2R_F_OUT_F32) {
-              float* Y = reinterpret_cast<float*>(P.y) + p * P.out_pix_stride + c0;
-#pragma unroll
-              for (int i = 0; i < 8; ++i)
-                if (c0 + i < Cout) Y[i] = v[i];
-            } else {
-              uint4 q;
-              q.x = pack_h2(v[0], v[1]);
-              q.y = pack_h2(v[2], v[3]);
-              q.z = pack_h2(v[4], v[5]);
-              q.w = pack_h2(v[6], v[7]);
-              *reinterpret_cast<uint4*>(reinterpret_cast<__half*>(P.y) + p * P.out_pix_stride + c0) = q;
-            }
-          }
-        }
-      }
-      if (!waited) {  // no columns assigned to this warp (tiny N): still take part in the hand-shake
-        mbar_wait(bar_accfull + 8 * acc, accph);
-        tc_fence_after();
-      }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(bar_accempty + 8 * acc);
-      if (ew == 0 && lane == 0) trace_ev(tr, G.trace_cap, 2, tri, 21, t);
-      acc ^= 1;
-      if (acc == 0) accph ^= 1;
+    // owning half of the output channels of its 32 rows
+    EpiArgs E;
+    E.add0 = P.add0; E.add1 = P.add1; E.y = P.y;
+    E.H = P.H; E.W = P.W; E.Cout = P.Cout; E.tiles_x = P.tiles_x; E.tiles_per_img = P.tiles_per_img;
+    E.ntiles = P.ntiles; E.cta_count = P.cta_count;
+    E.out_pix_stride = P.out_pix_stride; E.add_pix_stride = P.add_pix_stride; E.plane = P.plane; E.flags = P.flags;
+    if (P.flags & (I2R_F_OUT_NCHW_F32 | I2R_F_OUT_F32)) {
+      epilogue_role<1>(E, cta, sbase, tmem_base, ncols, Npad, warp - 4, warp & 3, lane, tr, trace_cap, dbg);
+    } else {
+      epilogue_role<0>(E, cta, sbase, tmem_base, ncols, Npad, warp - 4, warp & 3, lane, tr, trace_cap, dbg);
     }
   }
 
   tc_fence_before();
   __syncthreads();
+  if (tr != nullptr && tid == 96) {
+    int i1 = 1;
+    trace_ev(tr, trace_cap, 3, i1, 31, 0);
+  }
   if (warp == 2) tmem_dealloc(tmem_base, ncols);
 }
 
@@ -460,7 +583,7 @@ static int encode_amap(CUtensorMap* map, const void* x, int NB, int H, int W, in
 }
 
 static unsigned long long* g_trace = nullptr;
-static int g_trace_cta = 0, g_trace_cap = 0;
+static int g_trace_cta = 0, g_trace_cap = 0, g_dbg = 0;
 static bool is_std3x3(const i2r_conv_problem& P) {
   if (P.ntaps != 9) return false;
   for (int t = 0; t < 9; ++t)
@@ -503,6 +626,7 @@ extern "C" int i2r_conv_halo(const i2r_conv_problem* probs, int nprob, void* str
   G.trace = g_trace;
   G.trace_cta = g_trace_cta;
   G.trace_cap = g_trace_cap;
+  G.dbg = g_dbg;
   double cost[I2R_MAX_GROUP];
   int total_tiles = 0;
   uint32_t smem_need = 0;
@@ -512,15 +636,13 @@ extern "C" int i2r_conv_halo(const i2r_conv_problem* probs, int nprob, void* str
       set_error("i2r_conv_halo: problem %d is not a stride-1 3x3 / 1x1 problem this kernel supports", i);
       return I2R_E_UNSUPPORTED;
     }
-    if (!S.x || !S.w || !S.scale || !S.bias || !S.y) {
+    if (!S.x || !S.w_folded || !S.y) {
       set_error("i2r_conv_halo: problem %d: null pointer", i);
       return I2R_E_BADARG;
     }
     HaloProblem& P = G.p[i];
     P.x = static_cast<const __half*>(S.x);
-    P.w = static_cast<const uint8_t*>(S.w);
-    P.scale = S.scale;
-    P.bias = S.bias;
+    P.w = static_cast<const uint8_t*>(S.w_folded);
     P.add0 = static_cast<const __half*>(S.add0);
     P.add1 = static_cast<const __half*>(S.add1);
     P.y = S.y;
@@ -553,7 +675,7 @@ extern "C" int i2r_conv_halo(const i2r_conv_problem* probs, int nprob, void* str
     const int hw = T_TW + 2 * P.halo, hh = T_TH + 2 * P.halo;
     P.a_tx_bytes = static_cast<uint32_t>(hh * hw * 128);          // full box, zero-filled parts included
     P.a_stage_bytes = (P.a_tx_bytes + 1023u) & ~1023u;            // stages stay 1024-byte aligned (SW128)
-    P.w_total_bytes = static_cast<uint32_t>(S.ntaps) * P.nkc * S.Npad * 128;
+    P.w_total_bytes = static_cast<uint32_t>(S.ntaps * P.nkc + 1) * S.Npad * 128;   // bias block + taps
     P.w_resident = P.w_total_bytes <= T_W_RES_MAX ? 1 : 0;
     P.w_stage_bytes = static_cast<uint32_t>(S.Npad) * 128;
     uint32_t wregion;
@@ -567,6 +689,7 @@ extern "C" int i2r_conv_halo(const i2r_conv_problem* probs, int nprob, void* str
     }
     int astg = static_cast<int>((T_MAX_SMEM - T_A_OFF - wregion) / P.a_stage_bytes);
     if (astg > 4) astg = 4;
+    if (P.w_resident) astg &= ~1;   // two half-rings, one per MMA issuer
     if (astg < 2) {
       set_error("i2r_conv_halo: problem %d does not fit shared memory (A stage %u B, W region %u B)", i,
                 P.a_stage_bytes, wregion);
@@ -638,5 +761,10 @@ extern "C" int i2r_debug_trace(void* dev_buffer, int capacity_events, int cta) {
   i2r::g_trace = static_cast<unsigned long long*>(dev_buffer);
   i2r::g_trace_cap = capacity_events;
   i2r::g_trace_cta = cta;
+  return 0;
+}
+
+extern "C" int i2r_debug_flags(int flags) {
+  i2r::g_dbg = flags;
   return 0;
 }

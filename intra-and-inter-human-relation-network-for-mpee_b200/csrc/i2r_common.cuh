@@ -46,6 +46,25 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   }
 }
 
+// Wait used by roles that run far ahead of their consumers (TMA producers): back off between polls so the
+// spinning warp does not compete for issue slots with the epilogue warps of its scheduler partition.
+__device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0;
+  uint32_t spins = 0;
+  while (true) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (done) break;
+    __nanosleep(128);
+    if (++spins > (1u << 22)) __trap();
+  }
+}
+
 // ---------------------------------------------------------------- async copies
 // 16-byte global->shared copy, zero-filled when src_bytes == 0 (padding taps / rows past M).
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {

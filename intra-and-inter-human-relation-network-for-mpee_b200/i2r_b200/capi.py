@@ -13,7 +13,7 @@ F_OUT_NCHW_F32 = 2
 F_OUT_F32 = 4
 
 EXPORTS = [
-    "i2r_version", "i2r_last_error", "i2r_device_check", "i2r_sm_count", "i2r_conv_igemm", "i2r_conv_halo", "i2r_conv_halo_supported", "i2r_debug_trace",
+    "i2r_version", "i2r_last_error", "i2r_device_check", "i2r_sm_count", "i2r_conv_igemm", "i2r_conv_halo", "i2r_conv_halo_supported", "i2r_debug_trace", "i2r_debug_flags",
     "i2r_sizeof_conv_problem", "i2r_stem_conv3x3s2", "i2r_maxpool3x3s2", "i2r_attention_varlen", "i2r_attention_workspace_bytes", "i2r_layernorm", "i2r_add_f16",
 ]
 
@@ -33,6 +33,7 @@ class ConvProblem(ctypes.Structure):
         ("ntaps", ctypes.c_int32),
         ("dy", ctypes.c_int8 * (I2R_MAX_TAPS + 3)), ("dx", ctypes.c_int8 * (I2R_MAX_TAPS + 3)),
         ("flags", ctypes.c_uint32),
+        ("w_folded", ctypes.c_void_p),
     ]
 
 
@@ -64,6 +65,7 @@ def load():
         lib.i2r_conv_halo.argtypes = [ctypes.POINTER(ConvProblem), i32, vp]
         lib.i2r_conv_halo_supported.argtypes = [ctypes.POINTER(ConvProblem)]
         lib.i2r_debug_trace.argtypes = [vp, i32, i32]
+        lib.i2r_debug_flags.argtypes = [i32]
         lib.i2r_stem_conv3x3s2.argtypes = [vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp]
         lib.i2r_maxpool3x3s2.argtypes = [vp, vp, i32, i32, i32, i32, vp]
         lib.i2r_attention_varlen.argtypes = [vp, vp, vp, vp, i32, i32, i32, i32, i32, vp, i32, i32, i32, f32, vp, i64, vp]
@@ -76,8 +78,8 @@ def load():
         if lib.i2r_sizeof_conv_problem() != ctypes.sizeof(ConvProblem):
             raise I2RError("i2r_conv_problem layout mismatch: C %d vs ctypes %d" % (
                 lib.i2r_sizeof_conv_problem(), ctypes.sizeof(ConvProblem)))
-        if lib.i2r_version() != 1:
-            raise I2RError("libi2r_sm100.so ABI version %d, binding expects 1" % lib.i2r_version())
+        if lib.i2r_version() != 2:
+            raise I2RError("libi2r_sm100.so ABI version %d, binding expects 2" % lib.i2r_version())
         _lib = lib
         return lib
 

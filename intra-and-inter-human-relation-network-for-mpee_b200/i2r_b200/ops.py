@@ -5,7 +5,7 @@ import ctypes
 import torch
 
 from . import capi
-from .packing import ceil_to, pad_vec, pick_kc, pack_taps
+from .packing import ceil_to, pad_vec, pick_kc, pack_taps, pack_folded
 
 
 class ConvLayer:
@@ -24,6 +24,8 @@ class ConvLayer:
         self.w = pack_taps(mats, self.kc).to(device)
         self.scale = pad_vec(scale, self.npad, 1.0).to(device)
         self.bias = pad_vec(bias, self.npad, 0.0).to(device)
+        # operand image of the persistent halo kernel (scale folded into the weights, bias block first)
+        self.w_folded = pack_folded(mats, scale, bias, self.kc).to(device)
         self._halves = None
 
     @property
@@ -43,6 +45,7 @@ class ConvLayer:
                 sub.w = self.w[:, :, c0:c0 + h, :].contiguous()   # c0 % 8 == 0 keeps the row swizzle phase
                 sub.scale = self.scale[c0:c0 + h].contiguous()
                 sub.bias = self.bias[c0:c0 + h].contiguous()
+                sub.w_folded = self.w_folded[:, c0:c0 + h, :].contiguous()
                 sub._halves = None
                 parts.append((c0, sub))
             self._halves = parts
@@ -130,6 +133,7 @@ class Runner:
         for t in range(L.ntaps):
             p.dy[t], p.dx[t] = L.dy[t], L.dx[t]
         p.flags = flags
+        p.w_folded = L.w_folded.data_ptr()
         p._keep = (x, L, add0, add1, out)
         return p, out
 

@@ -102,3 +102,24 @@ def pad_vec(v, npad, fill=0.0):
     out = torch.full((npad,), fill, dtype=torch.float32)
     out[: v.numel()] = v.float()
     return out
+
+
+def pack_folded(mats, scale, bias, kc=KC):
+    """Operand image of the persistent halo kernel: fp16 [1 + ntaps*nch, Npad, 64].
+
+    Block 0 is the bias block -- row n holds fp16(bias[n]) in K slot 0 and fp16(bias[n] - slot0) in slot 1, so one
+    K=16 MMA against a tile of ones initialises the accumulator with the bias at ~22 bits; blocks 1.. are
+    pack_taps() of the weights with the BatchNorm scale folded in (fp32 product, one fp16 rounding)."""
+    cout, _ = mats[0].shape
+    npad = ceil_to(cout, 16)
+    sc = scale.float()[:cout].reshape(cout, 1)
+    taps = pack_taps([m.float() * sc for m in mats], kc)
+    ntaps, nch = taps.shape[0], taps.shape[1]
+    b = bias.float()[:cout]
+    hi = b.to(torch.float16)
+    lo = (b - hi.float()).to(torch.float16)
+    blk = torch.zeros(npad, 8, 8, dtype=torch.float16)
+    rows = torch.arange(cout)
+    blk[rows, 0 ^ (rows & 7), 0] = hi
+    blk[rows, 0 ^ (rows & 7), 1] = lo
+    return torch.cat([blk.reshape(1, npad, 64), taps.reshape(ntaps * nch, npad, 64)], 0).contiguous()

@@ -46,7 +46,7 @@ def test_cabi_library_exports_every_declared_symbol():
         assert hasattr(lib, name), name
     assert set(capi.EXPORTS) == declared
     lib.i2r_version.restype = ctypes.c_int
-    assert lib.i2r_version() == 1
+    assert lib.i2r_version() == 2
     assert lib.i2r_sizeof_conv_problem() == ctypes.sizeof(capi.ConvProblem)
 
 
