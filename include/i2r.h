@@ -75,6 +75,8 @@ typedef struct i2r_conv_problem {
   const void* w_folded;    /* i2r_conv_halo only: fp16 [1 + ntaps*ceil(Cin/64)][Npad][64] -- block 0 is the bias  */
                            /* block (K slot 0 = fp16(bias), slot 1 = fp16(bias - slot 0)), blocks 1.. are `w`     */
                            /* with scale[n] folded into every row n before the fp16 rounding                     */
+  int32_t w_folded_copies; /* >= 1: that image repeated back to back; CTA i streams copy i % copies, which spreads */
+                           /* the L2 lines every CTA reads at the same time over more L2 slices                    */
 } i2r_conv_problem;
 
 int i2r_version(void);

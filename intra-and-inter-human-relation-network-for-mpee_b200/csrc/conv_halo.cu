@@ -47,9 +47,11 @@ struct HaloProblem {
   uint32_t flags;
   int cta_begin, cta_count;
   int w_resident;
-  uint32_t w_total_bytes, w_stage_bytes;
+  uint32_t w_total_bytes, w_stage_bytes;   // w_stage_bytes = one (tap, K-chunk) block = Npad rows x 128 B
+  uint32_t w_slot_bytes;                   // streamed weights: one ring slot = TG blocks (3 taps of a 3x3, else 1)
   uint32_t a_stage_bytes, a_tx_bytes;
   int a_stages, w_stages;
+  int w_copies;
   uint32_t w_off;      // byte offset of the weight region in dynamic smem
 };
 
@@ -90,15 +92,18 @@ __device__ __forceinline__ HaloProblem load_problem(const HaloProblem& s) {
   p.add_pix_stride = opaque(s.add_pix_stride); p.plane = opaque(s.plane); p.flags = opaque(s.flags);
   p.cta_begin = opaque(s.cta_begin); p.cta_count = opaque(s.cta_count); p.w_resident = opaque(s.w_resident);
   p.w_total_bytes = opaque(s.w_total_bytes); p.w_stage_bytes = opaque(s.w_stage_bytes);
+  p.w_slot_bytes = opaque(s.w_slot_bytes);
   p.a_stage_bytes = opaque(s.a_stage_bytes); p.a_tx_bytes = opaque(s.a_tx_bytes);
   p.a_stages = opaque(s.a_stages); p.w_stages = opaque(s.w_stages); p.w_off = opaque(s.w_off);
+  p.w_copies = opaque(s.w_copies);
   return p;
 }
 
 constexpr int T_THREADS = 384;
 constexpr int T_TW = 8, T_TH = 16;
+constexpr int T_W_STAGES_MAX = 8;           // streamed-weight ring depth (barriers at [256,384))
 constexpr uint32_t T_ONES_OFF = 1024;       // 1 KB of fp16 1.0: the A operand of the bias MMA
-constexpr uint32_t T_A_OFF = 2048;          // dynamic smem: [0,256) barriers | [1024,2048) ones | A ring
+constexpr uint32_t T_A_OFF = 2048;          // dynamic smem: [0,384) barriers | [1024,2048) ones | A ring
 constexpr uint32_t T_MAX_SMEM = 226 * 1024;   // + 1 KB alignment slack = 227 KB opt-in limit
 constexpr uint32_t T_W_RES_MAX = 120 * 1024;
 
@@ -148,7 +153,7 @@ __device__ __forceinline__ void mma_role(const HaloProblem& P, const int cta, co
   constexpr int HALO = NTAPS == 9 ? 1 : 0;
   constexpr int PW = T_TW + 2 * HALO;   // halo line = PW pixels = PW 128-byte rows (dense TMA box)
   constexpr uint32_t A_SBO = PW * 128;
-  const uint32_t bar_afull = sbase, bar_aempty = sbase + 32, bar_wfull = sbase + 64, bar_wempty = sbase + 96;
+  const uint32_t bar_afull = sbase, bar_aempty = sbase + 32, bar_wfull = sbase + 256, bar_wempty = sbase + 320;
   const uint32_t bar_accfull = sbase + 128, bar_accempty = sbase + 144, bar_wres = sbase + 160;
   const uint32_t a_base = sbase + T_A_OFF;
   const uint32_t w_base = sbase + P.w_off;
@@ -158,6 +163,7 @@ __device__ __forceinline__ void mma_role(const HaloProblem& P, const int cta, co
   const uint32_t a_hi = sw128_desc_hi(A_SBO, 0);   // base_offset 0: the swizzle XOR follows absolute smem address bits
   const uint32_t w_stage16 = P.w_stage_bytes >> 4;                         // one (tap, K-chunk) block = Npad rows x 128 B
   const uint32_t b_tap = static_cast<uint32_t>(P.nkc) * w_stage16;         // resident: next tap
+  const uint32_t w_slot16 = P.w_slot_bytes >> 4;                           // streamed: one ring slot (TG blocks)
   const uint32_t w_lo0 = sw128_desc_lo(w_base);
   const uint32_t a_stage16 = P.a_stage_bytes >> 4;
   const uint32_t a_lo0 = sw128_desc_lo(a_base);
@@ -196,7 +202,7 @@ __device__ __forceinline__ void mma_role(const HaloProblem& P, const int cta, co
       mbar_wait(bar_wfull + 8 * (w_first + ws), wph);
       tc_fence_after();
       if (leader) {
-        umma_f16(d_tmem, desc64(ones_lo, ones_hi), desc64(w_lo0 + (w_first + ws) * w_stage16, b_hi), idesc, 0u);
+        umma_f16(d_tmem, desc64(ones_lo, ones_hi), desc64(w_lo0 + (w_first + ws) * w_slot16, b_hi), idesc, 0u);
         umma_commit(bar_wempty + 8 * (w_first + ws));
       }
       if (++ws == w_half) {
@@ -223,19 +229,25 @@ __device__ __forceinline__ void mma_role(const HaloProblem& P, const int cta, co
           }
         }
       } else {
+        // streamed weights arrive TG taps per ring slot: one barrier wait (~350 cycles with its fence) per TG*ksteps
+        // MMAs keeps the wait hidden behind the 8-deep MMA queue
+        constexpr int TG = NTAPS == 9 ? 3 : 1;
 #pragma unroll
-        for (int tap = 0; tap < NTAPS; ++tap) {
+        for (int tg = 0; tg < NTAPS / TG; ++tg) {
           mbar_wait(bar_wfull + 8 * (w_first + ws), wph);
           tc_fence_after();
           if (leader) {
-            const uint32_t b_lo = w_lo0 + (w_first + ws) * w_stage16;
-            const uint32_t a_t = a_lo + (HALO ? static_cast<uint32_t>(((tap / 3) * PW + (tap % 3)) * 8) : 0u);
-            const uint32_t accf = tap ? 1u : acc_kc;
-            switch (ksteps) {
-              case 4: issue_ksteps<4>(d_tmem, a_t, a_hi, b_lo, b_hi, idesc, accf); break;
-              case 3: issue_ksteps<3>(d_tmem, a_t, a_hi, b_lo, b_hi, idesc, accf); break;
-              case 2: issue_ksteps<2>(d_tmem, a_t, a_hi, b_lo, b_hi, idesc, accf); break;
-              default: issue_ksteps<1>(d_tmem, a_t, a_hi, b_lo, b_hi, idesc, accf); break;
+            const uint32_t b_lo = w_lo0 + (w_first + ws) * w_slot16;
+#pragma unroll
+            for (int j = 0; j < TG; ++j) {
+              const int tap = tg * TG + j;
+              const uint32_t a_t = a_lo + (HALO ? static_cast<uint32_t>(((tap / 3) * PW + (tap % 3)) * 8) : 0u);
+              switch (ksteps) {
+                case 4: issue_ksteps<4>(d_tmem, a_t, a_hi, b_lo + j * w_stage16, b_hi, idesc, 1u); break;
+                case 3: issue_ksteps<3>(d_tmem, a_t, a_hi, b_lo + j * w_stage16, b_hi, idesc, 1u); break;
+                case 2: issue_ksteps<2>(d_tmem, a_t, a_hi, b_lo + j * w_stage16, b_hi, idesc, 1u); break;
+                default: issue_ksteps<1>(d_tmem, a_t, a_hi, b_lo + j * w_stage16, b_hi, idesc, 1u); break;
+              }
             }
             umma_commit(bar_wempty + 8 * (w_first + ws));
           }
@@ -326,10 +338,12 @@ __device__ __forceinline__ void epilogue_role(const EpiArgs E, const int cta, co
         }
       }
       if (!waited) {
+        if (ew == 0 && lane == 0) trace_ev_dep(tr, trcap, 2, tri, 27, t, r0[0].x + static_cast<uint32_t>(p));
         mbar_wait(bar_accfull + 8 * acc, accph);
+        if (ew == 0 && lane == 0) trace_ev_dep(tr, trcap, 2, tri, 28, t, 0);
         tc_fence_after();
         waited = true;
-        if (ew == 0 && lane == 0) trace_ev(tr, trcap, 2, tri, 20, t);
+        if (ew == 0 && lane == 0) trace_ev_dep(tr, trcap, 2, tri, 20, t, 0);
       }
       uint32_t av[4][8];
 #pragma unroll
@@ -351,7 +365,7 @@ __device__ __forceinline__ void epilogue_role(const EpiArgs E, const int cta, co
               v[2 * i] = fmaxf(__uint_as_float(av[j][2 * i]) + (f0.x + f1.x), lo);
               v[2 * i + 1] = fmaxf(__uint_as_float(av[j][2 * i + 1]) + (f0.y + f1.y), lo);
             }
-            if (OUT == 0) {
+            if (!(E.flags & (I2R_F_OUT_NCHW_F32 | I2R_F_OUT_F32))) {
               uint4 q;
               q.x = pack_h2(v[0], v[1]);
               q.y = pack_h2(v[2], v[3]);
@@ -392,19 +406,118 @@ __device__ __forceinline__ void epilogue_role(const EpiArgs E, const int cta, co
   }
 }
 
+
+// Hot epilogue: fp16 NHWC output, Cout a multiple of 8, G chunks of 8 channels per pass with everything unrolled at
+// compile time and NADD residual tensors.  The epilogue warps are issue-bound (~4.5 cycles per instruction at two
+// warps per scheduler), so the instruction count per tile is what matters here: no per-chunk branches, no
+// reconvergence stacks, 32-bit pixel arithmetic.
+template <int G, int NADD>
+__device__ __forceinline__ void epilogue_fast(const EpiArgs E, const int cta, const uint32_t sbase, const uint32_t tmem_base,
+                                              const uint32_t ncols, const int cb, const int ce, const int ew, const int quad,
+                                              const int lane, unsigned long long* tr, const int trcap) {
+  const uint32_t bar_accfull = sbase + 128, bar_accempty = sbase + 144;
+  const int row = quad * 32 + lane;
+  const int ty_in = row >> 3, tx_in = row & 7;
+  const float lo = (E.flags & I2R_F_RELU) ? 0.0f : -3.0e38f;
+  const float inv_tpi = 1.0f / static_cast<float>(E.tiles_per_img), inv_tx = 1.0f / static_cast<float>(E.tiles_x);
+  __half* const ybase = reinterpret_cast<__half*>(E.y);
+  const uint32_t lane_taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
+  int acc = 0, tri = 0;
+  uint32_t accph = 0;
+  for (int t = cta; t < E.ntiles; t += E.cta_count) {
+    const int n = __float2int_rd((static_cast<float>(t) + 0.5f) * inv_tpi);
+    const int r = t - n * E.tiles_per_img;
+    const int ty = __float2int_rd((static_cast<float>(r) + 0.5f) * inv_tx);
+    const int tx = r - ty * E.tiles_x;
+    const int x = tx * T_TW + tx_in, y = ty * T_TH + ty_in;
+    const bool valid = (x < E.W) && (y < E.H);
+    const int p = (n * E.H + y) * E.W + x;
+    const uint32_t taddr = lane_taddr + static_cast<uint32_t>(acc) * (ncols >> 1);
+    const __half* a0 = E.add0 + static_cast<int64_t>(p) * E.add_pix_stride;
+    const __half* a1 = E.add1 + static_cast<int64_t>(p) * E.add_pix_stride;
+    __half* yp = ybase + static_cast<int64_t>(p) * E.out_pix_stride;
+    for (int c = cb; c < ce; c += G) {
+      uint4 r0[G], r1[G];
+#pragma unroll
+      for (int j = 0; j < G; ++j) {
+        r0[j] = make_uint4(0, 0, 0, 0);
+        r1[j] = make_uint4(0, 0, 0, 0);
+        if (NADD >= 1 && valid) r0[j] = __ldg(reinterpret_cast<const uint4*>(a0 + (c + j) * 8));
+        if (NADD >= 2 && valid) r1[j] = __ldg(reinterpret_cast<const uint4*>(a1 + (c + j) * 8));
+      }
+      if (c == cb) {
+        mbar_wait(bar_accfull + 8 * acc, accph);
+        tc_fence_after();
+        if (ew == 0 && lane == 0) trace_ev(tr, trcap, 2, tri, 20, t);
+      }
+      uint32_t av[G][8];
+#pragma unroll
+      for (int j = 0; j < G; ++j) tmem_ld8(taddr + (c + j) * 8, av[j]);
+      tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < G; ++j) {
+        const uint32_t q0[4] = {r0[j].x, r0[j].y, r0[j].z, r0[j].w};
+        const uint32_t q1[4] = {r1[j].x, r1[j].y, r1[j].z, r1[j].w};
+        uint32_t o[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          float va = __uint_as_float(av[j][2 * i]), vb = __uint_as_float(av[j][2 * i + 1]);
+          if (NADD >= 1) {
+            const float2 f0 = unpack_h2(q0[i]);
+            va += f0.x;
+            vb += f0.y;
+          }
+          if (NADD >= 2) {
+            const float2 f1 = unpack_h2(q1[i]);
+            va += f1.x;
+            vb += f1.y;
+          }
+          o[i] = pack_h2(fmaxf(va, lo), fmaxf(vb, lo));
+        }
+        if (valid) *reinterpret_cast<uint4*>(yp + (c + j) * 8) = make_uint4(o[0], o[1], o[2], o[3]);
+      }
+    }
+    if (ew == 0 && lane == 0) trace_ev(tr, trcap, 2, tri, 23, t);
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(bar_accempty + 8 * acc);
+    if (ew == 0 && lane == 0) trace_ev(tr, trcap, 2, tri, 21, t);
+    acc ^= 1;
+    if (acc == 0) accph ^= 1;
+  }
+}
+
+template <int NADD>
+__device__ __forceinline__ void epilogue_fast_dispatch(const EpiArgs& E, const int cta, const uint32_t sbase,
+                                                       const uint32_t tmem_base, const uint32_t ncols, const int cb,
+                                                       const int ce, const int ew, const int quad, const int lane,
+                                                       unsigned long long* tr, const int trcap) {
+  const int cw = ce - cb;
+  if (cw % 4 == 0) {
+    epilogue_fast<4, NADD>(E, cta, sbase, tmem_base, ncols, cb, ce, ew, quad, lane, tr, trcap);
+  } else if (cw % 3 == 0) {
+    epilogue_fast<3, NADD>(E, cta, sbase, tmem_base, ncols, cb, ce, ew, quad, lane, tr, trcap);
+  } else if (cw % 2 == 0) {
+    epilogue_fast<2, NADD>(E, cta, sbase, tmem_base, ncols, cb, ce, ew, quad, lane, tr, trcap);
+  } else {
+    epilogue_fast<1, NADD>(E, cta, sbase, tmem_base, ncols, cb, ce, ew, quad, lane, tr, trcap);
+  }
+}
+
 __global__ void __launch_bounds__(T_THREADS, 1) conv_halo_kernel(const __grid_constant__ HaloGroup G) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // SW128 tiles need 1024-B alignment
   int pi = 0;
   while (pi < G.nprob - 1 && static_cast<int>(blockIdx.x) >= G.p[pi].cta_begin + G.p[pi].cta_count) ++pi;
-  const HaloProblem P = load_problem(G.p[pi]);
+  HaloProblem P = load_problem(G.p[pi]);
   const int cta = blockIdx.x - P.cta_begin;
+  P.w += static_cast<size_t>(cta % P.w_copies) * P.w_total_bytes;
   const int dbg = opaque(G.dbg);
   const int trace_cap = opaque(G.trace_cap);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
   const uint32_t sbase = smem_u32(smem);
-  const uint32_t bar_afull = sbase, bar_aempty = sbase + 32, bar_wfull = sbase + 64, bar_wempty = sbase + 96;
+  const uint32_t bar_afull = sbase, bar_aempty = sbase + 32, bar_wfull = sbase + 256, bar_wempty = sbase + 320;
   const uint32_t bar_accfull = sbase + 128, bar_accempty = sbase + 144, bar_wres = sbase + 160;
   if (G.trace != nullptr && static_cast<int>(blockIdx.x) == G.trace_cta && tid == 96) {
     int i0 = 0;
@@ -422,6 +535,8 @@ __global__ void __launch_bounds__(T_THREADS, 1) conv_halo_kernel(const __grid_co
     for (int i = 0; i < 4; ++i) {
       mbar_init(bar_afull + 8 * i, 1);
       mbar_init(bar_aempty + 8 * i, 1);
+    }
+    for (int i = 0; i < T_W_STAGES_MAX; ++i) {
       mbar_init(bar_wfull + 8 * i, 1);
       mbar_init(bar_wempty + 8 * i, 1);
     }
@@ -491,16 +606,25 @@ __global__ void __launch_bounds__(T_THREADS, 1) conv_halo_kernel(const __grid_co
         int sr[2] = {0, 0};
         const int ring = 0;
         uint32_t phr[2] = {0, 0};
-        const int nblk = P.nkc * P.ntaps + 1;   // block 0 = bias, then (kc, tap) in the order the MMA issuers consume
+        const int tgs = P.ntaps == 9 ? 3 : 1;            // taps per ring slot
+        const int nslot = P.nkc * (P.ntaps / tgs) + 1;   // slot 0 = bias block, then (kc, tap group) in consumption order
         for (int t = cta; t < P.ntiles; t += P.cta_count) {
-          for (int b = 0; b < nblk; ++b) {
-            const int kc = (b - 1) / P.ntaps, tap = (b - 1) - kc * P.ntaps;
-            const int blk = b == 0 ? 0 : 1 + tap * P.nchp + kc;
+          for (int b = 0; b < nslot; ++b) {
             const int s = ring * w_half + sr[ring];
-            mbar_wait_relaxed(bar_wempty + 8 * s, phr[ring] ^ 1);
-            mbar_arrive_expect_tx(bar_wfull + 8 * s, P.w_stage_bytes);
-            bulk_g2s(w_base + s * P.w_stage_bytes, P.w + static_cast<size_t>(blk) * P.w_stage_bytes, P.w_stage_bytes,
-                     bar_wfull + 8 * s);
+            mbar_wait(bar_wempty + 8 * s, phr[ring] ^ 1);
+            const uint32_t dst = w_base + s * P.w_slot_bytes;
+            if (b == 0) {
+              mbar_arrive_expect_tx(bar_wfull + 8 * s, P.w_stage_bytes);
+              bulk_g2s(dst, P.w, P.w_stage_bytes, bar_wfull + 8 * s);
+            } else {
+              const int kc = (b - 1) / (P.ntaps / tgs), tg = (b - 1) - kc * (P.ntaps / tgs);
+              mbar_arrive_expect_tx(bar_wfull + 8 * s, P.w_stage_bytes * tgs);
+              for (int j = 0; j < tgs; ++j) {
+                const int blk = 1 + (tg * tgs + j) * P.nchp + kc;
+                bulk_g2s(dst + j * P.w_stage_bytes, P.w + static_cast<size_t>(blk) * P.w_stage_bytes, P.w_stage_bytes,
+                         bar_wfull + 8 * s);
+              }
+            }
             if (++sr[ring] == w_half) {
               sr[ring] = 0;
               phr[ring] ^= 1;
@@ -524,10 +648,17 @@ __global__ void __launch_bounds__(T_THREADS, 1) conv_halo_kernel(const __grid_co
     E.H = P.H; E.W = P.W; E.Cout = P.Cout; E.tiles_x = P.tiles_x; E.tiles_per_img = P.tiles_per_img;
     E.ntiles = P.ntiles; E.cta_count = P.cta_count;
     E.out_pix_stride = P.out_pix_stride; E.add_pix_stride = P.add_pix_stride; E.plane = P.plane; E.flags = P.flags;
-    if (P.flags & (I2R_F_OUT_NCHW_F32 | I2R_F_OUT_F32)) {
-      epilogue_role<1>(E, cta, sbase, tmem_base, ncols, Npad, warp - 4, warp & 3, lane, tr, trace_cap, dbg);
+    const int ew = warp - 4;
+    const int n8 = (P.Cout + 7) >> 3, half8 = (n8 + 1) >> 1;   // chunks holding real channels, split over the warp pair
+    const int cb = (ew >> 2) ? half8 : 0, ce = (ew >> 2) ? n8 : half8;
+    if ((P.flags & (I2R_F_OUT_NCHW_F32 | I2R_F_OUT_F32)) || (P.Cout & 7) || dbg != 0 || ce == cb) {
+      epilogue_role<1>(E, cta, sbase, tmem_base, ncols, Npad, ew, warp & 3, lane, tr, trace_cap, dbg);
+    } else if (P.add1 != nullptr) {
+      epilogue_fast_dispatch<2>(E, cta, sbase, tmem_base, ncols, cb, ce, ew, warp & 3, lane, tr, trace_cap);
+    } else if (P.add0 != nullptr) {
+      epilogue_fast_dispatch<1>(E, cta, sbase, tmem_base, ncols, cb, ce, ew, warp & 3, lane, tr, trace_cap);
     } else {
-      epilogue_role<0>(E, cta, sbase, tmem_base, ncols, Npad, warp - 4, warp & 3, lane, tr, trace_cap, dbg);
+      epilogue_fast_dispatch<0>(E, cta, sbase, tmem_base, ncols, cb, ce, ew, warp & 3, lane, tr, trace_cap);
     }
   }
 
@@ -643,6 +774,7 @@ extern "C" int i2r_conv_halo(const i2r_conv_problem* probs, int nprob, void* str
     HaloProblem& P = G.p[i];
     P.x = static_cast<const __half*>(S.x);
     P.w = static_cast<const uint8_t*>(S.w_folded);
+    P.w_copies = S.w_folded_copies > 1 ? S.w_folded_copies : 1;
     P.add0 = static_cast<const __half*>(S.add0);
     P.add1 = static_cast<const __half*>(S.add1);
     P.y = S.y;
@@ -678,19 +810,25 @@ extern "C" int i2r_conv_halo(const i2r_conv_problem* probs, int nprob, void* str
     P.w_total_bytes = static_cast<uint32_t>(S.ntaps * P.nkc + 1) * S.Npad * 128;   // bias block + taps
     P.w_resident = P.w_total_bytes <= T_W_RES_MAX ? 1 : 0;
     P.w_stage_bytes = static_cast<uint32_t>(S.Npad) * 128;
+    P.w_slot_bytes = P.w_stage_bytes * (S.ntaps == 9 ? 3 : 1);
     uint32_t wregion;
+    // streamed weights: the ring must cover the L2 round trip (~1300 cycles) at the rate the issuer drains it, so it
+    // gets up to T_W_STAGES_MAX stages and the activation ring two (one per K-chunk in flight is enough there)
+    int astg;
     if (P.w_resident) {
       P.w_stages = 1;
       wregion = P.w_total_bytes;
+      astg = static_cast<int>((T_MAX_SMEM - T_A_OFF - wregion) / P.a_stage_bytes);
+      if (astg > 4) astg = 4;
+      astg &= ~1;   // two half-rings, one per MMA issuer
     } else {
-      P.w_stages = 4;
-      while (P.w_stages > 2 && P.w_stages * P.w_stage_bytes > 110 * 1024) --P.w_stages;
-      wregion = P.w_stages * P.w_stage_bytes;
+      astg = 3;
+      while (astg > 2 && T_A_OFF + astg * P.a_stage_bytes + 3 * P.w_slot_bytes > T_MAX_SMEM) --astg;
+      P.w_stages = static_cast<int>((T_MAX_SMEM - T_A_OFF - astg * P.a_stage_bytes) / P.w_slot_bytes);
+      if (P.w_stages > T_W_STAGES_MAX) P.w_stages = T_W_STAGES_MAX;
+      wregion = P.w_stages * P.w_slot_bytes;
     }
-    int astg = static_cast<int>((T_MAX_SMEM - T_A_OFF - wregion) / P.a_stage_bytes);
-    if (astg > 4) astg = 4;
-    if (P.w_resident) astg &= ~1;   // two half-rings, one per MMA issuer
-    if (astg < 2) {
+    if (astg < 2 || P.w_stages < 1 || (!P.w_resident && P.w_stages < 2)) {
       set_error("i2r_conv_halo: problem %d does not fit shared memory (A stage %u B, W region %u B)", i,
                 P.a_stage_bytes, wregion);
       return I2R_E_UNSUPPORTED;
@@ -703,7 +841,17 @@ extern "C" int i2r_conv_halo(const i2r_conv_problem* probs, int nprob, void* str
     P.w_off = T_A_OFF + static_cast<uint32_t>(astg) * P.a_stage_bytes;
     const uint32_t need = P.w_off + wregion;
     if (need > smem_need) smem_need = need;
-    cost[i] = static_cast<double>(S.ntaps) * (S.Cin / 16) * (4096.0 + 32.0 * S.Npad) * (P.w_resident ? 1.0 : 1.3);  // per tile
+    {
+      // per-tile cost in SM cycles, from the measured models: one M128 x N x K16 MMA with shared-memory
+      // operands takes max(32 + N/4, N/2) cycles; streamed weights arrive at ~45 B/cycle/SM; the epilogue warps need
+      // ~600 + 10 cycles per output channel.
+      const double n = S.Npad;
+      const double mma = static_cast<double>(S.ntaps) * (S.Cin / 16) * ((32.0 + n / 4) > n / 2 ? (32.0 + n / 4) : n / 2) + 400.0;
+      const double stream = P.w_resident ? 0.0 : P.w_total_bytes / 45.0;
+      const double epi = 600.0 + 10.0 * n;
+      cost[i] = mma > stream ? mma : stream;
+      if (epi > cost[i]) cost[i] = epi;
+    }
     total_tiles += P.ntiles;
   }
   // CTA ranges: one CTA per tile while they fit; otherwise hand the SMs out greedily to whichever problem

@@ -33,7 +33,7 @@ class ConvProblem(ctypes.Structure):
         ("ntaps", ctypes.c_int32),
         ("dy", ctypes.c_int8 * (I2R_MAX_TAPS + 3)), ("dx", ctypes.c_int8 * (I2R_MAX_TAPS + 3)),
         ("flags", ctypes.c_uint32),
-        ("w_folded", ctypes.c_void_p),
+        ("w_folded", ctypes.c_void_p), ("w_folded_copies", ctypes.c_int32),
     ]
 
 

@@ -26,7 +26,16 @@ class ConvLayer:
         self.bias = pad_vec(bias, self.npad, 0.0).to(device)
         # operand image of the persistent halo kernel (scale folded into the weights, bias block first)
         self.w_folded = pack_folded(mats, scale, bias, self.kc).to(device)
+        self.w_copies = 1
         self._halves = None
+
+    STREAM_COPIES = int(__import__('os').environ.get('I2R_STREAM_COPIES', '1'))
+
+    def replicate(self, copies):
+        """Repeat the halo operand image `copies` times (streamed-weight layers: CTA i reads copy i % copies)."""
+        if copies > 1 and self.w_copies == 1:
+            self.w_folded = self.w_folded.unsqueeze(0).repeat(copies, 1, 1, 1).contiguous()
+            self.w_copies = copies
 
     @property
     def weight_bytes(self):
@@ -46,6 +55,7 @@ class ConvLayer:
                 sub.scale = self.scale[c0:c0 + h].contiguous()
                 sub.bias = self.bias[c0:c0 + h].contiguous()
                 sub.w_folded = self.w_folded[:, c0:c0 + h, :].contiguous()
+                sub.replicate(self.STREAM_COPIES)
                 sub._halves = None
                 parts.append((c0, sub))
             self._halves = parts
@@ -134,6 +144,7 @@ class Runner:
             p.dy[t], p.dx[t] = L.dy[t], L.dx[t]
         p.flags = flags
         p.w_folded = L.w_folded.data_ptr()
+        p.w_folded_copies = L.w_copies
         p._keep = (x, L, add0, add1, out)
         return p, out
 

@@ -40,6 +40,6 @@ for cta in [int(a) for a in sys.argv[1:] if a.isdigit()] or [0]:
     t0 = ev[0][0] if ev else 0
     print("=== cta %d: %d events, launch %.1f us" % (cta, n, e0.elapsed_time(e1) * 1e3))
     names = {1: "P.free", 2: "P.issued", 3: "P.publish", 10: "M.accfree", 11: "M.operands", 12: "M.commit",
-             20: "E.ready", 21: "E.stored", 22: "E.loaded", 24: "E.data", 25: "E.packed0", 26: "E.stg0", 23: "E.math", 30: "K.start", 31: "K.end", 13: "M.weights"}
+             20: "E.ready", 21: "E.stored", 27: "E.top", 28: "E.waited", 22: "E.loaded", 24: "E.data", 25: "E.packed0", 26: "E.stg0", 23: "E.math", 30: "K.start", 31: "K.end", 13: "M.weights"}
     for clk, tag, tile in ev[:int(os.environ.get("TRACE_MAX", "120"))]:
         print("%8d  %-11s tile %d" % (clk - t0, names.get(tag, tag), tile))
