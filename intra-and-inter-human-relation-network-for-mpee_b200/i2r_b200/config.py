@@ -80,7 +80,7 @@ def default_cfg():
         ENCODER_MULTI_LAYERS=4, USE_MULTI_POS=True, N_HEAD=8, ATTENTION_ACTIVATION="relu",
         POS_EMBEDDING="learnable", SINGLE_POS_EMBEDDING="sine", PE_ONLY_AT_BEGIN=False,
         INTER_SUPERVISION=True, UPSAMPLE_TYPE="multiplex", MULTI_POS_EMBEDDING="conv",
-        ATTENTION_TYPE="default", WINDOW_SIZE=4, MULTI_POS_EMBEDDING_DIM=96,
+        ATTENTION_TYPE="default", WINDOW_SIZE=4, MULTI_POS_EMBEDDING_DIM=96, DOMAIN_TRANS=False,
     ))
     c.DATASET = CfgNode(dict(ROOT="", DATASET="coco"))
     c.TEST = CfgNode(dict(MODEL_FILE="", FLIP_TEST=False))

@@ -1,0 +1,182 @@
+"""Two-stage I2R-Net wrapper shared by `models.interformer` and `models.interformer_2stage`:
+
+    first stage (per crop)  ->  max-pool to TRANS_SIZE  ->  inter-human encoder over the ragged N*h*w token
+    sequence of every image (+ conv position embedding of the person box masks)  ->  deconv upsample back to the
+    heatmap size  ->  + first-stage feature  ->  1x1 heatmap head.
+
+Reference: lib/models/interformer.py:129-323 and lib/models/interformer_2stage.py:208-423.  The two reference
+modules differ only in parameter names of the upsample path and in which encoder class they instantiate (same
+arithmetic); `flavor` selects the naming so the state_dict keys match either one.
+"""
+import math
+import os
+
+import torch
+import torch.nn as nn
+
+from . import capi
+from .encoder import EncoderProgram
+from .engine import GraphedForward
+from .hrnet_w48 import conv_bn_layer
+from .modules import DeconvProgram, EncoderParams, make_deconv_stack
+from .ops import Runner
+from .position import MaskEmbedParams, MaskEmbedProgram
+
+
+class TwoStageInterFormer(nn.Module):
+    def __init__(self, cfg, singleformer, flavor):
+        super().__init__()
+        assert flavor in ("interformer", "interformer_2stage")
+        m, extra = cfg.MODEL, cfg.MODEL.EXTRA
+        self.flavor = flavor
+        self.singleformer = singleformer
+        self.singleformer_fix = bool(m.SINGLEFORMER_FIX)
+        self.trans_size = list(m.TRANS_SIZE)
+        self.heatmap_size = list(m.HEATMAP_SIZE)
+        d_model = m.DIM_MODEL
+        self.use_multi_pos = bool(m.USE_MULTI_POS)
+        self.inter_supervision = bool(m.INTER_SUPERVISION)
+        self.upsample_type = m.UPSAMPLE_TYPE
+        self.multi_position_mode = m.MULTI_POS_EMBEDDING
+        if m.get("ATTENTION_TYPE", "default") != "default":
+            raise NotImplementedError("ATTENTION_TYPE=%r (every shipped config uses 'default')" % m.ATTENTION_TYPE)
+        if m.get("DOMAIN_TRANS", False):
+            raise NotImplementedError("DOMAIN_TRANS=True (no shipped config enables it)")
+        self.multi_position_embedding = MaskEmbedParams(self.trans_size, d_model, mode=self.multi_position_mode,
+                                                        vec_dim=m.MULTI_POS_EMBEDDING_DIM)
+        self.multi_global_encoder = EncoderParams(d_model, m.N_HEAD, m.DIM_FEEDFORWARD, m.ENCODER_MULTI_LAYERS)
+        self.deconv_with_bias = bool(extra.DECONV_WITH_BIAS)
+        # number of x2 upsampling steps from the token map back to the heatmap
+        self.up_steps = int(math.log(self.heatmap_size[0] // self.trans_size[1], 2))
+        if self.upsample_type == "upconv":
+            raise NotImplementedError("UPSAMPLE_TYPE='upconv' (no shipped config uses it)")
+        if self.upsample_type == "multiplex":
+            self.deconv_layers = make_deconv_stack(extra, self.deconv_with_bias)
+            self._deconv_keys = ["deconv_layers"] * (self.up_steps if flavor == "interformer_2stage" else 2)
+        elif self.upsample_type == "deconv":
+            if flavor == "interformer":          # interformer.py:67-127 -- `upsample_layer.deconv_layers.<i>`
+                holder = nn.Module()
+                holder.deconv_layers = nn.ModuleList(make_deconv_stack(extra, self.deconv_with_bias)
+                                                     for _ in range(self.up_steps))
+                self.upsample_layer = holder
+                self._deconv_keys = ["upsample_layer.deconv_layers.%d" % i for i in range(self.up_steps)]
+            else:                                # interformer_2stage.py:244-260 -- deconv_layers1..3
+                for i in (1, 2, 3):
+                    setattr(self, "deconv_layers%d" % i, make_deconv_stack(extra, self.deconv_with_bias))
+                self._deconv_keys = ["deconv_layers%d" % (i + 1) for i in range(self.up_steps)]
+        else:
+            raise ValueError("unknown UPSAMPLE_TYPE %r" % self.upsample_type)
+        k = extra["FINAL_CONV_KERNEL"]
+        self.final_layer = nn.Conv2d(d_model, m.NUM_JOINTS, k, 1, 1 if k == 3 else 0)
+        self._cfg = dict(d_model=d_model, nhead=m.N_HEAD, layers=m.ENCODER_MULTI_LAYERS, final_k=k,
+                         num_deconv=extra.NUM_DECONV_LAYERS)
+        self._program = None
+        self._graphs = GraphedForward(self._eager)
+        self.use_cuda_graph = os.environ.get("I2R_CUDA_GRAPH", "1") != "0"
+        self.check_impl = False
+        self._runner_factory = Runner
+
+    @property
+    def returns_dict(self):
+        return self.inter_supervision and not self.singleformer_fix
+
+    # ------------------------------------------------------------------ weights -> device program
+    def prepare(self, device=None):
+        device = torch.device(device) if device is not None else self.final_layer.weight.device
+        sd = {k: v.detach().cpu() for k, v in self.state_dict().items()}
+        c = self._cfg
+        if c["final_k"] != 1:
+            raise NotImplementedError("FINAL_CONV_KERNEL=3")
+        if self.use_multi_pos and self.multi_position_mode != "conv":
+            raise NotImplementedError("MULTI_POS_EMBEDDING=%r with USE_MULTI_POS (kernels exist for 'conv')" %
+                                      self.multi_position_mode)
+        prog = type("Program", (), {})()
+        prog.device = device
+        prog.runner = self._runner_factory(device, 1 if self.check_impl else 0)
+        prog.first = self.singleformer.build_program(device)
+        prog.mask_embed = MaskEmbedProgram(sd, "multi_position_embedding", device) if self.use_multi_pos else None
+        prog.encoder = EncoderProgram(sd, "multi_global_encoder", c["layers"], c["d_model"], c["nhead"], device)
+        cache = {}
+
+        def deconv(key):
+            if key not in cache:
+                cache[key] = [DeconvProgram(sd, "%s.%d" % (key, 3 * i), "%s.%d" % (key, 3 * i + 1), device)
+                              for i in range(c["num_deconv"])]
+            return cache[key]
+        prog.upsample = [deconv(k) for k in self._deconv_keys]
+        prog.head = conv_bn_layer(sd, "final_layer", None, device=device)
+        offsets = {}
+
+        def seq_offsets(length, tokens_per_person):
+            key = (tuple(length), tokens_per_person)
+            if key not in offsets:
+                offsets[key] = GraphedForward.seq_offsets(length, tokens_per_person, device)
+            return offsets[key]
+        prog.seq_offsets = seq_offsets
+        self._program = prog
+        self._graphs.reset()
+        return self
+
+    def load_state_dict(self, *a, **kw):
+        out = super().load_state_dict(*a, **kw)
+        self._program = None
+        return out
+
+    def _apply(self, fn, *a, **kw):
+        out = super()._apply(fn, *a, **kw)
+        self._program = None
+        return out
+
+    # ------------------------------------------------------------------ forward
+    def _eager(self, x, pos_mask, length):
+        p = self._program
+        r = p.runner
+        feat, heat_single = p.first.run(r, x)                               # [S,h,w,d] fp16, [S,K,h,w] fp32
+        tok = feat
+        for _ in range(int(math.log(feat.shape[2] // self.trans_size[-1], 2))):   # interformer.py:260-264
+            tok = r.maxpool(tok)
+        s, th, tw, d = tok.shape
+        pos = None
+        if p.mask_embed is not None:
+            pos = p.mask_embed.run(r, pos_mask, (th, tw)).view(s * th * tw, d)
+        cu = p.seq_offsets(length, th * tw)
+        y = p.encoder.run(r, tok.view(s * th * tw, d), pos, cu, max(length) * th * tw).view(s, th, tw, d)
+        for stack in p.upsample:
+            for dc in stack:
+                y = dc.run(r, y)
+        y = r.add(feat, y)                                                   # single_res + x
+        heat_multi = r.conv(p.head, y, out_mode="nchw32")
+        if self.returns_dict:
+            return {"single": heat_single, "multi": heat_multi}
+        return heat_multi
+
+    def forward(self, x, pos_mask, length):
+        length = [int(n) for n in length]
+        if sum(length) != x.shape[0] or x.shape[0] != pos_mask.shape[0]:
+            raise ValueError("sum(length)=%d must equal the number of crops %d" % (sum(length), x.shape[0]))
+        if min(length) < 1:
+            raise ValueError("every image needs at least one person crop")
+        dev = self.final_layer.weight.device
+        if dev.type != "cuda":
+            raise capi.I2RError("%s forward runs on a CUDA (sm_100a) device only; move the module with .cuda() -- "
+                                "there is no CPU fallback" % self.flavor)
+        if self._program is None or self._program.device != dev:
+            self.prepare(dev)
+        x = x.to(dev, dtype=torch.float32, non_blocking=True).contiguous()
+        pos_mask = pos_mask.to(dev, dtype=torch.float32, non_blocking=True).contiguous()
+        with torch.no_grad():
+            if self.use_cuda_graph:
+                return self._graphs(x, pos_mask, length)
+            return self._eager(x, pos_mask, length)
+
+
+def build(cfg, is_train, flavor, models_pkg):
+    """`get_pose_net` body of both reference modules: the first stage is resolved by name exactly as
+    interformer.py:139 / interformer_2stage.py:428 do (`eval('models.' + cfg.MODEL.SINGLEFORMER + '.get_pose_net')`)."""
+    name = cfg.MODEL.SINGLEFORMER
+    if not name:
+        raise NotImplementedError("MODEL.SINGLEFORMER is empty: the stand-alone HRNet path (lib/models/hrnet.py) is "
+                                  "not referenced by any shipped config")
+    factory = getattr(getattr(models_pkg, name), "get_pose_net")
+    single = factory(cfg, is_train, cfg.MODEL.SINGLE_MODEL, cfg.MODEL.END2END)
+    return TwoStageInterFormer(cfg, single, flavor)

@@ -20,49 +20,9 @@ from i2r_b200.ops import ConvLayer, Runner
 from i2r_b200.packing import deconv4x4s2_phase_taps, fold_bn
 from i2r_b200.position import MaskEmbedParams, MaskEmbedProgram, sine_table
 from i2r_b200.engine import GraphedForward
+from i2r_b200.modules import DeconvProgram, EncoderParams
 
 logger = logging.getLogger(__name__)
-
-
-class EncoderLayerParams(nn.Module):
-    """self_attn / linear1 / linear2 / norm1 / norm2 holder (reference :169-180)."""
-
-    def __init__(self, d_model, nhead, dim_feedforward):
-        super().__init__()
-        self.self_attn = nn.MultiheadAttention(d_model, nhead, dropout=0.1)
-        self.linear1 = nn.Linear(d_model, dim_feedforward)
-        self.linear2 = nn.Linear(dim_feedforward, d_model)
-        self.norm1 = nn.LayerNorm(d_model)
-        self.norm2 = nn.LayerNorm(d_model)
-
-
-class EncoderParams(nn.Module):
-    def __init__(self, d_model, nhead, dim_feedforward, num_layers):
-        super().__init__()
-        self.layers = nn.ModuleList([EncoderLayerParams(d_model, nhead, dim_feedforward) for _ in range(num_layers)])
-        for p in self.parameters():
-            if p.dim() > 1:
-                nn.init.xavier_uniform_(p)
-
-
-class DeconvProgram:
-    """ConvTranspose2d(4, s=2, p=1) + BN + ReLU as four 2x2-tap phase problems in one grid."""
-
-    def __init__(self, sd, conv_key, bn_key, device):
-        w = sd[conv_key + ".weight"].float()          # [Cin, Cout, 4, 4]
-        scale, bias = fold_bn(sd, bn_key, w.shape[1], conv_bias=sd.get(conv_key + ".bias"))
-        self.phases = []
-        for py in (0, 1):
-            for px in (0, 1):
-                mats, dys, dxs = deconv4x4s2_phase_taps(w, py, px)
-                self.phases.append(((py, px), ConvLayer(mats, dys, dxs, scale, bias, relu=True, device=device)))
-        self.cout = w.shape[1]
-
-    def run(self, r, x):
-        nb, h, w, _ = x.shape
-        out = torch.empty((nb, 2 * h, 2 * w, self.cout), dtype=torch.float16, device=x.device)
-        r.conv_group([(L, x, dict(out=out, out_hw=(2 * h, 2 * w), out_mul=2, out_off=off)) for off, L in self.phases])
-        return out
 
 
 class TransPoseH(nn.Module):

@@ -1,0 +1,116 @@
+"""TransPose-H ("transpose_h"): HRNet-W48-S + intra-human Transformer encoder over the 64x48 tokens of a crop;
+the first stage of the two-stage I2R-Net (cfg.MODEL.SINGLEFORMER = transpose_h).
+
+Drop-in for the reference module of the same name (lib/models/transpose_h.py:416-707): same factory signature
+`get_pose_net(cfg, is_train, pretrained_path, is_end2end)`, same state_dict keys/shapes, and
+`forward(x) -> (feature map [S,d,H/4,W/4], heatmaps [S,K,H/4,W/4])` computed by the sm_100a kernels.
+"""
+import logging
+import os
+
+import torch
+import torch.nn as nn
+
+from i2r_b200 import capi
+from i2r_b200.first_stage import FirstStageProgram
+from i2r_b200.hrnet_w48 import attach_backbone_params
+from i2r_b200.modules import EncoderParams
+from i2r_b200.ops import Runner
+from i2r_b200.position import sine_table
+
+logger = logging.getLogger(__name__)
+
+
+class TransPoseH(nn.Module):
+    def __init__(self, cfg, **kwargs):
+        super().__init__()
+        extra = cfg["MODEL"]["EXTRA"]
+        pre = attach_backbone_params(self, extra)
+        m = cfg.MODEL
+        d_model = m.DIM_MODEL
+        w, h = m.IMAGE_SIZE
+        self.res_layer = int(m.HRNET_RES_LAYER)
+        w, h = w // 2 ** self.res_layer, h // 2 ** self.res_layer
+        self.reduce = nn.Conv2d(pre[self.res_layer], d_model, 1, bias=False)
+        if m.POS_EMBEDDING not in ("none", "learnable", "sine"):
+            raise AssertionError("POS_EMBEDDING must be none/learnable/sine")
+        if m.POS_EMBEDDING == "none":
+            self.pos_embedding = None
+        elif m.POS_EMBEDDING == "learnable":
+            self.pos_embedding = nn.Parameter(torch.randn((h // 4) * (w // 4), 1, d_model))
+        else:
+            self.pos_embedding = nn.Parameter(sine_table(h // 4, w // 4, d_model), requires_grad=False)
+        self.global_encoder = EncoderParams(d_model, m.N_HEAD, m.DIM_FEEDFORWARD, m.ENCODER_LAYERS)
+        k = extra["FINAL_CONV_KERNEL"]
+        self.final_layer = nn.Conv2d(d_model, cfg["MODEL"]["NUM_JOINTS"], k, 1, 1 if k == 3 else 0)
+        self.pretrained_layers = extra["PRETRAINED_LAYERS"]
+        self._cfg = dict(d_model=d_model, nhead=m.N_HEAD, layers=m.ENCODER_LAYERS, final_k=k,
+                         res_layer=self.res_layer)
+        self._program = None
+        self._runner = None
+
+    def build_program(self, device):
+        """Fold BN, pack weights, upload: the device program the two-stage wrapper (or forward) runs."""
+        sd = {k: v.detach().cpu() for k, v in self.state_dict().items()}
+        return FirstStageProgram(self, sd, torch.device(device))
+
+    def load_state_dict(self, *a, **kw):
+        out = super().load_state_dict(*a, **kw)
+        self._program = None
+        return out
+
+    def _apply(self, fn, *a, **kw):
+        out = super()._apply(fn, *a, **kw)
+        self._program = None
+        return out
+
+    def forward(self, x):
+        dev = self.final_layer.weight.device
+        if dev.type != "cuda":
+            raise capi.I2RError("transpose_h forward runs on a CUDA (sm_100a) device only; move the module with "
+                                ".cuda() -- there is no CPU fallback")
+        if self._program is None or self._program.device != dev:
+            self._program = self.build_program(dev)
+            self._runner = Runner(dev, 0)
+        x = x.to(dev, dtype=torch.float32, non_blocking=True).contiguous()
+        with torch.no_grad():
+            feat, heat = self._program.run(self._runner, x)
+            return feat.permute(0, 3, 1, 2).float(), heat      # the reference returns NCHW fp32 tensors
+
+    def init_weights(self, pretrained="", print_load_info=False):
+        """Reference :657-688: N(0, 0.001) convs, identity BN, then the PRETRAINED_LAYERS of a checkpoint."""
+        for mod in self.modules():
+            if isinstance(mod, (nn.Conv2d, nn.ConvTranspose2d)):
+                nn.init.normal_(mod.weight, std=0.001)
+                if mod.bias is not None:
+                    nn.init.constant_(mod.bias, 0)
+            elif isinstance(mod, nn.BatchNorm2d):
+                nn.init.constant_(mod.weight, 1)
+                nn.init.constant_(mod.bias, 0)
+        if os.path.isfile(pretrained):
+            ckpt = torch.load(pretrained, map_location="cpu")
+            own = self.state_dict()
+            keep = {}
+            for name, t in ckpt.items():
+                if (name.split(".")[0] in self.pretrained_layers and name in own) or self.pretrained_layers[0] == "*":
+                    keep[name] = t
+                    if print_load_info:
+                        print(":: {} is loaded from {}".format(name, pretrained))
+            self.load_state_dict(keep, strict=False)
+        elif pretrained:
+            logger.error("=> please download pre-trained models first!")
+            raise ValueError("{} is not exist!".format(pretrained))
+        self._program = None
+
+
+def get_pose_net(cfg, is_train, pretrained_path="", is_end2end=False, **kwargs):
+    model = TransPoseH(cfg, **kwargs)
+    if is_train:
+        if is_end2end:
+            model.init_weights(cfg["MODEL"]["PRETRAINED"])
+        else:
+            ckpt = torch.load(pretrained_path, map_location="cpu")
+            model.load_state_dict(ckpt, strict=False)
+            if cfg["MODEL"]["SINGLEFORMER_FIX"]:
+                model.requires_grad_(False)
+    return model

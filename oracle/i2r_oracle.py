@@ -227,3 +227,81 @@ def vanilla_forward(sd, cfg, x, pos_mask, length, taps=None):
             y = F.relu(_bn(sd, "deconv_layers.%d" % (3 * i + 1), y))
     y = F.conv2d(y, sd["final_layer.weight"], sd["final_layer.bias"])
     return unpad_persons(y, length)
+
+
+def transpose_h_first_stage(sd, cfg, x, prefix=""):
+    """transpose_h.TransPoseH.forward (lib/models/transpose_h.py:623-655): backbone -> reduce on branch
+    HRNET_RES_LAYER -> post-norm encoder over the h*w tokens of each crop, pos = the [h*w,1,d] parameter ->
+    (feature map, final_layer heatmaps).  `sd` holds fp32 tensors; keys are looked up under `prefix`."""
+    m = cfg.MODEL
+    feats = hrnet_w48s_backbone(sd, x, prefix)
+    f = F.conv2d(feats[int(m.HRNET_RES_LAYER)], sd[prefix + "reduce.weight"])
+    bs, c, h, w = f.shape
+    src = f.flatten(2).permute(2, 0, 1)                                         # [h*w, S, c]
+    pos = sd.get(prefix + "pos_embedding")
+    y = encoder_post_norm(sd, prefix + "global_encoder", src, pos, None, m.ENCODER_LAYERS)
+    feat = y.permute(1, 2, 0).contiguous().view(bs, c, h, w)
+    return feat, F.conv2d(feat, sd[prefix + "final_layer.weight"], sd[prefix + "final_layer.bias"])
+
+
+def _deconv_block(sd, key, y, num_layers):
+    for i in range(num_layers):
+        y = F.conv_transpose2d(y, sd["%s.%d.weight" % (key, 3 * i)], sd.get("%s.%d.bias" % (key, 3 * i)), 2, 1, 0)
+        y = F.relu(_bn(sd, "%s.%d" % (key, 3 * i + 1), y))
+    return y
+
+
+def two_stage_forward(sd, cfg, x, pos_mask, length, taps=None):
+    """InterFormer.forward of lib/models/interformer.py:282-323 and lib/models/interformer_2stage.py:383-423
+    (same arithmetic; cfg.MODEL.NAME selects the parameter names of the upsample path) with a TransPose-H first
+    stage.  Returns {'single', 'multi'} or the 'multi' tensor, as the reference does."""
+    sd = {k: v.float() for k, v in sd.items() if v.dtype.is_floating_point}
+    m = cfg.MODEL
+    length = list(length)
+    if m.SINGLEFORMER != "transpose_h":
+        raise NotImplementedError("oracle first stage %r" % m.SINGLEFORMER)
+    feat, single = transpose_h_first_stage(sd, cfg, x, "singleformer.")
+    if taps is not None:
+        taps["feat"] = feat
+    t = feat
+    for _ in range(int(math.log(feat.shape[-1] // m.TRANS_SIZE[-1], 2))):      # interformer.py:260-264
+        t = F.max_pool2d(t, 3, 2, 1)
+    bs, n_max = len(length), max(length)
+    _, c, h, w = t.shape
+    pos = None
+    if m.USE_MULTI_POS:
+        if m.MULTI_POS_EMBEDDING != "conv":
+            raise NotImplementedError("oracle MULTI_POS_EMBEDDING %r" % m.MULTI_POS_EMBEDDING)
+        pos5 = mask_embedding_conv(sd, "multi_position_embedding", pad_persons(pos_mask, length), list(m.TRANS_SIZE))
+        pos = pos5.permute(0, 2, 1, 3, 4).flatten(2).permute(2, 0, 1)
+    mask = person_mask(length, (h, w)).flatten(1)
+    src = pad_persons(t, length).permute(0, 2, 1, 3, 4).flatten(2).permute(2, 0, 1)
+    y = encoder_post_norm(sd, "multi_global_encoder", src, pos, mask, m.ENCODER_MULTI_LAYERS)
+    y = y.permute(1, 2, 0).contiguous().view(bs, c, n_max, h, w)
+    y = unpad_persons(y.permute(0, 2, 1, 3, 4).reshape(bs * n_max, c, h, w), length)
+    if taps is not None:
+        taps["encoded"] = y
+    nl = m.EXTRA.NUM_DECONV_LAYERS
+    steps = int(math.log(m.HEATMAP_SIZE[0] // m.TRANS_SIZE[1], 2))
+    if m.UPSAMPLE_TYPE == "multiplex":
+        # interformer.py applies the stack twice (:310-312); interformer_2stage log2(ratio) times (:375-377)
+        for _ in range(steps if m.NAME == "interformer_2stage" else 2):
+            y = _deconv_block(sd, "deconv_layers", y, nl)
+    elif m.UPSAMPLE_TYPE == "deconv":
+        for i in range(steps):
+            key = "deconv_layers%d" % (i + 1) if m.NAME == "interformer_2stage" else "upsample_layer.deconv_layers.%d" % i
+            y = _deconv_block(sd, key, y, nl)
+    else:
+        raise NotImplementedError("oracle UPSAMPLE_TYPE %r" % m.UPSAMPLE_TYPE)
+    y = feat + y
+    multi = F.conv2d(y, sd["final_layer.weight"], sd["final_layer.bias"])
+    if m.INTER_SUPERVISION and not m.SINGLEFORMER_FIX:
+        return {"single": single, "multi": multi}
+    return multi
+
+
+def forward(sd, cfg, x, pos_mask, length, taps=None):
+    """Dispatch on cfg.MODEL.NAME like tools/test.py:87 does."""
+    if cfg.MODEL.NAME == "interformer_pureMulti":
+        return vanilla_forward(sd, cfg, x, pos_mask, length, taps)
+    return two_stage_forward(sd, cfg, x, pos_mask, length, taps)

@@ -27,6 +27,10 @@ CASES = {
     # name: (yaml, length, H, W)
     "vanilla_c1": ("coco/interformer_coco_w48_pure_en6.yaml", [1], 256, 192),
     "vanilla_ragged": ("coco/interformer_coco_w48_pure_en6.yaml", [2, 1], 256, 192),
+    # two-stage, TransPose-H first stage (6 intra layers over 3072 tokens per crop), 4 inter layers, multiplex deconv
+    "tph2stage_ragged": ("coco/interformer_coco_tph_192_p4_b4.yaml", [2, 1], 256, 192),
+    # `interformer` naming: CrowdPose TransPose-H (4 intra / 2 inter layers, no multi-pos, distinct deconvs, 14 joints)
+    "tph_crowdpose_ragged": ("crowdpose/interformer_crowdpose_tph_192_p6_b4.yaml", [1, 2], 256, 192),
 }
 
 
@@ -35,18 +39,22 @@ def main():
     torch.set_num_threads(os.cpu_count())
     models = {}
     for name, (yaml_rel, length, h, w) in CASES.items():
+        if len(sys.argv) > 1 and name not in sys.argv[1:]:
+            continue
         if yaml_rel not in models:
             cfg, model = ref_harness.build_reference_model(yaml_rel)
             sd = synth_state_dict(model.state_dict(), seed=0)
             model.load_state_dict(sd, strict=True)
             models[yaml_rel] = model
             keys = {k: [list(v.shape), str(v.dtype).replace("torch.", "")] for k, v in model.state_dict().items()}
-            with open(os.path.join(HERE, "state_dict_%s.json" % cfg.MODEL.NAME), "w") as f:
+            tag = cfg.MODEL.NAME if cfg.MODEL.NAME == "interformer_pureMulti" else os.path.basename(yaml_rel)[:-5]
+            with open(os.path.join(HERE, "state_dict_%s.json" % tag), "w") as f:
                 json.dump(keys, f, indent=0, sort_keys=True)
         model = models[yaml_rel]
         x, pm = synth_inputs(sum(length), h, w, seed=1)
         taps = {}
         hooks = []
+        only = [a for a in sys.argv[1:] if not a.startswith("-")]
         if hasattr(model, "reduce"):
             hooks.append(model.reduce.register_forward_hook(lambda m, i, o: taps.__setitem__("reduce", o.detach())))
         if hasattr(model, "global_encoder"):

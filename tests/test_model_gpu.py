@@ -90,3 +90,58 @@ def test_forward_rejects_bad_length_and_cpu(vanilla_cuda):
     cpu_cfg, cpu_model, _ = build_model()
     with pytest.raises(capi.I2RError):
         cpu_model(x, pm, [1])
+
+
+# ---------------------------------------------------------------------------------------------- two-stage models
+# TransPose-H first stage + inter-human stage.  PRECISION STATUS: these families run on the
+# single-pass fp16 kernels; the reference is ~5x more sensitive to operand rounding here than the vanilla model
+# (six post-norm LayerNorm layers sit on the direct path to the heatmaps), and the measured error is ~3e-3 --
+# ABOVE the 1e-3 north_star bar, which needs the split-operand mode.  The test pins the measured level so that a
+# regression shows, and records the numbers; it does not claim the 1e-3 bar for these families.
+TWO_STAGE_TOL = 6e-3
+TWO_STAGE = [
+    ("coco/interformer_coco_tph_192_p4_b4.yaml", "tph2stage_ragged"),
+    ("crowdpose/interformer_crowdpose_tph_192_p6_b4.yaml", "tph_crowdpose_ragged"),
+]
+
+
+@pytest.mark.parametrize("yaml_rel,case", TWO_STAGE, ids=[c[1] for c in TWO_STAGE])
+def test_two_stage_matches_reference_golden(yaml_rel, case):
+    cfg, model, _ = build_model(yaml_rel)
+    model = model.cuda()
+    g = load_golden(case)
+    length = [int(v) for v in g["length"]]
+    x, pm = inputs_for(length)
+    model.use_cuda_graph = False
+    out = model(x, pm, length)
+    torch.cuda.synchronize()
+    assert isinstance(out, dict) and sorted(out) == ["multi", "single"]
+    errs = {}
+    for k in out:
+        assert out[k].dtype == torch.float32 and tuple(out[k].shape) == g["out_" + k].shape and out[k].is_cuda
+        errs[k] = float(np.abs(out[k].cpu().numpy() - g["out_" + k]).max())
+    _report(test="two_stage_golden", case=case, max_abs_err=errs, meets_1e_3=bool(max(errs.values()) <= TOL),
+            out_max=float(np.abs(g["out_multi"]).max()), launches=model._program.runner.launches)
+    assert all(np.isfinite(v) and v <= TWO_STAGE_TOL for v in errs.values()), errs
+    # graph replay must reproduce the eager result exactly
+    model.use_cuda_graph = True
+    g1 = model(x, pm, length)
+    torch.cuda.synchronize()
+    assert all(torch.equal(g1[k], out[k]) for k in out)
+
+
+def test_transpose_h_standalone_forward():
+    """models.transpose_h.get_pose_net(...).forward(x) -> (feature map, heatmaps), the first stage on its own."""
+    from oracle import i2r_oracle
+    cfg, model, sd = build_model("coco/interformer_coco_tph_192_p4_b4.yaml")
+    first = model.singleformer.cuda()
+    x, _ = inputs_for([2])
+    feat, heat = first(x)
+    torch.cuda.synchronize()
+    sd1 = {k[len("singleformer."):]: v.float() for k, v in sd.items() if k.startswith("singleformer.") and v.dtype.is_floating_point}
+    with torch.no_grad():
+        rf, rh = i2r_oracle.transpose_h_first_stage(sd1, cfg, x)
+    assert tuple(feat.shape) == tuple(rf.shape) and tuple(heat.shape) == tuple(rh.shape)
+    e_feat, e_heat = float((feat.cpu() - rf).abs().max()), float((heat.cpu() - rh).abs().max())
+    _report(test="transpose_h_standalone", feat_err=e_feat, heat_err=e_heat, feat_max=float(rf.abs().max()))
+    assert e_heat <= TWO_STAGE_TOL and e_feat <= 5e-2, (e_feat, e_heat)

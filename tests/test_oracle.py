@@ -48,3 +48,29 @@ def test_unpad_matches_reference_helper():
     out = get_valid_output(t, [2, 1])
     assert torch.equal(out, torch.cat([t[0:2], t[2:3]], dim=0))
     assert torch.equal(out, i2r_oracle.unpad_persons(t, [2, 1]))
+
+
+TWO_STAGE = [
+    ("coco/interformer_coco_tph_192_p4_b4.yaml", "tph2stage_ragged", 1104),
+    ("crowdpose/interformer_crowdpose_tph_192_p6_b4.yaml", "tph_crowdpose_ragged", 1062),
+]
+
+
+@pytest.mark.parametrize("yaml_rel,case,nkeys", TWO_STAGE, ids=[c[1] for c in TWO_STAGE])
+def test_two_stage_oracle_and_surface_match_reference(yaml_rel, case, nkeys):
+    """TransPose-H first stage + inter-human stage (models.interformer / models.interformer_2stage): the oracle
+    restatement against outputs of the real reference, and the drop-in module's state_dict against the reference's."""
+    cfg, model, sd = build_model(yaml_rel)
+    with open(os.path.join(GOLDEN, "state_dict_%s.json" % os.path.basename(yaml_rel)[:-5])) as f:
+        ref = json.load(f)
+    own = {k: [list(v.shape), str(v.dtype).replace("torch.", "")] for k, v in model.state_dict().items()}
+    assert own == ref and len(own) == nkeys
+    g = load_golden(case)
+    length = [int(v) for v in g["length"]]
+    x, pm = inputs_for(length)
+    with torch.no_grad():
+        out = i2r_oracle.forward(sd, cfg, x, pm, length)
+    assert sorted(out) == ["multi", "single"]
+    for k in out:
+        err = float(np.abs(out[k].numpy() - g["out_" + k]).max())
+        assert err <= 2e-5, (k, err)
