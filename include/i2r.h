@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define I2R_ABI_VERSION 2
+#define I2R_ABI_VERSION 3
 
 #define I2R_E_BADARG (-1)
 #define I2R_E_UNSUPPORTED (-2)
@@ -38,6 +38,13 @@ extern "C" {
 #define I2R_F_RELU 1u        /* clamp at 0 after scale/bias/addends                         */
 #define I2R_F_OUT_NCHW_F32 2u /* write fp32 NCHW (heatmap head) instead of fp16 NHWC         */
 #define I2R_F_OUT_F32 4u      /* write fp32 NHWC (row-major [pixels, Cout])                  */
+/* Split-operand mode (the 1e-3 heatmap bar of the TransPose-H families needs ~22-bit operands): activations are
+ * fp16 PAIRS -- a pixel holds 2*C channels, [0,C) = hi, [C,2C) = lo, value = hi + lo -- and a product is
+ * x_hi*W_hi + x_lo*W_hi + x_hi*W_lo with fp32 accumulation, evaluated as ONE GEMM over K = [x_hi | x_lo | x_hi]
+ * against weights packed as [W_hi | W_hi | W_lo] (3*ceil(Cin/64) K-chunks per tap).  x, add0/add1 and an fp16
+ * NHWC output are all pair tensors (addend pointers address the hi half; lo is Cout channels further); Cin / Cout
+ * stay the logical channel counts; the pixel strides are the physical ones (>= 2*C). */
+#define I2R_F_SPLIT 8u
 
 /*
  * One implicit-GEMM problem:  Y[p, n] = act( scale[n] * sum_{t,c} X[src(p,t), c] * W[t, c, n]
@@ -101,15 +108,15 @@ int i2r_conv_halo_supported(const i2r_conv_problem* prob);
 int i2r_conv_halo(const i2r_conv_problem* probs, int nprob, void* stream);
 
 /* Stem / mask convolution on fp32 NCHW input with tiny Cin (3 or 1): 3x3 stride 2 pad 1 + folded
- * BN + ReLU -> fp16 NHWC [NB, H/2, W/2, Cout].  Replaces conv1/bn1/relu
+ * BN + ReLU -> fp16 NHWC [NB, H/2, W/2, Cout] (split != 0: pair tensor [.., 2*Cout], see I2R_F_SPLIT).  Replaces conv1/bn1/relu
  * (interformer_pureMulti.py:677-679) and position_embedding.conv1/bn1/relu
  * (position_embedding.py:108-110).  w: fp32 [Cin*9][Cout] (k = (c*3+ky)*3+kx). */
 int i2r_stem_conv3x3s2(const float* x, const float* w, const float* scale, const float* bias, void* y,
-                       int NB, int Cin, int H, int W, int Cout, void* stream);
+                       int NB, int Cin, int H, int W, int Cout, int split, void* stream);
 
 /* MaxPool2d(kernel 3, stride 2, padding 1) on fp16 NHWC (position_embedding.py:9,:113-114;
  * interformer.py:260-264). */
-int i2r_maxpool3x3s2(const void* x, void* y, int NB, int H, int W, int C, void* stream);
+int i2r_maxpool3x3s2(const void* x, void* y, int NB, int H, int W, int C, int split, void* stream);
 
 /* Single-head scaled-dot-product attention over ragged sequences (one per image):
  *   out[t, :] = softmax_j( scale * q[t,:] . k[j,:] ) v[j,:]   for j in the same sequence.
@@ -118,19 +125,23 @@ int i2r_maxpool3x3s2(const void* x, void* y, int NB, int H, int W, int C, void* 
  * When few (sequence, query-tile) pairs exist the keys are split across CTAs and merged by a second
  * kernel; `workspace` (i2r_attention_workspace_bytes(), may be NULL/0 = no splitting) holds the fp32 partials.
  * Equivalent to nn.MultiheadAttention(nhead=1) with key_padding_mask on padded persons
- * (interformer_pureMulti.py:199-204; torch F.multi_head_attention_forward). */
+ * (interformer_pureMulti.py:199-204; torch F.multi_head_attention_forward); with one crop per sequence it is the
+ * intra-human attention of TransPose-H (transpose_h.py:165-240).  split != 0: split-operand mode (I2R_F_SPLIT) --
+ * the lo half of each q/k/v/out row starts q_lo/k_lo/v_lo/o_lo elements after its hi half. */
 int64_t i2r_attention_workspace_bytes(int total_tokens, int D, int nseq, int max_seqlen);
 int i2r_attention_varlen(const void* q, const void* k, const void* v, void* out, int ldq, int ldk, int ldv,
                          int ldo, int D, const int32_t* cu_seqlens, int nseq, int max_seqlen, int total_tokens,
-                         float scale, void* workspace, int64_t workspace_bytes, void* stream);
+                         float scale, void* workspace, int64_t workspace_bytes, int split, int q_lo, int k_lo,
+                         int v_lo, int o_lo, void* stream);
 
 /* y = LayerNorm(x) * gamma + beta over the last dim C (<= 256, multiple of 8), fp16 in/out, fp32
  * math; optional y2 = y + pos (the next layer's q/k input).  (interformer_pureMulti.py:206,:209) */
 int i2r_layernorm(const void* x, const float* gamma, const float* beta, const void* pos, void* y, void* y2,
-                  int rows, int C, float eps, void* stream);
+                  int rows, int C, float eps, int split, void* stream);
 
-/* y = a + b elementwise on fp16, n multiple of 8 (with_pos_embed, interformer_pureMulti.py:189). */
-int i2r_add_f16(const void* a, const void* b, void* y, int64_t n, void* stream);
+/* y = a + b elementwise on fp16, n multiple of 8 (with_pos_embed, interformer_pureMulti.py:189; the residual
+ * `single_res + x`, interformer.py:315).  split_c > 0: the operands are pair tensors with C = split_c. */
+int i2r_add_f16(const void* a, const void* b, void* y, int64_t n, int split_c, void* stream);
 
 /* Profiling aid: while dev_buffer != NULL, CTA `cta` of every i2r_conv_halo launch writes (tag<<32 | tile, clock64)
  * pairs into four role regions (producer, MMA, epilogue, kernel start/end) of `capacity_events` pairs each (zero-filled by the caller).  Tags: 1/2/3

@@ -41,13 +41,17 @@ __device__ __forceinline__ void load_tile(uint32_t sdst, const __half* __restric
   }
 }
 
-template <int HD>
+// SPLIT: split-operand mode (include/i2r.h, I2R_F_SPLIT) -- q/k/v rows carry a lo half `*_lo` elements after the hi
+// half; scores = q_hi k_hi + q_hi k_lo + q_lo k_hi, O += P (v_hi + v_lo) with fp16 probabilities, and the output row
+// is written as a pair (lo half o_lo elements after the hi half).
+template <int HD, bool SPLIT>
 __global__ void __launch_bounds__(128) attention_kernel(const __half* __restrict__ q, const __half* __restrict__ k,
                                                         const __half* __restrict__ v, __half* __restrict__ out,
                                                         int ldq, int ldk, int ldv, int ldo,
                                                         const int32_t* __restrict__ cu_seqlens, float scale_log2e,
                                                         int nsplit, float* __restrict__ opart,
-                                                        float* __restrict__ mlpart) {
+                                                        float* __restrict__ mlpart, int q_lo, int k_lo, int v_lo,
+                                                        int o_lo) {
   constexpr int PITCH = (HD + 8) * 2;
   constexpr int TILE = ATT_BK * PITCH;
   constexpr int KS = HD / 16;  // k-steps over the head dim
@@ -62,6 +66,9 @@ __global__ void __launch_bounds__(128) attention_kernel(const __half* __restrict
   const uint32_t sQ = smem_u32(smem);
   const uint32_t sK = sQ + TILE;       // 2 stages
   const uint32_t sV = sK + 2 * TILE;   // 2 stages
+  const uint32_t sQl = sV + 2 * TILE;  // SPLIT: lo halves, same arrangement
+  const uint32_t sKl = sQl + TILE;
+  const uint32_t sVl = sKl + 2 * TILE;
 
   // split-KV: this CTA covers key tiles [kt_begin, kt_end) of the sequence (all of them when nsplit == 1)
   const int ntiles_all = (L + ATT_BK - 1) / ATT_BK;
@@ -72,10 +79,16 @@ __global__ void __launch_bounds__(128) attention_kernel(const __half* __restrict
     load_tile<HD>(sQ, q, ldq, t0 + q0, min(ATT_BQ, L - q0), tid);
     load_tile<HD>(sK, k, ldk, t0 + kt_begin * ATT_BK, min(ATT_BK, L - kt_begin * ATT_BK), tid);
     load_tile<HD>(sV, v, ldv, t0 + kt_begin * ATT_BK, min(ATT_BK, L - kt_begin * ATT_BK), tid);
+    if (SPLIT) {
+      load_tile<HD>(sQl, q + q_lo, ldq, t0 + q0, min(ATT_BQ, L - q0), tid);
+      load_tile<HD>(sKl, k + k_lo, ldk, t0 + kt_begin * ATT_BK, min(ATT_BK, L - kt_begin * ATT_BK), tid);
+      load_tile<HD>(sVl, v + v_lo, ldv, t0 + kt_begin * ATT_BK, min(ATT_BK, L - kt_begin * ATT_BK), tid);
+    }
     cp_async_commit();
   }
 
   uint32_t qf[KS][4];
+  uint32_t qfl[SPLIT ? KS : 1][4];
   float o[DT][4];
 #pragma unroll
   for (int i = 0; i < DT; ++i)
@@ -89,6 +102,10 @@ __global__ void __launch_bounds__(128) attention_kernel(const __half* __restrict
       const int kr = (kt + 1) * ATT_BK;
       load_tile<HD>(sK + (st ^ 1) * TILE, k, ldk, t0 + kr, min(ATT_BK, L - kr), tid);
       load_tile<HD>(sV + (st ^ 1) * TILE, v, ldv, t0 + kr, min(ATT_BK, L - kr), tid);
+      if (SPLIT) {
+        load_tile<HD>(sKl + (st ^ 1) * TILE, k + k_lo, ldk, t0 + kr, min(ATT_BK, L - kr), tid);
+        load_tile<HD>(sVl + (st ^ 1) * TILE, v + v_lo, ldv, t0 + kr, min(ATT_BK, L - kr), tid);
+      }
       cp_async_commit();
       cp_async_wait<1>();
     } else {
@@ -101,6 +118,7 @@ __global__ void __launch_bounds__(128) attention_kernel(const __half* __restrict
         const int row = warp * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
         const int col = ks * 16 + (lane >> 4) * 8;
         ldsm_x4(sQ + row * PITCH + col * 2, qf[ks][0], qf[ks][1], qf[ks][2], qf[ks][3]);
+        if (SPLIT) ldsm_x4(sQl + row * PITCH + col * 2, qfl[ks][0], qfl[ks][1], qfl[ks][2], qfl[ks][3]);
       }
     }
     // ---- S = Q K^T for this warp's 16 rows x 64 keys
@@ -120,6 +138,13 @@ __global__ void __launch_bounds__(128) attention_kernel(const __half* __restrict
         ldsm_x4(kb + key * PITCH + col * 2, b0, b1, b2, b3);
         mma16816(s[nt], qf[ks], b0, b1);
         mma16816(s[nt + 1], qf[ks], b2, b3);
+        if (SPLIT) {
+          mma16816(s[nt], qfl[ks], b0, b1);          // q_lo k_hi
+          mma16816(s[nt + 1], qfl[ks], b2, b3);
+          ldsm_x4(sKl + st * TILE + key * PITCH + col * 2, b0, b1, b2, b3);
+          mma16816(s[nt], qf[ks], b0, b1);           // q_hi k_lo
+          mma16816(s[nt + 1], qf[ks], b2, b3);
+        }
       }
     }
     // ---- online softmax (rows r0 = lane/4, r1 = r0+8 of the warp's 16)
@@ -179,6 +204,11 @@ __global__ void __launch_bounds__(128) attention_kernel(const __half* __restrict
         ldsm_x4_t(vb + key * PITCH + col * 2, b0, b1, b2, b3);
         mma16816(o[dt], pa, b0, b1);
         mma16816(o[dt + 1], pa, b2, b3);
+        if (SPLIT) {
+          ldsm_x4_t(sVl + st * TILE + key * PITCH + col * 2, b0, b1, b2, b3);
+          mma16816(o[dt], pa, b0, b1);
+          mma16816(o[dt + 1], pa, b2, b3);
+        }
       }
     }
     __syncthreads();  // all warps done with stage st before it is refilled
@@ -194,10 +224,24 @@ __global__ void __launch_bounds__(128) attention_kernel(const __half* __restrict
 #pragma unroll
     for (int dt = 0; dt < DT; ++dt) {
       const int col = dt * 8 + (lane & 3) * 2;
-      if (r0 < L)
-        *reinterpret_cast<uint32_t*>(out + static_cast<int64_t>(t0 + r0) * ldo + col) = pack_h2(o[dt][0] * i0, o[dt][1] * i0);
-      if (r1 < L)
-        *reinterpret_cast<uint32_t*>(out + static_cast<int64_t>(t0 + r1) * ldo + col) = pack_h2(o[dt][2] * i1, o[dt][3] * i1);
+      if (r0 < L) {
+        const uint32_t h = pack_h2(o[dt][0] * i0, o[dt][1] * i0);
+        *reinterpret_cast<uint32_t*>(out + static_cast<int64_t>(t0 + r0) * ldo + col) = h;
+        if (SPLIT) {
+          const float2 f = unpack_h2(h);
+          *reinterpret_cast<uint32_t*>(out + static_cast<int64_t>(t0 + r0) * ldo + o_lo + col) =
+              pack_h2(o[dt][0] * i0 - f.x, o[dt][1] * i0 - f.y);
+        }
+      }
+      if (r1 < L) {
+        const uint32_t h = pack_h2(o[dt][2] * i1, o[dt][3] * i1);
+        *reinterpret_cast<uint32_t*>(out + static_cast<int64_t>(t0 + r1) * ldo + col) = h;
+        if (SPLIT) {
+          const float2 f = unpack_h2(h);
+          *reinterpret_cast<uint32_t*>(out + static_cast<int64_t>(t0 + r1) * ldo + o_lo + col) =
+              pack_h2(o[dt][2] * i1 - f.x, o[dt][3] * i1 - f.y);
+        }
+      }
     }
   } else {
     // un-normalised partial result + (running max, running sum) for the merge kernel
@@ -221,7 +265,8 @@ __global__ void __launch_bounds__(128) attention_kernel(const __half* __restrict
 template <int HD>
 __global__ void __launch_bounds__(256) attention_merge_kernel(const float* __restrict__ opart,
                                                               const float* __restrict__ mlpart,
-                                                              __half* __restrict__ out, int ldo, int rows, int nsplit) {
+                                                              __half* __restrict__ out, int ldo, int rows, int nsplit,
+                                                              int o_lo) {
   const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (row >= rows) return;
@@ -245,7 +290,11 @@ __global__ void __launch_bounds__(256) attention_merge_kernel(const float* __res
 #pragma unroll
   for (int i = 0; i < (HD + 31) / 32; ++i) {
     const int c = lane + 32 * i;
-    if (c < HD) out[static_cast<int64_t>(row) * ldo + c] = __float2half_rn(acc[i] * inv);
+    if (c < HD) {
+      const __half h = __float2half_rn(acc[i] * inv);
+      out[static_cast<int64_t>(row) * ldo + c] = h;
+      if (o_lo > 0) out[static_cast<int64_t>(row) * ldo + o_lo + c] = __float2half_rn(acc[i] * inv - __half2float(h));
+    }
   }
 }
 
@@ -260,14 +309,14 @@ static int choose_nsplit(int nseq, int max_seqlen) {
   return ns;
 }
 
-template <int HD>
+template <int HD, bool SPLIT>
 static int launch_attention(const void* q, const void* k, const void* v, void* out, int ldq, int ldk, int ldv, int ldo,
                             const int32_t* cu, int nseq, int max_seqlen, int total_tokens, float scale, void* ws,
-                            int64_t ws_bytes, cudaStream_t st) {
-  constexpr int smem = 5 * ATT_BK * (HD + 8) * 2;
+                            int64_t ws_bytes, int q_lo, int k_lo, int v_lo, int o_lo, cudaStream_t st) {
+  constexpr int smem = (SPLIT ? 10 : 5) * ATT_BK * (HD + 8) * 2;
   static bool attr_done = false;
   if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(attention_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaError_t e = cudaFuncSetAttribute(attention_kernel<HD, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) {
       set_error("cudaFuncSetAttribute(attention): %s", cudaGetErrorString(e));
       return static_cast<int>(e);
@@ -280,13 +329,14 @@ static int launch_attention(const void* q, const void* k, const void* v, void* o
   float* opart = static_cast<float*>(ws);
   float* mlpart = opart ? opart + static_cast<int64_t>(total_tokens) * nsplit * HD : nullptr;
   dim3 grid((max_seqlen + ATT_BQ - 1) / ATT_BQ, nseq, nsplit);
-  attention_kernel<HD><<<grid, 128, smem, st>>>(static_cast<const __half*>(q), static_cast<const __half*>(k),
-                                                static_cast<const __half*>(v), static_cast<__half*>(out), ldq, ldk,
-                                                ldv, ldo, cu, scale * 1.4426950408889634f, nsplit, opart, mlpart);
+  attention_kernel<HD, SPLIT><<<grid, 128, smem, st>>>(
+      static_cast<const __half*>(q), static_cast<const __half*>(k), static_cast<const __half*>(v),
+      static_cast<__half*>(out), ldq, ldk, ldv, ldo, cu, scale * 1.4426950408889634f, nsplit, opart, mlpart, q_lo, k_lo,
+      v_lo, o_lo);
   int rc = check_launch("attention_kernel");
   if (rc || nsplit == 1) return rc;
   attention_merge_kernel<HD><<<(total_tokens + 7) / 8, 256, 0, st>>>(opart, mlpart, static_cast<__half*>(out), ldo,
-                                                                     total_tokens, nsplit);
+                                                                     total_tokens, nsplit, SPLIT ? o_lo : 0);
   return check_launch("attention_merge_kernel");
 }
 
@@ -300,7 +350,7 @@ extern "C" int64_t i2r_attention_workspace_bytes(int total_tokens, int D, int ns
 extern "C" int i2r_attention_varlen(const void* q, const void* k, const void* v, void* out, int ldq, int ldk, int ldv,
                                     int ldo, int D, const int32_t* cu_seqlens, int nseq, int max_seqlen,
                                     int total_tokens, float scale, void* workspace, int64_t workspace_bytes,
-                                    void* stream) {
+                                    int split, int q_lo, int k_lo, int v_lo, int o_lo, void* stream) {
   using namespace i2r;
   if (!q || !k || !v || !out || !cu_seqlens || nseq <= 0 || max_seqlen <= 0 || total_tokens <= 0 ||
       (ldq | ldk | ldv | ldo) % 8 != 0) {
@@ -308,13 +358,20 @@ extern "C" int i2r_attention_varlen(const void* q, const void* k, const void* v,
     return I2R_E_BADARG;
   }
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (split && ((q_lo | k_lo | v_lo | o_lo) % 8 != 0 || o_lo < D)) {
+    set_error("i2r_attention_varlen: split-operand offsets must be multiples of 8 (o_lo >= D)");
+    return I2R_E_BADARG;
+  }
+#define I2R_ATT_CASE(HD_)                                                                                              \
+  case HD_:                                                                                                            \
+    return split ? launch_attention<HD_, true>(q, k, v, out, ldq, ldk, ldv, ldo, cu_seqlens, nseq, max_seqlen,           \
+                                               total_tokens, scale, workspace, workspace_bytes, q_lo, k_lo, v_lo, o_lo, \
+                                               st)                                                                      \
+                 : launch_attention<HD_, false>(q, k, v, out, ldq, ldk, ldv, ldo, cu_seqlens, nseq, max_seqlen,          \
+                                                total_tokens, scale, workspace, workspace_bytes, 0, 0, 0, 0, st);
   switch (D) {
-    case 96:
-      return launch_attention<96>(q, k, v, out, ldq, ldk, ldv, ldo, cu_seqlens, nseq, max_seqlen, total_tokens, scale,
-                                  workspace, workspace_bytes, st);
-    case 80:
-      return launch_attention<80>(q, k, v, out, ldq, ldk, ldv, ldo, cu_seqlens, nseq, max_seqlen, total_tokens, scale,
-                                  workspace, workspace_bytes, st);
+    I2R_ATT_CASE(96)
+    I2R_ATT_CASE(80)
     default:
       set_error("i2r_attention_varlen: head dim %d unsupported (80 or 96)", D);
       return I2R_E_UNSUPPORTED;

@@ -39,7 +39,8 @@ struct HaloProblem {
   void* y;
   int NB, H, W, C, Cout, Npad;
   int ntaps, halo;
-  int KCH, nkc;        // channels per A stage, A stages per tile
+  int KCH, nkc;        // channels per A stage, A stages per tile (split-operand mode: 3 * nkr)
+  int nkr, split;      // real 64-channel K-chunks of the input; split-operand mode (I2R_F_SPLIT)
   int kgp, nchp;       // packed-weight geometry: k-groups per packed chunk, packed chunks per tap
   int tiles_x, tiles_per_img, ntiles;
   int in_pix_stride, out_pix_stride, add_pix_stride;
@@ -86,7 +87,7 @@ __device__ __forceinline__ HaloProblem load_problem(const HaloProblem& s) {
   p.x = opaque(s.x); p.w = opaque(s.w); p.add0 = opaque(s.add0); p.add1 = opaque(s.add1); p.y = opaque(s.y);
   p.NB = opaque(s.NB); p.H = opaque(s.H); p.W = opaque(s.W); p.C = opaque(s.C); p.Cout = opaque(s.Cout);
   p.Npad = opaque(s.Npad); p.ntaps = opaque(s.ntaps); p.halo = opaque(s.halo); p.KCH = opaque(s.KCH);
-  p.nkc = opaque(s.nkc); p.kgp = opaque(s.kgp); p.nchp = opaque(s.nchp); p.tiles_x = opaque(s.tiles_x);
+  p.nkc = opaque(s.nkc); p.nkr = opaque(s.nkr); p.split = opaque(s.split); p.kgp = opaque(s.kgp); p.nchp = opaque(s.nchp); p.tiles_x = opaque(s.tiles_x);
   p.tiles_per_img = opaque(s.tiles_per_img); p.ntiles = opaque(s.ntiles);
   p.in_pix_stride = opaque(s.in_pix_stride); p.out_pix_stride = opaque(s.out_pix_stride);
   p.add_pix_stride = opaque(s.add_pix_stride); p.plane = opaque(s.plane); p.flags = opaque(s.flags);
@@ -216,7 +217,7 @@ __device__ __forceinline__ void mma_role(const HaloProblem& P, const int cta, co
       if (leader) trace_ev(tr, trcap, 1, tri, 11, t);
       const uint32_t a_lo = a_lo0 + (a_first + as) * a_stage16;
       const uint32_t b_lo_kc = w_lo0 + (kc + 1) * w_stage16;   // block 0 is the bias block
-      const int ksteps = min(4, (P.C - kc * 64) >> 4);   // K=16 steps holding real channels in this chunk
+      const int ksteps = min(4, (P.C - (kc % P.nkr) * 64) >> 4);   // K=16 steps holding real channels in this chunk
       const uint32_t acc_kc = 1u;
       if (resident) {
         // one straight-line burst of NTAPS x ksteps MMAs issued by the elected lane
@@ -309,6 +310,7 @@ __device__ __forceinline__ void epilogue_role(const EpiArgs E, const int cta, co
   const float lo = (E.flags & I2R_F_RELU) ? 0.0f : -3.0e38f;
   const float inv_tpi = 1.0f / static_cast<float>(E.tiles_per_img), inv_tx = 1.0f / static_cast<float>(E.tiles_x);
   const bool has0 = E.add0 != nullptr && !(dbg & 2), has1 = E.add1 != nullptr && !(dbg & 2);
+  const bool split = (E.flags & I2R_F_SPLIT) != 0;
   int acc = 0, tri = 0;
   uint32_t accph = 0;
   for (int t = cta; t < E.ntiles; t += E.cta_count) {
@@ -337,6 +339,16 @@ __device__ __forceinline__ void epilogue_role(const EpiArgs E, const int cta, co
           if (has1) r1[j] = __ldg(reinterpret_cast<const uint4*>(a1 + (c + j) * 8));
         }
       }
+      uint4 l0[4], l1[4];   // split-operand addends: lo halves at channel offset Cout
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        l0[j] = make_uint4(0, 0, 0, 0);
+        l1[j] = make_uint4(0, 0, 0, 0);
+        if (split && j < nc && valid && (c + j) * 8 < E.Cout) {
+          if (has0) l0[j] = __ldg(reinterpret_cast<const uint4*>(a0 + E.Cout + (c + j) * 8));
+          if (has1) l1[j] = __ldg(reinterpret_cast<const uint4*>(a1 + E.Cout + (c + j) * 8));
+        }
+      }
       if (!waited) {
         if (ew == 0 && lane == 0) trace_ev_dep(tr, trcap, 2, tri, 27, t, r0[0].x + static_cast<uint32_t>(p));
         mbar_wait(bar_accfull + 8 * acc, accph);
@@ -358,12 +370,15 @@ __device__ __forceinline__ void epilogue_role(const EpiArgs E, const int cta, co
             const int c0 = (c + j) * 8;
             const uint32_t q0[4] = {r0[j].x, r0[j].y, r0[j].z, r0[j].w};
             const uint32_t q1[4] = {r1[j].x, r1[j].y, r1[j].z, r1[j].w};
+            const uint32_t p0[4] = {l0[j].x, l0[j].y, l0[j].z, l0[j].w};
+            const uint32_t p1[4] = {l1[j].x, l1[j].y, l1[j].z, l1[j].w};
             float v[8];
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
               const float2 f0 = unpack_h2(q0[i]), f1 = unpack_h2(q1[i]);
-              v[2 * i] = fmaxf(__uint_as_float(av[j][2 * i]) + (f0.x + f1.x), lo);
-              v[2 * i + 1] = fmaxf(__uint_as_float(av[j][2 * i + 1]) + (f0.y + f1.y), lo);
+              const float2 g0 = unpack_h2(p0[i]), g1 = unpack_h2(p1[i]);
+              v[2 * i] = fmaxf(__uint_as_float(av[j][2 * i]) + ((f0.x + g0.x) + (f1.x + g1.x)), lo);
+              v[2 * i + 1] = fmaxf(__uint_as_float(av[j][2 * i + 1]) + ((f0.y + g0.y) + (f1.y + g1.y)), lo);
             }
             if (!(E.flags & (I2R_F_OUT_NCHW_F32 | I2R_F_OUT_F32))) {
               uint4 q;
@@ -371,10 +386,21 @@ __device__ __forceinline__ void epilogue_role(const EpiArgs E, const int cta, co
               q.y = pack_h2(v[2], v[3]);
               q.z = pack_h2(v[4], v[5]);
               q.w = pack_h2(v[6], v[7]);
+              __half* yq = reinterpret_cast<__half*>(E.y) + static_cast<int64_t>(p) * E.out_pix_stride + c0;
               if (!(dbg & 2))
-                *reinterpret_cast<uint4*>(reinterpret_cast<__half*>(E.y) + static_cast<int64_t>(p) * E.out_pix_stride + c0) = q;
+                *reinterpret_cast<uint4*>(yq) = q;
               else if (q.x == 0x12345678u)
                 *reinterpret_cast<uint4*>(E.y) = q;
+              if (split) {   // lo half = fp16(v - fp16(v)) at channel offset Cout
+                const uint32_t hq[4] = {q.x, q.y, q.z, q.w};
+                uint32_t lq[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                  const float2 f = unpack_h2(hq[i]);
+                  lq[i] = pack_h2(v[2 * i] - f.x, v[2 * i + 1] - f.y);
+                }
+                *reinterpret_cast<uint4*>(yq + E.Cout) = make_uint4(lq[0], lq[1], lq[2], lq[3]);
+              }
             } else if (E.flags & I2R_F_OUT_NCHW_F32) {
               float* Y = reinterpret_cast<float*>(E.y);
               const int nr = p / E.plane, rem = p - nr * E.plane;
@@ -582,7 +608,10 @@ __global__ void __launch_bounds__(T_THREADS, 1) conv_halo_kernel(const __grid_co
             mbar_arrive(bar_afull + 8 * s);
           } else {
             mbar_arrive_expect_tx(bar_afull + 8 * s, P.a_tx_bytes);
-            tma_load_4d(a_base + s * P.a_stage_bytes, amap, kc * 64, x0, y0, n, bar_afull + 8 * s);
+            // split-operand mode walks [x_hi | x_lo | x_hi]: hi at channel 0, lo at channel C of the source pixel
+            const int third = kc / P.nkr, kr = kc - third * P.nkr;
+            tma_load_4d(a_base + s * P.a_stage_bytes, amap, (third == 1 ? P.C : 0) + kr * 64, x0, y0, n,
+                        bar_afull + 8 * s);
           }
           trace_ev(tr, trace_cap, 0, tri, 2, t);
           if (++sr[ring] == a_half) {
@@ -651,7 +680,7 @@ __global__ void __launch_bounds__(T_THREADS, 1) conv_halo_kernel(const __grid_co
     const int ew = warp - 4;
     const int n8 = (P.Cout + 7) >> 3, half8 = (n8 + 1) >> 1;   // chunks holding real channels, split over the warp pair
     const int cb = (ew >> 2) ? half8 : 0, ce = (ew >> 2) ? n8 : half8;
-    if ((P.flags & (I2R_F_OUT_NCHW_F32 | I2R_F_OUT_F32)) || (P.Cout & 7) || dbg != 0 || ce == cb) {
+    if ((P.flags & (I2R_F_OUT_NCHW_F32 | I2R_F_OUT_F32 | I2R_F_SPLIT)) || (P.Cout & 7) || dbg != 0 || ce == cb) {
       epilogue_role<1>(E, cta, sbase, tmem_base, ncols, Npad, ew, warp & 3, lane, tr, trace_cap, dbg);
     } else if (P.add1 != nullptr) {
       epilogue_fast_dispatch<2>(E, cta, sbase, tmem_base, ncols, cb, ce, ew, warp & 3, lane, tr, trace_cap);
@@ -794,7 +823,9 @@ extern "C" int i2r_conv_halo(const i2r_conv_problem* probs, int nprob, void* str
     P.Cout = S.Cout;
     P.Npad = S.Npad;
     P.KCH = 64;
-    P.nkc = (S.Cin + 63) / 64;
+    P.split = (S.flags & I2R_F_SPLIT) ? 1 : 0;
+    P.nkr = (S.Cin + 63) / 64;
+    P.nkc = P.split ? 3 * P.nkr : P.nkr;
     P.kgp = 8;
     P.nchp = P.nkc;
     P.tiles_x = (P.W + T_TW - 1) / T_TW;
@@ -835,7 +866,7 @@ extern "C" int i2r_conv_halo(const i2r_conv_problem* probs, int nprob, void* str
     }
     P.a_stages = astg;
     {
-      int rc = encode_amap(&G.amap[i], S.x, P.NB, P.H, P.W, P.C, S.in_pix_stride, hw, hh);
+      int rc = encode_amap(&G.amap[i], S.x, P.NB, P.H, P.W, P.split ? 2 * P.C : P.C, S.in_pix_stride, hw, hh);
       if (rc) return rc;
     }
     P.w_off = T_A_OFF + static_cast<uint32_t>(astg) * P.a_stage_bytes;
@@ -846,7 +877,7 @@ extern "C" int i2r_conv_halo(const i2r_conv_problem* probs, int nprob, void* str
       // operands takes max(32 + N/4, N/2) cycles; streamed weights arrive at ~45 B/cycle/SM; the epilogue warps need
       // ~600 + 10 cycles per output channel.
       const double n = S.Npad;
-      const double mma = static_cast<double>(S.ntaps) * (S.Cin / 16) * ((32.0 + n / 4) > n / 2 ? (32.0 + n / 4) : n / 2) + 400.0;
+      const double mma = static_cast<double>(S.ntaps) * (S.Cin / 16) * (P.split ? 3 : 1) * ((32.0 + n / 4) > n / 2 ? (32.0 + n / 4) : n / 2) + 400.0;
       const double stream = P.w_resident ? 0.0 : P.w_total_bytes / 45.0;
       const double epi = 600.0 + 10.0 * n;
       cost[i] = mma > stream ? mma : stream;

@@ -55,7 +55,11 @@ __device__ __forceinline__ void run_tile(const i2r_conv_problem& P, const int ti
   const int st_bytes = a_bytes + b_bytes;
   const uint32_t stages0 = sbase + SMEM_HDR;
 
-  const int nchunks = (P.Cin + 63) >> 6;
+  // split-operand mode: K runs over [x_hi | x_lo | x_hi] (three passes over the nkr real K-chunks; the input tensor
+  // stores hi at channel 0 and lo at channel Cin) against weights packed as [W_hi | W_hi | W_lo]
+  const bool split = (P.flags & I2R_F_SPLIT) != 0;
+  const int nkr = (P.Cin + 63) >> 6;
+  const int nchunks = split ? 3 * nkr : nkr;
   const int niter = P.ntaps * nchunks;
   const int M = P.NB * P.OH * P.OW;
 
@@ -128,7 +132,9 @@ __device__ __forceinline__ void run_tile(const i2r_conv_problem& P, const int ti
       const int dy = P.dy[t], dx = P.dx[t];
       const int tapoff = (dy * IWs + dx) * P.in_pix_stride;   // element offset of this tap (in_shift == 0)
       for (int c = 0; c < nchunks; ++c, ++it) {
-        const int kgc = min(8, (P.Cin - c * 64) >> 3);   // real 16-byte chunks per row in this K-chunk
+        const int third = c / nkr, kr = c - third * nkr;
+        const int coff = (third == 1 ? P.Cin : 0) + kr * 64;   // channel offset of this K-chunk in the source pixel
+        const int kgc = min(8, (P.Cin - kr * 64) >> 3);   // real 16-byte chunks per row in this K-chunk
         const int s = it % STAGES;
         const uint32_t ph = (it / STAGES) & 1;
         mbar_wait(bar_empty + 8 * s, ph ^ 1);
@@ -139,7 +145,7 @@ __device__ __forceinline__ void run_tile(const i2r_conv_problem& P, const int ti
         }
         if (sh == 0) {
           // fast path: source address = per-row base + per-tap offset (+ K-chunk), bounds from two compares
-          const __half* xc = X + tapoff + c * 64;
+          const __half* xc = X + tapoff + coff;
 #pragma unroll
           for (int i = 0; i < KG; ++i) {
             if (r_g[i] < kgc) {
@@ -160,7 +166,7 @@ __device__ __forceinline__ void run_tile(const i2r_conv_problem& P, const int ti
               const __half* src = X;
               if (ok) {
                 const int64_t pix = static_cast<int64_t>(r_nb[i] + (iy >> sh)) * IWs + (ix >> sh);
-                src = X + pix * P.in_pix_stride + c * 64 + r_g[i] * 8;
+                src = X + pix * P.in_pix_stride + coff + r_g[i] * 8;
               }
               cp_async16(a_s + r_dst[i], src, ok ? 16u : 0u);
             }
@@ -219,11 +225,13 @@ __device__ __forceinline__ void run_tile(const i2r_conv_problem& P, const int ti
 #pragma unroll
       for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]) * s_scale[c0 + i] + s_bias[c0 + i];
       if (valid) {
+        for (int part = 0; part < (split ? 2 : 1); ++part) {   // split addends: hi half, then lo half at +Cout
+        const int po = part * Cout;
         if (a0 != nullptr) {
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
             if (c0 + h * 8 < Cout) {
-              const uint4 q = *reinterpret_cast<const uint4*>(a0 + c0 + h * 8);
+              const uint4 q = *reinterpret_cast<const uint4*>(a0 + po + c0 + h * 8);
               const uint32_t w4[4] = {q.x, q.y, q.z, q.w};
 #pragma unroll
               for (int i = 0; i < 4; ++i) {
@@ -238,7 +246,7 @@ __device__ __forceinline__ void run_tile(const i2r_conv_problem& P, const int ti
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
             if (c0 + h * 8 < Cout) {
-              const uint4 q = *reinterpret_cast<const uint4*>(a1 + c0 + h * 8);
+              const uint4 q = *reinterpret_cast<const uint4*>(a1 + po + c0 + h * 8);
               const uint32_t w4[4] = {q.x, q.y, q.z, q.w};
 #pragma unroll
               for (int i = 0; i < 4; ++i) {
@@ -248,6 +256,7 @@ __device__ __forceinline__ void run_tile(const i2r_conv_problem& P, const int ti
               }
             }
           }
+        }
         }
         if (relu) {
 #pragma unroll
@@ -276,6 +285,16 @@ __device__ __forceinline__ void run_tile(const i2r_conv_problem& P, const int ti
               q.z = pack_h2(v[h * 8 + 4], v[h * 8 + 5]);
               q.w = pack_h2(v[h * 8 + 6], v[h * 8 + 7]);
               *reinterpret_cast<uint4*>(Y + h * 8) = q;
+              if (split) {   // lo half = fp16(v - fp16(v)) at channel offset Cout
+                const uint32_t hq[4] = {q.x, q.y, q.z, q.w};
+                uint32_t lq[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                  const float2 f = unpack_h2(hq[i]);
+                  lq[i] = pack_h2(v[h * 8 + 2 * i] - f.x, v[h * 8 + 2 * i + 1] - f.y);
+                }
+                *reinterpret_cast<uint4*>(Y + Cout + h * 8) = make_uint4(lq[0], lq[1], lq[2], lq[3]);
+              }
             }
           }
         }
@@ -296,7 +315,7 @@ __device__ __forceinline__ void run_tile(const i2r_conv_problem& P, const int ti
       mbar_wait(bar_full + 8 * s, ph);
       tc_fence_after();
       const uint32_t a_lo = a_lo0 + s * st16, b_lo = b_lo0 + s * st16;
-      const int ksteps = min(4, (P.Cin - (it % nchunks) * 64) >> 4);
+      const int ksteps = min(4, (P.Cin - ((it % nchunks) % nkr) * 64) >> 4);
       if (leader) {
         switch (ksteps) {
           case 4: issue_ksteps<4>(tmem_base, a_lo, a_hi, b_lo, b_hi, idesc, accum); break;
@@ -348,7 +367,9 @@ __global__ void __launch_bounds__(128) igemm_check_kernel(const __grid_constant_
   const int oyf = oy * P.out_mul + P.out_offy, oxf = ox * P.out_mul + P.out_offx;
   const int sh = P.in_shift;
   const int IHs = P.IH >> sh, IWs = P.IW >> sh;
-  const int nchunks = (P.Cin + 63) >> 6;
+  const bool split = (P.flags & I2R_F_SPLIT) != 0;
+  const int nkr = (P.Cin + 63) >> 6;
+  const int nchunks = split ? 3 * nkr : nkr;
   const __half* X = reinterpret_cast<const __half*>(P.x);
   const __half* Wp = reinterpret_cast<const __half*>(P.w);
   const int64_t opix = (static_cast<int64_t>(n) * P.OHf + oyf) * P.OWf + oxf;
@@ -364,6 +385,11 @@ __global__ void __launch_bounds__(128) igemm_check_kernel(const __grid_constant_
         const int ch = c >> 6, g = (c & 63) >> 3, e = c & 7;
         const int64_t wi = (static_cast<int64_t>(t * nchunks + ch) * P.Npad + co) * 64 + ((g ^ (co & 7)) << 3) + e;
         acc += __half2float(xp[c]) * __half2float(Wp[wi]);
+        if (split) {   // + x_lo * W_hi (second third of K) + x_hi * W_lo (last third)
+          const int64_t step = static_cast<int64_t>(nkr) * P.Npad * 64;
+          acc += __half2float(xp[P.Cin + c]) * __half2float(Wp[wi + step]);
+          acc += __half2float(xp[c]) * __half2float(Wp[wi + 2 * step]);
+        }
       }
     }
     float v = acc * P.scale[co] + P.bias[co];
@@ -371,11 +397,13 @@ __global__ void __launch_bounds__(128) igemm_check_kernel(const __grid_constant_
       const int s0 = P.add0_shift;
       const int64_t ap = (static_cast<int64_t>(n) * (P.OHf >> s0) + (oyf >> s0)) * (P.OWf >> s0) + (oxf >> s0);
       v += __half2float(reinterpret_cast<const __half*>(P.add0)[ap * P.add_pix_stride + co]);
+      if (split) v += __half2float(reinterpret_cast<const __half*>(P.add0)[ap * P.add_pix_stride + P.Cout + co]);
     }
     if (P.add1) {
       const int s1 = P.add1_shift;
       const int64_t ap = (static_cast<int64_t>(n) * (P.OHf >> s1) + (oyf >> s1)) * (P.OWf >> s1) + (oxf >> s1);
       v += __half2float(reinterpret_cast<const __half*>(P.add1)[ap * P.add_pix_stride + co]);
+      if (split) v += __half2float(reinterpret_cast<const __half*>(P.add1)[ap * P.add_pix_stride + P.Cout + co]);
     }
     if (P.flags & I2R_F_RELU) v = fmaxf(v, 0.f);
     if (P.flags & I2R_F_OUT_NCHW_F32) {
@@ -385,7 +413,9 @@ __global__ void __launch_bounds__(128) igemm_check_kernel(const __grid_constant_
     } else if (P.flags & I2R_F_OUT_F32) {
       reinterpret_cast<float*>(P.y)[opix * P.out_pix_stride + co] = v;
     } else {
-      reinterpret_cast<__half*>(P.y)[opix * P.out_pix_stride + co] = __float2half_rn(v);
+      const __half hv = __float2half_rn(v);
+      reinterpret_cast<__half*>(P.y)[opix * P.out_pix_stride + co] = hv;
+      if (split) reinterpret_cast<__half*>(P.y)[opix * P.out_pix_stride + P.Cout + co] = __float2half_rn(v - __half2float(hv));
     }
   }
 }

@@ -25,6 +25,35 @@ int check_launch(const char* what) {
   return 0;
 }
 
+// ---- split-operand ("pair") tensors: a row of 2*C fp16 = [hi(C) | lo(C)], value = hi + lo (include/i2r.h, I2R_F_SPLIT)
+__device__ __forceinline__ void load8(const __half* p, float (&v)[8]) {
+  const uint4 q = *reinterpret_cast<const uint4*>(p);
+  const uint32_t w4[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 f = unpack_h2(w4[i]);
+    v[2 * i] = f.x;
+    v[2 * i + 1] = f.y;
+  }
+}
+__device__ __forceinline__ void load8_pair(const __half* row, int C, int c, float (&v)[8]) {
+  float lo[8];
+  load8(row + c, v);
+  load8(row + C + c, lo);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] += lo[i];
+}
+__device__ __forceinline__ void store8(__half* p, const float (&v)[8]) {
+  *reinterpret_cast<uint4*>(p) = make_uint4(pack_h2(v[0], v[1]), pack_h2(v[2], v[3]), pack_h2(v[4], v[5]), pack_h2(v[6], v[7]));
+}
+__device__ __forceinline__ void store8_pair(__half* row, int C, int c, const float (&v)[8]) {
+  float lo[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) lo[i] = v[i] - __half2float(__float2half_rn(v[i]));
+  store8(row + c, v);
+  store8(row + C + c, lo);
+}
+
 // ------------------------------------------------------------------------------------------------
 // 3x3 stride-2 pad-1 convolution with Cin in {1,3} and 64 output channels (stem / mask embedding).
 // CTA = 8 x 32 output pixels: the (17 x 65 x CIN) fp32 input patch is staged in shared memory with coalesced
@@ -36,7 +65,7 @@ template <int CIN>
 __global__ void __launch_bounds__(256) stem_conv_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                         const float* __restrict__ scale,
                                                         const float* __restrict__ bias, __half* __restrict__ y,
-                                                        int NB, int H, int W) {
+                                                        int NB, int H, int W, int split) {
   constexpr int K = CIN * 9;
   __shared__ __align__(16) float sw[K * 64];
   __shared__ __align__(16) float ssc[64];
@@ -88,16 +117,17 @@ __global__ void __launch_bounds__(256) stem_conv_kernel(const float* __restrict_
     }
   }
   if (oy < OH && ox < OW) {
-    uint4* dst = reinterpret_cast<uint4*>(y + ((static_cast<int64_t>(n) * OH + oy) * OW + ox) * 64);
+    __half* row = y + ((static_cast<int64_t>(n) * OH + oy) * OW + ox) * (split ? 128 : 64);
 #pragma unroll
     for (int q = 0; q < 8; ++q) {
-      uint32_t o[4];
+      float o[8];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int c = q * 8 + 2 * i;
-        o[i] = pack_h2(fmaxf(acc[c] * ssc[c] + sbi[c], 0.f), fmaxf(acc[c + 1] * ssc[c + 1] + sbi[c + 1], 0.f));
+      for (int i = 0; i < 8; ++i) o[i] = fmaxf(acc[q * 8 + i] * ssc[q * 8 + i] + sbi[q * 8 + i], 0.f);
+      if (split) {
+        store8_pair(row, 64, q * 8, o);
+      } else {
+        store8(row + q * 8, o);
       }
-      dst[q] = make_uint4(o[0], o[1], o[2], o[3]);
     }
   }
 }
@@ -137,13 +167,45 @@ __global__ void __launch_bounds__(256) maxpool3x3s2_kernel(const __half* __restr
   }
 }
 
+// pair tensors: max over the VALUES hi + lo, re-split on store
+__global__ void __launch_bounds__(256) maxpool3x3s2_pair_kernel(const __half* __restrict__ x, __half* __restrict__ y,
+                                                                int NB, int H, int W, int C) {
+  const int OH = (H + 1) >> 1, OW = (W + 1) >> 1;
+  const int cv = C >> 3;
+  const int64_t total = static_cast<int64_t>(NB) * OH * OW * cv;
+  for (int64_t idx = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int c8 = static_cast<int>(idx % cv);
+    const int64_t p = idx / cv;
+    const int ox = static_cast<int>(p % OW);
+    const int oy = static_cast<int>((p / OW) % OH);
+    const int n = static_cast<int>(p / (static_cast<int64_t>(OW) * OH));
+    float m[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) m[i] = -3.0e38f;
+    for (int ky = 0; ky < 3; ++ky) {
+      const int iy = oy * 2 - 1 + ky;
+      if (iy < 0 || iy >= H) continue;
+      for (int kx = 0; kx < 3; ++kx) {
+        const int ix = ox * 2 - 1 + kx;
+        if (ix < 0 || ix >= W) continue;
+        float v[8];
+        load8_pair(x + ((static_cast<int64_t>(n) * H + iy) * W + ix) * 2 * C, C, c8 * 8, v);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) m[i] = fmaxf(m[i], v[i]);
+      }
+    }
+    store8_pair(y + p * 2 * C, C, c8 * 8, m);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // LayerNorm: one warp per row, 8 channels (16 B) per lane per pass, fp32 statistics (two-pass in
 // registers), optional y2 = y + pos.
 __global__ void __launch_bounds__(256) layernorm_kernel(const __half* __restrict__ x, const float* __restrict__ gamma,
                                                         const float* __restrict__ beta,
                                                         const __half* __restrict__ pos, __half* __restrict__ y,
-                                                        __half* __restrict__ y2, int rows, int C, float eps) {
+                                                        __half* __restrict__ y2, int rows, int C, float eps, int split) {
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (warp >= rows) return;
@@ -152,14 +214,12 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const __half* __restrict
   float v[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) v[i] = 0.f;
+  const int64_t ld = split ? 2 * C : C;   // pair tensors: rows of [hi(C) | lo(C)]
   if (act) {
-    const uint4 q = *reinterpret_cast<const uint4*>(x + static_cast<int64_t>(warp) * C + c);
-    const uint32_t w4[4] = {q.x, q.y, q.z, q.w};
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const float2 f = unpack_h2(w4[i]);
-      v[2 * i] = f.x;
-      v[2 * i + 1] = f.y;
+    if (split) {
+      load8_pair(x + warp * ld, C, c, v);
+    } else {
+      load8(x + warp * ld + c, v);
     }
   }
   float s = 0.f;
@@ -183,6 +243,17 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const __half* __restrict
     float o8[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) o8[i] = (v[i] - mean) * rstd * gamma[c + i] + beta[c + i];
+    if (split) {
+      store8_pair(y + warp * ld, C, c, o8);
+      if (y2 != nullptr) {
+        float pv[8];
+        load8_pair(pos + warp * ld, C, c, pv);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) pv[i] += o8[i];
+        store8_pair(y2 + warp * ld, C, c, pv);
+      }
+      return;
+    }
     uint4 q;
     q.x = pack_h2(o8[0], o8[1]);
     q.y = pack_h2(o8[2], o8[3]);
@@ -214,6 +285,23 @@ __global__ void __launch_bounds__(256) add_f16_kernel(const uint4* __restrict__ 
 #pragma unroll
     for (int k = 0; k < 4; ++k) r[k] = __hadd2(ha[k], hb[k]);
     y[i] = *reinterpret_cast<uint4*>(r);
+  }
+}
+
+// pair tensors: rows of [hi(C) | lo(C)]; y = (a_hi + a_lo) + (b_hi + b_lo), re-split
+__global__ void __launch_bounds__(256) add_pair_kernel(const __half* __restrict__ a, const __half* __restrict__ b,
+                                                       __half* __restrict__ y, int64_t rows, int C) {
+  const int cv = C >> 3;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < rows * cv;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t r = i / cv;
+    const int c = static_cast<int>(i - r * cv) * 8;
+    float va[8], vb[8];
+    load8_pair(a + r * 2 * C, C, c, va);
+    load8_pair(b + r * 2 * C, C, c, vb);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) va[k] += vb[k];
+    store8_pair(y + r * 2 * C, C, c, va);
   }
 }
 
@@ -254,7 +342,7 @@ extern "C" int i2r_sm_count(int dev) {
 }
 
 extern "C" int i2r_stem_conv3x3s2(const float* x, const float* w, const float* scale, const float* bias, void* y,
-                                  int NB, int Cin, int H, int W, int Cout, void* stream) {
+                                  int NB, int Cin, int H, int W, int Cout, int split, void* stream) {
   if (!x || !w || !scale || !bias || !y || NB <= 0 || (H & 1) || (W & 1) || Cout != 64) {
     set_error("i2r_stem_conv3x3s2: bad arguments (Cin=%d H=%d W=%d Cout=%d; Cout must be 64)", Cin, H, W, Cout);
     return I2R_E_BADARG;
@@ -262,9 +350,9 @@ extern "C" int i2r_stem_conv3x3s2(const float* x, const float* w, const float* s
   const dim3 grid((W / 2 + STEM_TW - 1) / STEM_TW, (H / 2 + STEM_TH - 1) / STEM_TH, NB);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (Cin == 3) {
-    stem_conv_kernel<3><<<grid, 256, 0, st>>>(x, w, scale, bias, static_cast<__half*>(y), NB, H, W);
+    stem_conv_kernel<3><<<grid, 256, 0, st>>>(x, w, scale, bias, static_cast<__half*>(y), NB, H, W, split);
   } else if (Cin == 1) {
-    stem_conv_kernel<1><<<grid, 256, 0, st>>>(x, w, scale, bias, static_cast<__half*>(y), NB, H, W);
+    stem_conv_kernel<1><<<grid, 256, 0, st>>>(x, w, scale, bias, static_cast<__half*>(y), NB, H, W, split);
   } else {
     set_error("i2r_stem_conv3x3s2: Cin=%d unsupported (1 or 3)", Cin);
     return I2R_E_UNSUPPORTED;
@@ -272,19 +360,24 @@ extern "C" int i2r_stem_conv3x3s2(const float* x, const float* w, const float* s
   return check_launch("stem_conv_kernel");
 }
 
-extern "C" int i2r_maxpool3x3s2(const void* x, void* y, int NB, int H, int W, int C, void* stream) {
+extern "C" int i2r_maxpool3x3s2(const void* x, void* y, int NB, int H, int W, int C, int split, void* stream) {
   if (!x || !y || NB <= 0 || H <= 0 || W <= 0 || C % 8 != 0) {
     set_error("i2r_maxpool3x3s2: bad arguments");
     return I2R_E_BADARG;
   }
   const int64_t items = static_cast<int64_t>(NB) * ((H + 1) / 2) * ((W + 1) / 2) * (C / 8);
-  maxpool3x3s2_kernel<<<grid_for(items, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      static_cast<const __half*>(x), static_cast<__half*>(y), NB, H, W, C);
+  if (split) {
+    maxpool3x3s2_pair_kernel<<<grid_for(items, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const __half*>(x), static_cast<__half*>(y), NB, H, W, C);
+  } else {
+    maxpool3x3s2_kernel<<<grid_for(items, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const __half*>(x), static_cast<__half*>(y), NB, H, W, C);
+  }
   return check_launch("maxpool3x3s2_kernel");
 }
 
 extern "C" int i2r_layernorm(const void* x, const float* gamma, const float* beta, const void* pos, void* y,
-                             void* y2, int rows, int C, float eps, void* stream) {
+                             void* y2, int rows, int C, float eps, int split, void* stream) {
   if (!x || !gamma || !beta || !y || rows <= 0 || C % 8 != 0 || C > 256 || (y2 && !pos)) {
     set_error("i2r_layernorm: bad arguments (rows=%d C=%d)", rows, C);
     return I2R_E_BADARG;
@@ -292,14 +385,23 @@ extern "C" int i2r_layernorm(const void* x, const float* gamma, const float* bet
   const int wpb = 8;
   layernorm_kernel<<<(rows + wpb - 1) / wpb, wpb * 32, 0, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const __half*>(x), gamma, beta, static_cast<const __half*>(pos), static_cast<__half*>(y),
-      static_cast<__half*>(y2), rows, C, eps);
+      static_cast<__half*>(y2), rows, C, eps, split);
   return check_launch("layernorm_kernel");
 }
 
-extern "C" int i2r_add_f16(const void* a, const void* b, void* y, int64_t n, void* stream) {
+extern "C" int i2r_add_f16(const void* a, const void* b, void* y, int64_t n, int split_c, void* stream) {
   if (!a || !b || !y || n <= 0 || n % 8 != 0) {
     set_error("i2r_add_f16: bad arguments");
     return I2R_E_BADARG;
+  }
+  if (split_c > 0) {
+    if (split_c % 8 != 0 || n % (2 * split_c) != 0) {
+      set_error("i2r_add_f16: pair tensors need C %% 8 == 0 and n a multiple of 2*C");
+      return I2R_E_BADARG;
+    }
+    add_pair_kernel<<<grid_for(n / 16, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const __half*>(a), static_cast<const __half*>(b), static_cast<__half*>(y), n / (2 * split_c), split_c);
+    return check_launch("add_pair_kernel");
   }
   add_f16_kernel<<<grid_for(n / 8, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const uint4*>(a), static_cast<const uint4*>(b), static_cast<uint4*>(y), n / 8);

@@ -11,6 +11,7 @@ I2R_MAX_GROUP = 6
 F_RELU = 1
 F_OUT_NCHW_F32 = 2
 F_OUT_F32 = 4
+F_SPLIT = 8
 
 EXPORTS = [
     "i2r_version", "i2r_last_error", "i2r_device_check", "i2r_sm_count", "i2r_conv_igemm", "i2r_conv_halo", "i2r_conv_halo_supported", "i2r_debug_trace", "i2r_debug_flags",
@@ -66,20 +67,21 @@ def load():
         lib.i2r_conv_halo_supported.argtypes = [ctypes.POINTER(ConvProblem)]
         lib.i2r_debug_trace.argtypes = [vp, i32, i32]
         lib.i2r_debug_flags.argtypes = [i32]
-        lib.i2r_stem_conv3x3s2.argtypes = [vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp]
-        lib.i2r_maxpool3x3s2.argtypes = [vp, vp, i32, i32, i32, i32, vp]
-        lib.i2r_attention_varlen.argtypes = [vp, vp, vp, vp, i32, i32, i32, i32, i32, vp, i32, i32, i32, f32, vp, i64, vp]
+        lib.i2r_stem_conv3x3s2.argtypes = [vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, vp]
+        lib.i2r_maxpool3x3s2.argtypes = [vp, vp, i32, i32, i32, i32, i32, vp]
+        lib.i2r_attention_varlen.argtypes = [vp, vp, vp, vp, i32, i32, i32, i32, i32, vp, i32, i32, i32, f32, vp, i64,
+                                             i32, i32, i32, i32, i32, vp]
         lib.i2r_attention_workspace_bytes.argtypes = [i32, i32, i32, i32]
         lib.i2r_attention_workspace_bytes.restype = i64
-        lib.i2r_layernorm.argtypes = [vp, vp, vp, vp, vp, vp, i32, i32, f32, vp]
-        lib.i2r_add_f16.argtypes = [vp, vp, vp, i64, vp]
+        lib.i2r_layernorm.argtypes = [vp, vp, vp, vp, vp, vp, i32, i32, f32, i32, vp]
+        lib.i2r_add_f16.argtypes = [vp, vp, vp, i64, i32, vp]
         for name in EXPORTS:
             getattr(lib, name)  # raises AttributeError if the symbol is missing
         if lib.i2r_sizeof_conv_problem() != ctypes.sizeof(ConvProblem):
             raise I2RError("i2r_conv_problem layout mismatch: C %d vs ctypes %d" % (
                 lib.i2r_sizeof_conv_problem(), ctypes.sizeof(ConvProblem)))
-        if lib.i2r_version() != 2:
-            raise I2RError("libi2r_sm100.so ABI version %d, binding expects 2" % lib.i2r_version())
+        if lib.i2r_version() != 3:
+            raise I2RError("libi2r_sm100.so ABI version %d, binding expects 3" % lib.i2r_version())
         _lib = lib
         return lib
 

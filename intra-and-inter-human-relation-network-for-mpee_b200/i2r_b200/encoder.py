@@ -48,15 +48,23 @@ class EncoderProgram:
         self.scale = 1.0 / math.sqrt(d_model // nhead)
 
     def run(self, r, src, pos, cu_seqlens, max_seqlen):
+        """src / pos: [T, d] fp16, or split tensors [T, 2d] (hi | lo) when the layers were built in split-operand mode."""
         d = self.d
+        split = self.layers[0].qk.split
         sp = r.add(src, pos) if pos is not None else src
         for li, L in enumerate(self.layers):
             pq, _ = r.linear_problem(L.qk, sp)
             pv, _ = r.linear_problem(L.v, src)
             r.launch([pq, pv])
-            qk = pq._keep[4].view(-1, 2 * d)
-            v = pv._keep[4].view(-1, d)
-            a = r.attention(qk[:, :d], qk[:, d:], v, cu_seqlens, max_seqlen, self.scale)
+            if split:     # qk: [T, (q_hi k_hi | q_lo k_lo)], v: [T, (v_hi | v_lo)]
+                qk = pq._keep[4].view(-1, 4 * d)
+                v = pv._keep[4].view(-1, 2 * d)
+                a = r.attention(qk[:, :d], qk[:, d:2 * d], v[:, :d], cu_seqlens, max_seqlen, self.scale,
+                                lo=(2 * d, 2 * d, d))
+            else:
+                qk = pq._keep[4].view(-1, 2 * d)
+                v = pv._keep[4].view(-1, d)
+                a = r.attention(qk[:, :d], qk[:, d:], v, cu_seqlens, max_seqlen, self.scale)
             x1 = r.linear(L.out, a, add0=src)
             s1, _ = r.layernorm(x1, L.n1[0], L.n1[1])
             h = r.linear(L.ff1, s1)

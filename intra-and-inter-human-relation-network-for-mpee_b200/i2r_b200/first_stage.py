@@ -10,6 +10,8 @@ import torch
 
 from .encoder import EncoderProgram
 from .hrnet_w48 import BackboneProgram, conv_bn_layer
+from .ops import _SPLIT_DEFAULT
+from .packing import split_pair
 
 
 class FirstStageProgram:
@@ -23,7 +25,12 @@ class FirstStageProgram:
             raise NotImplementedError("FINAL_CONV_KERNEL=3")
         self.head = conv_bn_layer(sd, "final_layer", None, device=device)
         pe = sd.get("pos_embedding")
-        self.pos_table = None if pe is None else pe.float().reshape(pe.shape[0], -1).to(device).half()
+        self.split = _SPLIT_DEFAULT[0]
+        if pe is None:
+            self.pos_table = None
+        else:
+            pe = pe.float().reshape(pe.shape[0], -1)
+            self.pos_table = (split_pair(pe) if self.split else pe.half()).to(device)
         self.device = device
         self._pos, self._cu = {}, {}
 
@@ -37,7 +44,7 @@ class FirstStageProgram:
         """x fp32 NCHW [S,3,H,W] -> (feat fp16 NHWC [S,h,w,d], heatmaps fp32 NCHW [S,K,h,w])."""
         feats = self.backbone.run(r, x)
         f = r.conv(self.reduce, feats[self.res_layer])
-        s, h, w, d = f.shape
+        s, h, w, d = f.shape      # d = 2 * d_model in split-operand mode (hi | lo)
         if self.pos_table is not None and self.pos_table.shape[0] != h * w:
             raise ValueError("pos_embedding holds %d tokens, the feature map %d" % (self.pos_table.shape[0], h * w))
         pos, cu = self._tiled(s, h * w)

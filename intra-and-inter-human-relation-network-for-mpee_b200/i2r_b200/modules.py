@@ -45,7 +45,8 @@ class DeconvProgram:
 
     def run(self, r, x):
         nb, h, w, _ = x.shape
-        out = torch.empty((nb, 2 * h, 2 * w, self.cout), dtype=torch.float16, device=x.device)
+        cw = self.cout * (2 if self.phases[0][1].split else 1)      # split-operand tensors carry (hi | lo)
+        out = torch.empty((nb, 2 * h, 2 * w, cw), dtype=torch.float16, device=x.device)
         r.conv_group([(L, x, dict(out=out, out_hw=(2 * h, 2 * w), out_mul=2, out_off=off)) for off, L in self.phases])
         return out
 

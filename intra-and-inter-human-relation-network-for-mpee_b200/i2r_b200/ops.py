@@ -5,14 +5,31 @@ import ctypes
 import torch
 
 from . import capi
-from .packing import ceil_to, pad_vec, pick_kc, pack_taps, pack_folded
+import contextlib
+
+from .packing import ceil_to, pad_vec, pick_kc, pack_taps, pack_folded, split_virtual_taps
+
+
+_SPLIT_DEFAULT = [False]
+
+
+@contextlib.contextmanager
+def split_precision(enabled=True):
+    """Layers constructed inside this context use the split-operand mode (see packing.split_virtual_taps)."""
+    old = _SPLIT_DEFAULT[0]
+    _SPLIT_DEFAULT[0] = bool(enabled)
+    try:
+        yield
+    finally:
+        _SPLIT_DEFAULT[0] = old
 
 
 class ConvLayer:
     """Device-resident parameters of one implicit-GEMM problem (weights packed, BN folded)."""
 
-    def __init__(self, mats, dys, dxs, scale, bias, stride=1, relu=False, device="cuda"):
+    def __init__(self, mats, dys, dxs, scale, bias, stride=1, relu=False, device="cuda", split=None):
         cout, cin = mats[0].shape
+        self.split = _SPLIT_DEFAULT[0] if split is None else bool(split)
         self.cin, self.cout = cin, cout
         self.kc = pick_kc(cin)
         self.npad = ceil_to(cout, 16)
@@ -21,11 +38,20 @@ class ConvLayer:
             raise ValueError("too many taps")
         self.dy, self.dx = list(dys), list(dxs)
         self.stride, self.relu = stride, relu
-        self.w = pack_taps(mats, self.kc).to(device)
+        if self.split:
+            sc = scale.float()[:cout].reshape(cout, 1)
+            self.w = pack_taps(split_virtual_taps(mats), self.kc).to(device)
+            folded = split_virtual_taps([m.float() * sc for m in mats])
+        else:
+            self.w = pack_taps(mats, self.kc).to(device)
+            folded = None
         self.scale = pad_vec(scale, self.npad, 1.0).to(device)
         self.bias = pad_vec(bias, self.npad, 0.0).to(device)
         # operand image of the persistent halo kernel (scale folded into the weights, bias block first)
-        self.w_folded = pack_folded(mats, scale, bias, self.kc).to(device)
+        if folded is not None:
+            self.w_folded = pack_folded(folded, torch.ones(cout), bias, self.kc).to(device)
+        else:
+            self.w_folded = pack_folded(mats, scale, bias, self.kc).to(device)
         self.w_copies = 1
         self._halves = None
 
@@ -78,6 +104,7 @@ class Runner:
         self.impl = impl
         self.use_tma = impl == 0   # route eligible problems to the persistent TMA kernel
         self.launches = 0
+        self.split = False     # split-operand activations (fp16 hi | lo pairs) for the non-GEMM kernels
         self.timing = None     # bench.py: list of (start_event, end_event, algorithmic_flops, nprob) per igemm launch
 
     # ------------------------------------------------------------------ implicit GEMM
@@ -85,7 +112,9 @@ class Runner:
                 relu=None, out_mode="nhwc16", out_hw=None, out_mul=1, out_off=(0, 0), ohow=None):
         """Build one problem.  x: fp16 [NB, Hs, Ws, C>=Cin] (channel stride 1).  Returns (ConvProblem, out)."""
         assert x.dtype == torch.float16 and x.dim() == 4 and x.stride(3) == 1
-        nb, hs, ws, _ = x.shape
+        nb, hs, ws, cphys = x.shape
+        assert cphys >= (2 * L.cin if L.split else L.cin), "input tensor has too few channels for this layer"
+        cw = 2 * L.cout if L.split else L.cout     # channels of an fp16 output / addend tensor (split: hi | lo)
         pix = x.stride(2)
         assert x.stride(1) == ws * pix and (nb == 1 or x.stride(0) == hs * ws * pix), "x must be pixel-contiguous"
         ih, iw = hs << in_shift, ws << in_shift
@@ -102,7 +131,7 @@ class Runner:
             flags |= capi.F_RELU
         if out is None:
             if out_mode == "nhwc16":
-                out = torch.empty((nb, ohf, owf, L.cout), dtype=torch.float16, device=x.device)
+                out = torch.empty((nb, ohf, owf, cw), dtype=torch.float16, device=x.device)
             elif out_mode == "nchw32":
                 out = torch.empty((nb, L.cout, ohf, owf), dtype=torch.float32, device=x.device)
             elif out_mode == "nhwc32":
@@ -122,10 +151,10 @@ class Runner:
         p.x, p.w, p.scale, p.bias = x.data_ptr(), L.w.data_ptr(), L.scale.data_ptr(), L.bias.data_ptr()
         p.add0 = add0.data_ptr() if add0 is not None else None
         p.add1 = add1.data_ptr() if add1 is not None else None
-        add_pix = L.cout
+        add_pix = cw
         for a in (add0, add1):
             if a is not None:
-                assert a.dtype == torch.float16 and a.dim() == 4 and a.stride(3) == 1 and a.shape[-1] == L.cout
+                assert a.dtype == torch.float16 and a.dim() == 4 and a.stride(3) == 1 and a.shape[-1] == cw
                 assert a.stride(1) == a.shape[2] * a.stride(2)
                 add_pix = a.stride(2)
         if add0 is not None and add1 is not None:
@@ -142,6 +171,8 @@ class Runner:
         p.ntaps = L.ntaps
         for t in range(L.ntaps):
             p.dy[t], p.dx[t] = L.dy[t], L.dx[t]
+        if L.split:
+            flags |= capi.F_SPLIT
         p.flags = flags
         p.w_folded = L.w_folded.data_ptr()
         p.w_folded_copies = L.w_copies
@@ -157,7 +188,8 @@ class Runner:
         split = (self.use_tma and std and L.stride == 1 and kw.get("in_shift", 0) == 0 and
                  kw.get("out_mul", 1) == 1 and kw.get("out_mode", "nhwc16") == "nhwc16" and
                  kw.get("add0_shift", 0) == 0 and kw.get("add1_shift", 0) == 0 and
-                 L.weight_bytes > self.TMA_WEIGHT_RESIDENT_MAX and L.cout == L.npad and L.cout % 32 == 0)
+                 L.weight_bytes > self.TMA_WEIGHT_RESIDENT_MAX and L.cout == L.npad and L.cout % 32 == 0 and
+                 not L.split)
         if not split:
             p, out = self.problem(L, x, **kw)
             return [p], out
@@ -213,7 +245,7 @@ class Runner:
         """x2d: fp16 [T, Cin] (row stride >= Cin) -> contiguous [T, Cout]: a 1x1 'convolution' over T pixels."""
         p, out = self.linear_problem(L, x2d, add0=add0, relu=relu)
         self.launch([p])
-        return out.view(x2d.shape[0], L.cout)
+        return out.view(x2d.shape[0], -1)
 
     def linear_problem(self, L, x2d, add0=None, relu=None):
         t, c = x2d.shape
@@ -228,9 +260,9 @@ class Runner:
     def stem(self, x, w, scale, bias, cout):
         nb, cin, h, wd = x.shape
         assert x.dtype == torch.float32 and x.is_contiguous()
-        y = torch.empty((nb, h // 2, wd // 2, cout), dtype=torch.float16, device=x.device)
+        y = torch.empty((nb, h // 2, wd // 2, cout * (2 if self.split else 1)), dtype=torch.float16, device=x.device)
         capi.check(self.lib.i2r_stem_conv3x3s2(x.data_ptr(), w.data_ptr(), scale.data_ptr(), bias.data_ptr(),
-                                                y.data_ptr(), nb, cin, h, wd, cout, _stream_ptr()),
+                                                y.data_ptr(), nb, cin, h, wd, cout, int(self.split), _stream_ptr()),
                    "i2r_stem_conv3x3s2")
         self.launches += 1
         return y
@@ -239,7 +271,8 @@ class Runner:
         nb, h, w, c = x.shape
         assert x.is_contiguous() and x.dtype == torch.float16
         y = torch.empty((nb, (h + 1) // 2, (w + 1) // 2, c), dtype=torch.float16, device=x.device)
-        capi.check(self.lib.i2r_maxpool3x3s2(x.data_ptr(), y.data_ptr(), nb, h, w, c, _stream_ptr()),
+        capi.check(self.lib.i2r_maxpool3x3s2(x.data_ptr(), y.data_ptr(), nb, h, w, c // 2 if self.split else c,
+                                              int(self.split), _stream_ptr()),
                    "i2r_maxpool3x3s2")
         self.launches += 1
         return y
@@ -251,30 +284,36 @@ class Runner:
         y2 = torch.empty_like(x2d) if pos is not None else None
         capi.check(self.lib.i2r_layernorm(x2d.data_ptr(), gamma.data_ptr(), beta.data_ptr(),
                                            pos.data_ptr() if pos is not None else None, y.data_ptr(),
-                                           y2.data_ptr() if y2 is not None else None, rows, c, eps,
-                                           _stream_ptr()), "i2r_layernorm")
+                                           y2.data_ptr() if y2 is not None else None, rows,
+                                           c // 2 if self.split else c, eps, int(self.split), _stream_ptr()),
+                   "i2r_layernorm")
         self.launches += 1
         return y, y2
 
     def add(self, a, b):
         assert a.shape == b.shape and a.is_contiguous() and b.is_contiguous()
         y = torch.empty_like(a)
-        capi.check(self.lib.i2r_add_f16(a.data_ptr(), b.data_ptr(), y.data_ptr(), a.numel(), _stream_ptr()),
+        capi.check(self.lib.i2r_add_f16(a.data_ptr(), b.data_ptr(), y.data_ptr(), a.numel(),
+                                         a.shape[-1] // 2 if self.split else 0, _stream_ptr()),
                    "i2r_add_f16")
         self.launches += 1
         return y
 
-    def attention(self, q, k, v, cu_seqlens, max_seqlen, scale):
-        """q,k,v: fp16 2-D views [T, D] (row stride arbitrary multiple of 8); returns [T, D] contiguous."""
+    def attention(self, q, k, v, cu_seqlens, max_seqlen, scale, lo=None):
+        """q,k,v: fp16 2-D views [T, D] (row stride arbitrary multiple of 8); returns [T, D] contiguous.
+        Split-operand mode: `lo` = (q_lo, k_lo, v_lo) element offsets from each hi view to its lo half; the result is
+        a split tensor [T, 2D]."""
         t, d = q.shape
-        out = torch.empty((t, d), dtype=torch.float16, device=q.device)
+        out = torch.empty((t, 2 * d if lo is not None else d), dtype=torch.float16, device=q.device)
         nseq = cu_seqlens.numel() - 1
         ws_bytes = int(self.lib.i2r_attention_workspace_bytes(t, d, nseq, max_seqlen))
         ws = torch.empty(max(ws_bytes, 16), dtype=torch.uint8, device=q.device) if ws_bytes else None
+        ql, kl, vl = lo if lo is not None else (0, 0, 0)
         capi.check(self.lib.i2r_attention_varlen(q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(),
                                                   q.stride(0), k.stride(0), v.stride(0), out.stride(0), d,
                                                   cu_seqlens.data_ptr(), nseq, max_seqlen, t, scale,
-                                                  ws.data_ptr() if ws is not None else None, ws_bytes, _stream_ptr()),
+                                                  ws.data_ptr() if ws is not None else None, ws_bytes,
+                                                  int(lo is not None), ql, kl, vl, d, _stream_ptr()),
                    "i2r_attention_varlen")
         self.launches += 1
         return out

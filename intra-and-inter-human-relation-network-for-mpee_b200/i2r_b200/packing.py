@@ -123,3 +123,36 @@ def pack_folded(mats, scale, bias, kc=KC):
     blk[rows, 0 ^ (rows & 7), 0] = hi
     blk[rows, 0 ^ (rows & 7), 1] = lo
     return torch.cat([blk.reshape(1, npad, 64), taps.reshape(ntaps * nch, npad, 64)], 0).contiguous()
+
+
+def split_virtual_taps(mats):
+    """Split-operand mode: activations travel as fp16 pairs (hi | lo, value = hi + lo) and a product is evaluated as
+    x_hi*W_hi + x_lo*W_hi + x_hi*W_lo (fp32 accumulation; the dropped lo*lo term is ~2^-22 relative).  Along K that
+    is ONE longer GEMM: A chunks [x_hi | x_lo | x_hi] against B chunks [W_hi | W_hi | W_lo].  Returns the per-tap
+    virtual weight matrices [Cout, 3 * ceil(Cin/64) * 64] (each third zero-padded to whole 64-slot K-chunks)."""
+    out = []
+    for m in mats:
+        m = m.float()
+        cout, cin = m.shape
+        kp = ceil_to(cin, KC)
+        hi = m.to(torch.float16).float()
+        lo = (m - hi).to(torch.float16).float()
+        v = torch.zeros(cout, 3 * kp)
+        v[:, :cin] = hi
+        v[:, kp:kp + cin] = hi
+        v[:, 2 * kp:2 * kp + cin] = lo
+        out.append(v)
+    return out
+
+
+def split_pair(t):
+    """fp32 tensor [..., C] -> fp16 [..., 2C] = (hi | lo)."""
+    hi = t.float().to(torch.float16)
+    lo = (t.float() - hi.float()).to(torch.float16)
+    return torch.cat([hi, lo], dim=-1)
+
+
+def merge_pair(t):
+    """fp16 [..., 2C] (hi | lo) -> fp32 [..., C]."""
+    c = t.shape[-1] // 2
+    return t[..., :c].float() + t[..., c:].float()

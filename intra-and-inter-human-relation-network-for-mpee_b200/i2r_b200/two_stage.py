@@ -19,7 +19,7 @@ from .encoder import EncoderProgram
 from .engine import GraphedForward
 from .hrnet_w48 import conv_bn_layer
 from .modules import DeconvProgram, EncoderParams, make_deconv_stack
-from .ops import Runner
+from .ops import Runner, split_precision
 from .position import MaskEmbedParams, MaskEmbedProgram
 
 
@@ -93,18 +93,12 @@ class TwoStageInterFormer(nn.Module):
         prog = type("Program", (), {})()
         prog.device = device
         prog.runner = self._runner_factory(device, 1 if self.check_impl else 0)
+        # the whole model shares the first stage's precision mode (split-operand unless overridden)
+        prog.split = getattr(self.singleformer, "precision", "fp16") == "split"
+        prog.runner.split = prog.split
         prog.first = self.singleformer.build_program(device)
-        prog.mask_embed = MaskEmbedProgram(sd, "multi_position_embedding", device) if self.use_multi_pos else None
-        prog.encoder = EncoderProgram(sd, "multi_global_encoder", c["layers"], c["d_model"], c["nhead"], device)
-        cache = {}
-
-        def deconv(key):
-            if key not in cache:
-                cache[key] = [DeconvProgram(sd, "%s.%d" % (key, 3 * i), "%s.%d" % (key, 3 * i + 1), device)
-                              for i in range(c["num_deconv"])]
-            return cache[key]
-        prog.upsample = [deconv(k) for k in self._deconv_keys]
-        prog.head = conv_bn_layer(sd, "final_layer", None, device=device)
+        with split_precision(prog.split):
+            self._build_second_stage(prog, sd, c, device)
         offsets = {}
 
         def seq_offsets(length, tokens_per_person):
@@ -116,6 +110,19 @@ class TwoStageInterFormer(nn.Module):
         self._program = prog
         self._graphs.reset()
         return self
+
+    def _build_second_stage(self, prog, sd, c, device):
+        prog.mask_embed = MaskEmbedProgram(sd, "multi_position_embedding", device) if self.use_multi_pos else None
+        prog.encoder = EncoderProgram(sd, "multi_global_encoder", c["layers"], c["d_model"], c["nhead"], device)
+        cache = {}
+
+        def deconv(key):
+            if key not in cache:
+                cache[key] = [DeconvProgram(sd, "%s.%d" % (key, 3 * i), "%s.%d" % (key, 3 * i + 1), device)
+                              for i in range(c["num_deconv"])]
+            return cache[key]
+        prog.upsample = [deconv(k) for k in self._deconv_keys]
+        prog.head = conv_bn_layer(sd, "final_layer", None, device=device)
 
     def load_state_dict(self, *a, **kw):
         out = super().load_state_dict(*a, **kw)

@@ -10,7 +10,7 @@ import torch.nn.functional as F
 
 from i2r_b200 import capi
 from i2r_b200.ops import Runner
-from i2r_b200.packing import unpack_taps
+from i2r_b200.packing import KC, ceil_to, merge_pair, split_pair, unpack_taps
 
 
 class EmuRunner(Runner):
@@ -19,6 +19,7 @@ class EmuRunner(Runner):
         self.use_tma = True     # exercise the N-split logic of Runner.problems
         self.timing = None
         self.launches = 0
+        self.split = False
         self.device = torch.device("cpu")
 
     def launch(self, problems):
@@ -32,11 +33,23 @@ class EmuRunner(Runner):
         nb, hs, ws, _ = x.shape
         sh = p.in_shift
         cin, npad, cout = p.Cin, p.Npad, p.Cout
-        w = unpack_taps(L.w, cin)                         # [ntaps, npad, cin]
+        split = bool(p.flags & capi.F_SPLIT)
+        if split:
+            # x = (hi | lo); product = (hi + lo) * W_hi + hi * W_lo with W = [W_hi | W_hi | W_lo] along K
+            kp = ceil_to(cin, KC)
+            wv = unpack_taps(L.w, 3 * kp)
+            w = wv[:, :, :cin]
+            w_lo = wv[:, :, 2 * kp:2 * kp + cin]
+            assert torch.equal(wv[:, :, kp:kp + cin], w)
+        else:
+            w = unpack_taps(L.w, cin)                         # [ntaps, npad, cin]
         oy = torch.arange(p.OH).view(-1, 1).expand(p.OH, p.OW)
         ox = torch.arange(p.OW).view(1, -1).expand(p.OH, p.OW)
         acc = torch.zeros(nb, p.OH, p.OW, npad)
         xf = x[..., :cin].float()
+        if split:
+            x_hi = xf
+            xf = xf + x[..., cin:2 * cin].float()
         for t in range(p.ntaps):
             wt = w[t]
             iy = oy * p.stride + int(p.dy[t])
@@ -46,48 +59,72 @@ class EmuRunner(Runner):
             sx = (ix.clamp(0, p.IW - 1) >> sh)
             a = xf[:, sy, sx, :] * ok[None, :, :, None]
             acc += a @ wt.t()
+            if split:
+                acc += (x_hi[:, sy, sx, :] * ok[None, :, :, None]) @ w_lo[t].t()
         v = acc[..., :cout] * L.scale[:cout] + L.bias[:cout]
         fy = oy * p.out_mul + p.out_offy
         fx = ox * p.out_mul + p.out_offx
         for a, s in ((add0, p.add0_shift), (add1, p.add1_shift)):
             if a is not None:
-                assert tuple(a.shape) == (nb, p.OHf >> s, p.OWf >> s, cout) and a.stride(2) == p.add_pix_stride
-                v = v + a.float()[:, fy >> s, fx >> s, :]
+                assert tuple(a.shape) == (nb, p.OHf >> s, p.OWf >> s, 2 * cout if split else cout)
+                assert a.stride(2) == p.add_pix_stride
+                af = merge_pair(a) if split else a.float()
+                v = v + af[:, fy >> s, fx >> s, :]
         if p.flags & capi.F_RELU:
             v = F.relu(v)
         if p.flags & capi.F_OUT_NCHW_F32:
             out[:, :, fy, fx] = v.permute(0, 3, 1, 2)
         elif p.flags & capi.F_OUT_F32:
             out[:, fy, fx, :] = v
+        elif split:
+            out[:, fy, fx, :] = split_pair(v)
         else:
             out[:, fy, fx, :] = v.half()
+
+    def _rd(self, x):
+        return merge_pair(x) if self.split else x.float()
+
+    def _wr(self, v):
+        return split_pair(v) if self.split else v.half()
 
     def stem(self, x, w, scale, bias, cout):
         cin = x.shape[1]
         wt = w.reshape(cin, 3, 3, cout).permute(3, 0, 1, 2)
         y = F.conv2d(x, wt, None, 2, 1) * scale.view(1, -1, 1, 1) + bias.view(1, -1, 1, 1)
         self.launches += 1
-        return F.relu(y).permute(0, 2, 3, 1).contiguous().half()
+        return self._wr(F.relu(y).permute(0, 2, 3, 1).contiguous())
 
     def maxpool(self, x):
         self.launches += 1
-        return F.max_pool2d(x.float().permute(0, 3, 1, 2), 3, 2, 1).permute(0, 2, 3, 1).contiguous().half()
+        return self._wr(F.max_pool2d(self._rd(x).permute(0, 3, 1, 2), 3, 2, 1).permute(0, 2, 3, 1).contiguous())
 
     def layernorm(self, x2d, gamma, beta, eps=1e-5, pos=None):
-        y = F.layer_norm(x2d.float(), (x2d.shape[1],), gamma, beta, eps)
+        xf = self._rd(x2d)
+        y = F.layer_norm(xf, (xf.shape[1],), gamma, beta, eps)
         self.launches += 1
-        return y.half(), ((y + pos.float()).half() if pos is not None else None)
+        return self._wr(y), (self._wr(y + self._rd(pos)) if pos is not None else None)
 
     def add(self, a, b):
         self.launches += 1
-        return (a.float() + b.float()).half()
+        return self._wr(self._rd(a) + self._rd(b))
 
-    def attention(self, q, k, v, cu_seqlens, max_seqlen, scale):
-        out = torch.empty(q.shape[0], q.shape[1], dtype=torch.float16)
+    def attention(self, q, k, v, cu_seqlens, max_seqlen, scale, lo=None):
+        t, d = q.shape
+        if lo is not None:      # split operands: lo halves sit `lo` elements after the hi views in the same rows
+            def lo_view(h, off):
+                return h.as_strided(h.shape, h.stride(), h.storage_offset() + off)
+            qh, kh, vh = q.float(), k.float(), v.float()
+            ql, kl, vl = lo_view(q, lo[0]).float(), lo_view(k, lo[1]).float(), lo_view(v, lo[2]).float()
+        out = torch.empty(t, 2 * d if lo is not None else d, dtype=torch.float16)
         cu = cu_seqlens.tolist()
         for a, b in zip(cu[:-1], cu[1:]):
             assert b - a <= max_seqlen
-            s = torch.softmax(q[a:b].float() @ k[a:b].float().t() * scale, dim=-1)
-            out[a:b] = (s.half().float() @ v[a:b].float()).half()
+            if lo is None:
+                s = torch.softmax(q[a:b].float() @ k[a:b].float().t() * scale, dim=-1)
+                out[a:b] = (s.half().float() @ v[a:b].float()).half()
+            else:
+                sc = (qh[a:b] + ql[a:b]) @ kh[a:b].t() + qh[a:b] @ kl[a:b].t()      # three-term score product
+                s = torch.softmax(sc * scale, dim=-1).half().float()                # probabilities stay fp16
+                out[a:b] = split_pair(s @ (vh[a:b] + vl[a:b]))
         self.launches += 1
         return out

@@ -298,3 +298,115 @@ def test_tma_residual_group(dev, runners):
         e = _diff(y, ref)
         _report(test="tma_group", c=L.cout, err=e)
         assert e[0] <= 8e-3, (L.cout, e)
+
+
+# ---------------------------------------------------------------------------------------------- split-operand mode
+SPLIT_CASES = [
+    # name, NB, H, W, Cin, Cout, k, stride, relu, residual
+    ("s_c48_3x3", 2, 64, 48, 48, 48, 3, 1, True, True),           # halo kernel, resident weights
+    ("s_c192_3x3", 3, 16, 12, 192, 192, 3, 1, True, True),        # halo kernel, streamed weights (9 K-chunks)
+    ("s_c96_3x3_s2", 2, 32, 24, 96, 192, 3, 2, True, False),      # gather kernel
+    ("s_c64to256_1x1", 1, 64, 48, 64, 256, 1, 1, False, False),   # halo 1x1
+    ("s_linear_96to192", 1, 3072, 1, 96, 192, 1, 1, True, False),
+]
+
+
+@pytest.mark.parametrize("case", SPLIT_CASES, ids=[c[0] for c in SPLIT_CASES])
+def test_split_operand_conv(case, dev, runners, gather_runner):
+    """Pair tensors (hi | lo) in, pair tensor out: the result must match an fp32 torch convolution on the FULL
+    precision values to ~1e-5 (three-term products), two orders of magnitude below the fp16 path."""
+    from i2r_b200.ops import ConvLayer
+    from i2r_b200.packing import conv_taps, merge_pair, split_pair
+    name, nb, h, w, cin, cout, k, stride, relu, residual = case
+    tc, chk = runners
+    g = torch.Generator().manual_seed(hash(name) % 1000)
+    wt = (torch.rand(cout, cin, k, k, generator=g) * 2 - 1) / math.sqrt(cin * k * k)
+    scale = torch.rand(cout, generator=g) + 0.5
+    bias = torch.randn(cout, generator=g) * 0.1
+    mats, dys, dxs = conv_taps(wt, pad=k // 2)
+    L = ConvLayer(mats, dys, dxs, scale, bias, stride=stride, relu=relu, device=dev, split=True)
+    x32 = torch.randn(nb, h, w, cin, generator=g)
+    x = split_pair(x32).to(dev)
+    oh, ow = (h + stride - 1) // stride, (w + stride - 1) // stride
+    kw = {}
+    ref = F.conv2d(merge_pair(x.cpu()).permute(0, 3, 1, 2).double(), wt.double(), None, stride, k // 2)
+    ref = ref * scale.double().view(1, -1, 1, 1) + bias.double().view(1, -1, 1, 1)
+    if residual:
+        r32 = torch.randn(nb, oh, ow, cout, generator=g)
+        res = split_pair(r32).to(dev)
+        kw["add0"] = res
+        ref = ref + merge_pair(res.cpu()).permute(0, 3, 1, 2).double()
+    if relu:
+        ref = F.relu(ref)
+    ref = ref.permute(0, 2, 3, 1).float()
+    errs = {}
+    for tag, r in (("tc", tc), ("ck", chk), ("ga", gather_runner)):
+        y = r.conv(L, x, **kw)
+        torch.cuda.synchronize()
+        assert tuple(y.shape) == (nb, oh, ow, 2 * cout)
+        errs[tag] = float((merge_pair(y.cpu()) - ref).abs().max())
+    _report(test="split_conv", case=name, err=errs)
+    assert all(v <= 6e-5 for v in errs.values()), errs   # fp32 accumulation over K up to 1728 + dropped lo*lo terms
+
+
+def test_split_small_kernels(dev, runners):
+    from i2r_b200.packing import merge_pair, split_pair
+    tc, _ = runners
+    tc.split = True
+    try:
+        g = torch.Generator().manual_seed(11)
+        # layernorm (+pos), add, maxpool on pair tensors
+        x32 = torch.randn(1000, 96, generator=g) * 3
+        p32 = torch.randn(1000, 96, generator=g)
+        gamma, beta = torch.rand(96, generator=g) + 0.5, torch.randn(96, generator=g) * 0.1
+        y, y2 = tc.layernorm(split_pair(x32).to(dev), gamma.to(dev), beta.to(dev), pos=split_pair(p32).to(dev))
+        ref = F.layer_norm(merge_pair(split_pair(x32)), (96,), gamma, beta, 1e-5)
+        e_ln = float((merge_pair(y.cpu()) - ref).abs().max())
+        e_ln2 = float((merge_pair(y2.cpu()) - (ref + merge_pair(split_pair(p32)))).abs().max())
+        a32, b32 = torch.randn(4, 8, 6, 48, generator=g), torch.randn(4, 8, 6, 48, generator=g)
+        s = tc.add(split_pair(a32).to(dev), split_pair(b32).to(dev))
+        e_add = float((merge_pair(s.cpu()) - (merge_pair(split_pair(a32)) + merge_pair(split_pair(b32)))).abs().max())
+        m32 = torch.randn(3, 17, 11, 96, generator=g)
+        mp = tc.maxpool(split_pair(m32).to(dev))
+        refm = F.max_pool2d(merge_pair(split_pair(m32)).permute(0, 3, 1, 2), 3, 2, 1).permute(0, 2, 3, 1)
+        e_mp = float((merge_pair(mp.cpu()) - refm).abs().max())
+        # stem
+        xs = torch.randn(2, 3, 64, 48, generator=g)
+        w = torch.randn(64, 3, 3, 3, generator=g) * 0.2
+        sc, bi = torch.rand(64, generator=g) + 0.5, torch.randn(64, generator=g) * 0.1
+        ys = tc.stem(xs.to(dev), w.permute(1, 2, 3, 0).reshape(-1, 64).contiguous().to(dev), sc.to(dev), bi.to(dev), 64)
+        refs = F.relu(F.conv2d(xs, w, None, 2, 1) * sc.view(1, -1, 1, 1) + bi.view(1, -1, 1, 1)).permute(0, 2, 3, 1)
+        e_st = float((merge_pair(ys.cpu()) - refs).abs().max())
+        torch.cuda.synchronize()
+    finally:
+        tc.split = False
+    _report(test="split_small", ln=e_ln, ln_pos=e_ln2, add=e_add, maxpool=e_mp, stem=e_st)
+    assert e_ln <= 1e-5 and e_ln2 <= 1e-5 and e_add <= 2e-6 and e_mp <= 1e-6 and e_st <= 2e-5, (e_ln, e_ln2, e_add, e_mp, e_st)
+
+
+@pytest.mark.parametrize("lens", [[3072], [192, 768, 64]])
+def test_split_attention(dev, runners, lens):
+    from i2r_b200.packing import merge_pair, split_pair
+    tc, _ = runners
+    g = torch.Generator().manual_seed(13)
+    t, d = sum(lens), 96
+    qk32 = torch.randn(t, 2 * d, generator=g)
+    v32 = torch.randn(t, d, generator=g)
+    qk = split_pair(qk32).to(dev)          # [t, (q_hi k_hi | q_lo k_lo)]
+    v = split_pair(v32).to(dev)            # [t, (v_hi | v_lo)]
+    cu = torch.tensor([0] + list(torch.tensor(lens).cumsum(0)), dtype=torch.int32).to(dev)
+    scale = d ** -0.5
+    out = tc.attention(qk[:, :d], qk[:, d:2 * d], v[:, :d], cu, max(lens), scale, lo=(2 * d, 2 * d, d))
+    torch.cuda.synchronize()
+    qf = merge_pair(qk.cpu())
+    vf = merge_pair(v.cpu())
+    ref = torch.empty(t, d)
+    o = 0
+    for n in lens:
+        s = torch.softmax(qf[o:o + n, :d].double() @ qf[o:o + n, d:].double().t() * scale, dim=-1)
+        ref[o:o + n] = (s @ vf[o:o + n].double()).float()
+        o += n
+    err = float((merge_pair(out.cpu()) - ref).abs().max())
+    _report(test="split_attention", lens=lens, err=err)
+    # fp16 probabilities bound the error: ~2^-11 relative on each of ~n averaged terms
+    assert tuple(out.shape) == (t, 2 * d) and err <= 4e-4, err

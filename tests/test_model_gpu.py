@@ -93,12 +93,12 @@ def test_forward_rejects_bad_length_and_cpu(vanilla_cuda):
 
 
 # ---------------------------------------------------------------------------------------------- two-stage models
-# TransPose-H first stage + inter-human stage.  PRECISION STATUS: these families run on the
-# single-pass fp16 kernels; the reference is ~5x more sensitive to operand rounding here than the vanilla model
-# (six post-norm LayerNorm layers sit on the direct path to the heatmaps), and the measured error is ~3e-3 --
-# ABOVE the 1e-3 north_star bar, which needs the split-operand mode.  The test pins the measured level so that a
-# regression shows, and records the numbers; it does not claim the 1e-3 bar for these families.
-TWO_STAGE_TOL = 6e-3
+# TransPose-H first stage + inter-human stage.  These families run in the SPLIT-OPERAND mode (fp16 hi+lo pairs,
+# three-term products): the reference is ~5x more sensitive to operand rounding here than the
+# vanilla model (six post-norm LayerNorm layers sit on the direct path to the heatmaps) and the single-pass fp16
+# kernels measure ~3e-3, above the 1e-3 north_star bar; `I2R_PRECISION_TPH=fp16` selects that faster mode.
+TWO_STAGE_TOL = TOL
+FP16_MODE_TOL = 6e-3
 TWO_STAGE = [
     ("coco/interformer_coco_tph_192_p4_b4.yaml", "tph2stage_ragged"),
     ("crowdpose/interformer_crowdpose_tph_192_p6_b4.yaml", "tph_crowdpose_ragged"),
@@ -144,4 +144,19 @@ def test_transpose_h_standalone_forward():
     assert tuple(feat.shape) == tuple(rf.shape) and tuple(heat.shape) == tuple(rh.shape)
     e_feat, e_heat = float((feat.cpu() - rf).abs().max()), float((heat.cpu() - rh).abs().max())
     _report(test="transpose_h_standalone", feat_err=e_feat, heat_err=e_heat, feat_max=float(rf.abs().max()))
-    assert e_heat <= TWO_STAGE_TOL and e_feat <= 5e-2, (e_feat, e_heat)
+    assert e_heat <= TWO_STAGE_TOL and e_feat <= 2e-3, (e_feat, e_heat)
+
+
+def test_two_stage_fp16_mode_runs():
+    """The single-pass fp16 mode of the two-stage family stays available (3x fewer MMAs, ~3e-3 error)."""
+    cfg, model, _ = build_model("coco/interformer_coco_tph_192_p4_b4.yaml")
+    model.singleformer.precision = "fp16"
+    model = model.cuda()
+    g = load_golden("tph2stage_ragged")
+    length = [int(v) for v in g["length"]]
+    x, pm = inputs_for(length)
+    out = model(x, pm, length)
+    torch.cuda.synchronize()
+    errs = {k: float(np.abs(out[k].cpu().numpy() - g["out_" + k]).max()) for k in out}
+    _report(test="two_stage_fp16_mode", max_abs_err=errs)
+    assert all(v <= FP16_MODE_TOL for v in errs.values()), errs
