@@ -143,6 +143,13 @@ int i2r_layernorm(const void* x, const float* gamma, const float* beta, const vo
  * `single_res + x`, interformer.py:315).  split_c > 0: the operands are pair tensors with C = split_c. */
 int i2r_add_f16(const void* a, const void* b, void* y, int64_t n, int split_c, void* stream);
 
+/* y[n,h,w,:] = act(x0[n,h,w,:] + t1[n,h>>shift1,w>>shift1,:] + t2[n,h>>shift2,w>>shift2,:]) on fp16 NHWC (t2 may be
+ * NULL; split != 0: pair tensors with C logical channels): the highest-resolution output branch of an HRNet fuse
+ * layer -- identity + nearest-upsampled 1x1-conv terms evaluated at their own resolution, sum, ReLU
+ * (interformer_pureMulti.py:392-410). */
+int i2r_upsum(const void* x0, const void* t1, int shift1, const void* t2, int shift2, void* y, int NB, int H, int W,
+              int C, int relu, int split, void* stream);
+
 /* Profiling aid: while dev_buffer != NULL, CTA `cta` of every i2r_conv_halo launch writes (tag<<32 | tile, clock64)
  * pairs into four role regions (producer, MMA, epilogue, kernel start/end) of `capacity_events` pairs each (zero-filled by the caller).  Tags: 1/2/3
  * producer slot free / loads issued / stage published, 10/11/12 MMA accumulator free / operands landed / tile

@@ -59,7 +59,11 @@ __device__ __forceinline__ void store8_pair(__half* row, int C, int c, const flo
 // CTA = 8 x 32 output pixels: the (17 x 65 x CIN) fp32 input patch is staged in shared memory with coalesced
 // loads; each thread owns one output pixel and all 64 channels (weights are warp-broadcast float4 reads),
 // then writes its 128-byte NHWC row.
-constexpr int STEM_TH = 8, STEM_TW = 32, STEM_PH = 2 * STEM_TH + 1, STEM_PW = 2 * STEM_TW + 1, STEM_PWP = STEM_PW + 1;
+// CTA = 8 x 32 output pixels: the (17 x 65 x CIN) fp32 input patch is staged in shared memory with coalesced loads.
+// A thread owns FOUR horizontally adjacent output pixels x 16 channels (a quarter of the 64): per tap it reads four
+// patch values and four float4 weight vectors for 64 FMAs, i.e. one shared-memory load per 8 FMAs (the first version
+// -- one pixel x 64 channels per thread -- issued one LDS per 4 FMAs and ran LDS-bound at 14x the HBM time).
+constexpr int STEM_TH = 8, STEM_TW = 32, STEM_PH = 2 * STEM_TH + 1, STEM_PW = 2 * STEM_TW + 1, STEM_PWP = STEM_PW + 2;
 
 template <int CIN>
 __global__ void __launch_bounds__(256) stem_conv_kernel(const float* __restrict__ x, const float* __restrict__ w,
@@ -91,42 +95,61 @@ __global__ void __launch_bounds__(256) stem_conv_kernel(const float* __restrict_
     patch[c][py][px] = v;
   }
   __syncthreads();
-  const int ty = tid >> 5, tx = tid & 31;
-  const int oy = oy0 + ty, ox = ox0 + tx;
-  float acc[64];
+  // thread -> (row ty, pixel group pg of 4 pixels, channel quarter cq): consecutive lanes take consecutive channel
+  // quarters of the same pixels, so a warp's stores cover 8 pixel groups x 128 B contiguous rows
+  const int cq = tid & 3, pg = (tid >> 2) & 7, ty = tid >> 5;
+  float acc[4][16];
 #pragma unroll
-  for (int i = 0; i < 64; ++i) acc[i] = 0.f;
+  for (int p = 0; p < 4; ++p)
+#pragma unroll
+    for (int i = 0; i < 16; ++i) acc[p][i] = 0.f;
   const float4* sw4 = reinterpret_cast<const float4*>(sw);
 #pragma unroll
   for (int c = 0; c < CIN; ++c) {
 #pragma unroll
     for (int ky = 0; ky < 3; ++ky) {
+      // the 4 pixels x 3 taps of this row touch 9 consecutive patch columns
+      float pv[9];
+#pragma unroll
+      for (int j = 0; j < 9; ++j) pv[j] = patch[c][2 * ty + ky][8 * pg + j];
 #pragma unroll
       for (int kx = 0; kx < 3; ++kx) {
-        const float v = patch[c][2 * ty + ky][2 * tx + kx];
         const int k = (c * 3 + ky) * 3 + kx;
 #pragma unroll
-        for (int q = 0; q < 16; ++q) {
-          const float4 wq = sw4[k * 16 + q];
-          acc[4 * q + 0] = fmaf(v, wq.x, acc[4 * q + 0]);
-          acc[4 * q + 1] = fmaf(v, wq.y, acc[4 * q + 1]);
-          acc[4 * q + 2] = fmaf(v, wq.z, acc[4 * q + 2]);
-          acc[4 * q + 3] = fmaf(v, wq.w, acc[4 * q + 3]);
+        for (int q = 0; q < 4; ++q) {
+          const float4 wq = sw4[k * 16 + cq * 4 + q];
+#pragma unroll
+          for (int p = 0; p < 4; ++p) {
+            const float v = pv[2 * p + kx];
+            acc[p][4 * q + 0] = fmaf(v, wq.x, acc[p][4 * q + 0]);
+            acc[p][4 * q + 1] = fmaf(v, wq.y, acc[p][4 * q + 1]);
+            acc[p][4 * q + 2] = fmaf(v, wq.z, acc[p][4 * q + 2]);
+            acc[p][4 * q + 3] = fmaf(v, wq.w, acc[p][4 * q + 3]);
+          }
         }
       }
     }
   }
-  if (oy < OH && ox < OW) {
-    __half* row = y + ((static_cast<int64_t>(n) * OH + oy) * OW + ox) * (split ? 128 : 64);
+  const int oy = oy0 + ty;
+  if (oy < OH) {
 #pragma unroll
-    for (int q = 0; q < 8; ++q) {
-      float o[8];
+    for (int p = 0; p < 4; ++p) {
+      const int ox = ox0 + 4 * pg + p;
+      if (ox >= OW) continue;
+      __half* row = y + ((static_cast<int64_t>(n) * OH + oy) * OW + ox) * (split ? 128 : 64);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) o[i] = fmaxf(acc[q * 8 + i] * ssc[q * 8 + i] + sbi[q * 8 + i], 0.f);
-      if (split) {
-        store8_pair(row, 64, q * 8, o);
-      } else {
-        store8(row + q * 8, o);
+      for (int h = 0; h < 2; ++h) {
+        float o[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int ch = cq * 16 + h * 8 + i;
+          o[i] = fmaxf(acc[p][h * 8 + i] * ssc[ch] + sbi[ch], 0.f);
+        }
+        if (split) {
+          store8_pair(row, 64, cq * 16 + h * 8, o);
+        } else {
+          store8(row + cq * 16 + h * 8, o);
+        }
       }
     }
   }
@@ -305,6 +328,43 @@ __global__ void __launch_bounds__(256) add_pair_kernel(const __half* __restrict_
   }
 }
 
+// y[n,h,w,:] = act(x0[n,h,w,:] + t1[n,h>>s1,w>>s1,:] + t2[n,h>>s2,w>>s2,:]) -- the highest-resolution output of an
+// HRNet fuse layer: identity branch + nearest-upsampled 1x1 terms computed at their own (lower) resolution, because
+// a 1x1 convolution commutes with nearest upsampling (interformer_pureMulti.py:392-410).  PAIR: pair tensors.
+template <bool PAIR>
+__global__ void __launch_bounds__(256) upsum_kernel(const __half* __restrict__ x0, const __half* __restrict__ t1,
+                                                    const __half* __restrict__ t2, __half* __restrict__ y, int NB,
+                                                    int H, int W, int C, int s1, int s2, int relu) {
+  const int cv = C >> 3;
+  const int ld = PAIR ? 2 * C : C;
+  const int64_t total = static_cast<int64_t>(NB) * H * W * cv;
+  for (int64_t idx = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(idx % cv) * 8;
+    const int64_t p = idx / cv;
+    const int wx = static_cast<int>(p % W);
+    const int hy = static_cast<int>((p / W) % H);
+    const int n = static_cast<int>(p / (static_cast<int64_t>(W) * H));
+    float v[8], a[8];
+    if (PAIR) load8_pair(x0 + p * ld, C, c, v); else load8(x0 + p * ld + c, v);
+    const int64_t p1 = (static_cast<int64_t>(n) * (H >> s1) + (hy >> s1)) * (W >> s1) + (wx >> s1);
+    if (PAIR) load8_pair(t1 + p1 * ld, C, c, a); else load8(t1 + p1 * ld + c, a);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] += a[i];
+    if (t2 != nullptr) {
+      const int64_t p2 = (static_cast<int64_t>(n) * (H >> s2) + (hy >> s2)) * (W >> s2) + (wx >> s2);
+      if (PAIR) load8_pair(t2 + p2 * ld, C, c, a); else load8(t2 + p2 * ld + c, a);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] += a[i];
+    }
+    if (relu) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] = fmaxf(v[i], 0.f);
+    }
+    if (PAIR) store8_pair(y + p * ld, C, c, v); else store8(y + p * ld + c, v);
+  }
+}
+
 static int grid_for(int64_t work_items, int block) {
   int64_t g = (work_items + block - 1) / block;
   const int64_t cap = 148 * 16;
@@ -406,4 +466,26 @@ extern "C" int i2r_add_f16(const void* a, const void* b, void* y, int64_t n, int
   add_f16_kernel<<<grid_for(n / 8, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const uint4*>(a), static_cast<const uint4*>(b), static_cast<uint4*>(y), n / 8);
   return check_launch("add_f16_kernel");
+}
+
+extern "C" int i2r_upsum(const void* x0, const void* t1, int shift1, const void* t2, int shift2, void* y, int NB, int H,
+                         int W, int C, int relu, int split, void* stream) {
+  if (!x0 || !t1 || !y || NB <= 0 || H <= 0 || W <= 0 || C % 8 != 0 || shift1 < 0 || shift2 < 0 ||
+      (H >> shift1) << shift1 != H || (W >> shift1) << shift1 != W ||
+      (t2 && ((H >> shift2) << shift2 != H || (W >> shift2) << shift2 != W))) {
+    set_error("i2r_upsum: bad arguments (H=%d W=%d C=%d shifts %d %d)", H, W, C, shift1, shift2);
+    return I2R_E_BADARG;
+  }
+  const int64_t items = static_cast<int64_t>(NB) * H * W * (C / 8);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (split) {
+    upsum_kernel<true><<<grid_for(items, 256), 256, 0, st>>>(static_cast<const __half*>(x0), static_cast<const __half*>(t1),
+                                                             static_cast<const __half*>(t2), static_cast<__half*>(y), NB,
+                                                             H, W, C, shift1, shift2, relu);
+  } else {
+    upsum_kernel<false><<<grid_for(items, 256), 256, 0, st>>>(static_cast<const __half*>(x0), static_cast<const __half*>(t1),
+                                                              static_cast<const __half*>(t2), static_cast<__half*>(y), NB,
+                                                              H, W, C, shift1, shift2, relu);
+  }
+  return check_launch("upsum_kernel");
 }

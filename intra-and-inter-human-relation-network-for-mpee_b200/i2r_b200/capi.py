@@ -15,7 +15,7 @@ F_SPLIT = 8
 
 EXPORTS = [
     "i2r_version", "i2r_last_error", "i2r_device_check", "i2r_sm_count", "i2r_conv_igemm", "i2r_conv_halo", "i2r_conv_halo_supported", "i2r_debug_trace", "i2r_debug_flags",
-    "i2r_sizeof_conv_problem", "i2r_stem_conv3x3s2", "i2r_maxpool3x3s2", "i2r_attention_varlen", "i2r_attention_workspace_bytes", "i2r_layernorm", "i2r_add_f16",
+    "i2r_sizeof_conv_problem", "i2r_stem_conv3x3s2", "i2r_maxpool3x3s2", "i2r_attention_varlen", "i2r_attention_workspace_bytes", "i2r_layernorm", "i2r_add_f16", "i2r_upsum",
 ]
 
 
@@ -75,6 +75,7 @@ def load():
         lib.i2r_attention_workspace_bytes.restype = i64
         lib.i2r_layernorm.argtypes = [vp, vp, vp, vp, vp, vp, i32, i32, f32, i32, vp]
         lib.i2r_add_f16.argtypes = [vp, vp, vp, i64, i32, vp]
+        lib.i2r_upsum.argtypes = [vp, vp, i32, vp, i32, vp, i32, i32, i32, i32, i32, i32, vp]
         for name in EXPORTS:
             getattr(lib, name)  # raises AttributeError if the symbol is missing
         if lib.i2r_sizeof_conv_problem() != ctypes.sizeof(ConvProblem):

@@ -229,30 +229,34 @@ class BackboneProgram:
     def _fuse(r, mod, xs):
         """Multi-resolution exchange: y_i = relu(sum_j f_ij(x_j))  (reference :392-410).
 
-        Every output branch ends in ONE implicit-GEMM whose epilogue adds the identity branch and the
-        remaining (already reduced-resolution) terms through nearest-upsampling addends; the 1x1 term
-        from the next-lower resolution reads its source through the gather's in_shift, because a 1x1
-        convolution commutes with nearest upsampling.
+        The lower-resolution output branches end in ONE implicit GEMM (the stride-2 3x3 from the branch above) whose
+        epilogue adds the identity branch and the remaining terms through (up-sampling) addends.  The highest
+        resolution branch has no convolution of its own left: a 1x1 convolution commutes with nearest upsampling, so
+        its 1x1 terms run at THEIR resolution (4x / 16x fewer MMAs than at the output resolution) and one
+        elementwise pass sums identity + upsampled terms and applies the ReLU.
         """
         f = mod.fuse
         if mod.nb == 2:
-            return r.conv_group([
-                (f[(0, 1)][0], xs[1], dict(in_shift=1, add0=xs[0], relu=True)),
-                (f[(1, 0)][0], xs[0], dict(add0=xs[1], relu=True)),
+            t01, y1 = r.conv_group([
+                (f[(0, 1)][0], xs[1], {}),                                  # 1x1 96->48 at 1/8 (commutes with upsampling)
+                (f[(1, 0)][0], xs[0], dict(add0=xs[1], relu=True)),          # 3x3 s2 48->96 + identity
             ])
+            return [r.upsum(xs[0], t01, 1), y1]
         if mod.nb != 3:
             raise NotImplementedError("fuse for %d resolution branches" % mod.nb)
-        t02, t12, u20, t21 = r.conv_group([
+        t01, t02, t12, u20, t21 = r.conv_group([
+            (f[(0, 1)][0], xs[1], {}),        # 1x1 96->48 at 1/8
             (f[(0, 2)][0], xs[2], {}),        # 1x1 192->48 at 1/16
             (f[(1, 2)][0], xs[2], {}),        # 1x1 192->96 at 1/16
             (f[(2, 0)][0], xs[0], {}),        # 3x3 s2 48->48 (+ReLU), first hop of the 0->2 chain
             (f[(2, 1)][0], xs[1], {}),        # 3x3 s2 96->192
         ])
-        return r.conv_group([
-            (f[(0, 1)][0], xs[1], dict(in_shift=1, add0=xs[0], add1=t02, add1_shift=2, relu=True)),
+        y1, y2 = r.conv_group([
             (f[(1, 0)][0], xs[0], dict(add0=xs[1], add1=t12, add1_shift=1, relu=True)),
             (f[(2, 0)][1], u20, dict(add0=xs[2], add1=t21, relu=True)),
         ])
+        # branch 0: identity + the two 1x1 terms evaluated at their own resolution, one HBM-bound pass
+        return [r.upsum(xs[0], t01, 1, t02, 2), y1, y2]
 
     def run(self, r, x):
         """x: fp32 NCHW [S,3,H,W] on the device -> list of fp16 NHWC branch maps after stage3."""

@@ -299,6 +299,18 @@ class Runner:
         self.launches += 1
         return y
 
+    def upsum(self, x0, t1, shift1, t2=None, shift2=0, relu=True):
+        """relu(x0 + up(t1) + up(t2)) with nearest upsampling by 2^shift (HRNet fuse, highest-resolution branch)."""
+        nb, h, w, c = x0.shape
+        assert x0.is_contiguous() and t1.is_contiguous() and (t2 is None or t2.is_contiguous())
+        assert t1.shape == (nb, h >> shift1, w >> shift1, c) and (t2 is None or t2.shape == (nb, h >> shift2, w >> shift2, c))
+        y = torch.empty_like(x0)
+        capi.check(self.lib.i2r_upsum(x0.data_ptr(), t1.data_ptr(), shift1, t2.data_ptr() if t2 is not None else None,
+                                      shift2, y.data_ptr(), nb, h, w, c // 2 if self.split else c, int(relu),
+                                      int(self.split), _stream_ptr()), "i2r_upsum")
+        self.launches += 1
+        return y
+
     def attention(self, q, k, v, cu_seqlens, max_seqlen, scale, lo=None):
         """q,k,v: fp16 2-D views [T, D] (row stride arbitrary multiple of 8); returns [T, D] contiguous.
         Split-operand mode: `lo` = (q_lo, k_lo, v_lo) element offsets from each hi view to its lo half; the result is

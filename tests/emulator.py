@@ -108,6 +108,16 @@ class EmuRunner(Runner):
         self.launches += 1
         return self._wr(self._rd(a) + self._rd(b))
 
+    def upsum(self, x0, t1, shift1, t2=None, shift2=0, relu=True):
+        nb, h, w, _ = x0.shape
+        ys = torch.arange(h).view(-1, 1).expand(h, w)
+        xs = torch.arange(w).view(1, -1).expand(h, w)
+        v = self._rd(x0) + self._rd(t1)[:, ys >> shift1, xs >> shift1, :]
+        if t2 is not None:
+            v = v + self._rd(t2)[:, ys >> shift2, xs >> shift2, :]
+        self.launches += 1
+        return self._wr(F.relu(v) if relu else v)
+
     def attention(self, q, k, v, cu_seqlens, max_seqlen, scale, lo=None):
         t, d = q.shape
         if lo is not None:      # split operands: lo halves sit `lo` elements after the hi views in the same rows
