@@ -63,7 +63,7 @@ __device__ __forceinline__ void store8_pair(__half* row, int C, int c, const flo
 // A thread owns FOUR horizontally adjacent output pixels x 16 channels (a quarter of the 64): per tap it reads four
 // patch values and four float4 weight vectors for 64 FMAs, i.e. one shared-memory load per 8 FMAs (the first version
 // -- one pixel x 64 channels per thread -- issued one LDS per 4 FMAs and ran LDS-bound at 14x the HBM time).
-constexpr int STEM_TH = 8, STEM_TW = 32, STEM_PH = 2 * STEM_TH + 1, STEM_PW = 2 * STEM_TW + 1, STEM_PWP = STEM_PW + 2;
+constexpr int STEM_TH = 8, STEM_TW = 32, STEM_PH = 2 * STEM_TH + 1, STEM_PW = 2 * STEM_TW + 1, STEM_PWP = STEM_PW + 4;
 
 template <int CIN>
 __global__ void __launch_bounds__(256) stem_conv_kernel(const float* __restrict__ x, const float* __restrict__ w,
@@ -76,7 +76,13 @@ __global__ void __launch_bounds__(256) stem_conv_kernel(const float* __restrict_
   __shared__ __align__(16) float sbi[64];
   __shared__ float patch[CIN][STEM_PH][STEM_PWP];
   const int tid = threadIdx.x;
-  for (int i = tid; i < K * 64; i += 256) sw[i] = w[i];
+  // weights re-ordered so that the four channel quarters read by the lanes of one instruction are 64 contiguous
+  // bytes: float4 slot (k*4 + q)*4 + cq holds channels [cq*16 + q*4, +4) of tap k (bank-conflict free)
+  for (int i = tid; i < K * 64; i += 256) {
+    const int k = i >> 6, ch = i & 63;
+    const int cq_ = ch >> 4, q_ = (ch >> 2) & 3, e_ = ch & 3;
+    sw[((k * 4 + q_) * 4 + cq_) * 4 + e_] = w[i];
+  }
   if (tid < 64) {
     ssc[tid] = scale[tid];
     sbi[tid] = bias[tid];
@@ -92,7 +98,7 @@ __global__ void __launch_bounds__(256) stem_conv_kernel(const float* __restrict_
     const int iy = iy0 + py, ix = ix0 + px;
     float v = 0.f;
     if (iy >= 0 && iy < H && ix >= 0 && ix < W) v = __ldg(x + ((static_cast<int64_t>(n) * CIN + c) * H + iy) * W + ix);
-    patch[c][py][px] = v;
+    patch[c][py][px + (px >> 5)] = v;   // skew one word per 32 columns: the 8 pixel groups of a warp hit 8 banks
   }
   __syncthreads();
   // thread -> (row ty, pixel group pg of 4 pixels, channel quarter cq): consecutive lanes take consecutive channel
@@ -111,13 +117,13 @@ __global__ void __launch_bounds__(256) stem_conv_kernel(const float* __restrict_
       // the 4 pixels x 3 taps of this row touch 9 consecutive patch columns
       float pv[9];
 #pragma unroll
-      for (int j = 0; j < 9; ++j) pv[j] = patch[c][2 * ty + ky][8 * pg + j];
+      for (int j = 0; j < 9; ++j) pv[j] = patch[c][2 * ty + ky][8 * pg + j + ((8 * pg + j) >> 5)];
 #pragma unroll
       for (int kx = 0; kx < 3; ++kx) {
         const int k = (c * 3 + ky) * 3 + kx;
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-          const float4 wq = sw4[k * 16 + cq * 4 + q];
+          const float4 wq = sw4[(k * 4 + q) * 4 + cq];
 #pragma unroll
           for (int p = 0; p < 4; ++p) {
             const float v = pv[2 * p + kx];
