@@ -57,6 +57,8 @@ __global__ void __launch_bounds__(128) attention_kernel(const __half* __restrict
   constexpr int KS = HD / 16;  // k-steps over the head dim
   constexpr int DT = HD / 8;   // 8-wide output tiles over the head dim
   extern __shared__ __align__(128) uint8_t smem[];
+  pdl_launch_dependents();
+  pdl_wait();
   const int seq = blockIdx.y;
   const int t0 = cu_seqlens[seq];
   const int L = cu_seqlens[seq + 1] - t0;
@@ -267,6 +269,8 @@ __global__ void __launch_bounds__(256) attention_merge_kernel(const float* __res
                                                               const float* __restrict__ mlpart,
                                                               __half* __restrict__ out, int ldo, int rows, int nsplit,
                                                               int o_lo) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (row >= rows) return;
@@ -329,13 +333,13 @@ static int launch_attention(const void* q, const void* k, const void* v, void* o
   float* opart = static_cast<float*>(ws);
   float* mlpart = opart ? opart + static_cast<int64_t>(total_tokens) * nsplit * HD : nullptr;
   dim3 grid((max_seqlen + ATT_BQ - 1) / ATT_BQ, nseq, nsplit);
-  attention_kernel<HD, SPLIT><<<grid, 128, smem, st>>>(
+  launch_pdl(attention_kernel<HD, SPLIT>, grid, dim3(128), smem, st,
       static_cast<const __half*>(q), static_cast<const __half*>(k), static_cast<const __half*>(v),
       static_cast<__half*>(out), ldq, ldk, ldv, ldo, cu, scale * 1.4426950408889634f, nsplit, opart, mlpart, q_lo, k_lo,
       v_lo, o_lo);
   int rc = check_launch("attention_kernel");
   if (rc || nsplit == 1) return rc;
-  attention_merge_kernel<HD><<<(total_tokens + 7) / 8, 256, 0, st>>>(opart, mlpart, static_cast<__half*>(out), ldo,
+  launch_pdl(attention_merge_kernel<HD>, dim3((total_tokens + 7) / 8), dim3(256), 0, st, opart, mlpart, static_cast<__half*>(out), ldo,
                                                                      total_tokens, nsplit, SPLIT ? o_lo : 0);
   return check_launch("attention_merge_kernel");
 }

@@ -541,6 +541,7 @@ __global__ void __launch_bounds__(T_THREADS, 1) conv_halo_kernel(const __grid_co
   const int dbg = opaque(G.dbg);
   const int trace_cap = opaque(G.trace_cap);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  pdl_launch_dependents();   // the next grid may start its prologue as soon as SMs free up (see i2r_common.cuh)
 
   const uint32_t sbase = smem_u32(smem);
   const uint32_t bar_afull = sbase, bar_aempty = sbase + 32, bar_wfull = sbase + 256, bar_wempty = sbase + 320;
@@ -591,6 +592,7 @@ __global__ void __launch_bounds__(T_THREADS, 1) conv_halo_kernel(const __grid_co
       // ================================================= activation producer: one TMA box per (tile, K-chunk)
       const CUtensorMap* amap = &G.amap[pi];
       prefetch_tmap(amap);
+      pdl_wait();   // activations come from the previous kernels (weights do not: warp 1 loads them right away)
       const int dual = P.w_resident;   // two MMA issuers, each with its own half-ring (see mma_role)
       const int a_half = dual ? P.a_stages >> 1 : P.a_stages;
       int sr[2] = {0, 0}, tri = 0, ring = 0;
@@ -672,6 +674,7 @@ __global__ void __launch_bounds__(T_THREADS, 1) conv_halo_kernel(const __grid_co
   } else {
     // ================================================= epilogue: 8 warps, two per TMEM lane quadrant, each
     // owning half of the output channels of its 32 rows
+    pdl_wait();   // addends are read and the output written only after every earlier kernel has finished
     EpiArgs E;
     E.add0 = P.add0; E.add1 = P.add1; E.y = P.y;
     E.H = P.H; E.W = P.W; E.Cout = P.Cout; E.tiles_x = P.tiles_x; E.tiles_per_img = P.tiles_per_img;
@@ -932,7 +935,7 @@ extern "C" int i2r_conv_halo(const i2r_conv_problem* probs, int nprob, void* str
     }
     attr_done = true;
   }
-  conv_halo_kernel<<<begin, T_THREADS, smem_need + 1024, static_cast<cudaStream_t>(stream)>>>(G);
+  launch_pdl(conv_halo_kernel, dim3(begin), dim3(T_THREADS), smem_need + 1024, static_cast<cudaStream_t>(stream), G);
   return check_launch("conv_halo_kernel");
 }
 

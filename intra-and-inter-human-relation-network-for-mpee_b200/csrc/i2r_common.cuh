@@ -12,6 +12,33 @@ namespace i2r {
 void set_error(const char* fmt, ...);
 int check_launch(const char* what);
 
+// ---------------------------------------------------------------- programmatic dependent launch
+// The forward is a chain of ~130 short dependent kernels.  Every kernel is launched with the programmatic stream
+// serialization attribute, calls pdl_launch_dependents() first (so the NEXT grid's CTAs are scheduled as soon as SMs
+// free up in this grid's tail and run their prologue: barrier init, TMEM allocation, weight loads) and pdl_wait()
+// before its first access to memory a predecessor may still be producing or reading.  Because every kernel of the
+// chain waits, completion is transitive: when a kernel passes its wait all earlier kernels have finished.
+// I2R_PDL=0 in the environment launches without the attribute (the device instructions are then no-ops).
+bool pdl_enabled();
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                              Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }

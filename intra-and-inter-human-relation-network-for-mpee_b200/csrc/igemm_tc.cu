@@ -67,6 +67,7 @@ __device__ __forceinline__ void run_tile(const i2r_conv_problem& P, const int ti
   while (ncols < static_cast<uint32_t>(Npad)) ncols <<= 1;
 
   // ---------------- setup
+  pdl_launch_dependents();
   if (tid == 0) {
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(bar_full + 8 * s, NPROD + 1);
@@ -89,6 +90,7 @@ __device__ __forceinline__ void run_tile(const i2r_conv_problem& P, const int ti
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();   // everything above is private set-up; activations, addends and the output are touched below
 
   if (warp < 4) {
     // =============================================================== A/B producers
@@ -352,6 +354,8 @@ __global__ void __launch_bounds__(NTHREADS) igemm_tc_kernel(const __grid_constan
 // Scalar check kernel (tests only): same problem struct and packed weights, one thread per output
 // pixel, fp32 accumulation of fp16 products.
 __global__ void __launch_bounds__(128) igemm_check_kernel(const __grid_constant__ ConvGroup G) {
+  pdl_launch_dependents();
+  pdl_wait();
   int tile = blockIdx.x;
   int pi = 0;
   while (pi < G.nprob - 1 && tile >= G.tile_end[pi]) ++pi;
@@ -476,7 +480,7 @@ static int launch_tc(const ConvGroup& G, int tiles, size_t smem, cudaStream_t st
     }
     attr_done = true;
   }
-  igemm_tc_kernel<STAGES><<<tiles, NTHREADS, smem, st>>>(G);
+  launch_pdl(igemm_tc_kernel<STAGES>, dim3(tiles), dim3(NTHREADS), smem, st, G);
   return check_launch("igemm_tc_kernel");
 }
 
@@ -505,7 +509,7 @@ extern "C" int i2r_conv_igemm(const i2r_conv_problem* probs, int nprob, int impl
   for (int i = nprob; i < I2R_MAX_GROUP; ++i) G.tile_end[i] = tiles;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (impl == 1) {
-    igemm_check_kernel<<<tiles, 128, 0, st>>>(G);
+    launch_pdl(igemm_check_kernel, dim3(tiles), dim3(128), 0, st, G);
     return check_launch("igemm_check_kernel");
   }
   if (impl != 0) {

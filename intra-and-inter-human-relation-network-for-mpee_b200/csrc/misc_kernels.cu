@@ -2,6 +2,8 @@
 // LayerNorm (+ fused positional add), elementwise add.  Warp-shuffle / 16-byte vectorised.
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
+#include <cstring>
 
 #include "i2r_common.cuh"
 
@@ -14,6 +16,15 @@ void set_error(const char* fmt, ...) {
   va_start(ap, fmt);
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
+}
+
+bool pdl_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("I2R_PDL");
+    v = (e != nullptr && strcmp(e, "0") == 0) ? 0 : 1;
+  }
+  return v != 0;
 }
 
 int check_launch(const char* what) {
@@ -71,6 +82,7 @@ __global__ void __launch_bounds__(256) stem_conv_kernel(const float* __restrict_
                                                         const float* __restrict__ bias, __half* __restrict__ y,
                                                         int NB, int H, int W, int split) {
   constexpr int K = CIN * 9;
+  pdl_launch_dependents();
   __shared__ __align__(16) float sw[K * 64];
   __shared__ __align__(16) float ssc[64];
   __shared__ __align__(16) float sbi[64];
@@ -87,6 +99,7 @@ __global__ void __launch_bounds__(256) stem_conv_kernel(const float* __restrict_
     ssc[tid] = scale[tid];
     sbi[tid] = bias[tid];
   }
+  pdl_wait();   // weights / scale / bias above are constants; the input and output below are not
   const int OH = H >> 1, OW = W >> 1;
   const int n = blockIdx.z;
   const int oy0 = blockIdx.y * STEM_TH, ox0 = blockIdx.x * STEM_TW;
@@ -164,6 +177,8 @@ __global__ void __launch_bounds__(256) stem_conv_kernel(const float* __restrict_
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) maxpool3x3s2_kernel(const __half* __restrict__ x, __half* __restrict__ y,
                                                            int NB, int H, int W, int C) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int OH = (H + 1) >> 1, OW = (W + 1) >> 1;
   const int cv = C >> 3;
   const int64_t total = static_cast<int64_t>(NB) * OH * OW * cv;
@@ -199,6 +214,8 @@ __global__ void __launch_bounds__(256) maxpool3x3s2_kernel(const __half* __restr
 // pair tensors: max over the VALUES hi + lo, re-split on store
 __global__ void __launch_bounds__(256) maxpool3x3s2_pair_kernel(const __half* __restrict__ x, __half* __restrict__ y,
                                                                 int NB, int H, int W, int C) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int OH = (H + 1) >> 1, OW = (W + 1) >> 1;
   const int cv = C >> 3;
   const int64_t total = static_cast<int64_t>(NB) * OH * OW * cv;
@@ -235,6 +252,8 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const __half* __restrict
                                                         const float* __restrict__ beta,
                                                         const __half* __restrict__ pos, __half* __restrict__ y,
                                                         __half* __restrict__ y2, int rows, int C, float eps, int split) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (warp >= rows) return;
@@ -305,6 +324,8 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const __half* __restrict
 
 __global__ void __launch_bounds__(256) add_f16_kernel(const uint4* __restrict__ a, const uint4* __restrict__ b,
                                                       uint4* __restrict__ y, int64_t n8) {
+  pdl_launch_dependents();
+  pdl_wait();
   for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n8;
        i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
     const uint4 qa = a[i], qb = b[i];
@@ -320,6 +341,8 @@ __global__ void __launch_bounds__(256) add_f16_kernel(const uint4* __restrict__ 
 // pair tensors: rows of [hi(C) | lo(C)]; y = (a_hi + a_lo) + (b_hi + b_lo), re-split
 __global__ void __launch_bounds__(256) add_pair_kernel(const __half* __restrict__ a, const __half* __restrict__ b,
                                                        __half* __restrict__ y, int64_t rows, int C) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int cv = C >> 3;
   for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < rows * cv;
        i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
@@ -341,6 +364,8 @@ template <bool PAIR>
 __global__ void __launch_bounds__(256) upsum_kernel(const __half* __restrict__ x0, const __half* __restrict__ t1,
                                                     const __half* __restrict__ t2, __half* __restrict__ y, int NB,
                                                     int H, int W, int C, int s1, int s2, int relu) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int cv = C >> 3;
   const int ld = PAIR ? 2 * C : C;
   const int64_t total = static_cast<int64_t>(NB) * H * W * cv;
@@ -416,9 +441,9 @@ extern "C" int i2r_stem_conv3x3s2(const float* x, const float* w, const float* s
   const dim3 grid((W / 2 + STEM_TW - 1) / STEM_TW, (H / 2 + STEM_TH - 1) / STEM_TH, NB);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (Cin == 3) {
-    stem_conv_kernel<3><<<grid, 256, 0, st>>>(x, w, scale, bias, static_cast<__half*>(y), NB, H, W, split);
+    launch_pdl(stem_conv_kernel<3>, dim3(grid), dim3(256), 0, st, x, w, scale, bias, static_cast<__half*>(y), NB, H, W, split);
   } else if (Cin == 1) {
-    stem_conv_kernel<1><<<grid, 256, 0, st>>>(x, w, scale, bias, static_cast<__half*>(y), NB, H, W, split);
+    launch_pdl(stem_conv_kernel<1>, dim3(grid), dim3(256), 0, st, x, w, scale, bias, static_cast<__half*>(y), NB, H, W, split);
   } else {
     set_error("i2r_stem_conv3x3s2: Cin=%d unsupported (1 or 3)", Cin);
     return I2R_E_UNSUPPORTED;
@@ -433,10 +458,10 @@ extern "C" int i2r_maxpool3x3s2(const void* x, void* y, int NB, int H, int W, in
   }
   const int64_t items = static_cast<int64_t>(NB) * ((H + 1) / 2) * ((W + 1) / 2) * (C / 8);
   if (split) {
-    maxpool3x3s2_pair_kernel<<<grid_for(items, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+    launch_pdl(maxpool3x3s2_pair_kernel, dim3(grid_for(items, 256)), dim3(256), 0, static_cast<cudaStream_t>(stream),
         static_cast<const __half*>(x), static_cast<__half*>(y), NB, H, W, C);
   } else {
-    maxpool3x3s2_kernel<<<grid_for(items, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+    launch_pdl(maxpool3x3s2_kernel, dim3(grid_for(items, 256)), dim3(256), 0, static_cast<cudaStream_t>(stream),
         static_cast<const __half*>(x), static_cast<__half*>(y), NB, H, W, C);
   }
   return check_launch("maxpool3x3s2_kernel");
@@ -449,7 +474,7 @@ extern "C" int i2r_layernorm(const void* x, const float* gamma, const float* bet
     return I2R_E_BADARG;
   }
   const int wpb = 8;
-  layernorm_kernel<<<(rows + wpb - 1) / wpb, wpb * 32, 0, static_cast<cudaStream_t>(stream)>>>(
+  launch_pdl(layernorm_kernel, dim3((rows + wpb - 1) / wpb), dim3(wpb * 32), 0, static_cast<cudaStream_t>(stream),
       static_cast<const __half*>(x), gamma, beta, static_cast<const __half*>(pos), static_cast<__half*>(y),
       static_cast<__half*>(y2), rows, C, eps, split);
   return check_launch("layernorm_kernel");
@@ -465,11 +490,11 @@ extern "C" int i2r_add_f16(const void* a, const void* b, void* y, int64_t n, int
       set_error("i2r_add_f16: pair tensors need C %% 8 == 0 and n a multiple of 2*C");
       return I2R_E_BADARG;
     }
-    add_pair_kernel<<<grid_for(n / 16, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+    launch_pdl(add_pair_kernel, dim3(grid_for(n / 16, 256)), dim3(256), 0, static_cast<cudaStream_t>(stream),
         static_cast<const __half*>(a), static_cast<const __half*>(b), static_cast<__half*>(y), n / (2 * split_c), split_c);
     return check_launch("add_pair_kernel");
   }
-  add_f16_kernel<<<grid_for(n / 8, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  launch_pdl(add_f16_kernel, dim3(grid_for(n / 8, 256)), dim3(256), 0, static_cast<cudaStream_t>(stream),
       static_cast<const uint4*>(a), static_cast<const uint4*>(b), static_cast<uint4*>(y), n / 8);
   return check_launch("add_f16_kernel");
 }
@@ -485,11 +510,11 @@ extern "C" int i2r_upsum(const void* x0, const void* t1, int shift1, const void*
   const int64_t items = static_cast<int64_t>(NB) * H * W * (C / 8);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (split) {
-    upsum_kernel<true><<<grid_for(items, 256), 256, 0, st>>>(static_cast<const __half*>(x0), static_cast<const __half*>(t1),
+    launch_pdl(upsum_kernel<true>, dim3(grid_for(items, 256)), dim3(256), 0, st, static_cast<const __half*>(x0), static_cast<const __half*>(t1),
                                                              static_cast<const __half*>(t2), static_cast<__half*>(y), NB,
                                                              H, W, C, shift1, shift2, relu);
   } else {
-    upsum_kernel<false><<<grid_for(items, 256), 256, 0, st>>>(static_cast<const __half*>(x0), static_cast<const __half*>(t1),
+    launch_pdl(upsum_kernel<false>, dim3(grid_for(items, 256)), dim3(256), 0, st, static_cast<const __half*>(x0), static_cast<const __half*>(t1),
                                                               static_cast<const __half*>(t2), static_cast<__half*>(y), NB,
                                                               H, W, C, shift1, shift2, relu);
   }
