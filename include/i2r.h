@@ -38,6 +38,9 @@ extern "C" {
 #define I2R_F_RELU 1u        /* clamp at 0 after scale/bias/addends                         */
 #define I2R_F_OUT_NCHW_F32 2u /* write fp32 NCHW (heatmap head) instead of fp16 NHWC         */
 #define I2R_F_OUT_F32 4u      /* write fp32 NHWC (row-major [pixels, Cout])                  */
+#define I2R_F_OUT_T16 16u     /* i2r_conv_halo only: write fp16 TRANSPOSED, y[c * out_pix_stride + p] (channel-major rows of
+                              * out_pix_stride pixels; with I2R_F_SPLIT the lo rows follow the Cout hi rows): the V^T operand of
+                              * i2r_attention_tc */
 /* Split-operand mode (the 1e-3 heatmap bar of the TransPose-H families needs ~22-bit operands): activations are
  * fp16 PAIRS -- a pixel holds 2*C channels, [0,C) = hi, [C,2C) = lo, value = hi + lo -- and a product is
  * x_hi*W_hi + x_lo*W_hi + x_hi*W_lo with fp32 accumulation, evaluated as ONE GEMM over K = [x_hi | x_lo | x_hi]
@@ -133,6 +136,19 @@ int i2r_attention_varlen(const void* q, const void* k, const void* v, void* out,
                          int ldo, int D, const int32_t* cu_seqlens, int nseq, int max_seqlen, int total_tokens,
                          float scale, void* workspace, int64_t workspace_bytes, int split, int q_lo, int k_lo,
                          int v_lo, int o_lo, void* stream);
+
+/* The same attention on the tcgen05 tensor cores (TMA-staged SWIZZLE_128B tiles, S/P/O in TMEM, one thread per
+ * query row for the streaming softmax); the product path of both encoders.  Differences in the operand contract:
+ *   - q, k: rows of D fp16 (split: 2*D -- the lo half DIRECTLY after the hi half), 16-byte aligned, strides % 8;
+ *   - vt:   V TRANSPOSED, fp16 [D (split: 2*D, lo rows after the hi rows)][ldvt tokens] -- what i2r_conv_halo writes
+ *           with I2R_F_OUT_T16; ldvt % 8 == 0;
+ *   - out:  [T, D] (split: hi at column 0, lo at column o_lo).
+ * Replaces F.multi_head_attention_forward's baddbmm / softmax / bmm (torch/nn/functional.py:6638-6650) as called
+ * from transpose_h.py:165-240 and attention.py:68-73.  D = 96. */
+int64_t i2r_attention_tc_workspace_bytes(int total_tokens, int D, int nseq, int max_seqlen);
+int i2r_attention_tc(const void* q, const void* k, const void* vt, void* out, int ldq, int ldk, int ldvt, int ldo,
+                     int D, const int32_t* cu_seqlens, int nseq, int max_seqlen, int total_tokens, float scale,
+                     void* workspace, int64_t workspace_bytes, int split, int o_lo, void* stream);
 
 /* y = LayerNorm(x) * gamma + beta over the last dim C (<= 256, multiple of 8), fp16 in/out, fp32
  * math; optional y2 = y + pos (the next layer's q/k input).  (interformer_pureMulti.py:206,:209) */

@@ -302,6 +302,24 @@ __global__ void __launch_bounds__(256) attention_merge_kernel(const float* __res
   }
 }
 
+// shared with attention_tc.cu (same partial format: un-normalised fp32 O, (max, sum) in the log2 domain)
+int attention_merge_launch(int HD, const float* opart, const float* mlpart, __half* out, int ldo, int rows, int nsplit,
+                           int o_lo, cudaStream_t st) {
+  const dim3 grid((rows + 7) / 8), block(256);
+  switch (HD) {
+    case 96:
+      launch_pdl(attention_merge_kernel<96>, grid, block, 0, st, opart, mlpart, out, ldo, rows, nsplit, o_lo);
+      break;
+    case 80:
+      launch_pdl(attention_merge_kernel<80>, grid, block, 0, st, opart, mlpart, out, ldo, rows, nsplit, o_lo);
+      break;
+    default:
+      set_error("attention_merge: head dim %d unsupported", HD);
+      return I2R_E_UNSUPPORTED;
+  }
+  return check_launch("attention_merge_kernel");
+}
+
 static int choose_nsplit(int nseq, int max_seqlen) {
   // enough CTAs for ~2 waves of 148 SMs, never more splits than key tiles, at most 8
   const int qtiles = (max_seqlen + ATT_BQ - 1) / ATT_BQ;

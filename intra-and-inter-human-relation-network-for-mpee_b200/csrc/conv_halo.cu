@@ -380,7 +380,16 @@ __device__ __forceinline__ void epilogue_role(const EpiArgs E, const int cta, co
               v[2 * i] = fmaxf(__uint_as_float(av[j][2 * i]) + ((f0.x + g0.x) + (f1.x + g1.x)), lo);
               v[2 * i + 1] = fmaxf(__uint_as_float(av[j][2 * i + 1]) + ((f0.y + g0.y) + (f1.y + g1.y)), lo);
             }
-            if (!(E.flags & (I2R_F_OUT_NCHW_F32 | I2R_F_OUT_F32))) {
+            if (E.flags & I2R_F_OUT_T16) {
+              // channel-major rows: lanes hold consecutive pixels, so each 2-byte store instruction is coalesced
+              __half* Y = reinterpret_cast<__half*>(E.y);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const __half h = __float2half_rn(v[i]);
+                Y[static_cast<int64_t>(c0 + i) * E.out_pix_stride + p] = h;
+                if (split) Y[static_cast<int64_t>(E.Cout + c0 + i) * E.out_pix_stride + p] = __float2half_rn(v[i] - __half2float(h));
+              }
+            } else if (!(E.flags & (I2R_F_OUT_NCHW_F32 | I2R_F_OUT_F32))) {
               uint4 q;
               q.x = pack_h2(v[0], v[1]);
               q.y = pack_h2(v[2], v[3]);
@@ -683,7 +692,8 @@ __global__ void __launch_bounds__(T_THREADS, 1) conv_halo_kernel(const __grid_co
     const int ew = warp - 4;
     const int n8 = (P.Cout + 7) >> 3, half8 = (n8 + 1) >> 1;   // chunks holding real channels, split over the warp pair
     const int cb = (ew >> 2) ? half8 : 0, ce = (ew >> 2) ? n8 : half8;
-    if ((P.flags & (I2R_F_OUT_NCHW_F32 | I2R_F_OUT_F32 | I2R_F_SPLIT)) || (P.Cout & 7) || dbg != 0 || ce == cb) {
+    if ((P.flags & (I2R_F_OUT_NCHW_F32 | I2R_F_OUT_F32 | I2R_F_SPLIT | I2R_F_OUT_T16)) || (P.Cout & 7) || dbg != 0 ||
+        ce == cb) {
       epilogue_role<1>(E, cta, sbase, tmem_base, ncols, Npad, ew, warp & 3, lane, tr, trace_cap, dbg);
     } else if (P.add1 != nullptr) {
       epilogue_fast_dispatch<2>(E, cta, sbase, tmem_base, ncols, cb, ce, ew, warp & 3, lane, tr, trace_cap);
@@ -708,7 +718,7 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-static EncodeTiledFn get_encode() {
+EncodeTiledFn get_encode() {   // also used by attention_tc.cu
   static EncodeTiledFn fn = nullptr;
   static bool tried = false;
   if (!tried) {

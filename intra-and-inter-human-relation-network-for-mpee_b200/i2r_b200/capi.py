@@ -12,10 +12,11 @@ F_RELU = 1
 F_OUT_NCHW_F32 = 2
 F_OUT_F32 = 4
 F_SPLIT = 8
+F_OUT_T16 = 16
 
 EXPORTS = [
     "i2r_version", "i2r_last_error", "i2r_device_check", "i2r_sm_count", "i2r_conv_igemm", "i2r_conv_halo", "i2r_conv_halo_supported", "i2r_debug_trace", "i2r_debug_flags",
-    "i2r_sizeof_conv_problem", "i2r_stem_conv3x3s2", "i2r_maxpool3x3s2", "i2r_attention_varlen", "i2r_attention_workspace_bytes", "i2r_layernorm", "i2r_add_f16", "i2r_upsum",
+    "i2r_sizeof_conv_problem", "i2r_stem_conv3x3s2", "i2r_maxpool3x3s2", "i2r_attention_varlen", "i2r_attention_workspace_bytes", "i2r_attention_tc", "i2r_attention_tc_workspace_bytes", "i2r_layernorm", "i2r_add_f16", "i2r_upsum",
 ]
 
 
@@ -73,6 +74,10 @@ def load():
                                              i32, i32, i32, i32, i32, vp]
         lib.i2r_attention_workspace_bytes.argtypes = [i32, i32, i32, i32]
         lib.i2r_attention_workspace_bytes.restype = i64
+        lib.i2r_attention_tc.argtypes = [vp, vp, vp, vp, i32, i32, i32, i32, i32, vp, i32, i32, i32, f32, vp, i64,
+                                         i32, i32, vp]
+        lib.i2r_attention_tc_workspace_bytes.argtypes = [i32, i32, i32, i32]
+        lib.i2r_attention_tc_workspace_bytes.restype = i64
         lib.i2r_layernorm.argtypes = [vp, vp, vp, vp, vp, vp, i32, i32, f32, i32, vp]
         lib.i2r_add_f16.argtypes = [vp, vp, vp, i64, i32, vp]
         lib.i2r_upsum.argtypes = [vp, vp, i32, vp, i32, vp, i32, i32, i32, i32, i32, i32, vp]

@@ -136,12 +136,18 @@ class Runner:
                 out = torch.empty((nb, L.cout, ohf, owf), dtype=torch.float32, device=x.device)
             elif out_mode == "nhwc32":
                 out = torch.empty((nb, ohf, owf, L.cout), dtype=torch.float32, device=x.device)
+            elif out_mode == "t16":      # channel-major [cw, pixels] (halo kernel only): V^T for the tcgen05 attention
+                out = torch.empty((cw, nb * ohf * owf), dtype=torch.float16, device=x.device)
             else:
                 raise ValueError(out_mode)
         if out_mode == "nchw32":
             flags |= capi.F_OUT_NCHW_F32
             out_pix = 0
             assert out.is_contiguous()
+        elif out_mode == "t16":
+            flags |= capi.F_OUT_T16
+            assert out.is_contiguous() and out.shape[1] == nb * ohf * owf
+            out_pix = out.stride(0)
         else:
             if out_mode == "nhwc32":
                 flags |= capi.F_OUT_F32
@@ -247,14 +253,14 @@ class Runner:
         self.launch([p])
         return out.view(x2d.shape[0], -1)
 
-    def linear_problem(self, L, x2d, add0=None, relu=None):
+    def linear_problem(self, L, x2d, add0=None, relu=None, out_mode="nhwc16"):
         t, c = x2d.shape
         assert x2d.stride(1) == 1
         ld = x2d.stride(0)
         x4 = x2d.as_strided((1, t, 1, c), (t * ld, ld, ld, 1))
         a4 = add0.as_strided((1, t, 1, add0.shape[1]), (t * add0.stride(0), add0.stride(0), add0.stride(0), 1)) \
             if add0 is not None else None
-        return self.problem(L, x4, add0=a4, relu=relu)
+        return self.problem(L, x4, add0=a4, relu=relu, out_mode=out_mode)
 
     # ------------------------------------------------------------------ small kernels
     def stem(self, x, w, scale, bias, cout):
@@ -328,4 +334,21 @@ class Runner:
                                                   int(lo is not None), ql, kl, vl, d, _stream_ptr()),
                    "i2r_attention_varlen")
         self.launches += 1
+        return out
+
+    def attention_tc(self, q, k, vt, cu_seqlens, max_seqlen, scale, split=False):
+        """tcgen05 attention.  q, k: fp16 2-D views [T, D] (split: [T, 2D] pairs, lo directly after hi), row strides
+        multiples of 8; vt: V transposed [D or 2D, T] (Runner.problem(out_mode="t16")).  Returns [T, D] ([T, 2D])."""
+        t, w = q.shape
+        d = w // 2 if split else w
+        assert k.shape == q.shape and vt.shape == (w, t) and vt.stride(1) == 1 and q.stride(1) == 1 and k.stride(1) == 1
+        out = torch.empty((t, w), dtype=torch.float16, device=q.device)
+        nseq = cu_seqlens.numel() - 1
+        ws_bytes = int(self.lib.i2r_attention_tc_workspace_bytes(t, d, nseq, max_seqlen))
+        ws = torch.empty(max(ws_bytes, 16), dtype=torch.uint8, device=q.device) if ws_bytes else None
+        capi.check(self.lib.i2r_attention_tc(q.data_ptr(), k.data_ptr(), vt.data_ptr(), out.data_ptr(), q.stride(0),
+                                              k.stride(0), vt.stride(0), out.stride(0), d, cu_seqlens.data_ptr(), nseq,
+                                              max_seqlen, t, scale, ws.data_ptr() if ws is not None else None,
+                                              ws_bytes, int(split), d, _stream_ptr()), "i2r_attention_tc")
+        self.launches += 1 + (1 if ws_bytes else 0)
         return out

@@ -76,6 +76,9 @@ class EmuRunner(Runner):
             out[:, :, fy, fx] = v.permute(0, 3, 1, 2)
         elif p.flags & capi.F_OUT_F32:
             out[:, fy, fx, :] = v
+        elif p.flags & capi.F_OUT_T16:
+            vv = split_pair(v) if split else v.half()
+            out.copy_(vv.reshape(-1, vv.shape[-1]).t())
         elif split:
             out[:, fy, fx, :] = split_pair(v)
         else:

@@ -1,0 +1,59 @@
+"""Per-launch GPU time of an eager forward queued behind a spin kernel (host launch gaps excluded), grouped by phase.
+Events bracket every Runner entry point; PDL overlap between neighbouring kernels is attributed to the later one."""
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import paths  # noqa: E402,F401
+
+sys.path.insert(0, os.path.join(paths.REPO, "tests"))
+from helpers import build_model, inputs_for  # noqa: E402
+from i2r_b200 import ops  # noqa: E402
+
+yaml = sys.argv[1] if len(sys.argv) > 1 else "coco/interformer_coco_w48_pure_en6.yaml"
+images, persons = (int(sys.argv[2]), int(sys.argv[3])) if len(sys.argv) > 3 else (8, 4)
+cfg, model, sd = build_model(yaml)
+model = model.cuda()
+model.use_cuda_graph = False
+length = [persons] * images
+x, pm = inputs_for(length)
+x, pm = x.cuda(), pm.cuda()
+model(x, pm, length)
+torch.cuda.synchronize()
+
+records = []
+
+
+def wrap(name):
+    orig = getattr(ops.Runner, name)
+
+    def f(self, *a, **kw):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        out = orig(self, *a, **kw)
+        e1.record()
+        desc = name
+        if name == "launch":
+            desc = "conv[" + ",".join("%dx%d:%d>%d%s" % (p.IH, p.IW, p.Cin, p.Cout, "k%d" % p.ntaps) for p in a[0]) + "]"
+        records.append((desc, e0, e1))
+        return out
+    setattr(ops.Runner, name, f)
+
+
+for n in ("launch", "stem", "maxpool", "layernorm", "add", "upsum", "attention"):
+    wrap(n)
+reps = 3
+tot = {}
+for rep in range(reps):
+    records.clear()
+    torch.cuda._sleep(40_000_000)
+    model(x, pm, length)
+    torch.cuda.synchronize()
+    for i, (d, a, b) in enumerate(records):
+        tot.setdefault(i, [d, 0.0])[1] += a.elapsed_time(b) * 1e3 / reps
+total = sum(v[1] for v in tot.values())
+print("eager spin-parked forward: %.1f us over %d launches (%s, %d crops)" % (total, len(tot), yaml, sum(length)))
+for i in sorted(tot):
+    print("%3d %8.1f us  %s" % (i, tot[i][1], tot[i][0][:150]))
