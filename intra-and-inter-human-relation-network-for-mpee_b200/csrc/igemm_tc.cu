@@ -499,6 +499,10 @@ extern "C" int i2r_conv_igemm(const i2r_conv_problem* probs, int nprob, int impl
   for (int i = 0; i < nprob; ++i) {
     int rc = validate(probs[i], i);
     if (rc) return rc;
+    if (probs[i].flags & I2R_F_OUT_T16) {
+      set_error("i2r_conv_igemm: problem %d asks for transposed output (I2R_F_OUT_T16), which only i2r_conv_halo writes", i);
+      return I2R_E_UNSUPPORTED;
+    }
     G.p[i] = probs[i];
     const int64_t M = static_cast<int64_t>(probs[i].NB) * probs[i].OH * probs[i].OW;
     tiles += static_cast<int>((M + BM - 1) / BM);

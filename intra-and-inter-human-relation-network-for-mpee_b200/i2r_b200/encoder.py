@@ -25,6 +25,11 @@ class EncoderLayerProgram:
         self.d = d
         self.qk = _linear_layer(w[: 2 * d], b[: 2 * d], device=device)
         self.v = _linear_layer(w[2 * d:], b[2 * d:], device=device)
+        if self.qk.split:
+            # separate q / k projections: each output row is then one contiguous (hi | lo) pair, the operand
+            # layout of the tcgen05 attention kernel
+            self.q = _linear_layer(w[:d], b[:d], device=device)
+            self.k = _linear_layer(w[d: 2 * d], b[d: 2 * d], device=device)
         self.out = _linear_layer(sd[prefix + ".self_attn.out_proj.weight"], sd[prefix + ".self_attn.out_proj.bias"],
                                  device=device)
         self.ff1 = _linear_layer(sd[prefix + ".linear1.weight"], sd[prefix + ".linear1.bias"], relu=True,
@@ -53,18 +58,19 @@ class EncoderProgram:
         split = self.layers[0].qk.split
         sp = r.add(src, pos) if pos is not None else src
         for li, L in enumerate(self.layers):
-            pq, _ = r.linear_problem(L.qk, sp)
-            pv, _ = r.linear_problem(L.v, src)
-            r.launch([pq, pv])
-            if split:     # qk: [T, (q_hi k_hi | q_lo k_lo)], v: [T, (v_hi | v_lo)]
-                qk = pq._keep[4].view(-1, 4 * d)
-                v = pv._keep[4].view(-1, 2 * d)
-                a = r.attention(qk[:, :d], qk[:, d:2 * d], v[:, :d], cu_seqlens, max_seqlen, self.scale,
-                                lo=(2 * d, 2 * d, d))
+            # V is written transposed (channel-major): the K-major B operand of the P.V product
+            pv, vt = r.linear_problem(L.v, src, out_mode="t16")
+            if split:     # q, k: [T, (hi | lo)]; vt: [(hi rows | lo rows), T]
+                pq, q = r.linear_problem(L.q, sp)
+                pk, k = r.linear_problem(L.k, sp)
+                r.launch([pq, pk, pv])
+                a = r.attention_tc(q.view(-1, 2 * d), k.view(-1, 2 * d), vt, cu_seqlens, max_seqlen, self.scale,
+                                   split=True)
             else:
-                qk = pq._keep[4].view(-1, 2 * d)
-                v = pv._keep[4].view(-1, d)
-                a = r.attention(qk[:, :d], qk[:, d:], v, cu_seqlens, max_seqlen, self.scale)
+                pq, qk = r.linear_problem(L.qk, sp)
+                r.launch([pq, pv])
+                qk = qk.view(-1, 2 * d)
+                a = r.attention_tc(qk[:, :d], qk[:, d:], vt, cu_seqlens, max_seqlen, self.scale)
             x1 = r.linear(L.out, a, add0=src)
             s1, _ = r.layernorm(x1, L.n1[0], L.n1[1])
             h = r.linear(L.ff1, s1)

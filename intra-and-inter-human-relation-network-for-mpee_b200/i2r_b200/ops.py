@@ -217,7 +217,11 @@ class Runner:
             e0.record()
         tma, gen = [], []
         for p in problems:
-            (tma if (self.use_tma and self.lib.i2r_conv_halo_supported(ctypes.byref(p))) else gen).append(p)
+            t16 = bool(p.flags & capi.F_OUT_T16)      # transposed output exists in the halo kernel only
+            halo = (self.use_tma or t16) and self.lib.i2r_conv_halo_supported(ctypes.byref(p))
+            if t16 and not halo:
+                raise capi.I2RError("transposed (t16) output needs a problem the halo kernel supports")
+            (tma if halo else gen).append(p)
         for group, fn in ((tma, "tma"), (gen, "igemm")):
             for i in range(0, len(group), capi.I2R_MAX_GROUP):
                 chunk = group[i:i + capi.I2R_MAX_GROUP]

@@ -141,3 +141,23 @@ class EmuRunner(Runner):
                 out[a:b] = split_pair(s @ (vh[a:b] + vl[a:b]))
         self.launches += 1
         return out
+
+    def attention_tc(self, q, k, vt, cu_seqlens, max_seqlen, scale, split=False):
+        t, w = q.shape
+        d = w // 2 if split else w
+        v = vt.t()
+        out = torch.empty(t, w, dtype=torch.float16)
+        cu = cu_seqlens.tolist()
+        for a, b in zip(cu[:-1], cu[1:]):
+            assert b - a <= max_seqlen
+            if not split:
+                s = torch.softmax(q[a:b].float() @ k[a:b].float().t() * scale, dim=-1)
+                out[a:b] = (s.half().float() @ v[a:b].float()).half()
+            else:
+                qh, ql = q[a:b, :d].float(), q[a:b, d:].float()
+                kh, kl = k[a:b, :d].float(), k[a:b, d:].float()
+                sc = (qh + ql) @ kh.t() + qh @ kl.t()                               # three-term score product
+                s = torch.softmax(sc * scale, dim=-1).half().float()                # probabilities stay fp16
+                out[a:b] = split_pair(s @ (v[a:b, :d].float() + v[a:b, d:].float()))
+        self.launches += 1
+        return out

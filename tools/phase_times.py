@@ -42,7 +42,7 @@ def wrap(name):
     setattr(ops.Runner, name, f)
 
 
-for n in ("launch", "stem", "maxpool", "layernorm", "add", "upsum", "attention"):
+for n in ("launch", "stem", "maxpool", "layernorm", "add", "upsum", "attention", "attention_tc"):
     wrap(n)
 reps = 3
 tot = {}
