@@ -150,6 +150,19 @@ int i2r_attention_tc(const void* q, const void* k, const void* vt, void* out, in
                      int D, const int32_t* cu_seqlens, int nseq, int max_seqlen, int total_tokens, float scale,
                      void* workspace, int64_t workspace_bytes, int split, int o_lo, void* stream);
 
+/* Fused tail of one post-norm encoder layer (everything after the attention) for d_model 96 / dim_feedforward 192:
+ *   x1 = attn W_o^T + b_o + src;  s1 = LN1(x1);  x2 = relu(s1 W_1^T + b_1) W_2^T + b_2 + s1;  out = LN2(x2);
+ *   out_pos = out + pos (optional: the q/k input of the next layer).
+ * attn / src / pos / out / out_pos: fp16 [T, 96] (split: [T, 192] pairs, lo directly after hi) with row strides
+ * ld_attn / ld_src / ld (pos, out and out_pos share ld).  wimg / params: i2r_b200/packing.py pack_encoder_tail
+ * (i2r_encoder_tail_weight_bytes(split) bytes of pre-swizzled fp16 weights; 768 fp32 biases and LayerNorm
+ * parameters).  Replaces TransformerEncoderLayer.forward_post after self_attn (lib/models/transpose_h.py:205-222,
+ * lib/models/attention.py:74-82, lib/models/interformer_pureMulti.py:205-213). */
+int64_t i2r_encoder_tail_weight_bytes(int split);
+int i2r_encoder_tail(const void* attn, int ld_attn, const void* src, int ld_src, const void* pos, void* out,
+                     void* out_pos, int ld, const void* wimg, const float* params, int T, int d_model, int dim_ff,
+                     float eps, int split, void* stream);
+
 /* y = LayerNorm(x) * gamma + beta over the last dim C (<= 256, multiple of 8), fp16 in/out, fp32
  * math; optional y2 = y + pos (the next layer's q/k input).  (interformer_pureMulti.py:206,:209) */
 int i2r_layernorm(const void* x, const float* gamma, const float* beta, const void* pos, void* y, void* y2,

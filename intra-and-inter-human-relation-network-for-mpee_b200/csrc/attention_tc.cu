@@ -18,61 +18,14 @@
 //
 // Split-operand mode (I2R_F_SPLIT): rows of q and k are fp16 pairs [hi | lo] (lo directly after hi), V^T has the lo
 // channel rows after the hi rows; S = q_hi k_hi + q_lo k_hi + q_hi k_lo (three MMAs per K step), O += P v_hi + P v_lo.
-#include <cuda.h>
-
-#include "i2r_common.cuh"
+#include "i2r_tma.cuh"
 
 namespace i2r {
 
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-EncodeTiledFn get_encode();   // conv_halo.cu
 int attention_merge_launch(int HD, const float* opart, const float* mlpart, __half* out, int ldo, int rows, int nsplit,
                            int o_lo, cudaStream_t st);   // attention.cu
 
 constexpr int TC_THREADS = 320;
-constexpr int TC_CH_BYTES = 128 * 128;   // one SW128 chunk: 128 rows x 64 fp16
-
-__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2,%3}], [%4];"
-      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(bar)
-      : "memory");
-}
-__device__ __forceinline__ void umma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc,
-                                            uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
-      ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,"
-      "%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
-        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-      : "r"(taddr)
-      : "memory");
-}
-__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
-  asm volatile(
-      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"
-      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
-        "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
-      : "memory");
-}
-__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
-__device__ __forceinline__ float ex2(float x) {
-  float y;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
 
 struct TcArgs {
   __half* out;
@@ -94,9 +47,6 @@ struct TcCfg {
   static constexpr int V_BYTES = 2 * V_CH;
   static constexpr int SMEM = 2 * Q_TILE + K_BYTES + V_BYTES + 256 + 1024;   // + barriers + alignment slack
 };
-
-// byte offset of K step `s` (16 channels; s counts over the [hi | lo] row) inside a chunked q / k tile
-__device__ __forceinline__ constexpr uint32_t kstep_off(int s) { return (s >> 2) * TC_CH_BYTES + (s & 3) * 32; }
 
 template <int HD, bool SPLIT>
 __device__ __forceinline__ void issue_qk(uint32_t d_tmem, uint32_t q_addr, uint32_t k_addr, uint32_t idesc) {
@@ -396,7 +346,7 @@ static int tc_choose_nsplit(int nseq, int max_seqlen, int sms) {
   return best;
 }
 
-static int tc_sms() {
+int device_sms() {
   static int sms = 0;
   if (sms == 0) {
     int dev = 0;
@@ -407,7 +357,7 @@ static int tc_sms() {
   return sms;
 }
 
-static int encode_2d(CUtensorMap* map, const void* base, uint64_t inner, uint64_t outer, uint64_t row_stride_elems,
+int encode_2d(CUtensorMap* map, const void* base, uint64_t inner, uint64_t outer, uint64_t row_stride_elems,
                      uint32_t box_inner, uint32_t box_outer) {
   EncodeTiledFn enc = get_encode();
   if (!enc) {
@@ -444,7 +394,7 @@ static int launch_attention_tc(const void* q, const void* k, const void* vt, voi
     }
     attr_done = true;
   }
-  int nsplit = tc_choose_nsplit(nseq, max_seqlen, tc_sms());
+  int nsplit = tc_choose_nsplit(nseq, max_seqlen, device_sms());
   const int64_t need = static_cast<int64_t>(total_tokens) * nsplit * (HD + 2) * 4;
   if (nsplit > 1 && (ws == nullptr || ws_bytes < need)) nsplit = 1;
   CUtensorMap mq, mk, mv;
@@ -472,7 +422,7 @@ static int launch_attention_tc(const void* q, const void* k, const void* vt, voi
 }  // namespace i2r
 
 extern "C" int64_t i2r_attention_tc_workspace_bytes(int total_tokens, int D, int nseq, int max_seqlen) {
-  const int ns = i2r::tc_choose_nsplit(nseq, max_seqlen, i2r::tc_sms());
+  const int ns = i2r::tc_choose_nsplit(nseq, max_seqlen, i2r::device_sms());
   return ns > 1 ? static_cast<int64_t>(total_tokens) * ns * (D + 2) * 4 : 0;
 }
 

@@ -10,7 +10,7 @@ import math
 
 import torch
 
-from .ops import ConvLayer
+from .ops import ConvLayer, EncoderTailParams
 
 
 def _linear_layer(weight, bias, relu=False, device="cuda"):
@@ -35,6 +35,13 @@ class EncoderLayerProgram:
         self.ff1 = _linear_layer(sd[prefix + ".linear1.weight"], sd[prefix + ".linear1.bias"], relu=True,
                                  device=device)
         self.ff2 = _linear_layer(sd[prefix + ".linear2.weight"], sd[prefix + ".linear2.bias"], device=device)
+        self.tail = None
+        if d == 96 and sd[prefix + ".linear1.weight"].shape[0] == 192:
+            self.tail = EncoderTailParams(
+                sd[prefix + ".self_attn.out_proj.weight"], sd[prefix + ".self_attn.out_proj.bias"],
+                sd[prefix + ".linear1.weight"], sd[prefix + ".linear1.bias"], sd[prefix + ".linear2.weight"],
+                sd[prefix + ".linear2.bias"], sd[prefix + ".norm1.weight"], sd[prefix + ".norm1.bias"],
+                sd[prefix + ".norm2.weight"], sd[prefix + ".norm2.bias"], device=device, split=self.qk.split)
         self.n1 = (sd[prefix + ".norm1.weight"].float().to(device), sd[prefix + ".norm1.bias"].float().to(device))
         self.n2 = (sd[prefix + ".norm2.weight"].float().to(device), sd[prefix + ".norm2.bias"].float().to(device))
 
@@ -71,6 +78,11 @@ class EncoderProgram:
                 r.launch([pq, pv])
                 qk = qk.view(-1, 2 * d)
                 a = r.attention_tc(qk[:, :d], qk[:, d:], vt, cu_seqlens, max_seqlen, self.scale)
+            last = li == len(self.layers) - 1
+            if L.tail is not None:
+                src, sp2 = r.encoder_tail(L.tail, a, src, pos=None if (last or pos is None) else pos)
+                sp = sp2 if sp2 is not None else src
+                continue
             x1 = r.linear(L.out, a, add0=src)
             s1, _ = r.layernorm(x1, L.n1[0], L.n1[1])
             h = r.linear(L.ff1, s1)

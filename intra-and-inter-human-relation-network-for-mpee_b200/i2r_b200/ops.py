@@ -356,3 +356,32 @@ class Runner:
                                               ws_bytes, int(split), d, _stream_ptr()), "i2r_attention_tc")
         self.launches += 1 + (1 if ws_bytes else 0)
         return out
+
+    def encoder_tail(self, tail, attn, src, pos=None, eps=1e-5):
+        """Fused out-proj + residual + LN1 + FFN + residual + LN2 (+ pos).  tail: EncoderTailParams; attn / src / pos:
+        fp16 [T, 96] ([T, 192] pairs in split mode).  Returns (src_next, src_next + pos or None)."""
+        t, w = attn.shape
+        assert src.shape == (t, w) and attn.stride(1) == 1 and src.stride(1) == 1 and w == (192 if tail.split else 96)
+        out = torch.empty((t, w), dtype=torch.float16, device=attn.device)
+        out_pos = torch.empty_like(out) if pos is not None else None
+        if pos is not None:
+            assert pos.shape == (t, w) and pos.is_contiguous()
+        capi.check(self.lib.i2r_encoder_tail(attn.data_ptr(), attn.stride(0), src.data_ptr(), src.stride(0),
+                                              pos.data_ptr() if pos is not None else None, out.data_ptr(),
+                                              out_pos.data_ptr() if out_pos is not None else None, w,
+                                              tail.wimg.data_ptr(), tail.params.data_ptr(), t, 96, 192, eps,
+                                              int(tail.split), _stream_ptr()), "i2r_encoder_tail")
+        self.launches += 1
+        return out, out_pos
+
+
+class EncoderTailParams:
+    """Device-resident operand image of i2r_encoder_tail for one encoder layer."""
+
+    def __init__(self, w_out, b_out, w1, b1, w2, b2, g1, be1, g2, be2, device="cuda", split=None):
+        from .packing import pack_encoder_tail
+        self.split = _SPLIT_DEFAULT[0] if split is None else bool(split)
+        self.host = tuple(t.detach().float().cpu() for t in (w_out, b_out, w1, b1, w2, b2, g1, be1, g2, be2))
+        img, params = pack_encoder_tail(*self.host, split=self.split)
+        self.wimg = img.to(device)
+        self.params = params.to(device)

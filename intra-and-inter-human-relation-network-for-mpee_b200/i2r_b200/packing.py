@@ -156,3 +156,38 @@ def merge_pair(t):
     """fp16 [..., 2C] (hi | lo) -> fp32 [..., C]."""
     c = t.shape[-1] // 2
     return t[..., :c].float() + t[..., c:].float()
+
+
+def _pack_rows_sw128(m):
+    """fp32 [N, K] (N % 8 == 0) -> fp16 [ceil(K/64), N, 64]: K-major SWIZZLE_128B chunks (16-byte groups XOR row & 7)."""
+    n, k = m.shape
+    nch = (k + KC - 1) // KC
+    mm = torch.zeros(n, nch * KC)
+    mm[:, :k] = m.float()
+    mm = mm.reshape(n, nch, 8, 8).to(torch.float16)
+    out = torch.zeros(nch, n, 8, 8, dtype=torch.float16)
+    rows = torch.arange(n)
+    for c in range(8):
+        out[:, rows, c ^ (rows & 7), :] = mm[:, :, c, :].permute(1, 0, 2)
+    return out.reshape(nch, n, 64)
+
+
+def pack_encoder_tail(w_out, b_out, w1, b1, w2, b2, g1, be1, g2, be2, split):
+    """Operand image of i2r_encoder_tail (csrc/encoder_tail.cu): five [96 x 96] matrices W_o, W_1[0:96], W_1[96:192],
+    W_2[:, 0:96], W_2[:, 96:192] as SWIZZLE_128B K-major chunks (split: K = [W_hi | W_lo]) and the fp32 vector
+    [b_o | b_1 | b_2 | gamma1 | beta1 | gamma2 | beta2]."""
+    d = w_out.shape[0]
+    assert w_out.shape == (d, d) and w1.shape == (2 * d, d) and w2.shape == (d, 2 * d) and d == 96
+    mats = [w_out, w1[:d], w1[d:], w2[:, :d], w2[:, d:]]
+    blocks = []
+    for m in mats:
+        m = m.float()
+        if split:
+            hi = m.to(torch.float16).float()
+            lo = (m - hi).to(torch.float16).float()
+            m = torch.cat([hi, lo], dim=1)
+        blocks.append(_pack_rows_sw128(m).reshape(-1))
+    img = torch.cat(blocks).contiguous()
+    params = torch.cat([v.float().reshape(-1) for v in (b_out, b1, b2, g1, be1, g2, be2)]).contiguous()
+    assert params.numel() == 768
+    return img, params

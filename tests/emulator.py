@@ -161,3 +161,19 @@ class EmuRunner(Runner):
                 out[a:b] = split_pair(s @ (v[a:b, :d].float() + v[a:b, d:].float()))
         self.launches += 1
         return out
+
+    def encoder_tail(self, tail, attn, src, pos=None, eps=1e-5):
+        w_out, b_out, w1, b1, w2, b2, g1, be1, g2, be2 = tail.host
+
+        def q(m):       # operand precision of the kernel: fp16, or the (hi + lo) pair in split mode
+            hi = m.half().float()
+            return hi + (m - hi).half().float() if tail.split else hi
+
+        def act(v):     # activations handed from an epilogue to the next GEMM through shared memory
+            return merge_pair(split_pair(v)) if tail.split else v.half().float()
+        a, s0 = self._rd(attn), self._rd(src)
+        s1 = act(F.layer_norm(a @ q(w_out).t() + b_out + s0, (96,), g1, be1, eps))
+        h = act(F.relu(s1 @ q(w1).t() + b1))
+        y = F.layer_norm(h @ q(w2).t() + b2 + s1, (96,), g2, be2, eps)
+        self.launches += 1
+        return self._wr(y), (self._wr(y + self._rd(pos)) if pos is not None else None)

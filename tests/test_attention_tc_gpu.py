@@ -129,3 +129,39 @@ def test_linear_transposed_output(dev, tc, split):
     err = float((val - ref).abs().max())
     _report(test="linear_t16", split=split, err=err)
     assert err <= (2e-5 if split else 4e-3), err
+
+
+@pytest.mark.parametrize("split", [False, True])
+@pytest.mark.parametrize("t,with_pos", [(1000, True), (128, False), (6144, True)])
+def test_encoder_tail(dev, tc, split, t, with_pos):
+    """Fused out-proj + residual + LN1 + FFN + residual + LN2 (+ pos) vs float64 torch on the same operands
+    (TransformerEncoderLayer.forward_post after self_attn, lib/models/transpose_h.py:205-222)."""
+    import torch.nn.functional as F
+    from i2r_b200.ops import EncoderTailParams
+    from i2r_b200.packing import merge_pair, split_pair
+    g = torch.Generator().manual_seed(11 + t)
+    d, f = 96, 192
+
+    def u(*shape, s=1.0):
+        return (torch.rand(*shape, generator=g) * 2 - 1) * s
+    w_out, b_out = u(d, d, s=d ** -0.5), u(d, s=0.1)
+    w1, b1 = u(f, d, s=d ** -0.5), u(f, s=0.1)
+    w2, b2 = u(d, f, s=f ** -0.5), u(d, s=0.1)
+    g1, be1, g2, be2 = 1 + u(d, s=0.3), u(d, s=0.1), 1 + u(d, s=0.3), u(d, s=0.1)
+    attn32, src32, pos32 = (torch.randn(t, d, generator=g) for _ in range(3))
+    enc = split_pair if split else (lambda v: v.half())
+    dec = (lambda v: merge_pair(v).double()) if split else (lambda v: v.double())
+    attn, src, pos = enc(attn32), enc(src32), enc(pos32)
+    tail = EncoderTailParams(w_out, b_out, w1, b1, w2, b2, g1, be1, g2, be2, device=dev, split=split)
+    out, out_pos = tc.encoder_tail(tail, attn.to(dev), src.to(dev), pos=pos.to(dev) if with_pos else None)
+    torch.cuda.synchronize()
+    D = torch.float64
+    s1 = F.layer_norm(dec(attn) @ w_out.to(D).t() + b_out.to(D) + dec(src), (d,), g1.to(D), be1.to(D), 1e-5)
+    h = F.relu(s1 @ w1.to(D).t() + b1.to(D))
+    ref = F.layer_norm(h @ w2.to(D).t() + b2.to(D) + s1, (d,), g2.to(D), be2.to(D), 1e-5)
+    err = float((dec(out.cpu()) - ref).abs().max())
+    err_pos = float((dec(out_pos.cpu()) - (ref + dec(pos))).abs().max()) if with_pos else 0.0
+    _report(test="encoder_tail", split=split, t=t, err=err, err_pos=err_pos)
+    tol = 3e-5 if split else 1.5e-2      # fp16 weights / activations through three GEMMs and two LayerNorms
+    assert (out_pos is None) == (not with_pos)
+    assert err <= tol and err_pos <= 2 * tol, (err, err_pos)
