@@ -117,6 +117,14 @@ int i2r_conv_halo(const i2r_conv_problem* probs, int nprob, void* stream);
 int i2r_stem_conv3x3s2(const float* x, const float* w, const float* scale, const float* bias, void* y,
                        int NB, int Cin, int H, int W, int Cout, int split, void* stream);
 
+/* The same layer on the tensor cores (the product path; the SIMT entry point above is the check implementation):
+ * a 128-pixel tile is one implicit GEMM [128 x 32] x [32 x 64]; input and weights travel as fp16 (hi, lo) pairs so
+ * the result keeps fp32-level accuracy.  wimg: i2r_stem_tc_weight_bytes() bytes from i2r_b200/packing.py
+ * pack_stem_tc (BatchNorm scale folded into the weights); bias: fp32 [64]. */
+int64_t i2r_stem_tc_weight_bytes(void);
+int i2r_stem_conv3x3s2_tc(const float* x, const void* wimg, const float* bias, void* y, int NB, int Cin, int H, int W,
+                          int Cout, int split, void* stream);
+
 /* MaxPool2d(kernel 3, stride 2, padding 1) on fp16 NHWC (position_embedding.py:9,:113-114;
  * interformer.py:260-264). */
 int i2r_maxpool3x3s2(const void* x, void* y, int NB, int H, int W, int C, int split, void* stream);

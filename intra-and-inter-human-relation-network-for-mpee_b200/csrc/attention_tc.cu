@@ -18,6 +18,8 @@
 //
 // Split-operand mode (I2R_F_SPLIT): rows of q and k are fp16 pairs [hi | lo] (lo directly after hi), V^T has the lo
 // channel rows after the hi rows; S = q_hi k_hi + q_lo k_hi + q_hi k_lo (three MMAs per K step), O += P v_hi + P v_lo.
+#include <stdlib.h>
+
 #include "i2r_tma.cuh"
 
 namespace i2r {
@@ -332,6 +334,11 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_const
 static int tc_choose_nsplit(int nseq, int max_seqlen, int sms) {
   const int qblocks = ((max_seqlen + 255) / 256) * nseq;
   const int nblk = (max_seqlen + 127) / 128;
+  static const int forced = []() {
+    const char* e = getenv("I2R_ATT_NSPLIT");     // tuning / test override
+    return e ? atoi(e) : 0;
+  }();
+  if (forced > 0) return forced < nblk ? forced : nblk;
   int best = 1;
   double best_cost = 1e30;
   for (int ns = 1; ns <= 8 && ns <= nblk; ++ns) {

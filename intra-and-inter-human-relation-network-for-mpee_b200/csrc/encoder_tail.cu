@@ -17,7 +17,8 @@
 
 namespace i2r {
 
-constexpr int ET_THREADS = 192;
+constexpr int ET_THREADS = 320;   // TMA warp, MMA warp, 8 epilogue warps
+constexpr int ET_HC = 48;          // channels per epilogue thread (two threads share a token row)
 constexpr int ET_D = 96;         // d_model
 constexpr int ET_F = 192;        // dim_feedforward
 constexpr int ET_NPARAM = 768;   // fp32: b_o[96] b_1[192] b_2[96] g1[96] be1[96] g2[96] be2[96]
@@ -28,7 +29,7 @@ struct EtCfg {
   static constexpr int A_BYTES = NCH * TC_CH_BYTES;         // activation operand tile: 128 rows
   static constexpr int W_CH = ET_D * 128;                   // one weight chunk: 96 rows x 128 B
   static constexpr int W_BYTES = NCH * W_CH;                // one [96 x 96] matrix
-  static constexpr int SMEM = 2 * A_BYTES + 3 * W_BYTES + ET_NPARAM * 4 + 256 + 1024;
+  static constexpr int SMEM = 2 * A_BYTES + 3 * W_BYTES + ET_NPARAM * 4 + 2048 + 256 + 1024;
 };
 
 struct EtArgs {
@@ -121,27 +122,70 @@ __device__ __forceinline__ void load_a16(uint32_t tile, int row, int c0, float (
   }
 }
 
+__device__ __forceinline__ float4 lds_f32x4(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
 __device__ __forceinline__ float lds_f32(uint32_t addr) {
   float v;
   asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
   return v;
 }
+__device__ __forceinline__ void sts_f32(uint32_t addr, float v) {
+  asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
+}
+__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
-// LayerNorm of the 96 register-resident values of one row (two-pass, fp32)
-__device__ __forceinline__ void layernorm96(float (&x)[ET_D], uint32_t gamma, uint32_t beta, float eps) {
-  float s = 0.f;
+// x[i] += p[i] for this thread's 48 channels (p: fp32 parameter vector in shared memory, 16-byte aligned)
+__device__ __forceinline__ void add_param48(float (&x)[ET_HC], uint32_t p) {
 #pragma unroll
-  for (int i = 0; i < ET_D; ++i) s += x[i];
-  const float mean = s * (1.f / ET_D);
-  float sq = 0.f;
-#pragma unroll
-  for (int i = 0; i < ET_D; ++i) {
-    const float d = x[i] - mean;
-    sq += d * d;
+  for (int i = 0; i < ET_HC / 4; ++i) {
+    const float4 b = lds_f32x4(p + 16 * i);
+    x[4 * i] += b.x;
+    x[4 * i + 1] += b.y;
+    x[4 * i + 2] += b.z;
+    x[4 * i + 3] += b.w;
   }
-  const float rstd = rsqrtf(sq * (1.f / ET_D) + eps);
+}
+
+// LayerNorm over the 96 channels of a row held by two threads (48 each): two-pass fp32 statistics, the halves
+// exchanged through `scratch` (float [2][128]) around a named barrier of the 256 epilogue threads.
+__device__ __forceinline__ void layernorm_pair(float (&x)[ET_HC], uint32_t gamma, uint32_t beta, float eps,
+                                               uint32_t scratch, int row, int hsel) {
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
 #pragma unroll
-  for (int i = 0; i < ET_D; ++i) x[i] = (x[i] - mean) * rstd * lds_f32(gamma + 4 * i) + lds_f32(beta + 4 * i);
+  for (int i = 0; i < ET_HC; i += 4) {
+    s0 += x[i];
+    s1 += x[i + 1];
+    s2 += x[i + 2];
+    s3 += x[i + 3];
+  }
+  const float part = (s0 + s1) + (s2 + s3);
+  sts_f32(scratch + 4 * (hsel * 128 + row), part);
+  epi_bar();
+  const float mean = (part + lds_f32(scratch + 4 * ((hsel ^ 1) * 128 + row))) * (1.f / ET_D);
+  s0 = s1 = s2 = s3 = 0.f;
+#pragma unroll
+  for (int i = 0; i < ET_HC; i += 4) {
+    const float d0 = x[i] - mean, d1 = x[i + 1] - mean, d2 = x[i + 2] - mean, d3 = x[i + 3] - mean;
+    s0 += d0 * d0;
+    s1 += d1 * d1;
+    s2 += d2 * d2;
+    s3 += d3 * d3;
+  }
+  const float partq = (s0 + s1) + (s2 + s3);
+  sts_f32(scratch + 4 * (256 + hsel * 128 + row), partq);
+  epi_bar();
+  const float rstd = rsqrtf((partq + lds_f32(scratch + 4 * (256 + (hsel ^ 1) * 128 + row))) * (1.f / ET_D) + eps);
+#pragma unroll
+  for (int i = 0; i < ET_HC / 4; ++i) {
+    const float4 g = lds_f32x4(gamma + 16 * i), b = lds_f32x4(beta + 16 * i);
+    x[4 * i] = (x[4 * i] - mean) * rstd * g.x + b.x;
+    x[4 * i + 1] = (x[4 * i + 1] - mean) * rstd * g.y + b.y;
+    x[4 * i + 2] = (x[4 * i + 2] - mean) * rstd * g.z + b.z;
+    x[4 * i + 3] = (x[4 * i + 3] - mean) * rstd * g.w + b.w;
+  }
 }
 
 template <bool SPLIT>
@@ -158,7 +202,8 @@ encoder_tail_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
   const uint32_t sH = sA + C::A_BYTES;          // src (residual of x1), then the hidden halves
   const uint32_t sW = sH + C::A_BYTES;          // 3 weight slots
   const uint32_t sPar = sW + 3 * C::W_BYTES;
-  const uint32_t sBar = sPar + ET_NPARAM * 4;
+  const uint32_t sScr = sPar + ET_NPARAM * 4;   // LayerNorm exchange: float [2 stats][2 halves][128 rows]
+  const uint32_t sBar = sScr + 2048;
   const uint32_t bA = sBar, bSrc = sBar + 8;
   const uint32_t bW = sBar + 16;      // [3] weight slot full
   const uint32_t bWe = sBar + 40;     // [3] weight slot free
@@ -173,10 +218,10 @@ encoder_tail_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
       mbar_init(bWe + 8 * i, 1);
     }
     mbar_init(bAcc1, 1);
-    mbar_init(bS1, 128);
+    mbar_init(bS1, 256);
     mbar_init(bH0, 1);
     mbar_init(bH1, 1);
-    mbar_init(bHfull, 128);
+    mbar_init(bHfull, 256);
     mbar_init(bHfree, 1);
     mbar_init(bAcc2, 1);
     fence_mbar_init();
@@ -251,46 +296,46 @@ encoder_tail_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
     }
   } else {
     // ------------------------------------------------------------------------------------- epilogues
+    // two threads per token row: warps 2-5 take channels [0, 48), warps 6-9 channels [48, 96) of every vector
     const int quad = warp & 3;
+    const int hsel = (warp - 2) >> 2;
+    const int ch0 = hsel * ET_HC;
     const int row = quad * 32 + lane;
-    const uint32_t lane_off = static_cast<uint32_t>(quad * 32) << 16;
+    const uint32_t lane_off = (static_cast<uint32_t>(quad * 32) << 16) + ch0;
     const int tok = tok0 + row;
     const bool ok = tok < E.T;
-    const uint32_t pBo = sPar, pB1 = sPar + 4 * 96, pB2 = sPar + 4 * 288, pG1 = sPar + 4 * 384, pBe1 = sPar + 4 * 480,
-                   pG2 = sPar + 4 * 576, pBe2 = sPar + 4 * 672;
-    float x[ET_D];
+    const uint32_t pBo = sPar + 4 * ch0, pB1 = sPar + 4 * (96 + ch0), pB2 = sPar + 4 * (288 + ch0),
+                   pG1 = sPar + 4 * (384 + ch0), pBe1 = sPar + 4 * (480 + ch0), pG2 = sPar + 4 * (576 + ch0),
+                   pBe2 = sPar + 4 * (672 + ch0);
+    float x[ET_HC];
     // ---- x1 = acc1 + b_o + src ; s1 = LN1(x1) -> sA
     mbar_wait(bSrc, 0);
     mbar_wait(bAcc1, 0);
     tc_fence_after();
 #pragma unroll
-    for (int c = 0; c < ET_D / 32; ++c) {
-      uint32_t r[32];
-      tmem_ld32(tAcc1 + lane_off + c * 32, r);
+    for (int c = 0; c < ET_HC / 16; ++c) {
+      uint32_t r[16];
+      tmem_ld16(tAcc1 + lane_off + c * 16, r);
+      float v[16];
+      load_a16<SPLIT>(sH, row, ch0 + c * 16, v);
       tmem_ld_wait();
 #pragma unroll
-      for (int i = 0; i < 32; ++i) x[c * 32 + i] = __uint_as_float(r[i]) + lds_f32(pBo + 4 * (c * 32 + i));
+      for (int i = 0; i < 16; ++i) x[c * 16 + i] = __uint_as_float(r[i]) + v[i];
     }
+    add_param48(x, pBo);
+    layernorm_pair(x, pG1, pBe1, E.eps, sScr, row, hsel);
 #pragma unroll
-    for (int c = 0; c < ET_D / 16; ++c) {
-      float v[16];
-      load_a16<SPLIT>(sH, row, c * 16, v);
-#pragma unroll
-      for (int i = 0; i < 16; ++i) x[c * 16 + i] += v[i];
-    }
-    layernorm96(x, pG1, pBe1, E.eps);
-#pragma unroll
-    for (int c = 0; c < ET_D / 16; ++c) {
+    for (int c = 0; c < ET_HC / 16; ++c) {
       float v[16];
 #pragma unroll
       for (int i = 0; i < 16; ++i) v[i] = x[c * 16 + i];
-      store_a16<SPLIT>(sA, row, c * 16, v);     // GEMM 1 has completed (bAcc1), so the attention tile is dead
+      store_a16<SPLIT>(sA, row, ch0 + c * 16, v);     // GEMM 1 has completed (bAcc1), so the attention tile is dead
     }
     fence_proxy_async();
     tc_fence_before();
     mbar_arrive(bS1);
-    // ---- hidden halves: h = relu(acc + b_1) -> sH.  Every thread touches only its own row of sA / sH, so the src
-    //      row read above and the overwrite below need no cross-thread ordering.
+    // ---- hidden halves: h = relu(acc + b_1) -> sH.  The src tile in sH is dead once BOTH threads of every row have
+    //      read it, which the LayerNorm barriers above already guarantee.
 #pragma unroll 1
     for (int hf = 0; hf < 2; ++hf) {
       mbar_wait(hf ? bH1 : bH0, 0);
@@ -300,45 +345,56 @@ encoder_tail_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
         tc_fence_after();
       }
 #pragma unroll
-      for (int c = 0; c < ET_D / 16; ++c) {
+      for (int c = 0; c < ET_HC / 16; ++c) {
         uint32_t r[16];
         tmem_ld16((hf ? tH1 : tH0) + lane_off + c * 16, r);
         tmem_ld_wait();
         float v[16];
 #pragma unroll
-        for (int i = 0; i < 16; ++i)
-          v[i] = fmaxf(__uint_as_float(r[i]) + lds_f32(pB1 + 4 * (hf * ET_D + c * 16 + i)), 0.f);
-        store_a16<SPLIT>(sH, row, c * 16, v);
+        for (int i = 0; i < 4; ++i) {
+          const float4 b = lds_f32x4(pB1 + 4 * (hf * ET_D + c * 16 + 4 * i));
+          v[4 * i] = fmaxf(__uint_as_float(r[4 * i]) + b.x, 0.f);
+          v[4 * i + 1] = fmaxf(__uint_as_float(r[4 * i + 1]) + b.y, 0.f);
+          v[4 * i + 2] = fmaxf(__uint_as_float(r[4 * i + 2]) + b.z, 0.f);
+          v[4 * i + 3] = fmaxf(__uint_as_float(r[4 * i + 3]) + b.w, 0.f);
+        }
+        store_a16<SPLIT>(sH, row, ch0 + c * 16, v);
       }
       fence_proxy_async();
       tc_fence_before();
       mbar_arrive(bHfull);
     }
-    // ---- x2 = acc2 + b_2 + s1 ; src' = LN2(x2)
+    // ---- x2 = acc2 + b_2 + s1 ; src' = LN2(x2).  The pos row (a constant of the model) is fetched first so that its
+    //      global-memory latency hides behind the last GEMM.
+    uint4 ph[ET_HC / 8], pl[SPLIT ? ET_HC / 8 : 1];
+    if (E.pos != nullptr && ok) {
+      const __half* prow = E.pos + static_cast<int64_t>(tok) * E.ld + ch0;
+#pragma unroll
+      for (int g = 0; g < ET_HC / 8; ++g) {
+        ph[g] = __ldg(reinterpret_cast<const uint4*>(prow + g * 8));
+        if (SPLIT) pl[g] = __ldg(reinterpret_cast<const uint4*>(prow + ET_D + g * 8));
+      }
+    }
     mbar_wait(bAcc2, 0);
     tc_fence_after();
 #pragma unroll
-    for (int c = 0; c < ET_D / 32; ++c) {
-      uint32_t r[32];
-      tmem_ld32(tAcc2 + lane_off + c * 32, r);
+    for (int c = 0; c < ET_HC / 16; ++c) {
+      uint32_t r[16];
+      tmem_ld16(tAcc2 + lane_off + c * 16, r);
+      float v[16];
+      load_a16<SPLIT>(sA, row, ch0 + c * 16, v);
       tmem_ld_wait();
 #pragma unroll
-      for (int i = 0; i < 32; ++i) x[c * 32 + i] = __uint_as_float(r[i]) + lds_f32(pB2 + 4 * (c * 32 + i));
+      for (int i = 0; i < 16; ++i) x[c * 16 + i] = __uint_as_float(r[i]) + v[i];
     }
-#pragma unroll
-    for (int c = 0; c < ET_D / 16; ++c) {
-      float v[16];
-      load_a16<SPLIT>(sA, row, c * 16, v);
-#pragma unroll
-      for (int i = 0; i < 16; ++i) x[c * 16 + i] += v[i];
-    }
-    layernorm96(x, pG2, pBe2, E.eps);
+    add_param48(x, pB2);
+    layernorm_pair(x, pG2, pBe2, E.eps, sScr, row, hsel);
     if (ok) {
-      __half* orow = E.out + static_cast<int64_t>(tok) * E.ld;
-      const __half* prow = E.pos ? E.pos + static_cast<int64_t>(tok) * E.ld : nullptr;
-      __half* qrow = E.pos ? E.out_pos + static_cast<int64_t>(tok) * E.ld : nullptr;
+      __half* orow = E.out + static_cast<int64_t>(tok) * E.ld + ch0;
+      const bool prow = E.pos != nullptr;
+      __half* qrow = E.pos ? E.out_pos + static_cast<int64_t>(tok) * E.ld + ch0 : nullptr;
 #pragma unroll
-      for (int g = 0; g < ET_D / 8; ++g) {
+      for (int g = 0; g < ET_HC / 8; ++g) {
         uint32_t h[4], lo[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
@@ -352,8 +408,7 @@ encoder_tail_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
         *reinterpret_cast<uint4*>(orow + g * 8) = make_uint4(h[0], h[1], h[2], h[3]);
         if (SPLIT) *reinterpret_cast<uint4*>(orow + ET_D + g * 8) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
         if (prow) {
-          const uint4 ph = *reinterpret_cast<const uint4*>(prow + g * 8);
-          const uint32_t pw[4] = {ph.x, ph.y, ph.z, ph.w};
+          const uint32_t pw[4] = {ph[g].x, ph[g].y, ph[g].z, ph[g].w};
           float s[8];
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
@@ -362,8 +417,7 @@ encoder_tail_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
             s[2 * i + 1] = x[g * 8 + 2 * i + 1] + f.y;
           }
           if (SPLIT) {
-            const uint4 pl = *reinterpret_cast<const uint4*>(prow + ET_D + g * 8);
-            const uint32_t pv[4] = {pl.x, pl.y, pl.z, pl.w};
+            const uint32_t pv[4] = {pl[g].x, pl[g].y, pl[g].z, pl[g].w};
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
               const float2 f = unpack_h2(pv[i]);

@@ -191,3 +191,20 @@ def pack_encoder_tail(w_out, b_out, w1, b1, w2, b2, g1, be1, g2, be2, split):
     params = torch.cat([v.float().reshape(-1) for v in (b_out, b1, b2, g1, be1, g2, be2)]).contiguous()
     assert params.numel() == 768
     return img, params
+
+
+def pack_stem_tc(w, scale):
+    """Operand image of i2r_stem_conv3x3s2_tc: w fp32 [K = Cin*9, 64] (k = (c*3+ky)*3+kx), BatchNorm scale folded in
+    (fp32 product) and split into an fp16 pair.  Rows = output channels, 64 K slots of 128 bytes each:
+    block 0 = [W_hi (32 slots, zero past K) | W_hi], block 1 = [W_lo | 0]; SWIZZLE_128B."""
+    k, cout = w.shape
+    assert cout == 64 and k <= 32
+    m = (w.float() * scale.float().reshape(1, cout)).t().contiguous()      # [64, K]
+    hi = m.to(torch.float16).float()
+    lo = (m - hi).to(torch.float16).float()
+    b1 = torch.zeros(cout, 64)
+    b1[:, :k] = hi
+    b1[:, 32:32 + k] = hi
+    b2 = torch.zeros(cout, 64)
+    b2[:, :k] = lo
+    return torch.cat([_pack_rows_sw128(b1).reshape(-1), _pack_rows_sw128(b2).reshape(-1)]).contiguous()

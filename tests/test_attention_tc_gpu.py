@@ -165,3 +165,31 @@ def test_encoder_tail(dev, tc, split, t, with_pos):
     tol = 3e-5 if split else 1.5e-2      # fp16 weights / activations through three GEMMs and two LayerNorms
     assert (out_pos is None) == (not with_pos)
     assert err <= tol and err_pos <= 2 * tol, (err, err_pos)
+
+
+@pytest.mark.parametrize("split", [False, True])
+@pytest.mark.parametrize("cin,h,w", [(3, 256, 192), (1, 256, 192), (3, 384, 288), (1, 72, 40)])
+def test_stem_tc(dev, tc, split, cin, h, w):
+    """Tensor-core stem (conv 3x3 s2 + folded BN + ReLU, fp32 NCHW -> fp16 NHWC) vs float64 torch; also partial tiles."""
+    import torch.nn.functional as F
+    from i2r_b200.packing import merge_pair
+    g = torch.Generator().manual_seed(100 + cin + h)
+    nb = 3
+    x = torch.randn(nb, cin, h, w, generator=g) * 1.5
+    wt = (torch.rand(64, cin, 3, 3, generator=g) * 2 - 1) / math.sqrt(cin * 9)
+    sc = torch.rand(64, generator=g) + 0.5
+    bi = torch.randn(64, generator=g) * 0.1
+    wk = wt.permute(1, 2, 3, 0).reshape(-1, 64).contiguous()
+    tc.split = split
+    try:
+        y = tc.stem(x.to(dev), wk.to(dev), sc.to(dev), bi.to(dev), 64)
+        torch.cuda.synchronize()
+    finally:
+        tc.split = False
+    ref = F.relu(F.conv2d(x.double(), wt.double(), None, 2, 1) * sc.double().view(1, -1, 1, 1)
+                 + bi.double().view(1, -1, 1, 1)).permute(0, 2, 3, 1)
+    got = merge_pair(y.cpu()).double() if split else y.cpu().double()
+    err = float((got - ref).abs().max())
+    _report(test="stem_tc", split=split, cin=cin, h=h, w=w, err=err, ref_max=float(ref.abs().max()))
+    assert tuple(y.shape) == (nb, h // 2, w // 2, 128 if split else 64)
+    assert err <= (2e-5 if split else 4e-3), err       # fp16 output rounding dominates the single-precision mode

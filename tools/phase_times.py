@@ -42,7 +42,7 @@ def wrap(name):
     setattr(ops.Runner, name, f)
 
 
-for n in ("launch", "stem", "maxpool", "layernorm", "add", "upsum", "attention", "attention_tc"):
+for n in ("launch", "stem", "maxpool", "layernorm", "add", "upsum", "attention", "attention_tc", "encoder_tail"):
     wrap(n)
 reps = 3
 tot = {}

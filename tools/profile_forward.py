@@ -12,7 +12,8 @@ sys.path.insert(0, os.path.join(paths.REPO, "tests"))
 from helpers import build_model, inputs_for  # noqa: E402
 
 images = int(sys.argv[1]) if len(sys.argv) > 1 else 8
-cfg, model, sd = build_model()
+yaml = sys.argv[2] if len(sys.argv) > 2 else "coco/interformer_coco_w48_pure_en6.yaml"
+cfg, model, sd = build_model(yaml)
 model = model.cuda()
 model.use_cuda_graph = False
 length = [4] * images
