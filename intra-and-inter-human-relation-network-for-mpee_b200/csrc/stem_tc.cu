@@ -63,15 +63,31 @@ __global__ void __launch_bounds__(128) stem_tc_kernel(const float* __restrict__ 
     const int rem = tile - n * (tiles_y * tiles_x);
     const int oy0 = (rem / tiles_x) * ST_TH, ox0 = (rem % tiles_x) * ST_TW;
     const int iy0 = oy0 * 2 - 1, ix0 = ox0 * 2 - 1;
-    // ---- input patch, coalesced along the image rows
-    for (int i = tid; i < CIN * ST_PH * ST_PW; i += 128) {
-      const int c = i / (ST_PH * ST_PW);
-      const int r = i - c * (ST_PH * ST_PW);
-      const int py = r / ST_PW, px = r - py * ST_PW;
-      const int iy = iy0 + py, ix = ix0 + px;
-      float v = 0.f;
-      if (iy >= 0 && iy < H && ix >= 0 && ix < W) v = __ldg(x + ((static_cast<int64_t>(n) * CIN + c) * H + iy) * W + ix);
-      patch[c][py][px] = v;
+    // ---- input patch, coalesced along the image rows; all loads are issued before the first shared-memory store so
+    //      that their latencies overlap (a load->store loop serialises on every load)
+    {
+      constexpr int TOTAL = CIN * ST_PH * ST_PW;
+      constexpr int NLD = (TOTAL + 127) / 128;
+      float v[NLD];
+#pragma unroll
+      for (int u = 0; u < NLD; ++u) {
+        const int i = tid + u * 128;
+        const int c = i / (ST_PH * ST_PW);
+        const int r = i - c * (ST_PH * ST_PW);
+        const int py = r / ST_PW, px = r - py * ST_PW;
+        const int iy = iy0 + py, ix = ix0 + px;
+        v[u] = 0.f;
+        if (i < TOTAL && iy >= 0 && iy < H && ix >= 0 && ix < W)
+          v[u] = __ldg(x + ((static_cast<int64_t>(n) * CIN + c) * H + iy) * W + ix);
+      }
+#pragma unroll
+      for (int u = 0; u < NLD; ++u) {
+        const int i = tid + u * 128;
+        const int c = i / (ST_PH * ST_PW);
+        const int r = i - c * (ST_PH * ST_PW);
+        const int py = r / ST_PW, px = r - py * ST_PW;
+        if (i < TOTAL) patch[c][py][px] = v[u];
+      }
     }
     __syncthreads();
     // ---- this pixel's operand row: slots [0, K) = hi, [32, 32 + K) = lo, the rest zero

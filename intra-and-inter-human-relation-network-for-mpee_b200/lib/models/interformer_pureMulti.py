@@ -113,7 +113,7 @@ class TransPoseH(nn.Module):
         return out
 
     # ------------------------------------------------------------------ forward
-    def _eager(self, x, pos_mask, length):
+    def _eager(self, x, pos_mask, length, mask_needed=None):
         p = self._program
         r = p.runner
         feats = p.backbone.run(r, x)
@@ -122,6 +122,8 @@ class TransPoseH(nn.Module):
         src = tok_map.view(s * th * tw, d)
         pos = None
         if p.mask_embed is not None:
+            if mask_needed is not None:
+                mask_needed()         # engine.GraphedForward: the graph is cut here (mask upload overlaps what precedes)
             pos = p.mask_embed.run(r, pos_mask, (th, tw)).view(s * th * tw, d)
         cu = p.seq_offsets(length, th * tw)
         y = p.encoder.run(r, src, pos, cu, max(length) * th * tw)
@@ -144,11 +146,13 @@ class TransPoseH(nn.Module):
                                 "move the module with .cuda() -- there is no CPU fallback")
         if self._program is None or self._program.device != dev:
             self.prepare(dev)
-        x = x.to(dev, dtype=torch.float32, non_blocking=True).contiguous()
-        pos_mask = pos_mask.to(dev, dtype=torch.float32, non_blocking=True).contiguous()
         with torch.no_grad():
-            if self.use_cuda_graph:
-                return self._graphs(x, pos_mask, length)
+            if self.use_cuda_graph:      # host tensors are uploaded straight into the graphs' static buffers
+                if x.dtype != torch.float32 or pos_mask.dtype != torch.float32:
+                    x, pos_mask = x.float(), pos_mask.float()
+                return self._graphs(x, pos_mask, length, device=dev)
+            x = x.to(dev, dtype=torch.float32, non_blocking=True).contiguous()
+            pos_mask = pos_mask.to(dev, dtype=torch.float32, non_blocking=True).contiguous()
             return self._eager(x, pos_mask, length)
 
     def init_weights(self, pretrained="", fixed=False, print_load_info=False):
