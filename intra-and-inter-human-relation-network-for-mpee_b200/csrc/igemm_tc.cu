@@ -35,7 +35,7 @@ constexpr int SMEM_BIAS_OFF = 256 + 1024;
 
 template <int STAGES>
 __device__ __forceinline__ void run_tile(const i2r_conv_problem& P, const int tile, uint8_t* smem) {
-  constexpr int LOOK = STAGES - 1;
+  constexpr int LOOK = STAGES > 2 ? STAGES - 2 : 1;   // cp.async groups in flight; the other stage(s) cover the MMA hand-over round trip
   constexpr int KG = 8;   // 16-byte chunk slots per 128-byte row; the last K-chunk may use fewer (Cin % 64 != 0)
   const int tid = threadIdx.x;
   const int warp = tid >> 5;
