@@ -244,6 +244,129 @@ def transpose_h_first_stage(sd, cfg, x, prefix=""):
     return feat, F.conv2d(feat, sd[prefix + "final_layer.weight"], sd[prefix + "final_layer.bias"])
 
 
+# ------------------------------------------------------------------------------------------------ HRFormer-B first stage
+def _hrt_window_attention(sd, p, x, heads, ws=7):
+    """InterlacedPoolAttention.forward + MHA_.forward (lib/models/hrformer.py:1164-1180, :627-935) on x [B, H, W, C]
+    (already LayerNorm-ed): center zero-pad H, W to multiples of 7 (:949-956), 7x7 windows as sequences
+    (:976-986), q/k/v = three biased Linear(C, C), q * head_dim**-0.5, softmax(q k^T) WITHOUT the relative position
+    bias (it is computed but its addition is commented out, :866-888) and without any mask -- padded tokens are zero
+    vectors, so their keys/values are the projection biases and they DO take part --, P v, out_proj, de-pad."""
+    b, h, w, c = x.shape
+    ph, pw = (-h) % ws, (-w) % ws
+    xp = F.pad(x, (0, 0, pw // 2, pw - pw // 2, ph // 2, ph - ph // 2))
+    hp, wp = h + ph, w + pw
+    qh, qw = hp // ws, wp // ws
+    # "n (qh ph) (qw pw) c -> (ph pw) (n qh qw) c"
+    t = xp.view(b, qh, ws, qw, ws, c).permute(2, 4, 0, 1, 3, 5).reshape(ws * ws, b * qh * qw, c)
+    hd = c // heads
+    q = F.linear(t, sd[p + ".q_proj.weight"], sd[p + ".q_proj.bias"]) * (float(hd) ** -0.5)
+    k = F.linear(t, sd[p + ".k_proj.weight"], sd[p + ".k_proj.bias"])
+    v = F.linear(t, sd[p + ".v_proj.weight"], sd[p + ".v_proj.bias"])
+    n, bw, _ = q.shape
+    q = q.contiguous().view(n, bw * heads, hd).transpose(0, 1)
+    k = k.contiguous().view(n, bw * heads, hd).transpose(0, 1)
+    v = v.contiguous().view(n, bw * heads, hd).transpose(0, 1)
+    a = torch.softmax(torch.bmm(q, k.transpose(1, 2)), dim=-1)
+    o = torch.bmm(a, v).transpose(0, 1).contiguous().view(n, bw, c)
+    o = F.linear(o, sd[p + ".out_proj.weight"], sd[p + ".out_proj.bias"])
+    # "(ph pw) (n qh qw) c -> n (qh ph) (qw pw) c"
+    o = o.view(ws, ws, b, qh, qw, c).permute(2, 3, 0, 4, 1, 5).reshape(b, hp, wp, c)
+    return o[:, ph // 2: ph // 2 + h, pw // 2: pw // 2 + w, :]
+
+
+def _hrt_block(sd, p, x, heads):
+    """GeneralTransformerBlock.forward (lib/models/hrformer.py:1230-1240) with MlpDWBN (:1094-1119): pre-norm
+    (LayerNorm eps 1e-6), x + attn(norm1 x), x + mlp(norm2 x); mlp = 1x1 conv + BN + GELU, depthwise 3x3 + BN + GELU,
+    1x1 conv + BN + GELU (drop_path / dropout are identity in eval)."""
+    b, c, h, w = x.shape
+    t = x.flatten(2).permute(0, 2, 1)                                                 # [B, HW, C]
+    n1 = F.layer_norm(t, (c,), sd[p + ".norm1.weight"], sd[p + ".norm1.bias"], 1e-6)
+    t = t + _hrt_window_attention(sd, p + ".attn.attn", n1.view(b, h, w, c), heads).reshape(b, h * w, c)
+    n2 = F.layer_norm(t, (c,), sd[p + ".norm2.weight"], sd[p + ".norm2.bias"], 1e-6)
+    m = n2.permute(0, 2, 1).reshape(b, c, h, w)
+    m = F.gelu(_bn(sd, p + ".mlp.norm1", F.conv2d(m, sd[p + ".mlp.fc1.weight"], sd[p + ".mlp.fc1.bias"])))
+    m = F.gelu(_bn(sd, p + ".mlp.norm2", F.conv2d(m, sd[p + ".mlp.dw3x3.weight"], sd[p + ".mlp.dw3x3.bias"], 1, 1, 1,
+                                                  m.shape[1])))
+    m = F.gelu(_bn(sd, p + ".mlp.norm3", F.conv2d(m, sd[p + ".mlp.fc2.weight"], sd[p + ".mlp.fc2.bias"])))
+    t = t + m.flatten(2).permute(0, 2, 1)
+    return t.permute(0, 2, 1).reshape(b, c, h, w)
+
+
+def _hrt_module(sd, p, xs, heads, multiscale_output=True):
+    """HighResolutionTransformerModule.forward (lib/models/hrformer.py:1708-1732) with _make_fuse_layers (:1616-1706):
+    branches of transformer blocks, then for every output branch i: sum_j f_ij(x_j), ReLU; f_ij = 1x1 conv + BN +
+    bilinear upsample x2^(j-i) (align_corners=False) for j > i, identity for j = i, a chain of [depthwise 3x3 s2 + BN +
+    1x1 conv + BN (+ ReLU except the last)] for j < i."""
+    nb = len(xs)
+    ys = []
+    for i in range(nb):
+        y = xs[i]
+        for blk in range(_count(sd, "%s.branches.%d" % (p, i))):
+            y = _hrt_block(sd, "%s.branches.%d.%d" % (p, i, blk), y, heads[i])
+        ys.append(y)
+    if nb == 1:
+        return ys
+    out = []
+    for i in range(nb if multiscale_output else 1):
+        acc = None
+        for j in range(nb):
+            fp = "%s.fuse_layers.%d.%d" % (p, i, j)
+            if j == i:
+                t = ys[j]
+            elif j > i:
+                t = _bn(sd, fp + ".1", F.conv2d(ys[j], sd[fp + ".0.weight"]))
+                t = F.interpolate(t, scale_factor=2 ** (j - i), mode="bilinear", align_corners=False)
+                t = F.interpolate(t, size=ys[i].shape[2:], mode="bilinear", align_corners=False)     # `resize` (:1723)
+            else:
+                t = ys[j]
+                for k in range(i - j):
+                    kp = "%s.%d" % (fp, k)
+                    t = _bn(sd, kp + ".1", F.conv2d(t, sd[kp + ".0.weight"], None, 2, 1, 1, t.shape[1]))
+                    t = _bn(sd, kp + ".3", F.conv2d(t, sd[kp + ".2.weight"]))
+                    if k != i - j - 1:
+                        t = F.relu(t)
+            acc = t if acc is None else acc + t
+        out.append(F.relu(acc))
+    return out
+
+
+HRT_STAGES = (                # lib/models/hrformer.py:2489-2525 (hard-coded in get_pose_net)
+    ("stage2", 1, (2, 4)),
+    ("stage3", 4, (2, 4, 8)),
+    ("stage4", 2, (2, 4, 8, 16)),
+)
+
+
+def hrformer_first_stage(sd, cfg, x, prefix=""):
+    """hrformer.HRFormer.forward (lib/models/hrformer.py:2477-2480) = HRT.forward (:2057-2092) + TopDownSimpleHead
+    with zero deconvs (:2343-2348): stem (two 3x3 s2 conv + BN + ReLU), two Bottlenecks, three transformer stages
+    (1 / 4 / 2 modules; the last module of stage 4 only produces branch 0), 1x1 head on branch 0.  Returns
+    (branch 0 feature [S, 78, H/4, W/4], heatmaps)."""
+    b = prefix + "backbone."
+    y = F.relu(_bn(sd, b + "bn1", _conv(sd, b + "conv1", x, 2)))
+    y = F.relu(_bn(sd, b + "bn2", _conv(sd, b + "conv2", y, 2)))
+    for i in range(_count(sd, b + "layer1")):
+        y = bottleneck(sd, "%slayer1.%d" % (b, i), y)
+
+    def transition(name, idx, t):
+        tp = "%s%s.%d" % (b, name, idx)
+        if (tp + ".0.weight") in sd and sd[tp + ".0.weight"].dim() == 4:     # 3x3 s1 conv + BN + ReLU (:1874-1890)
+            return F.relu(_bn(sd, tp + ".1", _conv(sd, tp + ".0", t)))
+        for j in range(_count(sd, tp)):                                         # 3x3 s2 conv + BN + ReLU chain
+            t = F.relu(_bn(sd, "%s.%d.1" % (tp, j), _conv(sd, "%s.%d.0" % (tp, j), t, 2)))
+        return t
+    xs = [transition("transition1", 0, y), transition("transition1", 1, y)]
+    for si, (stage, nmod, heads) in enumerate(HRT_STAGES):
+        if si > 0:
+            xs = xs + [transition("transition%d" % (si + 1), len(xs), xs[-1])]
+        for mi in range(nmod):
+            last = stage == "stage4" and mi == nmod - 1
+            xs = _hrt_module(sd, "%s%s.%d" % (b, stage, mi), xs, heads, multiscale_output=not last)
+    feat = xs[0]
+    hp = prefix + "keypoint_head.final_layer"
+    return feat, F.conv2d(feat, sd[hp + ".weight"], sd[hp + ".bias"])
+
+
 def _deconv_block(sd, key, y, num_layers):
     for i in range(num_layers):
         y = F.conv_transpose2d(y, sd["%s.%d.weight" % (key, 3 * i)], sd.get("%s.%d.bias" % (key, 3 * i)), 2, 1, 0)
@@ -258,9 +381,12 @@ def two_stage_forward(sd, cfg, x, pos_mask, length, taps=None):
     sd = {k: v.float() for k, v in sd.items() if v.dtype.is_floating_point}
     m = cfg.MODEL
     length = list(length)
-    if m.SINGLEFORMER != "transpose_h":
+    if m.SINGLEFORMER == "transpose_h":
+        feat, single = transpose_h_first_stage(sd, cfg, x, "singleformer.")
+    elif m.SINGLEFORMER == "hrformer":
+        feat, single = hrformer_first_stage(sd, cfg, x, "singleformer.")
+    else:
         raise NotImplementedError("oracle first stage %r" % m.SINGLEFORMER)
-    feat, single = transpose_h_first_stage(sd, cfg, x, "singleformer.")
     if taps is not None:
         taps["feat"] = feat
     t = feat

@@ -31,6 +31,10 @@ CASES = {
     "tph2stage_ragged": ("coco/interformer_coco_tph_192_p4_b4.yaml", [2, 1], 256, 192),
     # `interformer` naming: CrowdPose TransPose-H (4 intra / 2 inter layers, no multi-pos, distinct deconvs, 14 joints)
     "tph_crowdpose_ragged": ("crowdpose/interformer_crowdpose_tph_192_p6_b4.yaml", [1, 2], 256, 192),
+    # HRFormer-B first stage (window attention incl. padded tokens, MlpDWBN, bilinear fuse) + 2 inter layers, d = 78
+    "hrt2stage_ragged": ("coco/interformer_coco_hrt_192_p2_b12.yaml", [2, 1], 256, 192),
+    # 384x288: 96x72 branch-0 maps padded to 98x77 windows, 24x18 token maps per person
+    "hrt288_c1": ("coco/interformer_coco_hrt_288_p2_b4.yaml", [1], 384, 288),
 }
 
 

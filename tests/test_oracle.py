@@ -74,3 +74,34 @@ def test_two_stage_oracle_and_surface_match_reference(yaml_rel, case, nkeys):
     for k in out:
         err = float(np.abs(out[k].numpy() - g["out_" + k]).max())
         assert err <= 2e-5, (k, err)
+
+
+HRT = [
+    ("coco/interformer_coco_hrt_192_p2_b12.yaml", "hrt2stage_ragged", 256, 192),
+    ("coco/interformer_coco_hrt_288_p2_b4.yaml", "hrt288_c1", 384, 288),
+]
+
+
+@pytest.mark.parametrize("yaml_rel,case,h,w", HRT, ids=[c[1] for c in HRT])
+def test_hrformer_oracle_matches_reference(yaml_rel, case, h, w):
+    """HRFormer-B first stage (7x7 window attention incl. zero-padded tokens and WITHOUT the relative
+    position bias, MlpDWBN, bilinear fuse) + the inter-human stage at d = 78: the oracle restatement against outputs
+    of the REAL reference.  The weights are rebuilt from the committed key/shape list of the reference's state_dict
+    (synthetic values are keyed by parameter name, so they equal the ones the golden generator loaded)."""
+    from i2r_b200.config import load_experiment
+    from i2r_b200.synth import synth_inputs, synth_state_dict
+    cfg = load_experiment(yaml_rel)
+    with open(os.path.join(GOLDEN, "state_dict_%s.json" % os.path.basename(yaml_rel)[:-5])) as f:
+        ref = json.load(f)
+    assert len([k for k in ref if k.startswith("singleformer.backbone.")]) == 2074      # SURVEY.md 8b [measured]
+    shapes = {k: torch.zeros(v[0], dtype=getattr(torch, v[1])) for k, v in ref.items()}
+    sd = synth_state_dict(shapes, seed=0)
+    g = load_golden(case)
+    length = [int(v) for v in g["length"]]
+    x, pm = synth_inputs(sum(length), h, w, seed=1)
+    with torch.no_grad():
+        out = i2r_oracle.forward(sd, cfg, x, pm, length)
+    for k in ("single", "multi"):
+        assert out[k].shape == g["out_" + k].shape
+        err = float(np.abs(out[k].numpy() - g["out_" + k]).max())
+        assert err <= 5e-5, (k, err)
