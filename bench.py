@@ -22,7 +22,7 @@ import torch
 
 import paths  # noqa: F401
 
-GFLOP_PER_CROP = {"C2": 19.43, "C3": 43.75}      # algorithmic, 2*MAC, BASELINE.md section 2
+GFLOP_PER_CROP = {"C2": 19.43, "C3": 43.75, "C4": 28.24}      # algorithmic, 2*MAC, BASELINE.md section 2
 H, W = 256, 192
 # BASELINE.json configs that fit one GPU: C2 is the configuration the metric is quoted on (the default workload);
 # C3 (TransPose-H two-stage, split-operand precision) is selectable for measurements of that family.
@@ -36,6 +36,11 @@ WORKLOADS = {
                     "tokens per crop) + 4 inter layers, 256x192, 4 images x 4 persons = 16 crops per GPU per step",
                precision="split-operand fp16 pairs (hi+lo), three-term products, fp32 accumulate (tcgen05 kind::f16)",
                dtype="f16x2"),
+    # HRFormer-B first stage: oracle and parameter surface exist, the device program does not yet --
+    # selectable for `--impl reference` (CPU forward of the reference algorithm) only
+    "C4": dict(yaml="coco/interformer_coco_hrt_192_p2_b12.yaml", images=8, persons=8,
+               text="C4: HRFormer-B + I2R-Net (interformer), 256x192, 8 images x 8 persons = 64 crops per step",
+               precision="n/a (device program pending)", dtype="f32", device=False),
 }
 IMAGES_PER_RANK, PERSONS = 8, 4
 
@@ -152,6 +157,10 @@ def main():
     if args.impl == "reference":
         return run_reference(args)
 
+    if not WORKLOADS[args.workload].get("device", True):
+        print(json.dumps({"workload": args.workload, "unavailable": "the sm_100a device program of this model family is "
+                          "not built yet; only --impl reference runs it"}), flush=True)
+        return
     rank, world, local = _dist_env()
     if args.warmup < 3:
         args.warmup = 3

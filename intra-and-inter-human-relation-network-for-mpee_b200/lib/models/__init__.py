@@ -4,3 +4,4 @@ import models.interformer_pureMulti  # noqa: F401
 import models.transpose_h  # noqa: F401
 import models.interformer  # noqa: F401
 import models.interformer_2stage  # noqa: F401
+import models.hrformer  # noqa: F401
