@@ -152,7 +152,7 @@ int i2r_attention_varlen(const void* q, const void* k, const void* v, void* out,
  *           with I2R_F_OUT_T16; ldvt % 8 == 0;
  *   - out:  [T, D] (split: hi at column 0, lo at column o_lo).
  * Replaces F.multi_head_attention_forward's baddbmm / softmax / bmm (torch/nn/functional.py:6638-6650) as called
- * from transpose_h.py:165-240 and attention.py:68-73.  D = 96. */
+ * from transpose_h.py:165-240 and attention.py:68-73.  D = 96 or 80. */
 int64_t i2r_attention_tc_workspace_bytes(int total_tokens, int D, int nseq, int max_seqlen);
 int i2r_attention_tc(const void* q, const void* k, const void* vt, void* out, int ldq, int ldk, int ldvt, int ldo,
                      int D, const int32_t* cu_seqlens, int nseq, int max_seqlen, int total_tokens, float scale,

@@ -456,8 +456,13 @@ extern "C" int i2r_attention_tc(const void* q, const void* k, const void* vt, vo
                                                    total_tokens, scale, workspace, workspace_bytes, o_lo, st)
                    : launch_attention_tc<96, false>(q, k, vt, out, ldq, ldk, ldvt, ldo, cu_seqlens, nseq, max_seqlen,
                                                     total_tokens, scale, workspace, workspace_bytes, 0, st);
+    case 80:      // d_model 78 padded to 80 (HRFormer-B inter-human stage)
+      return split ? launch_attention_tc<80, true>(q, k, vt, out, ldq, ldk, ldvt, ldo, cu_seqlens, nseq, max_seqlen,
+                                                   total_tokens, scale, workspace, workspace_bytes, o_lo, st)
+                   : launch_attention_tc<80, false>(q, k, vt, out, ldq, ldk, ldvt, ldo, cu_seqlens, nseq, max_seqlen,
+                                                    total_tokens, scale, workspace, workspace_bytes, 0, st);
     default:
-      set_error("i2r_attention_tc: head dim %d unsupported (96)", D);
+      set_error("i2r_attention_tc: head dim %d unsupported (80, 96)", D);
       return I2R_E_UNSUPPORTED;
   }
 }

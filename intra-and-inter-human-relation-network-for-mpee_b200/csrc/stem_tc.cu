@@ -58,37 +58,42 @@ __global__ void __launch_bounds__(128) stem_tc_kernel(const float* __restrict__ 
   const int ty = tid >> 5, tx = tid & 31;
   uint32_t phase = 0;
   bool first = true;
+  constexpr int TOTAL = CIN * ST_PH * ST_PW;
+  constexpr int NLD = (TOTAL + 127) / 128;
+  // input patch of one tile, coalesced along the image rows, as NLD register values per thread.  The loads of tile i+1
+  // are issued right after the patch of tile i has been stored to shared memory, so their (cold, first-touch HBM)
+  // latency hides behind the MMAs and the epilogue of tile i.
+  auto load_patch = [&](int tile, float (&v)[NLD]) {
+    const int n = tile / (tiles_y * tiles_x);
+    const int rem = tile - n * (tiles_y * tiles_x);
+    const int iy0 = (rem / tiles_x) * ST_TH * 2 - 1, ix0 = (rem % tiles_x) * ST_TW * 2 - 1;
+#pragma unroll
+    for (int u = 0; u < NLD; ++u) {
+      const int i = tid + u * 128;
+      const int c = i / (ST_PH * ST_PW);
+      const int r = i - c * (ST_PH * ST_PW);
+      const int py = r / ST_PW, px = r - py * ST_PW;
+      const int iy = iy0 + py, ix = ix0 + px;
+      v[u] = 0.f;
+      if (i < TOTAL && tile < ntiles && iy >= 0 && iy < H && ix >= 0 && ix < W)
+        v[u] = __ldg(x + ((static_cast<int64_t>(n) * CIN + c) * H + iy) * W + ix);
+    }
+  };
+  float pv[NLD];
+  load_patch(blockIdx.x, pv);
   for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     const int n = tile / (tiles_y * tiles_x);
     const int rem = tile - n * (tiles_y * tiles_x);
     const int oy0 = (rem / tiles_x) * ST_TH, ox0 = (rem % tiles_x) * ST_TW;
-    const int iy0 = oy0 * 2 - 1, ix0 = ox0 * 2 - 1;
-    // ---- input patch, coalesced along the image rows; all loads are issued before the first shared-memory store so
-    //      that their latencies overlap (a load->store loop serialises on every load)
-    {
-      constexpr int TOTAL = CIN * ST_PH * ST_PW;
-      constexpr int NLD = (TOTAL + 127) / 128;
-      float v[NLD];
 #pragma unroll
-      for (int u = 0; u < NLD; ++u) {
-        const int i = tid + u * 128;
-        const int c = i / (ST_PH * ST_PW);
-        const int r = i - c * (ST_PH * ST_PW);
-        const int py = r / ST_PW, px = r - py * ST_PW;
-        const int iy = iy0 + py, ix = ix0 + px;
-        v[u] = 0.f;
-        if (i < TOTAL && iy >= 0 && iy < H && ix >= 0 && ix < W)
-          v[u] = __ldg(x + ((static_cast<int64_t>(n) * CIN + c) * H + iy) * W + ix);
-      }
-#pragma unroll
-      for (int u = 0; u < NLD; ++u) {
-        const int i = tid + u * 128;
-        const int c = i / (ST_PH * ST_PW);
-        const int r = i - c * (ST_PH * ST_PW);
-        const int py = r / ST_PW, px = r - py * ST_PW;
-        if (i < TOTAL) patch[c][py][px] = v[u];
-      }
+    for (int u = 0; u < NLD; ++u) {
+      const int i = tid + u * 128;
+      const int c = i / (ST_PH * ST_PW);
+      const int r = i - c * (ST_PH * ST_PW);
+      const int py = r / ST_PW, px = r - py * ST_PW;
+      if (i < TOTAL) patch[c][py][px] = pv[u];
     }
+    load_patch(tile + gridDim.x, pv);      // prefetch (no-op past the last tile)
     __syncthreads();
     // ---- this pixel's operand row: slots [0, K) = hi, [32, 32 + K) = lo, the rest zero
     {

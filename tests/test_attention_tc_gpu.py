@@ -193,3 +193,31 @@ def test_stem_tc(dev, tc, split, cin, h, w):
     _report(test="stem_tc", split=split, cin=cin, h=h, w=w, err=err, ref_max=float(ref.abs().max()))
     assert tuple(y.shape) == (nb, h // 2, w // 2, 128 if split else 64)
     assert err <= (2e-5 if split else 4e-3), err       # fp16 output rounding dominates the single-precision mode
+
+
+@pytest.mark.parametrize("split", [False, True])
+def test_attention_tc_head_dim_80(dev, tc, split):
+    """Head dim 80 = d_model 78 of the HRFormer-B inter-human stage padded to the K=16 step (pad channels are zero)."""
+    from i2r_b200.packing import merge_pair, split_pair
+    d, real, lens = 80, 78, [1536, 296, 192]      # token totals must be multiples of 8 (V^T row stride)
+    g = torch.Generator().manual_seed(80)
+    t = sum(lens)
+    q32, k32, v32 = (torch.randn(t, d, generator=g) for _ in range(3))
+    for m in (q32, k32, v32):
+        m[:, real:] = 0
+    cu = torch.tensor([0] + list(torch.tensor(lens).cumsum(0)), dtype=torch.int32, device=dev)
+    scale = 1.0 / math.sqrt(real)
+    if split:
+        q, k, v = split_pair(q32), split_pair(k32), split_pair(v32)
+        out = tc.attention_tc(q.to(dev), k.to(dev), v.t().contiguous().to(dev), cu, max(lens), scale, split=True)
+        torch.cuda.synchronize()
+        got, ref = merge_pair(out.cpu()).double(), _ref(merge_pair(q), merge_pair(k), merge_pair(v), lens, scale)
+    else:
+        q, k, v = q32.half(), k32.half(), v32.half()
+        out = tc.attention_tc(q.to(dev), k.to(dev), v.t().contiguous().to(dev), cu, max(lens), scale)
+        torch.cuda.synchronize()
+        got, ref = out.cpu().double(), _ref(q, k, v, lens, scale)
+    err = float((got - ref).abs().max())
+    _report(test="attention_tc_d80", split=split, err=err)
+    assert err <= (4e-4 if split else 3e-3), err
+    assert float(got[:, real:].abs().max()) == 0.0
