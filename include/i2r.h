@@ -171,6 +171,22 @@ int i2r_encoder_tail(const void* attn, int ld_attn, const void* src, int ld_src,
                      void* out_pos, int ld, const void* wimg, const float* params, int T, int d_model, int dim_ff,
                      float eps, int split, void* stream);
 
+/* ---- HBM-bound building blocks of the HRFormer-B first stage (lib/models/hrformer.py) ----
+ * Depthwise 3x3 convolution (padding 1, stride 1 or 2) + per-channel scale / bias (folded BatchNorm and conv bias) +
+ * activation (0 none, 1 ReLU, 2 erf-GELU) on fp16 NHWC (split: pair tensors).  w: fp32 [9][C] tap-major.  Replaces
+ * MlpDWBN.dw3x3/norm2/act2 (:1094-1119) and the depthwise stride-2 convs of the fuse layers (:1652-1703). */
+int i2r_dwconv3x3(const void* x, const float* w, const float* scale, const float* bias, void* y, int NB, int H, int W,
+                  int C, int stride, int act, int split, void* stream);
+/* y = [relu](x0 + sum_k bilinear_up(t_k, 2^shift_k)), align_corners = False (F.interpolate arithmetic): the
+ * higher-resolution outputs of HighResolutionTransformerModule's fuse layers (:1626-1644, :1714-1731) with the 1x1
+ * conv + BN terms t_k computed at their own resolution.  t2 / t3 optional (NULL). */
+int i2r_upsum_bilinear(const void* x0, const void* t1, int shift1, const void* t2, int shift2, const void* t3, int shift3,
+                       void* y, int NB, int H, int W, int C, int relu, int split, void* stream);
+/* LayerNorm over the first C_real channels of rows padded to C_pad (<= 768, multiple of 8) channels; pad channels are
+ * written as zero.  eps is a parameter (1e-6 in GeneralTransformerBlock, :1198). */
+int i2r_layernorm_padded(const void* x, const float* gamma, const float* beta, void* y, int rows, int C_real, int C_pad,
+                         float eps, int split, void* stream);
+
 /* y = LayerNorm(x) * gamma + beta over the last dim C (<= 256, multiple of 8), fp16 in/out, fp32
  * math; optional y2 = y + pos (the next layer's q/k input).  (interformer_pureMulti.py:206,:209) */
 int i2r_layernorm(const void* x, const float* gamma, const float* beta, const void* pos, void* y, void* y2,

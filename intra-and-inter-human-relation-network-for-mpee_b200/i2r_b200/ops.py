@@ -388,6 +388,49 @@ class Runner:
         self.launches += 1
         return out, out_pos
 
+    # ------------------------------------------------------------------ HRFormer-B building blocks
+    ACT = {None: 0, "none": 0, "relu": 1, "gelu": 2}
+
+    def dwconv3x3(self, x, w, scale, bias, stride=1, act=None):
+        """Depthwise 3x3 (pad 1) + scale/bias + activation.  x: fp16 NHWC (pair tensor when self.split); w fp32 [9, C]."""
+        nb, h, wd, cw = x.shape
+        c = cw // 2 if self.split else cw
+        assert x.is_contiguous() and w.shape == (9, c) and w.dtype == torch.float32 and w.is_contiguous()
+        y = torch.empty((nb, (h + stride - 1) // stride, (wd + stride - 1) // stride, cw), dtype=torch.float16,
+                        device=x.device)
+        capi.check(self.lib.i2r_dwconv3x3(x.data_ptr(), w.data_ptr(), scale.data_ptr(), bias.data_ptr(), y.data_ptr(),
+                                           nb, h, wd, c, stride, self.ACT[act], int(self.split), _stream_ptr()),
+                   "i2r_dwconv3x3")
+        self.launches += 1
+        return y
+
+    def upsum_bilinear(self, x0, terms, relu=True):
+        """relu(x0 + sum bilinear_up(t, 2^shift)) (align_corners=False).  terms: up to three (tensor, shift)."""
+        nb, h, w, cw = x0.shape
+        c = cw // 2 if self.split else cw
+        assert 1 <= len(terms) <= 3 and x0.is_contiguous()
+        args = []
+        for t, s in list(terms) + [(None, 0)] * (3 - len(terms)):
+            assert t is None or (t.is_contiguous() and t.shape == (nb, h >> s, w >> s, cw))
+            args += [t.data_ptr() if t is not None else None, s]
+        y = torch.empty_like(x0)
+        capi.check(self.lib.i2r_upsum_bilinear(x0.data_ptr(), *args, y.data_ptr(), nb, h, w, c, int(relu),
+                                                int(self.split), _stream_ptr()), "i2r_upsum_bilinear")
+        self.launches += 1
+        return y
+
+    def layernorm_padded(self, x2d, gamma, beta, c_real, eps=1e-6):
+        """LayerNorm over the first c_real channels of rows padded to C_pad channels (pad channels come out zero)."""
+        rows, cw = x2d.shape
+        cp = cw // 2 if self.split else cw
+        assert x2d.is_contiguous() and gamma.numel() == cp and beta.numel() == cp
+        y = torch.empty_like(x2d)
+        capi.check(self.lib.i2r_layernorm_padded(x2d.data_ptr(), gamma.data_ptr(), beta.data_ptr(), y.data_ptr(), rows,
+                                                  c_real, cp, eps, int(self.split), _stream_ptr()),
+                   "i2r_layernorm_padded")
+        self.launches += 1
+        return y
+
 
 class EncoderTailParams:
     """Device-resident operand image of i2r_encoder_tail for one encoder layer."""

@@ -1,0 +1,115 @@
+"""GPU parity of the HRFormer-B building-block kernels (depthwise 3x3 + BN + GELU, bilinear fuse, padded LayerNorm)
+against float64 torch restatements of the reference ops (lib/models/hrformer.py:1094-1119, :1616-1731, :1198)."""
+import json
+import os
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+import paths
+
+pytestmark = pytest.mark.gpu
+REPORT = os.path.join(paths.REPO, "gpurun_out", "kernel_report.jsonl")
+
+
+def _report(**kw):
+    os.makedirs(os.path.dirname(REPORT), exist_ok=True)
+    with open(REPORT, "a") as f:
+        f.write(json.dumps(kw) + "\n")
+
+
+@pytest.fixture(scope="module")
+def dev():
+    return torch.device("cuda:0")
+
+
+@pytest.fixture(scope="module")
+def tc(dev):
+    from i2r_b200.ops import Runner
+    return Runner(dev, impl=0)
+
+
+def _enc(v, split):
+    from i2r_b200.packing import split_pair
+    return split_pair(v) if split else v.half()
+
+
+def _dec(v, split):
+    from i2r_b200.packing import merge_pair
+    return merge_pair(v.cpu()).double() if split else v.cpu().double()
+
+
+@pytest.mark.parametrize("split", [False, True])
+@pytest.mark.parametrize("c,h,w,stride,act", [(312, 64, 48, 1, "gelu"), (80, 32, 24, 2, None), (640, 7, 5, 1, "relu"),
+                                              (160, 96, 72, 2, "gelu")])
+def test_dwconv3x3(dev, tc, split, c, h, w, stride, act):
+    g = torch.Generator().manual_seed(c + h + stride)
+    nb = 2
+    x32 = torch.randn(nb, h, w, c, generator=g)
+    wt = (torch.rand(c, 1, 3, 3, generator=g) * 2 - 1) / 3
+    sc = torch.rand(c, generator=g) + 0.5
+    bi = torch.randn(c, generator=g) * 0.1
+    x = _enc(x32, split)
+    tc.split = split
+    try:
+        y = tc.dwconv3x3(x.to(dev), wt.reshape(c, 9).t().contiguous().to(dev), sc.to(dev), bi.to(dev), stride, act)
+        torch.cuda.synchronize()
+    finally:
+        tc.split = False
+    xin = _dec(x, split).permute(0, 3, 1, 2)
+    ref = F.conv2d(xin, wt.double(), None, stride, 1, 1, c) * sc.double().view(1, -1, 1, 1) + bi.double().view(1, -1, 1, 1)
+    ref = {"gelu": F.gelu, "relu": F.relu, None: lambda t: t}[act](ref).permute(0, 2, 3, 1)
+    err = float((_dec(y, split) - ref).abs().max())
+    _report(test="dwconv3x3", split=split, c=c, stride=stride, act=act, err=err)
+    assert tuple(y.shape) == (nb, (h + stride - 1) // stride, (w + stride - 1) // stride, (2 if split else 1) * c)
+    assert err <= (5e-6 if split else 4e-3), err
+
+
+@pytest.mark.parametrize("split", [False, True])
+@pytest.mark.parametrize("shifts", [(1,), (1, 2), (1, 2, 3)])
+def test_upsum_bilinear(dev, tc, split, shifts):
+    g = torch.Generator().manual_seed(10 * len(shifts))
+    nb, h, w, c = 2, 64, 48, 80
+    x32 = torch.randn(nb, h, w, c, generator=g)
+    ts32 = [torch.randn(nb, h >> s, w >> s, c, generator=g) for s in shifts]
+    x0, ts = _enc(x32, split), [_enc(t, split) for t in ts32]
+    tc.split = split
+    try:
+        y = tc.upsum_bilinear(x0.to(dev), [(t.to(dev), s) for t, s in zip(ts, shifts)], relu=True)
+        torch.cuda.synchronize()
+    finally:
+        tc.split = False
+    ref = _dec(x0, split).permute(0, 3, 1, 2)
+    for t, s in zip(ts, shifts):
+        ref = ref + F.interpolate(_dec(t, split).permute(0, 3, 1, 2), scale_factor=2 ** s, mode="bilinear",
+                                  align_corners=False)
+    ref = F.relu(ref).permute(0, 2, 3, 1)
+    err = float((_dec(y, split) - ref).abs().max())
+    _report(test="upsum_bilinear", split=split, shifts=list(shifts), err=err)
+    assert err <= (5e-6 if split else 4e-3), err
+
+
+@pytest.mark.parametrize("split", [False, True])
+@pytest.mark.parametrize("c_real,c_pad", [(78, 80), (156, 160), (312, 320), (624, 640), (96, 96)])
+def test_layernorm_padded(dev, tc, split, c_real, c_pad):
+    g = torch.Generator().manual_seed(c_real)
+    rows = 1001
+    x32 = torch.randn(rows, c_pad, generator=g) * 2 + 0.3
+    x32[:, c_real:] = 7.0            # garbage in the pad channels must not leak into the statistics
+    gamma = torch.rand(c_pad, generator=g) + 0.5
+    beta = torch.randn(c_pad, generator=g) * 0.1
+    x = _enc(x32, split)
+    tc.split = split
+    try:
+        y = tc.layernorm_padded(x.to(dev), gamma.to(dev), beta.to(dev), c_real, eps=1e-6)
+        torch.cuda.synchronize()
+    finally:
+        tc.split = False
+    xin = _dec(x, split)[:, :c_real]
+    ref = F.layer_norm(xin, (c_real,), gamma[:c_real].double(), beta[:c_real].double(), 1e-6)
+    got = _dec(y, split)
+    err = float((got[:, :c_real] - ref).abs().max())
+    _report(test="layernorm_padded", split=split, c_real=c_real, err=err)
+    assert err <= (5e-6 if split else 4e-3), err
+    assert float(got[:, c_real:].abs().max()) == 0.0 if c_pad > c_real else True
