@@ -187,6 +187,23 @@ int i2r_upsum_bilinear(const void* x0, const void* t1, int shift1, const void* t
 int i2r_layernorm_padded(const void* x, const float* gamma, const float* beta, void* y, int rows, int C_real, int C_pad,
                          float eps, int split, void* stream);
 
+/* Window-major token layout of InterlacedPoolAttention (:949-1000): the H x W map is centre-padded with zeros to
+ * multiples of ws and cut into ws x ws windows; row = ((n*QH + qh)*QW + qw)*ws*ws + ph*ws + pw.
+ * i2r_window_rows() = NB * Hp * Wp rows.  i2r_ln_window_gather: y[row] = LayerNorm(x[pixel]) (first C_real of C_pad
+ * channels), zero rows at padded positions (the reference pads after norm1).  i2r_window_scatter_add:
+ * y[pixel] = x[pixel] + a[row(pixel)] -- reverse permutation, de-pad and the residual of GeneralTransformerBlock (:1234). */
+int64_t i2r_window_rows(int NB, int H, int W, int ws);
+int i2r_ln_window_gather(const void* x, const float* gamma, const float* beta, void* y, int NB, int H, int W, int C_real,
+                         int C_pad, int ws, float eps, int split, void* stream);
+int i2r_window_scatter_add(const void* x, const void* a, void* y, int NB, int H, int W, int C, int ws, int split,
+                           void* stream);
+/* softmax(scale * q k^T) v for nwin windows of win_len consecutive token rows and `heads` heads of head_pad (= 48:
+ * head_dim 39 zero-padded by the weight packing) channels each; no relative position bias (its addition is commented
+ * out in the reference, :866-888) and no mask (padded tokens take part).  MHA_.forward (:627-935). */
+int i2r_window_attention(const void* q, const void* k, const void* v, void* out, int ldq, int ldk, int ldv, int ldo,
+                         int nwin, int win_len, int heads, int head_pad, float scale, int split, int q_lo, int k_lo,
+                         int v_lo, int o_lo, void* stream);
+
 /* y = LayerNorm(x) * gamma + beta over the last dim C (<= 256, multiple of 8), fp16 in/out, fp32
  * math; optional y2 = y + pos (the next layer's q/k input).  (interformer_pureMulti.py:206,:209) */
 int i2r_layernorm(const void* x, const float* gamma, const float* beta, const void* pos, void* y, void* y2,

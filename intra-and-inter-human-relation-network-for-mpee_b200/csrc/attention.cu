@@ -51,7 +51,7 @@ __global__ void __launch_bounds__(128) attention_kernel(const __half* __restrict
                                                         const int32_t* __restrict__ cu_seqlens, float scale_log2e,
                                                         int nsplit, float* __restrict__ opart,
                                                         float* __restrict__ mlpart, int q_lo, int k_lo, int v_lo,
-                                                        int o_lo) {
+                                                        int o_lo, int uniform_len, int head_stride) {
   constexpr int PITCH = (HD + 8) * 2;
   constexpr int TILE = ATT_BK * PITCH;
   constexpr int KS = HD / 16;  // k-steps over the head dim
@@ -60,8 +60,16 @@ __global__ void __launch_bounds__(128) attention_kernel(const __half* __restrict
   pdl_launch_dependents();
   pdl_wait();
   const int seq = blockIdx.y;
-  const int t0 = cu_seqlens[seq];
-  const int L = cu_seqlens[seq + 1] - t0;
+  // window attention (HRFormer): equal-length sequences without an offset table, gridDim.z = heads (no key split)
+  const int t0 = cu_seqlens != nullptr ? cu_seqlens[seq] : seq * uniform_len;
+  const int L = cu_seqlens != nullptr ? cu_seqlens[seq + 1] - t0 : uniform_len;
+  if (head_stride > 0) {
+    const int hoff = blockIdx.z * head_stride;
+    q += hoff;
+    k += hoff;
+    v += hoff;
+    out += hoff;
+  }
   const int q0 = blockIdx.x * ATT_BQ;
   if (q0 >= L) return;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -75,7 +83,7 @@ __global__ void __launch_bounds__(128) attention_kernel(const __half* __restrict
   // split-KV: this CTA covers key tiles [kt_begin, kt_end) of the sequence (all of them when nsplit == 1)
   const int ntiles_all = (L + ATT_BK - 1) / ATT_BK;
   const int per_split = (ntiles_all + nsplit - 1) / nsplit;
-  const int kt_begin = blockIdx.z * per_split;
+  const int kt_begin = (head_stride > 0 ? 0 : blockIdx.z) * per_split;
   const int kt_end = min(ntiles_all, kt_begin + per_split);
   if (kt_begin < kt_end) {
     load_tile<HD>(sQ, q, ldq, t0 + q0, min(ATT_BQ, L - q0), tid);
@@ -354,7 +362,7 @@ static int launch_attention(const void* q, const void* k, const void* v, void* o
   launch_pdl(attention_kernel<HD, SPLIT>, grid, dim3(128), smem, st,
       static_cast<const __half*>(q), static_cast<const __half*>(k), static_cast<const __half*>(v),
       static_cast<__half*>(out), ldq, ldk, ldv, ldo, cu, scale * 1.4426950408889634f, nsplit, opart, mlpart, q_lo, k_lo,
-      v_lo, o_lo);
+      v_lo, o_lo, 0, 0);
   int rc = check_launch("attention_kernel");
   if (rc || nsplit == 1) return rc;
   launch_pdl(attention_merge_kernel<HD>, dim3((total_tokens + 7) / 8), dim3(256), 0, st, opart, mlpart, static_cast<__half*>(out), ldo,
@@ -398,4 +406,55 @@ extern "C" int i2r_attention_varlen(const void* q, const void* k, const void* v,
       set_error("i2r_attention_varlen: head dim %d unsupported (80 or 96)", D);
       return I2R_E_UNSUPPORTED;
   }
+}
+
+
+// Window attention of HRFormer-B (InterlacedPoolAttention / MHA_, lib/models/hrformer.py:1164-1180, :627-935): nwin
+// windows of `win_len` (49) consecutive token rows each (window-major layout written by i2r_ln_window_gather, padded
+// tokens included), `heads` heads of `head_pad` (48) channels each (head_dim 39 zero-padded by the packing of the
+// q/k/v projections); softmax(scale q k^T) v per (window, head), no relative position bias (:866-888), no mask.
+namespace i2r {
+template <bool SPLIT>
+static int launch_window_attention(const void* q, const void* k, const void* v, void* out, int ldq, int ldk, int ldv,
+                                   int ldo, int nwin, int win_len, int heads, float scale, int q_lo, int k_lo, int v_lo,
+                                   int o_lo, cudaStream_t st) {
+  constexpr int HD = 48;
+  constexpr int smem = (SPLIT ? 10 : 5) * ATT_BK * (HD + 8) * 2;
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(attention_kernel<HD, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) {
+      set_error("cudaFuncSetAttribute(window attention): %s", cudaGetErrorString(e));
+      return static_cast<int>(e);
+    }
+    attr_done = true;
+  }
+  dim3 grid((win_len + ATT_BQ - 1) / ATT_BQ, nwin, heads);
+  launch_pdl(attention_kernel<HD, SPLIT>, grid, dim3(128), smem, st, static_cast<const __half*>(q),
+             static_cast<const __half*>(k), static_cast<const __half*>(v), static_cast<__half*>(out), ldq, ldk, ldv, ldo,
+             static_cast<const int32_t*>(nullptr), scale * 1.4426950408889634f, 1, static_cast<float*>(nullptr),
+             static_cast<float*>(nullptr), q_lo, k_lo, v_lo, o_lo, win_len, HD);
+  return check_launch("attention_kernel(window)");
+}
+}  // namespace i2r
+
+extern "C" int i2r_window_attention(const void* q, const void* k, const void* v, void* out, int ldq, int ldk, int ldv,
+                                    int ldo, int nwin, int win_len, int heads, int head_pad, float scale, int split,
+                                    int q_lo, int k_lo, int v_lo, int o_lo, void* stream) {
+  using namespace i2r;
+  if (!q || !k || !v || !out || nwin <= 0 || win_len <= 0 || win_len > 64 * 1024 || heads <= 0 || head_pad != 48 ||
+      heads > 65535 || (ldq | ldk | ldv | ldo) % 8 != 0 ||
+      (split && (q_lo | k_lo | v_lo | o_lo) % 8 != 0)) {
+    set_error("i2r_window_attention: bad arguments (head_pad must be 48, strides multiples of 8)");
+    return I2R_E_BADARG;
+  }
+  if (nwin > 65535) {
+    set_error("i2r_window_attention: more than 65535 windows per launch (grid.y); split the batch");
+    return I2R_E_UNSUPPORTED;
+  }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  return split ? launch_window_attention<true>(q, k, v, out, ldq, ldk, ldv, ldo, nwin, win_len, heads, scale, q_lo, k_lo,
+                                               v_lo, o_lo, st)
+               : launch_window_attention<false>(q, k, v, out, ldq, ldk, ldv, ldo, nwin, win_len, heads, scale, 0, 0, 0, 0,
+                                                st);
 }

@@ -226,6 +226,112 @@ __global__ void __launch_bounds__(256) layernorm_padded_kernel(const __half* __r
   }
 }
 
+// ------------------------------------------------------------------------------------------------ window layout
+// Window-major token layout of InterlacedPoolAttention (lib/models/hrformer.py:949-986): the H x W map is centre-padded
+// with zeros to multiples of ws, cut into ws x ws windows; output row = ((n * QH + qh) * QW + qw) * ws*ws + ph * ws + pw.
+// ln_window_gather = LayerNorm (first C_real of C_pad channels) of every pixel written at its window row; rows of padded
+// positions are zero (the reference pads AFTER norm1, so their q/k/v are the projection biases).
+template <bool PAIR>
+__global__ void __launch_bounds__(256) ln_window_gather_kernel(const __half* __restrict__ x,
+                                                               const float* __restrict__ gamma,
+                                                               const float* __restrict__ beta, __half* __restrict__ y,
+                                                               int NB, int H, int W, int Cr, int Cp, int ws, float eps) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int Hp = (H + ws - 1) / ws * ws, Wp = (W + ws - 1) / ws * ws;
+  const int pt = (Hp - H) / 2, pl = (Wp - W) / 2;
+  const int QH = Hp / ws, QW = Wp / ws;
+  const int64_t rows = static_cast<int64_t>(NB) * Hp * Wp;
+  const int64_t row = (blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const int pos = static_cast<int>(row % (ws * ws));
+  const int64_t win = row / (ws * ws);
+  const int qw = static_cast<int>(win % QW), qh = static_cast<int>((win / QW) % QH);
+  const int n = static_cast<int>(win / (static_cast<int64_t>(QW) * QH));
+  const int py = qh * ws + pos / ws - pt, px = qw * ws + pos % ws - pl;
+  const int64_t ld = PAIR ? 2 * Cp : Cp;
+  __half* yr = y + row * ld;
+  const bool inside = py >= 0 && py < H && px >= 0 && px < W;
+  const __half* xr = x + ((static_cast<int64_t>(n) * H + (inside ? py : 0)) * W + (inside ? px : 0)) * ld;
+  float v[3][8];
+  float s = 0.f;
+#pragma unroll
+  for (int g = 0; g < 3; ++g) {
+    const int c = (lane + 32 * g) * 8;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[g][i] = 0.f;
+    if (c < Cp && inside) {
+      hk_load<PAIR>(xr, Cp, c, v[g]);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        if (c + i >= Cr) v[g][i] = 0.f;
+        s += v[g][i];
+      }
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  const float mean = s / Cr;
+  float sq = 0.f;
+#pragma unroll
+  for (int g = 0; g < 3; ++g) {
+    const int c = (lane + 32 * g) * 8;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      if (c + i < Cr) {
+        const float d = v[g][i] - mean;
+        sq += d * d;
+      }
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+  const float rstd = rsqrtf(sq / Cr + eps);
+#pragma unroll
+  for (int g = 0; g < 3; ++g) {
+    const int c = (lane + 32 * g) * 8;
+    if (c < Cp) {
+      float o8[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        o8[i] = (inside && c + i < Cr) ? (v[g][i] - mean) * rstd * __ldg(gamma + c + i) + __ldg(beta + c + i) : 0.f;
+      hk_store<PAIR>(yr, Cp, c, o8);
+    }
+  }
+}
+
+// y[pixel] = x[pixel] + a[window row of that pixel]  (reverse permutation + de-pad + residual, :987-1000, :1234)
+template <bool PAIR>
+__global__ void __launch_bounds__(256) window_scatter_add_kernel(const __half* __restrict__ x,
+                                                                 const __half* __restrict__ a, __half* __restrict__ y,
+                                                                 int NB, int H, int W, int C, int ws) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int Hp = (H + ws - 1) / ws * ws, Wp = (W + ws - 1) / ws * ws;
+  const int pt = (Hp - H) / 2, pl = (Wp - W) / 2;
+  const int QH = Hp / ws, QW = Wp / ws;
+  const int cv = C >> 3;
+  const int ld = PAIR ? 2 * C : C;
+  const int64_t total = static_cast<int64_t>(NB) * H * W * cv;
+  for (int64_t idx = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(idx % cv) * 8;
+    const int64_t p = idx / cv;
+    const int wx = static_cast<int>(p % W);
+    const int hy = static_cast<int>((p / W) % H);
+    const int n = static_cast<int>(p / (static_cast<int64_t>(W) * H));
+    const int yy = hy + pt, xx = wx + pl;
+    const int64_t row = ((static_cast<int64_t>(n) * QH + yy / ws) * QW + xx / ws) * (ws * ws) + (yy % ws) * ws + xx % ws;
+    float v[8], t[8];
+    hk_load<PAIR>(x + p * ld, C, c, v);
+    hk_load<PAIR>(a + row * ld, C, c, t);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] += t[i];
+    hk_store<PAIR>(y + p * ld, C, c, v);
+  }
+}
+
 }  // namespace i2r
 
 using namespace i2r;
@@ -288,4 +394,48 @@ extern "C" int i2r_layernorm_padded(const void* x, const float* gamma, const flo
                static_cast<const __half*>(x), gamma, beta, static_cast<__half*>(y), rows, C_real, C_pad, eps);
   }
   return check_launch("layernorm_padded_kernel");
+}
+
+extern "C" int64_t i2r_window_rows(int NB, int H, int W, int ws) {
+  if (NB <= 0 || H <= 0 || W <= 0 || ws <= 0) return 0;
+  return static_cast<int64_t>(NB) * ((H + ws - 1) / ws * ws) * ((W + ws - 1) / ws * ws);
+}
+
+extern "C" int i2r_ln_window_gather(const void* x, const float* gamma, const float* beta, void* y, int NB, int H, int W,
+                                    int C_real, int C_pad, int ws, float eps, int split, void* stream) {
+  if (!x || !gamma || !beta || !y || NB <= 0 || H <= 0 || W <= 0 || ws <= 0 || C_pad % 8 != 0 || C_pad > 768 ||
+      C_real < 1 || C_real > C_pad) {
+    set_error("i2r_ln_window_gather: bad arguments (C_real=%d C_pad=%d ws=%d)", C_real, C_pad, ws);
+    return I2R_E_BADARG;
+  }
+  const int64_t rows = i2r_window_rows(NB, H, W, ws);
+  const int wpb = 8;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const dim3 grid(static_cast<unsigned>((rows + wpb - 1) / wpb));
+  if (split) {
+    launch_pdl(ln_window_gather_kernel<true>, grid, dim3(wpb * 32), 0, st, static_cast<const __half*>(x), gamma, beta,
+               static_cast<__half*>(y), NB, H, W, C_real, C_pad, ws, eps);
+  } else {
+    launch_pdl(ln_window_gather_kernel<false>, grid, dim3(wpb * 32), 0, st, static_cast<const __half*>(x), gamma, beta,
+               static_cast<__half*>(y), NB, H, W, C_real, C_pad, ws, eps);
+  }
+  return check_launch("ln_window_gather_kernel");
+}
+
+extern "C" int i2r_window_scatter_add(const void* x, const void* a, void* y, int NB, int H, int W, int C, int ws,
+                                      int split, void* stream) {
+  if (!x || !a || !y || NB <= 0 || H <= 0 || W <= 0 || ws <= 0 || C % 8 != 0) {
+    set_error("i2r_window_scatter_add: bad arguments");
+    return I2R_E_BADARG;
+  }
+  const int64_t items = static_cast<int64_t>(NB) * H * W * (C / 8);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (split) {
+    launch_pdl(window_scatter_add_kernel<true>, dim3(hk_grid(items, 256)), dim3(256), 0, st,
+               static_cast<const __half*>(x), static_cast<const __half*>(a), static_cast<__half*>(y), NB, H, W, C, ws);
+  } else {
+    launch_pdl(window_scatter_add_kernel<false>, dim3(hk_grid(items, 256)), dim3(256), 0, st,
+               static_cast<const __half*>(x), static_cast<const __half*>(a), static_cast<__half*>(y), NB, H, W, C, ws);
+  }
+  return check_launch("window_scatter_add_kernel");
 }

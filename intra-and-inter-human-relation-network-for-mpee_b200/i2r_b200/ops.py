@@ -431,6 +431,44 @@ class Runner:
         self.launches += 1
         return y
 
+    def ln_window_gather(self, x, gamma, beta, c_real, ws=7, eps=1e-6):
+        """LayerNorm + window-major (padded) token layout.  x: [NB, H, W, C_pad] -> [NB*Hp*Wp, C_pad] (pair when split)."""
+        nb, h, w, cw = x.shape
+        cp = cw // 2 if self.split else cw
+        assert x.is_contiguous() and gamma.numel() == cp
+        rows = int(self.lib.i2r_window_rows(nb, h, w, ws))
+        y = torch.empty((rows, cw), dtype=torch.float16, device=x.device)
+        capi.check(self.lib.i2r_ln_window_gather(x.data_ptr(), gamma.data_ptr(), beta.data_ptr(), y.data_ptr(), nb, h, w,
+                                                  c_real, cp, ws, eps, int(self.split), _stream_ptr()),
+                   "i2r_ln_window_gather")
+        self.launches += 1
+        return y
+
+    def window_scatter_add(self, x, a, ws=7):
+        """x + (window-major rows `a` scattered back to pixels, padded positions dropped)."""
+        nb, h, w, cw = x.shape
+        c = cw // 2 if self.split else cw
+        assert x.is_contiguous() and a.is_contiguous() and a.shape == (int(self.lib.i2r_window_rows(nb, h, w, ws)), cw)
+        y = torch.empty_like(x)
+        capi.check(self.lib.i2r_window_scatter_add(x.data_ptr(), a.data_ptr(), y.data_ptr(), nb, h, w, c, ws,
+                                                    int(self.split), _stream_ptr()), "i2r_window_scatter_add")
+        self.launches += 1
+        return y
+
+    def window_attention(self, q, k, v, win_len, heads, scale, head_pad=48):
+        """q, k, v: fp16 2-D views [T, heads*head_pad] (split: hi views of pair rows [.., 2*heads*head_pad]); T = nwin *
+        win_len.  Returns [T, heads*head_pad] ([T, 2*heads*head_pad] pair)."""
+        t, cq = q.shape
+        assert cq == heads * head_pad and t % win_len == 0 and q.stride(1) == 1
+        out = torch.empty((t, 2 * cq if self.split else cq), dtype=torch.float16, device=q.device)
+        lo = cq if self.split else 0
+        capi.check(self.lib.i2r_window_attention(q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), q.stride(0),
+                                                  k.stride(0), v.stride(0), out.stride(0), t // win_len, win_len, heads,
+                                                  head_pad, scale, int(self.split), lo, lo, lo, lo, _stream_ptr()),
+                   "i2r_window_attention")
+        self.launches += 1
+        return out
+
 
 class EncoderTailParams:
     """Device-resident operand image of i2r_encoder_tail for one encoder layer."""

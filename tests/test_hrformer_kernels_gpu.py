@@ -113,3 +113,77 @@ def test_layernorm_padded(dev, tc, split, c_real, c_pad):
     _report(test="layernorm_padded", split=split, c_real=c_real, err=err)
     assert err <= (5e-6 if split else 4e-3), err
     assert float(got[:, c_real:].abs().max()) == 0.0 if c_pad > c_real else True
+
+
+def _window_rows_ref(x, ws=7):
+    """[NB, H, W, C] -> window-major rows [NB*QH*QW*ws*ws, C] with centre zero padding (hrformer.py:949-986)."""
+    nb, h, w, c = x.shape
+    ph, pw = (-h) % ws, (-w) % ws
+    xp = F.pad(x, (0, 0, pw // 2, pw - pw // 2, ph // 2, ph - ph // 2))
+    hp, wp = h + ph, w + pw
+    return xp.view(nb, hp // ws, ws, wp // ws, ws, c).permute(0, 1, 3, 2, 4, 5).reshape(-1, c), (ph, pw, hp, wp)
+
+
+@pytest.mark.parametrize("split", [False, True])
+@pytest.mark.parametrize("c_real,c_pad,h,w", [(78, 80, 64, 48), (156, 160, 32, 24), (624, 640, 8, 6), (78, 80, 96, 72)])
+def test_ln_window_gather_and_scatter(dev, tc, split, c_real, c_pad, h, w):
+    g = torch.Generator().manual_seed(c_real + h)
+    nb = 2
+    x32 = torch.randn(nb, h, w, c_pad, generator=g) * 1.5 + 0.2
+    x32[..., c_real:] = 0
+    gamma = torch.rand(c_pad, generator=g) + 0.5
+    beta = torch.randn(c_pad, generator=g) * 0.1
+    x = _enc(x32, split)
+    tc.split = split
+    try:
+        rows = tc.ln_window_gather(x.to(dev), gamma.to(dev), beta.to(dev), c_real)
+        back = tc.window_scatter_add(x.to(dev), rows)
+        torch.cuda.synchronize()
+    finally:
+        tc.split = False
+    xin = _dec(x, split)
+    ln = torch.zeros_like(xin)
+    ln[..., :c_real] = F.layer_norm(xin[..., :c_real], (c_real,), gamma[:c_real].double(), beta[:c_real].double(), 1e-6)
+    ref_rows, _ = _window_rows_ref(ln)
+    got = _dec(rows, split)
+    err = float((got - ref_rows).abs().max())
+    # scatter-add: x + LN(x) at every pixel (the window rows hold LN(x); padded rows are dropped)
+    err2 = float((_dec(back, split) - (xin + ln)).abs().max())
+    _report(test="ln_window_gather", split=split, c=c_real, h=h, err=err, err_scatter=err2)
+    assert tuple(got.shape) == tuple(ref_rows.shape)
+    assert err <= (5e-6 if split else 4e-3) and err2 <= (1e-5 if split else 8e-3), (err, err2)
+
+
+@pytest.mark.parametrize("split", [False, True])
+@pytest.mark.parametrize("heads,nwin", [(2, 140), (16, 4)])
+def test_window_attention(dev, tc, split, heads, nwin):
+    """49-token windows, head_dim 39 padded to 48 (pad channels zero), scale 39**-0.5, no bias / mask."""
+    from i2r_b200.packing import merge_pair, split_pair
+    g = torch.Generator().manual_seed(heads)
+    hd, hp, wl = 39, 48, 49
+    t = nwin * wl
+    qkv32 = torch.randn(3, t, heads, hp, generator=g)
+    qkv32[..., hd:] = 0
+    qkv32 = qkv32.reshape(3, t, heads * hp)
+    scale = hd ** -0.5
+    if split:
+        q, k, v = (split_pair(m) for m in qkv32)
+        vals = [merge_pair(m).double() for m in (q, k, v)]
+        cq = heads * hp
+        args = [m.to(dev)[:, :cq] for m in (q, k, v)]
+    else:
+        q, k, v = (m.half() for m in qkv32)
+        vals = [m.double() for m in (q, k, v)]
+        args = [m.to(dev) for m in (q, k, v)]
+    tc.split = split
+    try:
+        out = tc.window_attention(args[0], args[1], args[2], wl, heads, scale)
+        torch.cuda.synchronize()
+    finally:
+        tc.split = False
+    qd, kd, vd = (m.view(nwin, wl, heads, hp).permute(0, 2, 1, 3) for m in vals)
+    ref = (torch.softmax(qd @ kd.transpose(-1, -2) * scale, dim=-1) @ vd).permute(0, 2, 1, 3).reshape(t, heads * hp)
+    got = merge_pair(out.cpu()).double() if split else out.cpu().double()
+    err = float((got - ref).abs().max())
+    _report(test="window_attention", split=split, heads=heads, err=err)
+    assert err <= (4e-4 if split else 3e-3), err
