@@ -41,6 +41,8 @@ extern "C" {
 #define I2R_F_OUT_T16 16u     /* i2r_conv_halo only: write fp16 TRANSPOSED, y[c * out_pix_stride + p] (channel-major rows of
                               * out_pix_stride pixels; with I2R_F_SPLIT the lo rows follow the Cout hi rows): the V^T operand of
                               * i2r_attention_tc */
+#define I2R_F_GELU 32u        /* erf-GELU instead of ReLU (MlpDWBN of HRFormer-B, lib/models/hrformer.py:1094-1119)            */
+#define I2R_F_ACT_FIRST 64u   /* y = act(scale * acc + bias) + addends  (instead of act(... + addends)): x + mlp(x), :1236      */
 /* Split-operand mode (the 1e-3 heatmap bar of the TransPose-H families needs ~22-bit operands): activations are
  * fp16 PAIRS -- a pixel holds 2*C channels, [0,C) = hi, [C,2C) = lo, value = hi + lo -- and a product is
  * x_hi*W_hi + x_lo*W_hi + x_hi*W_lo with fp32 accumulation, evaluated as ONE GEMM over K = [x_hi | x_lo | x_hi]

@@ -377,8 +377,20 @@ __device__ __forceinline__ void epilogue_role(const EpiArgs E, const int cta, co
             for (int i = 0; i < 4; ++i) {
               const float2 f0 = unpack_h2(q0[i]), f1 = unpack_h2(q1[i]);
               const float2 g0 = unpack_h2(p0[i]), g1 = unpack_h2(p1[i]);
-              v[2 * i] = fmaxf(__uint_as_float(av[j][2 * i]) + ((f0.x + g0.x) + (f1.x + g1.x)), lo);
-              v[2 * i + 1] = fmaxf(__uint_as_float(av[j][2 * i + 1]) + ((f0.y + g0.y) + (f1.y + g1.y)), lo);
+              const float ax = (f0.x + g0.x) + (f1.x + g1.x), ay = (f0.y + g0.y) + (f1.y + g1.y);
+              if (E.flags & (I2R_F_GELU | I2R_F_ACT_FIRST)) {
+                const float sx = __uint_as_float(av[j][2 * i]), sy = __uint_as_float(av[j][2 * i + 1]);
+                if (E.flags & I2R_F_ACT_FIRST) {
+                  v[2 * i] = epi_act(sx, E.flags) + ax;
+                  v[2 * i + 1] = epi_act(sy, E.flags) + ay;
+                } else {
+                  v[2 * i] = epi_act(sx + ax, E.flags);
+                  v[2 * i + 1] = epi_act(sy + ay, E.flags);
+                }
+              } else {
+                v[2 * i] = fmaxf(__uint_as_float(av[j][2 * i]) + ax, lo);
+                v[2 * i + 1] = fmaxf(__uint_as_float(av[j][2 * i + 1]) + ay, lo);
+              }
             }
             if (E.flags & I2R_F_OUT_T16) {
               // channel-major rows: lanes hold consecutive pixels, so each 2-byte store instruction is coalesced
@@ -692,7 +704,8 @@ __global__ void __launch_bounds__(T_THREADS, 1) conv_halo_kernel(const __grid_co
     const int ew = warp - 4;
     const int n8 = (P.Cout + 7) >> 3, half8 = (n8 + 1) >> 1;   // chunks holding real channels, split over the warp pair
     const int cb = (ew >> 2) ? half8 : 0, ce = (ew >> 2) ? n8 : half8;
-    if ((P.flags & (I2R_F_OUT_NCHW_F32 | I2R_F_OUT_F32 | I2R_F_SPLIT | I2R_F_OUT_T16)) || (P.Cout & 7) || dbg != 0 ||
+    if ((P.flags & (I2R_F_OUT_NCHW_F32 | I2R_F_OUT_F32 | I2R_F_SPLIT | I2R_F_OUT_T16 | I2R_F_GELU | I2R_F_ACT_FIRST)) ||
+        (P.Cout & 7) || dbg != 0 ||
         ce == cb) {
       epilogue_role<1>(E, cta, sbase, tmem_base, ncols, Npad, ew, warp & 3, lane, tr, trace_cap, dbg);
     } else if (P.add1 != nullptr) {

@@ -216,6 +216,12 @@ __device__ __forceinline__ void issue_ksteps(uint32_t d_tmem, uint32_t a_lo, uin
   for (int k2 = 0; k2 < KS; ++k2)
     umma_f16(d_tmem, desc64(a_lo + 2 * k2, a_hi), desc64(b_lo + 2 * k2, b_hi), idesc, k2 ? 1u : acc_first);
 }
+// epilogue activation: ReLU (I2R_F_RELU), erf-GELU (I2R_F_GELU) or identity
+__device__ __forceinline__ float epi_act(float v, uint32_t flags) {
+  if (flags & I2R_F_GELU) return 0.5f * v * (1.f + erff(v * 0.70710678118654752f));
+  if (flags & I2R_F_RELU) return fmaxf(v, 0.f);
+  return v;
+}
 __device__ __forceinline__ uint32_t pack_h2(float a, float b) {
   __half2 h = __floats2half2_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&h);

@@ -227,6 +227,11 @@ __device__ __forceinline__ void run_tile(const i2r_conv_problem& P, const int ti
 #pragma unroll
       for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]) * s_scale[c0 + i] + s_bias[c0 + i];
       if (valid) {
+        const bool act_first = (P.flags & I2R_F_ACT_FIRST) != 0;
+        if (act_first) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] = epi_act(v[i], P.flags);
+        }
         for (int part = 0; part < (split ? 2 : 1); ++part) {   // split addends: hi half, then lo half at +Cout
         const int po = part * Cout;
         if (a0 != nullptr) {
@@ -260,9 +265,9 @@ __device__ __forceinline__ void run_tile(const i2r_conv_problem& P, const int ti
           }
         }
         }
-        if (relu) {
+        if (!act_first && (relu || (P.flags & I2R_F_GELU))) {
 #pragma unroll
-          for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.0f);
+          for (int i = 0; i < 16; ++i) v[i] = epi_act(v[i], P.flags);
         }
         if (P.flags & I2R_F_OUT_NCHW_F32) {
           float* Y = reinterpret_cast<float*>(P.y);
@@ -397,6 +402,7 @@ __global__ void __launch_bounds__(128) igemm_check_kernel(const __grid_constant_
       }
     }
     float v = acc * P.scale[co] + P.bias[co];
+    if (P.flags & I2R_F_ACT_FIRST) v = epi_act(v, P.flags);
     if (P.add0) {
       const int s0 = P.add0_shift;
       const int64_t ap = (static_cast<int64_t>(n) * (P.OHf >> s0) + (oyf >> s0)) * (P.OWf >> s0) + (oxf >> s0);
@@ -409,7 +415,7 @@ __global__ void __launch_bounds__(128) igemm_check_kernel(const __grid_constant_
       v += __half2float(reinterpret_cast<const __half*>(P.add1)[ap * P.add_pix_stride + co]);
       if (split) v += __half2float(reinterpret_cast<const __half*>(P.add1)[ap * P.add_pix_stride + P.Cout + co]);
     }
-    if (P.flags & I2R_F_RELU) v = fmaxf(v, 0.f);
+    if (!(P.flags & I2R_F_ACT_FIRST)) v = epi_act(v, P.flags);
     if (P.flags & I2R_F_OUT_NCHW_F32) {
       const int64_t plane = static_cast<int64_t>(P.OHf) * P.OWf;
       reinterpret_cast<float*>(P.y)[(static_cast<int64_t>(n) * P.Cout + co) * plane +

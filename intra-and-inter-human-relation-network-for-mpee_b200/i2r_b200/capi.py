@@ -13,6 +13,8 @@ F_OUT_NCHW_F32 = 2
 F_OUT_F32 = 4
 F_SPLIT = 8
 F_OUT_T16 = 16
+F_GELU = 32
+F_ACT_FIRST = 64
 
 EXPORTS = [
     "i2r_version", "i2r_last_error", "i2r_device_check", "i2r_sm_count", "i2r_conv_igemm", "i2r_conv_halo", "i2r_conv_halo_supported", "i2r_debug_trace", "i2r_debug_flags",

@@ -110,7 +110,8 @@ class Runner:
 
     # ------------------------------------------------------------------ implicit GEMM
     def problem(self, L, x, out=None, add0=None, add0_shift=0, add1=None, add1_shift=0, in_shift=0,
-                relu=None, out_mode="nhwc16", out_hw=None, out_mul=1, out_off=(0, 0), ohow=None):
+                relu=None, out_mode="nhwc16", out_hw=None, out_mul=1, out_off=(0, 0), ohow=None, gelu=False,
+                act_first=False):
         """Build one problem.  x: fp16 [NB, Hs, Ws, C>=Cin] (channel stride 1).  Returns (ConvProblem, out)."""
         assert x.dtype == torch.float16 and x.dim() == 4 and x.stride(3) == 1
         nb, hs, ws, cphys = x.shape
@@ -130,6 +131,10 @@ class Runner:
         flags = 0
         if (L.relu if relu is None else relu):
             flags |= capi.F_RELU
+        if gelu:                 # erf-GELU instead of ReLU
+            flags = (flags & ~capi.F_RELU) | capi.F_GELU
+        if act_first:            # y = act(conv) + addends
+            flags |= capi.F_ACT_FIRST
         if out is None:
             if out_mode == "nhwc16":
                 out = torch.empty((nb, ohf, owf, cw), dtype=torch.float16, device=x.device)

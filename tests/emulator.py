@@ -64,14 +64,20 @@ class EmuRunner(Runner):
         v = acc[..., :cout] * L.scale[:cout] + L.bias[:cout]
         fy = oy * p.out_mul + p.out_offy
         fx = ox * p.out_mul + p.out_offx
+        def act(t):
+            if p.flags & capi.F_GELU:
+                return F.gelu(t)
+            return F.relu(t) if p.flags & capi.F_RELU else t
+        if p.flags & capi.F_ACT_FIRST:
+            v = act(v)
         for a, s in ((add0, p.add0_shift), (add1, p.add1_shift)):
             if a is not None:
                 assert tuple(a.shape) == (nb, p.OHf >> s, p.OWf >> s, 2 * cout if split else cout)
                 assert a.stride(2) == p.add_pix_stride
                 af = merge_pair(a) if split else a.float()
                 v = v + af[:, fy >> s, fx >> s, :]
-        if p.flags & capi.F_RELU:
-            v = F.relu(v)
+        if not (p.flags & capi.F_ACT_FIRST):
+            v = act(v)
         if p.flags & capi.F_OUT_NCHW_F32:
             out[:, :, fy, fx] = v.permute(0, 3, 1, 2)
         elif p.flags & capi.F_OUT_F32:

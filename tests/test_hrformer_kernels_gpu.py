@@ -187,3 +187,32 @@ def test_window_attention(dev, tc, split, heads, nwin):
     err = float((got - ref).abs().max())
     _report(test="window_attention", split=split, heads=heads, err=err)
     assert err <= (4e-4 if split else 3e-3), err
+
+
+@pytest.mark.parametrize("split", [False, True])
+@pytest.mark.parametrize("path", ["halo", "igemm", "check"])
+@pytest.mark.parametrize("act_first", [False, True])
+def test_gemm_epilogue_gelu_and_act_first(dev, split, path, act_first):
+    """1x1 conv + folded BN + erf-GELU with a residual added before or after the activation (fc1 / fc2 of MlpDWBN)."""
+    import math
+    from i2r_b200.ops import ConvLayer, Runner, split_precision
+    g = torch.Generator().manual_seed(3 + int(act_first))
+    nb, h, w, cin, cout = 2, 16, 8, 80, 96
+    wt = (torch.rand(cout, cin, generator=g) * 2 - 1) / math.sqrt(cin)
+    sc = torch.rand(cout, generator=g) + 0.5
+    bi = torch.randn(cout, generator=g) * 0.1
+    x32 = torch.randn(nb, h, w, cin, generator=g)
+    a32 = torch.randn(nb, h, w, cout, generator=g)
+    r = Runner(dev, impl=1 if path == "check" else 0)
+    r.use_tma = path == "halo"
+    with split_precision(split):
+        L = ConvLayer([wt], [0], [0], sc, bi, device=dev)
+    x, a = _enc(x32, split).to(dev), _enc(a32, split).to(dev)
+    p, out = r.problem(L, x, add0=a, relu=False, gelu=True, act_first=act_first)
+    r.launch([p])
+    torch.cuda.synchronize()
+    lin = (_dec(x, split) @ wt.double().t()) * sc.double() + bi.double()
+    ref = F.gelu(lin) + _dec(a, split) if act_first else F.gelu(lin + _dec(a, split))
+    err = float((_dec(out, split) - ref).abs().max())
+    _report(test="gemm_gelu", split=split, path=path, act_first=act_first, err=err)
+    assert err <= (3e-5 if split else 6e-3), err
