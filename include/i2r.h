@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define I2R_ABI_VERSION 3
+#define I2R_ABI_VERSION 4
 
 #define I2R_E_BADARG (-1)
 #define I2R_E_UNSUPPORTED (-2)
@@ -89,6 +89,9 @@ typedef struct i2r_conv_problem {
                            /* with scale[n] folded into every row n before the fp16 rounding                     */
   int32_t w_folded_copies; /* >= 1: that image repeated back to back; CTA i streams copy i % copies, which spreads */
                            /* the L2 lines every CTA reads at the same time over more L2 slices                    */
+  int32_t pair_lo_offset;  /* I2R_F_SPLIT: channel offset from the hi half to the lo half inside y / add0 / add1   */
+                           /* rows; 0 = Cout.  Lets a problem produce a SLICE of the output channels of a wider   */
+                           /* pair tensor (layers with more than 256 output channels run as several problems)     */
 } i2r_conv_problem;
 
 int i2r_version(void);

@@ -203,6 +203,7 @@ __device__ __forceinline__ void run_tile(const i2r_conv_problem& P, const int ti
       oxf = ox * P.out_mul + P.out_offx;
     }
     const int Cout = P.Cout;
+    const int lo_off = P.pair_lo_offset > 0 ? P.pair_lo_offset : Cout;   // split mode: hi -> lo channel offset
     const __half* a0 = nullptr;
     const __half* a1 = nullptr;
     if (P.add0 != nullptr) {
@@ -233,7 +234,7 @@ __device__ __forceinline__ void run_tile(const i2r_conv_problem& P, const int ti
           for (int i = 0; i < 16; ++i) v[i] = epi_act(v[i], P.flags);
         }
         for (int part = 0; part < (split ? 2 : 1); ++part) {   // split addends: hi half, then lo half at +Cout
-        const int po = part * Cout;
+        const int po = part * lo_off;
         if (a0 != nullptr) {
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
@@ -300,7 +301,7 @@ __device__ __forceinline__ void run_tile(const i2r_conv_problem& P, const int ti
                   const float2 f = unpack_h2(hq[i]);
                   lq[i] = pack_h2(v[h * 8 + 2 * i] - f.x, v[h * 8 + 2 * i + 1] - f.y);
                 }
-                *reinterpret_cast<uint4*>(Y + Cout + h * 8) = make_uint4(lq[0], lq[1], lq[2], lq[3]);
+                *reinterpret_cast<uint4*>(Y + lo_off + h * 8) = make_uint4(lq[0], lq[1], lq[2], lq[3]);
               }
             }
           }
@@ -376,6 +377,7 @@ __global__ void __launch_bounds__(128) igemm_check_kernel(const __grid_constant_
   const int oyf = oy * P.out_mul + P.out_offy, oxf = ox * P.out_mul + P.out_offx;
   const int sh = P.in_shift;
   const int IHs = P.IH >> sh, IWs = P.IW >> sh;
+  const int lo_off_c = P.pair_lo_offset > 0 ? P.pair_lo_offset : P.Cout;
   const bool split = (P.flags & I2R_F_SPLIT) != 0;
   const int nkr = (P.Cin + 63) >> 6;
   const int nchunks = split ? 3 * nkr : nkr;
@@ -407,13 +409,13 @@ __global__ void __launch_bounds__(128) igemm_check_kernel(const __grid_constant_
       const int s0 = P.add0_shift;
       const int64_t ap = (static_cast<int64_t>(n) * (P.OHf >> s0) + (oyf >> s0)) * (P.OWf >> s0) + (oxf >> s0);
       v += __half2float(reinterpret_cast<const __half*>(P.add0)[ap * P.add_pix_stride + co]);
-      if (split) v += __half2float(reinterpret_cast<const __half*>(P.add0)[ap * P.add_pix_stride + P.Cout + co]);
+      if (split) v += __half2float(reinterpret_cast<const __half*>(P.add0)[ap * P.add_pix_stride + lo_off_c + co]);
     }
     if (P.add1) {
       const int s1 = P.add1_shift;
       const int64_t ap = (static_cast<int64_t>(n) * (P.OHf >> s1) + (oyf >> s1)) * (P.OWf >> s1) + (oxf >> s1);
       v += __half2float(reinterpret_cast<const __half*>(P.add1)[ap * P.add_pix_stride + co]);
-      if (split) v += __half2float(reinterpret_cast<const __half*>(P.add1)[ap * P.add_pix_stride + P.Cout + co]);
+      if (split) v += __half2float(reinterpret_cast<const __half*>(P.add1)[ap * P.add_pix_stride + lo_off_c + co]);
     }
     if (!(P.flags & I2R_F_ACT_FIRST)) v = epi_act(v, P.flags);
     if (P.flags & I2R_F_OUT_NCHW_F32) {
@@ -425,7 +427,7 @@ __global__ void __launch_bounds__(128) igemm_check_kernel(const __grid_constant_
     } else {
       const __half hv = __float2half_rn(v);
       reinterpret_cast<__half*>(P.y)[opix * P.out_pix_stride + co] = hv;
-      if (split) reinterpret_cast<__half*>(P.y)[opix * P.out_pix_stride + P.Cout + co] = __float2half_rn(v - __half2float(hv));
+      if (split) reinterpret_cast<__half*>(P.y)[opix * P.out_pix_stride + lo_off_c + co] = __float2half_rn(v - __half2float(hv));
     }
   }
 }

@@ -37,7 +37,7 @@ class ConvProblem(ctypes.Structure):
         ("ntaps", ctypes.c_int32),
         ("dy", ctypes.c_int8 * (I2R_MAX_TAPS + 3)), ("dx", ctypes.c_int8 * (I2R_MAX_TAPS + 3)),
         ("flags", ctypes.c_uint32),
-        ("w_folded", ctypes.c_void_p), ("w_folded_copies", ctypes.c_int32),
+        ("w_folded", ctypes.c_void_p), ("w_folded_copies", ctypes.c_int32), ("pair_lo_offset", ctypes.c_int32),
     ]
 
 
@@ -102,8 +102,8 @@ def load():
         if lib.i2r_sizeof_conv_problem() != ctypes.sizeof(ConvProblem):
             raise I2RError("i2r_conv_problem layout mismatch: C %d vs ctypes %d" % (
                 lib.i2r_sizeof_conv_problem(), ctypes.sizeof(ConvProblem)))
-        if lib.i2r_version() != 3:
-            raise I2RError("libi2r_sm100.so ABI version %d, binding expects 3" % lib.i2r_version())
+        if lib.i2r_version() != 4:
+            raise I2RError("libi2r_sm100.so ABI version %d, binding expects 4" % lib.i2r_version())
         _lib = lib
         return lib
 

@@ -11,6 +11,27 @@ from .packing import ceil_to, pad_vec, pick_kc, pack_taps, pack_folded, split_vi
 
 
 _SPLIT_DEFAULT = [False]
+_CHANNEL_PAD = [0]
+
+
+@contextlib.contextmanager
+def channel_padding(multiple=16):
+    """Layers constructed inside this context zero-pad their input channels (and output channels, except small heads)
+    to a multiple of `multiple`: the K = 16 granularity of the tensor-core GEMMs for the 78/156/312/624-channel
+    HRFormer-B branches.  Pad output channels get zero weights, scale 1 and bias 0, so they stay exactly zero."""
+    old = _CHANNEL_PAD[0]
+    _CHANNEL_PAD[0] = int(multiple)
+    try:
+        yield
+    finally:
+        _CHANNEL_PAD[0] = old
+
+
+def pad_channels(c, small_ok=True):
+    m = _CHANNEL_PAD[0]
+    if not m or (small_ok and c <= 32):      # heatmap heads (17 / 14 joints) keep their channel count
+        return c
+    return (c + m - 1) // m * m
 
 
 @contextlib.contextmanager
@@ -29,6 +50,17 @@ class ConvLayer:
 
     def __init__(self, mats, dys, dxs, scale, bias, stride=1, relu=False, device="cuda", split=None):
         cout, cin = mats[0].shape
+        cop, cip = pad_channels(cout), pad_channels(cin, small_ok=False)
+        if (cop, cip) != (cout, cin):
+            padded = []
+            for m in mats:
+                t = torch.zeros(cop, cip, dtype=torch.float32)
+                t[:cout, :cin] = m.float()
+                padded.append(t)
+            mats = padded
+            scale = torch.cat([scale.float().reshape(-1)[:cout], torch.ones(cop - cout)])
+            bias = torch.cat([bias.float().reshape(-1)[:cout], torch.zeros(cop - cout)])
+            cout, cin = cop, cip
         self.split = _SPLIT_DEFAULT[0] if split is None else bool(split)
         self.cin, self.cout = cin, cout
         self.kc = pick_kc(cin)
@@ -66,6 +98,29 @@ class ConvLayer:
     @property
     def weight_bytes(self):
         return self.w.numel() * 2
+
+    def chunks(self, width=256):
+        """Column chunks of at most `width` output channels (the kernels hold <= 256 accumulator columns): list of
+        (first channel, sub-layer).  Cached."""
+        key = ("chunks", width)
+        cache = self.__dict__.setdefault("_chunk_cache", {})
+        if key not in cache:
+            parts = []
+            for c0 in range(0, self.cout, width):
+                h = min(width, self.cout - c0)
+                sub = ConvLayer.__new__(ConvLayer)
+                sub.__dict__.update(self.__dict__)
+                sub.cout, sub.npad = h, ceil_to(h, 16)
+                assert sub.npad == h, "chunked layers need a multiple of 16 output channels"
+                sub.w = self.w[:, :, c0:c0 + h, :].contiguous()
+                sub.scale = self.scale[c0:c0 + h].contiguous()
+                sub.bias = self.bias[c0:c0 + h].contiguous()
+                sub.w_folded = self.w_folded[:, c0:c0 + h, :].contiguous()
+                sub._halves = None
+                sub._chunk_cache = {}
+                parts.append((c0, sub))
+            cache[key] = parts
+        return cache[key]
 
     def halves(self):
         """Two layers producing output channels [0, Cout/2) and [Cout/2, Cout) (N-split for the TMA kernel:
@@ -111,8 +166,10 @@ class Runner:
     # ------------------------------------------------------------------ implicit GEMM
     def problem(self, L, x, out=None, add0=None, add0_shift=0, add1=None, add1_shift=0, in_shift=0,
                 relu=None, out_mode="nhwc16", out_hw=None, out_mul=1, out_off=(0, 0), ohow=None, gelu=False,
-                act_first=False):
-        """Build one problem.  x: fp16 [NB, Hs, Ws, C>=Cin] (channel stride 1).  Returns (ConvProblem, out)."""
+                act_first=False, lo_offset=0):
+        """Build one problem.  x: fp16 [NB, Hs, Ws, C>=Cin] (channel stride 1).  Returns (ConvProblem, out).
+        lo_offset > 0 (split-operand mode only): `out` / `add0` / `add1` are the hi-half channel SLICES [.., Cout] of
+        wider pair tensors whose lo halves sit lo_offset channels further (one layer run as several problems)."""
         assert x.dtype == torch.float16 and x.dim() == 4 and x.stride(3) == 1
         nb, hs, ws, cphys = x.shape
         assert cphys >= (2 * L.cin if L.split else L.cin), "input tensor has too few channels for this layer"
@@ -166,7 +223,8 @@ class Runner:
         add_pix = cw
         for a in (add0, add1):
             if a is not None:
-                assert a.dtype == torch.float16 and a.dim() == 4 and a.stride(3) == 1 and a.shape[-1] == cw
+                assert a.dtype == torch.float16 and a.dim() == 4 and a.stride(3) == 1
+                assert a.shape[-1] == (L.cout if lo_offset else cw)
                 assert a.stride(1) == a.shape[2] * a.stride(2)
                 add_pix = a.stride(2)
         if add0 is not None and add1 is not None:
@@ -188,6 +246,8 @@ class Runner:
         p.flags = flags
         p.w_folded = L.w_folded.data_ptr()
         p.w_folded_copies = L.w_copies
+        p.pair_lo_offset = lo_offset
+        assert not lo_offset or (L.split and out_mode == "nhwc16")
         p._keep = (x, L, add0, add1, out)
         return p, out
 
@@ -202,6 +262,27 @@ class Runner:
                  kw.get("add0_shift", 0) == 0 and kw.get("add1_shift", 0) == 0 and
                  L.weight_bytes > self.TMA_WEIGHT_RESIDENT_MAX and L.cout == L.npad and L.cout % 32 == 0 and
                  not L.split)
+        if L.npad > 256:
+            # more output channels than accumulator columns: column chunks writing channel slices of one tensor
+            assert kw.get("out_mode", "nhwc16") == "nhwc16" and L.cout == L.npad
+            out = kw.pop("out", None)
+            if out is None:
+                if kw.get("ohow"):
+                    oh, ow = kw["ohow"]
+                else:
+                    st, sh = L.stride, kw.get("in_shift", 0)
+                    oh, ow = ((x.shape[1] << sh) + st - 1) // st, ((x.shape[2] << sh) + st - 1) // st
+                out = torch.empty((x.shape[0], oh, ow, (2 if L.split else 1) * L.cout), dtype=torch.float16,
+                                  device=x.device)
+            add0, add1 = kw.pop("add0", None), kw.pop("add1", None)
+            probs = []
+            for c0, sub in L.chunks(256):
+                sl = slice(c0, c0 + sub.cout)
+                p, _ = self.problem(sub, x, out=out[..., sl], add0=None if add0 is None else add0[..., sl],
+                                    add1=None if add1 is None else add1[..., sl],
+                                    lo_offset=L.cout if L.split else 0, **kw)
+                probs.append(p)
+            return probs, out
         if not split:
             p, out = self.problem(L, x, **kw)
             return [p], out

@@ -64,6 +64,11 @@ class EmuRunner(Runner):
         v = acc[..., :cout] * L.scale[:cout] + L.bias[:cout]
         fy = oy * p.out_mul + p.out_offy
         fx = ox * p.out_mul + p.out_offx
+        lo_off = int(p.pair_lo_offset)
+
+        def lo_view(t):     # the lo-half slice that sits lo_off channels after a hi-half slice of a pair tensor
+            return t.as_strided(t.shape, t.stride(), t.storage_offset() + lo_off)
+
         def act(t):
             if p.flags & capi.F_GELU:
                 return F.gelu(t)
@@ -72,9 +77,12 @@ class EmuRunner(Runner):
             v = act(v)
         for a, s in ((add0, p.add0_shift), (add1, p.add1_shift)):
             if a is not None:
-                assert tuple(a.shape) == (nb, p.OHf >> s, p.OWf >> s, 2 * cout if split else cout)
+                assert tuple(a.shape) == (nb, p.OHf >> s, p.OWf >> s, 2 * cout if (split and not lo_off) else cout)
                 assert a.stride(2) == p.add_pix_stride
-                af = merge_pair(a) if split else a.float()
+                if lo_off:
+                    af = a.float() + lo_view(a).float()
+                else:
+                    af = merge_pair(a) if split else a.float()
                 v = v + af[:, fy >> s, fx >> s, :]
         if not (p.flags & capi.F_ACT_FIRST):
             v = act(v)
@@ -85,6 +93,10 @@ class EmuRunner(Runner):
         elif p.flags & capi.F_OUT_T16:
             vv = split_pair(v) if split else v.half()
             out.copy_(vv.reshape(-1, vv.shape[-1]).t())
+        elif split and lo_off:
+            pair = split_pair(v)
+            out[:, fy, fx, :] = pair[..., :cout]
+            lo_view(out)[:, fy, fx, :] = pair[..., cout:]
         elif split:
             out[:, fy, fx, :] = split_pair(v)
         else:

@@ -63,7 +63,7 @@ def test_cabi_library_exports_every_declared_symbol():
         assert hasattr(lib, name), name
     assert set(capi.EXPORTS) == declared
     lib.i2r_version.restype = ctypes.c_int
-    assert lib.i2r_version() == 3
+    assert lib.i2r_version() == 4
     assert lib.i2r_sizeof_conv_problem() == ctypes.sizeof(capi.ConvProblem)
 
 
