@@ -10,7 +10,7 @@ import math
 
 import torch
 
-from .ops import ConvLayer, EncoderTailParams
+from .ops import ConvLayer, EncoderTailParams, pad_channels
 
 
 def _linear_layer(weight, bias, relu=False, device="cuda"):
@@ -25,7 +25,8 @@ class EncoderLayerProgram:
         self.d = d
         self.qk = _linear_layer(w[: 2 * d], b[: 2 * d], device=device)
         self.v = _linear_layer(w[2 * d:], b[2 * d:], device=device)
-        if self.qk.split:
+        self.separate_qk = self.qk.split or pad_channels(d, small_ok=False) != d
+        if self.separate_qk:
             # separate q / k projections: each output row is then one contiguous (hi | lo) pair, the operand
             # layout of the tcgen05 attention kernel
             self.q = _linear_layer(w[:d], b[:d], device=device)
@@ -42,8 +43,14 @@ class EncoderLayerProgram:
                 sd[prefix + ".linear1.weight"], sd[prefix + ".linear1.bias"], sd[prefix + ".linear2.weight"],
                 sd[prefix + ".linear2.bias"], sd[prefix + ".norm1.weight"], sd[prefix + ".norm1.bias"],
                 sd[prefix + ".norm2.weight"], sd[prefix + ".norm2.bias"], device=device, split=self.qk.split)
-        self.n1 = (sd[prefix + ".norm1.weight"].float().to(device), sd[prefix + ".norm1.bias"].float().to(device))
-        self.n2 = (sd[prefix + ".norm2.weight"].float().to(device), sd[prefix + ".norm2.bias"].float().to(device))
+        dp = pad_channels(d, small_ok=False)
+
+        def vec(key):      # LayerNorm parameters, zero-padded with the channels
+            v = torch.zeros(dp)
+            v[:d] = sd[prefix + key].float()
+            return v.to(device)
+        self.n1 = (vec(".norm1.weight"), vec(".norm1.bias"))
+        self.n2 = (vec(".norm2.weight"), vec(".norm2.bias"))
 
 
 class EncoderProgram:
@@ -56,7 +63,8 @@ class EncoderProgram:
             raise NotImplementedError("NORMALIZE_BEFORE=True (default False in every shipped config)")
         self.layers = [EncoderLayerProgram(sd, "%s.layers.%d" % (prefix, i), d_model, device)
                        for i in range(num_layers)]
-        self.d = d_model
+        self.d = pad_channels(d_model, small_ok=False)      # channels per token as stored (zero-padded to 16)
+        self.d_real = d_model
         self.scale = 1.0 / math.sqrt(d_model // nhead)
 
     def run(self, r, src, pos, cu_seqlens, max_seqlen):
@@ -67,12 +75,13 @@ class EncoderProgram:
         for li, L in enumerate(self.layers):
             # V is written transposed (channel-major): the K-major B operand of the P.V product
             pv, vt = r.linear_problem(L.v, src, out_mode="t16")
-            if split:     # q, k: [T, (hi | lo)]; vt: [(hi rows | lo rows), T]
+            if L.separate_qk:     # q, k: [T, (hi | lo)] (or [T, d_pad]); vt: [(hi rows | lo rows), T]
                 pq, q = r.linear_problem(L.q, sp)
                 pk, k = r.linear_problem(L.k, sp)
                 r.launch([pq, pk, pv])
-                a = r.attention_tc(q.view(-1, 2 * d), k.view(-1, 2 * d), vt, cu_seqlens, max_seqlen, self.scale,
-                                   split=True)
+                wq = 2 * d if split else d
+                a = r.attention_tc(q.view(-1, wq), k.view(-1, wq), vt, cu_seqlens, max_seqlen, self.scale,
+                                   split=split)
             else:
                 pq, qk = r.linear_problem(L.qk, sp)
                 r.launch([pq, pv])
@@ -84,6 +93,14 @@ class EncoderProgram:
                 sp = sp2 if sp2 is not None else src
                 continue
             x1 = r.linear(L.out, a, add0=src)
+            if self.d != self.d_real:      # zero-padded channels (d_model 78 -> 80): statistics over the real ones
+                if pos is not None:
+                    raise NotImplementedError("position embedding with a padded d_model")
+                s1 = r.layernorm_padded(x1, L.n1[0], L.n1[1], self.d_real, eps=1e-5)
+                h = r.linear(L.ff1, s1)
+                x2 = r.linear(L.ff2, h, add0=s1)
+                src = sp = r.layernorm_padded(x2, L.n2[0], L.n2[1], self.d_real, eps=1e-5)
+                continue
             s1, _ = r.layernorm(x1, L.n1[0], L.n1[1])
             h = r.linear(L.ff1, s1)
             x2 = r.linear(L.ff2, h, add0=s1)

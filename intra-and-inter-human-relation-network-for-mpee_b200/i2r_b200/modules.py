@@ -41,7 +41,7 @@ class DeconvProgram:
             for px in (0, 1):
                 mats, dys, dxs = deconv4x4s2_phase_taps(w, py, px)
                 self.phases.append(((py, px), ConvLayer(mats, dys, dxs, scale, bias, relu=True, device=device)))
-        self.cout = w.shape[1]
+        self.cout = self.phases[0][1].cout      # padded channel count inside ops.channel_padding
 
     def run(self, r, x):
         nb, h, w, _ = x.shape

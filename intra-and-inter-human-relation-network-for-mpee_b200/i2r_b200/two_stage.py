@@ -19,7 +19,7 @@ from .encoder import EncoderProgram
 from .engine import GraphedForward
 from .hrnet_w48 import conv_bn_layer
 from .modules import DeconvProgram, EncoderParams, make_deconv_stack
-from .ops import Runner, split_precision
+from .ops import Runner, channel_padding, split_precision
 from .position import MaskEmbedParams, MaskEmbedProgram
 
 
@@ -97,7 +97,7 @@ class TwoStageInterFormer(nn.Module):
         prog.split = getattr(self.singleformer, "precision", "fp16") == "split"
         prog.runner.split = prog.split
         prog.first = self.singleformer.build_program(device)
-        with split_precision(prog.split):
+        with split_precision(prog.split), channel_padding(16 if c["d_model"] % 16 else 0):
             self._build_second_stage(prog, sd, c, device)
         offsets = {}
 

@@ -7,13 +7,13 @@ list dumped from the real reference, tests/golden/state_dict_interformer_coco_hr
 HRFormer checkpoints load with strict=True and `models.interformer.get_pose_net` resolves this first stage by name
 exactly as interformer.py:139 does.
 
-STATUS: the boundary and the pinned oracle (`oracle/i2r_oracle.hrformer_first_stage`,
-<= 5e-5 against outputs of the real reference at 256x192 and 384x288) exist; the sm_100a device program -- window
-attention over 49-token windows incl. the zero-padded tokens and WITHOUT the relative position bias (:866-888),
-LayerNorm eps 1e-6, MlpDWBN (1x1 GEMMs + depthwise 3x3 + erf-GELU), bilinear fuse, 78-channel padding -- is the next
-build step.  Until then `build_program` / `forward` raise: there is deliberately no PyTorch or CPU fallback.
+The forward runs as the device program of `i2r_b200/hrformer_program.py` (window attention over 49-token windows incl.
+the zero-padded tokens and WITHOUT the relative position bias (:866-888), LayerNorm eps 1e-6, MlpDWBN = 1x1 GEMMs +
+depthwise 3x3 + erf-GELU, bilinear fuse, 78/156/312/624 channels zero-padded to multiples of 16); the pinned oracle is
+`oracle/i2r_oracle.hrformer_first_stage`.  There is deliberately no PyTorch or CPU fallback.
 """
 import logging
+import os
 
 import torch
 import torch.nn as nn
@@ -179,17 +179,41 @@ class HRFormer(nn.Module):
             raise NotImplementedError("HRFormer head with deconv layers (the reference builds it with 0, :2527)")
         self.backbone = _HRT(hrt_extra)
         self.keypoint_head = _Head(head_in_channel, head_out_channel)
-        self.precision = "split"
+        self.hrt_extra = hrt_extra
+        # 'split' = split-operand GEMMs (fp16 hi+lo pairs); 'fp16' = single-pass kernels
+        self.precision = os.environ.get("I2R_PRECISION_HRT", "split")
+        self._program = None
+        self._runner = None
 
     def build_program(self, device):
-        raise NotImplementedError(
-            "HRFormer-B first stage: the sm_100a device program is not built yet (SURVEY.md section 8 row a8; oracle and "
-            "parameter surface are in place).  There is no PyTorch/CPU fallback for the hot path by design.")
+        """Fold BN, pad channels to multiples of 16, pack weights, upload: the device program the two-stage wrapper
+        (or forward) runs."""
+        from i2r_b200.hrformer_program import HRTProgram
+        from i2r_b200.ops import channel_padding, split_precision
+        sd = {k: v.detach().cpu() for k, v in self.state_dict().items()}
+        with split_precision(self.precision == "split"), channel_padding(16):
+            return HRTProgram(self, sd, torch.device(device))
+
+    def load_state_dict(self, *a, **kw):
+        out = super().load_state_dict(*a, **kw)
+        self._program = None
+        return out
 
     def forward(self, x):
-        if x.device.type != "cuda":
+        """x fp32 [S,3,H,W] -> (branch-0 feature [S,78,H/4,W/4] fp32, heatmaps [S,K,H/4,W/4]) like the reference (:2477)."""
+        from i2r_b200.ops import Runner
+        from i2r_b200.packing import merge_pair
+        dev = self.keypoint_head.final_layer.weight.device
+        if dev.type != "cuda":
             raise capi.I2RError("hrformer forward runs on a CUDA (sm_100a) device only -- there is no CPU fallback")
-        return self.build_program(x.device)
+        if self._program is None or self._program.device != dev:
+            self._program = self.build_program(dev)
+            self._runner = Runner(dev, 0)
+            self._runner.split = self.precision == "split"
+        with torch.no_grad():
+            feat, heat = self._program.run(self._runner, x.to(dev, dtype=torch.float32).contiguous())
+        f = merge_pair(feat) if self.precision == "split" else feat.float()
+        return f[..., :78].permute(0, 3, 1, 2).contiguous(), heat
 
 
 def get_pose_net(cfg, is_train, model_path="", e2e_flag=False):

@@ -195,3 +195,79 @@ class EmuRunner(Runner):
         y = F.layer_norm(h @ q(w2).t() + b2 + s1, (96,), g2, be2, eps)
         self.launches += 1
         return self._wr(y), (self._wr(y + self._rd(pos)) if pos is not None else None)
+
+    # ------------------------------------------------------------------ HRFormer-B building blocks
+    def dwconv3x3(self, x, w, scale, bias, stride=1, act=None):
+        c = w.shape[1]
+        xf = self._rd(x).permute(0, 3, 1, 2)
+        wt = w.t().reshape(c, 1, 3, 3)
+        y = F.conv2d(xf, wt, None, stride, 1, 1, c) * scale.view(1, -1, 1, 1) + bias.view(1, -1, 1, 1)
+        y = {"gelu": F.gelu, "relu": F.relu, None: lambda t: t, "none": lambda t: t}[act](y)
+        self.launches += 1
+        return self._wr(y.permute(0, 2, 3, 1).contiguous())
+
+    def upsum_bilinear(self, x0, terms, relu=True):
+        v = self._rd(x0).permute(0, 3, 1, 2)
+        for t, s in terms:
+            v = v + F.interpolate(self._rd(t).permute(0, 3, 1, 2), scale_factor=2 ** s, mode="bilinear",
+                                  align_corners=False)
+        v = F.relu(v) if relu else v
+        self.launches += 1
+        return self._wr(v.permute(0, 2, 3, 1).contiguous())
+
+    def _ln_padded(self, xf, gamma, beta, c_real, eps):
+        y = torch.zeros_like(xf)
+        y[..., :c_real] = F.layer_norm(xf[..., :c_real], (c_real,), gamma[:c_real], beta[:c_real], eps)
+        return y
+
+    def layernorm_padded(self, x2d, gamma, beta, c_real, eps=1e-6):
+        self.launches += 1
+        return self._wr(self._ln_padded(self._rd(x2d), gamma, beta, c_real, eps))
+
+    @staticmethod
+    def _win_geom(h, w, ws):
+        ph, pw = (-h) % ws, (-w) % ws
+        return ph, pw, h + ph, w + pw
+
+    def ln_window_gather(self, x, gamma, beta, c_real, ws=7, eps=1e-6):
+        nb, h, w, _ = x.shape
+        ph, pw, hp, wp = self._win_geom(h, w, ws)
+        ln = self._ln_padded(self._rd(x), gamma, beta, c_real, eps)
+        xp = F.pad(ln, (0, 0, pw // 2, pw - pw // 2, ph // 2, ph - ph // 2))
+        c = xp.shape[-1]
+        rows = xp.view(nb, hp // ws, ws, wp // ws, ws, c).permute(0, 1, 3, 2, 4, 5).reshape(-1, c)
+        self.launches += 1
+        return self._wr(rows.contiguous())
+
+    def window_scatter_add(self, x, a, ws=7):
+        nb, h, w, _ = x.shape
+        ph, pw, hp, wp = self._win_geom(h, w, ws)
+        af = self._rd(a)
+        c = af.shape[-1]
+        m = af.view(nb, hp // ws, wp // ws, ws, ws, c).permute(0, 1, 3, 2, 4, 5).reshape(nb, hp, wp, c)
+        m = m[:, ph // 2: ph // 2 + h, pw // 2: pw // 2 + w, :]
+        self.launches += 1
+        return self._wr(self._rd(x) + m)
+
+    def window_attention(self, q, k, v, win_len, heads, scale, head_pad=48):
+        t, cq = q.shape
+
+        def val(m):
+            if not self.split:
+                return m.float()
+            lo = m.as_strided(m.shape, m.stride(), m.storage_offset() + cq)
+            return m.float(), lo.float()
+        nwin = t // win_len
+        if self.split:
+            (qh, ql), (kh, kl), (vh, vl) = val(q), val(k), val(v)
+            shp = lambda m: m.reshape(nwin, win_len, heads, head_pad).permute(0, 2, 1, 3)
+            sc = shp(qh + ql) @ shp(kh).transpose(-1, -2) + shp(qh) @ shp(kl).transpose(-1, -2)
+            p = torch.softmax(sc * scale, dim=-1).half().float()
+            o = (p @ shp(vh + vl)).permute(0, 2, 1, 3).reshape(t, cq)
+            out = split_pair(o)
+        else:
+            shp = lambda m: m.float().reshape(nwin, win_len, heads, head_pad).permute(0, 2, 1, 3)
+            p = torch.softmax(shp(q) @ shp(k).transpose(-1, -2) * scale, dim=-1).half().float()
+            out = (p @ shp(v)).permute(0, 2, 1, 3).reshape(t, cq).half()
+        self.launches += 1
+        return out

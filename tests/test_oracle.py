@@ -110,13 +110,10 @@ def test_hrformer_oracle_matches_reference(yaml_rel, case, h, w):
 @pytest.mark.parametrize("yaml_rel", [h[0] for h in HRT], ids=[h[1] for h in HRT])
 def test_hrformer_two_stage_surface_matches_reference(yaml_rel):
     """`models.interformer.get_pose_net` with SINGLEFORMER = hrformer: the drop-in module's state_dict (keys, shapes,
-    dtypes) equals the real reference's, so its checkpoints load with strict=True; the device program is pending and
-    must fail loudly instead of falling back."""
+    dtypes) equals the real reference's, so its checkpoints load with strict=True."""
     cfg, model, sd = build_model(yaml_rel)
     with open(os.path.join(GOLDEN, "state_dict_%s.json" % os.path.basename(yaml_rel)[:-5])) as f:
         ref = json.load(f)
     own = {k: [list(v.shape), str(v.dtype).replace("torch.", "")] for k, v in model.state_dict().items()}
     assert sorted(own) == sorted(ref)
     assert own == ref
-    with pytest.raises(NotImplementedError):
-        model.singleformer.build_program("cpu")
