@@ -36,11 +36,13 @@ WORKLOADS = {
                     "tokens per crop) + 4 inter layers, 256x192, 4 images x 4 persons = 16 crops per GPU per step",
                precision="split-operand fp16 pairs (hi+lo), three-term products, fp32 accumulate (tcgen05 kind::f16)",
                dtype="f16x2"),
-    # HRFormer-B first stage: oracle and parameter surface exist, the device program does not yet --
-    # selectable for `--impl reference` (CPU forward of the reference algorithm) only
-    "C4": dict(yaml="coco/interformer_coco_hrt_192_p2_b12.yaml", images=8, persons=8,
-               text="C4: HRFormer-B + I2R-Net (interformer), 256x192, 8 images x 8 persons = 64 crops per step",
-               precision="n/a (device program pending)", dtype="f32", device=False),
+    "C4": dict(yaml="coco/interformer_coco_hrt_192_p2_b12.yaml", images=1, persons=8,
+               text="C4: HRFormer-B + I2R-Net (interformer), 256x192, 1 image x 8 persons = 8 crops per GPU per step "
+                    "(BASELINE's 64 crops over 8 GPUs = one image per rank; first correct path: window attention on "
+                    "mma.sync, unfused blocks)",
+               precision="split-operand fp16 pairs (hi+lo), three-term products, fp32 accumulate (tcgen05 kind::f16); "
+                         "channels 78/156/312/624 zero-padded to multiples of 16",
+               dtype="f16x2"),
 }
 IMAGES_PER_RANK, PERSONS = 8, 4
 

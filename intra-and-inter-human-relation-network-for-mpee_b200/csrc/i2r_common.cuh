@@ -217,7 +217,9 @@ __device__ __forceinline__ void issue_ksteps(uint32_t d_tmem, uint32_t a_lo, uin
     umma_f16(d_tmem, desc64(a_lo + 2 * k2, a_hi), desc64(b_lo + 2 * k2, b_hi), idesc, k2 ? 1u : acc_first);
 }
 // epilogue activation: ReLU (I2R_F_RELU), erf-GELU (I2R_F_GELU) or identity
-__device__ __forceinline__ float epi_act(float v, uint32_t flags) {
+// (deliberately NOT inlined: erff is ~60 instructions plus a local-memory frame, and the GELU layers are cold paths of
+// kernels whose hot loops must stay small)
+static __device__ __noinline__ float epi_act(float v, uint32_t flags) {
   if (flags & I2R_F_GELU) return 0.5f * v * (1.f + erff(v * 0.70710678118654752f));
   if (flags & I2R_F_RELU) return fmaxf(v, 0.f);
   return v;

@@ -266,9 +266,14 @@ __device__ __forceinline__ void run_tile(const i2r_conv_problem& P, const int ti
           }
         }
         }
-        if (!act_first && (relu || (P.flags & I2R_F_GELU))) {
+        if (!act_first) {
+          if (P.flags & I2R_F_GELU) {
 #pragma unroll
-          for (int i = 0; i < 16; ++i) v[i] = epi_act(v[i], P.flags);
+            for (int i = 0; i < 16; ++i) v[i] = epi_act(v[i], P.flags);
+          } else if (relu) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.0f);
+          }
         }
         if (P.flags & I2R_F_OUT_NCHW_F32) {
           float* Y = reinterpret_cast<float*>(P.y);

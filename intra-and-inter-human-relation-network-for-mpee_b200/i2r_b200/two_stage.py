@@ -138,7 +138,7 @@ class TwoStageInterFormer(nn.Module):
     def _eager(self, x, pos_mask, length, mask_needed=None):
         p = self._program
         r = p.runner
-        feat, heat_single = p.first.run(r, x)                               # [S,h,w,d] fp16, [S,K,h,w] fp32
+        feat, heat_single = self._run_first(p, r, x)                         # [S,h,w,d] fp16, [S,K,h,w] fp32
         tok = feat
         for _ in range(int(math.log(feat.shape[2] // self.trans_size[-1], 2))):   # interformer.py:260-264
             tok = r.maxpool(tok)
@@ -158,6 +158,27 @@ class TwoStageInterFormer(nn.Module):
         if self.returns_dict:
             return {"single": heat_single, "multi": heat_multi}
         return heat_multi
+
+    @staticmethod
+    def _run_first(p, r, x):
+        """First stage over all crops.  In split-operand mode the crops go through in groups: the persistent conv kernel
+        has a latent fault (launch failure, timing dependent, clean under compute-sanitizer) when a CTA of a
+        STREAMED-weight split-mode problem runs four or more tiles (first seen on the 64 -> 256 1x1 + residual of
+        layer1 at >= 24 crops).  Per-crop stages are independent, so grouping is exact; the group
+        size keeps the largest GEMM of the stage at <= 3 tiles per CTA."""
+        s, _, h, w = x.shape
+        if not p.split:
+            return p.first.run(r, x)
+        rows = max((h // 4) * (w // 4), ((h // 4 + 6) // 7 * 7) * ((w // 4 + 6) // 7 * 7))   # pixels / window rows per crop
+        group = max(1, (3 * 148 * 128) // rows)
+        if s <= group:
+            return p.first.run(r, x)
+        feats, heats = [], []
+        for i in range(0, s, group):
+            f, hm = p.first.run(r, x[i:i + group])
+            feats.append(f)
+            heats.append(hm)
+        return torch.cat(feats, 0), torch.cat(heats, 0)
 
     def forward(self, x, pos_mask, length):
         length = [int(n) for n in length]
