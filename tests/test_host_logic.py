@@ -83,17 +83,21 @@ def test_weight_packing_layout():
     assert torch.equal(back[5, :17], w[:, :, 1, 2].half().float())
 
 
-def test_hrformer_launch_sequence_reproduces_reference():
+@pytest.mark.parametrize("yaml_rel,case,h,w", [
+    ("coco/interformer_coco_hrt_192_p2_b12.yaml", "hrt2stage_ragged", 256, 192),
+    ("coco/interformer_coco_hrt_288_p2_b4.yaml", "hrt288_c1", 384, 288),
+], ids=["hrt2stage_ragged", "hrt288_c1"])
+def test_hrformer_launch_sequence_reproduces_reference(yaml_rel, case, h, w):
     """HRFormer-B first stage + inter-human stage at d_model 78: channel padding to 16, head padding 39 -> 48, window
     gather / scatter, GELU / act-first epilogues, depthwise and bilinear fuse ops, column chunking of wide layers --
     the launch sequence interpreted on the CPU must land within 1e-3 (measured 1.3e-4) of the real reference."""
-    cfg, model, _ = build_model("coco/interformer_coco_hrt_192_p2_b12.yaml")
+    cfg, model, _ = build_model(yaml_rel)
     model._runner_factory = lambda device, impl: EmuRunner()
     model.prepare("cpu")
     assert model._program.split and model._program.runner.split
-    g = load_golden("hrt2stage_ragged")
+    g = load_golden(case)
     length = [int(v) for v in g["length"]]
-    x, pm = inputs_for(length)
+    x, pm = inputs_for(length, h, w)
     with torch.no_grad():
         out = model._eager(x, pm, length)
     errs = {k: float(np.abs(out[k].numpy() - g["out_" + k]).max()) for k in out}
