@@ -234,6 +234,12 @@ int i2r_debug_trace(void* dev_buffer, int capacity_events, int cta);
  * 2 = epilogue without global stores / residual loads, 4 = activation TMA only for the first ring pass,
  * 8 = no MMAs (commits only).  0 restores the product behaviour. */
 int i2r_debug_flags(int flags);
+/* Debug aid: every mbarrier wait of the tcgen05 kernels is time-bounded (2^31 SM cycles); a wait that times out traps
+ * (the launch fails with cudaErrorLaunchFailure instead of hanging the GPU).  With a hang buffer installed --
+ * HOST-MAPPED pinned memory of 4096 x 4 uint64, zero-filled by the caller, still readable after the context died --
+ * lane 0 of every timed-out warp first records {blockIdx.x << 32 | threadIdx.x, source line << 32 | barrier shared
+ * address, parity << 32 | dynamic shared base, clock64}.  NULL removes it.  Synchronises the device. */
+int i2r_debug_hang_buffer(void* host_mapped);
 
 /* sizeof(i2r_conv_problem) as compiled -- lets the ctypes binding verify its struct layout. */
 int i2r_sizeof_conv_problem(void);

@@ -344,7 +344,8 @@ static int launch_attention(const void* q, const void* k, const void* v, void* o
                             const int32_t* cu, int nseq, int max_seqlen, int total_tokens, float scale, void* ws,
                             int64_t ws_bytes, int q_lo, int k_lo, int v_lo, int o_lo, cudaStream_t st) {
   constexpr int smem = (SPLIT ? 10 : 5) * ATT_BK * (HD + 8) * 2;
-  static bool attr_done = false;
+  static bool attr_done_dev[MAX_DEVICES] = {};   // the opt-in is a per-device property
+  bool& attr_done = attr_done_dev[current_device()];
   if (!attr_done) {
     cudaError_t e = cudaFuncSetAttribute(attention_kernel<HD, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) {
@@ -420,7 +421,8 @@ static int launch_window_attention(const void* q, const void* k, const void* v, 
                                    int o_lo, cudaStream_t st) {
   constexpr int HD = 48;
   constexpr int smem = (SPLIT ? 10 : 5) * ATT_BK * (HD + 8) * 2;
-  static bool attr_done = false;
+  static bool attr_done_dev[MAX_DEVICES] = {};   // the opt-in is a per-device property
+  bool& attr_done = attr_done_dev[current_device()];
   if (!attr_done) {
     cudaError_t e = cudaFuncSetAttribute(attention_kernel<HD, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) {

@@ -354,7 +354,8 @@ static int tc_choose_nsplit(int nseq, int max_seqlen, int sms) {
 }
 
 int device_sms() {
-  static int sms = 0;
+  static int sms_dev[MAX_DEVICES] = {};
+  int& sms = sms_dev[current_device()];
   if (sms == 0) {
     int dev = 0;
     cudaGetDevice(&dev);
@@ -391,7 +392,8 @@ static int launch_attention_tc(const void* q, const void* k, const void* vt, voi
                                int ldo, const int32_t* cu, int nseq, int max_seqlen, int total_tokens, float scale,
                                void* ws, int64_t ws_bytes, int o_lo, cudaStream_t st) {
   using C = TcCfg<HD, SPLIT>;
-  static bool attr_done = false;
+  static bool attr_done_dev[MAX_DEVICES] = {};   // the opt-in is a per-device property
+  bool& attr_done = attr_done_dev[current_device()];
   if (!attr_done) {
     cudaError_t e = cudaFuncSetAttribute(attention_tc_kernel<HD, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          C::SMEM);
@@ -426,6 +428,7 @@ static int launch_attention_tc(const void* q, const void* k, const void* vt, voi
   return attention_merge_launch(HD, A.opart, A.mlpart, A.out, ldo, total_tokens, nsplit, SPLIT ? o_lo : 0, st);
 }
 
+I2R_HANG_SINK_SETTER(attention_tc)
 }  // namespace i2r
 
 extern "C" int64_t i2r_attention_tc_workspace_bytes(int total_tokens, int D, int nseq, int max_seqlen) {

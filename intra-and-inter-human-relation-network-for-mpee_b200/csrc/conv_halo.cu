@@ -38,6 +38,7 @@ struct HaloProblem {
   const __half* add1;
   void* y;
   int NB, H, W, C, Cout, Npad;
+  int lo_off;          // split mode: channel offset hi -> lo inside output / addend rows
   int ntaps, halo;
   int KCH, nkc;        // channels per A stage, A stages per tile (split-operand mode: 3 * nkr)
   int nkr, split;      // real 64-channel K-chunks of the input; split-operand mode (I2R_F_SPLIT)
@@ -85,7 +86,7 @@ __device__ __forceinline__ T* opaque(T* v) {
 __device__ __forceinline__ HaloProblem load_problem(const HaloProblem& s) {
   HaloProblem p;
   p.x = opaque(s.x); p.w = opaque(s.w); p.add0 = opaque(s.add0); p.add1 = opaque(s.add1); p.y = opaque(s.y);
-  p.NB = opaque(s.NB); p.H = opaque(s.H); p.W = opaque(s.W); p.C = opaque(s.C); p.Cout = opaque(s.Cout);
+  p.NB = opaque(s.NB); p.H = opaque(s.H); p.W = opaque(s.W); p.C = opaque(s.C); p.Cout = opaque(s.Cout); p.lo_off = opaque(s.lo_off);
   p.Npad = opaque(s.Npad); p.ntaps = opaque(s.ntaps); p.halo = opaque(s.halo); p.KCH = opaque(s.KCH);
   p.nkc = opaque(s.nkc); p.nkr = opaque(s.nkr); p.split = opaque(s.split); p.kgp = opaque(s.kgp); p.nchp = opaque(s.nchp); p.tiles_x = opaque(s.tiles_x);
   p.tiles_per_img = opaque(s.tiles_per_img); p.ntiles = opaque(s.ntiles);
@@ -187,20 +188,20 @@ __device__ __forceinline__ void mma_role(const HaloProblem& P, const int cta, co
   const int a_first = iw * a_half, w_first = iw * w_half;
   int as = 0, ws = 0;
   uint32_t aph = 0, wph = 0;
-  if (resident) mbar_wait(bar_wres, 0);
+  if (resident) mbar_wait_warp(bar_wres, 0);
   if (leader) trace_ev(tr, trcap, 1, tri, 13, 0);
   const uint32_t ones_lo = sw128_desc_lo(sbase + T_ONES_OFF);
   const uint32_t ones_hi = sw128_desc_hi(0, 0);   // SBO 0: every 8-row group reads the same 1 KB atom of ones
   for (int t = cta + iw * P.cta_count; t < P.ntiles; t += (dual ? 2 : 1) * P.cta_count) {
     const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc) * (ncols >> 1);
-    mbar_wait(bar_accempty + 8 * acc, accph ^ 1);
+    mbar_wait_warp(bar_accempty + 8 * acc, accph ^ 1);
     tc_fence_after();
     if (leader) trace_ev(tr, trcap, 1, tri, 10, t);
     // accumulator := bias (block 0 of the packed weights), then every tap accumulates
     if (resident) {
       if (leader) umma_f16(d_tmem, desc64(ones_lo, ones_hi), desc64(w_lo0, b_hi), idesc, 0u);
     } else {
-      mbar_wait(bar_wfull + 8 * (w_first + ws), wph);
+      mbar_wait_warp(bar_wfull + 8 * (w_first + ws), wph);
       tc_fence_after();
       if (leader) {
         umma_f16(d_tmem, desc64(ones_lo, ones_hi), desc64(w_lo0 + (w_first + ws) * w_slot16, b_hi), idesc, 0u);
@@ -212,7 +213,7 @@ __device__ __forceinline__ void mma_role(const HaloProblem& P, const int cta, co
       }
     }
     for (int kc = 0; kc < P.nkc; ++kc) {
-      mbar_wait(bar_afull + 8 * (a_first + as), aph);
+      mbar_wait_warp(bar_afull + 8 * (a_first + as), aph);
       tc_fence_after();
       if (leader) trace_ev(tr, trcap, 1, tri, 11, t);
       const uint32_t a_lo = a_lo0 + (a_first + as) * a_stage16;
@@ -235,7 +236,7 @@ __device__ __forceinline__ void mma_role(const HaloProblem& P, const int cta, co
         constexpr int TG = NTAPS == 9 ? 3 : 1;
 #pragma unroll
         for (int tg = 0; tg < NTAPS / TG; ++tg) {
-          mbar_wait(bar_wfull + 8 * (w_first + ws), wph);
+          mbar_wait_warp(bar_wfull + 8 * (w_first + ws), wph);
           tc_fence_after();
           if (leader) {
             const uint32_t b_lo = w_lo0 + (w_first + ws) * w_slot16;
@@ -293,7 +294,7 @@ struct EpiArgs {
   const __half* add0;
   const __half* add1;
   void* y;
-  int H, W, Cout, tiles_x, tiles_per_img, ntiles, cta_count;
+  int H, W, Cout, lo_off, tiles_x, tiles_per_img, ntiles, cta_count;
   int out_pix_stride, add_pix_stride, plane;
   uint32_t flags;
 };
@@ -345,8 +346,8 @@ __device__ __forceinline__ void epilogue_role(const EpiArgs E, const int cta, co
         l0[j] = make_uint4(0, 0, 0, 0);
         l1[j] = make_uint4(0, 0, 0, 0);
         if (split && j < nc && valid && (c + j) * 8 < E.Cout) {
-          if (has0) l0[j] = __ldg(reinterpret_cast<const uint4*>(a0 + E.Cout + (c + j) * 8));
-          if (has1) l1[j] = __ldg(reinterpret_cast<const uint4*>(a1 + E.Cout + (c + j) * 8));
+          if (has0) l0[j] = __ldg(reinterpret_cast<const uint4*>(a0 + E.lo_off + (c + j) * 8));
+          if (has1) l1[j] = __ldg(reinterpret_cast<const uint4*>(a1 + E.lo_off + (c + j) * 8));
         }
       }
       if (!waited) {
@@ -377,8 +378,20 @@ __device__ __forceinline__ void epilogue_role(const EpiArgs E, const int cta, co
             for (int i = 0; i < 4; ++i) {
               const float2 f0 = unpack_h2(q0[i]), f1 = unpack_h2(q1[i]);
               const float2 g0 = unpack_h2(p0[i]), g1 = unpack_h2(p1[i]);
-              v[2 * i] = fmaxf(__uint_as_float(av[j][2 * i]) + ((f0.x + g0.x) + (f1.x + g1.x)), lo);
-              v[2 * i + 1] = fmaxf(__uint_as_float(av[j][2 * i + 1]) + ((f0.y + g0.y) + (f1.y + g1.y)), lo);
+              const float ax = (f0.x + g0.x) + (f1.x + g1.x), ay = (f0.y + g0.y) + (f1.y + g1.y);
+              if (E.flags & (I2R_F_GELU | I2R_F_ACT_FIRST)) {
+                const float sx = __uint_as_float(av[j][2 * i]), sy = __uint_as_float(av[j][2 * i + 1]);
+                if (E.flags & I2R_F_ACT_FIRST) {
+                  v[2 * i] = epi_act(sx, E.flags) + ax;
+                  v[2 * i + 1] = epi_act(sy, E.flags) + ay;
+                } else {
+                  v[2 * i] = epi_act(sx + ax, E.flags);
+                  v[2 * i + 1] = epi_act(sy + ay, E.flags);
+                }
+              } else {
+                v[2 * i] = fmaxf(__uint_as_float(av[j][2 * i]) + ax, lo);
+                v[2 * i + 1] = fmaxf(__uint_as_float(av[j][2 * i + 1]) + ay, lo);
+              }
             }
             if (E.flags & I2R_F_OUT_T16) {
               // channel-major rows: lanes hold consecutive pixels, so each 2-byte store instruction is coalesced
@@ -387,7 +400,7 @@ __device__ __forceinline__ void epilogue_role(const EpiArgs E, const int cta, co
               for (int i = 0; i < 8; ++i) {
                 const __half h = __float2half_rn(v[i]);
                 Y[static_cast<int64_t>(c0 + i) * E.out_pix_stride + p] = h;
-                if (split) Y[static_cast<int64_t>(E.Cout + c0 + i) * E.out_pix_stride + p] = __float2half_rn(v[i] - __half2float(h));
+                if (split) Y[static_cast<int64_t>(E.lo_off + c0 + i) * E.out_pix_stride + p] = __float2half_rn(v[i] - __half2float(h));
               }
             } else if (!(E.flags & (I2R_F_OUT_NCHW_F32 | I2R_F_OUT_F32))) {
               uint4 q;
@@ -408,7 +421,7 @@ __device__ __forceinline__ void epilogue_role(const EpiArgs E, const int cta, co
                   const float2 f = unpack_h2(hq[i]);
                   lq[i] = pack_h2(v[2 * i] - f.x, v[2 * i + 1] - f.y);
                 }
-                *reinterpret_cast<uint4*>(yq + E.Cout) = make_uint4(lq[0], lq[1], lq[2], lq[3]);
+                *reinterpret_cast<uint4*>(yq + E.lo_off) = make_uint4(lq[0], lq[1], lq[2], lq[3]);
               }
             } else if (E.flags & I2R_F_OUT_NCHW_F32) {
               float* Y = reinterpret_cast<float*>(E.y);
@@ -686,13 +699,14 @@ __global__ void __launch_bounds__(T_THREADS, 1) conv_halo_kernel(const __grid_co
     pdl_wait();   // addends are read and the output written only after every earlier kernel has finished
     EpiArgs E;
     E.add0 = P.add0; E.add1 = P.add1; E.y = P.y;
-    E.H = P.H; E.W = P.W; E.Cout = P.Cout; E.tiles_x = P.tiles_x; E.tiles_per_img = P.tiles_per_img;
+    E.H = P.H; E.W = P.W; E.Cout = P.Cout; E.lo_off = P.lo_off; E.tiles_x = P.tiles_x; E.tiles_per_img = P.tiles_per_img;
     E.ntiles = P.ntiles; E.cta_count = P.cta_count;
     E.out_pix_stride = P.out_pix_stride; E.add_pix_stride = P.add_pix_stride; E.plane = P.plane; E.flags = P.flags;
     const int ew = warp - 4;
     const int n8 = (P.Cout + 7) >> 3, half8 = (n8 + 1) >> 1;   // chunks holding real channels, split over the warp pair
     const int cb = (ew >> 2) ? half8 : 0, ce = (ew >> 2) ? n8 : half8;
-    if ((P.flags & (I2R_F_OUT_NCHW_F32 | I2R_F_OUT_F32 | I2R_F_SPLIT | I2R_F_OUT_T16)) || (P.Cout & 7) || dbg != 0 ||
+    if ((P.flags & (I2R_F_OUT_NCHW_F32 | I2R_F_OUT_F32 | I2R_F_SPLIT | I2R_F_OUT_T16 | I2R_F_GELU | I2R_F_ACT_FIRST)) ||
+        (P.Cout & 7) || dbg != 0 ||
         ce == cb) {
       epilogue_role<1>(E, cta, sbase, tmem_base, ncols, Npad, ew, warp & 3, lane, tr, trace_cap, dbg);
     } else if (P.add1 != nullptr) {
@@ -764,6 +778,7 @@ static bool is_std3x3(const i2r_conv_problem& P) {
   return true;
 }
 
+I2R_HANG_SINK_SETTER(conv_halo)
 }  // namespace i2r
 
 extern "C" int i2r_conv_halo_supported(const i2r_conv_problem* P) {
@@ -775,12 +790,6 @@ extern "C" int i2r_conv_halo_supported(const i2r_conv_problem* P) {
   if (P->OH != P->IH || P->OW != P->IW || P->OHf != P->OH || P->OWf != P->OW) return 0;
   if ((P->add0 && P->add0_shift != 0) || (P->add1 && P->add1_shift != 0)) return 0;
   if (P->Cin % 16 != 0 || P->Npad > 256 || P->Npad % 16 != 0) return 0;
-  // GELU / activation-before-add epilogues and channel-slice outputs of pair tensors (pair_lo_offset) live in the
-  // gather kernel only: adding them to this kernel's generic epilogue changed its code generation enough to expose a
-  // timing-dependent launch failure on split-mode streamed-weight problems, so the device code
-  // of this file is kept exactly as validated and those (HRFormer-B) problems are routed to i2r_conv_igemm
-  if (P->flags & (I2R_F_GELU | I2R_F_ACT_FIRST)) return 0;
-  if (P->pair_lo_offset > 0 && P->pair_lo_offset != P->Cout) return 0;
   if (P->KC != 64) return 0;
   if (P->in_pix_stride % 8 != 0) return 0;
   if ((P->add0 || P->add1) && (P->add_pix_stride % 8 != 0 || P->add_pix_stride < P->Cout)) return 0;
@@ -793,7 +802,8 @@ extern "C" int i2r_conv_halo(const i2r_conv_problem* probs, int nprob, void* str
     set_error("i2r_conv_halo: nprob=%d out of range", nprob);
     return I2R_E_BADARG;
   }
-  static int num_sms = 0;
+  static int num_sms_dev[MAX_DEVICES] = {};
+  int& num_sms = num_sms_dev[current_device()];
   if (num_sms == 0) {
     int dev = 0;
     cudaGetDevice(&dev);
@@ -840,6 +850,7 @@ extern "C" int i2r_conv_halo(const i2r_conv_problem* probs, int nprob, void* str
     }
     P.C = S.Cin;
     P.Cout = S.Cout;
+    P.lo_off = S.pair_lo_offset > 0 ? S.pair_lo_offset : S.Cout;
     P.Npad = S.Npad;
     P.KCH = 64;
     P.split = (S.flags & I2R_F_SPLIT) ? 1 : 0;
@@ -942,7 +953,8 @@ extern "C" int i2r_conv_halo(const i2r_conv_problem* probs, int nprob, void* str
       begin += cnt[i];
     }
   }
-  static bool attr_done = false;
+  static bool attr_done_dev[MAX_DEVICES] = {};   // the opt-in is a per-device property
+  bool& attr_done = attr_done_dev[current_device()];
   if (!attr_done) {
     cudaError_t e = cudaFuncSetAttribute(conv_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, T_MAX_SMEM + 1024);
     if (e != cudaSuccess) {

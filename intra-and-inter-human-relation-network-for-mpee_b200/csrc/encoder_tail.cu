@@ -449,7 +449,8 @@ static int launch_encoder_tail(const void* attn, int ld_attn, const void* src, i
                                void* out_pos, int ld, const void* wimg, const float* params, int T, float eps,
                                cudaStream_t st) {
   using C = EtCfg<SPLIT>;
-  static bool attr_done = false;
+  static bool attr_done_dev[MAX_DEVICES] = {};   // the opt-in is a per-device property
+  bool& attr_done = attr_done_dev[current_device()];
   if (!attr_done) {
     cudaError_t e = cudaFuncSetAttribute(encoder_tail_kernel<SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM);
     if (e != cudaSuccess) {
@@ -477,6 +478,7 @@ static int launch_encoder_tail(const void* attn, int ld_attn, const void* src, i
   return check_launch("encoder_tail_kernel");
 }
 
+I2R_HANG_SINK_SETTER(encoder_tail)
 }  // namespace i2r
 
 extern "C" int64_t i2r_encoder_tail_weight_bytes(int split) {

@@ -12,6 +12,15 @@ namespace i2r {
 void set_error(const char* fmt, ...);
 int check_launch(const char* what);
 
+// Per-device caches (SM count, shared-memory opt-in done) are indexed by the current device ordinal: the reference's
+// tools/test.py wraps the module in nn.DataParallel(device_ids=cfg.GPUS), i.e. several devices in one process.
+constexpr int MAX_DEVICES = 64;
+inline int current_device() {
+  int d = 0;
+  cudaGetDevice(&d);
+  return (d < 0 || d >= MAX_DEVICES) ? 0 : d;
+}
+
 // ---------------------------------------------------------------- programmatic dependent launch
 // The forward is a chain of ~130 short dependent kernels.  Every kernel is launched with the programmatic stream
 // serialization attribute, calls pdl_launch_dependents() first (so the NEXT grid's CTAs are scheduled as soon as SMs
@@ -56,41 +65,89 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
-// Bounded wait: a protocol bug traps (launch error reported to the host) instead of hanging the GPU.
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+// Bounded waits: a protocol bug reports itself and traps (launch error on the host) instead of hanging the GPU.
+// The bound is TIME based (2^31 SM cycles, ~1.1 s: no legitimate wait of these kernels is longer than a few ms) so
+// every stuck role of every CTA times out within the same window.  When a hang sink is installed
+// (i2r_debug_hang_buffer: host-mapped memory, readable after the context died) lane 0 of each timed-out warp records
+// {blockIdx.x << 32 | threadIdx.x, source line << 32 | barrier shared address, parity << 32 | dynamic-smem base,
+// clock64} and lingers 2^28 cycles before the trap so that the other stuck roles get to report as well.
+static __device__ unsigned long long* g_hang_sink = nullptr;   // one copy per translation unit (no -rdc)
+static __device__ unsigned int g_hang_count = 0;
+constexpr unsigned int HANG_SINK_RECORDS = 4096;
+static __device__ __noinline__ void mbar_timeout(uint32_t bar, uint32_t parity, int line) {
+  extern __shared__ uint8_t hang_dyn_smem[];
+  unsigned long long* sink = g_hang_sink;
+  if (sink != nullptr) {
+    const unsigned int idx = atomicAdd(&g_hang_count, 1u);
+    if (idx < HANG_SINK_RECORDS) {
+      volatile unsigned long long* e = sink + 4ull * idx;
+      e[0] = (static_cast<unsigned long long>(blockIdx.x) << 32) | threadIdx.x;
+      e[1] = (static_cast<unsigned long long>(line) << 32) | bar;
+      e[2] = (static_cast<unsigned long long>(parity) << 32) |
+             static_cast<uint32_t>(__cvta_generic_to_shared(hang_dyn_smem));
+      e[3] = static_cast<unsigned long long>(clock64());
+    }
+    __threadfence_system();
+    const long long t1 = clock64();
+    while (clock64() - t1 < (1ll << 28)) {
+    }
+  }
+  __trap();
+}
+#define I2R_HANG_SINK_SETTER(name)                                              \
+  void hang_sink_##name(void* host_mapped) {                                    \
+    unsigned long long* p = static_cast<unsigned long long*>(host_mapped);      \
+    unsigned int zero = 0;                                                      \
+    cudaMemcpyToSymbol(g_hang_sink, &p, sizeof(p));                             \
+    cudaMemcpyToSymbol(g_hang_count, &zero, sizeof(zero));                      \
+  }
+
+__device__ __forceinline__ bool mbar_try(uint32_t bar, uint32_t parity) {
   uint32_t done = 0;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(done)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return done != 0;
+}
+__device__ __forceinline__ void mbar_wait_at(uint32_t bar, uint32_t parity, int line) {
+  if (mbar_try(bar, parity)) return;
+  const long long t0 = clock64();
   uint32_t spins = 0;
-  while (true) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(done)
-        : "r"(bar), "r"(parity)
-        : "memory");
-    if (done) break;
-    if (++spins > (1u << 24)) __trap();
+  while (!mbar_try(bar, parity)) {
+    if ((++spins & 1023u) == 0 && clock64() - t0 > (1ll << 31)) mbar_timeout(bar, parity, line);
   }
 }
-
 // Wait used by roles that run far ahead of their consumers (TMA producers): back off between polls so the
 // spinning warp does not compete for issue slots with the epilogue warps of its scheduler partition.
-__device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity) {
-  uint32_t done = 0;
+__device__ __forceinline__ void mbar_wait_relaxed_at(uint32_t bar, uint32_t parity, int line) {
+  if (mbar_try(bar, parity)) return;
+  const long long t0 = clock64();
   uint32_t spins = 0;
-  while (true) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(done)
-        : "r"(bar), "r"(parity)
-        : "memory");
-    if (done) break;
+  while (!mbar_try(bar, parity)) {
     __nanosleep(128);
-    if (++spins > (1u << 22)) __trap();
+    if ((++spins & 255u) == 0 && clock64() - t0 > (1ll << 31)) mbar_timeout(bar, parity, line);
   }
 }
+// Wait for a WHOLE WARP whose lanes do not all take part in the work that follows (MMA issuer warps: the loop is
+// warp-uniform, one elected lane issues).  ONE lane polls and the warp re-converges at __syncwarp.  Letting all 32
+// lanes poll independently is NOT equivalent: the polling loop is a divergent exit, nothing forces the lanes back
+// together before the next wait, and the elected lane -- the only one with work to do -- can run a whole ring
+// revolution ahead of lanes still sitting in an earlier wait; the barrier they watch then completes a second phase,
+// the parity they wait for becomes the parity of the CURRENT incomplete phase again, and they spin forever while
+// every other role of the CTA finishes (the round-1 "unspecified launch failure": 31 lanes of the issuer warp stuck on
+// wfull[s] of a finished CTA, profiles/r02_hang_hunt.txt).  Whether it happens depends on where the compiler places the
+// re-convergence point of the polling loop and on the scheduler, hence the sensitivity to unrelated code changes.
+__device__ __forceinline__ void mbar_wait_warp_at(uint32_t bar, uint32_t parity, int line) {
+  if ((threadIdx.x & 31u) == 0) mbar_wait_at(bar, parity, line);
+  __syncwarp();
+}
+#define mbar_wait(bar, parity) ::i2r::mbar_wait_at((bar), (parity), __LINE__)
+#define mbar_wait_warp(bar, parity) ::i2r::mbar_wait_warp_at((bar), (parity), __LINE__)
+#define mbar_wait_relaxed(bar, parity) ::i2r::mbar_wait_relaxed_at((bar), (parity), __LINE__)
 
 // ---------------------------------------------------------------- async copies
 // 16-byte global->shared copy, zero-filled when src_bytes == 0 (padding taps / rows past M).

@@ -325,7 +325,7 @@ __device__ __forceinline__ void run_tile(const i2r_conv_problem& P, const int ti
     for (int it = 0; it < niter; ++it) {
       const int s = it % STAGES;
       const uint32_t ph = (it / STAGES) & 1;
-      mbar_wait(bar_full + 8 * s, ph);
+      mbar_wait_warp(bar_full + 8 * s, ph);   // one lane polls (see i2r_common.cuh)
       tc_fence_after();
       const uint32_t a_lo = a_lo0 + s * st16, b_lo = b_lo0 + s * st16;
       const int ksteps = min(4, (P.Cin - ((it % nchunks) % nkr) * 64) >> 4);
@@ -484,7 +484,8 @@ static int validate(const i2r_conv_problem& P, int idx) {
 
 template <int STAGES>
 static int launch_tc(const ConvGroup& G, int tiles, size_t smem, cudaStream_t st) {
-  static bool attr_done = false;
+  static bool attr_done_dev[MAX_DEVICES] = {};   // the opt-in is a per-device property
+  bool& attr_done = attr_done_dev[current_device()];
   if (!attr_done) {
     cudaError_t e = cudaFuncSetAttribute(igemm_tc_kernel<STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     if (e != cudaSuccess) {
@@ -497,6 +498,7 @@ static int launch_tc(const ConvGroup& G, int tiles, size_t smem, cudaStream_t st
   return check_launch("igemm_tc_kernel");
 }
 
+I2R_HANG_SINK_SETTER(igemm_tc)
 }  // namespace i2r
 
 extern "C" int i2r_conv_igemm(const i2r_conv_problem* probs, int nprob, int impl, void* stream) {

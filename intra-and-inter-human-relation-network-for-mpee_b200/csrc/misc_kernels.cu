@@ -27,6 +27,12 @@ bool pdl_enabled() {
   return v != 0;
 }
 
+void hang_sink_attention_tc(void*);
+void hang_sink_conv_halo(void*);
+void hang_sink_encoder_tail(void*);
+void hang_sink_igemm_tc(void*);
+void hang_sink_stem_tc(void*);
+
 int check_launch(const char* what) {
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {
@@ -519,4 +525,16 @@ extern "C" int i2r_upsum(const void* x0, const void* t1, int shift1, const void*
                                                               H, W, C, shift1, shift2, relu);
   }
   return check_launch("upsum_kernel");
+}
+
+// Debug aid: install (or remove, with nullptr) the host-mapped record buffer the bounded mbarrier waits report to before
+// they trap (i2r_common.cuh: mbar_timeout).  4096 records of four 64-bit words; synchronises the device.
+extern "C" int i2r_debug_hang_buffer(void* host_mapped) {
+  using namespace i2r;
+  hang_sink_attention_tc(host_mapped);
+  hang_sink_conv_halo(host_mapped);
+  hang_sink_encoder_tail(host_mapped);
+  hang_sink_igemm_tc(host_mapped);
+  hang_sink_stem_tc(host_mapped);
+  return check_launch("i2r_debug_hang_buffer");
 }

@@ -174,6 +174,7 @@ __global__ void __launch_bounds__(128) stem_tc_kernel(const float* __restrict__ 
   if (warp == 0) tmem_dealloc(tmem, 64);
 }
 
+I2R_HANG_SINK_SETTER(stem_tc)
 }  // namespace i2r
 
 extern "C" int64_t i2r_stem_tc_weight_bytes(void) { return i2r::ST_WIMG_BYTES; }

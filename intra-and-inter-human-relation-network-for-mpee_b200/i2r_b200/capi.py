@@ -4,7 +4,8 @@ import os
 import threading
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libi2r_sm100.so")
+# I2R_LIB: debugging aid (tools/hang_hunt.py loads instrumented builds of the same ABI); the product path never sets it
+LIB_PATH = os.environ.get("I2R_LIB") or os.path.join(HERE, "libi2r_sm100.so")
 
 I2R_MAX_TAPS = 9
 I2R_MAX_GROUP = 6
@@ -17,7 +18,7 @@ F_GELU = 32
 F_ACT_FIRST = 64
 
 EXPORTS = [
-    "i2r_version", "i2r_last_error", "i2r_device_check", "i2r_sm_count", "i2r_conv_igemm", "i2r_conv_halo", "i2r_conv_halo_supported", "i2r_debug_trace", "i2r_debug_flags",
+    "i2r_version", "i2r_last_error", "i2r_device_check", "i2r_sm_count", "i2r_conv_igemm", "i2r_conv_halo", "i2r_conv_halo_supported", "i2r_debug_trace", "i2r_debug_flags", "i2r_debug_hang_buffer",
     "i2r_sizeof_conv_problem", "i2r_stem_conv3x3s2", "i2r_stem_conv3x3s2_tc", "i2r_stem_tc_weight_bytes", "i2r_maxpool3x3s2", "i2r_attention_varlen", "i2r_attention_workspace_bytes", "i2r_attention_tc", "i2r_encoder_tail", "i2r_encoder_tail_weight_bytes", "i2r_attention_tc_workspace_bytes", "i2r_layernorm", "i2r_add_f16", "i2r_upsum", "i2r_dwconv3x3", "i2r_upsum_bilinear", "i2r_layernorm_padded", "i2r_window_rows", "i2r_ln_window_gather", "i2r_window_scatter_add", "i2r_window_attention",
 ]
 
@@ -70,6 +71,8 @@ def load():
         lib.i2r_conv_halo_supported.argtypes = [ctypes.POINTER(ConvProblem)]
         lib.i2r_debug_trace.argtypes = [vp, i32, i32]
         lib.i2r_debug_flags.argtypes = [i32]
+        if "i2r_debug_hang_buffer" in EXPORTS:      # tools/hang_hunt.py drops it to load older builds (I2R_LIB)
+            lib.i2r_debug_hang_buffer.argtypes = [vp]
         lib.i2r_stem_conv3x3s2.argtypes = [vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, vp]
         lib.i2r_stem_conv3x3s2_tc.argtypes = [vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, vp]
         lib.i2r_stem_tc_weight_bytes.restype = i64

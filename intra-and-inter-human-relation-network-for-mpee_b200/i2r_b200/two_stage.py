@@ -16,14 +16,14 @@ import torch.nn as nn
 
 from . import capi
 from .encoder import EncoderProgram
-from .engine import GraphedForward
+from .module_base import DevicePathModule
 from .hrnet_w48 import conv_bn_layer
 from .modules import DeconvProgram, EncoderParams, make_deconv_stack
 from .ops import Runner, channel_padding, split_precision
 from .position import MaskEmbedParams, MaskEmbedProgram
 
 
-class TwoStageInterFormer(nn.Module):
+class TwoStageInterFormer(DevicePathModule):
     def __init__(self, cfg, singleformer, flavor):
         super().__init__()
         assert flavor in ("interformer", "interformer_2stage")
@@ -40,6 +40,10 @@ class TwoStageInterFormer(nn.Module):
         self.multi_position_mode = m.MULTI_POS_EMBEDDING
         if m.get("ATTENTION_TYPE", "default") != "default":
             raise NotImplementedError("ATTENTION_TYPE=%r (every shipped config uses 'default')" % m.ATTENTION_TYPE)
+        if flavor == "interformer" and m.get("NORMALIZE_BEFORE", False):
+            # lib/models/attention.py:1040 -- only this flavor's encoder honours the flag; silently running post-norm
+            # would return wrong heatmaps
+            raise NotImplementedError("NORMALIZE_BEFORE=True (pre-norm encoder; every shipped config uses post-norm)")
         if m.get("DOMAIN_TRANS", False):
             raise NotImplementedError("DOMAIN_TRANS=True (no shipped config enables it)")
         self.multi_position_embedding = MaskEmbedParams(self.trans_size, d_model, mode=self.multi_position_mode,
@@ -70,11 +74,7 @@ class TwoStageInterFormer(nn.Module):
         self.final_layer = nn.Conv2d(d_model, m.NUM_JOINTS, k, 1, 1 if k == 3 else 0)
         self._cfg = dict(d_model=d_model, nhead=m.N_HEAD, layers=m.ENCODER_MULTI_LAYERS, final_k=k,
                          num_deconv=extra.NUM_DECONV_LAYERS)
-        self._program = None
-        self._graphs = GraphedForward(self._eager)
-        self.use_cuda_graph = os.environ.get("I2R_CUDA_GRAPH", "1") != "0"
-        self.check_impl = False
-        self._runner_factory = Runner
+        self._init_device_path(Runner)
 
     @property
     def returns_dict(self):
@@ -99,16 +99,7 @@ class TwoStageInterFormer(nn.Module):
         prog.first = self.singleformer.build_program(device)
         with split_precision(prog.split), channel_padding(16 if c["d_model"] % 16 else 0):
             self._build_second_stage(prog, sd, c, device)
-        offsets = {}
-
-        def seq_offsets(length, tokens_per_person):
-            key = (tuple(length), tokens_per_person)
-            if key not in offsets:
-                offsets[key] = GraphedForward.seq_offsets(length, tokens_per_person, device)
-            return offsets[key]
-        prog.seq_offsets = seq_offsets
-        self._program = prog
-        self._graphs.reset()
+        self._program_ready(prog)
         return self
 
     def _build_second_stage(self, prog, sd, c, device):
@@ -124,32 +115,19 @@ class TwoStageInterFormer(nn.Module):
         prog.upsample = [deconv(k) for k in self._deconv_keys]
         prog.head = conv_bn_layer(sd, "final_layer", None, device=device)
 
-    def load_state_dict(self, *a, **kw):
-        out = super().load_state_dict(*a, **kw)
-        self._program = None
-        return out
-
-    def _apply(self, fn, *a, **kw):
-        out = super()._apply(fn, *a, **kw)
-        self._program = None
-        return out
-
     # ------------------------------------------------------------------ forward
-    def _eager(self, x, pos_mask, length, mask_needed=None):
-        p = self._program
-        r = p.runner
-        feat, heat_single = self._run_first(p, r, x)                         # [S,h,w,d] fp16, [S,K,h,w] fp32
+    # the four stages DevicePathModule._eager (and sharded.ShardedForward) compose
+    def _stage_tokens(self, p, r, x):
+        feat, heat_single = p.first.run(r, x)                                # [S,h,w,d] fp16, [S,K,h,w] fp32
         tok = feat
         for _ in range(int(math.log(feat.shape[2] // self.trans_size[-1], 2))):   # interformer.py:260-264
             tok = r.maxpool(tok)
-        s, th, tw, d = tok.shape
-        pos = None
-        if p.mask_embed is not None:
-            if mask_needed is not None:
-                mask_needed()         # engine.GraphedForward: the graph is cut here (mask upload overlaps what precedes)
-            pos = p.mask_embed.run(r, pos_mask, (th, tw)).view(s * th * tw, d)
-        cu = p.seq_offsets(length, th * tw)
-        y = p.encoder.run(r, tok.view(s * th * tw, d), pos, cu, max(length) * th * tw).view(s, th, tw, d)
+        return feat, heat_single, tok
+
+    def _stage_pos(self, p, r, pos_mask, hw):
+        return None if p.mask_embed is None else p.mask_embed.run(r, pos_mask, hw)
+
+    def _stage_head(self, p, r, y, feat, heat_single):
         for stack in p.upsample:
             for dc in stack:
                 y = dc.run(r, y)
@@ -158,48 +136,6 @@ class TwoStageInterFormer(nn.Module):
         if self.returns_dict:
             return {"single": heat_single, "multi": heat_multi}
         return heat_multi
-
-    @staticmethod
-    def _run_first(p, r, x):
-        """First stage over all crops.  In split-operand mode the crops go through in groups: the persistent conv kernel
-        has a latent fault (launch failure, timing dependent, clean under compute-sanitizer) when a CTA of a
-        STREAMED-weight split-mode problem runs four or more tiles (first seen on the 64 -> 256 1x1 + residual of
-        layer1 at >= 24 crops).  Per-crop stages are independent, so grouping is exact; the group
-        size keeps the largest GEMM of the stage at <= 3 tiles per CTA."""
-        s, _, h, w = x.shape
-        if not p.split:
-            return p.first.run(r, x)
-        rows = max((h // 4) * (w // 4), ((h // 4 + 6) // 7 * 7) * ((w // 4 + 6) // 7 * 7))   # pixels / window rows per crop
-        group = max(1, (3 * 148 * 128) // rows)
-        if s <= group:
-            return p.first.run(r, x)
-        feats, heats = [], []
-        for i in range(0, s, group):
-            f, hm = p.first.run(r, x[i:i + group])
-            feats.append(f)
-            heats.append(hm)
-        return torch.cat(feats, 0), torch.cat(heats, 0)
-
-    def forward(self, x, pos_mask, length):
-        length = [int(n) for n in length]
-        if sum(length) != x.shape[0] or x.shape[0] != pos_mask.shape[0]:
-            raise ValueError("sum(length)=%d must equal the number of crops %d" % (sum(length), x.shape[0]))
-        if min(length) < 1:
-            raise ValueError("every image needs at least one person crop")
-        dev = self.final_layer.weight.device
-        if dev.type != "cuda":
-            raise capi.I2RError("%s forward runs on a CUDA (sm_100a) device only; move the module with .cuda() -- "
-                                "there is no CPU fallback" % self.flavor)
-        if self._program is None or self._program.device != dev:
-            self.prepare(dev)
-        with torch.no_grad():
-            if self.use_cuda_graph:      # host tensors are uploaded straight into the graphs' static buffers
-                if x.dtype != torch.float32 or pos_mask.dtype != torch.float32:
-                    x, pos_mask = x.float(), pos_mask.float()
-                return self._graphs(x, pos_mask, length, device=dev)
-            x = x.to(dev, dtype=torch.float32, non_blocking=True).contiguous()
-            pos_mask = pos_mask.to(dev, dtype=torch.float32, non_blocking=True).contiguous()
-            return self._eager(x, pos_mask, length)
 
 
 def build(cfg, is_train, flavor, models_pkg):

@@ -19,13 +19,15 @@ from i2r_b200.hrnet_w48 import BackboneProgram, attach_backbone_params, conv_bn_
 from i2r_b200.ops import ConvLayer, Runner
 from i2r_b200.packing import deconv4x4s2_phase_taps, fold_bn
 from i2r_b200.position import MaskEmbedParams, MaskEmbedProgram, sine_table
-from i2r_b200.engine import GraphedForward
+from i2r_b200.module_base import DevicePathModule
 from i2r_b200.modules import DeconvProgram, EncoderParams
 
 logger = logging.getLogger(__name__)
 
 
-class TransPoseH(nn.Module):
+class TransPoseH(DevicePathModule):
+    flavor = "interformer_pureMulti"
+
     def __init__(self, cfg, **kwargs):
         super().__init__()
         extra = cfg["MODEL"]["EXTRA"]
@@ -63,11 +65,7 @@ class TransPoseH(nn.Module):
         self.pretrained_layers = extra["PRETRAINED_LAYERS"]
         self._cfg = dict(d_model=d_model, nhead=m.N_HEAD, layers=m.ENCODER_LAYERS, num_deconv=nl, final_k=k,
                          mode=m.MULTI_POS_EMBEDDING)
-        self._program = None
-        self._graphs = GraphedForward(self._eager)
-        self.use_cuda_graph = os.environ.get("I2R_CUDA_GRAPH", "1") != "0"
-        self.check_impl = False   # tests: route implicit GEMMs through the scalar check kernel
-        self._runner_factory = Runner
+        self._init_device_path(Runner)
 
     # ------------------------------------------------------------------ weights -> device program
     def prepare(self, device=None):
@@ -89,71 +87,24 @@ class TransPoseH(nn.Module):
         prog.deconvs = [DeconvProgram(sd, "deconv_layers.%d" % (3 * i), "deconv_layers.%d" % (3 * i + 1), device)
                         for i in range(c["num_deconv"])]
         prog.head = conv_bn_layer(sd, "final_layer", None, device=device)
-        offsets = {}
-
-        def seq_offsets(length, tokens_per_person):
-            # device copy of the per-image token offsets; cached so that graph capture sees no H2D copy
-            key = (tuple(length), tokens_per_person)
-            if key not in offsets:
-                offsets[key] = GraphedForward.seq_offsets(length, tokens_per_person, device)
-            return offsets[key]
-        prog.seq_offsets = seq_offsets
-        self._program = prog
-        self._graphs.reset()
+        self._program_ready(prog)
         return self
 
-    def load_state_dict(self, *a, **kw):
-        out = super().load_state_dict(*a, **kw)
-        self._program = None
-        return out
-
-    def _apply(self, fn, *a, **kw):
-        out = super()._apply(fn, *a, **kw)
-        self._program = None
-        return out
-
     # ------------------------------------------------------------------ forward
-    def _eager(self, x, pos_mask, length, mask_needed=None):
-        p = self._program
-        r = p.runner
+    # the four stages DevicePathModule._eager (and sharded.ShardedForward) compose
+    def _stage_tokens(self, p, r, x):
         feats = p.backbone.run(r, x)
-        tok_map = r.conv(p.reduce, feats[-1])                      # [S, 16, 12, d]
-        s, th, tw, d = tok_map.shape
-        src = tok_map.view(s * th * tw, d)
-        pos = None
-        if p.mask_embed is not None:
-            if mask_needed is not None:
-                mask_needed()         # engine.GraphedForward: the graph is cut here (mask upload overlaps what precedes)
-            pos = p.mask_embed.run(r, pos_mask, (th, tw)).view(s * th * tw, d)
-        cu = p.seq_offsets(length, th * tw)
-        y = p.encoder.run(r, src, pos, cu, max(length) * th * tw)
-        y = y.view(s, th, tw, d)
+        return None, None, r.conv(p.reduce, feats[-1])             # no first-stage feature / heatmaps; [S, 16, 12, d]
+
+    def _stage_pos(self, p, r, pos_mask, hw):
+        return None if p.mask_embed is None else p.mask_embed.run(r, pos_mask, hw)
+
+    def _stage_head(self, p, r, y, feat, heat_single):
         for dc in p.deconvs:      # the reference applies the same deconv stack twice (:774-775)
             y = dc.run(r, y)
         for dc in p.deconvs:
             y = dc.run(r, y)
         return r.conv(p.head, y, out_mode="nchw32")
-
-    def forward(self, x, pos_mask, length):
-        length = [int(n) for n in length]
-        if sum(length) != x.shape[0] or x.shape[0] != pos_mask.shape[0]:
-            raise ValueError("sum(length)=%d must equal the number of crops %d" % (sum(length), x.shape[0]))
-        if min(length) < 1:
-            raise ValueError("every image needs at least one person crop")
-        dev = self.final_layer.weight.device
-        if dev.type != "cuda":
-            raise capi.I2RError("interformer_pureMulti forward runs on a CUDA (sm_100a) device only; "
-                                "move the module with .cuda() -- there is no CPU fallback")
-        if self._program is None or self._program.device != dev:
-            self.prepare(dev)
-        with torch.no_grad():
-            if self.use_cuda_graph:      # host tensors are uploaded straight into the graphs' static buffers
-                if x.dtype != torch.float32 or pos_mask.dtype != torch.float32:
-                    x, pos_mask = x.float(), pos_mask.float()
-                return self._graphs(x, pos_mask, length, device=dev)
-            x = x.to(dev, dtype=torch.float32, non_blocking=True).contiguous()
-            pos_mask = pos_mask.to(dev, dtype=torch.float32, non_blocking=True).contiguous()
-            return self._eager(x, pos_mask, length)
 
     def init_weights(self, pretrained="", fixed=False, print_load_info=False):
         """Training-time initialisation (reference :779-813): N(0, 0.001) convs, identity BN, then the
@@ -181,7 +132,7 @@ class TransPoseH(nn.Module):
         elif pretrained:
             logger.error("=> please download pre-trained models first!")
             raise ValueError("{} is not exist!".format(pretrained))
-        self._program = None
+        self.invalidate()
 
 
 def get_pose_net(cfg, is_train, **kwargs):

@@ -35,7 +35,14 @@ CASES = {
     "hrt2stage_ragged": ("coco/interformer_coco_hrt_192_p2_b12.yaml", [2, 1], 256, 192),
     # 384x288: 96x72 branch-0 maps padded to 98x77 windows, 24x18 token maps per person
     "hrt288_c1": ("coco/interformer_coco_hrt_288_p2_b4.yaml", [1], 384, 288),
+    # BASELINE shapes of the HRFormer-B families, one image per rank: C4 = 8 persons at 256x192 (inter-human sequence of
+    # 1536 tokens), C5 = 12 persons at 384x288 (5184 tokens); plus a three-image ragged batch.  Heatmaps are stored
+    # subsampled (every 4th row / column, SUBSAMPLE below) to keep the fixtures small.
+    "hrt_c4_rank": ("coco/interformer_coco_hrt_192_p2_b12.yaml", [8], 256, 192),
+    "hrt_c5_rank": ("coco/interformer_coco_hrt_288_p2_b4.yaml", [12], 384, 288),
+    "hrt_ragged3": ("coco/interformer_coco_hrt_192_p2_b12.yaml", [3, 1, 2], 256, 192),
 }
+SUBSAMPLE = {"hrt_c4_rank": 4, "hrt_c5_rank": 4, "hrt_ragged3": 4}
 
 
 def main():
@@ -69,11 +76,15 @@ def main():
         for hk in hooks:
             hk.remove()
         arrays = {"length": np.asarray(length, dtype=np.int64)}
+        sub = SUBSAMPLE.get(name, 1)
+        if sub > 1:
+            arrays["subsample"] = np.asarray(sub, dtype=np.int64)
         if isinstance(out, dict):
             for k, v in out.items():
-                arrays["out_" + k] = v.numpy()
+                arrays["out_" + k] = v.numpy()[:, :, ::sub, ::sub]
+                arrays["absmax_" + k] = np.asarray(float(v.abs().max()))
         else:
-            arrays["out"] = out.numpy()
+            arrays["out"] = out.numpy()[:, :, ::sub, ::sub]
         for k, v in taps.items():
             arrays["tap_" + k] = v.numpy()
         np.savez_compressed(os.path.join(HERE, name + ".npz"), **arrays)
