@@ -360,7 +360,9 @@ def main():
     barrier()
     ms = e0.elapsed_time(e1)
     # ---- the same loop sustained for >= --sustain-seconds (clocks / power settle; the 20-step region is ~40 ms)
-    sus_steps = max(args.steps, int(args.sustain_seconds * 1e3 / max(ms / args.steps, 1e-3)))
+    from i2r_b200.sharding import max_over_ranks
+    ms_all = max_over_ranks([ms], device=dev)[0]      # every rank must run the same number of steps (collectives)
+    sus_steps = max(args.steps, int(args.sustain_seconds * 1e3 / max(ms_all / args.steps, 1e-3)))
     s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     s0.record()
@@ -398,7 +400,6 @@ def main():
     ms_e2e = f0.elapsed_time(f1)
     clocks = sampler.finish() if rank == 0 else None
 
-    from i2r_b200.sharding import max_over_ranks
     ms, ms_e2e, ms_sus = max_over_ranks([ms, ms_e2e, ms_sus], device=dev)
 
     if rank == 0:

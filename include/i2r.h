@@ -241,6 +241,27 @@ int i2r_debug_flags(int flags);
  * address, parity << 32 | dynamic shared base, clock64}.  NULL removes it.  Synchronises the device. */
 int i2r_debug_hang_buffer(void* host_mapped);
 
+/* ---- post-processing on the device (N1 flip-test fusion, N2 heatmap decode) ------------------------ */
+
+/* dst[r, w] = src[r, W-1-w] on fp32 rows of W elements (out of place): np.flip(input, 3) of the flip test
+ * (lib/core/function.py:145-149) for x [S,3,H,W] and pos_mask [S,1,H,W] viewed as rows. */
+int i2r_hflip_f32(const float* src, float* dst, int64_t rows, int W, void* stream);
+
+/* y[s,k,h,w] = 0.5 * (out[s,k,h,w] + out_flipped[s, perm[k], h, W-1-w]): `flip_back` (lib/utils/transforms.py:16-30:
+ * reverse the width axis, swap the matched left/right joints -- `perm` is that permutation as K int32 on the device)
+ * fused with `(output + output_flipped) * 0.5` (lib/core/function.py:158-162).  fp32 NCHW heatmaps. */
+int i2r_flip_merge(const float* out, const float* out_flipped, float* y, int S, int K, int H, int W, const int32_t* perm,
+                   void* stream);
+
+/* get_final_preds (lib/core/inference.py:90-112) for fp32 heatmaps hm [S,K,H,W] on the device: get_max_preds (:20-48:
+ * arg-max, x = idx % W, y = floor(idx / W), zeroed when the maximum is <= 0), gaussian_blur (:73-87: zero-padded
+ * cv2.GaussianBlur(ksize = blur_kernel, sigma from ksize) in double, renormalised to the original maximum), log of
+ * max(., 1e-10), taylor (:51-70: second-order step, interior maxima only), and, when transform_back != 0,
+ * transform_preds (lib/utils/transforms.py:50-56) with center / scale [S,2] fp32 on the device.
+ * preds [S,K,2] fp32 (x, y), maxvals [S,K] fp32.  One CTA per heatmap; H*W*16 bytes of shared memory (<= 200 KB). */
+int i2r_decode_heatmaps(const float* hm, int S, int K, int H, int W, const float* center, const float* scale,
+                        int blur_kernel, int transform_back, float* preds, float* maxvals, void* stream);
+
 /* sizeof(i2r_conv_problem) as compiled -- lets the ctypes binding verify its struct layout. */
 int i2r_sizeof_conv_problem(void);
 

@@ -117,3 +117,26 @@ class DevicePathModule(nn.Module):
                 x = x.to(dev, dtype=torch.float32, non_blocking=True).contiguous()
                 pos_mask = pos_mask.to(dev, dtype=torch.float32, non_blocking=True).contiguous()
                 return self._eager(x, pos_mask, length)
+
+    def forward_flip(self, x, pos_mask, length, flip_pairs):
+        """The reference's flip test (lib/core/function.py:142-162) as ONE forward: the crops and their mirror images
+        go through the network as one batch of 2*S crops (the mirrored crops of an image form an image of their own, so
+        the inter-human stage sees exactly what the reference's second forward sees), then
+        `(out + flip_back(out_flipped, flip_pairs)) * 0.5` (lib/utils/transforms.py:16-30) is one kernel on the device --
+        no numpy flips, no second launch sequence, no D2H / H2D round trip.  Returns what forward returns."""
+        from . import postproc
+        length = [int(n) for n in length]
+        dev = self._device()
+        if dev.type != "cuda":
+            raise capi.I2RError("%s forward_flip runs on a CUDA (sm_100a) device only" % self.flavor)
+        with torch.cuda.device(dev), torch.no_grad():
+            x = x.to(dev, dtype=torch.float32, non_blocking=True).contiguous()
+            pos_mask = pos_mask.to(dev, dtype=torch.float32, non_blocking=True).contiguous()
+            s = x.shape[0]
+            x2 = torch.cat([x, postproc.hflip(x)], 0)
+            m2 = torch.cat([pos_mask, postproc.hflip(pos_mask)], 0)
+            out = self.forward(x2, m2, length + length)
+
+            def merge(o):
+                return postproc.flip_merge(o[:s], o[s:], flip_pairs)
+            return {k: merge(v) for k, v in out.items()} if isinstance(out, dict) else merge(out)

@@ -61,3 +61,26 @@ def synth_inputs(num_crops, height=256, width=192, seed=1):
     x = g.standard_normal(size=(num_crops, 3, height, width), dtype=np.float32)
     pm = g.random(size=(num_crops, 1, height, width), dtype=np.float32)
     return torch.from_numpy(x), torch.from_numpy(pm)
+
+
+def synth_heatmaps(n, k, h, w, seed=0):
+    """Heatmap-like fp32 maps [n,k,h,w], bit-reproducible on every platform (integers from PCG64 and IEEE add / mul /
+    div only, no transcendental functions): one to three rational bumps amp / (1 + d^2 / s^2) plus small noise; map
+    (0,0) is entirely negative, (0,1) has its maximum in a corner, (0,2) one pixel outside the Taylor interior."""
+    g = np.random.default_rng(int(seed))
+    ys, xs = np.mgrid[0:h, 0:w].astype(np.float64)
+    hm = np.zeros((n, k, h, w), dtype=np.float32)
+    for i in range(n):
+        for j in range(k):
+            m = (g.integers(-1000, 1001, size=(h, w)).astype(np.float64)) / 100000.0
+            for _ in range(int(g.integers(1, 4))):
+                cy = float(g.integers(-200, 100 * h + 200)) / 100.0
+                cx = float(g.integers(-200, 100 * w + 200)) / 100.0
+                amp = float(g.integers(20, 101)) / 100.0
+                s2 = (float(g.integers(100, 301)) / 100.0) ** 2
+                m = m + amp / (1.0 + ((ys - cy) ** 2 + (xs - cx) ** 2) / (2.0 * s2))
+            hm[i, j] = m.astype(np.float32)
+    hm[0, 0] = -np.abs(hm[0, 0]) - np.float32(0.01)
+    hm[0, 1, 0, 0] = 5.0
+    hm[0, 2, h - 2, w - 3] = 5.0
+    return hm
