@@ -262,6 +262,21 @@ int i2r_flip_merge(const float* out, const float* out_flipped, float* y, int S, 
 int i2r_decode_heatmaps(const float* hm, int S, int K, int H, int W, const float* center, const float* scale,
                         int blur_kernel, int transform_back, float* preds, float* maxvals, void* stream);
 
+/* ---- input pipeline on the device (N3) -------------------------------------------------------------- */
+
+/* Person crops of ONE image: x[n] = Normalize(ToTensor(cv2.warpAffine(image, trans_n, (OW, OH), INTER_LINEAR)))
+ * (lib/dataset/JointsDataset.py:296-303, :329-330; tools/test.py:126-134).  image: uint8 RGB [IH, IW, 3] on the device;
+ * inv_affine: [N, 6] doubles on the device = the dst -> src matrix cv2.warpAffine derives from the forward matrix of
+ * get_affine_transform (lib/utils/transforms.py:58-92); mean3 / std3: host pointers to 3 floats; x: fp32 [N,3,OH,OW].
+ * 8-bit fixed-point arithmetic of cv2 (bit-exact against cv2 4.13). */
+int i2r_crop_persons(const uint8_t* image, int IH, int IW, const double* inv_affine, int N, int OH, int OW,
+                     const float* mean3, const float* std3, float* x, void* stream);
+
+/* Per-person box masks of one image: ToTensor(cv2.resize(rotate_bound(get_position(box), 0), (OW, OH)))
+ * (lib/dataset/JointsDataset.py:166-201, :323-331).  rect: int32 [N, 4] on the device, the inclusive corners
+ * (x0, y0, x1, y1) cv2.rectangle fills = (int(x), int(y), int(x+w), int(y+h)) ordered; pos_mask: fp32 [N,1,OH,OW]. */
+int i2r_box_masks(const int32_t* rect, int N, int IH, int IW, int OH, int OW, float* pos_mask, void* stream);
+
 /* sizeof(i2r_conv_problem) as compiled -- lets the ctypes binding verify its struct layout. */
 int i2r_sizeof_conv_problem(void);
 

@@ -25,6 +25,7 @@
 #include <cuda.h>
 
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "i2r_common.cuh"
@@ -55,6 +56,11 @@ struct HaloProblem {
   int a_stages, w_stages;
   int w_copies;
   uint32_t w_off;      // byte offset of the weight region in dynamic smem
+  // CTA-pair mode (tcgen05 cta_group::2): two CTAs of a cluster compute one M256 x Npad tile pair; each holds its own
+  // 128-pixel activation tile and HALF of the weight rows.  `ntiles` is then the number of tile PAIRS (loop bound of a
+  // pair), `ntiles_real` the number of 128-pixel tiles; CTA `rank` of pair q works on tile 2*j + rank.
+  int pair, ntiles_real;
+  uint32_t w_gstage;   // bytes between consecutive (tap, K-chunk) blocks of the packed weight image in global memory
 };
 
 struct HaloGroup {
@@ -64,6 +70,7 @@ struct HaloGroup {
   int dbg;                     // debug ablations (i2r_debug_flags): 1 = epilogue hand-shake only, 2 = no global stores / residual loads
   HaloProblem p[I2R_MAX_GROUP];
   int nprob;
+  int total_ctas;              // CTAs that own work; the grid may hold one filler CTA more (whole clusters)
 };
 
 // Launch parameters live in the constant bank; a loop that mentions P.field re-reads it with an indexed uniform
@@ -98,6 +105,7 @@ __device__ __forceinline__ HaloProblem load_problem(const HaloProblem& s) {
   p.a_stage_bytes = opaque(s.a_stage_bytes); p.a_tx_bytes = opaque(s.a_tx_bytes);
   p.a_stages = opaque(s.a_stages); p.w_stages = opaque(s.w_stages); p.w_off = opaque(s.w_off);
   p.w_copies = opaque(s.w_copies);
+  p.pair = opaque(s.pair); p.ntiles_real = opaque(s.ntiles_real); p.w_gstage = opaque(s.w_gstage);
   return p;
 }
 
@@ -134,36 +142,112 @@ __device__ __forceinline__ void trace_ev(unsigned long long* tr, int cap, int ro
   }
 }
 
-template <int NTAPS, int KS>
+// ---- CTA-pair (cta_group::2) primitives --------------------------------------------------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of `local` (a shared::cta address of this CTA) in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t mapa_rank(uint32_t local, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void tmem_alloc2(uint32_t smem_dst, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish2() {
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc2(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// One M256 x N x K16 product over the CTA pair: every CTA's descriptors address ITS OWN shared memory (128 rows of A,
+// N/2 rows of B at the same offsets in both CTAs); issued by the leader CTA only.  Columns [0, N/2) of the accumulator
+// come from the leader's B rows, [N/2, N) from the peer's (tools/mma2_probe.cu).
+__device__ __forceinline__ void umma2_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrive on the mbarrier at this shared-memory offset in BOTH CTAs once every MMA issued so far has completed
+__device__ __forceinline__ void umma2_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"(static_cast<uint16_t>(3)) : "memory");
+}
+template <bool PAIR>
+__device__ __forceinline__ void mma_g(uint32_t d, uint64_t a, uint64_t b, uint32_t idesc, uint32_t acc) {
+  if (PAIR) umma2_f16(d, a, b, idesc, acc); else umma_f16(d, a, b, idesc, acc);
+}
+template <bool PAIR>
+__device__ __forceinline__ void commit_g(uint32_t bar) {
+  if (PAIR) umma2_commit(bar); else umma_commit(bar);
+}
+template <int KS, bool PAIR>
+__device__ __forceinline__ void issue_ksteps_g(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                               uint32_t idesc, uint32_t acc_first) {
+#pragma unroll
+  for (int k2 = 0; k2 < KS; ++k2)
+    mma_g<PAIR>(d_tmem, desc64(a_lo + 2 * k2, a_hi), desc64(b_lo + 2 * k2, b_hi), idesc, k2 ? 1u : acc_first);
+}
+
+template <int NTAPS, int KS, bool PAIR>
 __device__ __forceinline__ void issue_taps(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_tap,
                                            uint32_t b_hi, uint32_t idesc, uint32_t acc_first) {
   constexpr int PW = NTAPS == 9 ? T_TW + 2 : T_TW;
 #pragma unroll
   for (int tap = 0; tap < NTAPS; ++tap) {
     const uint32_t a_t = a_lo + (NTAPS == 9 ? static_cast<uint32_t>(((tap / 3) * PW + (tap % 3)) * 8) : 0u);
-    issue_ksteps<KS>(d_tmem, a_t, a_hi, b_lo + tap * b_tap, b_hi, idesc, tap ? 1u : acc_first);
+    issue_ksteps_g<KS, PAIR>(d_tmem, a_t, a_hi, b_lo + tap * b_tap, b_hi, idesc, tap ? 1u : acc_first);
   }
 }
+
+// Barrier map (byte offsets from the 1024-aligned base of dynamic shared memory; 8 bytes each):
+//   afull[4] 0 (pair: the leader's counts both CTAs' tiles) | aempty[4] 32 | (64..127 free) | accfull[2] 128 |
+//   accempty[2] 144 | wres 160 | pwres 168 (pair: peer's resident weights landed) | tmem slot 176 |
+//   pwfull[8] 192 (pair, streamed: peer's weight slot landed) | wfull[8] 256 | wempty[8] 320
+constexpr uint32_t B_AFULL = 0, B_AEMPTY = 32, B_PFULL = 64, B_ACCFULL = 128, B_ACCEMPTY = 144, B_WRES = 160, B_PWRES = 168,
+                   B_PWFULL = 192, B_WFULL = 256, B_WEMPTY = 320;
 
 // MMA issue loop.  Everything here is warp-uniform (kernel parameters, loop counters, shared-memory
 // addresses), so descriptor arithmetic stays on the uniform datapath and costs two 32-bit adds per
 // tcgen05.mma: the loop must sustain one MMA every ~25 cycles for N = 48.
-template <int NTAPS>
+// MODE 0: one CTA per tile (cta_group::1).  MODE 1: leader of a CTA pair (cta_group::2: M256, waits for the peer's
+// operands as well, commits arrive in both CTAs).  MODE 2: the peer's SHADOW of this loop: it waits for the peer's own
+// operand barriers in the same order and forwards each completion to the leader's p-barrier (no MMAs, no commits).
+template <int NTAPS, int MODE>
 __device__ __forceinline__ void mma_role(const HaloProblem& P, const int cta, const uint32_t sbase,
                                          const uint32_t tmem_base, const uint32_t ncols, unsigned long long* tr,
                                          const int trcap, const int dbg, const int iw) {
+  constexpr bool PAIR = MODE != 0;
+  constexpr bool ISSUE = MODE != 2;
   constexpr int HALO = NTAPS == 9 ? 1 : 0;
   constexpr int PW = T_TW + 2 * HALO;   // halo line = PW pixels = PW 128-byte rows (dense TMA box)
   constexpr uint32_t A_SBO = PW * 128;
-  const uint32_t bar_afull = sbase, bar_aempty = sbase + 32, bar_wfull = sbase + 256, bar_wempty = sbase + 320;
-  const uint32_t bar_accfull = sbase + 128, bar_accempty = sbase + 144, bar_wres = sbase + 160;
+  const uint32_t bar_afull = sbase + B_AFULL, bar_aempty = sbase + B_AEMPTY, bar_wfull = sbase + B_WFULL,
+                 bar_wempty = sbase + B_WEMPTY;
+  const uint32_t bar_accfull = sbase + B_ACCFULL, bar_accempty = sbase + B_ACCEMPTY, bar_wres = sbase + B_WRES;
+  const uint32_t bar_pwres = sbase + B_PWRES, bar_pwfull = sbase + B_PWFULL;
+  // shadow: the leader's p-barriers as shared::cluster addresses
+  const uint32_t r_pwres = MODE == 2 ? mapa_rank(bar_pwres, 0) : 0u, r_pwfull = MODE == 2 ? mapa_rank(bar_pwfull, 0) : 0u;
   const uint32_t a_base = sbase + T_A_OFF;
   const uint32_t w_base = sbase + P.w_off;
   const int Npad = P.Npad;
-  const uint32_t idesc = make_idesc_f16(128, Npad);
+  const uint32_t idesc = make_idesc_f16(PAIR ? 256 : 128, Npad);
   const uint32_t b_hi = sw128_desc_hi(1024, 0);
   const uint32_t a_hi = sw128_desc_hi(A_SBO, 0);   // base_offset 0: the swizzle XOR follows absolute smem address bits
-  const uint32_t w_stage16 = P.w_stage_bytes >> 4;                         // one (tap, K-chunk) block = Npad rows x 128 B
+  const uint32_t w_stage16 = P.w_stage_bytes >> 4;                         // one (tap, K-chunk) block in shared memory
   const uint32_t b_tap = static_cast<uint32_t>(P.nkc) * w_stage16;         // resident: next tap
   const uint32_t w_slot16 = P.w_slot_bytes >> 4;                           // streamed: one ring slot (TG blocks)
   const uint32_t w_lo0 = sw128_desc_lo(w_base);
@@ -171,6 +255,7 @@ __device__ __forceinline__ void mma_role(const HaloProblem& P, const int cta, co
   const uint32_t a_lo0 = sw128_desc_lo(a_base);
   const bool resident = P.w_resident != 0;
   const bool leader = elect_one();
+  const bool lane0 = (threadIdx.x & 31u) == 0;
   int tri = 0;
   // Two issuer warps alternate over the CTA's tiles: issuer iw owns TMEM accumulator iw and local tiles
   // iw, iw+2, ...  While one issuer sits in its barrier waits (~300 cycles each with the shared-memory port
@@ -188,24 +273,32 @@ __device__ __forceinline__ void mma_role(const HaloProblem& P, const int cta, co
   const int a_first = iw * a_half, w_first = iw * w_half;
   int as = 0, ws = 0;
   uint32_t aph = 0, wph = 0;
-  if (resident) mbar_wait_warp(bar_wres, 0);
+  if (resident) {
+    mbar_wait_warp(bar_wres, 0);
+    if (MODE == 1) mbar_wait_warp(bar_pwres, 0);
+    if (MODE == 2 && lane0 && iw == 0) mbar_arrive_remote(r_pwres);
+  }
   if (leader) trace_ev(tr, trcap, 1, tri, 13, 0);
   const uint32_t ones_lo = sw128_desc_lo(sbase + T_ONES_OFF);
   const uint32_t ones_hi = sw128_desc_hi(0, 0);   // SBO 0: every 8-row group reads the same 1 KB atom of ones
   for (int t = cta + iw * P.cta_count; t < P.ntiles; t += (dual ? 2 : 1) * P.cta_count) {
     const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc) * (ncols >> 1);
-    mbar_wait_warp(bar_accempty + 8 * acc, accph ^ 1);
-    tc_fence_after();
+    if (ISSUE) {
+      mbar_wait_warp(bar_accempty + 8 * acc, accph ^ 1);
+      tc_fence_after();
+    }
     if (leader) trace_ev(tr, trcap, 1, tri, 10, t);
     // accumulator := bias (block 0 of the packed weights), then every tap accumulates
     if (resident) {
-      if (leader) umma_f16(d_tmem, desc64(ones_lo, ones_hi), desc64(w_lo0, b_hi), idesc, 0u);
+      if (ISSUE && leader) mma_g<PAIR>(d_tmem, desc64(ones_lo, ones_hi), desc64(w_lo0, b_hi), idesc, 0u);
     } else {
       mbar_wait_warp(bar_wfull + 8 * (w_first + ws), wph);
+      if (MODE == 1) mbar_wait_warp(bar_pwfull + 8 * (w_first + ws), wph);
+      if (MODE == 2 && lane0) mbar_arrive_remote(r_pwfull + 8 * (w_first + ws));
       tc_fence_after();
-      if (leader) {
-        umma_f16(d_tmem, desc64(ones_lo, ones_hi), desc64(w_lo0 + (w_first + ws) * w_slot16, b_hi), idesc, 0u);
-        umma_commit(bar_wempty + 8 * (w_first + ws));
+      if (ISSUE && leader) {
+        mma_g<PAIR>(d_tmem, desc64(ones_lo, ones_hi), desc64(w_lo0 + (w_first + ws) * w_slot16, b_hi), idesc, 0u);
+        commit_g<PAIR>(bar_wempty + 8 * (w_first + ws));
       }
       if (++ws == w_half) {
         ws = 0;
@@ -213,7 +306,9 @@ __device__ __forceinline__ void mma_role(const HaloProblem& P, const int cta, co
       }
     }
     for (int kc = 0; kc < P.nkc; ++kc) {
-      mbar_wait_warp(bar_afull + 8 * (a_first + as), aph);
+      // (pair mode: the leader's barrier counts BOTH CTAs' tiles -- the peer's TMA signals it directly -- so the shadow
+      // has nothing to wait for or forward here)
+      if (MODE != 2) mbar_wait_warp(bar_afull + 8 * (a_first + as), aph);
       tc_fence_after();
       if (leader) trace_ev(tr, trcap, 1, tri, 11, t);
       const uint32_t a_lo = a_lo0 + (a_first + as) * a_stage16;
@@ -222,12 +317,12 @@ __device__ __forceinline__ void mma_role(const HaloProblem& P, const int cta, co
       const uint32_t acc_kc = 1u;
       if (resident) {
         // one straight-line burst of NTAPS x ksteps MMAs issued by the elected lane
-        if (leader && !(dbg & 8)) {
+        if (ISSUE && leader && !(dbg & 8)) {
           switch (ksteps) {
-            case 4: issue_taps<NTAPS, 4>(d_tmem, a_lo, a_hi, b_lo_kc, b_tap, b_hi, idesc, acc_kc); break;
-            case 3: issue_taps<NTAPS, 3>(d_tmem, a_lo, a_hi, b_lo_kc, b_tap, b_hi, idesc, acc_kc); break;
-            case 2: issue_taps<NTAPS, 2>(d_tmem, a_lo, a_hi, b_lo_kc, b_tap, b_hi, idesc, acc_kc); break;
-            default: issue_taps<NTAPS, 1>(d_tmem, a_lo, a_hi, b_lo_kc, b_tap, b_hi, idesc, acc_kc); break;
+            case 4: issue_taps<NTAPS, 4, PAIR>(d_tmem, a_lo, a_hi, b_lo_kc, b_tap, b_hi, idesc, acc_kc); break;
+            case 3: issue_taps<NTAPS, 3, PAIR>(d_tmem, a_lo, a_hi, b_lo_kc, b_tap, b_hi, idesc, acc_kc); break;
+            case 2: issue_taps<NTAPS, 2, PAIR>(d_tmem, a_lo, a_hi, b_lo_kc, b_tap, b_hi, idesc, acc_kc); break;
+            default: issue_taps<NTAPS, 1, PAIR>(d_tmem, a_lo, a_hi, b_lo_kc, b_tap, b_hi, idesc, acc_kc); break;
           }
         }
       } else {
@@ -237,21 +332,23 @@ __device__ __forceinline__ void mma_role(const HaloProblem& P, const int cta, co
 #pragma unroll
         for (int tg = 0; tg < NTAPS / TG; ++tg) {
           mbar_wait_warp(bar_wfull + 8 * (w_first + ws), wph);
+          if (MODE == 1) mbar_wait_warp(bar_pwfull + 8 * (w_first + ws), wph);
+          if (MODE == 2 && lane0) mbar_arrive_remote(r_pwfull + 8 * (w_first + ws));
           tc_fence_after();
-          if (leader) {
+          if (ISSUE && leader) {
             const uint32_t b_lo = w_lo0 + (w_first + ws) * w_slot16;
 #pragma unroll
             for (int j = 0; j < TG; ++j) {
               const int tap = tg * TG + j;
               const uint32_t a_t = a_lo + (HALO ? static_cast<uint32_t>(((tap / 3) * PW + (tap % 3)) * 8) : 0u);
               switch (ksteps) {
-                case 4: issue_ksteps<4>(d_tmem, a_t, a_hi, b_lo + j * w_stage16, b_hi, idesc, 1u); break;
-                case 3: issue_ksteps<3>(d_tmem, a_t, a_hi, b_lo + j * w_stage16, b_hi, idesc, 1u); break;
-                case 2: issue_ksteps<2>(d_tmem, a_t, a_hi, b_lo + j * w_stage16, b_hi, idesc, 1u); break;
-                default: issue_ksteps<1>(d_tmem, a_t, a_hi, b_lo + j * w_stage16, b_hi, idesc, 1u); break;
+                case 4: issue_ksteps_g<4, PAIR>(d_tmem, a_t, a_hi, b_lo + j * w_stage16, b_hi, idesc, 1u); break;
+                case 3: issue_ksteps_g<3, PAIR>(d_tmem, a_t, a_hi, b_lo + j * w_stage16, b_hi, idesc, 1u); break;
+                case 2: issue_ksteps_g<2, PAIR>(d_tmem, a_t, a_hi, b_lo + j * w_stage16, b_hi, idesc, 1u); break;
+                default: issue_ksteps_g<1, PAIR>(d_tmem, a_t, a_hi, b_lo + j * w_stage16, b_hi, idesc, 1u); break;
               }
             }
-            umma_commit(bar_wempty + 8 * (w_first + ws));
+            commit_g<PAIR>(bar_wempty + 8 * (w_first + ws));
           }
           if (++ws == w_half) {
             ws = 0;
@@ -259,13 +356,13 @@ __device__ __forceinline__ void mma_role(const HaloProblem& P, const int cta, co
           }
         }
       }
-      if (leader) umma_commit(bar_aempty + 8 * (a_first + as));
+      if (ISSUE && leader) commit_g<PAIR>(bar_aempty + 8 * (a_first + as));
       if (++as == a_half) {
         as = 0;
         aph ^= 1;
       }
     }
-    if (leader) umma_commit(bar_accfull + 8 * acc);
+    if (ISSUE && leader) commit_g<PAIR>(bar_accfull + 8 * acc);
     if (leader) trace_ev(tr, trcap, 1, tri, 12, t);
     if (dual) {
       accph ^= 1;
@@ -283,6 +380,16 @@ __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map
       ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(bar)
       : "memory");
 }
+// CTA-pair mode, peer CTA: the box lands in THIS CTA's shared memory, its bytes are counted on the LEADER's mbarrier
+// (`bar_cluster` = shared::cluster address of the leader's barrier), so the leader's issuer waits on one barrier for both
+// activation tiles and no relay through a polling thread is needed.
+__device__ __forceinline__ void tma_load_4d_pair(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, int c3,
+                                                 uint32_t bar_cluster) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2,%3,%4,%5}], [%6];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(bar_cluster)
+      : "memory");
+}
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
 }
@@ -297,7 +404,12 @@ struct EpiArgs {
   int H, W, Cout, lo_off, tiles_x, tiles_per_img, ntiles, cta_count;
   int out_pix_stride, add_pix_stride, plane;
   uint32_t flags;
+  int pair, rank, ntiles_real;   // CTA-pair mode: this CTA's tile of pair-tile t is 2*t + rank (may lie past the end)
 };
+// accumulator hand-back: the leader's accempty barrier, locally or (peer CTA of a pair) through the cluster address
+__device__ __forceinline__ void arrive_accempty(const EpiArgs& E, uint32_t bar_local) {
+  if (E.pair && E.rank != 0) mbar_arrive_remote(mapa_rank(bar_local, 0)); else mbar_arrive(bar_local);
+}
 
 template <int OUT>
 __device__ __forceinline__ void epilogue_role(const EpiArgs E, const int cta, const uint32_t sbase, const uint32_t tmem_base,
@@ -314,14 +426,15 @@ __device__ __forceinline__ void epilogue_role(const EpiArgs E, const int cta, co
   const bool split = (E.flags & I2R_F_SPLIT) != 0;
   int acc = 0, tri = 0;
   uint32_t accph = 0;
-  for (int t = cta; t < E.ntiles; t += E.cta_count) {
+  for (int tp = cta; tp < E.ntiles; tp += E.cta_count) {
+    const int t = E.pair ? 2 * tp + E.rank : tp;
     // tile coordinates without integer division (exact for t < 2^22)
     const int n = __float2int_rd((static_cast<float>(t) + 0.5f) * inv_tpi);
     const int r = t - n * E.tiles_per_img;
     const int ty = __float2int_rd((static_cast<float>(r) + 0.5f) * inv_tx);
     const int tx = r - ty * E.tiles_x;
     const int x = tx * T_TW + tx_in, y = ty * T_TH + ty_in;
-    const bool valid = (x < E.W) && (y < E.H);
+    const bool valid = (x < E.W) && (y < E.H) && (t < E.ntiles_real);
     const int p = (n * E.H + y) * E.W + x;                       // pixel index (< 2^31)
     const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + static_cast<uint32_t>(acc) * (ncols >> 1);
     const __half* a0 = E.add0 + static_cast<int64_t>(p) * E.add_pix_stride;
@@ -447,7 +560,7 @@ __device__ __forceinline__ void epilogue_role(const EpiArgs E, const int cta, co
     if (ew == 0 && lane == 0) trace_ev(tr, trcap, 2, tri, 23, t);
     tc_fence_before();
     __syncwarp();
-    if (lane == 0) mbar_arrive(bar_accempty + 8 * acc);
+    if (lane == 0) arrive_accempty(E, bar_accempty + 8 * acc);
     if (ew == 0 && lane == 0) trace_ev(tr, trcap, 2, tri, 21, t);
     acc ^= 1;
     if (acc == 0) accph ^= 1;
@@ -472,13 +585,14 @@ __device__ __forceinline__ void epilogue_fast(const EpiArgs E, const int cta, co
   const uint32_t lane_taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
   int acc = 0, tri = 0;
   uint32_t accph = 0;
-  for (int t = cta; t < E.ntiles; t += E.cta_count) {
+  for (int tp = cta; tp < E.ntiles; tp += E.cta_count) {
+    const int t = E.pair ? 2 * tp + E.rank : tp;
     const int n = __float2int_rd((static_cast<float>(t) + 0.5f) * inv_tpi);
     const int r = t - n * E.tiles_per_img;
     const int ty = __float2int_rd((static_cast<float>(r) + 0.5f) * inv_tx);
     const int tx = r - ty * E.tiles_x;
     const int x = tx * T_TW + tx_in, y = ty * T_TH + ty_in;
-    const bool valid = (x < E.W) && (y < E.H);
+    const bool valid = (x < E.W) && (y < E.H) && (t < E.ntiles_real);
     const int p = (n * E.H + y) * E.W + x;
     const uint32_t taddr = lane_taddr + static_cast<uint32_t>(acc) * (ncols >> 1);
     const __half* a0 = E.add0 + static_cast<int64_t>(p) * E.add_pix_stride;
@@ -528,7 +642,7 @@ __device__ __forceinline__ void epilogue_fast(const EpiArgs E, const int cta, co
     if (ew == 0 && lane == 0) trace_ev(tr, trcap, 2, tri, 23, t);
     tc_fence_before();
     __syncwarp();
-    if (lane == 0) mbar_arrive(bar_accempty + 8 * acc);
+    if (lane == 0) arrive_accempty(E, bar_accempty + 8 * acc);
     if (ew == 0 && lane == 0) trace_ev(tr, trcap, 2, tri, 21, t);
     acc ^= 1;
     if (acc == 0) accph ^= 1;
@@ -552,22 +666,35 @@ __device__ __forceinline__ void epilogue_fast_dispatch(const EpiArgs& E, const i
   }
 }
 
+// CL = the launch is made of 2-CTA clusters and may hold CTA-pair problems.  A kernel image that contains cta_group::2
+// instructions can only be launched with an even cluster size (the driver rejects it otherwise: "cluster
+// misconfiguration"), so launches without pair problems use the CL = false instantiation, which has none.
+template <bool CL>
 __global__ void __launch_bounds__(T_THREADS, 1) conv_halo_kernel(const __grid_constant__ HaloGroup G) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // SW128 tiles need 1024-B alignment
+  if (static_cast<int>(blockIdx.x) >= G.total_ctas) return;   // filler CTA that makes the grid a whole number of clusters
   int pi = 0;
   while (pi < G.nprob - 1 && static_cast<int>(blockIdx.x) >= G.p[pi].cta_begin + G.p[pi].cta_count) ++pi;
   HaloProblem P = load_problem(G.p[pi]);
-  const int cta = blockIdx.x - P.cta_begin;
+  int cta = blockIdx.x - P.cta_begin;
   P.w += static_cast<size_t>(cta % P.w_copies) * P.w_total_bytes;
+  // CTA-pair problems: CTA `rank` of pair `cta >> 1`; every role below loops over tile PAIRS with the pair index
+  const bool pair = CL && P.pair != 0;
+  const int rank = pair ? static_cast<int>(cluster_ctarank()) : 0;
+  if (pair) {
+    cta >>= 1;
+    P.cta_count >>= 1;
+  }
   const int dbg = opaque(G.dbg);
   const int trace_cap = opaque(G.trace_cap);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   pdl_launch_dependents();   // the next grid may start its prologue as soon as SMs free up (see i2r_common.cuh)
 
   const uint32_t sbase = smem_u32(smem);
-  const uint32_t bar_afull = sbase, bar_aempty = sbase + 32, bar_wfull = sbase + 256, bar_wempty = sbase + 320;
-  const uint32_t bar_accfull = sbase + 128, bar_accempty = sbase + 144, bar_wres = sbase + 160;
+  const uint32_t bar_afull = sbase + B_AFULL, bar_aempty = sbase + B_AEMPTY, bar_wfull = sbase + B_WFULL,
+                 bar_wempty = sbase + B_WEMPTY;
+  const uint32_t bar_accfull = sbase + B_ACCFULL, bar_accempty = sbase + B_ACCEMPTY, bar_wres = sbase + B_WRES;
   if (G.trace != nullptr && static_cast<int>(blockIdx.x) == G.trace_cta && tid == 96) {
     int i0 = 0;
     trace_ev(G.trace, trace_cap, 3, i0, 30, 0);
@@ -584,24 +711,36 @@ __global__ void __launch_bounds__(T_THREADS, 1) conv_halo_kernel(const __grid_co
     for (int i = 0; i < 4; ++i) {
       mbar_init(bar_afull + 8 * i, 1);
       mbar_init(bar_aempty + 8 * i, 1);
+      mbar_init(sbase + B_PFULL + 8 * i, 1);
     }
     for (int i = 0; i < T_W_STAGES_MAX; ++i) {
       mbar_init(bar_wfull + 8 * i, 1);
       mbar_init(bar_wempty + 8 * i, 1);
+      mbar_init(sbase + B_PWFULL + 8 * i, 1);
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(bar_accfull + 8 * i, 1);
-      mbar_init(bar_accempty + 8 * i, 8);
+      mbar_init(bar_accempty + 8 * i, pair ? 16 : 8);   // pair: the epilogue warps of BOTH CTAs hand the accumulator back
     }
     mbar_init(bar_wres, 1);
+    mbar_init(sbase + B_PWRES, 1);
     fence_mbar_init();
-  }
-  if (warp == 2) {
-    tmem_alloc(smem_u32(tmem_slot), ncols);
-    tmem_relinquish();
   }
   if (tid < 256) reinterpret_cast<uint32_t*>(smem + T_ONES_OFF)[tid] = 0x3c003c00u;   // fp16 (1.0, 1.0)
   fence_proxy_async();   // the ones tile is read by the tensor core (async proxy)
+  if (CL && pair) {
+    // the peer's barriers must exist before a multicast commit / remote arrive can land on them, and both CTAs take
+    // part in the cta_group::2 allocation
+    __syncthreads();
+    cluster_sync_all();
+    if (warp == 2) {
+      tmem_alloc2(smem_u32(tmem_slot), ncols);
+      tmem_relinquish2();
+    }
+  } else if (warp == 2) {
+    tmem_alloc(smem_u32(tmem_slot), ncols);
+    tmem_relinquish();
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -617,9 +756,13 @@ __global__ void __launch_bounds__(T_THREADS, 1) conv_halo_kernel(const __grid_co
       pdl_wait();   // activations come from the previous kernels (weights do not: warp 1 loads them right away)
       const int dual = P.w_resident;   // two MMA issuers, each with its own half-ring (see mma_role)
       const int a_half = dual ? P.a_stages >> 1 : P.a_stages;
+      const uint32_t leader_afull = (CL && pair) ? mapa_rank(bar_afull, 0) : 0u;
       int sr[2] = {0, 0}, tri = 0, ring = 0;
       uint32_t phr[2] = {0, 0};
-      for (int t = cta; t < P.ntiles; t += P.cta_count, ring ^= dual) {
+      for (int tp = cta; tp < P.ntiles; tp += P.cta_count, ring ^= dual) {
+        // pair mode: this CTA's 128-pixel tile of pair-tile tp; a tile past the end (odd tile count) reads image
+        // index NB, i.e. an all-out-of-bounds box the TMA unit fills with zeros
+        const int t = pair ? min(2 * tp + rank, P.ntiles_real) : tp;
         const int n = t / P.tiles_per_img;
         const int r = t - n * P.tiles_per_img;
         const int ty = r / P.tiles_x, tx = r - ty * P.tiles_x;
@@ -628,14 +771,19 @@ __global__ void __launch_bounds__(T_THREADS, 1) conv_halo_kernel(const __grid_co
           const int s = ring * a_half + sr[ring];
           mbar_wait_relaxed(bar_aempty + 8 * s, phr[ring] ^ 1);
           trace_ev(tr, trace_cap, 0, tri, 1, t);
-          if ((dbg & 4) && t >= cta + P.a_stages * P.cta_count) {
+          if ((dbg & 4) && tp >= cta + P.a_stages * P.cta_count) {
             mbar_arrive(bar_afull + 8 * s);
           } else {
-            mbar_arrive_expect_tx(bar_afull + 8 * s, P.a_tx_bytes);
             // split-operand mode walks [x_hi | x_lo | x_hi]: hi at channel 0, lo at channel C of the source pixel
             const int third = kc / P.nkr, kr = kc - third * P.nkr;
-            tma_load_4d(a_base + s * P.a_stage_bytes, amap, (third == 1 ? P.C : 0) + kr * 64, x0, y0, n,
-                        bar_afull + 8 * s);
+            const int c0 = (third == 1 ? P.C : 0) + kr * 64;
+            if (CL && pair && rank != 0) {
+              // the peer's tile is accounted on the leader's barrier (which expects both tiles' bytes)
+              tma_load_4d_pair(a_base + s * P.a_stage_bytes, amap, c0, x0, y0, n, leader_afull + 8 * s);
+            } else {
+              mbar_arrive_expect_tx(bar_afull + 8 * s, pair ? 2 * P.a_tx_bytes : P.a_tx_bytes);
+              tma_load_4d(a_base + s * P.a_stage_bytes, amap, c0, x0, y0, n, bar_afull + 8 * s);
+            }
           }
           trace_ev(tr, trace_cap, 0, tri, 2, t);
           if (++sr[ring] == a_half) {
@@ -648,11 +796,21 @@ __global__ void __launch_bounds__(T_THREADS, 1) conv_halo_kernel(const __grid_co
   } else if (warp == 1) {
     if (lane == 0) {
       // ================================================= weight producer (1-D bulk copies on the TMA unit)
+      // pair mode: this CTA holds rows [rank * Npad/2, (rank+1) * Npad/2) of every (tap, K-chunk) block of the image
+      const uint32_t w_goff = pair ? static_cast<uint32_t>(rank) * P.w_stage_bytes : 0u;
+      const int nblocks = P.ntaps * P.nkc + 1;
       if (P.w_resident) {
-        mbar_arrive_expect_tx(bar_wres, P.w_total_bytes);
-        for (uint32_t off = 0; off < P.w_total_bytes; off += 16384) {
-          const uint32_t sz = min(16384u, P.w_total_bytes - off);
-          bulk_g2s(w_base + off, P.w + off, sz, bar_wres);
+        if (pair) {
+          mbar_arrive_expect_tx(bar_wres, static_cast<uint32_t>(nblocks) * P.w_stage_bytes);
+          for (int b = 0; b < nblocks; ++b)
+            bulk_g2s(w_base + b * P.w_stage_bytes, P.w + static_cast<size_t>(b) * P.w_gstage + w_goff, P.w_stage_bytes,
+                     bar_wres);
+        } else {
+          mbar_arrive_expect_tx(bar_wres, P.w_total_bytes);
+          for (uint32_t off = 0; off < P.w_total_bytes; off += 16384) {
+            const uint32_t sz = min(16384u, P.w_total_bytes - off);
+            bulk_g2s(w_base + off, P.w + off, sz, bar_wres);
+          }
         }
       } else {
         const int w_half = P.w_stages;   // streamed weights: single issuer, one ring
@@ -668,13 +826,13 @@ __global__ void __launch_bounds__(T_THREADS, 1) conv_halo_kernel(const __grid_co
             const uint32_t dst = w_base + s * P.w_slot_bytes;
             if (b == 0) {
               mbar_arrive_expect_tx(bar_wfull + 8 * s, P.w_stage_bytes);
-              bulk_g2s(dst, P.w, P.w_stage_bytes, bar_wfull + 8 * s);
+              bulk_g2s(dst, P.w + w_goff, P.w_stage_bytes, bar_wfull + 8 * s);
             } else {
               const int kc = (b - 1) / (P.ntaps / tgs), tg = (b - 1) - kc * (P.ntaps / tgs);
               mbar_arrive_expect_tx(bar_wfull + 8 * s, P.w_stage_bytes * tgs);
               for (int j = 0; j < tgs; ++j) {
                 const int blk = 1 + (tg * tgs + j) * P.nchp + kc;
-                bulk_g2s(dst + j * P.w_stage_bytes, P.w + static_cast<size_t>(blk) * P.w_stage_bytes, P.w_stage_bytes,
+                bulk_g2s(dst + j * P.w_stage_bytes, P.w + static_cast<size_t>(blk) * P.w_gstage + w_goff, P.w_stage_bytes,
                          bar_wfull + 8 * s);
               }
             }
@@ -688,10 +846,17 @@ __global__ void __launch_bounds__(T_THREADS, 1) conv_halo_kernel(const __grid_co
     }
   } else if (warp == 2 || warp == 3) {
     // ================================================= MMA issuers (whole warp runs the loop, one lane issues)
-    if (P.ntaps == 9) {
-      mma_role<9>(P, cta, sbase, tmem_base, ncols, warp == 2 ? tr : nullptr, trace_cap, dbg, warp - 2);
-    } else {
-      mma_role<1>(P, cta, sbase, tmem_base, ncols, warp == 2 ? tr : nullptr, trace_cap, dbg, warp - 2);
+    unsigned long long* trm = warp == 2 ? tr : nullptr;
+    const int iw = warp - 2;
+    if (!pair) {
+      if (P.ntaps == 9) mma_role<9, 0>(P, cta, sbase, tmem_base, ncols, trm, trace_cap, dbg, iw);
+      else mma_role<1, 0>(P, cta, sbase, tmem_base, ncols, trm, trace_cap, dbg, iw);
+    } else if (CL && rank == 0) {      // leader of the pair: issues the M256 MMAs for both CTAs
+      if (P.ntaps == 9) mma_role<9, CL ? 1 : 0>(P, cta, sbase, tmem_base, ncols, trm, trace_cap, dbg, iw);
+      else mma_role<1, CL ? 1 : 0>(P, cta, sbase, tmem_base, ncols, trm, trace_cap, dbg, iw);
+    } else if (CL) {                   // peer: forwards its operand-landed events to the leader
+      if (P.ntaps == 9) mma_role<9, CL ? 2 : 0>(P, cta, sbase, tmem_base, ncols, trm, trace_cap, dbg, iw);
+      else mma_role<1, CL ? 2 : 0>(P, cta, sbase, tmem_base, ncols, trm, trace_cap, dbg, iw);
     }
   } else {
     // ================================================= epilogue: 8 warps, two per TMEM lane quadrant, each
@@ -702,6 +867,7 @@ __global__ void __launch_bounds__(T_THREADS, 1) conv_halo_kernel(const __grid_co
     E.H = P.H; E.W = P.W; E.Cout = P.Cout; E.lo_off = P.lo_off; E.tiles_x = P.tiles_x; E.tiles_per_img = P.tiles_per_img;
     E.ntiles = P.ntiles; E.cta_count = P.cta_count;
     E.out_pix_stride = P.out_pix_stride; E.add_pix_stride = P.add_pix_stride; E.plane = P.plane; E.flags = P.flags;
+    E.pair = pair ? 1 : 0; E.rank = rank; E.ntiles_real = P.ntiles_real;
     const int ew = warp - 4;
     const int n8 = (P.Cout + 7) >> 3, half8 = (n8 + 1) >> 1;   // chunks holding real channels, split over the warp pair
     const int cb = (ew >> 2) ? half8 : 0, ce = (ew >> 2) ? n8 : half8;
@@ -724,7 +890,12 @@ __global__ void __launch_bounds__(T_THREADS, 1) conv_halo_kernel(const __grid_co
     int i1 = 1;
     trace_ev(tr, trace_cap, 3, i1, 31, 0);
   }
-  if (warp == 2) tmem_dealloc(tmem_base, ncols);
+  if (CL && pair) {
+    cluster_sync_all();   // no CTA of the pair may exit (or free its TMEM) while the other can still signal it
+    if (warp == 2) tmem_dealloc2(tmem_base, ncols);
+  } else if (warp == 2) {
+    tmem_dealloc(tmem_base, ncols);
+  }
 }
 
 // ------------------------------------------------------------------------------------------------ host
@@ -816,20 +987,49 @@ extern "C" int i2r_conv_halo(const i2r_conv_problem* probs, int nprob, void* str
   G.trace_cta = g_trace_cta;
   G.trace_cap = g_trace_cap;
   G.dbg = g_dbg;
-  double cost[I2R_MAX_GROUP];
-  int total_tiles = 0;
-  uint32_t smem_need = 0;
+  // CTA-pair mode (I2R_HALO_PAIR: 0 = never [default], 1 = where the single-CTA weight image does not fit shared memory,
+  // 2 = wherever the shape allows: tests).  Measured on C2 / C3 (profiles/r02_pair_mode.txt): correct everywhere, and the
+  // tensor work per output does drop (96-channel layers: one N=96 pair tile instead of two N=48 halves re-reading the
+  // activations; 192-channel layers: half the streamed bytes per CTA), but these layers are bound by the EPILOGUE warps
+  // (128 x 96 outputs per CTA per tile: 4.9 k cycles against 3.2 k of MMA), so whole-model throughput is unchanged on C2
+  // and 4 % lower on C3 (clusters start later); it stays an option until the epilogue gets more warps.
+  // Pair problems go first so that their CTA ranges start on even block indices (a pair = one cluster of two CTAs).
+  static const int pair_policy = []() {
+    const char* e = getenv("I2R_HALO_PAIR");
+    return e ? atoi(e) : 0;
+  }();
+  int order[I2R_MAX_GROUP], npair = 0;
+  bool want_pair[I2R_MAX_GROUP];
   for (int i = 0; i < nprob; ++i) {
     const i2r_conv_problem& S = probs[i];
     if (!i2r_conv_halo_supported(&S)) {
       set_error("i2r_conv_halo: problem %d is not a stride-1 3x3 / 1x1 problem this kernel supports", i);
       return I2R_E_UNSUPPORTED;
     }
+    const int nkc = ((S.Cin + 63) / 64) * ((S.flags & I2R_F_SPLIT) ? 3 : 1);
+    const uint32_t image = static_cast<uint32_t>(S.ntaps * nkc + 1) * S.Npad * 128;
+    const int64_t m = static_cast<int64_t>(S.NB) * S.IH * S.IW;
+    want_pair[i] = pair_policy != 0 && S.Npad % 16 == 0 && S.Npad >= 32 && m > 128 &&
+                   (pair_policy == 2 || image > T_W_RES_MAX);
+  }
+  for (int i = 0; i < nprob; ++i)
+    if (want_pair[i]) order[npair++] = i;
+  {
+    int k = npair;
+    for (int i = 0; i < nprob; ++i)
+      if (!want_pair[i]) order[k++] = i;
+  }
+  double cost[I2R_MAX_GROUP], startup[I2R_MAX_GROUP];
+  int total_ctas_min = 0;
+  uint32_t smem_need = 0;
+  for (int i = 0; i < nprob; ++i) {
+    const i2r_conv_problem& S = probs[order[i]];
     if (!S.x || !S.w_folded || !S.y) {
-      set_error("i2r_conv_halo: problem %d: null pointer", i);
+      set_error("i2r_conv_halo: problem %d: null pointer", order[i]);
       return I2R_E_BADARG;
     }
     HaloProblem& P = G.p[i];
+    P.pair = i < npair ? 1 : 0;
     P.x = static_cast<const __half*>(S.x);
     P.w = static_cast<const uint8_t*>(S.w_folded);
     P.w_copies = S.w_folded_copies > 1 ? S.w_folded_copies : 1;
@@ -860,7 +1060,8 @@ extern "C" int i2r_conv_halo(const i2r_conv_problem* probs, int nprob, void* str
     P.nchp = P.nkc;
     P.tiles_x = (P.W + T_TW - 1) / T_TW;
     P.tiles_per_img = P.tiles_x * ((P.H + T_TH - 1) / T_TH);
-    P.ntiles = P.tiles_per_img * P.NB;
+    P.ntiles_real = P.tiles_per_img * P.NB;
+    P.ntiles = P.pair ? (P.ntiles_real + 1) / 2 : P.ntiles_real;      // loop bound: tile pairs in pair mode
     P.in_pix_stride = S.in_pix_stride;
     P.out_pix_stride = S.out_pix_stride;
     P.add_pix_stride = S.add_pix_stride;
@@ -868,9 +1069,11 @@ extern "C" int i2r_conv_halo(const i2r_conv_problem* probs, int nprob, void* str
     const int hw = T_TW + 2 * P.halo, hh = T_TH + 2 * P.halo;
     P.a_tx_bytes = static_cast<uint32_t>(hh * hw * 128);          // full box, zero-filled parts included
     P.a_stage_bytes = (P.a_tx_bytes + 1023u) & ~1023u;            // stages stay 1024-byte aligned (SW128)
-    P.w_total_bytes = static_cast<uint32_t>(S.ntaps * P.nkc + 1) * S.Npad * 128;   // bias block + taps
-    P.w_resident = P.w_total_bytes <= T_W_RES_MAX ? 1 : 0;
-    P.w_stage_bytes = static_cast<uint32_t>(S.Npad) * 128;
+    P.w_total_bytes = static_cast<uint32_t>(S.ntaps * P.nkc + 1) * S.Npad * 128;   // bias block + taps (global image)
+    P.w_gstage = static_cast<uint32_t>(S.Npad) * 128;
+    P.w_stage_bytes = P.pair ? P.w_gstage / 2 : P.w_gstage;      // pair mode: every CTA holds half of the rows
+    const uint32_t w_cta_bytes = static_cast<uint32_t>(S.ntaps * P.nkc + 1) * P.w_stage_bytes;
+    P.w_resident = w_cta_bytes <= T_W_RES_MAX ? 1 : 0;
     P.w_slot_bytes = P.w_stage_bytes * (S.ntaps == 9 ? 3 : 1);
     uint32_t wregion;
     // streamed weights: the ring must cover the L2 round trip (~1300 cycles) at the rate the issuer drains it, so it
@@ -878,7 +1081,7 @@ extern "C" int i2r_conv_halo(const i2r_conv_problem* probs, int nprob, void* str
     int astg;
     if (P.w_resident) {
       P.w_stages = 1;
-      wregion = P.w_total_bytes;
+      wregion = w_cta_bytes;
       astg = static_cast<int>((T_MAX_SMEM - T_A_OFF - wregion) / P.a_stage_bytes);
       if (astg > 4) astg = 4;
       astg &= ~1;   // two half-rings, one per MMA issuer
@@ -890,7 +1093,7 @@ extern "C" int i2r_conv_halo(const i2r_conv_problem* probs, int nprob, void* str
       wregion = P.w_stages * P.w_slot_bytes;
     }
     if (astg < 2 || P.w_stages < 1 || (!P.w_resident && P.w_stages < 2)) {
-      set_error("i2r_conv_halo: problem %d does not fit shared memory (A stage %u B, W region %u B)", i,
+      set_error("i2r_conv_halo: problem %d does not fit shared memory (A stage %u B, W region %u B)", order[i],
                 P.a_stage_bytes, wregion);
       return I2R_E_UNSUPPORTED;
     }
@@ -903,41 +1106,77 @@ extern "C" int i2r_conv_halo(const i2r_conv_problem* probs, int nprob, void* str
     const uint32_t need = P.w_off + wregion;
     if (need > smem_need) smem_need = need;
     {
-      // per-tile cost in SM cycles, from the measured models: one M128 x N x K16 MMA with shared-memory
-      // operands takes max(32 + N/4, N/2) cycles; streamed weights arrive at ~45 B/cycle/SM; the epilogue warps need
-      // ~600 + 10 cycles per output channel.
+      // Cost model for the CTA allocation, in SM cycles (calibrated on per-CTA traces, profiles/r02_halo_cta_*):
+      //   unit  = one tile (pair mode: one tile pair, which keeps two SMs busy)
+      //   MMA   : M128 x N x K16 from shared memory max(32 + N/4, N/2); pair M256 max(44 + 0.15 N, 0.545 N)
+      //           (tools/mma_probe.cu, tools/mma2_probe.cu)
+      //   stream: streamed weights arrive at ~31 B/cycle/SM
+      //   epi   : the 8 epilogue warps are issue bound: ~900 + 20 cycles per output channel (+250 with a residual)
+      //   start : fixed cost before the first tile completes (barriers, TMEM, resident weights at ~35 B/cycle, pipeline
+      //           fill); clusters start later (both SMs of a TPC must be free)
       const double n = S.Npad;
-      const double mma = static_cast<double>(S.ntaps) * (S.Cin / 16) * (P.split ? 3 : 1) * ((32.0 + n / 4) > n / 2 ? (32.0 + n / 4) : n / 2) + 400.0;
-      const double stream = P.w_resident ? 0.0 : P.w_total_bytes / 45.0;
-      const double epi = 600.0 + 10.0 * n;
+      const double one = (32.0 + n / 4) > n / 2 ? (32.0 + n / 4) : n / 2;
+      const double two = (44.0 + 0.15 * n) > 0.545 * n ? (44.0 + 0.15 * n) : 0.545 * n;
+      const double mma = static_cast<double>(S.ntaps) * (S.Cin / 16) * (P.split ? 3 : 1) * (P.pair ? two : one) + 500.0;
+      const double stream = P.w_resident ? 0.0 : w_cta_bytes / 31.0;
+      const double epi = 900.0 + 20.0 * n * ((S.flags & I2R_F_SPLIT) ? 1.6 : 1.0) + ((S.add0 || S.add1) ? 250.0 : 0.0);
       cost[i] = mma > stream ? mma : stream;
       if (epi > cost[i]) cost[i] = epi;
+      startup[i] = 2500.0 + (P.w_resident ? w_cta_bytes / 35.0 : 1500.0) + (P.pair ? 3000.0 : 0.0);
     }
-    total_tiles += P.ntiles;
+    total_ctas_min += P.pair ? 2 * P.ntiles : P.ntiles;
   }
-  // CTA ranges: one CTA per tile while they fit; otherwise hand the SMs out greedily to whichever problem
-  // currently has the longest makespan ceil(tiles / CTAs) * tile_cost (tile_cost from the measured
-  // operand-fetch-bound MMA rate: ~ (4096 + 32 * Npad) bytes of shared-memory operands per K=16 step).
+  // CTA ranges: one worker (a CTA, or a CTA pair) per work unit while they fit; otherwise the allocation that minimises
+  // the makespan max_i (start_i + ceil(units_i / workers_i) * cost_i) subject to sum_i workers_i * ctas_per_worker_i <= SMs.
+  // The candidates for the optimum are start_i + k * cost_i; for a target T problem i needs
+  // ceil(units_i / floor((T - start_i) / cost_i)) workers.  (A greedy hand-out stalls on the plateaus of ceil(): it
+  // once gave 45 CTAs to 128 tiles -- 3 tiles each, exactly what 43 CTAs achieve -- while another problem starved.)
   int begin = 0;
-  if (total_tiles <= num_sms) {
-    for (int i = 0; i < nprob; ++i) {
-      G.p[i].cta_begin = begin;
-      G.p[i].cta_count = G.p[i].ntiles;
-      begin += G.p[i].ntiles;
-    }
+  int cnt[I2R_MAX_GROUP];      // workers per problem
+  if (total_ctas_min <= num_sms) {
+    for (int i = 0; i < nprob; ++i) cnt[i] = G.p[i].ntiles;
   } else {
-    int cnt[I2R_MAX_GROUP];
-    int left = num_sms;
-    for (int i = 0; i < nprob; ++i) {
-      cnt[i] = 1;
-      --left;
+    double best_t = 1e30;
+    int best_cnt[I2R_MAX_GROUP];
+    for (int i = 0; i < nprob; ++i) best_cnt[i] = 1;
+    for (int ci = 0; ci < nprob; ++ci) {
+      const int kmax = G.p[ci].ntiles < 4096 ? G.p[ci].ntiles : 4096;
+      for (int k = 1; k <= kmax; ++k) {
+        const double t = startup[ci] + k * cost[ci];
+        if (t >= best_t) break;
+        int used = 0;
+        int c[I2R_MAX_GROUP];
+        bool ok = true;
+        for (int i = 0; i < nprob && ok; ++i) {
+          const int per = static_cast<int>((t - startup[i]) / cost[i] + 1e-9);
+          if (per < 1) {
+            ok = false;
+            break;
+          }
+          c[i] = (G.p[i].ntiles + per - 1) / per;
+          used += c[i] * (G.p[i].pair ? 2 : 1);
+        }
+        if (ok && used <= num_sms) {
+          best_t = t;
+          for (int i = 0; i < nprob; ++i) best_cnt[i] = c[i];
+          break;      // larger k only raises t for this problem
+        }
+      }
     }
+    int used = 0;
+    for (int i = 0; i < nprob; ++i) {
+      cnt[i] = best_cnt[i];
+      used += cnt[i] * (G.p[i].pair ? 2 : 1);
+    }
+    // left-over SMs: to whoever has the highest average load per worker (they cannot lower the makespan bound, but they
+    // shorten the tail of the real, noisier execution)
+    int left = num_sms - used;
     while (left > 0) {
       int best = -1;
       double bestv = -1;
       for (int i = 0; i < nprob; ++i) {
-        if (cnt[i] >= G.p[i].ntiles) continue;
-        const double v = static_cast<double>((G.p[i].ntiles + cnt[i] - 1) / cnt[i]) * cost[i];
+        if (cnt[i] >= G.p[i].ntiles || (G.p[i].pair && left < 2)) continue;
+        const double v = startup[i] + static_cast<double>(G.p[i].ntiles) / cnt[i] * cost[i];
         if (v > bestv) {
           bestv = v;
           best = i;
@@ -945,25 +1184,49 @@ extern "C" int i2r_conv_halo(const i2r_conv_problem* probs, int nprob, void* str
       }
       if (best < 0) break;
       ++cnt[best];
-      --left;
-    }
-    for (int i = 0; i < nprob; ++i) {
-      G.p[i].cta_begin = begin;
-      G.p[i].cta_count = cnt[i];
-      begin += cnt[i];
+      left -= G.p[best].pair ? 2 : 1;
     }
   }
+  for (int i = 0; i < nprob; ++i) {
+    G.p[i].cta_begin = begin;
+    G.p[i].cta_count = cnt[i] * (G.p[i].pair ? 2 : 1);
+    begin += G.p[i].cta_count;
+  }
+  G.total_ctas = begin;
   static bool attr_done_dev[MAX_DEVICES] = {};   // the opt-in is a per-device property
   bool& attr_done = attr_done_dev[current_device()];
   if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(conv_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, T_MAX_SMEM + 1024);
+    cudaError_t e = cudaFuncSetAttribute(conv_halo_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         T_MAX_SMEM + 1024);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(conv_halo_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, T_MAX_SMEM + 1024);
     if (e != cudaSuccess) {
       set_error("cudaFuncSetAttribute(conv_halo): %s", cudaGetErrorString(e));
       return static_cast<int>(e);
     }
     attr_done = true;
   }
-  launch_pdl(conv_halo_kernel, dim3(begin), dim3(T_THREADS), smem_need + 1024, static_cast<cudaStream_t>(stream), G);
+  if (npair == 0) {
+    launch_pdl(conv_halo_kernel<false>, dim3(begin), dim3(T_THREADS), smem_need + 1024, static_cast<cudaStream_t>(stream),
+               G);
+  } else {
+    // clusters of two consecutive CTAs (the grid is padded to a whole number of clusters; a filler CTA exits at once)
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((begin + 1) & ~1);
+    cfg.blockDim = dim3(T_THREADS);
+    cfg.dynamicSmemBytes = smem_need + 1024;
+    cfg.stream = static_cast<cudaStream_t>(stream);
+    cudaLaunchAttribute attr[2];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+    attr[1].id = cudaLaunchAttributeClusterDimension;
+    attr[1].val.clusterDim.x = 2;
+    attr[1].val.clusterDim.y = 1;
+    attr[1].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 2;
+    cudaLaunchKernelEx(&cfg, conv_halo_kernel<true>, G);
+  }
   return check_launch("conv_halo_kernel");
 }
 

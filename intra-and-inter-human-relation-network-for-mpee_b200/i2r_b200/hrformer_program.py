@@ -120,33 +120,36 @@ class _Module:
                                          for s in range(i - j)]
 
     def run(self, r, xs):
-        ys = []
-        for b in range(self.nb):
-            y = xs[b]
-            for blk in self.blocks[b]:
-                y = blk.run(r, y)
-            ys.append(y)
-        out = []
-        for i in range(self.nout):
-            acc = ys[i]
-            ups = [j for j in range(self.nb) if j > i]
-            downs = [j for j in range(self.nb) if j < i]
-            for n, j in enumerate(downs):
-                t = ys[j]
-                chain = self.down[(i, j)]
-                for s, step in enumerate(chain):
-                    t = r.dwconv3x3(t, step.dw[0], step.dw[1], step.dw[2], 2, None)
-                    if s == len(chain) - 1:      # the last 1x1 of the chain accumulates onto the running sum
-                        final = not ups and n == len(downs) - 1
-                        t = r.conv(step.pw, t, add0=acc, relu=final)
-                    else:
-                        t = r.conv(step.pw, t)
-                acc = t
-            if ups:
-                terms = [(r.conv(self.up[(i, j)], ys[j]), j - i) for j in ups]
-                acc = r.upsum_bilinear(acc, terms, relu=True)
-            out.append(acc)
-        return out
+        def chain(b):
+            def go():
+                y = xs[b]
+                for blk in self.blocks[b]:
+                    y = blk.run(r, y)
+                return y
+            return go
+        ys = r.parallel([chain(b) for b in range(self.nb)])      # the branches are independent until the fuse layers
+        def fuse(i):
+            def go():
+                acc = ys[i]
+                ups = [j for j in range(self.nb) if j > i]
+                downs = [j for j in range(self.nb) if j < i]
+                for n, j in enumerate(downs):
+                    t = ys[j]
+                    chain = self.down[(i, j)]
+                    for s, step in enumerate(chain):
+                        t = r.dwconv3x3(t, step.dw[0], step.dw[1], step.dw[2], 2, None)
+                        if s == len(chain) - 1:      # the last 1x1 of the chain accumulates onto the running sum
+                            final = not ups and n == len(downs) - 1
+                            t = r.conv(step.pw, t, add0=acc, relu=final)
+                        else:
+                            t = r.conv(step.pw, t)
+                    acc = t
+                if ups:
+                    terms = [(r.conv(self.up[(i, j)], ys[j]), j - i) for j in ups]
+                    acc = r.upsum_bilinear(acc, terms, relu=True)
+                return acc
+            return go
+        return r.parallel([fuse(i) for i in range(self.nout)])      # one independent chain per output branch
 
 
 class HRTProgram:

@@ -162,6 +162,38 @@ class Runner:
         self.split = False     # split-operand activations (fp16 hi | lo pairs) for the non-GEMM kernels
         self._stem_images = {}  # packed operand images of the tensor-core stem kernel, keyed by the weight tensors
         self.timing = None     # bench.py: list of (start_event, end_event, algorithmic_flops, nprob) per igemm launch
+        self._side_streams = []
+        self.concurrent_branches = __import__("os").environ.get("I2R_CONCURRENT_BRANCHES", "1") != "0"
+
+    # ------------------------------------------------------------------ independent launch chains
+    def parallel(self, chains):
+        """Run independent launch chains (callables) concurrently: chain 0 on the current stream, the others on side
+        streams forked from it and joined back (fork / join by events, so the pattern is capturable into a CUDA graph as
+        parallel branches).  Every chain starts after all work queued so far and everything queued afterwards waits for
+        all chains, which also keeps the caching allocator's per-stream block reuse safe.  Returns the chains' results.
+        The resolution branches of an HRFormer module are such chains: at one image per rank their kernels fill a
+        fraction of the SMs each (lib/models/hrformer.py:1714-1731 runs them one after the other)."""
+        if len(chains) == 1 or self.device.type != "cuda" or not self.concurrent_branches:
+            return [c() for c in chains]
+        main = torch.cuda.current_stream(self.device)
+        while len(self._side_streams) < len(chains) - 1:
+            self._side_streams.append(torch.cuda.Stream(device=self.device))
+        fork = torch.cuda.Event()
+        fork.record(main)
+        out = [None] * len(chains)
+        joins = []
+        for i in range(1, len(chains)):
+            st = self._side_streams[i - 1]
+            st.wait_event(fork)
+            with torch.cuda.stream(st):
+                out[i] = chains[i]()
+                ev = torch.cuda.Event()
+                ev.record(st)
+                joins.append(ev)
+        out[0] = chains[0]()
+        for ev in joins:
+            main.wait_event(ev)
+        return out
 
     # ------------------------------------------------------------------ implicit GEMM
     def problem(self, L, x, out=None, add0=None, add0_shift=0, add1=None, add1_shift=0, in_shift=0,
@@ -252,6 +284,10 @@ class Runner:
         return p, out
 
     TMA_WEIGHT_RESIDENT_MAX = 120 * 1024
+    # N-split of layers whose weight image exceeds shared memory into two half-width problems (default).  With
+    # I2R_HALO_PAIR=1/2 such layers run as ONE problem on CTA pairs instead (tcgen05 cta_group::2: each CTA of a pair holds
+    # half of the weight rows, nobody re-reads the activations; csrc/conv_halo.cu explains why that is not the default).
+    N_SPLIT = __import__("os").environ.get("I2R_HALO_PAIR", "0") == "0"
 
     def problems(self, L, x, **kw):
         """Like problem(), but may split the output channels in two (see ConvLayer.halves).  Returns (list, out)."""
@@ -261,7 +297,7 @@ class Runner:
                  kw.get("out_mul", 1) == 1 and kw.get("out_mode", "nhwc16") == "nhwc16" and
                  kw.get("add0_shift", 0) == 0 and kw.get("add1_shift", 0) == 0 and
                  L.weight_bytes > self.TMA_WEIGHT_RESIDENT_MAX and L.cout == L.npad and L.cout % 32 == 0 and
-                 not L.split)
+                 not L.split and self.N_SPLIT)
         if L.npad > 256:
             # more output channels than accumulator columns: column chunks writing channel slices of one tensor
             assert kw.get("out_mode", "nhwc16") == "nhwc16" and L.cout == L.npad

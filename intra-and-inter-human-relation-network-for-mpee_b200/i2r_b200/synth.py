@@ -84,3 +84,39 @@ def synth_heatmaps(n, k, h, w, seed=0):
     hm[0, 1, 0, 0] = 5.0
     hm[0, 2, h - 2, w - 3] = 5.0
     return hm
+
+
+def synth_image(h, w, seed=0):
+    """Bit-reproducible RGB uint8 image [h,w,3]: smooth integer gradients, blocks and integer noise (PCG64 integers and
+    integer arithmetic only)."""
+    g = np.random.default_rng(int(seed))
+    ys, xs = np.mgrid[0:h, 0:w]
+    img = np.zeros((h, w, 3), dtype=np.int64)
+    for c in range(3):
+        a, b, d = (int(v) for v in g.integers(1, 7, size=3))
+        img[:, :, c] = (a * xs + b * ys + d * ((xs // 16 + ys // 16) % 2) * 40) % 256
+    for _ in range(12):
+        y0, x0 = int(g.integers(0, h - 20)), int(g.integers(0, w - 20))
+        hh, ww = int(g.integers(10, h // 3)), int(g.integers(10, w // 3))
+        img[y0:y0 + hh, x0:x0 + ww] = g.integers(0, 256, size=3)
+    img = (img + g.integers(-12, 13, size=img.shape)).clip(0, 255)
+    return img.astype(np.uint8)
+
+
+def synth_people(h, w, n, seed=0):
+    """n person boxes inside an h x w image with the center / scale the reference derives from a box
+    (lib/dataset/coco.py `_box2cs`: aspect ratio 192/256, pixel_std 200, 1.25 enlargement)."""
+    g = np.random.default_rng(int(seed))
+    people = []
+    for _ in range(n):
+        bw, bh = float(g.integers(40, w // 2)), float(g.integers(60, h // 2))
+        x, y = float(g.integers(0, w - int(bw))) + 0.25 * float(g.integers(0, 4)), float(g.integers(0, h - int(bh)))
+        center = np.array([x + bw * 0.5, y + bh * 0.5], dtype=np.float32)
+        aspect = 192.0 / 256.0
+        if bw > aspect * bh:
+            bh2, bw2 = bw / aspect, bw
+        else:
+            bh2, bw2 = bh, bh * aspect
+        scale = np.array([bw2 / 200.0, bh2 / 200.0], dtype=np.float32) * 1.25
+        people.append(dict(box=(x, y, bw, bh), center=center, scale=scale))
+    return people

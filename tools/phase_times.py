@@ -18,7 +18,8 @@ cfg, model, sd = build_model(yaml)
 model = model.cuda()
 model.use_cuda_graph = False
 length = [persons] * images
-x, pm = inputs_for(length)
+hw = (int(sys.argv[4]), int(sys.argv[5])) if len(sys.argv) > 5 else (256, 192)
+x, pm = inputs_for(length, *hw)
 x, pm = x.cuda(), pm.cuda()
 model(x, pm, length)
 torch.cuda.synchronize()
@@ -42,7 +43,8 @@ def wrap(name):
     setattr(ops.Runner, name, f)
 
 
-for n in ("launch", "stem", "maxpool", "layernorm", "add", "upsum", "attention", "attention_tc", "encoder_tail"):
+for n in ("launch", "stem", "maxpool", "layernorm", "add", "upsum", "attention", "attention_tc", "encoder_tail", "dwconv3x3",
+          "upsum_bilinear", "layernorm_padded", "ln_window_gather", "window_scatter_add", "window_attention"):
     wrap(n)
 reps = 3
 tot = {}
@@ -57,3 +59,14 @@ total = sum(v[1] for v in tot.values())
 print("eager spin-parked forward: %.1f us over %d launches (%s, %d crops)" % (total, len(tot), yaml, sum(length)))
 for i in sorted(tot):
     print("%3d %8.1f us  %s" % (i, tot[i][1], tot[i][0][:150]))
+by_kind = {}
+for i in tot:
+    k = tot[i][0].split("[")[0]
+    if k == "conv":
+        k = "conv " + ("igemm/halo 1x1" if "k1" in tot[i][0] and "k9" not in tot[i][0] else "3x3 / mixed")
+    by_kind.setdefault(k, [0, 0.0])
+    by_kind[k][0] += 1
+    by_kind[k][1] += tot[i][1]
+print("by kind:")
+for k, (n, t) in sorted(by_kind.items(), key=lambda kv: -kv[1][1]):
+    print("  %-28s %4d launches %9.1f us  %5.1f%%" % (k, n, t, 100 * t / total))
