@@ -241,6 +241,13 @@ int i2r_debug_flags(int flags);
  * address, parity << 32 | dynamic shared base, clock64}.  NULL removes it.  Synchronises the device. */
 int i2r_debug_hang_buffer(void* host_mapped);
 
+/* `res` multi-person position embedding, stem (lib/models/position_embedding.py:14-18, :90-93): box masks fp32
+ * [NB,1,H,W] -> conv_pre 3x3 (1 -> 3, w_pre fp32 [3][9]) -> resnet18 conv1 7x7 s2 p3 (3 -> 64, w1 fp32 [147][64] with
+ * k = (c*7 + ky)*7 + kx) -> folded bn1 (scale / bias fp32 [64]) -> ReLU, fp16 NHWC [NB, H/2, W/2, 64] (split != 0: pair
+ * tensor with 128 values per pixel).  The layers after it (max-pool, layer1, conv_end) use the generic entry points. */
+int i2r_mask_res_stem(const float* mask, const float* w_pre, const float* w1, const float* scale, const float* bias,
+                      void* y, int NB, int H, int W, int split, void* stream);
+
 /* ---- post-processing on the device (N1 flip-test fusion, N2 heatmap decode) ------------------------ */
 
 /* dst[r, w] = src[r, W-1-w] on fp32 rows of W elements (out of place): np.flip(input, 3) of the flip test

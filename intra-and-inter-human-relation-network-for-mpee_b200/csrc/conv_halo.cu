@@ -61,10 +61,17 @@ struct HaloProblem {
   // pair), `ntiles_real` the number of 128-pixel tiles; CTA `rank` of pair q works on tile 2*j + rank.
   int pair, ntiles_real;
   uint32_t w_gstage;   // bytes between consecutive (tap, K-chunk) blocks of the packed weight image in global memory
+  // staged output: the epilogue warps write the finished tile into shared memory ([128 pixels][Cout] fp16, the dense box
+  // of a 4-D TMA store; split mode: a hi tile and a lo tile) and one thread hands it to the TMA unit -- a warp's row-per-
+  // thread stores would touch 24-32 different 128-byte lines per instruction.  o_bufs = 0: direct stores (no room, or an
+  // output mode without a tensor-map form).
+  int o_bufs;
+  uint32_t o_off, o_tile_bytes;
 };
 
 struct HaloGroup {
   CUtensorMap amap[I2R_MAX_GROUP];
+  CUtensorMap omap[I2R_MAX_GROUP][2];   // staged output: hi (or only) tile, lo tile of a pair tensor
   unsigned long long* trace;   // optional event trace (tools/trace_halo.py): four role regions of trace_cap (tag<<32|tile, clock64) pairs
   int trace_cta, trace_cap;
   int dbg;                     // debug ablations (i2r_debug_flags): 1 = epilogue hand-shake only, 2 = no global stores / residual loads
@@ -106,12 +113,27 @@ __device__ __forceinline__ HaloProblem load_problem(const HaloProblem& s) {
   p.a_stages = opaque(s.a_stages); p.w_stages = opaque(s.w_stages); p.w_off = opaque(s.w_off);
   p.w_copies = opaque(s.w_copies);
   p.pair = opaque(s.pair); p.ntiles_real = opaque(s.ntiles_real); p.w_gstage = opaque(s.w_gstage);
+  p.o_bufs = opaque(s.o_bufs); p.o_off = opaque(s.o_off); p.o_tile_bytes = opaque(s.o_tile_bytes);
   return p;
 }
 
-constexpr int T_THREADS = 384;
+#ifndef I2R_EPI_WARPS
+#define I2R_EPI_WARPS 8
+#endif
+constexpr int T_EPI_WARPS = I2R_EPI_WARPS;  // per TMEM lane quadrant T_EPI_WARPS / 4 warps, each a slice of the output
+                                            // channels.  Measured with 8 / 12 / 16 (profiles/r02_epilogue_warps.txt): more
+                                            // warps help the long split-operand epilogues a little (C4 +5 %) and cost
+                                            // the fp16 path 4 % (C2).  Two alternating epilogue GROUPS (two tiles in
+                                            // flight, each warp all channels of its rows) were also tried: 5-13 % slower.
+                                            // Neither issue latency nor the store pattern is the limit: at N = 48 the
+                                            // tensor core's operand fetch alone keeps the shared-memory port ~100 % busy
+                                            // (148 KB per tile at 128 B/cycle), so every extra byte the epilogue moves
+                                            // through L1 / shared memory lengthens the tile (profiles/r02_epilogue_*.txt)
+constexpr int T_THREADS = 32 * (4 + T_EPI_WARPS);
 constexpr int T_TW = 8, T_TH = 16;
 constexpr int T_W_STAGES_MAX = 8;           // streamed-weight ring depth (barriers at [256,384))
+constexpr int T_A_STAGES_MAX = 8;           // activation ring depth (barriers at [0,128)): K-chunked 1x1 GEMMs (HRFormer: 6
+                                            // chunks per tile in split mode) are TMA-latency bound with fewer stages
 constexpr uint32_t T_ONES_OFF = 1024;       // 1 KB of fp16 1.0: the A operand of the bias MMA
 constexpr uint32_t T_A_OFF = 2048;          // dynamic smem: [0,384) barriers | [1024,2048) ones | A ring
 constexpr uint32_t T_MAX_SMEM = 226 * 1024;   // + 1 KB alignment slack = 227 KB opt-in limit
@@ -214,10 +236,10 @@ __device__ __forceinline__ void issue_taps(uint32_t d_tmem, uint32_t a_lo, uint3
 }
 
 // Barrier map (byte offsets from the 1024-aligned base of dynamic shared memory; 8 bytes each):
-//   afull[4] 0 (pair: the leader's counts both CTAs' tiles) | aempty[4] 32 | (64..127 free) | accfull[2] 128 |
+//   afull[8] 0 (pair: the leader's counts both CTAs' tiles) | aempty[8] 64 | accfull[2] 128 |
 //   accempty[2] 144 | wres 160 | pwres 168 (pair: peer's resident weights landed) | tmem slot 176 |
 //   pwfull[8] 192 (pair, streamed: peer's weight slot landed) | wfull[8] 256 | wempty[8] 320
-constexpr uint32_t B_AFULL = 0, B_AEMPTY = 32, B_PFULL = 64, B_ACCFULL = 128, B_ACCEMPTY = 144, B_WRES = 160, B_PWRES = 168,
+constexpr uint32_t B_AFULL = 0, B_AEMPTY = 64, B_ACCFULL = 128, B_ACCEMPTY = 144, B_WRES = 160, B_PWRES = 168,
                    B_PWFULL = 192, B_WFULL = 256, B_WEMPTY = 320;
 
 // MMA issue loop.  Everything here is warp-uniform (kernel parameters, loop counters, shared-memory
@@ -405,12 +427,66 @@ struct EpiArgs {
   int out_pix_stride, add_pix_stride, plane;
   uint32_t flags;
   int pair, rank, ntiles_real;   // CTA-pair mode: this CTA's tile of pair-tile t is 2*t + rank (may lie past the end)
+  int o_bufs;                    // staged output (see HaloProblem): buffers, shared-memory base, bytes per tile, maps
+  uint32_t o_base, o_tile_bytes;
+  const CUtensorMap* omap;       // [2]
 };
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.tile.bulk_group [%0, {%2,%3,%4,%5}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(map)), "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void epi_barrier() {      // the epilogue warps only (named barrier 1)
+  asm volatile("bar.sync 1, %0;" ::"n"(32 * T_EPI_WARPS) : "memory");
+}
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+// Staged output, per tile: (1) the issuing thread waits until the TMA unit has finished READING the buffer two tiles back,
+// (2) all epilogue warps meet, write their rows, fence them towards the async proxy and meet again, (3) the issuing
+// thread launches the store(s).  Tiles overhanging the image are clipped by the TMA unit.
+struct StageOut {
+  bool on, issuer;
+  uint32_t buf_addr;
+  int nbuf, b;
+  __device__ __forceinline__ void begin_tile(const EpiArgs& E) {
+    if (!on) return;
+    if (issuer) {
+      if (nbuf > 1) bulk_wait_read<1>(); else bulk_wait_read<0>();
+    }
+    epi_barrier();
+    buf_addr = E.o_base + static_cast<uint32_t>(b) * E.o_tile_bytes * ((E.flags & I2R_F_SPLIT) ? 2u : 1u);
+  }
+  __device__ __forceinline__ void end_tile(const EpiArgs& E, int x0, int y0, int n, bool tile_ok) {
+    if (!on) return;
+    fence_proxy_async();
+    epi_barrier();
+    if (issuer) {
+      if (tile_ok) {
+        tma_store_4d(E.omap, buf_addr, 0, x0, y0, n);
+        if (E.flags & I2R_F_SPLIT) tma_store_4d(E.omap + 1, buf_addr + E.o_tile_bytes, 0, x0, y0, n);
+      }
+      bulk_commit();
+    }
+    b = (b + 1 == nbuf) ? 0 : b + 1;
+  }
+  __device__ __forceinline__ void finish() {
+    if (on && issuer) bulk_wait_all();
+  }
+};
+
 // accumulator hand-back: the leader's accempty barrier, locally or (peer CTA of a pair) through the cluster address
 __device__ __forceinline__ void arrive_accempty(const EpiArgs& E, uint32_t bar_local) {
   if (E.pair && E.rank != 0) mbar_arrive_remote(mapa_rank(bar_local, 0)); else mbar_arrive(bar_local);
 }
 
+// (EG = 8-channel chunks in flight per pass: two keep the live set near 60 registers, which is what lets the kernel run
+// 12 epilogue warps at 128 registers per thread without spilling)
+constexpr int EG = 2;
 template <int OUT>
 __device__ __forceinline__ void epilogue_role(const EpiArgs E, const int cta, const uint32_t sbase, const uint32_t tmem_base,
                                               const uint32_t ncols, const int Npad, const int ew, const int quad,
@@ -418,14 +494,21 @@ __device__ __forceinline__ void epilogue_role(const EpiArgs E, const int cta, co
   const uint32_t bar_accfull = sbase + 128, bar_accempty = sbase + 144;
   const int row = quad * 32 + lane;
   const int ty_in = row >> 3, tx_in = row & 7;
-  const int n8 = Npad >> 3, half8 = (n8 + 1) >> 1;
-  const int cb = (ew >> 2) ? half8 : 0, ce = (ew >> 2) ? n8 : half8;   // 8-column chunks [cb, ce)
+  const int n8 = Npad >> 3, part8 = (n8 + (T_EPI_WARPS / 4) - 1) / (T_EPI_WARPS / 4);
+  const int cb = min(n8, (ew >> 2) * part8), ce = min(n8, cb + part8);   // 8-column chunks [cb, ce)
   const float lo = (E.flags & I2R_F_RELU) ? 0.0f : -3.0e38f;
   const float inv_tpi = 1.0f / static_cast<float>(E.tiles_per_img), inv_tx = 1.0f / static_cast<float>(E.tiles_x);
   const bool has0 = E.add0 != nullptr && !(dbg & 2), has1 = E.add1 != nullptr && !(dbg & 2);
   const bool split = (E.flags & I2R_F_SPLIT) != 0;
   int acc = 0, tri = 0;
   uint32_t accph = 0;
+  StageOut so;
+  so.on = E.o_bufs > 0;
+  so.issuer = ew == 0 && lane == 0;
+  so.nbuf = E.o_bufs;
+  so.b = 0;
+  so.buf_addr = 0;
+  const uint32_t srow = static_cast<uint32_t>(row) * static_cast<uint32_t>(E.Cout) * 2u;   // this pixel's row in the tile
   for (int tp = cta; tp < E.ntiles; tp += E.cta_count) {
     const int t = E.pair ? 2 * tp + E.rank : tp;
     // tile coordinates without integer division (exact for t < 2^22)
@@ -440,12 +523,13 @@ __device__ __forceinline__ void epilogue_role(const EpiArgs E, const int cta, co
     const __half* a0 = E.add0 + static_cast<int64_t>(p) * E.add_pix_stride;
     const __half* a1 = E.add1 + static_cast<int64_t>(p) * E.add_pix_stride;
     bool waited = false;
-    for (int c = cb; c < ce; c += 4) {
-      const int nc = min(4, ce - c);
+    so.begin_tile(E);
+    for (int c = cb; c < ce; c += EG) {
+      const int nc = min(EG, ce - c);
       // residual loads first: their latency hides behind the accumulator wait
-      uint4 r0[4], r1[4];
+      uint4 r0[EG], r1[EG];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
+      for (int j = 0; j < EG; ++j) {
         r0[j] = make_uint4(0, 0, 0, 0);
         r1[j] = make_uint4(0, 0, 0, 0);
         if (j < nc && valid && (c + j) * 8 < E.Cout) {
@@ -453,9 +537,9 @@ __device__ __forceinline__ void epilogue_role(const EpiArgs E, const int cta, co
           if (has1) r1[j] = __ldg(reinterpret_cast<const uint4*>(a1 + (c + j) * 8));
         }
       }
-      uint4 l0[4], l1[4];   // split-operand addends: lo halves at channel offset Cout
+      uint4 l0[EG], l1[EG];   // split-operand addends: lo halves at channel offset Cout
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
+      for (int j = 0; j < EG; ++j) {
         l0[j] = make_uint4(0, 0, 0, 0);
         l1[j] = make_uint4(0, 0, 0, 0);
         if (split && j < nc && valid && (c + j) * 8 < E.Cout) {
@@ -471,15 +555,15 @@ __device__ __forceinline__ void epilogue_role(const EpiArgs E, const int cta, co
         waited = true;
         if (ew == 0 && lane == 0) trace_ev_dep(tr, trcap, 2, tri, 20, t, 0);
       }
-      uint32_t av[4][8];
+      uint32_t av[EG][8];
 #pragma unroll
-      for (int j = 0; j < 4; ++j)
+      for (int j = 0; j < EG; ++j)
         if (j < nc) tmem_ld8(taddr + (c + j) * 8, av[j]);
       tmem_ld_wait();
       if (ew == 0 && lane == 0) trace_ev(tr, trcap, 2, tri, 22, t);
       if (!(dbg & 1)) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
+        for (int j = 0; j < EG; ++j) {
           if (j < nc && valid && (c + j) * 8 < E.Cout) {
             const int c0 = (c + j) * 8;
             const uint32_t q0[4] = {r0[j].x, r0[j].y, r0[j].z, r0[j].w};
@@ -522,7 +606,9 @@ __device__ __forceinline__ void epilogue_role(const EpiArgs E, const int cta, co
               q.z = pack_h2(v[4], v[5]);
               q.w = pack_h2(v[6], v[7]);
               __half* yq = reinterpret_cast<__half*>(E.y) + static_cast<int64_t>(p) * E.out_pix_stride + c0;
-              if (!(dbg & 2))
+              if (so.on)
+                st_shared_v4(so.buf_addr + srow + c0 * 2, q.x, q.y, q.z, q.w);
+              else if (!(dbg & 2))
                 *reinterpret_cast<uint4*>(yq) = q;
               else if (q.x == 0x12345678u)
                 *reinterpret_cast<uint4*>(E.y) = q;
@@ -534,7 +620,8 @@ __device__ __forceinline__ void epilogue_role(const EpiArgs E, const int cta, co
                   const float2 f = unpack_h2(hq[i]);
                   lq[i] = pack_h2(v[2 * i] - f.x, v[2 * i + 1] - f.y);
                 }
-                *reinterpret_cast<uint4*>(yq + E.lo_off) = make_uint4(lq[0], lq[1], lq[2], lq[3]);
+                if (so.on) st_shared_v4(so.buf_addr + E.o_tile_bytes + srow + c0 * 2, lq[0], lq[1], lq[2], lq[3]);
+                else *reinterpret_cast<uint4*>(yq + E.lo_off) = make_uint4(lq[0], lq[1], lq[2], lq[3]);
               }
             } else if (E.flags & I2R_F_OUT_NCHW_F32) {
               float* Y = reinterpret_cast<float*>(E.y);
@@ -561,10 +648,12 @@ __device__ __forceinline__ void epilogue_role(const EpiArgs E, const int cta, co
     tc_fence_before();
     __syncwarp();
     if (lane == 0) arrive_accempty(E, bar_accempty + 8 * acc);
+    so.end_tile(E, tx * T_TW, ty * T_TH, n, t < E.ntiles_real);
     if (ew == 0 && lane == 0) trace_ev(tr, trcap, 2, tri, 21, t);
     acc ^= 1;
     if (acc == 0) accph ^= 1;
   }
+  so.finish();
 }
 
 
@@ -585,6 +674,13 @@ __device__ __forceinline__ void epilogue_fast(const EpiArgs E, const int cta, co
   const uint32_t lane_taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
   int acc = 0, tri = 0;
   uint32_t accph = 0;
+  StageOut so;
+  so.on = E.o_bufs > 0;
+  so.issuer = ew == 0 && lane == 0;
+  so.nbuf = E.o_bufs;
+  so.b = 0;
+  so.buf_addr = 0;
+  const uint32_t srow = static_cast<uint32_t>(row) * static_cast<uint32_t>(E.Cout) * 2u;   // this pixel's row in the tile
   for (int tp = cta; tp < E.ntiles; tp += E.cta_count) {
     const int t = E.pair ? 2 * tp + E.rank : tp;
     const int n = __float2int_rd((static_cast<float>(t) + 0.5f) * inv_tpi);
@@ -595,6 +691,7 @@ __device__ __forceinline__ void epilogue_fast(const EpiArgs E, const int cta, co
     const bool valid = (x < E.W) && (y < E.H) && (t < E.ntiles_real);
     const int p = (n * E.H + y) * E.W + x;
     const uint32_t taddr = lane_taddr + static_cast<uint32_t>(acc) * (ncols >> 1);
+    so.begin_tile(E);
     const __half* a0 = E.add0 + static_cast<int64_t>(p) * E.add_pix_stride;
     const __half* a1 = E.add1 + static_cast<int64_t>(p) * E.add_pix_stride;
     __half* yp = ybase + static_cast<int64_t>(p) * E.out_pix_stride;
@@ -636,17 +733,20 @@ __device__ __forceinline__ void epilogue_fast(const EpiArgs E, const int cta, co
           }
           o[i] = pack_h2(fmaxf(va, lo), fmaxf(vb, lo));
         }
-        if (valid) *reinterpret_cast<uint4*>(yp + (c + j) * 8) = make_uint4(o[0], o[1], o[2], o[3]);
+        if (so.on) st_shared_v4(so.buf_addr + srow + (c + j) * 16, o[0], o[1], o[2], o[3]);
+        else if (valid) *reinterpret_cast<uint4*>(yp + (c + j) * 8) = make_uint4(o[0], o[1], o[2], o[3]);
       }
     }
     if (ew == 0 && lane == 0) trace_ev(tr, trcap, 2, tri, 23, t);
     tc_fence_before();
     __syncwarp();
     if (lane == 0) arrive_accempty(E, bar_accempty + 8 * acc);
+    so.end_tile(E, tx * T_TW, ty * T_TH, n, t < E.ntiles_real);
     if (ew == 0 && lane == 0) trace_ev(tr, trcap, 2, tri, 21, t);
     acc ^= 1;
     if (acc == 0) accph ^= 1;
   }
+  so.finish();
 }
 
 template <int NADD>
@@ -708,10 +808,9 @@ __global__ void __launch_bounds__(T_THREADS, 1) conv_halo_kernel(const __grid_co
   while (ncols < static_cast<uint32_t>(2 * Npad)) ncols <<= 1;
 
   if (tid == 0) {
-    for (int i = 0; i < 4; ++i) {
+    for (int i = 0; i < T_A_STAGES_MAX; ++i) {
       mbar_init(bar_afull + 8 * i, 1);
       mbar_init(bar_aempty + 8 * i, 1);
-      mbar_init(sbase + B_PFULL + 8 * i, 1);
     }
     for (int i = 0; i < T_W_STAGES_MAX; ++i) {
       mbar_init(bar_wfull + 8 * i, 1);
@@ -720,7 +819,7 @@ __global__ void __launch_bounds__(T_THREADS, 1) conv_halo_kernel(const __grid_co
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(bar_accfull + 8 * i, 1);
-      mbar_init(bar_accempty + 8 * i, pair ? 16 : 8);   // pair: the epilogue warps of BOTH CTAs hand the accumulator back
+      mbar_init(bar_accempty + 8 * i, pair ? 2 * T_EPI_WARPS : T_EPI_WARPS);   // pair: the epilogue warps of BOTH CTAs
     }
     mbar_init(bar_wres, 1);
     mbar_init(sbase + B_PWRES, 1);
@@ -868,9 +967,11 @@ __global__ void __launch_bounds__(T_THREADS, 1) conv_halo_kernel(const __grid_co
     E.ntiles = P.ntiles; E.cta_count = P.cta_count;
     E.out_pix_stride = P.out_pix_stride; E.add_pix_stride = P.add_pix_stride; E.plane = P.plane; E.flags = P.flags;
     E.pair = pair ? 1 : 0; E.rank = rank; E.ntiles_real = P.ntiles_real;
+    E.o_bufs = P.o_bufs; E.o_base = sbase + P.o_off; E.o_tile_bytes = P.o_tile_bytes; E.omap = &G.omap[pi][0];
     const int ew = warp - 4;
-    const int n8 = (P.Cout + 7) >> 3, half8 = (n8 + 1) >> 1;   // chunks holding real channels, split over the warp pair
-    const int cb = (ew >> 2) ? half8 : 0, ce = (ew >> 2) ? n8 : half8;
+    // chunks holding real channels, split over the warps of a lane quadrant
+    const int n8 = (P.Cout + 7) >> 3, part8 = (n8 + (T_EPI_WARPS / 4) - 1) / (T_EPI_WARPS / 4);
+    const int cb = min(n8, (ew >> 2) * part8), ce = min(n8, cb + part8);
     if ((P.flags & (I2R_F_OUT_NCHW_F32 | I2R_F_OUT_F32 | I2R_F_SPLIT | I2R_F_OUT_T16 | I2R_F_GELU | I2R_F_ACT_FIRST)) ||
         (P.Cout & 7) || dbg != 0 ||
         ce == cb) {
@@ -940,6 +1041,29 @@ static int encode_amap(CUtensorMap* map, const void* x, int NB, int H, int W, in
   return 0;
 }
 
+// Output tensor (C, W, H, N) for TMA stores: box = (Cout channels, 8 px, 16 lines, 1), no swizzle -- the shared-memory tile
+// is the dense [128 pixels][Cout] array the epilogue writes.
+static int encode_omap(CUtensorMap* map, void* y, int NB, int H, int W, int Cout, int pix_stride) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) {
+    set_error("cuTensorMapEncodeTiled entry point unavailable");
+    return I2R_E_DEVICE;
+  }
+  const cuuint64_t pb = static_cast<cuuint64_t>(pix_stride) * 2;
+  const cuuint32_t ones[4] = {1, 1, 1, 1};
+  const cuuint64_t dims[4] = {(cuuint64_t)Cout, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)NB};
+  const cuuint64_t strides[3] = {pb, pb * W, pb * W * H};
+  const cuuint32_t box[4] = {(cuuint32_t)Cout, (cuuint32_t)T_TW, (cuuint32_t)T_TH, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, y, dims, strides, box, ones, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled (output) failed (%d) for [%d,%d,%d,%d] pix_stride %d", (int)r, NB, H, W, Cout,
+              pix_stride);
+    return I2R_E_DEVICE;
+  }
+  return 0;
+}
+
 static unsigned long long* g_trace = nullptr;
 static int g_trace_cta = 0, g_trace_cap = 0, g_dbg = 0;
 static bool is_std3x3(const i2r_conv_problem& P) {
@@ -997,6 +1121,11 @@ extern "C" int i2r_conv_halo(const i2r_conv_problem* probs, int nprob, void* str
   static const int pair_policy = []() {
     const char* e = getenv("I2R_HALO_PAIR");
     return e ? atoi(e) : 0;
+  }();
+  // I2R_HALO_STAGE=0 switches the staged (shared memory + TMA store) output path off
+  static const int stage_policy = []() {
+    const char* e = getenv("I2R_HALO_STAGE");
+    return e ? atoi(e) : 1;
   }();
   int order[I2R_MAX_GROUP], npair = 0;
   bool want_pair[I2R_MAX_GROUP];
@@ -1083,7 +1212,7 @@ extern "C" int i2r_conv_halo(const i2r_conv_problem* probs, int nprob, void* str
       P.w_stages = 1;
       wregion = w_cta_bytes;
       astg = static_cast<int>((T_MAX_SMEM - T_A_OFF - wregion) / P.a_stage_bytes);
-      if (astg > 4) astg = 4;
+      if (astg > T_A_STAGES_MAX) astg = T_A_STAGES_MAX;
       astg &= ~1;   // two half-rings, one per MMA issuer
     } else {
       astg = 3;
@@ -1097,13 +1226,40 @@ extern "C" int i2r_conv_halo(const i2r_conv_problem* probs, int nprob, void* str
                 P.a_stage_bytes, wregion);
       return I2R_E_UNSUPPORTED;
     }
+    // staged output tiles (fp16 NHWC outputs with whole 8-channel chunks): two buffers, else one, else direct stores;
+    // the activation ring gives up stages for them down to two (resident weights: two per issuer)
+    P.o_bufs = 0;
+    P.o_tile_bytes = (static_cast<uint32_t>(T_TW * T_TH) * S.Cout * 2 + 127u) & ~127u;
+    const bool stageable = stage_policy != 0 && !(S.flags & (I2R_F_OUT_NCHW_F32 | I2R_F_OUT_F32 | I2R_F_OUT_T16)) &&
+                           S.Cout % 8 == 0 && S.Cout <= 256 && S.out_pix_stride % 8 == 0 &&
+                           (!P.split || P.lo_off % 8 == 0);
+    if (stageable) {
+      const uint32_t per_buf = P.o_tile_bytes * (P.split ? 2u : 1u);
+      const int astg_min = P.w_resident ? 4 : 2;
+      for (int nb = 2; nb >= 1 && P.o_bufs == 0; --nb) {
+        int a = astg;
+        while (a > astg_min && T_A_OFF + a * P.a_stage_bytes + wregion + nb * per_buf + 128 > T_MAX_SMEM) a -= P.w_resident ? 2 : 1;
+        if (T_A_OFF + a * P.a_stage_bytes + wregion + nb * per_buf + 128 <= T_MAX_SMEM) {
+          P.o_bufs = nb;
+          astg = a;
+        }
+      }
+    }
     P.a_stages = astg;
     {
       int rc = encode_amap(&G.amap[i], S.x, P.NB, P.H, P.W, P.split ? 2 * P.C : P.C, S.in_pix_stride, hw, hh);
       if (rc) return rc;
     }
     P.w_off = T_A_OFF + static_cast<uint32_t>(astg) * P.a_stage_bytes;
-    const uint32_t need = P.w_off + wregion;
+    P.o_off = (P.w_off + wregion + 127u) & ~127u;
+    if (P.o_bufs) {
+      // the output as a 4-D tensor (C, W, H, N) with the same tile geometry as the activation map, dense boxes
+      int rc = encode_omap(&G.omap[i][0], S.y, P.NB, P.H, P.W, S.Cout, S.out_pix_stride);
+      if (!rc && P.split)
+        rc = encode_omap(&G.omap[i][1], static_cast<__half*>(S.y) + P.lo_off, P.NB, P.H, P.W, S.Cout, S.out_pix_stride);
+      if (rc) return rc;
+    }
+    const uint32_t need = P.o_off + P.o_bufs * P.o_tile_bytes * (P.split ? 2u : 1u);
     if (need > smem_need) smem_need = need;
     {
       // Cost model for the CTA allocation, in SM cycles (calibrated on per-CTA traces, profiles/r02_halo_cta_*):

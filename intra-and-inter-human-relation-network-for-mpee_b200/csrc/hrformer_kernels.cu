@@ -45,7 +45,7 @@ __device__ __forceinline__ void hk_store(__half* row, int C, int c, const float 
 }
 __device__ __forceinline__ float hk_act(float v, int act) {
   if (act == 1) return fmaxf(v, 0.f);
-  if (act == 2) return 0.5f * v * (1.f + erff(v * 0.70710678118654752f));   // nn.GELU (erf form)
+  if (act == 2) return gelu_erf(v);   // nn.GELU (erf form)
   return v;
 }
 static int hk_grid(int64_t items, int block) {
@@ -76,30 +76,46 @@ __global__ void __launch_bounds__(256) dwconv3x3_kernel(const __half* __restrict
     const int ox = static_cast<int>(p % OW);
     const int oy = static_cast<int>((p / OW) % OH);
     const int n = static_cast<int>(p / (static_cast<int64_t>(OW) * OH));
+    // all nine taps are fetched before the first FMA (18 independent 16-byte loads in flight per thread in pair mode:
+    // the kernel is latency bound otherwise -- border tests inside the FMA chain serialised load, use, load, use)
+    uint4 hi[9], lo[9];
+#pragma unroll
+    for (int t = 0; t < 9; ++t) {
+      const int iy = oy * stride - 1 + t / 3, ix = ox * stride - 1 + t % 3;
+      const bool ok = iy >= 0 && iy < H && ix >= 0 && ix < W;
+      const __half* src = x + ((static_cast<int64_t>(n) * H + (ok ? iy : 0)) * W + (ok ? ix : 0)) * ld + c;
+      hi[t] = ok ? __ldg(reinterpret_cast<const uint4*>(src)) : make_uint4(0, 0, 0, 0);
+      if (PAIR) lo[t] = ok ? __ldg(reinterpret_cast<const uint4*>(src + C)) : make_uint4(0, 0, 0, 0);
+    }
     float acc[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) acc[i] = 0.f;
 #pragma unroll
-    for (int ky = 0; ky < 3; ++ky) {
-      const int iy = oy * stride - 1 + ky;
-      if (iy < 0 || iy >= H) continue;
+    for (int t = 0; t < 9; ++t) {
+      const uint32_t hw4[4] = {hi[t].x, hi[t].y, hi[t].z, hi[t].w};
+      const uint32_t lw4[4] = {lo[t].x, lo[t].y, lo[t].z, lo[t].w};
+      float v[8];
 #pragma unroll
-      for (int kx = 0; kx < 3; ++kx) {
-        const int ix = ox * stride - 1 + kx;
-        if (ix < 0 || ix >= W) continue;
-        float v[8];
-        hk_load<PAIR>(x + ((static_cast<int64_t>(n) * H + iy) * W + ix) * ld, C, c, v);
-        const float4 w0 = __ldg(reinterpret_cast<const float4*>(w + (ky * 3 + kx) * C + c));
-        const float4 w1 = __ldg(reinterpret_cast<const float4*>(w + (ky * 3 + kx) * C + c + 4));
-        acc[0] = fmaf(v[0], w0.x, acc[0]);
-        acc[1] = fmaf(v[1], w0.y, acc[1]);
-        acc[2] = fmaf(v[2], w0.z, acc[2]);
-        acc[3] = fmaf(v[3], w0.w, acc[3]);
-        acc[4] = fmaf(v[4], w1.x, acc[4]);
-        acc[5] = fmaf(v[5], w1.y, acc[5]);
-        acc[6] = fmaf(v[6], w1.z, acc[6]);
-        acc[7] = fmaf(v[7], w1.w, acc[7]);
+      for (int i = 0; i < 4; ++i) {
+        const float2 f = unpack_h2(hw4[i]);
+        v[2 * i] = f.x;
+        v[2 * i + 1] = f.y;
+        if (PAIR) {
+          const float2 g = unpack_h2(lw4[i]);
+          v[2 * i] += g.x;
+          v[2 * i + 1] += g.y;
+        }
       }
+      const float4 w0 = __ldg(reinterpret_cast<const float4*>(w + t * C + c));
+      const float4 w1 = __ldg(reinterpret_cast<const float4*>(w + t * C + c + 4));
+      acc[0] = fmaf(v[0], w0.x, acc[0]);
+      acc[1] = fmaf(v[1], w0.y, acc[1]);
+      acc[2] = fmaf(v[2], w0.z, acc[2]);
+      acc[3] = fmaf(v[3], w0.w, acc[3]);
+      acc[4] = fmaf(v[4], w1.x, acc[4]);
+      acc[5] = fmaf(v[5], w1.y, acc[5]);
+      acc[6] = fmaf(v[6], w1.z, acc[6]);
+      acc[7] = fmaf(v[7], w1.w, acc[7]);
     }
 #pragma unroll
     for (int i = 0; i < 8; ++i) acc[i] = hk_act(fmaf(acc[i], __ldg(scale + c + i), __ldg(bias + c + i)), act);

@@ -273,11 +273,25 @@ __device__ __forceinline__ void issue_ksteps(uint32_t d_tmem, uint32_t a_lo, uin
   for (int k2 = 0; k2 < KS; ++k2)
     umma_f16(d_tmem, desc64(a_lo + 2 * k2, a_hi), desc64(b_lo + 2 * k2, b_hi), idesc, k2 ? 1u : acc_first);
 }
+// erf-GELU, 0.5 x (1 + erf(x / sqrt 2)), with erf from Abramowitz & Stegun 7.1.26 (|error| <= 1.5e-7, i.e. at fp32
+// rounding level): one reciprocal, one exp2 and seven FMAs instead of the ~45 instructions of erff().  The GELU layers
+// of HRFormer-B (MlpDWBN, lib/models/hrformer.py:1094-1119) evaluate it 25 M times per crop in epilogue warps that are
+// instruction-issue bound.
+__device__ __forceinline__ float gelu_erf(float v) {
+  const float z = fabsf(v) * 0.70710678118654752f;
+  const float t = __frcp_rn(fmaf(0.3275911f, z, 1.0f));
+  float p = fmaf(t, 1.061405429f, -1.453152027f);
+  p = fmaf(t, p, 1.421413741f);
+  p = fmaf(t, p, -0.284496736f);
+  p = fmaf(t, p, 0.254829592f);
+  const float e = exp2f(-1.4426950408889634f * z * z);
+  const float erf_abs = fmaf(-p * t, e, 1.0f);          // erf(|v| / sqrt 2)
+  return 0.5f * v + 0.5f * fabsf(v) * erf_abs;          // 0.5 v (1 + sign(v) erf_abs)
+}
 // epilogue activation: ReLU (I2R_F_RELU), erf-GELU (I2R_F_GELU) or identity
-// (deliberately NOT inlined: erff is ~60 instructions plus a local-memory frame, and the GELU layers are cold paths of
-// kernels whose hot loops must stay small)
+// (deliberately NOT inlined: the GELU layers are cold paths of kernels whose hot loops must stay small)
 static __device__ __noinline__ float epi_act(float v, uint32_t flags) {
-  if (flags & I2R_F_GELU) return 0.5f * v * (1.f + erff(v * 0.70710678118654752f));
+  if (flags & I2R_F_GELU) return gelu_erf(v);
   if (flags & I2R_F_RELU) return fmaxf(v, 0.f);
   return v;
 }

@@ -18,7 +18,7 @@ F_GELU = 32
 F_ACT_FIRST = 64
 
 EXPORTS = [
-    "i2r_version", "i2r_last_error", "i2r_device_check", "i2r_sm_count", "i2r_conv_igemm", "i2r_conv_halo", "i2r_conv_halo_supported", "i2r_debug_trace", "i2r_debug_flags", "i2r_debug_hang_buffer", "i2r_hflip_f32", "i2r_flip_merge", "i2r_decode_heatmaps", "i2r_crop_persons", "i2r_box_masks",
+    "i2r_version", "i2r_last_error", "i2r_device_check", "i2r_sm_count", "i2r_conv_igemm", "i2r_conv_halo", "i2r_conv_halo_supported", "i2r_debug_trace", "i2r_debug_flags", "i2r_debug_hang_buffer", "i2r_hflip_f32", "i2r_flip_merge", "i2r_decode_heatmaps", "i2r_crop_persons", "i2r_box_masks", "i2r_mask_res_stem",
     "i2r_sizeof_conv_problem", "i2r_stem_conv3x3s2", "i2r_stem_conv3x3s2_tc", "i2r_stem_tc_weight_bytes", "i2r_maxpool3x3s2", "i2r_attention_varlen", "i2r_attention_workspace_bytes", "i2r_attention_tc", "i2r_encoder_tail", "i2r_encoder_tail_weight_bytes", "i2r_attention_tc_workspace_bytes", "i2r_layernorm", "i2r_add_f16", "i2r_upsum", "i2r_dwconv3x3", "i2r_upsum_bilinear", "i2r_layernorm_padded", "i2r_window_rows", "i2r_ln_window_gather", "i2r_window_scatter_add", "i2r_window_attention",
 ]
 
@@ -102,6 +102,7 @@ def load():
         lib.i2r_upsum.argtypes = [vp, vp, i32, vp, i32, vp, i32, i32, i32, i32, i32, i32, vp]
         lib.i2r_hflip_f32.argtypes = [vp, vp, i64, i32, vp]
         lib.i2r_flip_merge.argtypes = [vp, vp, vp, i32, i32, i32, i32, vp, vp]
+        lib.i2r_mask_res_stem.argtypes = [vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, vp]
         lib.i2r_crop_persons.argtypes = [vp, i32, i32, vp, i32, i32, i32, vp, vp, vp, vp]
         lib.i2r_box_masks.argtypes = [vp, i32, i32, i32, i32, i32, vp, vp]
         lib.i2r_decode_heatmaps.argtypes = [vp, i32, i32, i32, i32, vp, vp, i32, i32, vp, vp, vp]

@@ -67,8 +67,10 @@ class EncoderProgram:
         self.d_real = d_model
         self.scale = 1.0 / math.sqrt(d_model // nhead)
 
-    def run(self, r, src, pos, cu_seqlens, max_seqlen):
-        """src / pos: [T, d] fp16, or split tensors [T, 2d] (hi | lo) when the layers were built in split-operand mode."""
+    def run(self, r, src, pos, cu_seqlens, max_seqlen, attn_tap=None):
+        """src / pos: [T, d] fp16, or split tensors [T, 2d] (hi | lo) when the layers were built in split-operand mode.
+        attn_tap(layer, q [T,d] fp32, k [T,d] fp32, scale): visualisation aid -- called with the projected queries / keys
+        of every layer when forward hooks are registered on the `self_attn` holders (module_base.attention_hooks)."""
         d = self.d
         split = self.layers[0].qk.split
         sp = r.add(src, pos) if pos is not None else src
@@ -80,12 +82,19 @@ class EncoderProgram:
                 pk, k = r.linear_problem(L.k, sp)
                 r.launch([pq, pk, pv])
                 wq = 2 * d if split else d
+                if attn_tap is not None:
+                    q2, k2 = q.view(-1, wq).float(), k.view(-1, wq).float()
+                    if split:
+                        q2, k2 = q2[:, :d] + q2[:, d:], k2[:, :d] + k2[:, d:]
+                    attn_tap(li, q2[:, :self.d_real], k2[:, :self.d_real], self.scale)
                 a = r.attention_tc(q.view(-1, wq), k.view(-1, wq), vt, cu_seqlens, max_seqlen, self.scale,
                                    split=split)
             else:
                 pq, qk = r.linear_problem(L.qk, sp)
                 r.launch([pq, pv])
                 qk = qk.view(-1, 2 * d)
+                if attn_tap is not None:
+                    attn_tap(li, qk[:, :d].float(), qk[:, d:].float(), self.scale)
                 a = r.attention_tc(qk[:, :d], qk[:, d:], vt, cu_seqlens, max_seqlen, self.scale)
             last = li == len(self.layers) - 1
             if L.tail is not None:

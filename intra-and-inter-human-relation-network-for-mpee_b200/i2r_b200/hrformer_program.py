@@ -79,7 +79,15 @@ class _Block:
     def run(self, r, x):
         nb, h, w, cw = x.shape
         rows = r.ln_window_gather(x, self.n1[0], self.n1[1], self.c, WS)
-        q, k, v = (_lin(r, L, rows) for L in (self.q, self.k, self.v))
+        # the three projections read the same rows: one grouped launch (column chunks of > 256 outputs included)
+        t, c = rows.shape
+        probs, qkv = [], []
+        for L in (self.q, self.k, self.v):
+            ps, o = r.problems(L, rows.view(1, t, 1, c))
+            probs.extend(ps)
+            qkv.append(o.view(t, -1))
+        r.launch(probs)
+        q, k, v = qkv
         hq = self.heads * HEAD_PAD
         a = r.window_attention(q[:, :hq], k[:, :hq], v[:, :hq], WS * WS, self.heads, self.scale, HEAD_PAD)
         o = _lin(r, self.o, a)

@@ -76,6 +76,43 @@ class DevicePathModule(nn.Module):
             self._exact = ExactPlans(self._program.device)
         return self._exact.get([int(n) for n in length_or_plan])
 
+    # ------------------------------------------------------------------ visualisation hooks
+    def _hook_targets(self):
+        """(token-map layer or None, inter-human encoder holder): the sub-modules the reference's visualize.py:164-175
+        registers forward hooks on (`model.reduce`, `model.global_encoder.layers[i].self_attn`)."""
+        enc = getattr(self, "global_encoder", None) or getattr(self, "multi_global_encoder", None)
+        return getattr(self, "reduce", None), enc
+
+    def _hooked(self):
+        red, enc = self._hook_targets()
+        if red is not None and red._forward_hooks:
+            return True
+        return enc is not None and any(layer.self_attn._forward_hooks for layer in enc.layers)
+
+    def _fire_hooks(self, module, inputs, output):
+        for hook in list(module._forward_hooks.values()):
+            hook(module, inputs, output)
+
+    def _attn_tap(self, length, tokens):
+        """The forward never materialises attention weights (streaming softmax in TMEM); when a hook asks for them they
+        are rebuilt here, per image, from the projected queries and keys of the layer: [bs, L, L] fp32 with L =
+        max(length) * tokens, zero for padded persons -- what nn.MultiheadAttention returns as `output[1]`."""
+        red, enc = self._hook_targets()
+        lmax = max(length) * tokens
+
+        def tap(layer, q, k, scale):
+            mod = enc.layers[layer].self_attn
+            if not mod._forward_hooks:
+                return
+            w = torch.zeros((len(length), lmax, lmax), dtype=torch.float32, device=q.device)
+            at = 0
+            for b, n in enumerate(length):
+                t = n * tokens
+                w[b, :t, :t] = torch.softmax((q[at:at + t] * scale) @ k[at:at + t].t(), dim=-1)
+                at += t
+            self._fire_hooks(mod, (), (None, w))
+        return tap
+
     # ------------------------------------------------------------------ forward
     def _eager(self, x, pos_mask, length, hooks=None):
         """The launch sequence of one forward.  `length`: persons per image, or an engine.SeqPlan (graph capture:
@@ -86,12 +123,21 @@ class DevicePathModule(nn.Module):
         plan = self._plan(length)
         feat, heat_single, tok = self._stage_tokens(p, r, x)
         s, th, tw, d = tok.shape
+        tap = None
+        if hooks is None and self._hooked():      # eager calls only (forward disables graph replay while hooks exist)
+            red, _ = self._hook_targets()
+            if red is not None and red._forward_hooks:
+                t32 = tok.float()
+                if getattr(p, "split", False):
+                    t32 = t32[..., :d // 2] + t32[..., d // 2:]
+                self._fire_hooks(red, (), t32.permute(0, 3, 1, 2).contiguous())
+            tap = self._attn_tap(plan.length, th * tw)
         pos = None
         if p.mask_embed is not None:
             if hooks is not None:
                 hooks.mask_needed()
             pos = self._stage_pos(p, r, pos_mask, (th, tw)).view(s * th * tw, d)
-        y = p.encoder.run(r, tok.view(s * th * tw, d), pos, plan.cu(th * tw), plan.max_seqlen(th * tw))
+        y = p.encoder.run(r, tok.view(s * th * tw, d), pos, plan.cu(th * tw), plan.max_seqlen(th * tw), attn_tap=tap)
         return self._stage_head(p, r, y.view(s, th, tw, d), feat, heat_single)
 
     def _device(self):
@@ -110,7 +156,7 @@ class DevicePathModule(nn.Module):
         with torch.cuda.device(dev):
             self._ensure_program(dev)
             with torch.no_grad():
-                if self.use_cuda_graph:      # host tensors are uploaded through the engine's staging buffers
+                if self.use_cuda_graph and not self._hooked():      # host tensors go through the engine's staging buffers
                     if x.dtype != torch.float32 or pos_mask.dtype != torch.float32:
                         x, pos_mask = x.float(), pos_mask.float()
                     return self._graphs(x, pos_mask, length, device=dev)

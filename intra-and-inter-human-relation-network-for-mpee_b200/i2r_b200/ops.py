@@ -413,6 +413,17 @@ class Runner:
         self.launches += 1
         return y
 
+    def mask_res_stem(self, mask, w_pre, w1, scale, bias):
+        """conv_pre 3x3 (1 -> 3) + resnet18 conv1 7x7 s2 (3 -> 64) + bn1 + ReLU on fp32 masks [S,1,H,W] -> fp16 NHWC."""
+        nb, cin, h, wd = mask.shape
+        assert cin == 1 and mask.dtype == torch.float32 and mask.is_contiguous()
+        y = torch.empty((nb, h // 2, wd // 2, 64 * (2 if self.split else 1)), dtype=torch.float16, device=mask.device)
+        capi.check(self.lib.i2r_mask_res_stem(mask.data_ptr(), w_pre.data_ptr(), w1.data_ptr(), scale.data_ptr(),
+                                              bias.data_ptr(), y.data_ptr(), nb, h, wd, int(self.split), _stream_ptr()),
+                   "i2r_mask_res_stem")
+        self.launches += 1
+        return y
+
     def maxpool(self, x):
         nb, h, w, c = x.shape
         assert x.is_contiguous() and x.dtype == torch.float16

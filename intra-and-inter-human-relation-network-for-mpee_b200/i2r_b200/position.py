@@ -57,6 +57,41 @@ class MaskEmbedParams(nn.Module):
             raise ValueError("unknown MULTI_POS_EMBEDDING %r" % mode)
 
 
+class MaskEmbedResProgram:
+    """Mode 'res' (reference position_embedding.py:14-18, :90-108): conv_pre + resnet18 stem as one kernel
+    (csrc/mask_res.cu), max-pool, resnet18.layer1 (two BasicBlocks) and conv_end on the generic conv kernels, then the
+    max-pools down to TRANS_SIZE."""
+
+    def __init__(self, sd, prefix, device):
+        from .hrnet_w48 import _Unit
+        self.w_pre = sd[prefix + ".conv_pre.weight"].float().reshape(3, 9).contiguous().to(device)
+        w1 = sd[prefix + ".res.0.weight"].float()                      # [64,3,7,7] -> [147,64], k = (c*7+ky)*7+kx
+        self.w1 = w1.permute(1, 2, 3, 0).reshape(147, 64).contiguous().to(device)
+        sc, bi = fold_bn(sd, prefix + ".res.1", 64)
+        self.scale, self.bias = sc.to(device), bi.to(device)
+        self.blocks = [_Unit(sd, "%s.res.4.%d" % (prefix, b), "BASIC", device) for b in (0, 1)]
+        self.conv_end = conv_bn_layer(sd, prefix + ".conv_end", None, device=device)
+
+    def run(self, r, pos_mask, trans_hw):
+        y = r.mask_res_stem(pos_mask, self.w_pre, self.w1, self.scale, self.bias)
+        y = r.maxpool(y)
+        for u in self.blocks:
+            h = r.conv(u.c1, y)
+            y = r.conv(u.c2, h, add0=y)
+        y = r.conv(self.conv_end, y)
+        for _ in range(int(math.log(y.shape[2] // trans_hw[1], 2))):
+            y = r.maxpool(y)
+        return y
+
+
+def build_mask_embed_program(mode, sd, prefix, device):
+    if mode == "conv":
+        return MaskEmbedProgram(sd, prefix, device)
+    if mode == "res":
+        return MaskEmbedResProgram(sd, prefix, device)
+    raise NotImplementedError("MULTI_POS_EMBEDDING=%r with USE_MULTI_POS (kernels exist for 'conv' and 'res')" % mode)
+
+
 class MaskEmbedProgram:
     def __init__(self, sd, prefix, device):
         w = sd[prefix + ".conv1.weight"].float()           # [64,1,3,3] -> [9,64]

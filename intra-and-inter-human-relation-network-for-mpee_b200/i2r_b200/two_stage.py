@@ -20,7 +20,7 @@ from .module_base import DevicePathModule
 from .hrnet_w48 import conv_bn_layer
 from .modules import DeconvProgram, EncoderParams, make_deconv_stack
 from .ops import Runner, channel_padding, split_precision
-from .position import MaskEmbedParams, MaskEmbedProgram
+from .position import MaskEmbedParams, build_mask_embed_program
 
 
 class TwoStageInterFormer(DevicePathModule):
@@ -29,7 +29,14 @@ class TwoStageInterFormer(DevicePathModule):
         assert flavor in ("interformer", "interformer_2stage")
         m, extra = cfg.MODEL, cfg.MODEL.EXTRA
         self.flavor = flavor
-        self.singleformer = singleformer
+        # cfg.MODEL.SINGLEFORMER empty: the stand-alone HRNet produces the token maps directly (interformer.py:143,
+        # :291-292: no first-stage heatmaps, no max-pool, no residual), its parameters live under `backbone.body.*`
+        self.have_singleformer = singleformer is not None
+        if self.have_singleformer:
+            self.singleformer = singleformer
+        else:
+            import models.backbone
+            self.backbone = models.backbone.build_backbone(cfg)
         self.singleformer_fix = bool(m.SINGLEFORMER_FIX)
         self.trans_size = list(m.TRANS_SIZE)
         self.heatmap_size = list(m.HEATMAP_SIZE)
@@ -52,9 +59,20 @@ class TwoStageInterFormer(DevicePathModule):
         self.deconv_with_bias = bool(extra.DECONV_WITH_BIAS)
         # number of x2 upsampling steps from the token map back to the heatmap
         self.up_steps = int(math.log(self.heatmap_size[0] // self.trans_size[1], 2))
-        if self.upsample_type == "upconv":
-            raise NotImplementedError("UPSAMPLE_TYPE='upconv' (no shipped config uses it)")
-        if self.upsample_type == "multiplex":
+        if self.upsample_type == "upconv":      # interformer.py:25-64
+            holder = nn.Module()
+            scale = self.heatmap_size[0] // self.trans_size[1]
+            holder.fuse_layers = nn.Sequential(nn.Conv2d(d_model, d_model, 1, 1, 0, bias=False), nn.BatchNorm2d(d_model),
+                                               nn.Upsample(scale_factor=scale, mode="nearest"))
+            holder.double_conv = nn.Sequential(
+                nn.Conv2d(d_model, d_model, 3, padding=1, bias=False), nn.BatchNorm2d(d_model), nn.ReLU(inplace=True),
+                nn.Conv2d(d_model, d_model, 3, padding=1, bias=False), nn.BatchNorm2d(d_model), nn.ReLU(inplace=True))
+            self.upsample_layer = holder
+            self._upconv_shift = int(math.log(scale, 2))
+            if 2 ** self._upconv_shift != scale:
+                raise NotImplementedError("UpConv scale factor %d is not a power of two" % scale)
+            self._deconv_keys = []
+        elif self.upsample_type == "multiplex":
             self.deconv_layers = make_deconv_stack(extra, self.deconv_with_bias)
             self._deconv_keys = ["deconv_layers"] * (self.up_steps if flavor == "interformer_2stage" else 2)
         elif self.upsample_type == "deconv":
@@ -78,7 +96,7 @@ class TwoStageInterFormer(DevicePathModule):
 
     @property
     def returns_dict(self):
-        return self.inter_supervision and not self.singleformer_fix
+        return self.inter_supervision and self.have_singleformer and not self.singleformer_fix
 
     # ------------------------------------------------------------------ weights -> device program
     def prepare(self, device=None):
@@ -87,23 +105,25 @@ class TwoStageInterFormer(DevicePathModule):
         c = self._cfg
         if c["final_k"] != 1:
             raise NotImplementedError("FINAL_CONV_KERNEL=3")
-        if self.use_multi_pos and self.multi_position_mode != "conv":
-            raise NotImplementedError("MULTI_POS_EMBEDDING=%r with USE_MULTI_POS (kernels exist for 'conv')" %
+        if self.use_multi_pos and self.multi_position_mode not in ("conv", "res"):
+            raise NotImplementedError("MULTI_POS_EMBEDDING=%r with USE_MULTI_POS (kernels exist for 'conv' and 'res')" %
                                       self.multi_position_mode)
         prog = type("Program", (), {})()
         prog.device = device
         prog.runner = self._runner_factory(device, 1 if self.check_impl else 0)
         # the whole model shares the first stage's precision mode (split-operand unless overridden)
-        prog.split = getattr(self.singleformer, "precision", "fp16") == "split"
+        first_stage = self.singleformer if self.have_singleformer else self.backbone.body
+        prog.split = getattr(first_stage, "precision", "fp16") == "split"
         prog.runner.split = prog.split
-        prog.first = self.singleformer.build_program(device)
+        prog.first = first_stage.build_program(device)
         with split_precision(prog.split), channel_padding(16 if c["d_model"] % 16 else 0):
             self._build_second_stage(prog, sd, c, device)
         self._program_ready(prog)
         return self
 
     def _build_second_stage(self, prog, sd, c, device):
-        prog.mask_embed = MaskEmbedProgram(sd, "multi_position_embedding", device) if self.use_multi_pos else None
+        prog.mask_embed = build_mask_embed_program(self.multi_position_mode, sd, "multi_position_embedding",
+                                                   device) if self.use_multi_pos else None
         prog.encoder = EncoderProgram(sd, "multi_global_encoder", c["layers"], c["d_model"], c["nhead"], device)
         cache = {}
 
@@ -113,11 +133,20 @@ class TwoStageInterFormer(DevicePathModule):
                               for i in range(c["num_deconv"])]
             return cache[key]
         prog.upsample = [deconv(k) for k in self._deconv_keys]
+        prog.upconv = None
+        if self.upsample_type == "upconv":
+            u = "upsample_layer."
+            prog.upconv = (conv_bn_layer(sd, u + "fuse_layers.0", u + "fuse_layers.1", device=device),
+                           conv_bn_layer(sd, u + "double_conv.0", u + "double_conv.1", relu=True, device=device),
+                           conv_bn_layer(sd, u + "double_conv.3", u + "double_conv.4", relu=True, device=device))
         prog.head = conv_bn_layer(sd, "final_layer", None, device=device)
 
     # ------------------------------------------------------------------ forward
     # the four stages DevicePathModule._eager (and sharded.ShardedForward) compose
     def _stage_tokens(self, p, r, x):
+        if not self.have_singleformer:
+            feats = p.first.backbone.run(r, x)
+            return None, None, r.conv(p.first.reduce, feats[-1])            # token map at TRANS_SIZE already
         feat, heat_single = p.first.run(r, x)                                # [S,h,w,d] fp16, [S,K,h,w] fp32
         tok = feat
         for _ in range(int(math.log(feat.shape[2] // self.trans_size[-1], 2))):   # interformer.py:260-264
@@ -131,7 +160,14 @@ class TwoStageInterFormer(DevicePathModule):
         for stack in p.upsample:
             for dc in stack:
                 y = dc.run(r, y)
-        y = r.add(feat, y)                                                   # single_res + x
+        if p.upconv is not None:
+            # UpConv: 1x1 + BN at the token resolution (commutes with the nearest up-sampling that follows it), then the
+            # first 3x3 reads the map through a >> shift gather, the second runs at the heatmap resolution
+            y = r.conv(p.upconv[0], y)
+            y = r.conv(p.upconv[1], y, in_shift=self._upconv_shift)
+            y = r.conv(p.upconv[2], y)
+        if feat is not None:
+            y = r.add(feat, y)                                               # single_res + x
         heat_multi = r.conv(p.head, y, out_mode="nchw32")
         if self.returns_dict:
             return {"single": heat_single, "multi": heat_multi}
@@ -143,8 +179,7 @@ def build(cfg, is_train, flavor, models_pkg):
     interformer.py:139 / interformer_2stage.py:428 do (`eval('models.' + cfg.MODEL.SINGLEFORMER + '.get_pose_net')`)."""
     name = cfg.MODEL.SINGLEFORMER
     if not name:
-        raise NotImplementedError("MODEL.SINGLEFORMER is empty: the stand-alone HRNet path (lib/models/hrnet.py) is "
-                                  "not referenced by any shipped config")
+        return TwoStageInterFormer(cfg, None, flavor)
     factory = getattr(getattr(models_pkg, name), "get_pose_net")
     single = factory(cfg, is_train, cfg.MODEL.SINGLE_MODEL, cfg.MODEL.END2END)
     return TwoStageInterFormer(cfg, single, flavor)

@@ -18,7 +18,7 @@ from i2r_b200.encoder import EncoderProgram
 from i2r_b200.hrnet_w48 import BackboneProgram, attach_backbone_params, conv_bn_layer
 from i2r_b200.ops import ConvLayer, Runner
 from i2r_b200.packing import deconv4x4s2_phase_taps, fold_bn
-from i2r_b200.position import MaskEmbedParams, MaskEmbedProgram, sine_table
+from i2r_b200.position import MaskEmbedParams, build_mask_embed_program, sine_table
 from i2r_b200.module_base import DevicePathModule
 from i2r_b200.modules import DeconvProgram, EncoderParams
 
@@ -73,8 +73,8 @@ class TransPoseH(DevicePathModule):
         device = torch.device(device) if device is not None else self.final_layer.weight.device
         sd = {k: v.detach().cpu() for k, v in self.state_dict().items()}
         c = self._cfg
-        if c["mode"] != "conv" and self.use_multi_pos:
-            raise NotImplementedError("MULTI_POS_EMBEDDING=%r (shipped configs use 'conv')" % c["mode"])
+        if c["mode"] not in ("conv", "res") and self.use_multi_pos:
+            raise NotImplementedError("MULTI_POS_EMBEDDING=%r (kernels exist for 'conv' and 'res')" % c["mode"])
         if c["final_k"] != 1:
             raise NotImplementedError("FINAL_CONV_KERNEL=3")
         prog = type("Program", (), {})()
@@ -82,7 +82,7 @@ class TransPoseH(DevicePathModule):
         prog.runner = self._runner_factory(device, 1 if self.check_impl else 0)
         prog.backbone = BackboneProgram(self, sd, device)
         prog.reduce = conv_bn_layer(sd, "reduce", None, device=device)
-        prog.mask_embed = MaskEmbedProgram(sd, "position_embedding", device) if self.use_multi_pos else None
+        prog.mask_embed = build_mask_embed_program(c["mode"], sd, "position_embedding", device) if self.use_multi_pos else None
         prog.encoder = EncoderProgram(sd, "global_encoder", c["layers"], c["d_model"], c["nhead"], device)
         prog.deconvs = [DeconvProgram(sd, "deconv_layers.%d" % (3 * i), "deconv_layers.%d" % (3 * i + 1), device)
                         for i in range(c["num_deconv"])]

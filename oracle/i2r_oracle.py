@@ -154,6 +154,31 @@ def mask_embedding_conv(sd, p, pos_mask5, trans_size):
     return x.reshape(bs, n, x.shape[-3], x.shape[-2], x.shape[-1])
 
 
+def mask_embedding_res(sd, p, pos_mask5, trans_size):
+    """PositionEmbeddingImage.forward, mode 'res' (lib/models/position_embedding.py:14-18, :90-108): conv_pre 3x3 (1 -> 3),
+    the first five children of torchvision resnet18 (conv1 7x7 s2 p3, bn1, relu, maxpool 3/2/1, layer1 = two BasicBlocks),
+    conv_end 3x3 (64 -> d), then max-pools down to TRANS_SIZE."""
+    bs, n, c, h, w = pos_mask5.shape
+    x = pos_mask5.reshape(bs * n, c, h, w)
+    x = _conv(sd, p + ".conv_pre", x)
+    x = F.relu(_bn(sd, p + ".res.1", F.conv2d(x, sd[p + ".res.0.weight"], None, 2, 3)))
+    x = F.max_pool2d(x, 3, 2, 1)
+    for b in (0, 1):
+        x = basic_block(sd, "%s.res.4.%d" % (p, b), x)
+    x = _conv(sd, p + ".conv_end", x)
+    for _ in range(int(math.log(x.shape[-1] // trans_size[-1], 2))):
+        x = F.max_pool2d(x, 3, 2, 1)
+    return x.reshape(bs, n, x.shape[-3], x.shape[-2], x.shape[-1])
+
+
+def mask_embedding(sd, p, pos_mask5, trans_size, mode):
+    if mode == "conv":
+        return mask_embedding_conv(sd, p, pos_mask5, trans_size)
+    if mode == "res":
+        return mask_embedding_res(sd, p, pos_mask5, trans_size)
+    raise NotImplementedError("MULTI_POS_EMBEDDING=%r" % mode)
+
+
 def mha_single_head(sd, p, q_in, k_in, v_in, key_padding_mask):
     """nn.MultiheadAttention(nhead=1) forward as torch implements it (torch/nn/functional.py
     multi_head_attention_forward): packed in_proj, q * head_dim**-0.5, -inf on padded keys, softmax,
@@ -209,7 +234,8 @@ def vanilla_forward(sd, cfg, x, pos_mask, length, taps=None):
     _, c, h, w = x.shape
     pos = None
     if m.USE_MULTI_POS:
-        pos5 = mask_embedding_conv(sd, "position_embedding", pad_persons(pos_mask, length), list(m.TRANS_SIZE))
+        pos5 = mask_embedding(sd, "position_embedding", pad_persons(pos_mask, length), list(m.TRANS_SIZE),
+                              m.MULTI_POS_EMBEDDING)
         if taps is not None:
             taps["pos"] = unpad_persons(pos5.reshape((bs * n_max,) + tuple(pos5.shape[2:])), length)
         pos = pos5.permute(0, 2, 1, 3, 4).flatten(2).permute(2, 0, 1)          # [N*h*w, bs, c]
@@ -385,20 +411,24 @@ def two_stage_forward(sd, cfg, x, pos_mask, length, taps=None):
         feat, single = transpose_h_first_stage(sd, cfg, x, "singleformer.")
     elif m.SINGLEFORMER == "hrformer":
         feat, single = hrformer_first_stage(sd, cfg, x, "singleformer.")
+    elif not m.SINGLEFORMER:
+        # stand-alone HRNet backbone (interformer.py:143, :291-292; lib/models/hrnet.py:413-446): token map directly
+        feat, single = None, None
+        t = F.conv2d(hrnet_w48s_backbone(sd, x, "backbone.body.")[-1], sd["backbone.body.reduce.weight"])
     else:
         raise NotImplementedError("oracle first stage %r" % m.SINGLEFORMER)
     if taps is not None:
         taps["feat"] = feat
-    t = feat
-    for _ in range(int(math.log(feat.shape[-1] // m.TRANS_SIZE[-1], 2))):      # interformer.py:260-264
-        t = F.max_pool2d(t, 3, 2, 1)
+    if feat is not None:
+        t = feat
+        for _ in range(int(math.log(feat.shape[-1] // m.TRANS_SIZE[-1], 2))):      # interformer.py:260-264
+            t = F.max_pool2d(t, 3, 2, 1)
     bs, n_max = len(length), max(length)
     _, c, h, w = t.shape
     pos = None
     if m.USE_MULTI_POS:
-        if m.MULTI_POS_EMBEDDING != "conv":
-            raise NotImplementedError("oracle MULTI_POS_EMBEDDING %r" % m.MULTI_POS_EMBEDDING)
-        pos5 = mask_embedding_conv(sd, "multi_position_embedding", pad_persons(pos_mask, length), list(m.TRANS_SIZE))
+        pos5 = mask_embedding(sd, "multi_position_embedding", pad_persons(pos_mask, length), list(m.TRANS_SIZE),
+                              m.MULTI_POS_EMBEDDING)
         pos = pos5.permute(0, 2, 1, 3, 4).flatten(2).permute(2, 0, 1)
     mask = person_mask(length, (h, w)).flatten(1)
     src = pad_persons(t, length).permute(0, 2, 1, 3, 4).flatten(2).permute(2, 0, 1)
@@ -417,11 +447,18 @@ def two_stage_forward(sd, cfg, x, pos_mask, length, taps=None):
         for i in range(steps):
             key = "deconv_layers%d" % (i + 1) if m.NAME == "interformer_2stage" else "upsample_layer.deconv_layers.%d" % i
             y = _deconv_block(sd, key, y, nl)
+    elif m.UPSAMPLE_TYPE == "upconv":      # interformer.py:25-64
+        u = "upsample_layer."
+        y = _bn(sd, u + "fuse_layers.1", _conv(sd, u + "fuse_layers.0", y))
+        y = F.interpolate(y, scale_factor=m.HEATMAP_SIZE[0] // m.TRANS_SIZE[1], mode="nearest")
+        y = F.relu(_bn(sd, u + "double_conv.1", _conv(sd, u + "double_conv.0", y)))
+        y = F.relu(_bn(sd, u + "double_conv.4", _conv(sd, u + "double_conv.3", y)))
     else:
         raise NotImplementedError("oracle UPSAMPLE_TYPE %r" % m.UPSAMPLE_TYPE)
-    y = feat + y
+    if feat is not None:
+        y = feat + y
     multi = F.conv2d(y, sd["final_layer.weight"], sd["final_layer.bias"])
-    if m.INTER_SUPERVISION and not m.SINGLEFORMER_FIX:
+    if m.INTER_SUPERVISION and m.SINGLEFORMER and not m.SINGLEFORMER_FIX:
         return {"single": single, "multi": multi}
     return multi
 

@@ -115,6 +115,13 @@ class EmuRunner(Runner):
         self.launches += 1
         return self._wr(F.relu(y).permute(0, 2, 3, 1).contiguous())
 
+    def mask_res_stem(self, mask, w_pre, w1, scale, bias):
+        pre = F.conv2d(mask, w_pre.reshape(3, 1, 3, 3), None, 1, 1)
+        y = F.conv2d(pre, w1.reshape(3, 7, 7, 64).permute(3, 0, 1, 2), None, 2, 3)
+        y = y * scale.view(1, -1, 1, 1) + bias.view(1, -1, 1, 1)
+        self.launches += 1
+        return self._wr(F.relu(y).permute(0, 2, 3, 1).contiguous())
+
     def maxpool(self, x):
         self.launches += 1
         return self._wr(F.max_pool2d(self._rd(x).permute(0, 3, 1, 2), 3, 2, 1).permute(0, 2, 3, 1).contiguous())

@@ -41,7 +41,12 @@ CASES = {
     "hrt_c4_rank": ("coco/interformer_coco_hrt_192_p2_b12.yaml", [8], 256, 192),
     "hrt_c5_rank": ("coco/interformer_coco_hrt_288_p2_b4.yaml", [12], 384, 288),
     "hrt_ragged3": ("coco/interformer_coco_hrt_192_p2_b12.yaml", [3, 1, 2], 256, 192),
+    # compat extras: no first stage (stand-alone HRNet backbone, lib/models/backbone.py) + UpConv upsampling
+    "hrnet_upconv_ragged": ("crowdpose/interformer_crowdpose_tph_192_p6_b4.yaml", [2, 1], 256, 192),
+    # `res` multi-person position embedding (resnet18 stem on the box masks), the shipped OCHuman TransPose-H config
+    "tph_ochuman_res_ragged": ("OCHuman/interformer_ochuman_tph_192_p3_b8.yaml", [1, 2], 256, 192),
 }
+OPTS = {"hrnet_upconv_ragged": ["MODEL.SINGLEFORMER", "", "MODEL.UPSAMPLE_TYPE", "upconv", "MODEL.INIT_WEIGHTS", False]}
 SUBSAMPLE = {"hrt_c4_rank": 4, "hrt_c5_rank": 4, "hrt_ragged3": 4}
 
 
@@ -52,16 +57,19 @@ def main():
     for name, (yaml_rel, length, h, w) in CASES.items():
         if len(sys.argv) > 1 and name not in sys.argv[1:]:
             continue
-        if yaml_rel not in models:
-            cfg, model = ref_harness.build_reference_model(yaml_rel)
+        mkey = (yaml_rel, name if name in OPTS else "")
+        if mkey not in models:
+            cfg, model = ref_harness.build_reference_model(yaml_rel, OPTS.get(name, ()))
             sd = synth_state_dict(model.state_dict(), seed=0)
             model.load_state_dict(sd, strict=True)
-            models[yaml_rel] = model
+            models[mkey] = model
             keys = {k: [list(v.shape), str(v.dtype).replace("torch.", "")] for k, v in model.state_dict().items()}
             tag = cfg.MODEL.NAME if cfg.MODEL.NAME == "interformer_pureMulti" else os.path.basename(yaml_rel)[:-5]
+            if name in OPTS:
+                tag = name
             with open(os.path.join(HERE, "state_dict_%s.json" % tag), "w") as f:
                 json.dump(keys, f, indent=0, sort_keys=True)
-        model = models[yaml_rel]
+        model = models[mkey]
         x, pm = synth_inputs(sum(length), h, w, seed=1)
         taps = {}
         hooks = []

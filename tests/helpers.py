@@ -12,10 +12,10 @@ GOLDEN = os.path.join(paths.REPO, "tests", "golden")
 VANILLA_YAML = "coco/interformer_coco_w48_pure_en6.yaml"
 
 
-def build_model(yaml_rel=VANILLA_YAML, seed=0):
+def build_model(yaml_rel=VANILLA_YAML, seed=0, opts=()):
     """Drop-in module with synthetic weights (same weights the golden files were generated with)."""
     import models  # the repo's lib/models
-    cfg = load_experiment(yaml_rel)
+    cfg = load_experiment(yaml_rel, opts)
     torch.manual_seed(0)
     model = eval("models." + cfg.MODEL.NAME + ".get_pose_net")(cfg, is_train=False)
     sd = synth_state_dict(model.state_dict(), seed=seed)
