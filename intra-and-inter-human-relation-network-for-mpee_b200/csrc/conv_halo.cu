@@ -749,6 +749,143 @@ __device__ __forceinline__ void epilogue_fast(const EpiArgs E, const int cta, co
   so.finish();
 }
 
+// Hot epilogue of the split-operand models (pair tensors: hi | lo): the same compile-time-unrolled structure as
+// epilogue_fast, with pair addends, hi = fp16(v), lo = fp16(v - hi) and the activation fixed at compile time
+// (ACT 0: clamp = ReLU / none, 1: erf-GELU after the addends, 2: erf-GELU before the addends).  The generic epilogue
+// re-tests flags per element and calls the activation out of line: 7.9 k cycles per 128 x 96 tile, 49 k for a 128 x 256
+// GELU tile (profiles/r02_epilogue_warps.txt) against < 1 k cycles of MMA.
+template <int G, int NADD, int ACT>
+__device__ __forceinline__ void epilogue_split_fast(const EpiArgs E, const int cta, const uint32_t sbase,
+                                                    const uint32_t tmem_base, const uint32_t ncols, const int cb, const int ce,
+                                                    const int ew, const int quad, const int lane, unsigned long long* tr,
+                                                    const int trcap) {
+  const uint32_t bar_accfull = sbase + 128, bar_accempty = sbase + 144;
+  const int row = quad * 32 + lane;
+  const int ty_in = row >> 3, tx_in = row & 7;
+  const float lo = (E.flags & I2R_F_RELU) ? 0.0f : -3.0e38f;
+  const float inv_tpi = 1.0f / static_cast<float>(E.tiles_per_img), inv_tx = 1.0f / static_cast<float>(E.tiles_x);
+  __half* const ybase = reinterpret_cast<__half*>(E.y);
+  const uint32_t lane_taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
+  int acc = 0, tri = 0;
+  uint32_t accph = 0;
+  StageOut so;
+  so.on = E.o_bufs > 0;
+  so.issuer = ew == 0 && lane == 0;
+  so.nbuf = E.o_bufs;
+  so.b = 0;
+  so.buf_addr = 0;
+  const uint32_t srow = static_cast<uint32_t>(row) * static_cast<uint32_t>(E.Cout) * 2u;
+  for (int tp = cta; tp < E.ntiles; tp += E.cta_count) {
+    const int t = E.pair ? 2 * tp + E.rank : tp;
+    const int n = __float2int_rd((static_cast<float>(t) + 0.5f) * inv_tpi);
+    const int r = t - n * E.tiles_per_img;
+    const int ty = __float2int_rd((static_cast<float>(r) + 0.5f) * inv_tx);
+    const int tx = r - ty * E.tiles_x;
+    const int x = tx * T_TW + tx_in, y = ty * T_TH + ty_in;
+    const bool valid = (x < E.W) && (y < E.H) && (t < E.ntiles_real);
+    const int p = (n * E.H + y) * E.W + x;
+    const uint32_t taddr = lane_taddr + static_cast<uint32_t>(acc) * (ncols >> 1);
+    const __half* a0 = E.add0 + static_cast<int64_t>(p) * E.add_pix_stride;
+    const __half* a1 = E.add1 + static_cast<int64_t>(p) * E.add_pix_stride;
+    __half* yp = ybase + static_cast<int64_t>(p) * E.out_pix_stride;
+    so.begin_tile(E);
+    for (int c = cb; c < ce; c += G) {
+      uint4 r0[G], r1[G], l0[G], l1[G];
+#pragma unroll
+      for (int j = 0; j < G; ++j) {
+        r0[j] = l0[j] = r1[j] = l1[j] = make_uint4(0, 0, 0, 0);
+        if (NADD >= 1 && valid) {
+          r0[j] = __ldg(reinterpret_cast<const uint4*>(a0 + (c + j) * 8));
+          l0[j] = __ldg(reinterpret_cast<const uint4*>(a0 + E.lo_off + (c + j) * 8));
+        }
+        if (NADD >= 2 && valid) {
+          r1[j] = __ldg(reinterpret_cast<const uint4*>(a1 + (c + j) * 8));
+          l1[j] = __ldg(reinterpret_cast<const uint4*>(a1 + E.lo_off + (c + j) * 8));
+        }
+      }
+      if (c == cb) {
+        mbar_wait(bar_accfull + 8 * acc, accph);
+        tc_fence_after();
+        if (ew == 0 && lane == 0) trace_ev(tr, trcap, 2, tri, 20, t);
+      }
+      uint32_t av[G][8];
+#pragma unroll
+      for (int j = 0; j < G; ++j) tmem_ld8(taddr + (c + j) * 8, av[j]);
+      tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < G; ++j) {
+        const uint32_t q0[4] = {r0[j].x, r0[j].y, r0[j].z, r0[j].w};
+        const uint32_t q1[4] = {r1[j].x, r1[j].y, r1[j].z, r1[j].w};
+        const uint32_t p0[4] = {l0[j].x, l0[j].y, l0[j].z, l0[j].w};
+        const uint32_t p1[4] = {l1[j].x, l1[j].y, l1[j].z, l1[j].w};
+        uint32_t oh[4], ol[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          float va = __uint_as_float(av[j][2 * i]), vb = __uint_as_float(av[j][2 * i + 1]);
+          float ax = 0.f, ay = 0.f;
+          if (NADD >= 1) {
+            const float2 f0 = unpack_h2(q0[i]), g0 = unpack_h2(p0[i]);
+            ax = f0.x + g0.x;
+            ay = f0.y + g0.y;
+          }
+          if (NADD >= 2) {
+            const float2 f1 = unpack_h2(q1[i]), g1 = unpack_h2(p1[i]);
+            ax += f1.x + g1.x;
+            ay += f1.y + g1.y;
+          }
+          if (ACT == 2) {
+            va = gelu_erf(va) + ax;
+            vb = gelu_erf(vb) + ay;
+          } else if (ACT == 1) {
+            va = gelu_erf(va + ax);
+            vb = gelu_erf(vb + ay);
+          } else {
+            va = fmaxf(va + ax, lo);
+            vb = fmaxf(vb + ay, lo);
+          }
+          oh[i] = pack_h2(va, vb);
+          const float2 h = unpack_h2(oh[i]);
+          ol[i] = pack_h2(va - h.x, vb - h.y);
+        }
+        if (so.on) {
+          st_shared_v4(so.buf_addr + srow + (c + j) * 16, oh[0], oh[1], oh[2], oh[3]);
+          st_shared_v4(so.buf_addr + E.o_tile_bytes + srow + (c + j) * 16, ol[0], ol[1], ol[2], ol[3]);
+        } else if (valid) {
+          *reinterpret_cast<uint4*>(yp + (c + j) * 8) = make_uint4(oh[0], oh[1], oh[2], oh[3]);
+          *reinterpret_cast<uint4*>(yp + E.lo_off + (c + j) * 8) = make_uint4(ol[0], ol[1], ol[2], ol[3]);
+        }
+      }
+    }
+    if (ew == 0 && lane == 0) trace_ev(tr, trcap, 2, tri, 23, t);
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) arrive_accempty(E, bar_accempty + 8 * acc);
+    so.end_tile(E, tx * T_TW, ty * T_TH, n, t < E.ntiles_real);
+    if (ew == 0 && lane == 0) trace_ev(tr, trcap, 2, tri, 21, t);
+    acc ^= 1;
+    if (acc == 0) accph ^= 1;
+  }
+  so.finish();
+}
+
+template <int NADD, int ACT>
+__device__ __forceinline__ void epilogue_split_dispatch(const EpiArgs& E, const int cta, const uint32_t sbase,
+                                                        const uint32_t tmem_base, const uint32_t ncols, const int cb,
+                                                        const int ce, const int ew, const int quad, const int lane,
+                                                        unsigned long long* tr, const int trcap) {
+  if ((ce - cb) % 2 == 0) epilogue_split_fast<2, NADD, ACT>(E, cta, sbase, tmem_base, ncols, cb, ce, ew, quad, lane, tr, trcap);
+  else epilogue_split_fast<1, NADD, ACT>(E, cta, sbase, tmem_base, ncols, cb, ce, ew, quad, lane, tr, trcap);
+}
+template <int ACT>
+__device__ __forceinline__ void epilogue_split_dispatch_nadd(const EpiArgs& E, const int cta, const uint32_t sbase,
+                                                             const uint32_t tmem_base, const uint32_t ncols, const int cb,
+                                                             const int ce, const int ew, const int quad, const int lane,
+                                                             unsigned long long* tr, const int trcap) {
+  if (E.add1 != nullptr) epilogue_split_dispatch<2, ACT>(E, cta, sbase, tmem_base, ncols, cb, ce, ew, quad, lane, tr, trcap);
+  else if (E.add0 != nullptr) epilogue_split_dispatch<1, ACT>(E, cta, sbase, tmem_base, ncols, cb, ce, ew, quad, lane, tr, trcap);
+  else epilogue_split_dispatch<0, ACT>(E, cta, sbase, tmem_base, ncols, cb, ce, ew, quad, lane, tr, trcap);
+}
+
 template <int NADD>
 __device__ __forceinline__ void epilogue_fast_dispatch(const EpiArgs& E, const int cta, const uint32_t sbase,
                                                        const uint32_t tmem_base, const uint32_t ncols, const int cb,
@@ -972,9 +1109,18 @@ __global__ void __launch_bounds__(T_THREADS, 1) conv_halo_kernel(const __grid_co
     // chunks holding real channels, split over the warps of a lane quadrant
     const int n8 = (P.Cout + 7) >> 3, part8 = (n8 + (T_EPI_WARPS / 4) - 1) / (T_EPI_WARPS / 4);
     const int cb = min(n8, (ew >> 2) * part8), ce = min(n8, cb + part8);
-    if ((P.flags & (I2R_F_OUT_NCHW_F32 | I2R_F_OUT_F32 | I2R_F_SPLIT | I2R_F_OUT_T16 | I2R_F_GELU | I2R_F_ACT_FIRST)) ||
-        (P.Cout & 7) || dbg != 0 ||
-        ce == cb) {
+    const bool plain_out = !(P.flags & (I2R_F_OUT_NCHW_F32 | I2R_F_OUT_F32 | I2R_F_OUT_T16)) && !(P.Cout & 7) && dbg == 0 &&
+                           ce != cb;
+    if (plain_out && (P.flags & I2R_F_SPLIT) && (!(P.flags & I2R_F_ACT_FIRST) || (P.flags & I2R_F_GELU))) {
+      // split-operand hot path (pair tensors), activation fixed at compile time
+      if (!(P.flags & I2R_F_GELU))
+        epilogue_split_dispatch_nadd<0>(E, cta, sbase, tmem_base, ncols, cb, ce, ew, warp & 3, lane, tr, trace_cap);
+      else if (P.flags & I2R_F_ACT_FIRST)
+        epilogue_split_dispatch_nadd<2>(E, cta, sbase, tmem_base, ncols, cb, ce, ew, warp & 3, lane, tr, trace_cap);
+      else
+        epilogue_split_dispatch_nadd<1>(E, cta, sbase, tmem_base, ncols, cb, ce, ew, warp & 3, lane, tr, trace_cap);
+    } else if ((P.flags & (I2R_F_OUT_NCHW_F32 | I2R_F_OUT_F32 | I2R_F_SPLIT | I2R_F_OUT_T16 | I2R_F_GELU | I2R_F_ACT_FIRST)) ||
+               (P.Cout & 7) || dbg != 0 || ce == cb) {
       epilogue_role<1>(E, cta, sbase, tmem_base, ncols, Npad, ew, warp & 3, lane, tr, trace_cap, dbg);
     } else if (P.add1 != nullptr) {
       epilogue_fast_dispatch<2>(E, cta, sbase, tmem_base, ncols, cb, ce, ew, warp & 3, lane, tr, trace_cap);

@@ -76,38 +76,107 @@ __global__ void __launch_bounds__(256) dwconv3x3_kernel(const __half* __restrict
     const int ox = static_cast<int>(p % OW);
     const int oy = static_cast<int>((p / OW) % OH);
     const int n = static_cast<int>(p / (static_cast<int64_t>(OW) * OH));
-    // all nine taps are fetched before the first FMA (18 independent 16-byte loads in flight per thread in pair mode:
-    // the kernel is latency bound otherwise -- border tests inside the FMA chain serialised load, use, load, use)
-    uint4 hi[9], lo[9];
+    float acc[8];
 #pragma unroll
-    for (int t = 0; t < 9; ++t) {
-      const int iy = oy * stride - 1 + t / 3, ix = ox * stride - 1 + t % 3;
-      const bool ok = iy >= 0 && iy < H && ix >= 0 && ix < W;
-      const __half* src = x + ((static_cast<int64_t>(n) * H + (ok ? iy : 0)) * W + (ok ? ix : 0)) * ld + c;
-      hi[t] = ok ? __ldg(reinterpret_cast<const uint4*>(src)) : make_uint4(0, 0, 0, 0);
-      if (PAIR) lo[t] = ok ? __ldg(reinterpret_cast<const uint4*>(src + C)) : make_uint4(0, 0, 0, 0);
+    for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky) {
+      const int iy = oy * stride - 1 + ky;
+      if (iy < 0 || iy >= H) continue;
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx) {
+        const int ix = ox * stride - 1 + kx;
+        if (ix < 0 || ix >= W) continue;
+        float v[8];
+        hk_load<PAIR>(x + ((static_cast<int64_t>(n) * H + iy) * W + ix) * ld, C, c, v);
+        const float4 w0 = __ldg(reinterpret_cast<const float4*>(w + (ky * 3 + kx) * C + c));
+        const float4 w1 = __ldg(reinterpret_cast<const float4*>(w + (ky * 3 + kx) * C + c + 4));
+        acc[0] = fmaf(v[0], w0.x, acc[0]);
+        acc[1] = fmaf(v[1], w0.y, acc[1]);
+        acc[2] = fmaf(v[2], w0.z, acc[2]);
+        acc[3] = fmaf(v[3], w0.w, acc[3]);
+        acc[4] = fmaf(v[4], w1.x, acc[4]);
+        acc[5] = fmaf(v[5], w1.y, acc[5]);
+        acc[6] = fmaf(v[6], w1.z, acc[6]);
+        acc[7] = fmaf(v[7], w1.w, acc[7]);
+      }
     }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = hk_act(fmaf(acc[i], __ldg(scale + c + i), __ldg(bias + c + i)), act);
+    hk_store<PAIR>(y + p * ld, C, c, acc);
+  }
+}
+
+// Stride-1 variant with a shared-memory halo patch: CTA = 8 x 8 output pixels x 64 channels.  The (10 x 10 pixel) patch is
+// loaded once (1.56x the tile instead of the 9x re-reads of the kernel above, which made the 320-channel MlpDWBN layer of
+// HRFormer's highest-resolution branch run at 1.2 TB/s of L2 traffic), weights of the 64 channels sit in shared memory.
+constexpr int DW_T = 8, DW_P = DW_T + 2, DW_CB = 64;
+template <bool PAIR>
+__global__ void __launch_bounds__(256) dwconv3x3_tile_kernel(const __half* __restrict__ x, const float* __restrict__ w,
+                                                             const float* __restrict__ scale,
+                                                             const float* __restrict__ bias, __half* __restrict__ y, int NB,
+                                                             int H, int W, int C, int act) {
+  __shared__ __align__(16) __half patch[(PAIR ? 2 : 1) * DW_P * DW_P * DW_CB];
+  __shared__ __align__(16) float sw[9 * DW_CB];
+  pdl_launch_dependents();
+  const int tid = threadIdx.x;
+  const int cblocks = C / DW_CB;
+  const int tiles_x = (W + DW_T - 1) / DW_T, tiles_y = (H + DW_T - 1) / DW_T;
+  int b = blockIdx.x;
+  const int cb = b % cblocks;
+  b /= cblocks;
+  const int tx = b % tiles_x;
+  b /= tiles_x;
+  const int ty = b % tiles_y;
+  const int n = b / tiles_y;
+  const int c0 = cb * DW_CB;
+  const int ld = PAIR ? 2 * C : C;
+  for (int i = tid; i < 9 * DW_CB; i += 256) sw[i] = __ldg(w + (i / DW_CB) * C + c0 + (i % DW_CB));
+  pdl_wait();
+  // patch[half][py][px][64 ch]: 8 chunks of 16 bytes per pixel and half
+  constexpr int CHUNKS = DW_P * DW_P * (DW_CB / 8);
+  for (int i = tid; i < CHUNKS * (PAIR ? 2 : 1); i += 256) {
+    const int half = i / CHUNKS, j = i - half * CHUNKS;
+    const int g = j % (DW_CB / 8), pp = j / (DW_CB / 8);
+    const int iy = ty * DW_T - 1 + pp / DW_P, ix = tx * DW_T - 1 + pp % DW_P;
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (iy >= 0 && iy < H && ix >= 0 && ix < W)
+      v = __ldg(reinterpret_cast<const uint4*>(x + ((static_cast<int64_t>(n) * H + iy) * W + ix) * ld + half * C + c0 + g * 8));
+    *reinterpret_cast<uint4*>(patch + (half * DW_P * DW_P + pp) * DW_CB + g * 8) = v;
+  }
+  __syncthreads();
+  for (int it = tid; it < DW_T * DW_T * (DW_CB / 8); it += 256) {
+    const int g = it % (DW_CB / 8), pp = it / (DW_CB / 8);
+    const int oy = pp / DW_T, ox = pp % DW_T;
+    const int gy = ty * DW_T + oy, gx = tx * DW_T + ox;
+    if (gy >= H || gx >= W) continue;
     float acc[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) acc[i] = 0.f;
 #pragma unroll
     for (int t = 0; t < 9; ++t) {
-      const uint32_t hw4[4] = {hi[t].x, hi[t].y, hi[t].z, hi[t].w};
-      const uint32_t lw4[4] = {lo[t].x, lo[t].y, lo[t].z, lo[t].w};
+      const int pi = (oy + t / 3) * DW_P + ox + t % 3;
+      const uint4 hq = *reinterpret_cast<const uint4*>(patch + pi * DW_CB + g * 8);
+      const uint32_t hw4[4] = {hq.x, hq.y, hq.z, hq.w};
       float v[8];
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         const float2 f = unpack_h2(hw4[i]);
         v[2 * i] = f.x;
         v[2 * i + 1] = f.y;
-        if (PAIR) {
-          const float2 g = unpack_h2(lw4[i]);
-          v[2 * i] += g.x;
-          v[2 * i + 1] += g.y;
+      }
+      if (PAIR) {
+        const uint4 lq = *reinterpret_cast<const uint4*>(patch + (DW_P * DW_P + pi) * DW_CB + g * 8);
+        const uint32_t lw4[4] = {lq.x, lq.y, lq.z, lq.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float2 f = unpack_h2(lw4[i]);
+          v[2 * i] += f.x;
+          v[2 * i + 1] += f.y;
         }
       }
-      const float4 w0 = __ldg(reinterpret_cast<const float4*>(w + t * C + c));
-      const float4 w1 = __ldg(reinterpret_cast<const float4*>(w + t * C + c + 4));
+      const float4 w0 = *reinterpret_cast<const float4*>(sw + t * DW_CB + g * 8);
+      const float4 w1 = *reinterpret_cast<const float4*>(sw + t * DW_CB + g * 8 + 4);
       acc[0] = fmaf(v[0], w0.x, acc[0]);
       acc[1] = fmaf(v[1], w0.y, acc[1]);
       acc[2] = fmaf(v[2], w0.z, acc[2]);
@@ -117,9 +186,10 @@ __global__ void __launch_bounds__(256) dwconv3x3_kernel(const __half* __restrict
       acc[6] = fmaf(v[6], w1.z, acc[6]);
       acc[7] = fmaf(v[7], w1.w, acc[7]);
     }
+    const int c = c0 + g * 8;
 #pragma unroll
     for (int i = 0; i < 8; ++i) acc[i] = hk_act(fmaf(acc[i], __ldg(scale + c + i), __ldg(bias + c + i)), act);
-    hk_store<PAIR>(y + p * ld, C, c, acc);
+    hk_store<PAIR>(y + ((static_cast<int64_t>(n) * H + gy) * W + gx) * ld, C, c, acc);
   }
 }
 
@@ -183,23 +253,24 @@ __global__ void __launch_bounds__(256) upsum_bilinear_kernel(const __half* __res
 
 // ------------------------------------------------------------------------------------------------ padded LayerNorm
 // one warp per row; lane handles the 8-channel groups lane, lane + 32, lane + 64 (C_pad <= 768)
-template <bool PAIR>
+template <bool PAIR, int LPR>
 __global__ void __launch_bounds__(256) layernorm_padded_kernel(const __half* __restrict__ x,
                                                                const float* __restrict__ gamma,
                                                                const float* __restrict__ beta, __half* __restrict__ y,
                                                                int rows, int Cr, int Cp, float eps) {
   pdl_launch_dependents();
   pdl_wait();
-  const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
-  if (row >= rows) return;
+  const int row_raw = (blockIdx.x * blockDim.x + threadIdx.x) / LPR;
+  const int lane = threadIdx.x % LPR;      // LPR lanes share a row (16 for rows of <= 128 channels: two rows per warp)
+  const bool live = row_raw < rows;        // no early return: the full-mask shuffles below need every lane of the warp
+  const int row = live ? row_raw : rows - 1;
   const int64_t ld = PAIR ? 2 * Cp : Cp;
   const __half* xr = x + row * ld;
   float v[3][8];
   float s = 0.f;
 #pragma unroll
   for (int g = 0; g < 3; ++g) {
-    const int c = (lane + 32 * g) * 8;
+    const int c = (lane + LPR * g) * 8;
 #pragma unroll
     for (int i = 0; i < 8; ++i) v[g][i] = 0.f;
     if (c < Cp) {
@@ -212,12 +283,12 @@ __global__ void __launch_bounds__(256) layernorm_padded_kernel(const __half* __r
     }
   }
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  for (int o = LPR / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
   const float mean = s / Cr;
   float sq = 0.f;
 #pragma unroll
   for (int g = 0; g < 3; ++g) {
-    const int c = (lane + 32 * g) * 8;
+    const int c = (lane + LPR * g) * 8;
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       if (c + i < Cr) {
@@ -227,17 +298,17 @@ __global__ void __launch_bounds__(256) layernorm_padded_kernel(const __half* __r
     }
   }
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+  for (int o = LPR / 2; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
   const float rstd = rsqrtf(sq / Cr + eps);
 #pragma unroll
   for (int g = 0; g < 3; ++g) {
-    const int c = (lane + 32 * g) * 8;
+    const int c = (lane + LPR * g) * 8;
     if (c < Cp) {
       float o8[8];
 #pragma unroll
       for (int i = 0; i < 8; ++i)
         o8[i] = (c + i < Cr) ? (v[g][i] - mean) * rstd * __ldg(gamma + c + i) + __ldg(beta + c + i) : 0.f;
-      hk_store<PAIR>(y + row * ld, Cp, c, o8);
+      if (live) hk_store<PAIR>(y + row * ld, Cp, c, o8);
     }
   }
 }
@@ -247,7 +318,7 @@ __global__ void __launch_bounds__(256) layernorm_padded_kernel(const __half* __r
 // with zeros to multiples of ws, cut into ws x ws windows; output row = ((n * QH + qh) * QW + qw) * ws*ws + ph * ws + pw.
 // ln_window_gather = LayerNorm (first C_real of C_pad channels) of every pixel written at its window row; rows of padded
 // positions are zero (the reference pads AFTER norm1, so their q/k/v are the projection biases).
-template <bool PAIR>
+template <bool PAIR, int LPR>
 __global__ void __launch_bounds__(256) ln_window_gather_kernel(const __half* __restrict__ x,
                                                                const float* __restrict__ gamma,
                                                                const float* __restrict__ beta, __half* __restrict__ y,
@@ -258,9 +329,10 @@ __global__ void __launch_bounds__(256) ln_window_gather_kernel(const __half* __r
   const int pt = (Hp - H) / 2, pl = (Wp - W) / 2;
   const int QH = Hp / ws, QW = Wp / ws;
   const int64_t rows = static_cast<int64_t>(NB) * Hp * Wp;
-  const int64_t row = (blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
-  if (row >= rows) return;
+  const int64_t row_raw = (blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x) / LPR;
+  const int lane = threadIdx.x % LPR;      // LPR lanes share a row (16 for rows of <= 128 channels: two rows per warp)
+  const bool live = row_raw < rows;        // no early return: the full-mask shuffles below need every lane of the warp
+  const int64_t row = live ? row_raw : rows - 1;
   const int pos = static_cast<int>(row % (ws * ws));
   const int64_t win = row / (ws * ws);
   const int qw = static_cast<int>(win % QW), qh = static_cast<int>((win / QW) % QH);
@@ -274,7 +346,7 @@ __global__ void __launch_bounds__(256) ln_window_gather_kernel(const __half* __r
   float s = 0.f;
 #pragma unroll
   for (int g = 0; g < 3; ++g) {
-    const int c = (lane + 32 * g) * 8;
+    const int c = (lane + LPR * g) * 8;
 #pragma unroll
     for (int i = 0; i < 8; ++i) v[g][i] = 0.f;
     if (c < Cp && inside) {
@@ -287,12 +359,12 @@ __global__ void __launch_bounds__(256) ln_window_gather_kernel(const __half* __r
     }
   }
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  for (int o = LPR / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
   const float mean = s / Cr;
   float sq = 0.f;
 #pragma unroll
   for (int g = 0; g < 3; ++g) {
-    const int c = (lane + 32 * g) * 8;
+    const int c = (lane + LPR * g) * 8;
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       if (c + i < Cr) {
@@ -302,17 +374,17 @@ __global__ void __launch_bounds__(256) ln_window_gather_kernel(const __half* __r
     }
   }
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+  for (int o = LPR / 2; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
   const float rstd = rsqrtf(sq / Cr + eps);
 #pragma unroll
   for (int g = 0; g < 3; ++g) {
-    const int c = (lane + 32 * g) * 8;
+    const int c = (lane + LPR * g) * 8;
     if (c < Cp) {
       float o8[8];
 #pragma unroll
       for (int i = 0; i < 8; ++i)
         o8[i] = (inside && c + i < Cr) ? (v[g][i] - mean) * rstd * __ldg(gamma + c + i) + __ldg(beta + c + i) : 0.f;
-      hk_store<PAIR>(yr, Cp, c, o8);
+      if (live) hk_store<PAIR>(yr, Cp, c, o8);
     }
   }
 }
@@ -362,6 +434,18 @@ extern "C" int i2r_dwconv3x3(const void* x, const float* w, const float* scale, 
   const int OH = (H + stride - 1) / stride, OW = (W + stride - 1) / stride;
   const int64_t items = static_cast<int64_t>(NB) * OH * OW * (C / 8);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (stride == 1 && C % DW_CB == 0) {      // shared-memory tiled variant
+    const int64_t ctas = static_cast<int64_t>(NB) * ((H + DW_T - 1) / DW_T) * ((W + DW_T - 1) / DW_T) * (C / DW_CB);
+    if (ctas < (1ll << 31)) {
+      if (split)
+        launch_pdl(dwconv3x3_tile_kernel<true>, dim3(static_cast<unsigned>(ctas)), dim3(256), 0, st,
+                   static_cast<const __half*>(x), w, scale, bias, static_cast<__half*>(y), NB, H, W, C, act);
+      else
+        launch_pdl(dwconv3x3_tile_kernel<false>, dim3(static_cast<unsigned>(ctas)), dim3(256), 0, st,
+                   static_cast<const __half*>(x), w, scale, bias, static_cast<__half*>(y), NB, H, W, C, act);
+      return check_launch("dwconv3x3_tile_kernel");
+    }
+  }
   if (split) {
     launch_pdl(dwconv3x3_kernel<true>, dim3(hk_grid(items, 256)), dim3(256), 0, st, static_cast<const __half*>(x), w,
                scale, bias, static_cast<__half*>(y), NB, H, W, C, stride, act);
@@ -400,14 +484,18 @@ extern "C" int i2r_layernorm_padded(const void* x, const float* gamma, const flo
     set_error("i2r_layernorm_padded: bad arguments (rows=%d C_real=%d C_pad=%d)", rows, C_real, C_pad);
     return I2R_E_BADARG;
   }
-  const int wpb = 8;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const bool narrow = C_pad <= 128;      // 16 lanes per row: two rows per warp
+  const int rpb = narrow ? 16 : 8;       // rows per 256-thread block
+  const dim3 grid((rows + rpb - 1) / rpb);
+  const __half* xs = static_cast<const __half*>(x);
+  __half* ys = static_cast<__half*>(y);
   if (split) {
-    launch_pdl(layernorm_padded_kernel<true>, dim3((rows + wpb - 1) / wpb), dim3(wpb * 32), 0, st,
-               static_cast<const __half*>(x), gamma, beta, static_cast<__half*>(y), rows, C_real, C_pad, eps);
+    if (narrow) launch_pdl(layernorm_padded_kernel<true, 16>, grid, dim3(256), 0, st, xs, gamma, beta, ys, rows, C_real, C_pad, eps);
+    else launch_pdl(layernorm_padded_kernel<true, 32>, grid, dim3(256), 0, st, xs, gamma, beta, ys, rows, C_real, C_pad, eps);
   } else {
-    launch_pdl(layernorm_padded_kernel<false>, dim3((rows + wpb - 1) / wpb), dim3(wpb * 32), 0, st,
-               static_cast<const __half*>(x), gamma, beta, static_cast<__half*>(y), rows, C_real, C_pad, eps);
+    if (narrow) launch_pdl(layernorm_padded_kernel<false, 16>, grid, dim3(256), 0, st, xs, gamma, beta, ys, rows, C_real, C_pad, eps);
+    else launch_pdl(layernorm_padded_kernel<false, 32>, grid, dim3(256), 0, st, xs, gamma, beta, ys, rows, C_real, C_pad, eps);
   }
   return check_launch("layernorm_padded_kernel");
 }
@@ -425,15 +513,18 @@ extern "C" int i2r_ln_window_gather(const void* x, const float* gamma, const flo
     return I2R_E_BADARG;
   }
   const int64_t rows = i2r_window_rows(NB, H, W, ws);
-  const int wpb = 8;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  const dim3 grid(static_cast<unsigned>((rows + wpb - 1) / wpb));
+  const bool narrow = C_pad <= 128;      // 16 lanes per row: two rows per warp
+  const int rpb = narrow ? 16 : 8;
+  const dim3 grid(static_cast<unsigned>((rows + rpb - 1) / rpb));
+  const __half* xs = static_cast<const __half*>(x);
+  __half* ys = static_cast<__half*>(y);
   if (split) {
-    launch_pdl(ln_window_gather_kernel<true>, grid, dim3(wpb * 32), 0, st, static_cast<const __half*>(x), gamma, beta,
-               static_cast<__half*>(y), NB, H, W, C_real, C_pad, ws, eps);
+    if (narrow) launch_pdl(ln_window_gather_kernel<true, 16>, grid, dim3(256), 0, st, xs, gamma, beta, ys, NB, H, W, C_real, C_pad, ws, eps);
+    else launch_pdl(ln_window_gather_kernel<true, 32>, grid, dim3(256), 0, st, xs, gamma, beta, ys, NB, H, W, C_real, C_pad, ws, eps);
   } else {
-    launch_pdl(ln_window_gather_kernel<false>, grid, dim3(wpb * 32), 0, st, static_cast<const __half*>(x), gamma, beta,
-               static_cast<__half*>(y), NB, H, W, C_real, C_pad, ws, eps);
+    if (narrow) launch_pdl(ln_window_gather_kernel<false, 16>, grid, dim3(256), 0, st, xs, gamma, beta, ys, NB, H, W, C_real, C_pad, ws, eps);
+    else launch_pdl(ln_window_gather_kernel<false, 32>, grid, dim3(256), 0, st, xs, gamma, beta, ys, NB, H, W, C_real, C_pad, ws, eps);
   }
   return check_launch("ln_window_gather_kernel");
 }
