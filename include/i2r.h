@@ -19,6 +19,7 @@
 #ifndef I2R_H_
 #define I2R_H_
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -33,6 +34,8 @@ extern "C" {
 
 #define I2R_MAX_TAPS 9
 #define I2R_MAX_GROUP 6
+#define I2R_MAX_CHAIN_PROBLEMS 40 /* problems of one chained halo launch (all layers together) */
+#define I2R_MAX_CHAIN_LAYERS 16
 
 /* i2r_conv_problem::flags */
 #define I2R_F_RELU 1u        /* clamp at 0 after scale/bias/addends                         */
@@ -114,6 +117,22 @@ int i2r_conv_igemm(const i2r_conv_problem* probs, int nprob, int impl, void* str
  * others go through i2r_conv_igemm. */
 int i2r_conv_halo_supported(const i2r_conv_problem* prob);
 int i2r_conv_halo(const i2r_conv_problem* probs, int nprob, void* stream);
+
+/* CHAINED launch: `nlayers` groups of problems (layer l = probs[sum(layer_count[:l]) ..][layer_count[l]], each group what
+ * one i2r_conv_halo call would take) that would otherwise be `nlayers` back-to-back launches -- the conv1 / conv2 (+
+ * residual) sequence of the BasicBlocks of an HRNet module (interformer_pureMulti.py:37-66, :284-330), the 1x1 / 3x3 / 1x1
+ * sequence of the layer1 Bottlenecks (:69-107) -- run as ONE persistent grid.  Every CTA walks the layers in order; a tile
+ * of a later layer starts as soon as the tiles it reads (the same IMAGE of the producing problems, found by address-range
+ * overlap of inputs / addends with earlier outputs) have been stored, which the producers publish through per-image
+ * pixel counters in `workspace` (device memory, >= i2r_conv_halo_chain_workspace(...) bytes, zeroed by this call on
+ * `stream`).  No grid-wide barrier, no launch gap, one prologue per chain.
+ * Requirements beyond i2r_conv_halo's: no CTA-pair problems, fp16 NHWC outputs, a
+ * layer's outputs must not alias anything an earlier layer of the chain reads or writes, and at most ONE chained launch
+ * may be in flight on a device at a time (CTAs of the grid wait for each other: issue chains on one stream).
+ * Returns I2R_E_UNSUPPORTED (nothing launched) when the chain does not qualify -- launch the layers one by one then. */
+int i2r_conv_halo_chain(const i2r_conv_problem* probs, const int* layer_count, int nlayers, void* workspace,
+                        size_t workspace_bytes, void* stream);
+size_t i2r_conv_halo_chain_workspace(const i2r_conv_problem* probs, int nprob);
 
 /* Stem / mask convolution on fp32 NCHW input with tiny Cin (3 or 1): 3x3 stride 2 pad 1 + folded
  * BN + ReLU -> fp16 NHWC [NB, H/2, W/2, Cout] (split != 0: pair tensor [.., 2*Cout], see I2R_F_SPLIT).  Replaces conv1/bn1/relu
@@ -234,6 +253,10 @@ int i2r_debug_trace(void* dev_buffer, int capacity_events, int cta);
  * 2 = epilogue without global stores / residual loads, 4 = activation TMA only for the first ring pass,
  * 8 = no MMAs (commits only).  0 restores the product behaviour. */
 int i2r_debug_flags(int flags);
+/* Profiling aid for i2r_conv_halo_chain (results become wrong with any bit set): 1 = tiles do not wait for their
+ * producers, 2 = they poll but skip the acquire / proxy fences, 4 = finished tiles are published after the shared-memory
+ * read of their TMA store instead of its completion.  0 restores the product behaviour. */
+int i2r_debug_chain_flags(int flags);
 /* Debug aid: every mbarrier wait of the tcgen05 kernels is time-bounded (2^31 SM cycles); a wait that times out traps
  * (the launch fails with cudaErrorLaunchFailure instead of hanging the GPU).  With a hang buffer installed --
  * HOST-MAPPED pinned memory of 4096 x 4 uint64, zero-filled by the caller, still readable after the context died --

@@ -32,6 +32,8 @@
 
 namespace i2r {
 
+constexpr int I2R_MAX_DEP = 4;
+
 struct HaloProblem {
   const __half* x;
   const uint8_t* w;
@@ -67,18 +69,38 @@ struct HaloProblem {
   // output mode without a tensor-map form).
   int o_bufs;
   uint32_t o_off, o_tile_bytes;
+  // chained launch (several dependent layers in one grid, see conv_halo_kernel): `done[n]` counts the output pixels of
+  // image n that have reached global memory; a tile of a consumer waits until the images it reads are complete in every
+  // producer `dep[i]` (image-local when producer and consumer share the image geometry, else dep_whole[i] = all of the
+  // producer's images).  img_px / nimg: the REAL image geometry (a 1x1 problem is re-tiled as one 8-pixel-wide strip).
+  int* done;
+  const int* dep[I2R_MAX_DEP];
+  int dep_whole[I2R_MAX_DEP], dep_px[I2R_MAX_DEP];
+  int ndep;
+  int img_px, nimg, strip;
 };
 
-struct HaloGroup {
-  CUtensorMap amap[I2R_MAX_GROUP];
-  CUtensorMap omap[I2R_MAX_GROUP][2];   // staged output: hi (or only) tile, lo tile of a pair tensor
+template <int NP, int NL>
+struct HaloGroupT {
+  static constexpr bool kChain = NL > 1;   // chained launches are a separate kernel instantiation (CH below)
+  CUtensorMap amap[NP];
+  CUtensorMap omap[NP][2];   // staged output: hi (or only) tile, lo tile of a pair tensor
   unsigned long long* trace;   // optional event trace (tools/trace_halo.py): four role regions of trace_cap (tag<<32|tile, clock64) pairs
   int trace_cta, trace_cap;
   int dbg;                     // debug ablations (i2r_debug_flags): 1 = epilogue hand-shake only, 2 = no global stores / residual loads
-  HaloProblem p[I2R_MAX_GROUP];
+  HaloProblem p[NP];
   int nprob;
   int total_ctas;              // CTAs that own work; the grid may hold one filler CTA more (whole clusters)
+  // chained launch: layer l = problems [layer_begin[l], layer_begin[l + 1]); ncols = TMEM columns every CTA allocates
+  // (covers the widest problem of the chain; 0 = single layer, sized per problem)
+  int nlayers;
+  int layer_begin[NL + 1];
+  uint32_t ncols;
+  int chain_dbg;               // timing ablations (i2r_debug_chain_flags; results are WRONG with any bit set): 1 = consumers
+                               // do not wait, 2 = consumers poll but skip the fences, 4 = publish after the .read wait
 };
+using HaloGroup = HaloGroupT<I2R_MAX_GROUP, 1>;
+using HaloChain = HaloGroupT<I2R_MAX_CHAIN_PROBLEMS, I2R_MAX_CHAIN_LAYERS>;
 
 // Launch parameters live in the constant bank; a loop that mentions P.field re-reads it with an indexed uniform
 // load (LDCU c[0][UR+off], ~100 cycles of latency on the branch that consumes it -- measured as the top
@@ -97,6 +119,7 @@ __device__ __forceinline__ T* opaque(T* v) {
   asm("" : "+l"(v));
   return v;
 }
+template <bool CH>
 __device__ __forceinline__ HaloProblem load_problem(const HaloProblem& s) {
   HaloProblem p;
   p.x = opaque(s.x); p.w = opaque(s.w); p.add0 = opaque(s.add0); p.add1 = opaque(s.add1); p.y = opaque(s.y);
@@ -114,6 +137,18 @@ __device__ __forceinline__ HaloProblem load_problem(const HaloProblem& s) {
   p.w_copies = opaque(s.w_copies);
   p.pair = opaque(s.pair); p.ntiles_real = opaque(s.ntiles_real); p.w_gstage = opaque(s.w_gstage);
   p.o_bufs = opaque(s.o_bufs); p.o_off = opaque(s.o_off); p.o_tile_bytes = opaque(s.o_tile_bytes);
+  p.done = nullptr; p.ndep = 0; p.img_px = 0; p.nimg = 0; p.strip = 0;
+  if (CH) {
+    p.done = opaque(s.done); p.ndep = opaque(s.ndep); p.img_px = opaque(s.img_px); p.nimg = opaque(s.nimg);
+    p.strip = opaque(s.strip);
+  }
+#pragma unroll
+  for (int i = 0; i < I2R_MAX_DEP; ++i) {
+    p.dep[i] = nullptr; p.dep_whole[i] = 0; p.dep_px[i] = 0;
+    if (CH) {
+      p.dep[i] = opaque(s.dep[i]); p.dep_whole[i] = opaque(s.dep_whole[i]); p.dep_px[i] = opaque(s.dep_px[i]);
+    }
+  }
   return p;
 }
 
@@ -395,6 +430,97 @@ __device__ __forceinline__ void mma_role(const HaloProblem& P, const int cta, co
   }
 }
 
+// ---- chained launches: cross-CTA completion counters -----------------------------------------------------------
+// Producer side (one epilogue thread): the tile's TMA store has COMPLETED (cp.async.bulk.wait_group, not .read), then a
+// gpu-scope release-add of the tile's valid pixels.  Consumer side (the activation producer thread): relaxed polls, one
+// gpu-scope acquire fence, and a proxy fence because the data is read by the TMA unit (async proxy), not by this thread.
+__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
+__device__ __forceinline__ void fence_acq_rel_gpu() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
+__device__ __forceinline__ int ld_relaxed_gpu(const int* p) {
+  int v;
+  asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void red_release_gpu_add(int* p, int v) {
+  asm volatile("red.release.gpu.global.add.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __noinline__ void chain_spin(const int* ctr, int need, int line) {
+  const long long t0 = clock64();
+  uint32_t spins = 0;
+  while (ld_relaxed_gpu(ctr) < need) {
+    __nanosleep(64);
+    if ((++spins & 255u) == 0 && clock64() - t0 > (1ll << 31))
+      mbar_timeout(static_cast<uint32_t>(reinterpret_cast<uintptr_t>(ctr)), static_cast<uint32_t>(need), line);
+  }
+}
+// images [n0, n1] an output tile of problem geometry (strip / tiles_per_img / H / W / img_px) lies in
+__device__ __forceinline__ void tile_images(int strip, int t, int tiles_per_img, int H, int W, int img_px, int& n0, int& n1) {
+  if (strip) {
+    const int p0 = t * (T_TW * T_TH), p1 = min(p0 + T_TW * T_TH, H * W);
+    n0 = p0 / img_px;
+    n1 = (p1 - 1) / img_px;
+  } else {
+    n0 = n1 = t / tiles_per_img;
+  }
+}
+struct ChainWait {
+  int n0, n1;          // images already known complete in every image-local producer (tiles come in image order)
+  uint32_t whole_ok;   // whole-tensor producers already known complete
+};
+struct ChainDeps {     // by-value argument pack of the out-of-line wait (keeps the producer loop small)
+  const int* dep[I2R_MAX_DEP];
+  int whole[I2R_MAX_DEP], px[I2R_MAX_DEP];
+  int ndep, img_px, strip, tiles_per_img, H, W;
+};
+__device__ __noinline__ void chain_wait_tile(const ChainDeps D, int t, ChainWait* cwp, bool fences) {
+  ChainWait cw = *cwp;
+  int n0, n1;
+  tile_images(D.strip, t, D.tiles_per_img, D.H, D.W, D.img_px, n0, n1);
+  const uint32_t all = (1u << D.ndep) - 1u;
+  if (n0 >= cw.n0 && n1 <= cw.n1 && cw.whole_ok == all) return;
+  int v[I2R_MAX_DEP];
+#pragma unroll
+  for (int d = 0; d < I2R_MAX_DEP; ++d)      // the common case first: one poll per producer, all in flight together
+    v[d] = (d < D.ndep && !D.whole[d]) ? ld_relaxed_gpu(D.dep[d] + n0) : 0x7fffffff;
+#pragma unroll
+  for (int d = 0; d < I2R_MAX_DEP; ++d) {
+    if (d >= D.ndep) continue;
+    if (D.whole[d]) {
+      if (!((cw.whole_ok >> d) & 1u))
+        for (int n = 0; n < D.whole[d]; ++n) chain_spin(D.dep[d] + n, D.px[d], __LINE__);
+    } else {
+      if (v[d] < D.img_px) chain_spin(D.dep[d] + n0, D.img_px, __LINE__);
+      for (int n = n0 + 1; n <= n1; ++n) chain_spin(D.dep[d] + n, D.img_px, __LINE__);
+    }
+  }
+  cw.whole_ok = all;
+  cw.n0 = n0;
+  cw.n1 = n1;
+  *cwp = cw;
+  if (fences) {
+    fence_acq_rel_gpu();
+    fence_proxy_async_all();
+  }
+}
+// a finished tile: add its valid pixels to the counter(s) of the image(s) it lies in
+__device__ __noinline__ void chain_publish(int* done, int t, int strip, int img_px, int tiles_per_img, int tiles_x, int H,
+                                           int W, int cdbg) {
+  if (t < 0 || (cdbg & 8)) return;
+  if (cdbg & 16) {
+    const int n = strip ? (t * (T_TW * T_TH)) / img_px : t / tiles_per_img;
+    asm volatile("red.relaxed.gpu.global.add.s32 [%0], %1;" ::"l"(done + n), "r"(1) : "memory");
+    return;
+  }
+  if (strip) {
+    const int p0 = t * (T_TW * T_TH), p1 = min(p0 + T_TW * T_TH, H * W);
+    for (int n = p0 / img_px; n * img_px < p1; ++n)
+      red_release_gpu_add(done + n, min(p1, (n + 1) * img_px) - max(p0, n * img_px));
+  } else {
+    const int n = t / tiles_per_img, r = t - n * tiles_per_img, ty = r / tiles_x, tx = r - ty * tiles_x;
+    red_release_gpu_add(done + n, min(T_TW, W - tx * T_TW) * min(T_TH, H - ty * T_TH));
+  }
+}
+
 __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, int c3,
                                             uint32_t bar) {
   asm volatile(
@@ -430,6 +556,8 @@ struct EpiArgs {
   int o_bufs;                    // staged output (see HaloProblem): buffers, shared-memory base, bytes per tile, maps
   uint32_t o_base, o_tile_bytes;
   const CUtensorMap* omap;       // [2]
+  int* done;                     // chained launch: this problem's per-image completion counters (else null)
+  int img_px, strip, cdbg;
 };
 __device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2, int c3) {
   asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.tile.bulk_group [%0, {%2,%3,%4,%5}], [%1];"
@@ -439,6 +567,8 @@ __device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, uint32_t sr
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait() { asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory"); }
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void epi_barrier() {      // the epilogue warps only (named barrier 1)
   asm volatile("bar.sync 1, %0;" ::"n"(32 * T_EPI_WARPS) : "memory");
@@ -449,20 +579,69 @@ __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t
 // Staged output, per tile: (1) the issuing thread waits until the TMA unit has finished READING the buffer two tiles back,
 // (2) all epilogue warps meet, write their rows, fence them towards the async proxy and meet again, (3) the issuing
 // thread launches the store(s).  Tiles overhanging the image are clipped by the TMA unit.
+// Chained launch: the issuing thread also publishes finished tiles -- a tile counts once its store group has COMPLETED
+// (wait_group without .read), which with two buffers is known one tile later; `t_old` / `t_new` are the tiles stored
+// but not yet published.  (Problems without a staged path publish after a gpu-scope fence of every storing thread.)
+// Addends of a chained launch were written by other CTAs of the SAME grid: the read-only (ld.global.nc) path is not
+// coherent with them, so chained launches read them through L2 (ld.global.cg)
+template <bool CH>
+__device__ __forceinline__ uint4 ld_addend(const uint4* p) { return CH ? __ldcg(p) : __ldg(p); }
+
 struct StageOut {
   bool on, issuer;
   uint32_t buf_addr;
   int nbuf, b;
+  int t_old, t_new;
+  __device__ __forceinline__ void init(const EpiArgs& E, bool is_issuer) {
+    on = E.o_bufs > 0;
+    issuer = is_issuer;
+    nbuf = E.o_bufs;
+    b = 0;
+    buf_addr = 0;
+    t_old = t_new = -1;
+  }
+  __device__ __forceinline__ void publish(const EpiArgs& E, int t) {
+    chain_publish(E.done, t, E.strip, E.img_px, E.tiles_per_img, E.tiles_x, E.H, E.W, E.cdbg);
+  }
+  __device__ __noinline__ void chain_begin(const EpiArgs& E) {
+    if (E.cdbg & 4) {
+      if (nbuf > 1) bulk_wait_read<1>(); else bulk_wait_read<0>();
+    } else {
+      if (nbuf > 1) bulk_wait<1>(); else bulk_wait<0>();
+    }
+    if (!(E.cdbg & 24)) fence_proxy_async_all();
+    publish(E, t_old);
+    t_old = -1;
+    if (nbuf <= 1) {
+      publish(E, t_new);
+      t_new = -1;
+    }
+  }
+  template <bool CH>
   __device__ __forceinline__ void begin_tile(const EpiArgs& E) {
     if (!on) return;
     if (issuer) {
-      if (nbuf > 1) bulk_wait_read<1>(); else bulk_wait_read<0>();
+      if (CH && E.done != nullptr) {
+        chain_begin(E);
+      } else {
+        if (nbuf > 1) bulk_wait_read<1>(); else bulk_wait_read<0>();
+      }
     }
     epi_barrier();
     buf_addr = E.o_base + static_cast<uint32_t>(b) * E.o_tile_bytes * ((E.flags & I2R_F_SPLIT) ? 2u : 1u);
   }
-  __device__ __forceinline__ void end_tile(const EpiArgs& E, int x0, int y0, int n, bool tile_ok) {
-    if (!on) return;
+  template <bool CH>
+  __device__ __forceinline__ void end_tile(const EpiArgs& E, int x0, int y0, int n, bool tile_ok, int t) {
+    if (!on) {
+      if (CH && E.done != nullptr) {
+        // direct stores, chained launch: every thread's stores are ordered before the barrier at gpu scope, then one
+        // thread publishes the tile
+        fence_acq_rel_gpu();
+        epi_barrier();
+        if (issuer && tile_ok) publish(E, t);
+      }
+      return;
+    }
     fence_proxy_async();
     epi_barrier();
     if (issuer) {
@@ -471,11 +650,23 @@ struct StageOut {
         if (E.flags & I2R_F_SPLIT) tma_store_4d(E.omap + 1, buf_addr + E.o_tile_bytes, 0, x0, y0, n);
       }
       bulk_commit();
+      if (CH) {
+        t_old = t_new;     // (published by the begin_tile in between unless there was none to publish)
+        t_new = tile_ok ? t : -1;
+      }
     }
     b = (b + 1 == nbuf) ? 0 : b + 1;
   }
-  __device__ __forceinline__ void finish() {
-    if (on && issuer) bulk_wait_all();
+  template <bool CH>
+  __device__ __forceinline__ void finish(const EpiArgs& E) {
+    if (on && issuer) {
+      bulk_wait_all();
+      if (CH && E.done != nullptr) {
+        fence_proxy_async_all();
+        publish(E, t_old);
+        publish(E, t_new);
+      }
+    }
   }
 };
 
@@ -487,7 +678,7 @@ __device__ __forceinline__ void arrive_accempty(const EpiArgs& E, uint32_t bar_l
 // (EG = 8-channel chunks in flight per pass: two keep the live set near 60 registers, which is what lets the kernel run
 // 12 epilogue warps at 128 registers per thread without spilling)
 constexpr int EG = 2;
-template <int OUT>
+template <int OUT, bool CH>
 __device__ __forceinline__ void epilogue_role(const EpiArgs E, const int cta, const uint32_t sbase, const uint32_t tmem_base,
                                               const uint32_t ncols, const int Npad, const int ew, const int quad,
                                               const int lane, unsigned long long* tr, const int trcap, const int dbg) {
@@ -503,11 +694,7 @@ __device__ __forceinline__ void epilogue_role(const EpiArgs E, const int cta, co
   int acc = 0, tri = 0;
   uint32_t accph = 0;
   StageOut so;
-  so.on = E.o_bufs > 0;
-  so.issuer = ew == 0 && lane == 0;
-  so.nbuf = E.o_bufs;
-  so.b = 0;
-  so.buf_addr = 0;
+  so.init(E, ew == 0 && lane == 0);
   const uint32_t srow = static_cast<uint32_t>(row) * static_cast<uint32_t>(E.Cout) * 2u;   // this pixel's row in the tile
   for (int tp = cta; tp < E.ntiles; tp += E.cta_count) {
     const int t = E.pair ? 2 * tp + E.rank : tp;
@@ -523,7 +710,7 @@ __device__ __forceinline__ void epilogue_role(const EpiArgs E, const int cta, co
     const __half* a0 = E.add0 + static_cast<int64_t>(p) * E.add_pix_stride;
     const __half* a1 = E.add1 + static_cast<int64_t>(p) * E.add_pix_stride;
     bool waited = false;
-    so.begin_tile(E);
+    so.template begin_tile<CH>(E);
     for (int c = cb; c < ce; c += EG) {
       const int nc = min(EG, ce - c);
       // residual loads first: their latency hides behind the accumulator wait
@@ -533,8 +720,8 @@ __device__ __forceinline__ void epilogue_role(const EpiArgs E, const int cta, co
         r0[j] = make_uint4(0, 0, 0, 0);
         r1[j] = make_uint4(0, 0, 0, 0);
         if (j < nc && valid && (c + j) * 8 < E.Cout) {
-          if (has0) r0[j] = __ldg(reinterpret_cast<const uint4*>(a0 + (c + j) * 8));
-          if (has1) r1[j] = __ldg(reinterpret_cast<const uint4*>(a1 + (c + j) * 8));
+          if (has0) r0[j] = ld_addend<CH>(reinterpret_cast<const uint4*>(a0 + (c + j) * 8));
+          if (has1) r1[j] = ld_addend<CH>(reinterpret_cast<const uint4*>(a1 + (c + j) * 8));
         }
       }
       uint4 l0[EG], l1[EG];   // split-operand addends: lo halves at channel offset Cout
@@ -543,8 +730,8 @@ __device__ __forceinline__ void epilogue_role(const EpiArgs E, const int cta, co
         l0[j] = make_uint4(0, 0, 0, 0);
         l1[j] = make_uint4(0, 0, 0, 0);
         if (split && j < nc && valid && (c + j) * 8 < E.Cout) {
-          if (has0) l0[j] = __ldg(reinterpret_cast<const uint4*>(a0 + E.lo_off + (c + j) * 8));
-          if (has1) l1[j] = __ldg(reinterpret_cast<const uint4*>(a1 + E.lo_off + (c + j) * 8));
+          if (has0) l0[j] = ld_addend<CH>(reinterpret_cast<const uint4*>(a0 + E.lo_off + (c + j) * 8));
+          if (has1) l1[j] = ld_addend<CH>(reinterpret_cast<const uint4*>(a1 + E.lo_off + (c + j) * 8));
         }
       }
       if (!waited) {
@@ -648,12 +835,12 @@ __device__ __forceinline__ void epilogue_role(const EpiArgs E, const int cta, co
     tc_fence_before();
     __syncwarp();
     if (lane == 0) arrive_accempty(E, bar_accempty + 8 * acc);
-    so.end_tile(E, tx * T_TW, ty * T_TH, n, t < E.ntiles_real);
+    so.template end_tile<CH>(E, tx * T_TW, ty * T_TH, n, t < E.ntiles_real, t);
     if (ew == 0 && lane == 0) trace_ev(tr, trcap, 2, tri, 21, t);
     acc ^= 1;
     if (acc == 0) accph ^= 1;
   }
-  so.finish();
+  so.template finish<CH>(E);
 }
 
 
@@ -661,7 +848,7 @@ __device__ __forceinline__ void epilogue_role(const EpiArgs E, const int cta, co
 // compile time and NADD residual tensors.  The epilogue warps are issue-bound (~4.5 cycles per instruction at two
 // warps per scheduler), so the instruction count per tile is what matters here: no per-chunk branches, no
 // reconvergence stacks, 32-bit pixel arithmetic.
-template <int G, int NADD>
+template <int G, int NADD, bool CH>
 __device__ __forceinline__ void epilogue_fast(const EpiArgs E, const int cta, const uint32_t sbase, const uint32_t tmem_base,
                                               const uint32_t ncols, const int cb, const int ce, const int ew, const int quad,
                                               const int lane, unsigned long long* tr, const int trcap) {
@@ -675,11 +862,7 @@ __device__ __forceinline__ void epilogue_fast(const EpiArgs E, const int cta, co
   int acc = 0, tri = 0;
   uint32_t accph = 0;
   StageOut so;
-  so.on = E.o_bufs > 0;
-  so.issuer = ew == 0 && lane == 0;
-  so.nbuf = E.o_bufs;
-  so.b = 0;
-  so.buf_addr = 0;
+  so.init(E, ew == 0 && lane == 0);
   const uint32_t srow = static_cast<uint32_t>(row) * static_cast<uint32_t>(E.Cout) * 2u;   // this pixel's row in the tile
   for (int tp = cta; tp < E.ntiles; tp += E.cta_count) {
     const int t = E.pair ? 2 * tp + E.rank : tp;
@@ -691,7 +874,7 @@ __device__ __forceinline__ void epilogue_fast(const EpiArgs E, const int cta, co
     const bool valid = (x < E.W) && (y < E.H) && (t < E.ntiles_real);
     const int p = (n * E.H + y) * E.W + x;
     const uint32_t taddr = lane_taddr + static_cast<uint32_t>(acc) * (ncols >> 1);
-    so.begin_tile(E);
+    so.template begin_tile<CH>(E);
     const __half* a0 = E.add0 + static_cast<int64_t>(p) * E.add_pix_stride;
     const __half* a1 = E.add1 + static_cast<int64_t>(p) * E.add_pix_stride;
     __half* yp = ybase + static_cast<int64_t>(p) * E.out_pix_stride;
@@ -701,8 +884,8 @@ __device__ __forceinline__ void epilogue_fast(const EpiArgs E, const int cta, co
       for (int j = 0; j < G; ++j) {
         r0[j] = make_uint4(0, 0, 0, 0);
         r1[j] = make_uint4(0, 0, 0, 0);
-        if (NADD >= 1 && valid) r0[j] = __ldg(reinterpret_cast<const uint4*>(a0 + (c + j) * 8));
-        if (NADD >= 2 && valid) r1[j] = __ldg(reinterpret_cast<const uint4*>(a1 + (c + j) * 8));
+        if (NADD >= 1 && valid) r0[j] = ld_addend<CH>(reinterpret_cast<const uint4*>(a0 + (c + j) * 8));
+        if (NADD >= 2 && valid) r1[j] = ld_addend<CH>(reinterpret_cast<const uint4*>(a1 + (c + j) * 8));
       }
       if (c == cb) {
         mbar_wait(bar_accfull + 8 * acc, accph);
@@ -741,12 +924,12 @@ __device__ __forceinline__ void epilogue_fast(const EpiArgs E, const int cta, co
     tc_fence_before();
     __syncwarp();
     if (lane == 0) arrive_accempty(E, bar_accempty + 8 * acc);
-    so.end_tile(E, tx * T_TW, ty * T_TH, n, t < E.ntiles_real);
+    so.template end_tile<CH>(E, tx * T_TW, ty * T_TH, n, t < E.ntiles_real, t);
     if (ew == 0 && lane == 0) trace_ev(tr, trcap, 2, tri, 21, t);
     acc ^= 1;
     if (acc == 0) accph ^= 1;
   }
-  so.finish();
+  so.template finish<CH>(E);
 }
 
 // Hot epilogue of the split-operand models (pair tensors: hi | lo): the same compile-time-unrolled structure as
@@ -754,7 +937,7 @@ __device__ __forceinline__ void epilogue_fast(const EpiArgs E, const int cta, co
 // (ACT 0: clamp = ReLU / none, 1: erf-GELU after the addends, 2: erf-GELU before the addends).  The generic epilogue
 // re-tests flags per element and calls the activation out of line: 7.9 k cycles per 128 x 96 tile, 49 k for a 128 x 256
 // GELU tile (profiles/r02_epilogue_warps.txt) against < 1 k cycles of MMA.
-template <int G, int NADD, int ACT>
+template <int G, int NADD, int ACT, bool CH>
 __device__ __forceinline__ void epilogue_split_fast(const EpiArgs E, const int cta, const uint32_t sbase,
                                                     const uint32_t tmem_base, const uint32_t ncols, const int cb, const int ce,
                                                     const int ew, const int quad, const int lane, unsigned long long* tr,
@@ -769,11 +952,7 @@ __device__ __forceinline__ void epilogue_split_fast(const EpiArgs E, const int c
   int acc = 0, tri = 0;
   uint32_t accph = 0;
   StageOut so;
-  so.on = E.o_bufs > 0;
-  so.issuer = ew == 0 && lane == 0;
-  so.nbuf = E.o_bufs;
-  so.b = 0;
-  so.buf_addr = 0;
+  so.init(E, ew == 0 && lane == 0);
   const uint32_t srow = static_cast<uint32_t>(row) * static_cast<uint32_t>(E.Cout) * 2u;
   for (int tp = cta; tp < E.ntiles; tp += E.cta_count) {
     const int t = E.pair ? 2 * tp + E.rank : tp;
@@ -788,19 +967,19 @@ __device__ __forceinline__ void epilogue_split_fast(const EpiArgs E, const int c
     const __half* a0 = E.add0 + static_cast<int64_t>(p) * E.add_pix_stride;
     const __half* a1 = E.add1 + static_cast<int64_t>(p) * E.add_pix_stride;
     __half* yp = ybase + static_cast<int64_t>(p) * E.out_pix_stride;
-    so.begin_tile(E);
+    so.template begin_tile<CH>(E);
     for (int c = cb; c < ce; c += G) {
       uint4 r0[G], r1[G], l0[G], l1[G];
 #pragma unroll
       for (int j = 0; j < G; ++j) {
         r0[j] = l0[j] = r1[j] = l1[j] = make_uint4(0, 0, 0, 0);
         if (NADD >= 1 && valid) {
-          r0[j] = __ldg(reinterpret_cast<const uint4*>(a0 + (c + j) * 8));
-          l0[j] = __ldg(reinterpret_cast<const uint4*>(a0 + E.lo_off + (c + j) * 8));
+          r0[j] = ld_addend<CH>(reinterpret_cast<const uint4*>(a0 + (c + j) * 8));
+          l0[j] = ld_addend<CH>(reinterpret_cast<const uint4*>(a0 + E.lo_off + (c + j) * 8));
         }
         if (NADD >= 2 && valid) {
-          r1[j] = __ldg(reinterpret_cast<const uint4*>(a1 + (c + j) * 8));
-          l1[j] = __ldg(reinterpret_cast<const uint4*>(a1 + E.lo_off + (c + j) * 8));
+          r1[j] = ld_addend<CH>(reinterpret_cast<const uint4*>(a1 + (c + j) * 8));
+          l1[j] = ld_addend<CH>(reinterpret_cast<const uint4*>(a1 + E.lo_off + (c + j) * 8));
         }
       }
       if (c == cb) {
@@ -860,60 +1039,84 @@ __device__ __forceinline__ void epilogue_split_fast(const EpiArgs E, const int c
     tc_fence_before();
     __syncwarp();
     if (lane == 0) arrive_accempty(E, bar_accempty + 8 * acc);
-    so.end_tile(E, tx * T_TW, ty * T_TH, n, t < E.ntiles_real);
+    so.template end_tile<CH>(E, tx * T_TW, ty * T_TH, n, t < E.ntiles_real, t);
     if (ew == 0 && lane == 0) trace_ev(tr, trcap, 2, tri, 21, t);
     acc ^= 1;
     if (acc == 0) accph ^= 1;
   }
-  so.finish();
+  so.template finish<CH>(E);
 }
 
-template <int NADD, int ACT>
+template <int NADD, int ACT, bool CH>
 __device__ __forceinline__ void epilogue_split_dispatch(const EpiArgs& E, const int cta, const uint32_t sbase,
                                                         const uint32_t tmem_base, const uint32_t ncols, const int cb,
                                                         const int ce, const int ew, const int quad, const int lane,
                                                         unsigned long long* tr, const int trcap) {
-  if ((ce - cb) % 2 == 0) epilogue_split_fast<2, NADD, ACT>(E, cta, sbase, tmem_base, ncols, cb, ce, ew, quad, lane, tr, trcap);
-  else epilogue_split_fast<1, NADD, ACT>(E, cta, sbase, tmem_base, ncols, cb, ce, ew, quad, lane, tr, trcap);
+  if ((ce - cb) % 2 == 0) epilogue_split_fast<2, NADD, ACT, CH>(E, cta, sbase, tmem_base, ncols, cb, ce, ew, quad, lane, tr, trcap);
+  else epilogue_split_fast<1, NADD, ACT, CH>(E, cta, sbase, tmem_base, ncols, cb, ce, ew, quad, lane, tr, trcap);
 }
-template <int ACT>
+template <int ACT, bool CH>
 __device__ __forceinline__ void epilogue_split_dispatch_nadd(const EpiArgs& E, const int cta, const uint32_t sbase,
                                                              const uint32_t tmem_base, const uint32_t ncols, const int cb,
                                                              const int ce, const int ew, const int quad, const int lane,
                                                              unsigned long long* tr, const int trcap) {
-  if (E.add1 != nullptr) epilogue_split_dispatch<2, ACT>(E, cta, sbase, tmem_base, ncols, cb, ce, ew, quad, lane, tr, trcap);
-  else if (E.add0 != nullptr) epilogue_split_dispatch<1, ACT>(E, cta, sbase, tmem_base, ncols, cb, ce, ew, quad, lane, tr, trcap);
-  else epilogue_split_dispatch<0, ACT>(E, cta, sbase, tmem_base, ncols, cb, ce, ew, quad, lane, tr, trcap);
+  if (E.add1 != nullptr) epilogue_split_dispatch<2, ACT, CH>(E, cta, sbase, tmem_base, ncols, cb, ce, ew, quad, lane, tr, trcap);
+  else if (E.add0 != nullptr) epilogue_split_dispatch<1, ACT, CH>(E, cta, sbase, tmem_base, ncols, cb, ce, ew, quad, lane, tr, trcap);
+  else epilogue_split_dispatch<0, ACT, CH>(E, cta, sbase, tmem_base, ncols, cb, ce, ew, quad, lane, tr, trcap);
 }
 
-template <int NADD>
+template <int NADD, bool CH>
 __device__ __forceinline__ void epilogue_fast_dispatch(const EpiArgs& E, const int cta, const uint32_t sbase,
                                                        const uint32_t tmem_base, const uint32_t ncols, const int cb,
                                                        const int ce, const int ew, const int quad, const int lane,
                                                        unsigned long long* tr, const int trcap) {
   const int cw = ce - cb;
   if (cw % 4 == 0) {
-    epilogue_fast<4, NADD>(E, cta, sbase, tmem_base, ncols, cb, ce, ew, quad, lane, tr, trcap);
+    epilogue_fast<4, NADD, CH>(E, cta, sbase, tmem_base, ncols, cb, ce, ew, quad, lane, tr, trcap);
   } else if (cw % 3 == 0) {
-    epilogue_fast<3, NADD>(E, cta, sbase, tmem_base, ncols, cb, ce, ew, quad, lane, tr, trcap);
+    epilogue_fast<3, NADD, CH>(E, cta, sbase, tmem_base, ncols, cb, ce, ew, quad, lane, tr, trcap);
   } else if (cw % 2 == 0) {
-    epilogue_fast<2, NADD>(E, cta, sbase, tmem_base, ncols, cb, ce, ew, quad, lane, tr, trcap);
+    epilogue_fast<2, NADD, CH>(E, cta, sbase, tmem_base, ncols, cb, ce, ew, quad, lane, tr, trcap);
   } else {
-    epilogue_fast<1, NADD>(E, cta, sbase, tmem_base, ncols, cb, ce, ew, quad, lane, tr, trcap);
+    epilogue_fast<1, NADD, CH>(E, cta, sbase, tmem_base, ncols, cb, ce, ew, quad, lane, tr, trcap);
   }
 }
 
 // CL = the launch is made of 2-CTA clusters and may hold CTA-pair problems.  A kernel image that contains cta_group::2
 // instructions can only be launched with an even cluster size (the driver rejects it otherwise: "cluster
 // misconfiguration"), so launches without pair problems use the CL = false instantiation, which has none.
-template <bool CL>
-__global__ void __launch_bounds__(T_THREADS, 1) conv_halo_kernel(const __grid_constant__ HaloGroup G) {
+//
+// CHAINED launches (GT = HaloChain, G.nlayers > 1; never with CTA pairs): the grid walks G.nlayers dependent layers.
+// Each layer has its own CTA partition (cta_begin / cta_count of its problems); between two layers a CTA only
+// re-synchronises with ITSELF (all roles drained, barriers re-initialised, rings restart at stage 0) -- the ordering
+// between CTAs is per tile: the activation producer waits for the per-image completion counters of the producing
+// problems (chain_wait_tile) and the store-issuing epilogue thread publishes them (StageOut::publish).  CTAs stride over
+// a problem's tiles in image order, so the images a CTA needs at the start of layer l + 1 were finished early in layer
+// l by everybody: the wait is almost always already satisfied and the grid never drains.  Progress: all CTAs of the
+// grid are co-resident (grid <= SM count, one CTA per SM) and dependencies only point to earlier layers.
+template <bool CL, class GT>
+__global__ void __launch_bounds__(T_THREADS, 1) conv_halo_kernel(const __grid_constant__ GT G) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // SW128 tiles need 1024-B alignment
   if (static_cast<int>(blockIdx.x) >= G.total_ctas) return;   // filler CTA that makes the grid a whole number of clusters
-  int pi = 0;
-  while (pi < G.nprob - 1 && static_cast<int>(blockIdx.x) >= G.p[pi].cta_begin + G.p[pi].cta_count) ++pi;
-  HaloProblem P = load_problem(G.p[pi]);
+  constexpr bool CH = GT::kChain;
+  const int nlayers = CH ? opaque(G.nlayers) : 1;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t sbase = smem_u32(smem);
+  pdl_launch_dependents();   // the next grid may start its prologue as soon as SMs free up (see i2r_common.cuh)
+  uint32_t tmem_chain = 0;   // chained launch: the allocation made in layer 0 serves every layer
+ for (int layer = 0; layer < nlayers; ++layer) {
+  int pi = CH ? G.layer_begin[layer] : 0;
+  const int pend = CH ? G.layer_begin[layer + 1] : G.nprob;
+  if (layer > 0) {
+    // every role of this CTA has finished the previous layer: restart the barriers (phase 0) before anyone uses them
+    tc_fence_before();
+    __syncthreads();
+  }
+  while (pi < pend - 1 && static_cast<int>(blockIdx.x) >= G.p[pi].cta_begin + G.p[pi].cta_count) ++pi;
+  if (static_cast<int>(blockIdx.x) < G.p[pi].cta_begin || static_cast<int>(blockIdx.x) >= G.p[pi].cta_begin + G.p[pi].cta_count)
+    continue;   // no work for this CTA in this layer (block-uniform)
+  HaloProblem P = load_problem<CH>(G.p[pi]);
   int cta = blockIdx.x - P.cta_begin;
   P.w += static_cast<size_t>(cta % P.w_copies) * P.w_total_bytes;
   // CTA-pair problems: CTA `rank` of pair `cta >> 1`; every role below loops over tile PAIRS with the pair index
@@ -924,11 +1127,8 @@ __global__ void __launch_bounds__(T_THREADS, 1) conv_halo_kernel(const __grid_co
     P.cta_count >>= 1;
   }
   const int dbg = opaque(G.dbg);
+  const int cdbg = CH ? opaque(G.chain_dbg) : 0;
   const int trace_cap = opaque(G.trace_cap);
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  pdl_launch_dependents();   // the next grid may start its prologue as soon as SMs free up (see i2r_common.cuh)
-
-  const uint32_t sbase = smem_u32(smem);
   const uint32_t bar_afull = sbase + B_AFULL, bar_aempty = sbase + B_AEMPTY, bar_wfull = sbase + B_WFULL,
                  bar_wempty = sbase + B_WEMPTY;
   const uint32_t bar_accfull = sbase + B_ACCFULL, bar_accempty = sbase + B_ACCEMPTY, bar_wres = sbase + B_WRES;
@@ -943,8 +1143,14 @@ __global__ void __launch_bounds__(T_THREADS, 1) conv_halo_kernel(const __grid_co
   const int Npad = P.Npad;
   uint32_t ncols = 32;
   while (ncols < static_cast<uint32_t>(2 * Npad)) ncols <<= 1;
+  if (CH) ncols = opaque(G.ncols);
+  const bool first = layer == 0 || tmem_chain == 0;   // (a CTA may sit out the first layers of a chain)
 
   if (tid == 0) {
+    if (!first) {   // every initialised barrier of the map (176 = TMEM slot, 184 unused)
+      for (uint32_t off = 0; off < 384; off += 8)
+        if (off != 176 && off != 184) mbar_inval(sbase + off);
+    }
     for (int i = 0; i < T_A_STAGES_MAX; ++i) {
       mbar_init(bar_afull + 8 * i, 1);
       mbar_init(bar_aempty + 8 * i, 1);
@@ -962,9 +1168,11 @@ __global__ void __launch_bounds__(T_THREADS, 1) conv_halo_kernel(const __grid_co
     mbar_init(sbase + B_PWRES, 1);
     fence_mbar_init();
   }
-  if (tid < 256) reinterpret_cast<uint32_t*>(smem + T_ONES_OFF)[tid] = 0x3c003c00u;   // fp16 (1.0, 1.0)
+  if (first && tid < 256) reinterpret_cast<uint32_t*>(smem + T_ONES_OFF)[tid] = 0x3c003c00u;   // fp16 (1.0, 1.0)
   fence_proxy_async();   // the ones tile is read by the tensor core (async proxy)
-  if (CL && pair) {
+  if (!first) {
+    // TMEM stays allocated across the layers of a chain
+  } else if (CL && pair) {
     // the peer's barriers must exist before a multicast commit / remote arrive can land on them, and both CTAs take
     // part in the cta_group::2 allocation
     __syncthreads();
@@ -981,6 +1189,7 @@ __global__ void __launch_bounds__(T_THREADS, 1) conv_halo_kernel(const __grid_co
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  tmem_chain = tmem_base | 0x80000000u;   // (TMEM addresses are 25-bit: the flag bit only marks "allocated")
 
   unsigned long long* tr = (G.trace != nullptr && static_cast<int>(blockIdx.x) == G.trace_cta) ? G.trace : nullptr;
 
@@ -995,7 +1204,20 @@ __global__ void __launch_bounds__(T_THREADS, 1) conv_halo_kernel(const __grid_co
       const uint32_t leader_afull = (CL && pair) ? mapa_rank(bar_afull, 0) : 0u;
       int sr[2] = {0, 0}, tri = 0, ring = 0;
       uint32_t phr[2] = {0, 0};
+      ChainWait cw;
+      cw.n0 = 0;
+      cw.n1 = -1;
+      cw.whole_ok = 0;
+      ChainDeps cd;
+#pragma unroll
+      for (int d = 0; d < I2R_MAX_DEP; ++d) {
+        cd.dep[d] = P.dep[d];
+        cd.whole[d] = P.dep_whole[d];
+        cd.px[d] = P.dep_px[d];
+      }
+      cd.ndep = P.ndep; cd.img_px = P.img_px; cd.strip = P.strip; cd.tiles_per_img = P.tiles_per_img; cd.H = P.H; cd.W = P.W;
       for (int tp = cta; tp < P.ntiles; tp += P.cta_count, ring ^= dual) {
+        if (CH && P.ndep != 0 && !(cdbg & 1)) chain_wait_tile(cd, tp, &cw, !(cdbg & 2));   // chained launch: the images this tile reads are complete
         // pair mode: this CTA's 128-pixel tile of pair-tile tp; a tile past the end (odd tile count) reads image
         // index NB, i.e. an all-out-of-bounds box the TMA unit fills with zeros
         const int t = pair ? min(2 * tp + rank, P.ntiles_real) : tp;
@@ -1105,6 +1327,7 @@ __global__ void __launch_bounds__(T_THREADS, 1) conv_halo_kernel(const __grid_co
     E.out_pix_stride = P.out_pix_stride; E.add_pix_stride = P.add_pix_stride; E.plane = P.plane; E.flags = P.flags;
     E.pair = pair ? 1 : 0; E.rank = rank; E.ntiles_real = P.ntiles_real;
     E.o_bufs = P.o_bufs; E.o_base = sbase + P.o_off; E.o_tile_bytes = P.o_tile_bytes; E.omap = &G.omap[pi][0];
+    E.done = P.done; E.img_px = P.img_px; E.strip = P.strip; E.cdbg = cdbg;
     const int ew = warp - 4;
     // chunks holding real channels, split over the warps of a lane quadrant
     const int n8 = (P.Cout + 7) >> 3, part8 = (n8 + (T_EPI_WARPS / 4) - 1) / (T_EPI_WARPS / 4);
@@ -1114,23 +1337,24 @@ __global__ void __launch_bounds__(T_THREADS, 1) conv_halo_kernel(const __grid_co
     if (plain_out && (P.flags & I2R_F_SPLIT) && (!(P.flags & I2R_F_ACT_FIRST) || (P.flags & I2R_F_GELU))) {
       // split-operand hot path (pair tensors), activation fixed at compile time
       if (!(P.flags & I2R_F_GELU))
-        epilogue_split_dispatch_nadd<0>(E, cta, sbase, tmem_base, ncols, cb, ce, ew, warp & 3, lane, tr, trace_cap);
+        epilogue_split_dispatch_nadd<0, CH>(E, cta, sbase, tmem_base, ncols, cb, ce, ew, warp & 3, lane, tr, trace_cap);
       else if (P.flags & I2R_F_ACT_FIRST)
-        epilogue_split_dispatch_nadd<2>(E, cta, sbase, tmem_base, ncols, cb, ce, ew, warp & 3, lane, tr, trace_cap);
+        epilogue_split_dispatch_nadd<2, CH>(E, cta, sbase, tmem_base, ncols, cb, ce, ew, warp & 3, lane, tr, trace_cap);
       else
-        epilogue_split_dispatch_nadd<1>(E, cta, sbase, tmem_base, ncols, cb, ce, ew, warp & 3, lane, tr, trace_cap);
+        epilogue_split_dispatch_nadd<1, CH>(E, cta, sbase, tmem_base, ncols, cb, ce, ew, warp & 3, lane, tr, trace_cap);
     } else if ((P.flags & (I2R_F_OUT_NCHW_F32 | I2R_F_OUT_F32 | I2R_F_SPLIT | I2R_F_OUT_T16 | I2R_F_GELU | I2R_F_ACT_FIRST)) ||
                (P.Cout & 7) || dbg != 0 || ce == cb) {
-      epilogue_role<1>(E, cta, sbase, tmem_base, ncols, Npad, ew, warp & 3, lane, tr, trace_cap, dbg);
+      epilogue_role<1, CH>(E, cta, sbase, tmem_base, ncols, Npad, ew, warp & 3, lane, tr, trace_cap, dbg);
     } else if (P.add1 != nullptr) {
-      epilogue_fast_dispatch<2>(E, cta, sbase, tmem_base, ncols, cb, ce, ew, warp & 3, lane, tr, trace_cap);
+      epilogue_fast_dispatch<2, CH>(E, cta, sbase, tmem_base, ncols, cb, ce, ew, warp & 3, lane, tr, trace_cap);
     } else if (P.add0 != nullptr) {
-      epilogue_fast_dispatch<1>(E, cta, sbase, tmem_base, ncols, cb, ce, ew, warp & 3, lane, tr, trace_cap);
+      epilogue_fast_dispatch<1, CH>(E, cta, sbase, tmem_base, ncols, cb, ce, ew, warp & 3, lane, tr, trace_cap);
     } else {
-      epilogue_fast_dispatch<0>(E, cta, sbase, tmem_base, ncols, cb, ce, ew, warp & 3, lane, tr, trace_cap);
+      epilogue_fast_dispatch<0, CH>(E, cta, sbase, tmem_base, ncols, cb, ce, ew, warp & 3, lane, tr, trace_cap);
     }
   }
 
+  if (CH) continue;   // chained launch: one tear-down after the last layer (below)
   tc_fence_before();
   __syncthreads();
   if (tr != nullptr && tid == 96) {
@@ -1142,6 +1366,12 @@ __global__ void __launch_bounds__(T_THREADS, 1) conv_halo_kernel(const __grid_co
     if (warp == 2) tmem_dealloc2(tmem_base, ncols);
   } else if (warp == 2) {
     tmem_dealloc(tmem_base, ncols);
+  }
+ }
+  if (CH) {
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2 && tmem_chain != 0) tmem_dealloc(tmem_chain & 0x7fffffffu, opaque(G.ncols));
   }
 }
 
@@ -1211,7 +1441,7 @@ static int encode_omap(CUtensorMap* map, void* y, int NB, int H, int W, int Cout
 }
 
 static unsigned long long* g_trace = nullptr;
-static int g_trace_cta = 0, g_trace_cap = 0, g_dbg = 0;
+static int g_trace_cta = 0, g_trace_cap = 0, g_dbg = 0, g_chain_dbg = 0;
 static bool is_std3x3(const i2r_conv_problem& P) {
   if (P.ntaps != 9) return false;
   for (int t = 0; t < 9; ++t)
@@ -1237,12 +1467,8 @@ extern "C" int i2r_conv_halo_supported(const i2r_conv_problem* P) {
   return 1;
 }
 
-extern "C" int i2r_conv_halo(const i2r_conv_problem* probs, int nprob, void* stream) {
-  using namespace i2r;
-  if (!probs || nprob < 1 || nprob > I2R_MAX_GROUP) {
-    set_error("i2r_conv_halo: nprob=%d out of range", nprob);
-    return I2R_E_BADARG;
-  }
+namespace i2r {
+static int sm_count() {
   static int num_sms_dev[MAX_DEVICES] = {};
   int& num_sms = num_sms_dev[current_device()];
   if (num_sms == 0) {
@@ -1250,13 +1476,37 @@ extern "C" int i2r_conv_halo(const i2r_conv_problem* probs, int nprob, void* str
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
   }
-  HaloGroup G;
-  memset(&G, 0, sizeof(G));
-  G.nprob = nprob;
-  G.trace = g_trace;
-  G.trace_cta = g_trace_cta;
-  G.trace_cap = g_trace_cap;
-  G.dbg = g_dbg;
+  return num_sms;
+}
+
+static int halo_func_attrs() {
+  static bool attr_done_dev[MAX_DEVICES] = {};   // the opt-in is a per-device property
+  bool& attr_done = attr_done_dev[current_device()];
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(conv_halo_kernel<false, HaloGroup>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         T_MAX_SMEM + 1024);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(conv_halo_kernel<true, HaloGroup>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               T_MAX_SMEM + 1024);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(conv_halo_kernel<false, HaloChain>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               T_MAX_SMEM + 1024);
+    if (e != cudaSuccess) {
+      set_error("cudaFuncSetAttribute(conv_halo): %s", cudaGetErrorString(e));
+      return static_cast<int>(e);
+    }
+    attr_done = true;
+  }
+  return 0;
+}
+
+// Plans ONE group of independent problems (a launch of i2r_conv_halo, or one layer of a chain) into G.p[base ..
+// base + nprob): geometry, shared-memory layout, tensor maps, CTA ranges.  `src[i]` = index into probs of G.p[base + i]
+// (pair problems are moved to the front).  allow_pair = false: never plan CTA-pair problems (chains).
+template <class GT>
+static int plan_layer(GT& G, const int base, const i2r_conv_problem* probs, const int nprob, const int num_sms,
+                      const bool allow_pair, const bool need_stage, uint32_t& smem_need, int& total_ctas, int& npair_out,
+                      int* src) {
   // CTA-pair mode (I2R_HALO_PAIR: 0 = never [default], 1 = where the single-CTA weight image does not fit shared memory,
   // 2 = wherever the shape allows: tests).  Measured on C2 / C3 (profiles/r02_pair_mode.txt): correct everywhere, and the
   // tensor work per output does drop (96-channel layers: one N=96 pair tile instead of two N=48 halves re-reading the
@@ -1273,7 +1523,8 @@ extern "C" int i2r_conv_halo(const i2r_conv_problem* probs, int nprob, void* str
     const char* e = getenv("I2R_HALO_STAGE");
     return e ? atoi(e) : 1;
   }();
-  int order[I2R_MAX_GROUP], npair = 0;
+  int* order = src;
+  int npair = 0;
   bool want_pair[I2R_MAX_GROUP];
   for (int i = 0; i < nprob; ++i) {
     const i2r_conv_problem& S = probs[i];
@@ -1284,7 +1535,7 @@ extern "C" int i2r_conv_halo(const i2r_conv_problem* probs, int nprob, void* str
     const int nkc = ((S.Cin + 63) / 64) * ((S.flags & I2R_F_SPLIT) ? 3 : 1);
     const uint32_t image = static_cast<uint32_t>(S.ntaps * nkc + 1) * S.Npad * 128;
     const int64_t m = static_cast<int64_t>(S.NB) * S.IH * S.IW;
-    want_pair[i] = pair_policy != 0 && S.Npad % 16 == 0 && S.Npad >= 32 && m > 128 &&
+    want_pair[i] = allow_pair && pair_policy != 0 && S.Npad % 16 == 0 && S.Npad >= 32 && m > 128 &&
                    (pair_policy == 2 || image > T_W_RES_MAX);
   }
   for (int i = 0; i < nprob; ++i)
@@ -1296,14 +1547,13 @@ extern "C" int i2r_conv_halo(const i2r_conv_problem* probs, int nprob, void* str
   }
   double cost[I2R_MAX_GROUP], startup[I2R_MAX_GROUP];
   int total_ctas_min = 0;
-  uint32_t smem_need = 0;
   for (int i = 0; i < nprob; ++i) {
     const i2r_conv_problem& S = probs[order[i]];
     if (!S.x || !S.w_folded || !S.y) {
       set_error("i2r_conv_halo: problem %d: null pointer", order[i]);
       return I2R_E_BADARG;
     }
-    HaloProblem& P = G.p[i];
+    HaloProblem& P = G.p[base + i];
     P.pair = i < npair ? 1 : 0;
     P.x = static_cast<const __half*>(S.x);
     P.w = static_cast<const uint8_t*>(S.w_folded);
@@ -1318,10 +1568,14 @@ extern "C" int i2r_conv_halo(const i2r_conv_problem* probs, int nprob, void* str
     P.W = S.IW;
     const int64_t mtot = static_cast<int64_t>(S.NB) * S.IH * S.IW;
     P.plane = S.OHf * S.OWf;
+    P.img_px = S.IH * S.IW;
+    P.nimg = S.NB;
+    P.strip = 0;
     if (S.ntaps == 1 && mtot % 8 == 0) {  // pixels are independent: re-tile as an 8-wide strip
       P.NB = 1;
       P.W = 8;
       P.H = static_cast<int>(mtot / 8);
+      P.strip = 1;
     }
     P.C = S.Cin;
     P.Cout = S.Cout;
@@ -1391,18 +1645,23 @@ extern "C" int i2r_conv_halo(const i2r_conv_problem* probs, int nprob, void* str
         }
       }
     }
+    if (need_stage && P.o_bufs == 0) {
+      set_error("i2r_conv_halo_chain: problem %d has no staged (TMA store) output path", order[i]);
+      return I2R_E_UNSUPPORTED;
+    }
     P.a_stages = astg;
     {
-      int rc = encode_amap(&G.amap[i], S.x, P.NB, P.H, P.W, P.split ? 2 * P.C : P.C, S.in_pix_stride, hw, hh);
+      int rc = encode_amap(&G.amap[base + i], S.x, P.NB, P.H, P.W, P.split ? 2 * P.C : P.C, S.in_pix_stride, hw, hh);
       if (rc) return rc;
     }
     P.w_off = T_A_OFF + static_cast<uint32_t>(astg) * P.a_stage_bytes;
     P.o_off = (P.w_off + wregion + 127u) & ~127u;
     if (P.o_bufs) {
       // the output as a 4-D tensor (C, W, H, N) with the same tile geometry as the activation map, dense boxes
-      int rc = encode_omap(&G.omap[i][0], S.y, P.NB, P.H, P.W, S.Cout, S.out_pix_stride);
+      int rc = encode_omap(&G.omap[base + i][0], S.y, P.NB, P.H, P.W, S.Cout, S.out_pix_stride);
       if (!rc && P.split)
-        rc = encode_omap(&G.omap[i][1], static_cast<__half*>(S.y) + P.lo_off, P.NB, P.H, P.W, S.Cout, S.out_pix_stride);
+        rc = encode_omap(&G.omap[base + i][1], static_cast<__half*>(S.y) + P.lo_off, P.NB, P.H, P.W, S.Cout,
+                         S.out_pix_stride);
       if (rc) return rc;
     }
     const uint32_t need = P.o_off + P.o_bufs * P.o_tile_bytes * (P.split ? 2u : 1u);
@@ -1436,13 +1695,13 @@ extern "C" int i2r_conv_halo(const i2r_conv_problem* probs, int nprob, void* str
   int begin = 0;
   int cnt[I2R_MAX_GROUP];      // workers per problem
   if (total_ctas_min <= num_sms) {
-    for (int i = 0; i < nprob; ++i) cnt[i] = G.p[i].ntiles;
+    for (int i = 0; i < nprob; ++i) cnt[i] = G.p[base + i].ntiles;
   } else {
     double best_t = 1e30;
     int best_cnt[I2R_MAX_GROUP];
     for (int i = 0; i < nprob; ++i) best_cnt[i] = 1;
     for (int ci = 0; ci < nprob; ++ci) {
-      const int kmax = G.p[ci].ntiles < 4096 ? G.p[ci].ntiles : 4096;
+      const int kmax = G.p[base + ci].ntiles < 4096 ? G.p[base + ci].ntiles : 4096;
       for (int k = 1; k <= kmax; ++k) {
         const double t = startup[ci] + k * cost[ci];
         if (t >= best_t) break;
@@ -1455,8 +1714,8 @@ extern "C" int i2r_conv_halo(const i2r_conv_problem* probs, int nprob, void* str
             ok = false;
             break;
           }
-          c[i] = (G.p[i].ntiles + per - 1) / per;
-          used += c[i] * (G.p[i].pair ? 2 : 1);
+          c[i] = (G.p[base + i].ntiles + per - 1) / per;
+          used += c[i] * (G.p[base + i].pair ? 2 : 1);
         }
         if (ok && used <= num_sms) {
           best_t = t;
@@ -1468,7 +1727,7 @@ extern "C" int i2r_conv_halo(const i2r_conv_problem* probs, int nprob, void* str
     int used = 0;
     for (int i = 0; i < nprob; ++i) {
       cnt[i] = best_cnt[i];
-      used += cnt[i] * (G.p[i].pair ? 2 : 1);
+      used += cnt[i] * (G.p[base + i].pair ? 2 : 1);
     }
     // left-over SMs: to whoever has the highest average load per worker (they cannot lower the makespan bound, but they
     // shorten the tail of the real, noisier execution)
@@ -1477,8 +1736,8 @@ extern "C" int i2r_conv_halo(const i2r_conv_problem* probs, int nprob, void* str
       int best = -1;
       double bestv = -1;
       for (int i = 0; i < nprob; ++i) {
-        if (cnt[i] >= G.p[i].ntiles || (G.p[i].pair && left < 2)) continue;
-        const double v = startup[i] + static_cast<double>(G.p[i].ntiles) / cnt[i] * cost[i];
+        if (cnt[i] >= G.p[base + i].ntiles || (G.p[base + i].pair && left < 2)) continue;
+        const double v = startup[i] + static_cast<double>(G.p[base + i].ntiles) / cnt[i] * cost[i];
         if (v > bestv) {
           bestv = v;
           best = i;
@@ -1486,31 +1745,74 @@ extern "C" int i2r_conv_halo(const i2r_conv_problem* probs, int nprob, void* str
       }
       if (best < 0) break;
       ++cnt[best];
-      left -= G.p[best].pair ? 2 : 1;
+      left -= G.p[base + best].pair ? 2 : 1;
     }
   }
   for (int i = 0; i < nprob; ++i) {
-    G.p[i].cta_begin = begin;
-    G.p[i].cta_count = cnt[i] * (G.p[i].pair ? 2 : 1);
-    begin += G.p[i].cta_count;
+    G.p[base + i].cta_begin = begin;
+    G.p[base + i].cta_count = cnt[i] * (G.p[base + i].pair ? 2 : 1);
+    begin += G.p[base + i].cta_count;
   }
+  total_ctas = begin;
+  npair_out = npair;
+  return 0;
+}
+
+template <class GT>
+static void group_header(GT& G) {
+  memset(&G, 0, sizeof(G));
+  G.trace = g_trace;
+  G.trace_cta = g_trace_cta;
+  G.trace_cap = g_trace_cap;
+  G.dbg = g_dbg;
+}
+
+// byte range a problem's tensor spans: [ptr, ptr + ((pixels - 1) * pix_stride + channels) * 2)
+struct ByteRange {
+  uintptr_t lo, hi;
+  bool hits(const ByteRange& o) const { return lo < o.hi && o.lo < hi; }
+};
+static ByteRange range_of(const void* ptr, int64_t pixels, int64_t pix_stride, int64_t channels) {
+  ByteRange r;
+  r.lo = reinterpret_cast<uintptr_t>(ptr);
+  r.hi = r.lo + static_cast<uintptr_t>(((pixels - 1) * pix_stride + channels) * 2);
+  return r;
+}
+static ByteRange in_range(const i2r_conv_problem& S) {
+  return range_of(S.x, static_cast<int64_t>(S.NB) * S.IH * S.IW, S.in_pix_stride, (S.flags & I2R_F_SPLIT) ? 2 * S.Cin : S.Cin);
+}
+static ByteRange out_range(const i2r_conv_problem& S) {
+  const int lo = S.pair_lo_offset > 0 ? S.pair_lo_offset : S.Cout;
+  return range_of(S.y, static_cast<int64_t>(S.NB) * S.OHf * S.OWf, S.out_pix_stride, (S.flags & I2R_F_SPLIT) ? lo + S.Cout : S.Cout);
+}
+static ByteRange add_range(const i2r_conv_problem& S, const void* a) {
+  const int lo = S.pair_lo_offset > 0 ? S.pair_lo_offset : S.Cout;
+  return range_of(a, static_cast<int64_t>(S.NB) * S.OHf * S.OWf, S.add_pix_stride, (S.flags & I2R_F_SPLIT) ? lo + S.Cout : S.Cout);
+}
+}  // namespace i2r
+
+extern "C" int i2r_conv_halo(const i2r_conv_problem* probs, int nprob, void* stream) {
+  using namespace i2r;
+  if (!probs || nprob < 1 || nprob > I2R_MAX_GROUP) {
+    set_error("i2r_conv_halo: nprob=%d out of range", nprob);
+    return I2R_E_BADARG;
+  }
+  HaloGroup G;
+  group_header(G);
+  G.nprob = nprob;
+  G.nlayers = 1;
+  G.layer_begin[0] = 0;
+  G.layer_begin[1] = nprob;
+  uint32_t smem_need = 0;
+  int begin = 0, npair = 0, src[I2R_MAX_GROUP];
+  int rc = plan_layer(G, 0, probs, nprob, sm_count(), true, false, smem_need, begin, npair, src);
+  if (rc) return rc;
   G.total_ctas = begin;
-  static bool attr_done_dev[MAX_DEVICES] = {};   // the opt-in is a per-device property
-  bool& attr_done = attr_done_dev[current_device()];
-  if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(conv_halo_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         T_MAX_SMEM + 1024);
-    if (e == cudaSuccess)
-      e = cudaFuncSetAttribute(conv_halo_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, T_MAX_SMEM + 1024);
-    if (e != cudaSuccess) {
-      set_error("cudaFuncSetAttribute(conv_halo): %s", cudaGetErrorString(e));
-      return static_cast<int>(e);
-    }
-    attr_done = true;
-  }
+  rc = halo_func_attrs();
+  if (rc) return rc;
   if (npair == 0) {
-    launch_pdl(conv_halo_kernel<false>, dim3(begin), dim3(T_THREADS), smem_need + 1024, static_cast<cudaStream_t>(stream),
-               G);
+    launch_pdl(conv_halo_kernel<false, HaloGroup>, dim3(begin), dim3(T_THREADS), smem_need + 1024,
+               static_cast<cudaStream_t>(stream), G);
   } else {
     // clusters of two consecutive CTAs (the grid is padded to a whole number of clusters; a filler CTA exits at once)
     cudaLaunchConfig_t cfg = {};
@@ -1527,15 +1829,168 @@ extern "C" int i2r_conv_halo(const i2r_conv_problem* probs, int nprob, void* str
     attr[1].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 2;
-    cudaLaunchKernelEx(&cfg, conv_halo_kernel<true>, G);
+    cudaLaunchKernelEx(&cfg, conv_halo_kernel<true, HaloGroup>, G);
   }
   return check_launch("conv_halo_kernel");
+}
+
+extern "C" size_t i2r_conv_halo_chain_workspace(const i2r_conv_problem* probs, int nprob) {
+  size_t n = 0;
+  for (int i = 0; probs && i < nprob; ++i) n += static_cast<size_t>(probs[i].NB);
+  return n * sizeof(int);
+}
+
+extern "C" int i2r_conv_halo_chain(const i2r_conv_problem* probs, const int* layer_count, int nlayers, void* workspace,
+                                   size_t workspace_bytes, void* stream) {
+  using namespace i2r;
+  if (!probs || !layer_count || nlayers < 1 || nlayers > I2R_MAX_CHAIN_LAYERS || !workspace) {
+    set_error("i2r_conv_halo_chain: bad arguments (nlayers=%d)", nlayers);
+    return I2R_E_BADARG;
+  }
+  int nprob = 0;
+  for (int l = 0; l < nlayers; ++l) {
+    if (layer_count[l] < 1 || layer_count[l] > I2R_MAX_GROUP) {
+      set_error("i2r_conv_halo_chain: layer %d has %d problems", l, layer_count[l]);
+      return I2R_E_BADARG;
+    }
+    nprob += layer_count[l];
+  }
+  for (int i = 0; i < nprob; ++i)
+    if (probs[i].flags & (I2R_F_OUT_NCHW_F32 | I2R_F_OUT_F32 | I2R_F_OUT_T16)) {
+      set_error("i2r_conv_halo_chain: problem %d: only fp16 NHWC outputs can be chained", i);
+      return I2R_E_UNSUPPORTED;
+    }
+  if (nprob > I2R_MAX_CHAIN_PROBLEMS) {
+    set_error("i2r_conv_halo_chain: %d problems (max %d)", nprob, I2R_MAX_CHAIN_PROBLEMS);
+    return I2R_E_UNSUPPORTED;
+  }
+  if (workspace_bytes < i2r_conv_halo_chain_workspace(probs, nprob)) {
+    set_error("i2r_conv_halo_chain: workspace too small");
+    return I2R_E_BADARG;
+  }
+  const int num_sms = sm_count();
+  static thread_local HaloChain G;   // 25 KB: not on the stack; per thread (nn.DataParallel drives one device per thread)
+  group_header(G);
+  G.nprob = nprob;
+  G.nlayers = nlayers;
+  G.chain_dbg = g_chain_dbg;
+  uint32_t smem_need = 0;
+  int grid = 0;
+  int src[I2R_MAX_CHAIN_PROBLEMS];   // G.p[i] was planned from probs[src[i]]
+  int base = 0;
+  for (int l = 0; l < nlayers; ++l) {
+    int ctas = 0, npair = 0, lsrc[I2R_MAX_GROUP];
+    G.layer_begin[l] = base;
+    int rc = plan_layer(G, base, probs + base, layer_count[l], num_sms, false, false, smem_need, ctas, npair, lsrc);
+    if (rc) return rc;
+    if (ctas > num_sms) {   // (more problems than SMs cannot happen with <= I2R_MAX_GROUP problems; be explicit)
+      set_error("i2r_conv_halo_chain: layer %d needs %d CTAs", l, ctas);
+      return I2R_E_UNSUPPORTED;
+    }
+    for (int i = 0; i < layer_count[l]; ++i) src[base + i] = base + lsrc[i];
+    if (ctas > grid) grid = ctas;
+    base += layer_count[l];
+  }
+  G.layer_begin[nlayers] = base;
+  G.total_ctas = grid;
+  // completion counters and dependencies (address-range overlap with the outputs of EARLIER layers)
+  int* ws = static_cast<int*>(workspace);
+  int layer_of[I2R_MAX_CHAIN_PROBLEMS];
+  {
+    int off = 0;
+    for (int l = 0, i = 0; l < nlayers; ++l)
+      for (int k = 0; k < layer_count[l]; ++k, ++i) layer_of[i] = l;
+    for (int i = 0; i < nprob; ++i) {
+      G.p[i].done = ws + off;
+      off += probs[src[i]].NB;
+    }
+  }
+  uint32_t ncols = 32;
+  for (int i = 0; i < nprob; ++i) {
+    const i2r_conv_problem& S = probs[src[i]];
+    HaloProblem& P = G.p[i];
+    while (ncols < static_cast<uint32_t>(2 * P.Npad)) ncols <<= 1;
+    const ByteRange rin = in_range(S), rout = out_range(S);
+    P.ndep = 0;
+    for (int j = 0; j < nprob; ++j) {
+      if (layer_of[j] >= layer_of[i]) {
+        // same or later layer: outputs must be disjoint from everything this problem touches (checked one way is enough
+        // for later layers: they run the symmetric test against this problem below)
+        if (j != i && layer_of[j] == layer_of[i] && out_range(probs[src[j]]).hits(rout)) {
+          // two problems of a layer writing channel slices of one tensor interleave in memory: ranges overlap, bytes
+          // do not -- allowed, as in i2r_conv_halo
+        }
+        continue;
+      }
+      const i2r_conv_problem& Q = probs[src[j]];
+      const ByteRange qout = out_range(Q);
+      bool reads = qout.hits(rin);
+      if (S.add0 && qout.hits(add_range(S, S.add0))) reads = true;
+      if (S.add1 && qout.hits(add_range(S, S.add1))) reads = true;
+      // write-after-read / write-after-write across layers is not ordered by the counters
+      bool clobbers = rout.hits(in_range(Q)) || (Q.add0 && rout.hits(add_range(Q, Q.add0))) ||
+                      (Q.add1 && rout.hits(add_range(Q, Q.add1))) || rout.hits(qout);
+      if (clobbers) {
+        set_error("i2r_conv_halo_chain: the output of problem %d overlaps a tensor of problem %d in an earlier layer", src[i],
+                  src[j]);
+        return I2R_E_UNSUPPORTED;
+      }
+      if (!reads) continue;
+      if (P.ndep == I2R_MAX_DEP) {
+        set_error("i2r_conv_halo_chain: problem %d reads more than %d earlier outputs", src[i], I2R_MAX_DEP);
+        return I2R_E_UNSUPPORTED;
+      }
+      const HaloProblem& PQ = G.p[j];
+      const bool local = PQ.nimg == P.nimg && PQ.img_px == P.img_px;   // same images: a tile needs only its own image(s)
+      P.dep[P.ndep] = PQ.done;
+      P.dep_whole[P.ndep] = local ? 0 : PQ.nimg;
+      P.dep_px[P.ndep] = PQ.img_px;
+      ++P.ndep;
+    }
+  }
+  G.ncols = ncols;
+  int rc = halo_func_attrs();
+  if (rc) return rc;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  cudaError_t e = cudaMemsetAsync(workspace, 0, i2r_conv_halo_chain_workspace(probs, nprob), st);
+  if (e != cudaSuccess) {
+    set_error("i2r_conv_halo_chain: cudaMemsetAsync: %s", cudaGetErrorString(e));
+    return static_cast<int>(e);
+  }
+  // CTAs of this grid wait for each other: with I2R_HALO_CHAIN_COOP=1 the launch is cooperative (the driver guarantees
+  // co-residency of the whole grid even when other work shares the device); the default plain launch relies on the
+  // documented rule (one chained launch in flight per device) and keeps programmatic dependent launch
+  static const int coop = []() {
+    const char* v = getenv("I2R_HALO_CHAIN_COOP");
+    return v ? atoi(v) : 0;
+  }();
+  if (coop) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(T_THREADS);
+    cfg.dynamicSmemBytes = smem_need + 1024;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeCooperative;
+    attr[0].val.cooperative = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaLaunchKernelEx(&cfg, conv_halo_kernel<false, HaloChain>, G);
+  } else {
+    launch_pdl(conv_halo_kernel<false, HaloChain>, dim3(grid), dim3(T_THREADS), smem_need + 1024, st, G);
+  }
+  return check_launch("conv_halo_kernel(chain)");
 }
 
 extern "C" int i2r_debug_trace(void* dev_buffer, int capacity_events, int cta) {
   i2r::g_trace = static_cast<unsigned long long*>(dev_buffer);
   i2r::g_trace_cap = capacity_events;
   i2r::g_trace_cta = cta;
+  return 0;
+}
+
+extern "C" int i2r_debug_chain_flags(int flags) {
+  i2r::g_chain_dbg = flags;
   return 0;
 }
 

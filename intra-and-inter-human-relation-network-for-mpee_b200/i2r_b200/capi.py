@@ -9,6 +9,9 @@ LIB_PATH = os.environ.get("I2R_LIB") or os.path.join(HERE, "libi2r_sm100.so")
 
 I2R_MAX_TAPS = 9
 I2R_MAX_GROUP = 6
+I2R_MAX_CHAIN_PROBLEMS = 40
+I2R_MAX_CHAIN_LAYERS = 16
+E_UNSUPPORTED = -2
 F_RELU = 1
 F_OUT_NCHW_F32 = 2
 F_OUT_F32 = 4
@@ -18,7 +21,7 @@ F_GELU = 32
 F_ACT_FIRST = 64
 
 EXPORTS = [
-    "i2r_version", "i2r_last_error", "i2r_device_check", "i2r_sm_count", "i2r_conv_igemm", "i2r_conv_halo", "i2r_conv_halo_supported", "i2r_debug_trace", "i2r_debug_flags", "i2r_debug_hang_buffer", "i2r_hflip_f32", "i2r_flip_merge", "i2r_decode_heatmaps", "i2r_crop_persons", "i2r_box_masks", "i2r_mask_res_stem",
+    "i2r_version", "i2r_last_error", "i2r_device_check", "i2r_sm_count", "i2r_conv_igemm", "i2r_conv_halo", "i2r_conv_halo_supported", "i2r_conv_halo_chain", "i2r_conv_halo_chain_workspace", "i2r_debug_trace", "i2r_debug_flags", "i2r_debug_chain_flags", "i2r_debug_hang_buffer", "i2r_hflip_f32", "i2r_flip_merge", "i2r_decode_heatmaps", "i2r_crop_persons", "i2r_box_masks", "i2r_mask_res_stem",
     "i2r_sizeof_conv_problem", "i2r_stem_conv3x3s2", "i2r_stem_conv3x3s2_tc", "i2r_stem_tc_weight_bytes", "i2r_maxpool3x3s2", "i2r_attention_varlen", "i2r_attention_workspace_bytes", "i2r_attention_tc", "i2r_encoder_tail", "i2r_encoder_tail_weight_bytes", "i2r_attention_tc_workspace_bytes", "i2r_layernorm", "i2r_add_f16", "i2r_upsum", "i2r_dwconv3x3", "i2r_upsum_bilinear", "i2r_layernorm_padded", "i2r_window_rows", "i2r_ln_window_gather", "i2r_window_scatter_add", "i2r_window_attention",
 ]
 
@@ -69,8 +72,15 @@ def load():
         lib.i2r_conv_igemm.argtypes = [ctypes.POINTER(ConvProblem), i32, i32, vp]
         lib.i2r_conv_halo.argtypes = [ctypes.POINTER(ConvProblem), i32, vp]
         lib.i2r_conv_halo_supported.argtypes = [ctypes.POINTER(ConvProblem)]
+        if "i2r_conv_halo_chain" in EXPORTS:
+            lib.i2r_conv_halo_chain.argtypes = [ctypes.POINTER(ConvProblem), ctypes.POINTER(ctypes.c_int), i32, vp,
+                                                ctypes.c_size_t, vp]
+            lib.i2r_conv_halo_chain_workspace.argtypes = [ctypes.POINTER(ConvProblem), i32]
+            lib.i2r_conv_halo_chain_workspace.restype = ctypes.c_size_t
         lib.i2r_debug_trace.argtypes = [vp, i32, i32]
         lib.i2r_debug_flags.argtypes = [i32]
+        if "i2r_debug_chain_flags" in EXPORTS:
+            lib.i2r_debug_chain_flags.argtypes = [i32]
         if "i2r_debug_hang_buffer" in EXPORTS:      # tools/hang_hunt.py drops it to load older builds (I2R_LIB)
             lib.i2r_debug_hang_buffer.argtypes = [vp]
         lib.i2r_stem_conv3x3s2.argtypes = [vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, vp]

@@ -261,6 +261,13 @@ class BackboneProgram:
     def run(self, r, x):
         """x: fp32 NCHW [S,3,H,W] on the device -> list of fp16 NHWC branch maps after stage3."""
         h = r.stem(x, self.stem_w, self.stem_scale, self.stem_bias, 64)
+        # with I2R_HALO_CHAIN=1 consecutive halo-kernel launches (layer1's 13 convs, the 8 BasicBlock layers of every
+        # module) run as chained grids; everything else (stride-2 / resampling problems, upsum) flushes the open chain
+        # first.  Default: the context is inert and every layer is its own launch.
+        with r.chain():
+            return self._run_from_stem(r, h)
+
+    def _run_from_stem(self, r, h):
         h = r.conv(self.conv2, h)
         for u in self.layer1:
             h = self._bottleneck(r, u, h)

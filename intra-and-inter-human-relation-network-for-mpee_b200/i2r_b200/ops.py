@@ -143,8 +143,54 @@ class ConvLayer:
         return self._halves
 
 
+def halo_smem_bytes(p):
+    """Shared-memory traffic conv_halo_kernel generates for one problem, in bytes (the kernel's binding resource at
+    these widths): per 128-pixel tile the tensor core reads A (128 x 16 fp16 = 4 KB) and B (Npad x 16 fp16)
+    for every (tap, K=16 step) MMA plus the bias MMA, the TMA unit writes the halo tile of every 64-channel K-chunk and
+    -- when the weight image does not stay resident (> 120 KB) -- the whole weight image, and a staged fp16 output tile
+    is written once and read once.  Split-operand problems run 3 K passes and store hi | lo."""
+    split = 3 if (p.flags & capi.F_SPLIT) else 1
+    npix = p.NB * p.IH * p.IW
+    if p.ntaps == 1 and npix % 8 == 0:
+        tiles = -(-npix // 128)
+    else:
+        tiles = p.NB * (-(-p.IW // 8)) * (-(-p.IH // 16))
+    ksteps = -(-p.Cin // 16) * split
+    mma = (p.ntaps * ksteps + 1) * (128 * 32 + p.Npad * 32)
+    halo = 2 if p.ntaps == 9 else 0
+    a_in = -(-p.Cin // 64) * split * (8 + halo) * (16 + halo) * 128
+    w_image = (p.ntaps * -(-p.Cin // 64) * split + 1) * p.Npad * 128
+    w_in = w_image if w_image > 120 * 1024 else 0
+    out = 2 * 128 * p.Cout * 2 * (2 if split == 3 else 1)
+    return tiles * (mma + a_in + w_in + out)
+
+
 def _stream_ptr():
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+class _Chain:
+    def __init__(self, runner):
+        self.r = runner
+        self.outer = False
+
+    def __enter__(self):
+        r = self.r
+        if r._chain is not None or not r.chain_enabled or not r.use_tma or r._in_parallel:
+            self.outer = True        # nested, disabled or inside concurrent branches: plain launches
+        else:
+            r._chain = []
+        return self
+
+    def __exit__(self, exc_type, exc, tb):
+        r = self.r
+        if not self.outer:
+            try:
+                if exc_type is None:
+                    r._flush_chain()
+            finally:
+                r._chain = None
+        return False
 
 
 class Runner:
@@ -164,6 +210,16 @@ class Runner:
         self.timing = None     # bench.py: list of (start_event, end_event, algorithmic_flops, nprob) per igemm launch
         self._side_streams = []
         self.concurrent_branches = __import__("os").environ.get("I2R_CONCURRENT_BRANCHES", "1") != "0"
+        # chained halo launches (Runner.chain), I2R_HALO_CHAIN=1.  Off by default: bit-identical to separate launches
+        # (tests/test_halo_chain_gpu.py) but not faster -- with the hand-shake removed entirely a chained HRNet module
+        # takes exactly as long as its eight PDL-overlapped launches (180.6 vs 181.2 us at 32 crops), because each layer's
+        # critical path is the CTAs streaming the 192-channel weights, not the launch boundary
+        # (profiles/r02_chain_mode.txt)
+        self.chain_enabled = __import__("os").environ.get("I2R_HALO_CHAIN", "0") == "1"
+        self._chain = None       # open chain: list of layers (lists of ConvProblem)
+        self._chain_ws = None    # completion counters of the chained launches (grown on demand, zeroed per launch)
+        self._in_parallel = 0
+        self.chains = 0          # chained launches made (bench.py / tests)
 
     # ------------------------------------------------------------------ independent launch chains
     def parallel(self, chains):
@@ -175,6 +231,13 @@ class Runner:
         fraction of the SMs each (lib/models/hrformer.py:1714-1731 runs them one after the other)."""
         if len(chains) == 1 or self.device.type != "cuda" or not self.concurrent_branches:
             return [c() for c in chains]
+        self._in_parallel += 1      # CTAs of a chained launch wait for each other: never two of them at once
+        try:
+            return self._parallel(chains)
+        finally:
+            self._in_parallel -= 1
+
+    def _parallel(self, chains):
         main = torch.cuda.current_stream(self.device)
         while len(self._side_streams) < len(chains) - 1:
             self._side_streams.append(torch.cuda.Stream(device=self.device))
@@ -334,7 +397,61 @@ class Runner:
             probs.append(p)
         return probs, out
 
+    # ------------------------------------------------------------------ chained launches
+    def chain(self):
+        """Context manager: the conv / conv_group launches issued inside -- dependent layers of halo-kernel problems,
+        e.g. the conv1 / conv2 sequence of an HRNet module's BasicBlocks -- are collected and run as ONE persistent grid
+        (i2r_conv_halo_chain: per-image completion counters instead of launch boundaries).  Outputs are allocated as
+        usual and must not be read by anything else before the context closes.  Falls back to one launch per layer when
+        the chain does not qualify; a launch with problems the halo kernel does not take flushes the chain first."""
+        return _Chain(self)
+
+    def _flush_chain(self):
+        layers, self._chain = self._chain, []
+        if not layers:
+            return
+        chained = False
+        if len(layers) > 1:
+            flat = [p for layer in layers for p in layer]
+            arr = (capi.ConvProblem * len(flat))(*flat)
+            need = int(self.lib.i2r_conv_halo_chain_workspace(arr, len(flat)))
+            if self._chain_ws is None or self._chain_ws.numel() * 4 < need:
+                self._chain_ws = torch.zeros(max(4096, need // 4 * 2), dtype=torch.int32, device=self.device)
+            counts = (ctypes.c_int * len(layers))(*[len(layer) for layer in layers])
+            if self.timing is not None:
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+            rc = self.lib.i2r_conv_halo_chain(arr, counts, len(layers), self._chain_ws.data_ptr(),
+                                              self._chain_ws.numel() * 4, _stream_ptr())
+            if rc == 0:
+                chained = True
+                self.launches += 1
+                self.chains += 1
+                if self.timing is not None:
+                    e1.record()
+                    flops = sum(2.0 * p.NB * p.OH * p.OW * p.Cout * p.Cin * p.ntaps for p in flat)
+                    self.timing.append((e0, e1, flops, len(flat), sum(halo_smem_bytes(p) for p in flat)))
+            elif rc != capi.E_UNSUPPORTED:
+                capi.check(rc, "i2r_conv_halo_chain")
+        if not chained:
+            for layer in layers:
+                self._launch_now(layer)
+
     def launch(self, problems):
+        if self._chain is not None and not self._in_parallel:
+            halo = all(not (p.flags & (capi.F_OUT_T16 | capi.F_OUT_F32 | capi.F_OUT_NCHW_F32)) and self.use_tma and
+                       self.lib.i2r_conv_halo_supported(ctypes.byref(p)) for p in problems)
+            room = (len(self._chain) < capi.I2R_MAX_CHAIN_LAYERS and len(problems) <= capi.I2R_MAX_GROUP and
+                    sum(len(layer) for layer in self._chain) + len(problems) <= capi.I2R_MAX_CHAIN_PROBLEMS)
+            if halo and not room:
+                self._flush_chain()
+            if halo:
+                self._chain.append(list(problems))
+                return
+            self._flush_chain()
+        self._launch_now(problems)
+
+    def _launch_now(self, problems):
         if self.timing is not None:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
@@ -357,7 +474,8 @@ class Runner:
         if self.timing is not None:
             e1.record()
             flops = sum(2.0 * p.NB * p.OH * p.OW * p.Cout * p.Cin * p.ntaps for p in problems)
-            self.timing.append((e0, e1, flops, len(problems)))
+            smem = sum(halo_smem_bytes(p) for p in tma) if not gen else 0
+            self.timing.append((e0, e1, flops, len(problems), smem))
 
     def conv(self, L, x, **kw):
         probs, out = self.problems(L, x, **kw)
@@ -602,6 +720,21 @@ class Runner:
         self.launches += 1
         return out
 
+
+
+def _flushes_chain(fn):
+    def wrapped(self, *a, **kw):
+        if self._chain:          # an open chain with deferred layers: they come first in stream order
+            self._flush_chain()
+        return fn(self, *a, **kw)
+    wrapped.__name__, wrapped.__doc__ = fn.__name__, fn.__doc__
+    return wrapped
+
+
+for _name in ("parallel", "stem", "mask_res_stem", "maxpool", "layernorm", "add", "upsum", "attention", "attention_tc",
+              "encoder_tail", "dwconv3x3", "upsum_bilinear", "layernorm_padded", "ln_window_gather", "window_scatter_add",
+              "window_attention"):
+    setattr(Runner, _name, _flushes_chain(getattr(Runner, _name)))
 
 class EncoderTailParams:
     """Device-resident operand image of i2r_encoder_tail for one encoder layer."""

@@ -21,6 +21,7 @@ class EmuRunner(Runner):
         self.launches = 0
         self.split = False
         self.device = torch.device("cpu")
+        self._chain, self.chain_enabled, self._in_parallel, self.chains = None, False, 0, 0   # no chained launches here
 
     def launch(self, problems):
         for p in problems:

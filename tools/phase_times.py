@@ -25,25 +25,35 @@ model(x, pm, length)
 torch.cuda.synchronize()
 
 records = []
+pending = [[]]
 
 
 def wrap(name):
     orig = getattr(ops.Runner, name)
 
     def f(self, *a, **kw):
+        if name == "_flush_chain":
+            pending[0] = [list(layer) for layer in (self._chain or [])] if len(self._chain or []) > 1 else []
+            if not pending[0]:       # nothing or a single layer: the inner _launch_now records it
+                return orig(self, *a, **kw)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         out = orig(self, *a, **kw)
         e1.record()
         desc = name
-        if name == "launch":
+        if name == "_launch_now":
             desc = "conv[" + ",".join("%dx%d:%d>%d%s" % (p.IH, p.IW, p.Cin, p.Cout, "k%d" % p.ntaps) for p in a[0]) + "]"
+        if name == "_flush_chain":
+            if not pending[0]:
+                return out
+            desc = "chain[%d layers: %s]" % (len(pending[0]), " | ".join(
+                ",".join("%dx%d:%d>%d%s" % (p.IH, p.IW, p.Cin, p.Cout, "k%d" % p.ntaps) for p in layer) for layer in pending[0][:2]))
         records.append((desc, e0, e1))
         return out
     setattr(ops.Runner, name, f)
 
 
-for n in ("launch", "stem", "maxpool", "layernorm", "add", "upsum", "attention", "attention_tc", "encoder_tail", "dwconv3x3",
+for n in ("_launch_now", "_flush_chain", "stem", "maxpool", "layernorm", "add", "upsum", "attention", "attention_tc", "encoder_tail", "dwconv3x3",
           "upsum_bilinear", "layernorm_padded", "ln_window_gather", "window_scatter_add", "window_attention"):
     wrap(n)
 reps = 3
