@@ -22,6 +22,13 @@
 //                 TMEM lane quadrant, each owning half of the output channels.
 //   grid        : persistent; each problem of a grouped launch owns a contiguous CTA range sized
 //                 by its share of the work, CTAs stride over that problem's tiles.
+//   stride 2    : a stride-2 3x3 convolution (HRNet transitions and fuse chains, the second stem convolution) reads,
+//                 for an 8x16 OUTPUT tile, the (2*8+1) x (2*16+1) input pixels around it.  They are staged as FOUR
+//                 PARITY PLANES -- TMA boxes with elementStrides (1, 2, 2, 1), i.e. every other pixel in x and y:
+//                 (row, col) parities ee (17 lines x 9 px), eo (17 x 8), oe (16 x 9), oo (16 x 8) relative to the
+//                 top-left input pixel (2*y0 - 1, 2*x0 - 1).  Inside a plane the pixels a tap needs for the 128 outputs
+//                 are again a shifted dense window (tap (dy, dx): plane (dy == 0, dx == 0), shifted by one line if dy = +1
+//                 and by one pixel if dx = +1), so the same descriptor-window MMAs apply with a per-tap (offset, SBO).
 #include <cuda.h>
 
 #include <cstdio>
@@ -43,6 +50,8 @@ struct HaloProblem {
   int NB, H, W, C, Cout, Npad;
   int lo_off;          // split mode: channel offset hi -> lo inside output / addend rows
   int ntaps, halo;
+  int s2;              // stride-2 3x3: four parity planes per activation stage (see the header comment)
+  int add1_shift;      // add1 is a tensor of (H >> s) x (W >> s) pixels, read with nearest up-sampling
   int KCH, nkc;        // channels per A stage, A stages per tile (split-operand mode: 3 * nkr)
   int nkr, split;      // real 64-channel K-chunks of the input; split-operand mode (I2R_F_SPLIT)
   int kgp, nchp;       // packed-weight geometry: k-groups per packed chunk, packed chunks per tap
@@ -85,6 +94,8 @@ struct HaloGroupT {
   static constexpr bool kChain = NL > 1;   // chained launches are a separate kernel instantiation (CH below)
   CUtensorMap amap[NP];
   CUtensorMap omap[NP][2];   // staged output: hi (or only) tile, lo tile of a pair tensor
+  static constexpr int NP2 = NL > 1 ? 1 : NP;   // (chained launches take no stride-2 problems: parameter space)
+  CUtensorMap amap2[NP2][3];  // stride-2 problems: the eo / oe / oo parity planes (amap = ee)
   unsigned long long* trace;   // optional event trace (tools/trace_halo.py): four role regions of trace_cap (tag<<32|tile, clock64) pairs
   int trace_cta, trace_cap;
   int dbg;                     // debug ablations (i2r_debug_flags): 1 = epilogue hand-shake only, 2 = no global stores / residual loads
@@ -124,7 +135,7 @@ __device__ __forceinline__ HaloProblem load_problem(const HaloProblem& s) {
   HaloProblem p;
   p.x = opaque(s.x); p.w = opaque(s.w); p.add0 = opaque(s.add0); p.add1 = opaque(s.add1); p.y = opaque(s.y);
   p.NB = opaque(s.NB); p.H = opaque(s.H); p.W = opaque(s.W); p.C = opaque(s.C); p.Cout = opaque(s.Cout); p.lo_off = opaque(s.lo_off);
-  p.Npad = opaque(s.Npad); p.ntaps = opaque(s.ntaps); p.halo = opaque(s.halo); p.KCH = opaque(s.KCH);
+  p.Npad = opaque(s.Npad); p.ntaps = opaque(s.ntaps); p.halo = opaque(s.halo); p.KCH = opaque(s.KCH); p.s2 = opaque(s.s2); p.add1_shift = opaque(s.add1_shift);
   p.nkc = opaque(s.nkc); p.nkr = opaque(s.nkr); p.split = opaque(s.split); p.kgp = opaque(s.kgp); p.nchp = opaque(s.nchp); p.tiles_x = opaque(s.tiles_x);
   p.tiles_per_img = opaque(s.tiles_per_img); p.ntiles = opaque(s.ntiles);
   p.in_pix_stride = opaque(s.in_pix_stride); p.out_pix_stride = opaque(s.out_pix_stride);
@@ -259,14 +270,30 @@ __device__ __forceinline__ void issue_ksteps_g(uint32_t d_tmem, uint32_t a_lo, u
     mma_g<PAIR>(d_tmem, desc64(a_lo + 2 * k2, a_hi), desc64(b_lo + 2 * k2, b_hi), idesc, k2 ? 1u : acc_first);
 }
 
-template <int NTAPS, int KS, bool PAIR>
+// Stride-2 parity planes inside one activation stage (byte offsets, all multiples of 1024 so that every plane keeps the
+// SWIZZLE_128B phase of a stage base): ee 17 x 9 rows | eo 17 x 8 | oe 16 x 9 | oo 16 x 8 rows of 128 bytes.
+constexpr uint32_t S2_EE = 0, S2_EO = 20480, S2_OE = 37888, S2_OO = 56320, S2_STAGE = 72704;
+constexpr uint32_t S2_TX = (17 * 9 + 17 * 8 + 16 * 9 + 16 * 8) * 128;
+// tap t = (dy + 1) * 3 + (dx + 1): descriptor start offset in 16-byte units and whether its plane is 9 pixels wide
+__device__ __forceinline__ constexpr uint32_t s2_tap_off(int t) {
+  return (t == 0 ? S2_EE : t == 1 ? S2_EO : t == 2 ? S2_EE + 128 : t == 3 ? S2_OE : t == 4 ? S2_OO : t == 5 ? S2_OE + 128
+          : t == 6 ? S2_EE + 9 * 128 : t == 7 ? S2_EO + 8 * 128 : S2_EE + 10 * 128) >> 4;
+}
+__device__ __forceinline__ constexpr bool s2_tap_wide(int t) { return t != 1 && t != 4 && t != 7; }
+template <int NTAPS, int S2>
+__device__ __forceinline__ constexpr uint32_t tap_off16(int tap) {
+  return S2 ? s2_tap_off(tap) : (NTAPS == 9 ? static_cast<uint32_t>(((tap / 3) * (T_TW + 2) + (tap % 3)) * 8) : 0u);
+}
+
+template <int NTAPS, int KS, bool PAIR, int S2 = 0>
 __device__ __forceinline__ void issue_taps(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_tap,
-                                           uint32_t b_hi, uint32_t idesc, uint32_t acc_first) {
-  constexpr int PW = NTAPS == 9 ? T_TW + 2 : T_TW;
+                                           uint32_t b_hi, uint32_t idesc, uint32_t acc_first, uint32_t a_hi8 = 0) {
+  // (S2: a_hi = descriptor high word of the 9-pixel-wide planes, a_hi8 of the 8-pixel-wide ones)
 #pragma unroll
   for (int tap = 0; tap < NTAPS; ++tap) {
-    const uint32_t a_t = a_lo + (NTAPS == 9 ? static_cast<uint32_t>(((tap / 3) * PW + (tap % 3)) * 8) : 0u);
-    issue_ksteps_g<KS, PAIR>(d_tmem, a_t, a_hi, b_lo + tap * b_tap, b_hi, idesc, tap ? 1u : acc_first);
+    const uint32_t a_t = a_lo + tap_off16<NTAPS, S2>(tap);
+    issue_ksteps_g<KS, PAIR>(d_tmem, a_t, (S2 && !s2_tap_wide(tap)) ? a_hi8 : a_hi, b_lo + tap * b_tap, b_hi, idesc,
+                             tap ? 1u : acc_first);
   }
 }
 
@@ -283,14 +310,14 @@ constexpr uint32_t B_AFULL = 0, B_AEMPTY = 64, B_ACCFULL = 128, B_ACCEMPTY = 144
 // MODE 0: one CTA per tile (cta_group::1).  MODE 1: leader of a CTA pair (cta_group::2: M256, waits for the peer's
 // operands as well, commits arrive in both CTAs).  MODE 2: the peer's SHADOW of this loop: it waits for the peer's own
 // operand barriers in the same order and forwards each completion to the leader's p-barrier (no MMAs, no commits).
-template <int NTAPS, int MODE>
+template <int NTAPS, int MODE, int S2 = 0>
 __device__ __forceinline__ void mma_role(const HaloProblem& P, const int cta, const uint32_t sbase,
                                          const uint32_t tmem_base, const uint32_t ncols, unsigned long long* tr,
                                          const int trcap, const int dbg, const int iw) {
   constexpr bool PAIR = MODE != 0;
   constexpr bool ISSUE = MODE != 2;
   constexpr int HALO = NTAPS == 9 ? 1 : 0;
-  constexpr int PW = T_TW + 2 * HALO;   // halo line = PW pixels = PW 128-byte rows (dense TMA box)
+  constexpr int PW = S2 ? T_TW + 1 : T_TW + 2 * HALO;   // halo line = PW pixels = PW 128-byte rows (dense TMA box)
   constexpr uint32_t A_SBO = PW * 128;
   const uint32_t bar_afull = sbase + B_AFULL, bar_aempty = sbase + B_AEMPTY, bar_wfull = sbase + B_WFULL,
                  bar_wempty = sbase + B_WEMPTY;
@@ -304,6 +331,7 @@ __device__ __forceinline__ void mma_role(const HaloProblem& P, const int cta, co
   const uint32_t idesc = make_idesc_f16(PAIR ? 256 : 128, Npad);
   const uint32_t b_hi = sw128_desc_hi(1024, 0);
   const uint32_t a_hi = sw128_desc_hi(A_SBO, 0);   // base_offset 0: the swizzle XOR follows absolute smem address bits
+  const uint32_t a_hi8 = sw128_desc_hi(T_TW * 128, 0);   // stride 2: the 8-pixel-wide parity planes
   const uint32_t w_stage16 = P.w_stage_bytes >> 4;                         // one (tap, K-chunk) block in shared memory
   const uint32_t b_tap = static_cast<uint32_t>(P.nkc) * w_stage16;         // resident: next tap
   const uint32_t w_slot16 = P.w_slot_bytes >> 4;                           // streamed: one ring slot (TG blocks)
@@ -376,10 +404,10 @@ __device__ __forceinline__ void mma_role(const HaloProblem& P, const int cta, co
         // one straight-line burst of NTAPS x ksteps MMAs issued by the elected lane
         if (ISSUE && leader && !(dbg & 8)) {
           switch (ksteps) {
-            case 4: issue_taps<NTAPS, 4, PAIR>(d_tmem, a_lo, a_hi, b_lo_kc, b_tap, b_hi, idesc, acc_kc); break;
-            case 3: issue_taps<NTAPS, 3, PAIR>(d_tmem, a_lo, a_hi, b_lo_kc, b_tap, b_hi, idesc, acc_kc); break;
-            case 2: issue_taps<NTAPS, 2, PAIR>(d_tmem, a_lo, a_hi, b_lo_kc, b_tap, b_hi, idesc, acc_kc); break;
-            default: issue_taps<NTAPS, 1, PAIR>(d_tmem, a_lo, a_hi, b_lo_kc, b_tap, b_hi, idesc, acc_kc); break;
+            case 4: issue_taps<NTAPS, 4, PAIR, S2>(d_tmem, a_lo, a_hi, b_lo_kc, b_tap, b_hi, idesc, acc_kc, a_hi8); break;
+            case 3: issue_taps<NTAPS, 3, PAIR, S2>(d_tmem, a_lo, a_hi, b_lo_kc, b_tap, b_hi, idesc, acc_kc, a_hi8); break;
+            case 2: issue_taps<NTAPS, 2, PAIR, S2>(d_tmem, a_lo, a_hi, b_lo_kc, b_tap, b_hi, idesc, acc_kc, a_hi8); break;
+            default: issue_taps<NTAPS, 1, PAIR, S2>(d_tmem, a_lo, a_hi, b_lo_kc, b_tap, b_hi, idesc, acc_kc, a_hi8); break;
           }
         }
       } else {
@@ -397,12 +425,13 @@ __device__ __forceinline__ void mma_role(const HaloProblem& P, const int cta, co
 #pragma unroll
             for (int j = 0; j < TG; ++j) {
               const int tap = tg * TG + j;
-              const uint32_t a_t = a_lo + (HALO ? static_cast<uint32_t>(((tap / 3) * PW + (tap % 3)) * 8) : 0u);
+              const uint32_t a_t = a_lo + tap_off16<NTAPS, S2>(tap);
+              const uint32_t a_h = (S2 && !s2_tap_wide(tap)) ? a_hi8 : a_hi;
               switch (ksteps) {
-                case 4: issue_ksteps_g<4, PAIR>(d_tmem, a_t, a_hi, b_lo + j * w_stage16, b_hi, idesc, 1u); break;
-                case 3: issue_ksteps_g<3, PAIR>(d_tmem, a_t, a_hi, b_lo + j * w_stage16, b_hi, idesc, 1u); break;
-                case 2: issue_ksteps_g<2, PAIR>(d_tmem, a_t, a_hi, b_lo + j * w_stage16, b_hi, idesc, 1u); break;
-                default: issue_ksteps_g<1, PAIR>(d_tmem, a_t, a_hi, b_lo + j * w_stage16, b_hi, idesc, 1u); break;
+                case 4: issue_ksteps_g<4, PAIR>(d_tmem, a_t, a_h, b_lo + j * w_stage16, b_hi, idesc, 1u); break;
+                case 3: issue_ksteps_g<3, PAIR>(d_tmem, a_t, a_h, b_lo + j * w_stage16, b_hi, idesc, 1u); break;
+                case 2: issue_ksteps_g<2, PAIR>(d_tmem, a_t, a_h, b_lo + j * w_stage16, b_hi, idesc, 1u); break;
+                default: issue_ksteps_g<1, PAIR>(d_tmem, a_t, a_h, b_lo + j * w_stage16, b_hi, idesc, 1u); break;
               }
             }
             commit_g<PAIR>(bar_wempty + 8 * (w_first + ws));
@@ -558,6 +587,7 @@ struct EpiArgs {
   const CUtensorMap* omap;       // [2]
   int* done;                     // chained launch: this problem's per-image completion counters (else null)
   int img_px, strip, cdbg;
+  int add1_shift;                // add1 pixel = (y >> s, x >> s) of a (H >> s) x (W >> s) tensor
 };
 __device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2, int c3) {
   asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.tile.bulk_group [%0, {%2,%3,%4,%5}], [%1];"
@@ -708,7 +738,8 @@ __device__ __forceinline__ void epilogue_role(const EpiArgs E, const int cta, co
     const int p = (n * E.H + y) * E.W + x;                       // pixel index (< 2^31)
     const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + static_cast<uint32_t>(acc) * (ncols >> 1);
     const __half* a0 = E.add0 + static_cast<int64_t>(p) * E.add_pix_stride;
-    const __half* a1 = E.add1 + static_cast<int64_t>(p) * E.add_pix_stride;
+    const int p1 = E.add1_shift ? ((n * (E.H >> E.add1_shift) + (y >> E.add1_shift)) * (E.W >> E.add1_shift) + (x >> E.add1_shift)) : p;
+    const __half* a1 = E.add1 + static_cast<int64_t>(p1) * E.add_pix_stride;
     bool waited = false;
     so.template begin_tile<CH>(E);
     for (int c = cb; c < ce; c += EG) {
@@ -876,7 +907,8 @@ __device__ __forceinline__ void epilogue_fast(const EpiArgs E, const int cta, co
     const uint32_t taddr = lane_taddr + static_cast<uint32_t>(acc) * (ncols >> 1);
     so.template begin_tile<CH>(E);
     const __half* a0 = E.add0 + static_cast<int64_t>(p) * E.add_pix_stride;
-    const __half* a1 = E.add1 + static_cast<int64_t>(p) * E.add_pix_stride;
+    const int p1 = E.add1_shift ? ((n * (E.H >> E.add1_shift) + (y >> E.add1_shift)) * (E.W >> E.add1_shift) + (x >> E.add1_shift)) : p;
+    const __half* a1 = E.add1 + static_cast<int64_t>(p1) * E.add_pix_stride;
     __half* yp = ybase + static_cast<int64_t>(p) * E.out_pix_stride;
     for (int c = cb; c < ce; c += G) {
       uint4 r0[G], r1[G];
@@ -965,7 +997,8 @@ __device__ __forceinline__ void epilogue_split_fast(const EpiArgs E, const int c
     const int p = (n * E.H + y) * E.W + x;
     const uint32_t taddr = lane_taddr + static_cast<uint32_t>(acc) * (ncols >> 1);
     const __half* a0 = E.add0 + static_cast<int64_t>(p) * E.add_pix_stride;
-    const __half* a1 = E.add1 + static_cast<int64_t>(p) * E.add_pix_stride;
+    const int p1 = E.add1_shift ? ((n * (E.H >> E.add1_shift) + (y >> E.add1_shift)) * (E.W >> E.add1_shift) + (x >> E.add1_shift)) : p;
+    const __half* a1 = E.add1 + static_cast<int64_t>(p1) * E.add_pix_stride;
     __half* yp = ybase + static_cast<int64_t>(p) * E.out_pix_stride;
     so.template begin_tile<CH>(E);
     for (int c = cb; c < ce; c += G) {
@@ -1198,6 +1231,11 @@ __global__ void __launch_bounds__(T_THREADS, 1) conv_halo_kernel(const __grid_co
       // ================================================= activation producer: one TMA box per (tile, K-chunk)
       const CUtensorMap* amap = &G.amap[pi];
       prefetch_tmap(amap);
+      if (P.s2) {
+        prefetch_tmap(&G.amap2[CH ? 0 : pi][0]);
+        prefetch_tmap(&G.amap2[CH ? 0 : pi][1]);
+        prefetch_tmap(&G.amap2[CH ? 0 : pi][2]);
+      }
       pdl_wait();   // activations come from the previous kernels (weights do not: warp 1 loads them right away)
       const int dual = P.w_resident;   // two MMA issuers, each with its own half-ring (see mma_role)
       const int a_half = dual ? P.a_stages >> 1 : P.a_stages;
@@ -1235,7 +1273,16 @@ __global__ void __launch_bounds__(T_THREADS, 1) conv_halo_kernel(const __grid_co
             // split-operand mode walks [x_hi | x_lo | x_hi]: hi at channel 0, lo at channel C of the source pixel
             const int third = kc / P.nkr, kr = kc - third * P.nkr;
             const int c0 = (third == 1 ? P.C : 0) + kr * 64;
-            if (CL && pair && rank != 0) {
+            if (P.s2) {
+              // stride 2: four parity planes of the (2*8+1) x (2*16+1) input pixels around the output tile
+              const uint32_t dst = a_base + s * P.a_stage_bytes;
+              const int xi = 2 * tx * T_TW - 1, yi = 2 * ty * T_TH - 1;
+              mbar_arrive_expect_tx(bar_afull + 8 * s, P.a_tx_bytes);
+              tma_load_4d(dst + S2_EE, amap, c0, xi, yi, n, bar_afull + 8 * s);
+              tma_load_4d(dst + S2_EO, &G.amap2[CH ? 0 : pi][0], c0, xi + 1, yi, n, bar_afull + 8 * s);
+              tma_load_4d(dst + S2_OE, &G.amap2[CH ? 0 : pi][1], c0, xi, yi + 1, n, bar_afull + 8 * s);
+              tma_load_4d(dst + S2_OO, &G.amap2[CH ? 0 : pi][2], c0, xi + 1, yi + 1, n, bar_afull + 8 * s);
+            } else if (CL && pair && rank != 0) {
               // the peer's tile is accounted on the leader's barrier (which expects both tiles' bytes)
               tma_load_4d_pair(a_base + s * P.a_stage_bytes, amap, c0, x0, y0, n, leader_afull + 8 * s);
             } else {
@@ -1307,7 +1354,8 @@ __global__ void __launch_bounds__(T_THREADS, 1) conv_halo_kernel(const __grid_co
     unsigned long long* trm = warp == 2 ? tr : nullptr;
     const int iw = warp - 2;
     if (!pair) {
-      if (P.ntaps == 9) mma_role<9, 0>(P, cta, sbase, tmem_base, ncols, trm, trace_cap, dbg, iw);
+      if (P.s2) mma_role<9, 0, 1>(P, cta, sbase, tmem_base, ncols, trm, trace_cap, dbg, iw);
+      else if (P.ntaps == 9) mma_role<9, 0>(P, cta, sbase, tmem_base, ncols, trm, trace_cap, dbg, iw);
       else mma_role<1, 0>(P, cta, sbase, tmem_base, ncols, trm, trace_cap, dbg, iw);
     } else if (CL && rank == 0) {      // leader of the pair: issues the M256 MMAs for both CTAs
       if (P.ntaps == 9) mma_role<9, CL ? 1 : 0>(P, cta, sbase, tmem_base, ncols, trm, trace_cap, dbg, iw);
@@ -1327,7 +1375,7 @@ __global__ void __launch_bounds__(T_THREADS, 1) conv_halo_kernel(const __grid_co
     E.out_pix_stride = P.out_pix_stride; E.add_pix_stride = P.add_pix_stride; E.plane = P.plane; E.flags = P.flags;
     E.pair = pair ? 1 : 0; E.rank = rank; E.ntiles_real = P.ntiles_real;
     E.o_bufs = P.o_bufs; E.o_base = sbase + P.o_off; E.o_tile_bytes = P.o_tile_bytes; E.omap = &G.omap[pi][0];
-    E.done = P.done; E.img_px = P.img_px; E.strip = P.strip; E.cdbg = cdbg;
+    E.done = P.done; E.img_px = P.img_px; E.strip = P.strip; E.cdbg = cdbg; E.add1_shift = P.add1_shift;
     const int ew = warp - 4;
     // chunks holding real channels, split over the warps of a lane quadrant
     const int n8 = (P.Cout + 7) >> 3, part8 = (n8 + (T_EPI_WARPS / 4) - 1) / (T_EPI_WARPS / 4);
@@ -1396,7 +1444,10 @@ EncodeTiledFn get_encode() {   // also used by attention_tc.cu
 
 // NHWC activation tensor as a 4-D TMA tensor (C, W, H, N); box = (64 channels, halo width, halo height, 1) with
 // 128-byte swizzle: one 128-byte shared-memory row per pixel.  Out-of-range pixels and channels read as zero.
-static int encode_amap(CUtensorMap* map, const void* x, int NB, int H, int W, int C, int pix_stride, int hw, int hh) {
+// estride = 2 (stride-2 convolutions): every other pixel in x and y, hw / hh are then the TRAVERSED extents (the box
+// holds ceil(hw / 2) x ceil(hh / 2) pixels; profiles/r02_tma_element_stride_probe.txt).
+static int encode_amap(CUtensorMap* map, const void* x, int NB, int H, int W, int C, int pix_stride, int hw, int hh,
+                       int estride = 1) {
   EncodeTiledFn enc = get_encode();
   if (!enc) {
     set_error("cuTensorMapEncodeTiled entry point unavailable");
@@ -1407,9 +1458,10 @@ static int encode_amap(CUtensorMap* map, const void* x, int NB, int H, int W, in
   const cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)NB};
   const cuuint64_t strides[3] = {pb, pb * W, pb * W * H};
   const cuuint32_t box[4] = {64, (cuuint32_t)hw, (cuuint32_t)hh, 1};
-  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(x), dims, strides, box, ones,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  const cuuint32_t es[4] = {1, (cuuint32_t)estride, (cuuint32_t)estride, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(x), dims, strides, box,
+                   estride == 1 ? ones : es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled failed (%d) for [%d,%d,%d,%d] pix_stride %d", (int)r, NB, H, W, C, pix_stride);
     return I2R_E_DEVICE;
@@ -1457,9 +1509,25 @@ extern "C" int i2r_conv_halo_supported(const i2r_conv_problem* P) {
   if (!P) return 0;
   const bool k1 = P->ntaps == 1 && P->dy[0] == 0 && P->dx[0] == 0;
   if (!(k1 || is_std3x3(*P))) return 0;
-  if (P->stride != 1 || P->in_shift != 0 || P->out_mul != 1 || P->out_offy != 0 || P->out_offx != 0) return 0;
-  if (P->OH != P->IH || P->OW != P->IW || P->OHf != P->OH || P->OWf != P->OW) return 0;
-  if ((P->add0 && P->add0_shift != 0) || (P->add1 && P->add1_shift != 0)) return 0;
+  if (P->in_shift != 0 || P->out_mul != 1 || P->out_offy != 0 || P->out_offx != 0) return 0;
+  if (P->OHf != P->OH || P->OWf != P->OW) return 0;
+  if (P->stride == 2) {
+    // stride-2 3x3, padding 1 (parity-plane staging): two 71 KB activation stages + the weights must fit
+    if (!is_std3x3(*P) || P->OH != (P->IH + 1) / 2 || P->OW != (P->IW + 1) / 2) return 0;
+    const uint32_t nkc = static_cast<uint32_t>((P->Cin + 63) / 64) * ((P->flags & I2R_F_SPLIT) ? 3u : 1u);
+    const uint32_t image = (9u * nkc + 1u) * P->Npad * 128u;
+    // (weights stay resident only if they fit beside the two stages; else a ring of two three-tap slots)
+    const bool resident = image <= T_W_RES_MAX && T_A_OFF + 2u * S2_STAGE + image + 128u <= T_MAX_SMEM;
+    const uint32_t wregion = resident ? image : 2u * 3u * P->Npad * 128u;
+    if (T_A_OFF + 2u * S2_STAGE + wregion + 128u > T_MAX_SMEM) return 0;
+  } else if (P->stride != 1 || P->OH != P->IH || P->OW != P->IW) {
+    return 0;
+  }
+  // the second addend may be a half-resolution tensor (nearest up-sampling by 2^add1_shift, HRNet fuse layers)
+  if (P->add0 && P->add0_shift != 0) return 0;
+  if (P->add1 && (P->add1_shift < 0 || P->add1_shift > 2 || (P->OH & ((1 << P->add1_shift) - 1)) ||
+                  (P->OW & ((1 << P->add1_shift) - 1))))
+    return 0;
   if (P->Cin % 16 != 0 || P->Npad > 256 || P->Npad % 16 != 0) return 0;
   if (P->KC != 64) return 0;
   if (P->in_pix_stride % 8 != 0) return 0;
@@ -1563,15 +1631,17 @@ static int plan_layer(GT& G, const int base, const i2r_conv_problem* probs, cons
     P.y = S.y;
     P.ntaps = S.ntaps;
     P.halo = S.ntaps == 9 ? 1 : 0;
+    P.s2 = S.stride == 2 ? 1 : 0;
     P.NB = S.NB;
-    P.H = S.IH;
-    P.W = S.IW;
-    const int64_t mtot = static_cast<int64_t>(S.NB) * S.IH * S.IW;
+    P.H = S.OH;          // tile geometry = OUTPUT pixels (== input pixels unless stride 2)
+    P.W = S.OW;
+    P.add1_shift = S.add1 ? S.add1_shift : 0;
+    const int64_t mtot = static_cast<int64_t>(S.NB) * S.OH * S.OW;
     P.plane = S.OHf * S.OWf;
-    P.img_px = S.IH * S.IW;
+    P.img_px = S.OH * S.OW;
     P.nimg = S.NB;
     P.strip = 0;
-    if (S.ntaps == 1 && mtot % 8 == 0) {  // pixels are independent: re-tile as an 8-wide strip
+    if (S.ntaps == 1 && mtot % 8 == 0 && !(S.add1 && S.add1_shift)) {  // pixels are independent: re-tile as an 8-wide strip
       P.NB = 1;
       P.W = 8;
       P.H = static_cast<int>(mtot / 8);
@@ -1598,11 +1668,16 @@ static int plan_layer(GT& G, const int base, const i2r_conv_problem* probs, cons
     const int hw = T_TW + 2 * P.halo, hh = T_TH + 2 * P.halo;
     P.a_tx_bytes = static_cast<uint32_t>(hh * hw * 128);          // full box, zero-filled parts included
     P.a_stage_bytes = (P.a_tx_bytes + 1023u) & ~1023u;            // stages stay 1024-byte aligned (SW128)
+    if (P.s2) {
+      P.a_tx_bytes = S2_TX;
+      P.a_stage_bytes = S2_STAGE;
+    }
     P.w_total_bytes = static_cast<uint32_t>(S.ntaps * P.nkc + 1) * S.Npad * 128;   // bias block + taps (global image)
     P.w_gstage = static_cast<uint32_t>(S.Npad) * 128;
     P.w_stage_bytes = P.pair ? P.w_gstage / 2 : P.w_gstage;      // pair mode: every CTA holds half of the rows
     const uint32_t w_cta_bytes = static_cast<uint32_t>(S.ntaps * P.nkc + 1) * P.w_stage_bytes;
     P.w_resident = w_cta_bytes <= T_W_RES_MAX ? 1 : 0;
+    if (P.s2 && T_A_OFF + 2u * S2_STAGE + w_cta_bytes + 128u > T_MAX_SMEM) P.w_resident = 0;   // stream instead
     P.w_slot_bytes = P.w_stage_bytes * (S.ntaps == 9 ? 3 : 1);
     uint32_t wregion;
     // streamed weights: the ring must cover the L2 round trip (~1300 cycles) at the rate the issuer drains it, so it
@@ -1615,7 +1690,7 @@ static int plan_layer(GT& G, const int base, const i2r_conv_problem* probs, cons
       if (astg > T_A_STAGES_MAX) astg = T_A_STAGES_MAX;
       astg &= ~1;   // two half-rings, one per MMA issuer
     } else {
-      astg = 3;
+      astg = P.s2 ? 2 : 3;
       while (astg > 2 && T_A_OFF + astg * P.a_stage_bytes + 3 * P.w_slot_bytes > T_MAX_SMEM) --astg;
       P.w_stages = static_cast<int>((T_MAX_SMEM - T_A_OFF - astg * P.a_stage_bytes) / P.w_slot_bytes);
       if (P.w_stages > T_W_STAGES_MAX) P.w_stages = T_W_STAGES_MAX;
@@ -1651,7 +1726,20 @@ static int plan_layer(GT& G, const int base, const i2r_conv_problem* probs, cons
     }
     P.a_stages = astg;
     {
-      int rc = encode_amap(&G.amap[base + i], S.x, P.NB, P.H, P.W, P.split ? 2 * P.C : P.C, S.in_pix_stride, hw, hh);
+      const int cphys = P.split ? 2 * P.C : P.C;
+      int rc;
+      if (P.s2 && GT::kChain) {
+        set_error("i2r_conv_halo_chain: stride-2 problems cannot be chained");
+        return I2R_E_UNSUPPORTED;
+      }
+      if (P.s2) {   // parity planes ee / eo / oe / oo: traversed extents 17 or 16 pixels by 33 or 32 lines, every other one kept
+        rc = encode_amap(&G.amap[base + i], S.x, S.NB, S.IH, S.IW, cphys, S.in_pix_stride, 17, 33, 2);
+        if (!rc) rc = encode_amap(&G.amap2[GT::kChain ? 0 : base + i][0], S.x, S.NB, S.IH, S.IW, cphys, S.in_pix_stride, 16, 33, 2);
+        if (!rc) rc = encode_amap(&G.amap2[GT::kChain ? 0 : base + i][1], S.x, S.NB, S.IH, S.IW, cphys, S.in_pix_stride, 17, 32, 2);
+        if (!rc) rc = encode_amap(&G.amap2[GT::kChain ? 0 : base + i][2], S.x, S.NB, S.IH, S.IW, cphys, S.in_pix_stride, 16, 32, 2);
+      } else {
+        rc = encode_amap(&G.amap[base + i], S.x, P.NB, P.H, P.W, cphys, S.in_pix_stride, hw, hh);
+      }
       if (rc) return rc;
     }
     P.w_off = T_A_OFF + static_cast<uint32_t>(astg) * P.a_stage_bytes;
@@ -1779,7 +1867,7 @@ static ByteRange range_of(const void* ptr, int64_t pixels, int64_t pix_stride, i
   return r;
 }
 static ByteRange in_range(const i2r_conv_problem& S) {
-  return range_of(S.x, static_cast<int64_t>(S.NB) * S.IH * S.IW, S.in_pix_stride, (S.flags & I2R_F_SPLIT) ? 2 * S.Cin : S.Cin);
+  return range_of(S.x, static_cast<int64_t>(S.NB) * S.IH * S.IW, S.in_pix_stride, (S.flags & I2R_F_SPLIT) ? 2 * S.Cin : S.Cin);   // (input pixels)
 }
 static ByteRange out_range(const i2r_conv_problem& S) {
   const int lo = S.pair_lo_offset > 0 ? S.pair_lo_offset : S.Cout;

@@ -150,15 +150,15 @@ def halo_smem_bytes(p):
     -- when the weight image does not stay resident (> 120 KB) -- the whole weight image, and a staged fp16 output tile
     is written once and read once.  Split-operand problems run 3 K passes and store hi | lo."""
     split = 3 if (p.flags & capi.F_SPLIT) else 1
-    npix = p.NB * p.IH * p.IW
+    npix = p.NB * p.OH * p.OW
     if p.ntaps == 1 and npix % 8 == 0:
         tiles = -(-npix // 128)
     else:
-        tiles = p.NB * (-(-p.IW // 8)) * (-(-p.IH // 16))
+        tiles = p.NB * (-(-p.OW // 8)) * (-(-p.OH // 16))
     ksteps = -(-p.Cin // 16) * split
     mma = (p.ntaps * ksteps + 1) * (128 * 32 + p.Npad * 32)
     halo = 2 if p.ntaps == 9 else 0
-    a_in = -(-p.Cin // 64) * split * (8 + halo) * (16 + halo) * 128
+    a_in = -(-p.Cin // 64) * split * ((8 + halo) * (16 + halo) * 128 if p.stride == 1 else 71808)
     w_image = (p.ntaps * -(-p.Cin // 64) * split + 1) * p.Npad * 128
     w_in = w_image if w_image > 120 * 1024 else 0
     out = 2 * 128 * p.Cout * 2 * (2 if split == 3 else 1)
@@ -356,7 +356,10 @@ class Runner:
         """Like problem(), but may split the output channels in two (see ConvLayer.halves).  Returns (list, out)."""
         std = (L.ntaps == 1 and L.dy[0] == 0 and L.dx[0] == 0) or (
             L.ntaps == 9 and all(L.dy[t] == t // 3 - 1 and L.dx[t] == t % 3 - 1 for t in range(9)))
-        split = (self.use_tma and std and L.stride == 1 and kw.get("in_shift", 0) == 0 and
+        # stride-2 3x3 problems (parity-plane staging, two 71 KB activation stages) only have room for weight-ring slots
+        # of <= 96 output channels: wider layers run as two halves as well
+        s2_wide = L.stride == 2 and L.ntaps == 9 and L.npad > 96
+        split = (self.use_tma and std and (L.stride == 1 or s2_wide) and kw.get("in_shift", 0) == 0 and
                  kw.get("out_mul", 1) == 1 and kw.get("out_mode", "nhwc16") == "nhwc16" and
                  kw.get("add0_shift", 0) == 0 and kw.get("add1_shift", 0) == 0 and
                  L.weight_bytes > self.TMA_WEIGHT_RESIDENT_MAX and L.cout == L.npad and L.cout % 32 == 0 and
@@ -387,7 +390,9 @@ class Runner:
             return [p], out
         out = kw.pop("out", None)
         if out is None:
-            out = torch.empty((x.shape[0], x.shape[1], x.shape[2], L.cout), dtype=torch.float16, device=x.device)
+            oh, ow = kw["ohow"] if kw.get("ohow") else ((x.shape[1] + L.stride - 1) // L.stride,
+                                                        (x.shape[2] + L.stride - 1) // L.stride)
+            out = torch.empty((x.shape[0], oh, ow, L.cout), dtype=torch.float16, device=x.device)
         add0, add1 = kw.pop("add0", None), kw.pop("add1", None)
         probs = []
         for c0, sub in L.halves():
@@ -440,6 +445,7 @@ class Runner:
     def launch(self, problems):
         if self._chain is not None and not self._in_parallel:
             halo = all(not (p.flags & (capi.F_OUT_T16 | capi.F_OUT_F32 | capi.F_OUT_NCHW_F32)) and self.use_tma and
+                       p.stride == 1 and
                        self.lib.i2r_conv_halo_supported(ctypes.byref(p)) for p in problems)
             room = (len(self._chain) < capi.I2R_MAX_CHAIN_LAYERS and len(problems) <= capi.I2R_MAX_GROUP and
                     sum(len(layer) for layer in self._chain) + len(problems) <= capi.I2R_MAX_CHAIN_PROBLEMS)

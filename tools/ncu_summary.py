@@ -15,6 +15,8 @@ want = ["Kernel Name", "gpu__time_duration.sum", "launch__grid_size", "launch__r
         "lts__throughput.avg.pct_of_peak_sustained_elapsed", "sm__warps_active.avg.pct_of_peak_sustained_active",
         "smsp__inst_executed.sum", "sm__cycles_elapsed.max", "smsp__cycles_active.avg",
         "l1tex__data_pipe_tc_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed"]
+# every shared-memory / L1 data-bank metric the report holds (the halo kernel's binding resource)
+want += [h for h in hdr if ("mem_shared" in h or "data_bank" in h) and "pct_of_peak_sustained_elapsed" in h and h not in want]
 for w in want:
     if w not in hdr:
         continue

@@ -16,8 +16,10 @@ yaml = sys.argv[2] if len(sys.argv) > 2 else "coco/interformer_coco_w48_pure_en6
 cfg, model, sd = build_model(yaml)
 model = model.cuda()
 model.use_cuda_graph = False
-length = [4] * images
-x, pm = inputs_for(length)
+persons = int(sys.argv[3]) if len(sys.argv) > 3 else 4
+length = [persons] * images
+hw = (int(sys.argv[4]), int(sys.argv[5])) if len(sys.argv) > 5 else (256, 192)
+x, pm = inputs_for(length, *hw)
 x, pm = x.cuda(), pm.cuda()
 for _ in range(2):
     model(x, pm, length)
