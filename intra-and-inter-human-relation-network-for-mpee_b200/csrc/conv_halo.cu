@@ -54,6 +54,11 @@ struct HaloProblem {
   int add1_shift;      // add1 is a tensor of (H >> s) x (W >> s) pixels, read with nearest up-sampling
   int KCH, nkc;        // channels per A stage, A stages per tile (split-operand mode: 3 * nkr)
   int nkr, split;      // real 64-channel K-chunks of the input; split-operand mode (I2R_F_SPLIT)
+  int sp2;             // split-operand problem in the stage-once scheme (mma_role_split): nkc = 2 * nkr activation stages
+                       // (x_hi, x_lo per real chunk) and two weight blocks (W_hi, W_lo) per (tap, real chunk)
+  uint32_t w_smem_bytes;   // resident weights: bytes of the shared-memory copy (sp2: the W_hi duplicate is dropped)
+  int w_bps;               // sp2, streamed: weight blocks per ring slot; the blocks of a tile come in consumption order
+                           // (real chunk, tap, [W_hi, W_lo]) and are cut into slots of w_bps blocks (1, 2, 3 or 6)
   int kgp, nchp;       // packed-weight geometry: k-groups per packed chunk, packed chunks per tap
   int tiles_x, tiles_per_img, ntiles;
   int in_pix_stride, out_pix_stride, add_pix_stride;
@@ -78,6 +83,7 @@ struct HaloProblem {
   // output mode without a tensor-map form).
   int o_bufs;
   uint32_t o_off, o_tile_bytes;
+  int res_tma;         // the first addend arrives through TMA into the staged-output buffer (see StageOut)
   // chained launch (several dependent layers in one grid, see conv_halo_kernel): `done[n]` counts the output pixels of
   // image n that have reached global memory; a tile of a consumer waits until the images it reads are complete in every
   // producer `dep[i]` (image-local when producer and consumer share the image geometry, else dep_whole[i] = all of the
@@ -96,6 +102,7 @@ struct HaloGroupT {
   CUtensorMap omap[NP][2];   // staged output: hi (or only) tile, lo tile of a pair tensor
   static constexpr int NP2 = NL > 1 ? 1 : NP;   // (chained launches take no stride-2 problems: parameter space)
   CUtensorMap amap2[NP2][3];  // stride-2 problems: the eo / oe / oo parity planes (amap = ee)
+  CUtensorMap rmap[NP2][2];   // res_tma problems: the first addend (hi, lo) with the geometry of omap
   unsigned long long* trace;   // optional event trace (tools/trace_halo.py): four role regions of trace_cap (tag<<32|tile, clock64) pairs
   int trace_cta, trace_cap;
   int dbg;                     // debug ablations (i2r_debug_flags): 1 = epilogue hand-shake only, 2 = no global stores / residual loads
@@ -136,7 +143,8 @@ __device__ __forceinline__ HaloProblem load_problem(const HaloProblem& s) {
   p.x = opaque(s.x); p.w = opaque(s.w); p.add0 = opaque(s.add0); p.add1 = opaque(s.add1); p.y = opaque(s.y);
   p.NB = opaque(s.NB); p.H = opaque(s.H); p.W = opaque(s.W); p.C = opaque(s.C); p.Cout = opaque(s.Cout); p.lo_off = opaque(s.lo_off);
   p.Npad = opaque(s.Npad); p.ntaps = opaque(s.ntaps); p.halo = opaque(s.halo); p.KCH = opaque(s.KCH); p.s2 = opaque(s.s2); p.add1_shift = opaque(s.add1_shift);
-  p.nkc = opaque(s.nkc); p.nkr = opaque(s.nkr); p.split = opaque(s.split); p.kgp = opaque(s.kgp); p.nchp = opaque(s.nchp); p.tiles_x = opaque(s.tiles_x);
+  p.nkc = opaque(s.nkc); p.nkr = opaque(s.nkr); p.split = opaque(s.split); p.sp2 = opaque(s.sp2);
+  p.w_smem_bytes = opaque(s.w_smem_bytes); p.w_bps = opaque(s.w_bps); p.kgp = opaque(s.kgp); p.nchp = opaque(s.nchp); p.tiles_x = opaque(s.tiles_x);
   p.tiles_per_img = opaque(s.tiles_per_img); p.ntiles = opaque(s.ntiles);
   p.in_pix_stride = opaque(s.in_pix_stride); p.out_pix_stride = opaque(s.out_pix_stride);
   p.add_pix_stride = opaque(s.add_pix_stride); p.plane = opaque(s.plane); p.flags = opaque(s.flags);
@@ -148,6 +156,7 @@ __device__ __forceinline__ HaloProblem load_problem(const HaloProblem& s) {
   p.w_copies = opaque(s.w_copies);
   p.pair = opaque(s.pair); p.ntiles_real = opaque(s.ntiles_real); p.w_gstage = opaque(s.w_gstage);
   p.o_bufs = opaque(s.o_bufs); p.o_off = opaque(s.o_off); p.o_tile_bytes = opaque(s.o_tile_bytes);
+  p.res_tma = opaque(s.res_tma);
   p.done = nullptr; p.ndep = 0; p.img_px = 0; p.nimg = 0; p.strip = 0;
   if (CH) {
     p.done = opaque(s.done); p.ndep = opaque(s.ndep); p.img_px = opaque(s.img_px); p.nimg = opaque(s.nimg);
@@ -302,7 +311,7 @@ __device__ __forceinline__ void issue_taps(uint32_t d_tmem, uint32_t a_lo, uint3
 //   accempty[2] 144 | wres 160 | pwres 168 (pair: peer's resident weights landed) | tmem slot 176 |
 //   pwfull[8] 192 (pair, streamed: peer's weight slot landed) | wfull[8] 256 | wempty[8] 320
 constexpr uint32_t B_AFULL = 0, B_AEMPTY = 64, B_ACCFULL = 128, B_ACCEMPTY = 144, B_WRES = 160, B_PWRES = 168,
-                   B_PWFULL = 192, B_WFULL = 256, B_WEMPTY = 320;
+                   B_PWFULL = 192, B_WFULL = 256, B_WEMPTY = 320, B_RESFULL = 384;   // resfull[2]: addend tile landed
 
 // MMA issue loop.  Everything here is warp-uniform (kernel parameters, loop counters, shared-memory
 // addresses), so descriptor arithmetic stays on the uniform datapath and costs two 32-bit adds per
@@ -550,6 +559,160 @@ __device__ __noinline__ void chain_publish(int* done, int t, int strip, int img_
   }
 }
 
+// x_hi W_hi + x_lo W_hi + x_hi W_lo for KS K=16 steps of every tap: straight-line code with immediate offsets
+template <int NTAPS, int KS>
+__device__ __forceinline__ void issue_taps_split(uint32_t d_tmem, uint32_t ah, uint32_t al, uint32_t a_hi, uint32_t bh0,
+                                                 uint32_t b_tap, uint32_t w_stage16, uint32_t b_hi, uint32_t idesc) {
+#pragma unroll
+  for (int tap = 0; tap < NTAPS; ++tap) {
+    const uint32_t to = tap_off16<NTAPS, 0>(tap);
+    const uint32_t bh = bh0 + tap * b_tap, bl = bh + w_stage16;
+#pragma unroll
+    for (int k2 = 0; k2 < KS; ++k2) {
+      umma_f16(d_tmem, desc64(ah + to + 2 * k2, a_hi), desc64(bh + 2 * k2, b_hi), idesc, 1u);
+      umma_f16(d_tmem, desc64(al + to + 2 * k2, a_hi), desc64(bh + 2 * k2, b_hi), idesc, 1u);
+      umma_f16(d_tmem, desc64(ah + to + 2 * k2, a_hi), desc64(bl + 2 * k2, b_hi), idesc, 1u);
+    }
+  }
+}
+
+// Split-operand problems, stage-once scheme (single CTA per tile, stride 1): K walks the REAL 64-channel chunks; a chunk
+// has two activation stages (x_hi, x_lo: consecutive stages of the ring) and two weight blocks per tap (W_hi, W_lo); every
+// K=16 step issues x_hi W_hi + x_lo W_hi + x_hi W_lo.  The [x_hi | x_lo | x_hi] x [W_hi | W_hi | W_lo] K layout of the
+// packed image (and of the other kernels) would stage x_hi and W_hi twice: a third more L2 -> SM traffic on layers that
+// are bound by exactly that (~30 B/clk/SM), and a third more shared memory for resident weights (the 48-channel 3x3
+// layers of the split-mode backbones fit only without the duplicate).
+template <int NTAPS>
+__device__ __forceinline__ void mma_role_split(const HaloProblem& P, const int cta, const uint32_t sbase,
+                                               const uint32_t tmem_base, const uint32_t ncols, unsigned long long* tr,
+                                               const int trcap, const int iw) {
+  constexpr int HALO = NTAPS == 9 ? 1 : 0;
+  constexpr int PW = T_TW + 2 * HALO;
+  const uint32_t bar_afull = sbase + B_AFULL, bar_aempty = sbase + B_AEMPTY, bar_wfull = sbase + B_WFULL,
+                 bar_wempty = sbase + B_WEMPTY;
+  const uint32_t bar_accfull = sbase + B_ACCFULL, bar_accempty = sbase + B_ACCEMPTY, bar_wres = sbase + B_WRES;
+  const uint32_t a_base = sbase + T_A_OFF, w_base = sbase + P.w_off;
+  const uint32_t idesc = make_idesc_f16(128, P.Npad);
+  const uint32_t b_hi = sw128_desc_hi(1024, 0);
+  const uint32_t a_hi = sw128_desc_hi(PW * 128, 0);
+  const uint32_t w_stage16 = P.w_stage_bytes >> 4;
+  const uint32_t b_tap = static_cast<uint32_t>(2 * P.nkr) * w_stage16;      // resident: next tap
+  const uint32_t w_slot16 = P.w_slot_bytes >> 4;                           // streamed: one slot = (W_hi, W_lo) of one tap
+  const uint32_t w_lo0 = sw128_desc_lo(w_base);
+  const uint32_t a_stage16 = P.a_stage_bytes >> 4;
+  const uint32_t a_lo0 = sw128_desc_lo(a_base);
+  const bool resident = P.w_resident != 0;
+  const bool leader = elect_one();
+  int tri = 0;
+  const bool dual = resident;
+  if (!dual && iw != 0) return;
+  int acc = dual ? iw : 0;
+  uint32_t accph = 0;
+  const int a_half = dual ? P.a_stages >> 1 : P.a_stages, w_half = P.w_stages;
+  const int a_first = iw * a_half;
+  int as = 0, ws = 0, wpos = 0;
+  uint32_t aph = 0, wph = 0;
+  if (resident) mbar_wait_warp(bar_wres, 0);
+  const uint32_t ones_lo = sw128_desc_lo(sbase + T_ONES_OFF);
+  const uint32_t ones_hi = sw128_desc_hi(0, 0);
+  for (int t = cta + iw * P.cta_count; t < P.ntiles; t += (dual ? 2 : 1) * P.cta_count) {
+    const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc) * (ncols >> 1);
+    mbar_wait_warp(bar_accempty + 8 * acc, accph ^ 1);
+    tc_fence_after();
+    if (leader) trace_ev(tr, trcap, 1, tri, 10, t);
+    if (resident) {
+      if (leader) umma_f16(d_tmem, desc64(ones_lo, ones_hi), desc64(w_lo0, b_hi), idesc, 0u);
+    } else {
+      mbar_wait_warp(bar_wfull + 8 * ws, wph);
+      tc_fence_after();
+      if (leader) {
+        umma_f16(d_tmem, desc64(ones_lo, ones_hi), desc64(w_lo0 + ws * w_slot16, b_hi), idesc, 0u);
+        umma_commit(bar_wempty + 8 * ws);
+      }
+      if (++ws == w_half) {
+        ws = 0;
+        wph ^= 1;
+      }
+    }
+    for (int kr = 0; kr < P.nkr; ++kr) {
+      const int s_h = a_first + as;
+      mbar_wait_warp(bar_afull + 8 * s_h, aph);
+      if (++as == a_half) {
+        as = 0;
+        aph ^= 1;
+      }
+      const int s_l = a_first + as;
+      mbar_wait_warp(bar_afull + 8 * s_l, aph);
+      if (++as == a_half) {
+        as = 0;
+        aph ^= 1;
+      }
+      tc_fence_after();
+      if (leader) trace_ev(tr, trcap, 1, tri, 11, t);
+      const uint32_t ah = a_lo0 + s_h * a_stage16, al = a_lo0 + s_l * a_stage16;
+      const int ksteps = min(4, (P.C - kr * 64) >> 4);
+      if (resident) {
+        if (leader) {
+          const uint32_t bh0 = w_lo0 + (1 + 2 * kr) * w_stage16;
+          switch (ksteps) {
+            case 4: issue_taps_split<NTAPS, 4>(d_tmem, ah, al, a_hi, bh0, b_tap, w_stage16, b_hi, idesc); break;
+            case 3: issue_taps_split<NTAPS, 3>(d_tmem, ah, al, a_hi, bh0, b_tap, w_stage16, b_hi, idesc); break;
+            case 2: issue_taps_split<NTAPS, 2>(d_tmem, ah, al, a_hi, bh0, b_tap, w_stage16, b_hi, idesc); break;
+            default: issue_taps_split<NTAPS, 1>(d_tmem, ah, al, a_hi, bh0, b_tap, w_stage16, b_hi, idesc); break;
+          }
+        }
+      } else {
+        // streamed: blocks arrive in consumption order (tap: W_hi, W_lo), w_bps blocks per ring slot.  Small slots keep
+        // most of the ring IN FLIGHT: the stream is latency bound (~3 k cycles under load), 31 B/clk/SM with ~100 KB in
+        // flight, 46 B/clk with 150 KB (measured), so a ring of many 12-25 KB slots beats two 74 KB ones
+#pragma unroll
+        for (int tap = 0; tap < NTAPS; ++tap) {
+          const uint32_t to = tap_off16<NTAPS, 0>(tap);
+#pragma unroll
+          for (int lo = 0; lo < 2; ++lo) {
+            if (wpos == 0) {
+              mbar_wait_warp(bar_wfull + 8 * ws, wph);
+              tc_fence_after();
+            }
+            if (leader) {
+              const uint32_t b = w_lo0 + ws * w_slot16 + wpos * w_stage16;
+              if (lo == 0) {        // x_hi W_hi + x_lo W_hi
+                for (int k2 = 0; k2 < ksteps; ++k2) {
+                  umma_f16(d_tmem, desc64(ah + to + 2 * k2, a_hi), desc64(b + 2 * k2, b_hi), idesc, 1u);
+                  umma_f16(d_tmem, desc64(al + to + 2 * k2, a_hi), desc64(b + 2 * k2, b_hi), idesc, 1u);
+                }
+              } else {              // x_hi W_lo
+                for (int k2 = 0; k2 < ksteps; ++k2)
+                  umma_f16(d_tmem, desc64(ah + to + 2 * k2, a_hi), desc64(b + 2 * k2, b_hi), idesc, 1u);
+              }
+            }
+            if (++wpos == P.w_bps) {
+              wpos = 0;
+              if (leader) umma_commit(bar_wempty + 8 * ws);
+              if (++ws == w_half) {
+                ws = 0;
+                wph ^= 1;
+              }
+            }
+          }
+        }
+      }
+      if (leader) {
+        umma_commit(bar_aempty + 8 * s_h);
+        umma_commit(bar_aempty + 8 * s_l);
+      }
+    }
+    if (leader) umma_commit(bar_accfull + 8 * acc);
+    if (leader) trace_ev(tr, trcap, 1, tri, 12, t);
+    if (dual) {
+      accph ^= 1;
+    } else {
+      acc ^= 1;
+      if (acc == 0) accph ^= 1;
+    }
+  }
+}
+
 __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, int c3,
                                             uint32_t bar) {
   asm volatile(
@@ -588,6 +751,9 @@ struct EpiArgs {
   int* done;                     // chained launch: this problem's per-image completion counters (else null)
   int img_px, strip, cdbg;
   int add1_shift;                // add1 pixel = (y >> s, x >> s) of a (H >> s) x (W >> s) tensor
+  int res_tma;                   // add0 is fetched by the TMA unit into the staged-output buffer (StageOut)
+  uint32_t res_bar;              // resfull[2]
+  const CUtensorMap* rmap;       // [2]: add0 hi (or only), lo
 };
 __device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2, int c3) {
   asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.tile.bulk_group [%0, {%2,%3,%4,%5}], [%1];"
@@ -603,12 +769,32 @@ __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wa
 __device__ __forceinline__ void epi_barrier() {      // the epilogue warps only (named barrier 1)
   asm volatile("bar.sync 1, %0;" ::"n"(32 * T_EPI_WARPS) : "memory");
 }
+__device__ __forceinline__ uint4 ld_shared_v4(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+  return v;
+}
 __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
   asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
+// Staged tile layout: ceil(Cout / 64) blocks of [128 pixels][64 channels = 128 bytes] with the SWIZZLE_128B pattern
+// (16-byte chunk j of row r sits at chunk j ^ (r & 7)), the shared-memory side of 4-D TMA stores with a (64, 8, 16, 1) box
+// (channels past Cout are clipped by the tensor map).  One thread owns one row: with dense [128][Cout] rows the 32 threads
+// of a warp hit addresses Cout*2 bytes apart -- a 32-way bank conflict at 256 channels (12.7 k cycles per 128 x 256
+// tile in layer1, 8-way at 48) -- with the swizzle a warp's 16-byte stores fall on all 32 banks (4 wavefronts).
+constexpr uint32_t T_OBLK = 128u * 128u;
+__device__ __forceinline__ uint32_t stage_addr(uint32_t buf, uint32_t row, uint32_t chunk) {
+  return buf + (chunk >> 3) * T_OBLK + row * 128u + (((chunk & 7u) ^ (row & 7u)) << 4);
+}
+
 // Staged output, per tile: (1) the issuing thread waits until the TMA unit has finished READING the buffer two tiles back,
 // (2) all epilogue warps meet, write their rows, fence them towards the async proxy and meet again, (3) the issuing
 // thread launches the store(s).  Tiles overhanging the image are clipped by the TMA unit.
+// Addend through TMA (E.res_tma; two buffers, no pairs / chains): one thread per ROW reading its residual with 16-byte
+// global loads touches 32 different 128-byte lines per warp instruction -- 6 k of the 11 k cycles of a 128 x 256 layer1
+// tile.  Instead the issuing thread has the TMA unit load the addend tile of the NEXT tile into the (free) other staging
+// buffer right after it issued the current store; the epilogue threads wait for resfull[b], read their 16-byte pieces from
+// the swizzled tile (conflict free) and overwrite them in place with the result, which the TMA store then takes.
 // Chained launch: the issuing thread also publishes finished tiles -- a tile counts once its store group has COMPLETED
 // (wait_group without .read), which with two buffers is known one tile later; `t_old` / `t_new` are the tiles stored
 // but not yet published.  (Problems without a staged path publish after a gpu-scope fence of every storing thread.)
@@ -622,13 +808,27 @@ struct StageOut {
   uint32_t buf_addr;
   int nbuf, b;
   int t_old, t_new;
-  __device__ __forceinline__ void init(const EpiArgs& E, bool is_issuer) {
+  int ntile;           // tiles begun (phase of resfull[b])
+  __device__ __forceinline__ void issue_res(const EpiArgs& E, int t, int bb) {
+    const int n = t / E.tiles_per_img, r = t - n * E.tiles_per_img, ty = r / E.tiles_x, tx = r - ty * E.tiles_x;
+    const bool split = (E.flags & I2R_F_SPLIT) != 0;
+    const uint32_t dst = E.o_base + static_cast<uint32_t>(bb) * E.o_tile_bytes * (split ? 2u : 1u);
+    const uint32_t bar = E.res_bar + 8u * bb;
+    mbar_arrive_expect_tx(bar, E.o_tile_bytes * (split ? 2u : 1u));
+    for (int c0 = 0, blk = 0; c0 < E.Cout; c0 += 64, ++blk) {
+      tma_load_4d(dst + blk * T_OBLK, E.rmap, c0, tx * T_TW, ty * T_TH, n, bar);
+      if (split) tma_load_4d(dst + E.o_tile_bytes + blk * T_OBLK, E.rmap + 1, c0, tx * T_TW, ty * T_TH, n, bar);
+    }
+  }
+  __device__ __forceinline__ void init(const EpiArgs& E, bool is_issuer, int first_tile) {
     on = E.o_bufs > 0;
     issuer = is_issuer;
     nbuf = E.o_bufs;
     b = 0;
     buf_addr = 0;
     t_old = t_new = -1;
+    ntile = 0;
+    if (on && E.res_tma && issuer && first_tile < E.ntiles) issue_res(E, first_tile, 0);
   }
   __device__ __forceinline__ void publish(const EpiArgs& E, int t) {
     chain_publish(E.done, t, E.strip, E.img_px, E.tiles_per_img, E.tiles_x, E.H, E.W, E.cdbg);
@@ -650,6 +850,13 @@ struct StageOut {
   template <bool CH>
   __device__ __forceinline__ void begin_tile(const EpiArgs& E) {
     if (!on) return;
+    buf_addr = E.o_base + static_cast<uint32_t>(b) * E.o_tile_bytes * ((E.flags & I2R_F_SPLIT) ? 2u : 1u);
+    if (!CH && E.res_tma) {
+      // the addend tile landed in buffer b (it was requested only after the store that last used b had been read)
+      mbar_wait_warp(E.res_bar + 8u * b, static_cast<uint32_t>(ntile >> 1) & 1u);
+      ++ntile;
+      return;
+    }
     if (issuer) {
       if (CH && E.done != nullptr) {
         chain_begin(E);
@@ -676,13 +883,19 @@ struct StageOut {
     epi_barrier();
     if (issuer) {
       if (tile_ok) {
-        tma_store_4d(E.omap, buf_addr, 0, x0, y0, n);
-        if (E.flags & I2R_F_SPLIT) tma_store_4d(E.omap + 1, buf_addr + E.o_tile_bytes, 0, x0, y0, n);
+        for (int c0 = 0, blk = 0; c0 < E.Cout; c0 += 64, ++blk) {
+          tma_store_4d(E.omap, buf_addr + blk * T_OBLK, c0, x0, y0, n);
+          if (E.flags & I2R_F_SPLIT) tma_store_4d(E.omap + 1, buf_addr + E.o_tile_bytes + blk * T_OBLK, c0, x0, y0, n);
+        }
       }
       bulk_commit();
       if (CH) {
         t_old = t_new;     // (published by the begin_tile in between unless there was none to publish)
         t_new = tile_ok ? t : -1;
+      }
+      if (!CH && E.res_tma && t + E.cta_count < E.ntiles) {
+        bulk_wait_read<1>();                  // the other buffer's store (one tile back) has been read
+        issue_res(E, t + E.cta_count, b ^ 1);
       }
     }
     b = (b + 1 == nbuf) ? 0 : b + 1;
@@ -724,8 +937,7 @@ __device__ __forceinline__ void epilogue_role(const EpiArgs E, const int cta, co
   int acc = 0, tri = 0;
   uint32_t accph = 0;
   StageOut so;
-  so.init(E, ew == 0 && lane == 0);
-  const uint32_t srow = static_cast<uint32_t>(row) * static_cast<uint32_t>(E.Cout) * 2u;   // this pixel's row in the tile
+  so.init(E, ew == 0 && lane == 0, cta);
   for (int tp = cta; tp < E.ntiles; tp += E.cta_count) {
     const int t = E.pair ? 2 * tp + E.rank : tp;
     // tile coordinates without integer division (exact for t < 2^22)
@@ -751,7 +963,9 @@ __device__ __forceinline__ void epilogue_role(const EpiArgs E, const int cta, co
         r0[j] = make_uint4(0, 0, 0, 0);
         r1[j] = make_uint4(0, 0, 0, 0);
         if (j < nc && valid && (c + j) * 8 < E.Cout) {
-          if (has0) r0[j] = ld_addend<CH>(reinterpret_cast<const uint4*>(a0 + (c + j) * 8));
+          if (has0)
+            r0[j] = E.res_tma ? ld_shared_v4(stage_addr(so.buf_addr, row, c + j))
+                              : ld_addend<CH>(reinterpret_cast<const uint4*>(a0 + (c + j) * 8));
           if (has1) r1[j] = ld_addend<CH>(reinterpret_cast<const uint4*>(a1 + (c + j) * 8));
         }
       }
@@ -761,7 +975,9 @@ __device__ __forceinline__ void epilogue_role(const EpiArgs E, const int cta, co
         l0[j] = make_uint4(0, 0, 0, 0);
         l1[j] = make_uint4(0, 0, 0, 0);
         if (split && j < nc && valid && (c + j) * 8 < E.Cout) {
-          if (has0) l0[j] = ld_addend<CH>(reinterpret_cast<const uint4*>(a0 + E.lo_off + (c + j) * 8));
+          if (has0)
+            l0[j] = E.res_tma ? ld_shared_v4(stage_addr(so.buf_addr + E.o_tile_bytes, row, c + j))
+                              : ld_addend<CH>(reinterpret_cast<const uint4*>(a0 + E.lo_off + (c + j) * 8));
           if (has1) l1[j] = ld_addend<CH>(reinterpret_cast<const uint4*>(a1 + E.lo_off + (c + j) * 8));
         }
       }
@@ -825,7 +1041,7 @@ __device__ __forceinline__ void epilogue_role(const EpiArgs E, const int cta, co
               q.w = pack_h2(v[6], v[7]);
               __half* yq = reinterpret_cast<__half*>(E.y) + static_cast<int64_t>(p) * E.out_pix_stride + c0;
               if (so.on)
-                st_shared_v4(so.buf_addr + srow + c0 * 2, q.x, q.y, q.z, q.w);
+                st_shared_v4(stage_addr(so.buf_addr, row, c + j), q.x, q.y, q.z, q.w);
               else if (!(dbg & 2))
                 *reinterpret_cast<uint4*>(yq) = q;
               else if (q.x == 0x12345678u)
@@ -838,7 +1054,7 @@ __device__ __forceinline__ void epilogue_role(const EpiArgs E, const int cta, co
                   const float2 f = unpack_h2(hq[i]);
                   lq[i] = pack_h2(v[2 * i] - f.x, v[2 * i + 1] - f.y);
                 }
-                if (so.on) st_shared_v4(so.buf_addr + E.o_tile_bytes + srow + c0 * 2, lq[0], lq[1], lq[2], lq[3]);
+                if (so.on) st_shared_v4(stage_addr(so.buf_addr + E.o_tile_bytes, row, c + j), lq[0], lq[1], lq[2], lq[3]);
                 else *reinterpret_cast<uint4*>(yq + E.lo_off) = make_uint4(lq[0], lq[1], lq[2], lq[3]);
               }
             } else if (E.flags & I2R_F_OUT_NCHW_F32) {
@@ -893,8 +1109,7 @@ __device__ __forceinline__ void epilogue_fast(const EpiArgs E, const int cta, co
   int acc = 0, tri = 0;
   uint32_t accph = 0;
   StageOut so;
-  so.init(E, ew == 0 && lane == 0);
-  const uint32_t srow = static_cast<uint32_t>(row) * static_cast<uint32_t>(E.Cout) * 2u;   // this pixel's row in the tile
+  so.init(E, ew == 0 && lane == 0, cta);
   for (int tp = cta; tp < E.ntiles; tp += E.cta_count) {
     const int t = E.pair ? 2 * tp + E.rank : tp;
     const int n = __float2int_rd((static_cast<float>(t) + 0.5f) * inv_tpi);
@@ -916,7 +1131,10 @@ __device__ __forceinline__ void epilogue_fast(const EpiArgs E, const int cta, co
       for (int j = 0; j < G; ++j) {
         r0[j] = make_uint4(0, 0, 0, 0);
         r1[j] = make_uint4(0, 0, 0, 0);
-        if (NADD >= 1 && valid) r0[j] = ld_addend<CH>(reinterpret_cast<const uint4*>(a0 + (c + j) * 8));
+        if (NADD >= 1) {
+          if (E.res_tma) r0[j] = ld_shared_v4(stage_addr(so.buf_addr, row, c + j));   // (rows outside the image: zero fill)
+          else if (valid) r0[j] = ld_addend<CH>(reinterpret_cast<const uint4*>(a0 + (c + j) * 8));
+        }
         if (NADD >= 2 && valid) r1[j] = ld_addend<CH>(reinterpret_cast<const uint4*>(a1 + (c + j) * 8));
       }
       if (c == cb) {
@@ -948,7 +1166,7 @@ __device__ __forceinline__ void epilogue_fast(const EpiArgs E, const int cta, co
           }
           o[i] = pack_h2(fmaxf(va, lo), fmaxf(vb, lo));
         }
-        if (so.on) st_shared_v4(so.buf_addr + srow + (c + j) * 16, o[0], o[1], o[2], o[3]);
+        if (so.on) st_shared_v4(stage_addr(so.buf_addr, row, c + j), o[0], o[1], o[2], o[3]);
         else if (valid) *reinterpret_cast<uint4*>(yp + (c + j) * 8) = make_uint4(o[0], o[1], o[2], o[3]);
       }
     }
@@ -984,8 +1202,7 @@ __device__ __forceinline__ void epilogue_split_fast(const EpiArgs E, const int c
   int acc = 0, tri = 0;
   uint32_t accph = 0;
   StageOut so;
-  so.init(E, ew == 0 && lane == 0);
-  const uint32_t srow = static_cast<uint32_t>(row) * static_cast<uint32_t>(E.Cout) * 2u;
+  so.init(E, ew == 0 && lane == 0, cta);
   for (int tp = cta; tp < E.ntiles; tp += E.cta_count) {
     const int t = E.pair ? 2 * tp + E.rank : tp;
     const int n = __float2int_rd((static_cast<float>(t) + 0.5f) * inv_tpi);
@@ -1006,7 +1223,10 @@ __device__ __forceinline__ void epilogue_split_fast(const EpiArgs E, const int c
 #pragma unroll
       for (int j = 0; j < G; ++j) {
         r0[j] = l0[j] = r1[j] = l1[j] = make_uint4(0, 0, 0, 0);
-        if (NADD >= 1 && valid) {
+        if (NADD >= 1 && E.res_tma) {
+          r0[j] = ld_shared_v4(stage_addr(so.buf_addr, row, c + j));
+          l0[j] = ld_shared_v4(stage_addr(so.buf_addr + E.o_tile_bytes, row, c + j));
+        } else if (NADD >= 1 && valid) {
           r0[j] = ld_addend<CH>(reinterpret_cast<const uint4*>(a0 + (c + j) * 8));
           l0[j] = ld_addend<CH>(reinterpret_cast<const uint4*>(a0 + E.lo_off + (c + j) * 8));
         }
@@ -1060,8 +1280,8 @@ __device__ __forceinline__ void epilogue_split_fast(const EpiArgs E, const int c
           ol[i] = pack_h2(va - h.x, vb - h.y);
         }
         if (so.on) {
-          st_shared_v4(so.buf_addr + srow + (c + j) * 16, oh[0], oh[1], oh[2], oh[3]);
-          st_shared_v4(so.buf_addr + E.o_tile_bytes + srow + (c + j) * 16, ol[0], ol[1], ol[2], ol[3]);
+          st_shared_v4(stage_addr(so.buf_addr, row, c + j), oh[0], oh[1], oh[2], oh[3]);
+          st_shared_v4(stage_addr(so.buf_addr + E.o_tile_bytes, row, c + j), ol[0], ol[1], ol[2], ol[3]);
         } else if (valid) {
           *reinterpret_cast<uint4*>(yp + (c + j) * 8) = make_uint4(oh[0], oh[1], oh[2], oh[3]);
           *reinterpret_cast<uint4*>(yp + E.lo_off + (c + j) * 8) = make_uint4(ol[0], ol[1], ol[2], ol[3]);
@@ -1199,6 +1419,10 @@ __global__ void __launch_bounds__(T_THREADS, 1) conv_halo_kernel(const __grid_co
     }
     mbar_init(bar_wres, 1);
     mbar_init(sbase + B_PWRES, 1);
+    if (first) {
+      mbar_init(sbase + B_RESFULL, 1);
+      mbar_init(sbase + B_RESFULL + 8, 1);
+    }
     fence_mbar_init();
   }
   if (first && tid < 256) reinterpret_cast<uint32_t*>(smem + T_ONES_OFF)[tid] = 0x3c003c00u;   // fp16 (1.0, 1.0)
@@ -1271,7 +1495,8 @@ __global__ void __launch_bounds__(T_THREADS, 1) conv_halo_kernel(const __grid_co
             mbar_arrive(bar_afull + 8 * s);
           } else {
             // split-operand mode walks [x_hi | x_lo | x_hi]: hi at channel 0, lo at channel C of the source pixel
-            const int third = kc / P.nkr, kr = kc - third * P.nkr;
+            // (stage-once scheme: x_hi, x_lo of real chunk kc >> 1)
+            const int third = P.sp2 ? (kc & 1) : kc / P.nkr, kr = P.sp2 ? (kc >> 1) : kc - third * P.nkr;
             const int c0 = (third == 1 ? P.C : 0) + kr * 64;
             if (P.s2) {
               // stride 2: four parity planes of the (2*8+1) x (2*16+1) input pixels around the output tile
@@ -1304,7 +1529,48 @@ __global__ void __launch_bounds__(T_THREADS, 1) conv_halo_kernel(const __grid_co
       // pair mode: this CTA holds rows [rank * Npad/2, (rank+1) * Npad/2) of every (tap, K-chunk) block of the image
       const uint32_t w_goff = pair ? static_cast<uint32_t>(rank) * P.w_stage_bytes : 0u;
       const int nblocks = P.ntaps * P.nkc + 1;
-      if (P.w_resident) {
+      if (P.sp2 && P.w_resident) {
+        // compact copy without the duplicate W_hi: [bias][tap][real chunk][W_hi, W_lo]
+        mbar_arrive_expect_tx(bar_wres, P.w_smem_bytes);
+        bulk_g2s(w_base, P.w, P.w_stage_bytes, bar_wres);
+        for (int tap = 0; tap < P.ntaps; ++tap)
+          for (int kr = 0; kr < P.nkr; ++kr) {
+            const uint32_t dst = w_base + static_cast<uint32_t>(1 + (tap * P.nkr + kr) * 2) * P.w_stage_bytes;
+            const size_t g_hi = static_cast<size_t>(1 + tap * P.nchp + kr) * P.w_gstage;
+            bulk_g2s(dst, P.w + g_hi, P.w_stage_bytes, bar_wres);
+            bulk_g2s(dst + P.w_stage_bytes, P.w + g_hi + static_cast<size_t>(2 * P.nkr) * P.w_gstage, P.w_stage_bytes, bar_wres);
+          }
+      } else if (P.sp2) {
+        // streamed: slot 0 of a tile = the bias block, then the 2 * ntaps * nkr blocks of the tile in consumption order
+        // (real chunk, tap, [W_hi, W_lo]), w_bps blocks per slot
+        const int w_half = P.w_stages;
+        int sr = 0;
+        uint32_t phr = 0;
+        const int nblk = 2 * P.ntaps * P.nkr;
+        for (int t = cta; t < P.ntiles; t += P.cta_count) {
+          mbar_wait(bar_wempty + 8 * sr, phr ^ 1);
+          mbar_arrive_expect_tx(bar_wfull + 8 * sr, P.w_stage_bytes);
+          bulk_g2s(w_base + sr * P.w_slot_bytes, P.w, P.w_stage_bytes, bar_wfull + 8 * sr);
+          if (++sr == w_half) {
+            sr = 0;
+            phr ^= 1;
+          }
+          for (int q0 = 0; q0 < nblk; q0 += P.w_bps) {
+            mbar_wait(bar_wempty + 8 * sr, phr ^ 1);
+            mbar_arrive_expect_tx(bar_wfull + 8 * sr, P.w_bps * P.w_stage_bytes);
+            for (int j = 0; j < P.w_bps; ++j) {
+              const int q = q0 + j;
+              const int kr = q / (2 * P.ntaps), rem = q - kr * 2 * P.ntaps, tap = rem >> 1, lo = rem & 1;
+              const size_t g = static_cast<size_t>(1 + tap * P.nchp + (lo ? 2 * P.nkr : 0) + kr) * P.w_gstage;
+              bulk_g2s(w_base + sr * P.w_slot_bytes + j * P.w_stage_bytes, P.w + g, P.w_stage_bytes, bar_wfull + 8 * sr);
+            }
+            if (++sr == w_half) {
+              sr = 0;
+              phr ^= 1;
+            }
+          }
+        }
+      } else if (P.w_resident) {
         if (pair) {
           mbar_arrive_expect_tx(bar_wres, static_cast<uint32_t>(nblocks) * P.w_stage_bytes);
           for (int b = 0; b < nblocks; ++b)
@@ -1353,7 +1619,10 @@ __global__ void __launch_bounds__(T_THREADS, 1) conv_halo_kernel(const __grid_co
     // ================================================= MMA issuers (whole warp runs the loop, one lane issues)
     unsigned long long* trm = warp == 2 ? tr : nullptr;
     const int iw = warp - 2;
-    if (!pair) {
+    if (!pair && P.sp2) {
+      if (P.ntaps == 9) mma_role_split<9>(P, cta, sbase, tmem_base, ncols, trm, trace_cap, iw);
+      else mma_role_split<1>(P, cta, sbase, tmem_base, ncols, trm, trace_cap, iw);
+    } else if (!pair) {
       if (P.s2) mma_role<9, 0, 1>(P, cta, sbase, tmem_base, ncols, trm, trace_cap, dbg, iw);
       else if (P.ntaps == 9) mma_role<9, 0>(P, cta, sbase, tmem_base, ncols, trm, trace_cap, dbg, iw);
       else mma_role<1, 0>(P, cta, sbase, tmem_base, ncols, trm, trace_cap, dbg, iw);
@@ -1376,6 +1645,7 @@ __global__ void __launch_bounds__(T_THREADS, 1) conv_halo_kernel(const __grid_co
     E.pair = pair ? 1 : 0; E.rank = rank; E.ntiles_real = P.ntiles_real;
     E.o_bufs = P.o_bufs; E.o_base = sbase + P.o_off; E.o_tile_bytes = P.o_tile_bytes; E.omap = &G.omap[pi][0];
     E.done = P.done; E.img_px = P.img_px; E.strip = P.strip; E.cdbg = cdbg; E.add1_shift = P.add1_shift;
+    E.res_tma = (CH || pair) ? 0 : P.res_tma; E.res_bar = sbase + B_RESFULL; E.rmap = &G.rmap[CH ? 0 : pi][0];
     const int ew = warp - 4;
     // chunks holding real channels, split over the warps of a lane quadrant
     const int n8 = (P.Cout + 7) >> 3, part8 = (n8 + (T_EPI_WARPS / 4) - 1) / (T_EPI_WARPS / 4);
@@ -1469,8 +1739,8 @@ static int encode_amap(CUtensorMap* map, const void* x, int NB, int H, int W, in
   return 0;
 }
 
-// Output tensor (C, W, H, N) for TMA stores: box = (Cout channels, 8 px, 16 lines, 1), no swizzle -- the shared-memory tile
-// is the dense [128 pixels][Cout] array the epilogue writes.
+// Output tensor (C, W, H, N) for TMA stores: box = (64 channels, 8 px, 16 lines, 1) with SWIZZLE_128B -- one block of the
+// staged tile (stage_addr); the channel extent of the map is Cout, so the last block's surplus channels are clipped.
 static int encode_omap(CUtensorMap* map, void* y, int NB, int H, int W, int Cout, int pix_stride) {
   EncodeTiledFn enc = get_encode();
   if (!enc) {
@@ -1481,9 +1751,9 @@ static int encode_omap(CUtensorMap* map, void* y, int NB, int H, int W, int Cout
   const cuuint32_t ones[4] = {1, 1, 1, 1};
   const cuuint64_t dims[4] = {(cuuint64_t)Cout, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)NB};
   const cuuint64_t strides[3] = {pb, pb * W, pb * W * H};
-  const cuuint32_t box[4] = {(cuuint32_t)Cout, (cuuint32_t)T_TW, (cuuint32_t)T_TH, 1};
+  const cuuint32_t box[4] = {64, (cuuint32_t)T_TW, (cuuint32_t)T_TH, 1};
   CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, y, dims, strides, box, ones, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                   CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled (output) failed (%d) for [%d,%d,%d,%d] pix_stride %d", (int)r, NB, H, W, Cout,
               pix_stride);
@@ -1654,9 +1924,25 @@ static int plan_layer(GT& G, const int base, const i2r_conv_problem* probs, cons
     P.KCH = 64;
     P.split = (S.flags & I2R_F_SPLIT) ? 1 : 0;
     P.nkr = (S.Cin + 63) / 64;
-    P.nkc = P.split ? 3 * P.nkr : P.nkr;
+    // split-operand problems: stage-once scheme unless CTA pairs or stride 2 (two 71 KB stages per real chunk do not fit)
+    static const int sp2_policy = []() {
+      const char* e = getenv("I2R_HALO_SPLIT_ONCE");
+      return e ? atoi(e) : 1;
+    }();
+    P.sp2 = (sp2_policy && P.split && !P.pair && !P.s2) ? 1 : 0;
+    if (P.sp2 && sp2_policy == 1) {
+      // measured per layer class (profiles/r02_split_stage_once.txt): the scheme wins where the de-duplicated weights
+      // become resident (48-channel 3x3: tile 8.1 k -> 4.2 k cycles), for 1x1 problems (K-heavy MLP GEMMs of HRFormer: -27 %)
+      // and for wide streamed 3x3 layers (192 channels: -16 %); narrow streamed 3x3 layers lose (their per-block MMA
+      // bursts are too short for the slot hand-shake) and keep the three-pass K layout.  I2R_HALO_SPLIT_ONCE=2: everywhere.
+      const uint32_t dedup = static_cast<uint32_t>(S.ntaps * 2 * P.nkr + 1) * static_cast<uint32_t>(S.Npad) * 128u;
+      const uint32_t a_stage = static_cast<uint32_t>((T_TH + 2 * P.halo) * (T_TW + 2 * P.halo) * 128 + 1023) & ~1023u;
+      const bool resident = dedup <= T_W_RES_MAX && T_A_OFF + 4u * a_stage + dedup <= T_MAX_SMEM;
+      if (!(resident || S.ntaps == 1 || S.Npad >= 128)) P.sp2 = 0;
+    }
+    P.nkc = P.split ? (P.sp2 ? 2 : 3) * P.nkr : P.nkr;
     P.kgp = 8;
-    P.nchp = P.nkc;
+    P.nchp = P.split ? 3 * P.nkr : P.nkr;   // the packed image always has [W_hi | W_hi | W_lo] chunks per tap
     P.tiles_x = (P.W + T_TW - 1) / T_TW;
     P.tiles_per_img = P.tiles_x * ((P.H + T_TH - 1) / T_TH);
     P.ntiles_real = P.tiles_per_img * P.NB;
@@ -1672,13 +1958,22 @@ static int plan_layer(GT& G, const int base, const i2r_conv_problem* probs, cons
       P.a_tx_bytes = S2_TX;
       P.a_stage_bytes = S2_STAGE;
     }
-    P.w_total_bytes = static_cast<uint32_t>(S.ntaps * P.nkc + 1) * S.Npad * 128;   // bias block + taps (global image)
+    P.w_total_bytes = static_cast<uint32_t>(S.ntaps * P.nchp + 1) * S.Npad * 128;   // bias block + taps (global image)
     P.w_gstage = static_cast<uint32_t>(S.Npad) * 128;
     P.w_stage_bytes = P.pair ? P.w_gstage / 2 : P.w_gstage;      // pair mode: every CTA holds half of the rows
     const uint32_t w_cta_bytes = static_cast<uint32_t>(S.ntaps * P.nkc + 1) * P.w_stage_bytes;
     P.w_resident = w_cta_bytes <= T_W_RES_MAX ? 1 : 0;
     if (P.s2 && T_A_OFF + 2u * S2_STAGE + w_cta_bytes + 128u > T_MAX_SMEM) P.w_resident = 0;   // stream instead
+    if (P.sp2 && T_A_OFF + 4u * P.a_stage_bytes + w_cta_bytes > T_MAX_SMEM) P.w_resident = 0;   // (two stages per issuer)
     P.w_slot_bytes = P.w_stage_bytes * (S.ntaps == 9 ? 3 : 1);
+    P.w_bps = 1;
+    if (P.sp2) {
+      // slots of <= 36 KB; the count must divide the 2 * ntaps blocks of a real chunk
+      const int fit = static_cast<int>(36864u / P.w_stage_bytes);
+      P.w_bps = S.ntaps == 9 ? (fit >= 6 ? 6 : fit >= 3 ? 3 : fit >= 2 ? 2 : 1) : (fit >= 2 ? 2 : 1);
+      P.w_slot_bytes = P.w_bps * P.w_stage_bytes;
+    }
+    P.w_smem_bytes = w_cta_bytes;
     uint32_t wregion;
     // streamed weights: the ring must cover the L2 round trip (~1300 cycles) at the rate the issuer drains it, so it
     // gets up to T_W_STAGES_MAX stages and the activation ring two (one per K-chunk in flight is enough there)
@@ -1690,8 +1985,13 @@ static int plan_layer(GT& G, const int base, const i2r_conv_problem* probs, cons
       if (astg > T_A_STAGES_MAX) astg = T_A_STAGES_MAX;
       astg &= ~1;   // two half-rings, one per MMA issuer
     } else {
-      astg = P.s2 ? 2 : 3;
-      while (astg > 2 && T_A_OFF + astg * P.a_stage_bytes + 3 * P.w_slot_bytes > T_MAX_SMEM) --astg;
+      static const int sp2_astg = []() {     // tuning override (tools/sessions): activation stages of streamed sp2 problems
+        const char* e = getenv("I2R_HALO_SPLIT_ASTG");
+        return e ? atoi(e) : 0;
+      }();
+      astg = P.s2 ? 2 : (P.sp2 ? 4 : 3);   // (stage-once split: x_hi and x_lo of two real chunks)
+      if (P.sp2 && sp2_astg) astg = sp2_astg;
+      while (astg > 2 && T_A_OFF + astg * P.a_stage_bytes + 3 * P.w_slot_bytes > T_MAX_SMEM) astg -= P.sp2 ? 2 : 1;
       P.w_stages = static_cast<int>((T_MAX_SMEM - T_A_OFF - astg * P.a_stage_bytes) / P.w_slot_bytes);
       if (P.w_stages > T_W_STAGES_MAX) P.w_stages = T_W_STAGES_MAX;
       wregion = P.w_stages * P.w_slot_bytes;
@@ -1704,17 +2004,23 @@ static int plan_layer(GT& G, const int base, const i2r_conv_problem* probs, cons
     // staged output tiles (fp16 NHWC outputs with whole 8-channel chunks): two buffers, else one, else direct stores;
     // the activation ring gives up stages for them down to two (resident weights: two per issuer)
     P.o_bufs = 0;
-    P.o_tile_bytes = (static_cast<uint32_t>(T_TW * T_TH) * S.Cout * 2 + 127u) & ~127u;
+    P.o_tile_bytes = static_cast<uint32_t>((S.Cout + 63) / 64) * T_OBLK;   // 64-channel swizzled blocks (stage_addr)
     const bool stageable = stage_policy != 0 && !(S.flags & (I2R_F_OUT_NCHW_F32 | I2R_F_OUT_F32 | I2R_F_OUT_T16)) &&
                            S.Cout % 8 == 0 && S.Cout <= 256 && S.out_pix_stride % 8 == 0 &&
                            (!P.split || P.lo_off % 8 == 0);
     if (stageable) {
       const uint32_t per_buf = P.o_tile_bytes * (P.split ? 2u : 1u);
-      const int astg_min = P.w_resident ? 4 : 2;
+      // wide single-chunk 1x1 layers with an addend (layer1 conv3: 64 -> 256) are bound by the addend fetch, which wants
+      // two staging buffers (res_tma below): they may go down to one activation stage per issuer
+      const bool wide_res = S.add0 && S.Cout >= 128 && S.ntaps == 1 && P.nkc == 1;
+      const int astg_min = P.w_resident ? (wide_res ? 2 : 4) : 2;
+      auto total = [&](int a, int nb) {   // exact: the staging buffers start 1024-byte aligned
+        return ((T_A_OFF + a * P.a_stage_bytes + wregion + 1023u) & ~1023u) + nb * per_buf;
+      };
       for (int nb = 2; nb >= 1 && P.o_bufs == 0; --nb) {
         int a = astg;
-        while (a > astg_min && T_A_OFF + a * P.a_stage_bytes + wregion + nb * per_buf + 128 > T_MAX_SMEM) a -= P.w_resident ? 2 : 1;
-        if (T_A_OFF + a * P.a_stage_bytes + wregion + nb * per_buf + 128 <= T_MAX_SMEM) {
+        while (a > astg_min && total(a, nb) > T_MAX_SMEM) a -= P.w_resident ? 2 : 1;
+        if (total(a, nb) <= T_MAX_SMEM) {
           P.o_bufs = nb;
           astg = a;
         }
@@ -1743,7 +2049,7 @@ static int plan_layer(GT& G, const int base, const i2r_conv_problem* probs, cons
       if (rc) return rc;
     }
     P.w_off = T_A_OFF + static_cast<uint32_t>(astg) * P.a_stage_bytes;
-    P.o_off = (P.w_off + wregion + 127u) & ~127u;
+    P.o_off = (P.w_off + wregion + 1023u) & ~1023u;   // swizzled blocks: 1024-byte aligned
     if (P.o_bufs) {
       // the output as a 4-D tensor (C, W, H, N) with the same tile geometry as the activation map, dense boxes
       int rc = encode_omap(&G.omap[base + i][0], S.y, P.NB, P.H, P.W, S.Cout, S.out_pix_stride);
@@ -1751,6 +2057,24 @@ static int plan_layer(GT& G, const int base, const i2r_conv_problem* probs, cons
         rc = encode_omap(&G.omap[base + i][1], static_cast<__half*>(S.y) + P.lo_off, P.NB, P.H, P.W, S.Cout,
                          S.out_pix_stride);
       if (rc) return rc;
+    }
+    // first addend through TMA into the staging buffers (two buffers, plain problems only; I2R_HALO_RES_TMA=0: off)
+    static const int res_policy = []() {
+      const char* e = getenv("I2R_HALO_RES_TMA");
+      return e ? atoi(e) : 1;
+    }();
+    P.res_tma = 0;
+    // (only for wide rows: at <= 96 channels the kernel is bound by the shared-memory port and the extra tile write +
+    // read costs more than the scattered global loads: C2 -7 % when applied everywhere)
+    if (res_policy && (S.Cout >= 128 || res_policy == 2) && P.o_bufs == 2 && S.add0 && !P.pair && !GT::kChain &&
+        S.add_pix_stride % 8 == 0 &&
+        (reinterpret_cast<uintptr_t>(S.add0) & 15) == 0) {
+      int rc = encode_omap(&G.rmap[base + i][0], const_cast<void*>(S.add0), P.NB, P.H, P.W, S.Cout, S.add_pix_stride);
+      if (!rc && P.split)
+        rc = encode_omap(&G.rmap[base + i][1], const_cast<__half*>(static_cast<const __half*>(S.add0)) + P.lo_off, P.NB,
+                         P.H, P.W, S.Cout, S.add_pix_stride);
+      if (rc) return rc;
+      P.res_tma = 1;
     }
     const uint32_t need = P.o_off + P.o_bufs * P.o_tile_bytes * (P.split ? 2u : 1u);
     if (need > smem_need) smem_need = need;

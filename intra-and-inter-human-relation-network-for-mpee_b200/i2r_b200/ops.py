@@ -158,8 +158,9 @@ def halo_smem_bytes(p):
     ksteps = -(-p.Cin // 16) * split
     mma = (p.ntaps * ksteps + 1) * (128 * 32 + p.Npad * 32)
     halo = 2 if p.ntaps == 9 else 0
-    a_in = -(-p.Cin // 64) * split * ((8 + halo) * (16 + halo) * 128 if p.stride == 1 else 71808)
-    w_image = (p.ntaps * -(-p.Cin // 64) * split + 1) * p.Npad * 128
+    staged = (2 if p.stride == 1 else 3) if split == 3 else 1     # stride-1 split problems stage x_hi / W_hi once
+    a_in = -(-p.Cin // 64) * staged * ((8 + halo) * (16 + halo) * 128 if p.stride == 1 else 71808)
+    w_image = (p.ntaps * -(-p.Cin // 64) * staged + 1) * p.Npad * 128
     w_in = w_image if w_image > 120 * 1024 else 0
     out = 2 * 128 * p.Cout * 2 * (2 if split == 3 else 1)
     return tiles * (mma + a_in + w_in + out)
