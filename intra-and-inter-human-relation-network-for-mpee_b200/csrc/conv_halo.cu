@@ -1991,6 +1991,11 @@ static int plan_layer(GT& G, const int base, const i2r_conv_problem* probs, cons
       }();
       astg = P.s2 ? 2 : (P.sp2 ? 4 : 3);   // (stage-once split: x_hi and x_lo of two real chunks)
       if (P.sp2 && sp2_astg) astg = sp2_astg;
+      static const int st_astg = []() {      // tuning override: activation stages of the other streamed stride-1 problems
+        const char* e = getenv("I2R_HALO_STREAM_ASTG");
+        return e ? atoi(e) : 0;
+      }();
+      if (!P.sp2 && !P.s2 && st_astg) astg = st_astg;
       while (astg > 2 && T_A_OFF + astg * P.a_stage_bytes + 3 * P.w_slot_bytes > T_MAX_SMEM) astg -= P.sp2 ? 2 : 1;
       P.w_stages = static_cast<int>((T_MAX_SMEM - T_A_OFF - astg * P.a_stage_bytes) / P.w_slot_bytes);
       if (P.w_stages > T_W_STAGES_MAX) P.w_stages = T_W_STAGES_MAX;
