@@ -227,6 +227,13 @@ int i2r_window_scatter_add(const void* x, const void* a, void* y, int NB, int H,
 int i2r_window_attention(const void* q, const void* k, const void* v, void* out, int ldq, int ldk, int ldv, int ldo,
                          int nwin, int win_len, int heads, int head_pad, float scale, int split, int q_lo, int k_lo,
                          int v_lo, int o_lo, void* stream);
+/* The same operation on tcgen05 / TMEM / TMA for the shape HRFormer-B uses (win_len 49, head_pad 48): two windows per
+ * 128-row tile, S = Q K^T and O = P V on the tensor cores (P from TMEM, V as an MN-major operand straight from the
+ * token-major tile), block-diagonal softmax in the epilogue warps.  The product path; i2r_window_attention (mma.sync)
+ * stays as the check implementation and for other window sizes.  Other shapes return I2R_E_UNSUPPORTED. */
+int i2r_window_attention_tc(const void* q, const void* k, const void* v, void* out, int ldq, int ldk, int ldv, int ldo,
+                         int nwin, int win_len, int heads, int head_pad, float scale, int split, int q_lo, int k_lo,
+                         int v_lo, int o_lo, void* stream);
 
 /* y = LayerNorm(x) * gamma + beta over the last dim C (<= 256, multiple of 8), fp16 in/out, fp32
  * math; optional y2 = y + pos (the next layer's q/k input).  (interformer_pureMulti.py:206,:209) */

@@ -32,6 +32,7 @@ void hang_sink_conv_halo(void*);
 void hang_sink_encoder_tail(void*);
 void hang_sink_igemm_tc(void*);
 void hang_sink_stem_tc(void*);
+void hang_sink_window_attention_tc(void*);
 
 int check_launch(const char* what) {
   cudaError_t e = cudaGetLastError();
@@ -536,5 +537,6 @@ extern "C" int i2r_debug_hang_buffer(void* host_mapped) {
   hang_sink_encoder_tail(host_mapped);
   hang_sink_igemm_tc(host_mapped);
   hang_sink_stem_tc(host_mapped);
+  hang_sink_window_attention_tc(host_mapped);
   return check_launch("i2r_debug_hang_buffer");
 }

@@ -6,7 +6,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(os.path.dirname(HERE), "csrc")
 LIB_PATH = os.path.join(HERE, "libi2r_sm100.so")
-SOURCES = ["igemm_tc.cu", "conv_halo.cu", "misc_kernels.cu", "attention.cu", "attention_tc.cu", "encoder_tail.cu", "stem_tc.cu", "hrformer_kernels.cu", "postproc.cu", "preproc.cu", "mask_res.cu"]
+SOURCES = ["igemm_tc.cu", "conv_halo.cu", "misc_kernels.cu", "attention.cu", "attention_tc.cu", "window_attention_tc.cu", "encoder_tail.cu", "stem_tc.cu", "hrformer_kernels.cu", "postproc.cu", "preproc.cu", "mask_res.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "-shared",

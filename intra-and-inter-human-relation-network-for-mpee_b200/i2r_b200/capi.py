@@ -22,7 +22,7 @@ F_ACT_FIRST = 64
 
 EXPORTS = [
     "i2r_version", "i2r_last_error", "i2r_device_check", "i2r_sm_count", "i2r_conv_igemm", "i2r_conv_halo", "i2r_conv_halo_supported", "i2r_conv_halo_chain", "i2r_conv_halo_chain_workspace", "i2r_debug_trace", "i2r_debug_flags", "i2r_debug_chain_flags", "i2r_debug_hang_buffer", "i2r_hflip_f32", "i2r_flip_merge", "i2r_decode_heatmaps", "i2r_crop_persons", "i2r_box_masks", "i2r_mask_res_stem",
-    "i2r_sizeof_conv_problem", "i2r_stem_conv3x3s2", "i2r_stem_conv3x3s2_tc", "i2r_stem_tc_weight_bytes", "i2r_maxpool3x3s2", "i2r_attention_varlen", "i2r_attention_workspace_bytes", "i2r_attention_tc", "i2r_encoder_tail", "i2r_encoder_tail_weight_bytes", "i2r_attention_tc_workspace_bytes", "i2r_layernorm", "i2r_add_f16", "i2r_upsum", "i2r_dwconv3x3", "i2r_upsum_bilinear", "i2r_layernorm_padded", "i2r_window_rows", "i2r_ln_window_gather", "i2r_window_scatter_add", "i2r_window_attention",
+    "i2r_sizeof_conv_problem", "i2r_stem_conv3x3s2", "i2r_stem_conv3x3s2_tc", "i2r_stem_tc_weight_bytes", "i2r_maxpool3x3s2", "i2r_attention_varlen", "i2r_attention_workspace_bytes", "i2r_attention_tc", "i2r_encoder_tail", "i2r_encoder_tail_weight_bytes", "i2r_attention_tc_workspace_bytes", "i2r_layernorm", "i2r_add_f16", "i2r_upsum", "i2r_dwconv3x3", "i2r_upsum_bilinear", "i2r_layernorm_padded", "i2r_window_rows", "i2r_ln_window_gather", "i2r_window_scatter_add", "i2r_window_attention", "i2r_window_attention_tc",
 ]
 
 
@@ -107,6 +107,8 @@ def load():
         lib.i2r_window_scatter_add.argtypes = [vp, vp, vp, i32, i32, i32, i32, i32, i32, vp]
         lib.i2r_window_attention.argtypes = [vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, f32, i32, i32, i32,
                                              i32, i32, vp]
+        if "i2r_window_attention_tc" in EXPORTS:
+            lib.i2r_window_attention_tc.argtypes = lib.i2r_window_attention.argtypes
         lib.i2r_layernorm.argtypes = [vp, vp, vp, vp, vp, vp, i32, i32, f32, i32, vp]
         lib.i2r_add_f16.argtypes = [vp, vp, vp, i64, i32, vp]
         lib.i2r_upsum.argtypes = [vp, vp, i32, vp, i32, vp, i32, i32, i32, i32, i32, i32, vp]

@@ -221,6 +221,7 @@ class Runner:
         self._chain_ws = None    # completion counters of the chained launches (grown on demand, zeroed per launch)
         self._in_parallel = 0
         self.chains = 0          # chained launches made (bench.py / tests)
+        self.window_att_tc = __import__("os").environ.get("I2R_WINDOW_ATT", "tc") != "mma"
 
     # ------------------------------------------------------------------ independent launch chains
     def parallel(self, chains):
@@ -720,7 +721,11 @@ class Runner:
         assert cq == heads * head_pad and t % win_len == 0 and q.stride(1) == 1
         out = torch.empty((t, 2 * cq if self.split else cq), dtype=torch.float16, device=q.device)
         lo = cq if self.split else 0
-        capi.check(self.lib.i2r_window_attention(q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), q.stride(0),
+        # product path: tcgen05 kernel (49-token windows, 48-channel heads); impl=1 / I2R_WINDOW_ATT=mma: mma.sync kernel
+        fn = self.lib.i2r_window_attention
+        if self.impl == 0 and win_len == 49 and head_pad == 48 and self.window_att_tc:
+            fn = self.lib.i2r_window_attention_tc
+        capi.check(fn(q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), q.stride(0),
                                                   k.stride(0), v.stride(0), out.stride(0), t // win_len, win_len, heads,
                                                   head_pad, scale, int(self.split), lo, lo, lo, lo, _stream_ptr()),
                    "i2r_window_attention")

@@ -154,10 +154,12 @@ def test_ln_window_gather_and_scatter(dev, tc, split, c_real, c_pad, h, w):
     assert err <= (5e-6 if split else 4e-3) and err2 <= (1e-5 if split else 8e-3), (err, err2)
 
 
+@pytest.mark.parametrize("kernel", ["tcgen05", "mma_sync"])
 @pytest.mark.parametrize("split", [False, True])
-@pytest.mark.parametrize("heads,nwin", [(2, 140), (16, 4)])
-def test_window_attention(dev, tc, split, heads, nwin):
-    """49-token windows, head_dim 39 padded to 48 (pad channels zero), scale 39**-0.5, no bias / mask."""
+@pytest.mark.parametrize("heads,nwin", [(2, 140), (16, 4), (4, 7), (8, 1)])
+def test_window_attention(dev, tc, split, heads, nwin, kernel):
+    """49-token windows, head_dim 39 padded to 48 (pad channels zero), scale 39**-0.5, no bias / mask.  Product kernel
+    (tcgen05: two windows per 128-row tile, odd window counts leave half a tile empty) and the mma.sync check kernel."""
     from i2r_b200.packing import merge_pair, split_pair
     g = torch.Generator().manual_seed(heads)
     hd, hp, wl = 39, 48, 49
@@ -176,16 +178,21 @@ def test_window_attention(dev, tc, split, heads, nwin):
         vals = [m.double() for m in (q, k, v)]
         args = [m.to(dev) for m in (q, k, v)]
     tc.split = split
+    tc.window_att_tc = kernel == "tcgen05"
     try:
         out = tc.window_attention(args[0], args[1], args[2], wl, heads, scale)
         torch.cuda.synchronize()
+        again = tc.window_attention(args[0], args[1], args[2], wl, heads, scale)
+        torch.cuda.synchronize()
+        assert torch.equal(out, again)
     finally:
         tc.split = False
+        tc.window_att_tc = True
     qd, kd, vd = (m.view(nwin, wl, heads, hp).permute(0, 2, 1, 3) for m in vals)
     ref = (torch.softmax(qd @ kd.transpose(-1, -2) * scale, dim=-1) @ vd).permute(0, 2, 1, 3).reshape(t, heads * hp)
     got = merge_pair(out.cpu()).double() if split else out.cpu().double()
     err = float((got - ref).abs().max())
-    _report(test="window_attention", split=split, heads=heads, err=err)
+    _report(test="window_attention", split=split, heads=heads, nwin=nwin, kernel=kernel, err=err)
     assert err <= (4e-4 if split else 3e-3), err
 
 
