@@ -186,7 +186,7 @@ constexpr int T_EPI_WARPS = I2R_EPI_WARPS;  // per TMEM lane quadrant T_EPI_WARP
                                             // through L1 / shared memory lengthens the tile (profiles/r02_epilogue_*.txt)
 constexpr int T_THREADS = 32 * (4 + T_EPI_WARPS);
 constexpr int T_TW = 8, T_TH = 16;
-constexpr int T_W_STAGES_MAX = 8;           // streamed-weight ring depth (barriers at [256,384))
+constexpr int T_W_STAGES_MAX = 16;          // streamed-weight ring depth (barriers at [512,768)); pair mode uses <= 8
 constexpr int T_A_STAGES_MAX = 8;           // activation ring depth (barriers at [0,128)): K-chunked 1x1 GEMMs (HRFormer: 6
                                             // chunks per tile in split mode) are TMA-latency bound with fewer stages
 constexpr uint32_t T_ONES_OFF = 1024;       // 1 KB of fp16 1.0: the A operand of the bias MMA
@@ -311,7 +311,8 @@ __device__ __forceinline__ void issue_taps(uint32_t d_tmem, uint32_t a_lo, uint3
 //   accempty[2] 144 | wres 160 | pwres 168 (pair: peer's resident weights landed) | tmem slot 176 |
 //   pwfull[8] 192 (pair, streamed: peer's weight slot landed) | wfull[8] 256 | wempty[8] 320
 constexpr uint32_t B_AFULL = 0, B_AEMPTY = 64, B_ACCFULL = 128, B_ACCEMPTY = 144, B_WRES = 160, B_PWRES = 168,
-                   B_PWFULL = 192, B_WFULL = 256, B_WEMPTY = 320, B_RESFULL = 384;   // resfull[2]: addend tile landed
+                   B_PWFULL = 192, B_RESFULL = 384, B_WFULL = 512, B_WEMPTY = 640;   // resfull[2]: addend tile landed;
+                                                                                     // wfull[16] / wempty[16]
 
 // MMA issue loop.  Everything here is warp-uniform (kernel parameters, loop counters, shared-memory
 // addresses), so descriptor arithmetic stays on the uniform datapath and costs two 32-bit adds per
@@ -576,6 +577,27 @@ __device__ __forceinline__ void issue_taps_split(uint32_t d_tmem, uint32_t ah, u
   }
 }
 
+// one weight block of a tap: HI = W_hi (x_hi W_hi + x_lo W_hi), else W_lo (x_hi W_lo)
+template <int KS, bool HI>
+__device__ __forceinline__ void issue_split_block(uint32_t d_tmem, uint32_t ah, uint32_t al, uint32_t a_hi, uint32_t b,
+                                                  uint32_t b_hi, uint32_t idesc) {
+#pragma unroll
+  for (int k2 = 0; k2 < KS; ++k2) {
+    umma_f16(d_tmem, desc64(ah + 2 * k2, a_hi), desc64(b + 2 * k2, b_hi), idesc, 1u);
+    if (HI) umma_f16(d_tmem, desc64(al + 2 * k2, a_hi), desc64(b + 2 * k2, b_hi), idesc, 1u);
+  }
+}
+template <bool HI>
+__device__ __forceinline__ void issue_split_block_ks(int ksteps, uint32_t d_tmem, uint32_t ah, uint32_t al, uint32_t a_hi,
+                                                     uint32_t b, uint32_t b_hi, uint32_t idesc) {
+  switch (ksteps) {
+    case 4: issue_split_block<4, HI>(d_tmem, ah, al, a_hi, b, b_hi, idesc); break;
+    case 3: issue_split_block<3, HI>(d_tmem, ah, al, a_hi, b, b_hi, idesc); break;
+    case 2: issue_split_block<2, HI>(d_tmem, ah, al, a_hi, b, b_hi, idesc); break;
+    default: issue_split_block<1, HI>(d_tmem, ah, al, a_hi, b, b_hi, idesc); break;
+  }
+}
+
 // Split-operand problems, stage-once scheme (single CTA per tile, stride 1): K walks the REAL 64-channel chunks; a chunk
 // has two activation stages (x_hi, x_lo: consecutive stages of the ring) and two weight blocks per tap (W_hi, W_lo); every
 // K=16 step issues x_hi W_hi + x_lo W_hi + x_hi W_lo.  The [x_hi | x_lo | x_hi] x [W_hi | W_hi | W_lo] K layout of the
@@ -610,7 +632,7 @@ __device__ __forceinline__ void mma_role_split(const HaloProblem& P, const int c
   uint32_t accph = 0;
   const int a_half = dual ? P.a_stages >> 1 : P.a_stages, w_half = P.w_stages;
   const int a_first = iw * a_half;
-  int as = 0, ws = 0, wpos = 0;
+  int as = 0, ws = 0;
   uint32_t aph = 0, wph = 0;
   if (resident) mbar_wait_warp(bar_wres, 0);
   const uint32_t ones_lo = sw128_desc_lo(sbase + T_ONES_OFF);
@@ -662,33 +684,41 @@ __device__ __forceinline__ void mma_role_split(const HaloProblem& P, const int c
           }
         }
       } else {
-        // streamed: blocks arrive in consumption order (tap: W_hi, W_lo), w_bps blocks per ring slot.  Small slots keep
-        // most of the ring IN FLIGHT: the stream is latency bound (~3 k cycles under load), 31 B/clk/SM with ~100 KB in
-        // flight, 46 B/clk with 150 KB (measured), so a ring of many 12-25 KB slots beats two 74 KB ones
+        // streamed: blocks arrive in consumption order (tap: W_hi, W_lo); a ring slot holds one tap (W_hi + W_lo, w_bps = 2)
+        // or one block (w_bps = 1, blocks of >= 24 KB).  Small slots keep most of the ring IN FLIGHT: the stream is
+        // latency bound (~3 k cycles under load: 31 B/clk/SM with ~100 KB in flight, 46 B/clk with 150 KB), and a slot
+        // hand-shake (~350 cycles) wants >= 12 MMAs behind it.  ONE elected-lane region per slot, MMAs unrolled.
+        if (P.w_bps == 2) {
 #pragma unroll
-        for (int tap = 0; tap < NTAPS; ++tap) {
-          const uint32_t to = tap_off16<NTAPS, 0>(tap);
+          for (int tap = 0; tap < NTAPS; ++tap) {
+            const uint32_t to = tap_off16<NTAPS, 0>(tap);
+            mbar_wait_warp(bar_wfull + 8 * ws, wph);
+            tc_fence_after();
+            if (leader) {
+              const uint32_t b = w_lo0 + ws * w_slot16;
+              issue_split_block_ks<true>(ksteps, d_tmem, ah + to, al + to, a_hi, b, b_hi, idesc);
+              issue_split_block_ks<false>(ksteps, d_tmem, ah + to, al + to, a_hi, b + w_stage16, b_hi, idesc);
+              umma_commit(bar_wempty + 8 * ws);
+            }
+            if (++ws == w_half) {
+              ws = 0;
+              wph ^= 1;
+            }
+          }
+        } else {
 #pragma unroll
-          for (int lo = 0; lo < 2; ++lo) {
-            if (wpos == 0) {
+          for (int tap = 0; tap < NTAPS; ++tap) {
+            const uint32_t to = tap_off16<NTAPS, 0>(tap);
+#pragma unroll
+            for (int lo = 0; lo < 2; ++lo) {
               mbar_wait_warp(bar_wfull + 8 * ws, wph);
               tc_fence_after();
-            }
-            if (leader) {
-              const uint32_t b = w_lo0 + ws * w_slot16 + wpos * w_stage16;
-              if (lo == 0) {        // x_hi W_hi + x_lo W_hi
-                for (int k2 = 0; k2 < ksteps; ++k2) {
-                  umma_f16(d_tmem, desc64(ah + to + 2 * k2, a_hi), desc64(b + 2 * k2, b_hi), idesc, 1u);
-                  umma_f16(d_tmem, desc64(al + to + 2 * k2, a_hi), desc64(b + 2 * k2, b_hi), idesc, 1u);
-                }
-              } else {              // x_hi W_lo
-                for (int k2 = 0; k2 < ksteps; ++k2)
-                  umma_f16(d_tmem, desc64(ah + to + 2 * k2, a_hi), desc64(b + 2 * k2, b_hi), idesc, 1u);
+              if (leader) {
+                const uint32_t b = w_lo0 + ws * w_slot16;
+                if (lo == 0) issue_split_block_ks<true>(ksteps, d_tmem, ah + to, al + to, a_hi, b, b_hi, idesc);
+                else issue_split_block_ks<false>(ksteps, d_tmem, ah + to, al + to, a_hi, b, b_hi, idesc);
+                umma_commit(bar_wempty + 8 * ws);
               }
-            }
-            if (++wpos == P.w_bps) {
-              wpos = 0;
-              if (leader) umma_commit(bar_wempty + 8 * ws);
               if (++ws == w_half) {
                 ws = 0;
                 wph ^= 1;
@@ -1400,9 +1430,10 @@ __global__ void __launch_bounds__(T_THREADS, 1) conv_halo_kernel(const __grid_co
   const bool first = layer == 0 || tmem_chain == 0;   // (a CTA may sit out the first layers of a chain)
 
   if (tid == 0) {
-    if (!first) {   // every initialised barrier of the map (176 = TMEM slot, 184 unused)
-      for (uint32_t off = 0; off < 384; off += 8)
+    if (!first) {   // every barrier this block initialises (176 = TMEM slot, 184 unused, 256..511: resfull + free)
+      for (uint32_t off = 0; off < 256; off += 8)
         if (off != 176 && off != 184) mbar_inval(sbase + off);
+      for (uint32_t off = B_WFULL; off < B_WEMPTY + 8 * T_W_STAGES_MAX; off += 8) mbar_inval(sbase + off);
     }
     for (int i = 0; i < T_A_STAGES_MAX; ++i) {
       mbar_init(bar_afull + 8 * i, 1);
@@ -1411,7 +1442,7 @@ __global__ void __launch_bounds__(T_THREADS, 1) conv_halo_kernel(const __grid_co
     for (int i = 0; i < T_W_STAGES_MAX; ++i) {
       mbar_init(bar_wfull + 8 * i, 1);
       mbar_init(bar_wempty + 8 * i, 1);
-      mbar_init(sbase + B_PWFULL + 8 * i, 1);
+      if (i < 8) mbar_init(sbase + B_PWFULL + 8 * i, 1);
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(bar_accfull + 8 * i, 1);
@@ -1968,9 +1999,8 @@ static int plan_layer(GT& G, const int base, const i2r_conv_problem* probs, cons
     P.w_slot_bytes = P.w_stage_bytes * (S.ntaps == 9 ? 3 : 1);
     P.w_bps = 1;
     if (P.sp2) {
-      // slots of <= 36 KB; the count must divide the 2 * ntaps blocks of a real chunk
-      const int fit = static_cast<int>(36864u / P.w_stage_bytes);
-      P.w_bps = S.ntaps == 9 ? (fit >= 6 ? 6 : fit >= 3 ? 3 : fit >= 2 ? 2 : 1) : (fit >= 2 ? 2 : 1);
+      // one tap (W_hi + W_lo) per slot; single blocks once a block reaches 24 KB (>= 192 output channels)
+      P.w_bps = P.w_stage_bytes >= 24576u ? 1 : 2;
       P.w_slot_bytes = P.w_bps * P.w_stage_bytes;
     }
     P.w_smem_bytes = w_cta_bytes;
@@ -1998,7 +2028,7 @@ static int plan_layer(GT& G, const int base, const i2r_conv_problem* probs, cons
       if (!P.sp2 && !P.s2 && st_astg) astg = st_astg;
       while (astg > 2 && T_A_OFF + astg * P.a_stage_bytes + 3 * P.w_slot_bytes > T_MAX_SMEM) astg -= P.sp2 ? 2 : 1;
       P.w_stages = static_cast<int>((T_MAX_SMEM - T_A_OFF - astg * P.a_stage_bytes) / P.w_slot_bytes);
-      if (P.w_stages > T_W_STAGES_MAX) P.w_stages = T_W_STAGES_MAX;
+      if (P.w_stages > (P.pair ? 8 : T_W_STAGES_MAX)) P.w_stages = P.pair ? 8 : T_W_STAGES_MAX;
       wregion = P.w_stages * P.w_slot_bytes;
     }
     if (astg < 2 || P.w_stages < 1 || (!P.w_resident && P.w_stages < 2)) {
