@@ -84,6 +84,7 @@ struct HaloProblem {
   int o_bufs;
   uint32_t o_off, o_tile_bytes;
   int res_tma;         // the first addend arrives through TMA into the staged-output buffer (see StageOut)
+  int o_swz;           // staged tile: 1 = 64-channel SWIZZLE_128B blocks, 0 = dense [128][Cout] rows (narrow layers)
   // chained launch (several dependent layers in one grid, see conv_halo_kernel): `done[n]` counts the output pixels of
   // image n that have reached global memory; a tile of a consumer waits until the images it reads are complete in every
   // producer `dep[i]` (image-local when producer and consumer share the image geometry, else dep_whole[i] = all of the
@@ -156,7 +157,7 @@ __device__ __forceinline__ HaloProblem load_problem(const HaloProblem& s) {
   p.w_copies = opaque(s.w_copies);
   p.pair = opaque(s.pair); p.ntiles_real = opaque(s.ntiles_real); p.w_gstage = opaque(s.w_gstage);
   p.o_bufs = opaque(s.o_bufs); p.o_off = opaque(s.o_off); p.o_tile_bytes = opaque(s.o_tile_bytes);
-  p.res_tma = opaque(s.res_tma);
+  p.res_tma = opaque(s.res_tma); p.o_swz = opaque(s.o_swz);
   p.done = nullptr; p.ndep = 0; p.img_px = 0; p.nimg = 0; p.strip = 0;
   if (CH) {
     p.done = opaque(s.done); p.ndep = opaque(s.ndep); p.img_px = opaque(s.img_px); p.nimg = opaque(s.nimg);
@@ -782,6 +783,8 @@ struct EpiArgs {
   int img_px, strip, cdbg;
   int add1_shift;                // add1 pixel = (y >> s, x >> s) of a (H >> s) x (W >> s) tensor
   int res_tma;                   // add0 is fetched by the TMA unit into the staged-output buffer (StageOut)
+  int o_swz;                     // staged tile layout (see stage_addr)
+  uint32_t o_row;                // dense layout: bytes per row (Cout * 2)
   uint32_t res_bar;              // resfull[2]
   const CUtensorMap* rmap;       // [2]: add0 hi (or only), lo
 };
@@ -815,6 +818,12 @@ __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t
 constexpr uint32_t T_OBLK = 128u * 128u;
 __device__ __forceinline__ uint32_t stage_addr(uint32_t buf, uint32_t row, uint32_t chunk) {
   return buf + (chunk >> 3) * T_OBLK + row * 128u + (((chunk & 7u) ^ (row & 7u)) << 4);
+}
+// Narrow layers (< 128 channels) keep the dense [128][Cout] tile of a (Cout, 8, 16, 1) un-swizzled box: their conflicts are
+// mild and the kernel is bound by shared-memory traffic there -- the 64-channel blocks make the TMA unit read 16 KB for
+// a 12 KB tile (measured: stage-3 BasicBlock launches 27.7 -> 28.9 us with swizzled blocks everywhere).
+__device__ __forceinline__ uint32_t stage_addr(const EpiArgs& E, uint32_t buf, uint32_t row, uint32_t chunk) {
+  return E.o_swz ? stage_addr(buf, row, chunk) : buf + row * E.o_row + chunk * 16u;
 }
 
 // Staged output, per tile: (1) the issuing thread waits until the TMA unit has finished READING the buffer two tiles back,
@@ -913,9 +922,14 @@ struct StageOut {
     epi_barrier();
     if (issuer) {
       if (tile_ok) {
-        for (int c0 = 0, blk = 0; c0 < E.Cout; c0 += 64, ++blk) {
-          tma_store_4d(E.omap, buf_addr + blk * T_OBLK, c0, x0, y0, n);
-          if (E.flags & I2R_F_SPLIT) tma_store_4d(E.omap + 1, buf_addr + E.o_tile_bytes + blk * T_OBLK, c0, x0, y0, n);
+        if (E.o_swz) {
+          for (int c0 = 0, blk = 0; c0 < E.Cout; c0 += 64, ++blk) {
+            tma_store_4d(E.omap, buf_addr + blk * T_OBLK, c0, x0, y0, n);
+            if (E.flags & I2R_F_SPLIT) tma_store_4d(E.omap + 1, buf_addr + E.o_tile_bytes + blk * T_OBLK, c0, x0, y0, n);
+          }
+        } else {
+          tma_store_4d(E.omap, buf_addr, 0, x0, y0, n);
+          if (E.flags & I2R_F_SPLIT) tma_store_4d(E.omap + 1, buf_addr + E.o_tile_bytes, 0, x0, y0, n);
         }
       }
       bulk_commit();
@@ -994,7 +1008,7 @@ __device__ __forceinline__ void epilogue_role(const EpiArgs E, const int cta, co
         r1[j] = make_uint4(0, 0, 0, 0);
         if (j < nc && valid && (c + j) * 8 < E.Cout) {
           if (has0)
-            r0[j] = E.res_tma ? ld_shared_v4(stage_addr(so.buf_addr, row, c + j))
+            r0[j] = E.res_tma ? ld_shared_v4(stage_addr(E, so.buf_addr, row, c + j))
                               : ld_addend<CH>(reinterpret_cast<const uint4*>(a0 + (c + j) * 8));
           if (has1) r1[j] = ld_addend<CH>(reinterpret_cast<const uint4*>(a1 + (c + j) * 8));
         }
@@ -1006,7 +1020,7 @@ __device__ __forceinline__ void epilogue_role(const EpiArgs E, const int cta, co
         l1[j] = make_uint4(0, 0, 0, 0);
         if (split && j < nc && valid && (c + j) * 8 < E.Cout) {
           if (has0)
-            l0[j] = E.res_tma ? ld_shared_v4(stage_addr(so.buf_addr + E.o_tile_bytes, row, c + j))
+            l0[j] = E.res_tma ? ld_shared_v4(stage_addr(E, so.buf_addr + E.o_tile_bytes, row, c + j))
                               : ld_addend<CH>(reinterpret_cast<const uint4*>(a0 + E.lo_off + (c + j) * 8));
           if (has1) l1[j] = ld_addend<CH>(reinterpret_cast<const uint4*>(a1 + E.lo_off + (c + j) * 8));
         }
@@ -1071,7 +1085,7 @@ __device__ __forceinline__ void epilogue_role(const EpiArgs E, const int cta, co
               q.w = pack_h2(v[6], v[7]);
               __half* yq = reinterpret_cast<__half*>(E.y) + static_cast<int64_t>(p) * E.out_pix_stride + c0;
               if (so.on)
-                st_shared_v4(stage_addr(so.buf_addr, row, c + j), q.x, q.y, q.z, q.w);
+                st_shared_v4(stage_addr(E, so.buf_addr, row, c + j), q.x, q.y, q.z, q.w);
               else if (!(dbg & 2))
                 *reinterpret_cast<uint4*>(yq) = q;
               else if (q.x == 0x12345678u)
@@ -1084,7 +1098,7 @@ __device__ __forceinline__ void epilogue_role(const EpiArgs E, const int cta, co
                   const float2 f = unpack_h2(hq[i]);
                   lq[i] = pack_h2(v[2 * i] - f.x, v[2 * i + 1] - f.y);
                 }
-                if (so.on) st_shared_v4(stage_addr(so.buf_addr + E.o_tile_bytes, row, c + j), lq[0], lq[1], lq[2], lq[3]);
+                if (so.on) st_shared_v4(stage_addr(E, so.buf_addr + E.o_tile_bytes, row, c + j), lq[0], lq[1], lq[2], lq[3]);
                 else *reinterpret_cast<uint4*>(yq + E.lo_off) = make_uint4(lq[0], lq[1], lq[2], lq[3]);
               }
             } else if (E.flags & I2R_F_OUT_NCHW_F32) {
@@ -1125,7 +1139,7 @@ __device__ __forceinline__ void epilogue_role(const EpiArgs E, const int cta, co
 // compile time and NADD residual tensors.  The epilogue warps are issue-bound (~4.5 cycles per instruction at two
 // warps per scheduler), so the instruction count per tile is what matters here: no per-chunk branches, no
 // reconvergence stacks, 32-bit pixel arithmetic.
-template <int G, int NADD, bool CH>
+template <int G, int NADD, bool CH, bool SWZ>
 __device__ __forceinline__ void epilogue_fast(const EpiArgs E, const int cta, const uint32_t sbase, const uint32_t tmem_base,
                                               const uint32_t ncols, const int cb, const int ce, const int ew, const int quad,
                                               const int lane, unsigned long long* tr, const int trcap) {
@@ -1140,6 +1154,7 @@ __device__ __forceinline__ void epilogue_fast(const EpiArgs E, const int cta, co
   uint32_t accph = 0;
   StageOut so;
   so.init(E, ew == 0 && lane == 0, cta);
+  const uint32_t srow = static_cast<uint32_t>(row) * E.o_row;   // dense layout: this pixel's row in the tile
   for (int tp = cta; tp < E.ntiles; tp += E.cta_count) {
     const int t = E.pair ? 2 * tp + E.rank : tp;
     const int n = __float2int_rd((static_cast<float>(t) + 0.5f) * inv_tpi);
@@ -1162,7 +1177,7 @@ __device__ __forceinline__ void epilogue_fast(const EpiArgs E, const int cta, co
         r0[j] = make_uint4(0, 0, 0, 0);
         r1[j] = make_uint4(0, 0, 0, 0);
         if (NADD >= 1) {
-          if (E.res_tma) r0[j] = ld_shared_v4(stage_addr(so.buf_addr, row, c + j));   // (rows outside the image: zero fill)
+          if ((SWZ && E.res_tma)) r0[j] = ld_shared_v4((SWZ ? stage_addr(so.buf_addr, row, c + j) : so.buf_addr + srow + (c + j) * 16u));   // (rows outside the image: zero fill)
           else if (valid) r0[j] = ld_addend<CH>(reinterpret_cast<const uint4*>(a0 + (c + j) * 8));
         }
         if (NADD >= 2 && valid) r1[j] = ld_addend<CH>(reinterpret_cast<const uint4*>(a1 + (c + j) * 8));
@@ -1196,7 +1211,7 @@ __device__ __forceinline__ void epilogue_fast(const EpiArgs E, const int cta, co
           }
           o[i] = pack_h2(fmaxf(va, lo), fmaxf(vb, lo));
         }
-        if (so.on) st_shared_v4(stage_addr(so.buf_addr, row, c + j), o[0], o[1], o[2], o[3]);
+        if (so.on) st_shared_v4((SWZ ? stage_addr(so.buf_addr, row, c + j) : so.buf_addr + srow + (c + j) * 16u), o[0], o[1], o[2], o[3]);
         else if (valid) *reinterpret_cast<uint4*>(yp + (c + j) * 8) = make_uint4(o[0], o[1], o[2], o[3]);
       }
     }
@@ -1217,7 +1232,7 @@ __device__ __forceinline__ void epilogue_fast(const EpiArgs E, const int cta, co
 // (ACT 0: clamp = ReLU / none, 1: erf-GELU after the addends, 2: erf-GELU before the addends).  The generic epilogue
 // re-tests flags per element and calls the activation out of line: 7.9 k cycles per 128 x 96 tile, 49 k for a 128 x 256
 // GELU tile (profiles/r02_epilogue_warps.txt) against < 1 k cycles of MMA.
-template <int G, int NADD, int ACT, bool CH>
+template <int G, int NADD, int ACT, bool CH, bool SWZ>
 __device__ __forceinline__ void epilogue_split_fast(const EpiArgs E, const int cta, const uint32_t sbase,
                                                     const uint32_t tmem_base, const uint32_t ncols, const int cb, const int ce,
                                                     const int ew, const int quad, const int lane, unsigned long long* tr,
@@ -1233,6 +1248,7 @@ __device__ __forceinline__ void epilogue_split_fast(const EpiArgs E, const int c
   uint32_t accph = 0;
   StageOut so;
   so.init(E, ew == 0 && lane == 0, cta);
+  const uint32_t srow = static_cast<uint32_t>(row) * E.o_row;   // dense layout: this pixel's row in the tile
   for (int tp = cta; tp < E.ntiles; tp += E.cta_count) {
     const int t = E.pair ? 2 * tp + E.rank : tp;
     const int n = __float2int_rd((static_cast<float>(t) + 0.5f) * inv_tpi);
@@ -1253,9 +1269,9 @@ __device__ __forceinline__ void epilogue_split_fast(const EpiArgs E, const int c
 #pragma unroll
       for (int j = 0; j < G; ++j) {
         r0[j] = l0[j] = r1[j] = l1[j] = make_uint4(0, 0, 0, 0);
-        if (NADD >= 1 && E.res_tma) {
-          r0[j] = ld_shared_v4(stage_addr(so.buf_addr, row, c + j));
-          l0[j] = ld_shared_v4(stage_addr(so.buf_addr + E.o_tile_bytes, row, c + j));
+        if (NADD >= 1 && (SWZ && E.res_tma)) {
+          r0[j] = ld_shared_v4((SWZ ? stage_addr(so.buf_addr, row, c + j) : so.buf_addr + srow + (c + j) * 16u));
+          l0[j] = ld_shared_v4((SWZ ? stage_addr(so.buf_addr + E.o_tile_bytes, row, c + j) : so.buf_addr + E.o_tile_bytes + srow + (c + j) * 16u));
         } else if (NADD >= 1 && valid) {
           r0[j] = ld_addend<CH>(reinterpret_cast<const uint4*>(a0 + (c + j) * 8));
           l0[j] = ld_addend<CH>(reinterpret_cast<const uint4*>(a0 + E.lo_off + (c + j) * 8));
@@ -1310,8 +1326,8 @@ __device__ __forceinline__ void epilogue_split_fast(const EpiArgs E, const int c
           ol[i] = pack_h2(va - h.x, vb - h.y);
         }
         if (so.on) {
-          st_shared_v4(stage_addr(so.buf_addr, row, c + j), oh[0], oh[1], oh[2], oh[3]);
-          st_shared_v4(stage_addr(so.buf_addr + E.o_tile_bytes, row, c + j), ol[0], ol[1], ol[2], ol[3]);
+          st_shared_v4((SWZ ? stage_addr(so.buf_addr, row, c + j) : so.buf_addr + srow + (c + j) * 16u), oh[0], oh[1], oh[2], oh[3]);
+          st_shared_v4((SWZ ? stage_addr(so.buf_addr + E.o_tile_bytes, row, c + j) : so.buf_addr + E.o_tile_bytes + srow + (c + j) * 16u), ol[0], ol[1], ol[2], ol[3]);
         } else if (valid) {
           *reinterpret_cast<uint4*>(yp + (c + j) * 8) = make_uint4(oh[0], oh[1], oh[2], oh[3]);
           *reinterpret_cast<uint4*>(yp + E.lo_off + (c + j) * 8) = make_uint4(ol[0], ol[1], ol[2], ol[3]);
@@ -1335,8 +1351,8 @@ __device__ __forceinline__ void epilogue_split_dispatch(const EpiArgs& E, const 
                                                         const uint32_t tmem_base, const uint32_t ncols, const int cb,
                                                         const int ce, const int ew, const int quad, const int lane,
                                                         unsigned long long* tr, const int trcap) {
-  if ((ce - cb) % 2 == 0) epilogue_split_fast<2, NADD, ACT, CH>(E, cta, sbase, tmem_base, ncols, cb, ce, ew, quad, lane, tr, trcap);
-  else epilogue_split_fast<1, NADD, ACT, CH>(E, cta, sbase, tmem_base, ncols, cb, ce, ew, quad, lane, tr, trcap);
+  if ((ce - cb) % 2 == 0) { if (E.o_swz) epilogue_split_fast<2, NADD, ACT, CH, true>(E, cta, sbase, tmem_base, ncols, cb, ce, ew, quad, lane, tr, trcap); else epilogue_split_fast<2, NADD, ACT, CH, false>(E, cta, sbase, tmem_base, ncols, cb, ce, ew, quad, lane, tr, trcap); }
+  else { if (E.o_swz) epilogue_split_fast<1, NADD, ACT, CH, true>(E, cta, sbase, tmem_base, ncols, cb, ce, ew, quad, lane, tr, trcap); else epilogue_split_fast<1, NADD, ACT, CH, false>(E, cta, sbase, tmem_base, ncols, cb, ce, ew, quad, lane, tr, trcap); }
 }
 template <int ACT, bool CH>
 __device__ __forceinline__ void epilogue_split_dispatch_nadd(const EpiArgs& E, const int cta, const uint32_t sbase,
@@ -1355,13 +1371,13 @@ __device__ __forceinline__ void epilogue_fast_dispatch(const EpiArgs& E, const i
                                                        unsigned long long* tr, const int trcap) {
   const int cw = ce - cb;
   if (cw % 4 == 0) {
-    epilogue_fast<4, NADD, CH>(E, cta, sbase, tmem_base, ncols, cb, ce, ew, quad, lane, tr, trcap);
+    if (E.o_swz) epilogue_fast<4, NADD, CH, true>(E, cta, sbase, tmem_base, ncols, cb, ce, ew, quad, lane, tr, trcap); else epilogue_fast<4, NADD, CH, false>(E, cta, sbase, tmem_base, ncols, cb, ce, ew, quad, lane, tr, trcap);
   } else if (cw % 3 == 0) {
-    epilogue_fast<3, NADD, CH>(E, cta, sbase, tmem_base, ncols, cb, ce, ew, quad, lane, tr, trcap);
+    if (E.o_swz) epilogue_fast<3, NADD, CH, true>(E, cta, sbase, tmem_base, ncols, cb, ce, ew, quad, lane, tr, trcap); else epilogue_fast<3, NADD, CH, false>(E, cta, sbase, tmem_base, ncols, cb, ce, ew, quad, lane, tr, trcap);
   } else if (cw % 2 == 0) {
-    epilogue_fast<2, NADD, CH>(E, cta, sbase, tmem_base, ncols, cb, ce, ew, quad, lane, tr, trcap);
+    if (E.o_swz) epilogue_fast<2, NADD, CH, true>(E, cta, sbase, tmem_base, ncols, cb, ce, ew, quad, lane, tr, trcap); else epilogue_fast<2, NADD, CH, false>(E, cta, sbase, tmem_base, ncols, cb, ce, ew, quad, lane, tr, trcap);
   } else {
-    epilogue_fast<1, NADD, CH>(E, cta, sbase, tmem_base, ncols, cb, ce, ew, quad, lane, tr, trcap);
+    if (E.o_swz) epilogue_fast<1, NADD, CH, true>(E, cta, sbase, tmem_base, ncols, cb, ce, ew, quad, lane, tr, trcap); else epilogue_fast<1, NADD, CH, false>(E, cta, sbase, tmem_base, ncols, cb, ce, ew, quad, lane, tr, trcap);
   }
 }
 
@@ -1676,6 +1692,7 @@ __global__ void __launch_bounds__(T_THREADS, 1) conv_halo_kernel(const __grid_co
     E.pair = pair ? 1 : 0; E.rank = rank; E.ntiles_real = P.ntiles_real;
     E.o_bufs = P.o_bufs; E.o_base = sbase + P.o_off; E.o_tile_bytes = P.o_tile_bytes; E.omap = &G.omap[pi][0];
     E.done = P.done; E.img_px = P.img_px; E.strip = P.strip; E.cdbg = cdbg; E.add1_shift = P.add1_shift;
+    E.o_swz = P.o_swz; E.o_row = static_cast<uint32_t>(P.Cout) * 2u;
     E.res_tma = (CH || pair) ? 0 : P.res_tma; E.res_bar = sbase + B_RESFULL; E.rmap = &G.rmap[CH ? 0 : pi][0];
     const int ew = warp - 4;
     // chunks holding real channels, split over the warps of a lane quadrant
@@ -1772,7 +1789,7 @@ static int encode_amap(CUtensorMap* map, const void* x, int NB, int H, int W, in
 
 // Output tensor (C, W, H, N) for TMA stores: box = (64 channels, 8 px, 16 lines, 1) with SWIZZLE_128B -- one block of the
 // staged tile (stage_addr); the channel extent of the map is Cout, so the last block's surplus channels are clipped.
-static int encode_omap(CUtensorMap* map, void* y, int NB, int H, int W, int Cout, int pix_stride) {
+static int encode_omap(CUtensorMap* map, void* y, int NB, int H, int W, int Cout, int pix_stride, bool swz = true) {
   EncodeTiledFn enc = get_encode();
   if (!enc) {
     set_error("cuTensorMapEncodeTiled entry point unavailable");
@@ -1782,9 +1799,10 @@ static int encode_omap(CUtensorMap* map, void* y, int NB, int H, int W, int Cout
   const cuuint32_t ones[4] = {1, 1, 1, 1};
   const cuuint64_t dims[4] = {(cuuint64_t)Cout, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)NB};
   const cuuint64_t strides[3] = {pb, pb * W, pb * W * H};
-  const cuuint32_t box[4] = {64, (cuuint32_t)T_TW, (cuuint32_t)T_TH, 1};
+  const cuuint32_t box[4] = {swz ? 64u : (cuuint32_t)Cout, (cuuint32_t)T_TW, (cuuint32_t)T_TH, 1};
   CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, y, dims, strides, box, ones, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                   swz ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled (output) failed (%d) for [%d,%d,%d,%d] pix_stride %d", (int)r, NB, H, W, Cout,
               pix_stride);
@@ -1904,7 +1922,7 @@ static int plan_layer(GT& G, const int base, const i2r_conv_problem* probs, cons
     const int nkc = ((S.Cin + 63) / 64) * ((S.flags & I2R_F_SPLIT) ? 3 : 1);
     const uint32_t image = static_cast<uint32_t>(S.ntaps * nkc + 1) * S.Npad * 128;
     const int64_t m = static_cast<int64_t>(S.NB) * S.IH * S.IW;
-    want_pair[i] = allow_pair && pair_policy != 0 && S.Npad % 16 == 0 && S.Npad >= 32 && m > 128 &&
+    want_pair[i] = allow_pair && pair_policy != 0 && S.stride == 1 && S.Npad % 16 == 0 && S.Npad >= 32 && m > 128 &&
                    (pair_policy == 2 || image > T_W_RES_MAX);
   }
   for (int i = 0; i < nprob; ++i)
@@ -2039,7 +2057,13 @@ static int plan_layer(GT& G, const int base, const i2r_conv_problem* probs, cons
     // staged output tiles (fp16 NHWC outputs with whole 8-channel chunks): two buffers, else one, else direct stores;
     // the activation ring gives up stages for them down to two (resident weights: two per issuer)
     P.o_bufs = 0;
-    P.o_tile_bytes = static_cast<uint32_t>((S.Cout + 63) / 64) * T_OBLK;   // 64-channel swizzled blocks (stage_addr)
+    static const int swz_min = []() {      // narrowest layer that stages swizzled 64-channel blocks
+      const char* e = getenv("I2R_HALO_STAGE_SWZ_MIN");
+      return e ? atoi(e) : 128;
+    }();
+    P.o_swz = S.Cout >= swz_min ? 1 : 0;
+    P.o_tile_bytes = P.o_swz ? static_cast<uint32_t>((S.Cout + 63) / 64) * T_OBLK      // 64-channel swizzled blocks
+                             : ((static_cast<uint32_t>(T_TW * T_TH) * S.Cout * 2 + 1023u) & ~1023u);
     const bool stageable = stage_policy != 0 && !(S.flags & (I2R_F_OUT_NCHW_F32 | I2R_F_OUT_F32 | I2R_F_OUT_T16)) &&
                            S.Cout % 8 == 0 && S.Cout <= 256 && S.out_pix_stride % 8 == 0 &&
                            (!P.split || P.lo_off % 8 == 0);
@@ -2087,10 +2111,10 @@ static int plan_layer(GT& G, const int base, const i2r_conv_problem* probs, cons
     P.o_off = (P.w_off + wregion + 1023u) & ~1023u;   // swizzled blocks: 1024-byte aligned
     if (P.o_bufs) {
       // the output as a 4-D tensor (C, W, H, N) with the same tile geometry as the activation map, dense boxes
-      int rc = encode_omap(&G.omap[base + i][0], S.y, P.NB, P.H, P.W, S.Cout, S.out_pix_stride);
+      int rc = encode_omap(&G.omap[base + i][0], S.y, P.NB, P.H, P.W, S.Cout, S.out_pix_stride, P.o_swz != 0);
       if (!rc && P.split)
         rc = encode_omap(&G.omap[base + i][1], static_cast<__half*>(S.y) + P.lo_off, P.NB, P.H, P.W, S.Cout,
-                         S.out_pix_stride);
+                         S.out_pix_stride, P.o_swz != 0);
       if (rc) return rc;
     }
     // first addend through TMA into the staging buffers (two buffers, plain problems only; I2R_HALO_RES_TMA=0: off)
@@ -2101,7 +2125,7 @@ static int plan_layer(GT& G, const int base, const i2r_conv_problem* probs, cons
     P.res_tma = 0;
     // (only for wide rows: at <= 96 channels the kernel is bound by the shared-memory port and the extra tile write +
     // read costs more than the scattered global loads: C2 -7 % when applied everywhere)
-    if (res_policy && (S.Cout >= 128 || res_policy == 2) && P.o_bufs == 2 && S.add0 && !P.pair && !GT::kChain &&
+    if (res_policy && (S.Cout >= 128 || res_policy == 2) && P.o_swz && P.o_bufs == 2 && S.add0 && !P.pair && !GT::kChain &&
         S.add_pix_stride % 8 == 0 &&
         (reinterpret_cast<uintptr_t>(S.add0) & 15) == 0) {
       int rc = encode_omap(&G.rmap[base + i][0], const_cast<void*>(S.add0), P.NB, P.H, P.W, S.Cout, S.add_pix_stride);

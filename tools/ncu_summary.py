@@ -4,6 +4,7 @@ import subprocess
 import sys
 
 rep = sys.argv[1]
+cols = [int(c) for c in sys.argv[2].split(",")] if len(sys.argv) > 2 else None      # optional: launches to keep
 out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(out.splitlines()))
 hdr, units = rows[0], rows[1]
@@ -22,4 +23,6 @@ for w in want:
         continue
     i = hdr.index(w)
     vals = [r[i][:60] for r in rows[2:]]
+    if cols is not None:
+        vals = [vals[c] for c in cols]
     print("%-82s %s  [%s]" % (w, " | ".join(vals), units[i]))

@@ -1,0 +1,14 @@
+#!/bin/bash
+cd "$GRAFT_REPO_ROOT" || exit 1
+mkdir -p gpurun_out
+exec > gpurun_out/s38.log 2>&1
+echo "=== tests"; timeout 1500 python -m pytest tests/test_kernels_gpu.py tests/test_halo_stress_gpu.py tests/test_halo_s2_gpu.py tests/test_halo_chain_gpu.py tests/test_halo_pair_gpu.py tests/test_model_gpu.py tests/test_model_gpu_hrt.py -m gpu -q 2>&1 | tail -4
+for m in 128 0 64 100000; do
+export I2R_HALO_STAGE_SWZ_MIN=$m
+timeout 600 python bench.py --steps 20 --warmup 5 --no-cpu-baseline --sustain-seconds 0.3 2>&1 | tail -1 | python -c "import sys,json; d=json.loads(sys.stdin.read()); print('swz_min=$m C2', round(d['value'],1), round(d['e2e']['value'],1), round(d['roofline']['achieved'],1))"
+done
+for m in 128 0; do
+export I2R_HALO_STAGE_SWZ_MIN=$m
+timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --sustain-seconds 0.3 --workload C4 2>&1 | tail -1 | python -c "import sys,json; d=json.loads(sys.stdin.read()); print('swz_min=$m C4', round(d['value'],1), round(d['e2e']['value'],1))"
+timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --sustain-seconds 0.3 --workload C3 2>&1 | tail -1 | python -c "import sys,json; d=json.loads(sys.stdin.read()); print('swz_min=$m C3', round(d['value'],1), round(d['e2e']['value'],1))"
+done
