@@ -3,7 +3,7 @@
 cd "$GRAFT_REPO_ROOT" || exit 1
 mkdir -p gpurun_out
 exec > gpurun_out/f1.log 2>&1
-echo "=== gpu suite"; timeout 1500 python -m pytest tests -m gpu -q -x --durations=5 2>&1 | tail -6
+echo "=== gpu suite"; timeout 1500 python -m pytest tests -m gpu -q --durations=3 2>&1 | tail -6
 echo "=== smoke"; timeout 300 python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" 2>&1 | tail -3
 echo "=== bench C2 (default invocation)"; timeout 900 python bench.py 2>&1 | tail -1 > gpurun_out/r02_bench_c2.json; python -c "
 import json; d=json.load(open('gpurun_out/r02_bench_c2.json')); print(d['value'], d['e2e'], d['roofline']['achieved'], d['roofline']['frac'], d['roofline']['traffic'], d['roofline']['smem_port'], d.get('cpu_baseline'), d['clocks'])"
