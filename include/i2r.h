@@ -108,13 +108,17 @@ int i2r_sm_count(int dev);
  * (tests only; same problem struct, same packed weights). */
 int i2r_conv_igemm(const i2r_conv_problem* probs, int nprob, int impl, void* stream);
 
-/* Persistent halo-tile variant for the problems that dominate the FLOPs: stride-1 3x3 (BasicBlock /
- * Bottleneck convs, interformer_pureMulti.py:37-107) and 1x1 / nn.Linear problems with no resampling
- * (in_shift 0, out_mul 1, addend shifts 0).  Each 8x16-pixel tile's activation halo is staged once in
- * shared memory and the nine taps are shifted UMMA descriptor windows of it; weights arrive as TMA
- * bulk copies and stay resident in shared memory when they fit; two TMEM accumulators overlap the
- * epilogue with the next tile.  i2r_conv_halo_supported() returns 1 when a problem qualifies;
- * others go through i2r_conv_igemm. */
+/* Persistent halo-tile variant for the problems that dominate the FLOPs: 3x3 convolutions of stride 1 (BasicBlock /
+ * Bottleneck convs, interformer_pureMulti.py:37-107) and stride 2 (second stem conv :680-682, transitions :543-582,
+ * fuse chains :353-387) and 1x1 / nn.Linear problems with no input resampling (in_shift 0, out_mul 1).  add0 is read at
+ * output resolution; add1 may be a tensor of (OH >> add1_shift) x (OW >> add1_shift) pixels that is up-sampled (nearest)
+ * in the epilogue (HRNet fuse, :392-410).  Stride 1: each 8x16-pixel tile's activation halo is staged once in shared
+ * memory and the nine taps are shifted UMMA descriptor windows of it.  Stride 2: the (2*8+1) x (2*16+1) input pixels of
+ * a tile are staged as four parity planes through TMA boxes with element strides 2, and every tap is a shifted window of
+ * one plane.  Weights arrive as TMA bulk copies and stay resident in shared memory when they fit; two TMEM accumulators
+ * overlap the epilogue with the next tile; fp16 NHWC outputs leave through shared-memory staging and TMA stores.
+ * Split-operand problems (I2R_F_SPLIT) stage x_hi / x_lo and W_hi / W_lo once per real 64-channel chunk where that is the
+ * faster scheme.  i2r_conv_halo_supported() returns 1 when a problem qualifies; others go through i2r_conv_igemm. */
 int i2r_conv_halo_supported(const i2r_conv_problem* prob);
 int i2r_conv_halo(const i2r_conv_problem* probs, int nprob, void* stream);
 

@@ -1,4 +1,4 @@
-// Persistent, warp-specialised convolution kernel for stride-1 3x3 and 1x1 problems (sm_100a):
+// Persistent, warp-specialised convolution kernel for 3x3 (stride 1 and 2) and 1x1 problems (sm_100a):
 // halo-tile activation staging -> tcgen05.mma with TMEM accumulators -> fused epilogue.
 //
 //   tile        : 8 (x) by 16 (y) output pixels = 128 accumulator rows, all Npad output channels
@@ -17,9 +17,11 @@
 //                 ONE extra K=16 MMA per tile (A = a tile of ones, B = [bias_hi, bias_lo, 0...] per channel) that
 //                 initialises the accumulator, so the epilogue touches neither shared nor constant memory.
 //   D           : two TMEM accumulators so the epilogue of tile i overlaps the MMAs of tile i+1.
-//   warps       : 0 = activation TMA producer, 1 = weight producer, 2 = TMEM owner + MMA issuer,
-//                 4..11 = epilogue (TMEM -> registers -> scale/bias/residual/ReLU -> global), two warps per
-//                 TMEM lane quadrant, each owning half of the output channels.
+//   warps       : 0 = activation TMA producer, 1 = weight producer, 2 = TMEM owner + MMA issuer, 3 = second MMA issuer
+//                 (resident weights: the two issuers alternate tiles, each with its own accumulator and half-ring),
+//                 4..11 = epilogue (TMEM -> registers -> residual(s) / ReLU / GELU -> fp16 tile staged in shared memory ->
+//                 TMA store; direct 16-byte stores when the tile does not fit), two warps per TMEM lane quadrant, each
+//                 owning half of the output channels.
 //   grid        : persistent; each problem of a grouped launch owns a contiguous CTA range sized
 //                 by its share of the work, CTAs stride over that problem's tiles.
 //   stride 2    : a stride-2 3x3 convolution (HRNet transitions and fuse chains, the second stem convolution) reads,

@@ -6,13 +6,13 @@ block (GeneralTransformerBlock, :1230-1240) is the launch sequence
 
     LayerNorm(eps 1e-6) + window-major gather (7x7 windows, centre zero padding)   i2r_ln_window_gather
     q / k / v projections (heads zero-padded 39 -> 48 channels by the packing)     i2r_conv_halo (1x1 GEMMs)
-    softmax(q k^T / sqrt(39)) v per (window, head), no RPE bias, no mask           i2r_window_attention
+    softmax(q k^T / sqrt(39)) v per (window, head), no RPE bias, no mask           i2r_window_attention_tc
     out_proj                                                                        i2r_conv_halo
     scatter back + residual                                                         i2r_window_scatter_add
     LayerNorm                                                                       i2r_layernorm_padded
-    fc1 1x1 + BN + GELU                                                             i2r_conv_igemm (I2R_F_GELU)
+    fc1 1x1 + BN + GELU                                                             i2r_conv_halo (I2R_F_GELU)
     depthwise 3x3 + BN + GELU                                                       i2r_dwconv3x3
-    fc2 1x1 + BN + GELU, + residual AFTER the activation                            i2r_conv_igemm (GELU | ACT_FIRST)
+    fc2 1x1 + BN + GELU, + residual AFTER the activation                            i2r_conv_halo (GELU | ACT_FIRST)
 
 and the fuse layers (:1616-1731) are 1x1 GEMMs at the source resolution + one bilinear up-sum pass per output branch,
 depthwise stride-2 + 1x1 chains for the down-sampling terms.
