@@ -103,3 +103,18 @@ def test_hrformer_launch_sequence_reproduces_reference(yaml_rel, case, h, w):
     errs = {k: float(np.abs(out[k].numpy() - g["out_" + k]).max()) for k in out}
     print("emulated HRFormer split-operand max-abs error", errs, "launches", model._program.runner.launches)
     assert sorted(out) == ["multi", "single"] and all(v <= 5e-4 for v in errs.values()), errs
+
+
+def test_every_environment_knob_is_documented():
+    """Every I2R_* variable the package or the library reads appears in INTEGRATION.md section 3."""
+    import re
+    pkg = os.path.join(paths.REPO, "intra-and-inter-human-relation-network-for-mpee_b200")
+    used = set()
+    for root, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh")):
+                text = open(os.path.join(root, f), errors="ignore").read()
+                used |= set(re.findall(r'(?:getenv\(|environ\.get\(|environ\[)\s*[\'"](I2R_[A-Z0-9_]+)[\'"]', text))
+    doc = open(os.path.join(paths.REPO, "INTEGRATION.md")).read()
+    missing = sorted(v for v in used if v not in doc)
+    assert used and not missing, missing
